@@ -1,0 +1,141 @@
+"""Generate the committed golden fixtures under tests/golden/.
+
+Run ONLY in the build container (needs /root/reference); the fixtures it writes are committed so
+that the GPU box -- which has no reference tree -- can run the parity tests.
+
+  python tests/golden/make_golden.py
+
+Writes
+  ref_data.npz        the reference's shipped data files, as float64 binary:
+                        chtxs_m, chtxs_f  [11,1681]  (Chtxs_data_dx0.025_dt0.001/chtxs_{m,f}_t0.01.csv)
+                        solidbody_t0.25, _t0.5, _t1  [6561]   (data/solidbody_t*_u.csv)
+  ref_fct_cases.npz   inputs + outputs of the reference's OWN functions, imported unmodified from
+                      /root/reference/helpers.py with dolfin/matplotlib stubbed (oracle/ref_loader.py):
+                      FCT_alg_ref (4 cases incl. rhs / non_flux_mat / pruned zeros), ChebSI,
+                      artificial_diffusion_mat, L2_norm_sq_Q, L2_norm_sq_Omega, cost_functional.
+"""
+import os
+import sys
+
+import numpy as np
+from scipy.sparse import lil_matrix
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle.p1assembly import P1Assembler          # noqa: E402
+from oracle.p1mesh import RectMesh                 # noqa: E402
+from oracle.fct_numpy import Pattern               # noqa: E402
+from oracle.ref_loader import REFERENCE_DIR, load_reference_helpers   # noqa: E402
+
+
+def ref_data():
+    out = {}
+    d = os.path.join(REFERENCE_DIR, "Chtxs_data_dx0.025_dt0.001")
+    out["chtxs_m"] = np.genfromtxt(os.path.join(d, "chtxs_m_t0.01.csv"), delimiter=",").reshape(11, 1681)
+    out["chtxs_f"] = np.genfromtxt(os.path.join(d, "chtxs_f_t0.01.csv"), delimiter=",").reshape(11, 1681)
+    for t in ("0.25", "0.5", "1"):
+        out[f"solidbody_t{t}"] = np.genfromtxt(os.path.join(REFERENCE_DIR, "data", f"solidbody_t{t}_u.csv"),
+                                               delimiter=",")
+    np.savez_compressed(os.path.join(HERE, "ref_data.npz"), **out)
+    print("ref_data.npz:", {k: v.shape for k, v in out.items()})
+
+
+def ref_fct_cases():
+    hp = load_reference_helpers()
+    rng = np.random.default_rng(5)
+    out = {}
+
+    def run_case(tag, n, a1, a2, A, rhs, u_n, dt, S, asm, pat, mesh):
+        nodes = mesh.nodes
+        M = asm.mass()
+        Ml = lil_matrix(pat.csr(M))
+        MLl = hp.row_lump(Ml, nodes)
+        nb = mesh.dof_neighbors()
+        Ain = pat.csr(A)
+        Ain.eliminate_zeros()          # what reaches FCT_alg_ref after scipy arithmetic (App. D-5)
+        Sin = None if S is None else pat.csr(S)
+        u1 = hp.FCT_alg_ref(Ain, rhs, u_n, dt, nodes, Ml, MLl, nb, non_flux_mat=Sin)
+        out[f"{tag}_n"] = np.array([n])
+        out[f"{tag}_box"] = np.array([a1, a2], dtype=np.float64)
+        out[f"{tag}_A"] = A
+        out[f"{tag}_rhs"] = rhs
+        out[f"{tag}_un"] = u_n
+        out[f"{tag}_dt"] = np.array([dt])
+        out[f"{tag}_S"] = np.zeros(0) if S is None else S
+        out[f"{tag}_out"] = np.asarray(u1).ravel()
+        print(tag, "done", nodes)
+
+    # case a: solid-body rotation + drift operator (advection_solidbody_FCT.py), legacy sign -> ref sign
+    n, a1, a2 = 16, -1.0, 1.0
+    mesh = RectMesh(n, a1, a2); asm = P1Assembler(mesh); pat = Pattern(*mesh.pattern())
+    om = np.pi / 40
+    xy = mesh.dof_xy
+    A = -asm.conv_conservative_p1(-xy[:, 1] / om + 2, xy[:, 0] / om + 2)
+    u_n = (np.hypot(xy[:, 0], xy[:, 1] - 1 / 3) < 1 / 3).astype(np.float64)
+    run_case("solid", n, a1, a2, A, np.zeros(mesh.nodes), u_n, 0.125 ** 2 / 4, None, asm, pat, mesh)
+
+    # case b: chemotaxis operator Dm*K - chi*Aa, random fields (helpers.py:1350-1356)
+    n, a1, a2 = 12, 0.0, 1.0
+    mesh = RectMesh(n, a1, a2); asm = P1Assembler(mesh); pat = Pattern(*mesh.pattern())
+    m = 1.5 + 0.1 * (0.5 - rng.random(mesh.nodes))
+    f = 1.5 + 0.1 * (0.5 - rng.random(mesh.nodes))
+    K = asm.stiffness()
+    Aa = asm.chemotaxis_conv(f, lambda phi, xyq: np.exp(-0.5 * asm.at_quad(m, phi)), degree=4)
+    run_case("chtxs", n, a1, a2, 0.05 * K - 0.25 * Aa, np.zeros(mesh.nodes), m, 1e-3, None, asm, pat, mesh)
+
+    # case c: Schnakenberg-like: wind operator, rhs, non_flux_mat = gamma*M (helpers.py:579-589)
+    n, a1, a2 = 10, 0.0, 1.0
+    mesh = RectMesh(n, a1, a2); asm = P1Assembler(mesh); pat = Pattern(*mesh.pattern())
+    wind = lambda x, y: ((y - 0.5) * x * (1 - x), -(x - 0.5) * y * (1 - y))
+    Aw = asm.conv_conservative(wind, degree=5)
+    K = asm.stiffness(); M = asm.mass()
+    u_n = 1.0 + 0.1 * np.cos(2 * np.pi * (mesh.dof_xy[:, 0] + mesh.dof_xy[:, 1]))
+    rhs = asm.load_p1_product(u_n, u_n, scale=230.82) + asm.load_constant(23.082)
+    run_case("schnak", n, a1, a2, 0.01 * K - 100 * Aw, rhs, u_n, 1e-3, 230.82 * M, asm, pat, mesh)
+
+    # case d: drift-control operator (advection_solidbody_FCT_PDECO_alltime.py:222-228), random control
+    n, a1, a2 = 12, -1.0, 1.0
+    mesh = RectMesh(n, a1, a2); asm = P1Assembler(mesh); pat = Pattern(*mesh.pattern())
+    c = 1.0 + rng.random(mesh.nodes)
+    A_u = asm.drift_mass(c, 1.0, 1.0) + asm.drift_conv(c, 1.0, 1.0)
+    xy = mesh.dof_xy
+    u_n = np.exp(-20 * ((xy[:, 0] + 2 / 3) ** 2 + 5 * (xy[:, 1] + 5 / 6) ** 2))
+    rhs = asm.load_p1_product(rng.random(mesh.nodes))
+    run_case("drift", n, a1, a2, -A_u, rhs, u_n, 0.01, None, asm, pat, mesh)
+
+    # ChebSI / artificial_diffusion_mat / norms on the last mesh
+    M = asm.mass()
+    Mc = pat.csr(M)
+    b = rng.random(mesh.nodes)
+    out["cheb_b"] = b
+    out["cheb_out"] = hp.ChebSI(b, Mc, Mc.diagonal(), 20, 0.5, 2)
+    out["cheb7_out"] = hp.ChebSI(b, Mc, Mc.diagonal(), 7, 0.5, 2)
+    Dref = hp.artificial_diffusion_mat(lil_matrix(pat.csr(A_u)))
+    out["adm_in"] = A_u
+    out["adm_out"] = pat.embed(Dref)
+    ns, dt = 4, 0.05
+    phi = rng.random((ns + 1) * mesh.nodes)
+    tgt = rng.random((ns + 1) * mesh.nodes)
+    ctl = rng.random((ns + 1) * mesh.nodes)
+    out["norm_phi"] = phi
+    out["norm_tgt"] = tgt
+    out["norm_ctl"] = ctl
+    out["norm_Q"] = np.array([hp.L2_norm_sq_Q(phi, ns, dt, Mc)])
+    out["norm_Omega"] = np.array([hp.L2_norm_sq_Omega(phi[:mesh.nodes], Mc)])
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        out["cost_alltime"] = np.array([hp.cost_functional(phi, tgt, ctl, ns, dt, Mc, 0.01, "alltime")])
+        out["cost_finaltime"] = np.array([hp.cost_functional(phi, tgt[:mesh.nodes], ctl, ns, dt, Mc, 0.01,
+                                                             "finaltime")])
+        out["cost_alltime2"] = np.array([hp.cost_functional(phi, tgt, ctl, ns, dt, Mc, 0.01, "alltime",
+                                                            var2=tgt, var2_target=phi)])
+    out["norm_meta"] = np.array([ns, dt, 0.01])
+    np.savez_compressed(os.path.join(HERE, "ref_fct_cases.npz"), **out)
+    print("ref_fct_cases.npz written:", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    ref_data()
+    ref_fct_cases()
