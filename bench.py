@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- FCT steps/s of the drift-control advection PDECO on the 4096^2 P1 mesh (BASELINE.json config 5).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells 4096] [--nt 4]
+
+One bench "step" = one gradient-iteration pass of the hot path over N_t time levels of the synthetic
+4097^2-DoF problem: state sweep (N_t x [drift-operator assembly + FCT step]) + adjoint sweep (N_t x [assembly
++ M(uhat-u) + FCT step]) + gradient (N_t+1 x [load vector + SpMV + 20 Chebyshev iterations]) + cost functional,
+all device-resident.  `value` = FCT steps (state + adjoint) per second, whole job.  `e2e` = the same metric
+through the host-buffer C-ABI call (fct_advdrift_state_host: control slices H2D, state slices D2H inside the
+timed region, pinned host memory).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def step_bytes(n, nnz, cells, k_j):
+    """algorithmic bytes of one FCT step, SURVEY.md App. E / DESIGN.md"""
+    return (344 + 12 * k_j) * nnz + (1108 + 28 * k_j) * n + 12 * cells
+
+
+def cheb_iter_bytes(n, nnz):
+    """one Chebyshev iteration: M values + column indices + rowptr + 5 vectors (App. E, P4)"""
+    return 12 * nnz + 4 * n + 5 * 8 * n
+
+
+class ClockSampler:
+    """samples nvidia-smi SM clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def rd():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=rd, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (bounded sample)
+# ------------------------------------------------------------------------------------------------------
+def cpu_port_steps_per_s(cells_full, sample_cells, nsteps):
+    """Times the oracle's FCT state step (numpy/scipy, 1 core, Jacobi twin of the GPU solver -- a direct solve
+    is impractical beyond ~1M DoF) on a `sample_cells`^2 mesh and scales linearly in DoF to the
+    full mesh (every pass of the Jacobi-based step is O(nnz))."""
+    from oracle import pdeco_numpy as drv
+    orc = drv.AdvectionDriftPDECO(sample_cells, 0.0, 1.0, solver="jacobi")
+    h = 1.0 / sample_cells
+    dt = 0.25 * h / (2 * np.sqrt(2))
+    u0 = orc.gaussian_ic()
+    c = np.full((nsteps + 1, orc.nodes), 1.0)
+    xy = orc.mesh.dof_xy
+    c += 0.5 * np.sin(3 * xy[:, 0]) * np.cos(2 * xy[:, 1])
+    t0 = time.perf_counter()
+    orc.state(c, u0, nsteps, dt)
+    el = time.perf_counter() - t0
+    sps_sample = nsteps / el
+    scale = (sample_cells + 1) ** 2 / float((cells_full + 1) ** 2)
+    return sps_sample * scale, sps_sample, el
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(args.cells, 512)
+    sps, sps_sample, el = 0.0, 0.0, 0.0
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, vs, e = cpu_port_steps_per_s(args.cells, sample, 2)
+        if i >= args.warmup:
+            times.append((v, vs, e))
+    sps = float(np.mean([t[0] for t in times]))
+    sample_txt = (f"oracle port (numpy/scipy CSR, Jacobi low-order solve), {2} FCT state steps on a {sample}^2-cell mesh "
+                  f"per bench step, {np.mean([t[1] for t in times]):.3f} steps/s there, scaled by DoF ratio to {args.cells}^2")
+    line = {"impl": "reference", "metric": "FCT steps/sec", "value": sps, "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([t[2] for t in times])),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic {args.cells}^2-cell unit-square advection FCT PDECO (BASELINE config 5)"},
+            "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample_txt},
+            "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def synth_problem(mesh, nt, dt):
+    """config 5: Gaussian IC, initial control c = 1 (+ a smooth perturbation so that the
+    drift-mass term is exercised), target = the IC translated by the exact drift of c = 2."""
+    xy = mesh.dof_xy
+    x, y = 2 * xy[:, 0] - 1, 2 * xy[:, 1] - 1
+    u0 = np.exp(-20 * ((x + 2 / 3) ** 2 + 5 * (y + 5 / 6) ** 2))
+    c = 1.0 + 0.25 * np.sin(3 * xy[:, 0]) * np.cos(2 * xy[:, 1])
+    uhat = []
+    for k in range(nt + 1):
+        s = 2.0 * k * dt * 2          # shift in [-1,1] coordinates
+        uhat.append(np.exp(-20 * ((x - s + 2 / 3) ** 2 + 5 * (y - s + 5 / 6) ** 2)))
+    return u0, c, np.array(uhat)
+
+
+def run_gpu_arm(args):
+    import fem_fct_pdeco_b200 as fp
+    from fem_fct_pdeco_b200.mesh import RectMeshP1
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from fem_fct_pdeco_b200 import distributed as dist_mod
+        return dist_mod.bench_multi(args, rank, world, local_rank)
+
+    if fp.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    n_cells, nt = args.cells, args.nt
+    h = 1.0 / n_cells
+    dt = 0.25 * h / (2 * np.sqrt(2))
+    beta = 0.01
+    t_setup = time.perf_counter()
+    mesh = RectMeshP1(n_cells, 0.0, 1.0)
+    ctx = mesh.context(device=local_rank)
+    n, nnz, ncell = mesh.nodes, mesh.nnz, mesh.ncells
+    u0, c0, uhat = synth_problem(mesh, nt, dt)
+    M = ctx.static()[0]
+    L = (nt + 1) * n
+    d_c = ctx.array(np.tile(c0, nt + 1))
+    utr = np.zeros(L); utr[:n] = u0
+    d_u = ctx.array(utr)
+    d_uhat = ctx.array(uhat.ravel())
+    d_p, d_d = ctx.empty(L), ctx.empty(L)
+    del utr
+    t_setup = time.perf_counter() - t_setup
+
+    sweeps_hist = []
+
+    def gradient_pass():
+        s1 = ctx.advdrift_state(d_c, d_u, nt, dt)
+        s2 = ctx.advdrift_adjoint(d_c, d_u, d_uhat, d_p, nt, dt)
+        ctx.advdrift_gradient(d_c, d_u, d_p, d_d, nt, beta)
+        J = 0.5 * ctx.norm_sq_Q(M, d_u, nt, dt, target=d_uhat) + beta / 2 * ctx.norm_sq_Q(M, d_c, nt, dt)
+        sweeps_hist.append((s1, s2))
+        return J
+
+    for _ in range(args.warmup):
+        gradient_pass()
+    ctx.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = ctx.event(), ctx.event()
+    del sweeps_hist[:]
+    ctx.record(e0)
+    for _ in range(args.steps):
+        J = gradient_pass()
+    ctx.record(e1)
+    ms = ctx.elapsed_ms(e0, e1)
+    launches = ctx.launch_count() - l0
+    fct_steps = 2 * nt * args.steps
+    value = fct_steps / (ms * 1e-3)
+    k_state = np.mean([s[0] for s in sweeps_hist]) / nt
+    k_adj = np.mean([s[1] for s in sweeps_hist]) / nt
+
+    # ---- dominant kernel (k_cheb_iter) timed live with CUDA events on the library's stream ----------
+    Md = ctx.static()[2]
+    b, y = d_d.slice(0, n), d_p.slice(0, n)        # scratch slices (overwritten by the next pass anyway)
+    reps = 5
+    ctx.chebsi(M, Md, b, y, 20)
+    ctx.record(e0)
+    for _ in range(reps):
+        ctx.chebsi(M, Md, b, y, 20)
+    ctx.record(e1)
+    t20 = ctx.elapsed_ms(e0, e1)
+    ctx.record(e0)
+    for _ in range(reps):
+        ctx.chebsi(M, Md, b, y, 1)                   # the vector-only first iteration (k_cheb_first)
+    ctx.record(e1)
+    t1 = ctx.elapsed_ms(e0, e1)
+    cheb_ms = (t20 - t1) / (reps * 19)               # 19 k_cheb_iter launches per ChebSI call
+    peak, peak_src = _peaks()
+    cb = cheb_iter_bytes(n, nnz)
+    achieved = cb / (cheb_ms * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C-ABI (H2D of control slices, D2H of state slices inside) -----
+    hc = ctx.pinned(L); hu = ctx.pinned(L)
+    hc[:] = np.tile(c0, nt + 1); hu[:] = 0.0; hu[:n] = u0
+    ctx.advdrift_state_host(hc, hu, nt, dt)          # warm-up
+    t0 = time.perf_counter()
+    reps_e2e = max(1, args.steps // 2)
+    for _ in range(reps_e2e):
+        ctx.advdrift_state_host(hc, hu, nt, dt)      # synchronises before returning
+    e2e_s = time.perf_counter() - t0
+    e2e_value = nt * reps_e2e / e2e_s
+    clocks = sampler.stop()
+
+    # whole-step roofline (algorithmic bytes of an FCT step with the sweeps actually executed)
+    k_mean = 0.5 * (k_state + k_adj)
+    step_gb = step_bytes(n, nnz, ncell, k_mean) / 1e9
+    line = {
+        "metric": "FCT steps/sec", "value": value, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {n_cells}^2-cell unit-square drift-control advection FCT PDECO "
+                               f"(BASELINE config 5): {n} DoF, {nnz} nnz; bench step = state+adjoint sweeps over "
+                               f"{nt} time levels + gradient + cost",
+                   "time_levels": nt, "dt": dt, "l2_flush": "working set per pass >> L2 (matrix values alone are "
+                   f"{8 * nnz / 1e6:.0f} MB)", "jacobi_sweeps_per_step": {"state": k_state, "adjoint": k_adj},
+                   "cost_functional": J, "setup_s": t_setup},
+        "roofline": {"bound": "hbm", "kernel": "k_cheb_iter", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": cb, "ms_per_launch": cheb_ms},
+        "step_roofline": {"algorithmic_GB_per_fct_step": step_gb, "achieved_GBs": step_gb * value,
+                          "frac": step_gb * value / peak,
+                          "note": "pass time also contains gradient + cost work not counted in the FCT-step bytes"},
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                "call": "fct_advdrift_state_host (state sweep, pinned host trajectories)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if not args.no_cpu:
+        sps, sps_sample, el = cpu_port_steps_per_s(n_cells, min(n_cells, 512), 2)
+        line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": 1, "kind": "port",
+                                "sample": f"oracle port (numpy/scipy, Jacobi low-order solve): 2 FCT state steps on a "
+                                          f"{min(n_cells, 512)}^2-cell mesh = {sps_sample:.3f} steps/s in {el:.1f} s, "
+                                          f"scaled by DoF ratio to {n_cells}^2"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=4096, help="cells per side (4096 = BASELINE config 5)")
+    ap.add_argument("--nt", type=int, default=4, help="time levels per bench step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

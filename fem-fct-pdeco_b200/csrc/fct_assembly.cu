@@ -1,0 +1,416 @@
+// P1 element assembly into the fixed CSR pattern, as a row-gather: one thread per matrix row walks the
+// (<= 6 on the structured mesh) cells incident to its vertex in ascending cell order, evaluates the row of
+// each element tensor and adds it into the row's slots held in shared memory; the finished rows leave through
+// a coalesced store.  No atomics: the summation order is the cell order (what dolfin's cell loop and the
+// oracle's bincount do), so results are bit-reproducible and independent of the GPU count.
+//
+// Replaces the dolfin `assemble(...)` calls on the reference's hot path (helpers.py:87-104 and the call
+// sites listed per form in include/fctpdeco.h).
+#include "fct_common.cuh"
+#include "../../include/fctpdeco.h"
+
+#include <vector>
+
+extern __shared__ __align__(16) unsigned char fct_smem[];
+
+// FIAT default triangle schemes (reference-triangle coordinates (xi,eta), weights sum to 1/2).
+// Degree 4: Strang-Fix 6-point with the literal 15-digit constants FIAT ships (the chemotaxis golden depends on
+// them); degree 5: Strang-Fix 7-point.
+__constant__ double c_q4[6][3] = {
+    {0.091576213509771, 0.091576213509771, 0.109951743655322 / 2},
+    {0.816847572980459, 0.091576213509771, 0.109951743655322 / 2},
+    {0.091576213509771, 0.816847572980459, 0.109951743655322 / 2},
+    {0.445948490915965, 0.445948490915965, 0.223381589678011 / 2},
+    {0.108103018168070, 0.445948490915965, 0.223381589678011 / 2},
+    {0.445948490915965, 0.108103018168070, 0.223381589678011 / 2}};
+__constant__ double c_q5[7][3] = {
+    {1.0 / 3.0, 1.0 / 3.0, 0.225 / 2},
+    {0.10128650732345633, 0.10128650732345633, 0.12593918054482717 / 2},
+    {0.79742698535308720, 0.10128650732345633, 0.12593918054482717 / 2},
+    {0.10128650732345633, 0.79742698535308720, 0.12593918054482717 / 2},
+    {0.47014206410511505, 0.47014206410511505, 0.13239415278850616 / 2},
+    {0.05971587178976981, 0.47014206410511505, 0.13239415278850616 / 2},
+    {0.47014206410511505, 0.05971587178976981, 0.13239415278850616 / 2}};
+
+struct CellGeom {
+    int d[3];          // DoFs
+    double gx[3], gy[3];
+    double detJ, area;
+};
+
+__device__ __forceinline__ CellGeom cell_geom(const int32_t* __restrict__ cells, const double* __restrict__ xy, int c) {
+    CellGeom g;
+    g.d[0] = cells[3 * c]; g.d[1] = cells[3 * c + 1]; g.d[2] = cells[3 * c + 2];
+    const double2 p0 = reinterpret_cast<const double2*>(xy)[g.d[0]];
+    const double2 p1 = reinterpret_cast<const double2*>(xy)[g.d[1]];
+    const double2 p2 = reinterpret_cast<const double2*>(xy)[g.d[2]];
+    const double det = (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+    g.gx[1] = (p2.y - p0.y) / det;  g.gy[1] = -(p2.x - p0.x) / det;
+    g.gx[2] = -(p1.y - p0.y) / det; g.gy[2] = (p1.x - p0.x) / det;
+    g.gx[0] = -(g.gx[1] + g.gx[2]); g.gy[0] = -(g.gy[1] + g.gy[2]);
+    g.detJ = fabs(det);
+    g.area = 0.5 * g.detJ;
+    return g;
+}
+
+struct FormArgs {
+    const double* f0;
+    const double* f1;
+    const double* f2;
+    const double* f3;
+    double s0, s1;
+};
+
+// e[b] = A_e[a][b] for the local row a of cell geometry g
+template <int KIND>
+__device__ __forceinline__ void element_row(const CellGeom& g, int a, const FormArgs& fa, double e[3]) {
+    if (KIND == FCT_FORM_MASS) {
+        const double m = g.area / 12.0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) e[b] = (b == a) ? 2.0 * m : m;
+    } else if (KIND == FCT_FORM_STIFFNESS) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) e[b] = g.area * (g.gx[a] * g.gx[b] + g.gy[a] * g.gy[b]);
+    } else if (KIND == FCT_FORM_DRIFT) {
+        const double c0 = fa.f0[g.d[0]], c1 = fa.f0[g.d[1]], c2 = fa.f0[g.d[2]];
+        const double cc[3] = {c0, c1, c2};
+        const double gcx = c0 * g.gx[0] + c1 * g.gx[1] + c2 * g.gx[2];
+        const double gcy = c0 * g.gy[0] + c1 * g.gy[1] + c2 * g.gy[2];
+        const double s = fa.s0 * gcx + fa.s1 * gcy;           // b . grad c
+        const double m = g.area / 12.0;
+        const double bg = fa.s0 * g.gx[a] + fa.s1 * g.gy[a];  // b . grad phi_a
+        const double csum = (c0 + c1) + c2;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const double mass = (s * m) * ((b == a) ? 2.0 : 1.0);
+            const double conv = bg * (m * (csum + cc[b]));
+            e[b] = mass + conv;
+        }
+    } else if (KIND == FCT_FORM_WIND_P1 || KIND == FCT_FORM_WIND_P1_T) {
+        const double wx[3] = {fa.f0[g.d[0]], fa.f0[g.d[1]], fa.f0[g.d[2]]};
+        const double wy[3] = {fa.f1[g.d[0]], fa.f1[g.d[1]], fa.f1[g.d[2]]};
+        const double sx = (wx[0] + wx[1]) + wx[2], sy = (wy[0] + wy[1]) + wy[2];
+        const double m = g.area / 12.0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (KIND == FCT_FORM_WIND_P1) e[b] = g.gx[a] * (m * (sx + wx[b])) + g.gy[a] * (m * (sy + wy[b]));
+            else e[b] = g.gx[b] * (m * (sx + wx[a])) + g.gy[b] * (m * (sy + wy[a]));
+        }
+    } else if (KIND == FCT_FORM_WMASS1 || KIND == FCT_FORM_WMASS2 || KIND == FCT_FORM_WMASS3) {
+        e[0] = e[1] = e[2] = 0.0;
+        const double a0[3] = {fa.f0[g.d[0]], fa.f0[g.d[1]], fa.f0[g.d[2]]};
+        double a1[3] = {1, 1, 1}, a2[3] = {1, 1, 1};
+        if (KIND >= FCT_FORM_WMASS2) { a1[0] = fa.f1[g.d[0]]; a1[1] = fa.f1[g.d[1]]; a1[2] = fa.f1[g.d[2]]; }
+        if (KIND >= FCT_FORM_WMASS3) { a2[0] = fa.f2[g.d[0]]; a2[1] = fa.f2[g.d[1]]; a2[2] = fa.f2[g.d[2]]; }
+        for (int q = 0; q < 7; ++q) {
+            const double ph[3] = {1.0 - c_q5[q][0] - c_q5[q][1], c_q5[q][0], c_q5[q][1]};
+            double v = a0[0] * ph[0] + a0[1] * ph[1] + a0[2] * ph[2];
+            if (KIND >= FCT_FORM_WMASS2) v *= a1[0] * ph[0] + a1[1] * ph[1] + a1[2] * ph[2];
+            if (KIND >= FCT_FORM_WMASS3) v *= a2[0] * ph[0] + a2[1] * ph[1] + a2[2] * ph[2];
+            const double w = c_q5[q][2] * v * ph[a];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) e[b] += w * ph[b];
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) e[b] *= g.detJ;
+    } else if (KIND == FCT_FORM_CHTX || KIND == FCT_FORM_CHTX_EXP) {
+        const double f0 = fa.f0[g.d[0]], f1 = fa.f0[g.d[1]], f2 = fa.f0[g.d[2]];
+        const double gfx = f0 * g.gx[0] + f1 * g.gx[1] + f2 * g.gx[2];
+        const double gfy = f0 * g.gy[0] + f1 * g.gy[1] + f2 * g.gy[2];
+        const double s = gfx * g.gx[a] + gfy * g.gy[a];
+        if (KIND == FCT_FORM_CHTX) {
+            e[0] = e[1] = e[2] = s * (g.area / 3.0);
+        } else {
+            const double m0 = fa.f1[g.d[0]], m1 = fa.f1[g.d[1]], m2 = fa.f1[g.d[2]];
+            double W[3] = {0, 0, 0};
+            for (int q = 0; q < 6; ++q) {
+                const double ph[3] = {1.0 - c_q4[q][0] - c_q4[q][1], c_q4[q][0], c_q4[q][1]};
+                const double mq = m0 * ph[0] + m1 * ph[1] + m2 * ph[2];
+                const double w = c_q4[q][2] * exp(-fa.s0 * mq);
+#pragma unroll
+                for (int b = 0; b < 3; ++b) W[b] += w * ph[b];
+            }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) e[b] = s * (W[b] * g.detJ);
+        }
+    } else if (KIND == FCT_FORM_CHTX_ADJ) {
+        const double v0 = fa.f0[g.d[0]], v1 = fa.f0[g.d[1]], v2 = fa.f0[g.d[2]];
+        const double gvx = v0 * g.gx[0] + v1 * g.gx[1] + v2 * g.gx[2];
+        const double gvy = v0 * g.gy[0] + v1 * g.gy[1] + v2 * g.gy[2];
+        const double u0 = fa.f1[g.d[0]], u1 = fa.f1[g.d[1]], u2 = fa.f1[g.d[2]];
+        double Wa = 0.0;
+        for (int q = 0; q < 7; ++q) {
+            const double ph[3] = {1.0 - c_q5[q][0] - c_q5[q][1], c_q5[q][0], c_q5[q][1]};
+            const double uq = u0 * ph[0] + u1 * ph[1] + u2 * ph[2];
+            Wa += c_q5[q][2] * ((1.0 - fa.s0 * uq) * exp(-fa.s0 * uq)) * ph[a];
+        }
+        Wa *= g.detJ;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) e[b] = Wa * (g.gx[b] * gvx + g.gy[b] * gvy);
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(FCT_RB)
+k_assemble_matrix(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                  const int32_t* __restrict__ v2c_ptr, const int32_t* __restrict__ v2c_idx,
+                  const int32_t* __restrict__ cells, const double* __restrict__ xy, FormArgs fa, double scale,
+                  int accumulate, double* __restrict__ out, int row_begin, int row_end, int64_t nnz, int cap) {
+    double* sV = reinterpret_cast<double*>(fct_smem);
+    double* sO = sV + cap;                                   // previous values when accumulating
+    int32_t* sC = reinterpret_cast<int32_t*>(sO + (accumulate ? cap : 0));
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_s32(sC, colidx, b, nnz);
+    if (accumulate) stage_f64(sO, out, b, nnz);
+    __syncthreads();
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        for (int k = ks; k < ke; ++k) sV[k] = 0.0;
+        const int cs = v2c_ptr[r], ce = v2c_ptr[r + 1];
+        for (int ci = cs; ci < ce; ++ci) {
+            const int c = v2c_idx[ci];
+            const CellGeom g = cell_geom(cells, xy, c);
+            const int a = (g.d[0] == r) ? 0 : ((g.d[1] == r) ? 1 : 2);
+            double e[3];
+            element_row<KIND>(g, a, fa, e);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int col = g.d[q];
+                for (int k = ks; k < ke; ++k)
+                    if (sC[k] == col) { sV[k] += e[q]; break; }
+            }
+        }
+        for (int k = ks; k < ke; ++k) sV[k] = accumulate ? (sO[k] + scale * sV[k]) : (scale * sV[k]);
+    }
+    __syncthreads();
+    unstage_f64(out, sV, b);
+}
+
+// ---- linear forms ------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ double element_load(const CellGeom& g, int a, const FormArgs& fa) {
+    if (KIND == FCT_LOAD_CONST) {
+        return fa.s0 * (g.area / 3.0);
+    } else if (KIND == FCT_LOAD_DRIFT_GRAD) {
+        const double u0 = fa.f1[g.d[0]], u1 = fa.f1[g.d[1]], u2 = fa.f1[g.d[2]];
+        const double gux = u0 * g.gx[0] + u1 * g.gx[1] + u2 * g.gx[2];
+        const double guy = u0 * g.gy[0] + u1 * g.gy[1] + u2 * g.gy[2];
+        const double s = fa.s0 * gux + fa.s1 * guy;
+        const double p[3] = {fa.f0[g.d[0]], fa.f0[g.d[1]], fa.f0[g.d[2]]};
+        return (s * (g.area / 12.0)) * (((p[0] + p[1]) + p[2]) + p[a]);
+    } else if (KIND == FCT_LOAD_CHTX_ADJ) {
+        const double p0 = fa.f0[g.d[0]], p1 = fa.f0[g.d[1]], p2 = fa.f0[g.d[2]];
+        const double gpx = p0 * g.gx[0] + p1 * g.gx[1] + p2 * g.gx[2];
+        const double gpy = p0 * g.gy[0] + p1 * g.gy[1] + p2 * g.gy[2];
+        const double u0 = fa.f1[g.d[0]], u1 = fa.f1[g.d[1]], u2 = fa.f1[g.d[2]];
+        double I = 0.0;
+        for (int q = 0; q < 6; ++q) {
+            const double ph[3] = {1.0 - c_q4[q][0] - c_q4[q][1], c_q4[q][0], c_q4[q][1]};
+            const double uq = u0 * ph[0] + u1 * ph[1] + u2 * ph[2];
+            I += c_q4[q][2] * (fa.s1 * uq * exp(-fa.s0 * uq));
+        }
+        return (gpx * g.gx[a] + gpy * g.gy[a]) * (I * g.detJ);
+    } else {   // FCT_LOAD_P1_1..4: product of 1..4 P1 fields, 7-point degree-5 rule
+        const double* fs[4] = {fa.f0, fa.f1, fa.f2, fa.f3};
+        const int nf = KIND - FCT_LOAD_P1_1 + 1;
+        double v[4][3];
+        for (int i = 0; i < nf; ++i) { v[i][0] = fs[i][g.d[0]]; v[i][1] = fs[i][g.d[1]]; v[i][2] = fs[i][g.d[2]]; }
+        double acc = 0.0;
+        for (int q = 0; q < 7; ++q) {
+            const double ph[3] = {1.0 - c_q5[q][0] - c_q5[q][1], c_q5[q][0], c_q5[q][1]};
+            double t = 1.0;
+            for (int i = 0; i < nf; ++i) t *= v[i][0] * ph[0] + v[i][1] * ph[1] + v[i][2] * ph[2];
+            acc += c_q5[q][2] * t * ph[a];
+        }
+        return acc * g.detJ;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(FCT_RB)
+k_assemble_vector(const int32_t* __restrict__ v2c_ptr, const int32_t* __restrict__ v2c_idx,
+                  const int32_t* __restrict__ cells, const double* __restrict__ xy, FormArgs fa, double scale,
+                  int accumulate, double* __restrict__ out, int row_begin, int row_end) {
+    const int r = row_begin + blockIdx.x * FCT_RB + threadIdx.x;
+    if (r >= row_end) return;
+    double acc = 0.0;
+    const int cs = v2c_ptr[r], ce = v2c_ptr[r + 1];
+    for (int ci = cs; ci < ce; ++ci) {
+        const int c = v2c_idx[ci];
+        const CellGeom g = cell_geom(cells, xy, c);
+        const int a = (g.d[0] == r) ? 0 : ((g.d[1] == r) ? 1 : 2);
+        acc += element_load<KIND>(g, a, fa);
+    }
+    out[r] = accumulate ? (out[r] + scale * acc) : (scale * acc);
+}
+
+// ======================================================================================================
+template <int KIND>
+static int launch_matrix(fct_ctx* ctx, const FormArgs& fa, double scale, int accumulate, double* out) {
+    // all local rows, halo rows included: their entries (j,i) towards owned rows i are complete because every
+    // cell containing an owned vertex is local, and those are the only halo-row values the FCT step reads (a_ji).
+    const int nb = (ctx->n + FCT_RB - 1) / FCT_RB;
+    const size_t smem = (size_t)ctx->cap * (8 * (accumulate ? 2 : 1) + 4);
+    k_assemble_matrix<KIND><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->v2c_ptr, ctx->v2c_idx,
+                                                               ctx->cells, ctx->xy, fa, scale, accumulate, out,
+                                                               0, ctx->n, ctx->nnz, ctx->cap);
+    ctx->launches++;
+    return fct_launch_error(ctx, "fct_assemble_matrix");
+}
+
+template <int KIND>
+static int configure_matrix(int bytes) {
+    FCT_CUDA(cudaFuncSetAttribute(k_assemble_matrix<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return 0;
+}
+
+int fct_assembly_configure(fct_ctx* ctx) {
+    const int bytes = FCT_SMEM_OPTIN; (void)ctx;
+    int rc = 0;
+    rc |= configure_matrix<FCT_FORM_MASS>(bytes);
+    rc |= configure_matrix<FCT_FORM_STIFFNESS>(bytes);
+    rc |= configure_matrix<FCT_FORM_DRIFT>(bytes);
+    rc |= configure_matrix<FCT_FORM_WIND_P1>(bytes);
+    rc |= configure_matrix<FCT_FORM_WIND_P1_T>(bytes);
+    rc |= configure_matrix<FCT_FORM_WMASS1>(bytes);
+    rc |= configure_matrix<FCT_FORM_WMASS2>(bytes);
+    rc |= configure_matrix<FCT_FORM_WMASS3>(bytes);
+    rc |= configure_matrix<FCT_FORM_CHTX>(bytes);
+    rc |= configure_matrix<FCT_FORM_CHTX_EXP>(bytes);
+    rc |= configure_matrix<FCT_FORM_CHTX_ADJ>(bytes);
+    return rc;
+}
+
+extern "C" int fct_ctx_set_mesh(fct_ctx* ctx, int64_t ncells, const int32_t* cell_dofs, const double* dof_xy) {
+    FCT_CHECK(ctx && cell_dofs && dof_xy && ncells >= 1, "fct_ctx_set_mesh: bad argument");
+    FCT_CHECK(3 * ncells < 2147483647LL, "fct_ctx_set_mesh: too many cells for int32 incidence");
+    const int n = ctx->n;
+    // vertex -> incident cells, ascending cell index (counting sort)
+    std::vector<int32_t> ptr((size_t)n + 1, 0);
+    for (int64_t i = 0; i < 3 * ncells; ++i) {
+        const int32_t d = cell_dofs[i];
+        FCT_CHECK(d >= 0 && d < n, "fct_ctx_set_mesh: cell %lld references DoF %d outside [0,%d)", (long long)(i / 3), d, n);
+        ptr[(size_t)d + 1]++;
+    }
+    for (int i = 0; i < n; ++i) ptr[(size_t)i + 1] += ptr[i];
+    std::vector<int32_t> idx((size_t)(3 * ncells));
+    {
+        std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+        for (int64_t c = 0; c < ncells; ++c)
+            for (int q = 0; q < 3; ++q) idx[(size_t)fill[cell_dofs[3 * c + q]]++] = (int32_t)c;
+    }
+    cudaFree(ctx->cells); cudaFree(ctx->xy); cudaFree(ctx->v2c_ptr); cudaFree(ctx->v2c_idx);
+    ctx->cells = nullptr; ctx->xy = nullptr; ctx->v2c_ptr = nullptr; ctx->v2c_idx = nullptr;
+    FCT_CUDA(cudaMalloc((void**)&ctx->cells, sizeof(int32_t) * 3 * (size_t)ncells));
+    FCT_CUDA(cudaMalloc((void**)&ctx->xy, sizeof(double) * 2 * (size_t)n));
+    FCT_CUDA(cudaMalloc((void**)&ctx->v2c_ptr, sizeof(int32_t) * ((size_t)n + 1)));
+    FCT_CUDA(cudaMalloc((void**)&ctx->v2c_idx, sizeof(int32_t) * 3 * (size_t)ncells));
+    FCT_CUDA(cudaMemcpy(ctx->cells, cell_dofs, sizeof(int32_t) * 3 * (size_t)ncells, cudaMemcpyHostToDevice));
+    FCT_CUDA(cudaMemcpy(ctx->xy, dof_xy, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+    FCT_CUDA(cudaMemcpy(ctx->v2c_ptr, ptr.data(), sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+    FCT_CUDA(cudaMemcpy(ctx->v2c_idx, idx.data(), sizeof(int32_t) * 3 * (size_t)ncells, cudaMemcpyHostToDevice));
+    ctx->ncells = ncells;
+    return 0;
+}
+
+extern "C" int fct_assemble_matrix(fct_ctx* ctx, int32_t kind, const double* c0, const double* c1, const double* c2,
+                                   double s0, double s1, double scale, int32_t accumulate, double* out) {
+    FCT_CHECK(ctx && out, "fct_assemble_matrix: null argument");
+    FCT_CHECK(ctx->cells, "fct_assemble_matrix: no mesh set (fct_ctx_set_mesh)");
+    FormArgs fa{c0, c1, c2, nullptr, s0, s1};
+    const int acc = accumulate ? 1 : 0;
+    switch (kind) {
+        case FCT_FORM_MASS: return launch_matrix<FCT_FORM_MASS>(ctx, fa, scale, acc, out);
+        case FCT_FORM_STIFFNESS: return launch_matrix<FCT_FORM_STIFFNESS>(ctx, fa, scale, acc, out);
+        case FCT_FORM_DRIFT:
+            FCT_CHECK(c0, "fct_assemble_matrix(DRIFT): coef0 (control) required");
+            return launch_matrix<FCT_FORM_DRIFT>(ctx, fa, scale, acc, out);
+        case FCT_FORM_WIND_P1:
+            FCT_CHECK(c0 && c1, "fct_assemble_matrix(WIND_P1): coef0/coef1 (wind components) required");
+            return launch_matrix<FCT_FORM_WIND_P1>(ctx, fa, scale, acc, out);
+        case FCT_FORM_WIND_P1_T:
+            FCT_CHECK(c0 && c1, "fct_assemble_matrix(WIND_P1_T): coef0/coef1 (wind components) required");
+            return launch_matrix<FCT_FORM_WIND_P1_T>(ctx, fa, scale, acc, out);
+        case FCT_FORM_WMASS1:
+            FCT_CHECK(c0, "fct_assemble_matrix(WMASS1): coef0 required");
+            return launch_matrix<FCT_FORM_WMASS1>(ctx, fa, scale, acc, out);
+        case FCT_FORM_WMASS2:
+            FCT_CHECK(c0 && c1, "fct_assemble_matrix(WMASS2): coef0, coef1 required");
+            return launch_matrix<FCT_FORM_WMASS2>(ctx, fa, scale, acc, out);
+        case FCT_FORM_WMASS3:
+            FCT_CHECK(c0 && c1 && c2, "fct_assemble_matrix(WMASS3): coef0..2 required");
+            return launch_matrix<FCT_FORM_WMASS3>(ctx, fa, scale, acc, out);
+        case FCT_FORM_CHTX:
+            FCT_CHECK(c0, "fct_assemble_matrix(CHTX): coef0 required");
+            return launch_matrix<FCT_FORM_CHTX>(ctx, fa, scale, acc, out);
+        case FCT_FORM_CHTX_EXP:
+            FCT_CHECK(c0 && c1, "fct_assemble_matrix(CHTX_EXP): coef0, coef1 required");
+            return launch_matrix<FCT_FORM_CHTX_EXP>(ctx, fa, scale, acc, out);
+        case FCT_FORM_CHTX_ADJ:
+            FCT_CHECK(c0 && c1, "fct_assemble_matrix(CHTX_ADJ): coef0, coef1 required");
+            return launch_matrix<FCT_FORM_CHTX_ADJ>(ctx, fa, scale, acc, out);
+        default: break;
+    }
+    fct_set_error("fct_assemble_matrix: unknown form kind %d", kind);
+    return 2;
+}
+
+template <int KIND>
+static int launch_vector(fct_ctx* ctx, const FormArgs& fa, double scale, int accumulate, double* out) {
+    const int nb = fct_nblocks(ctx);
+    if (nb <= 0) return 0;
+    k_assemble_vector<KIND><<<nb, FCT_RB, 0, ctx->stream>>>(ctx->v2c_ptr, ctx->v2c_idx, ctx->cells, ctx->xy, fa, scale,
+                                                            accumulate, out, ctx->row_begin, ctx->row_end);
+    ctx->launches++;
+    return fct_launch_error(ctx, "fct_assemble_vector");
+}
+
+extern "C" int fct_assemble_vector(fct_ctx* ctx, int32_t kind, const double* c0, const double* c1, const double* c2,
+                                   const double* c3, double s0, double s1, double scale, int32_t accumulate,
+                                   double* out) {
+    FCT_CHECK(ctx && out, "fct_assemble_vector: null argument");
+    FCT_CHECK(ctx->cells, "fct_assemble_vector: no mesh set (fct_ctx_set_mesh)");
+    FormArgs fa{c0, c1, c2, c3, s0, s1};
+    const int acc = accumulate ? 1 : 0;
+    switch (kind) {
+        case FCT_LOAD_P1_1:
+            FCT_CHECK(c0, "fct_assemble_vector(P1_1): coef0 required");
+            return launch_vector<FCT_LOAD_P1_1>(ctx, fa, scale, acc, out);
+        case FCT_LOAD_P1_2:
+            FCT_CHECK(c0 && c1, "fct_assemble_vector(P1_2): coef0, coef1 required");
+            return launch_vector<FCT_LOAD_P1_2>(ctx, fa, scale, acc, out);
+        case FCT_LOAD_P1_3:
+            FCT_CHECK(c0 && c1 && c2, "fct_assemble_vector(P1_3): coef0..2 required");
+            return launch_vector<FCT_LOAD_P1_3>(ctx, fa, scale, acc, out);
+        case FCT_LOAD_P1_4:
+            FCT_CHECK(c0 && c1 && c2 && c3, "fct_assemble_vector(P1_4): coef0..3 required");
+            return launch_vector<FCT_LOAD_P1_4>(ctx, fa, scale, acc, out);
+        case FCT_LOAD_CONST: return launch_vector<FCT_LOAD_CONST>(ctx, fa, scale, acc, out);
+        case FCT_LOAD_DRIFT_GRAD:
+            FCT_CHECK(c0 && c1, "fct_assemble_vector(DRIFT_GRAD): coef0 (p), coef1 (u) required");
+            return launch_vector<FCT_LOAD_DRIFT_GRAD>(ctx, fa, scale, acc, out);
+        case FCT_LOAD_CHTX_ADJ:
+            FCT_CHECK(c0 && c1, "fct_assemble_vector(CHTX_ADJ): coef0 (p), coef1 (u) required");
+            return launch_vector<FCT_LOAD_CHTX_ADJ>(ctx, fa, scale, acc, out);
+        default: break;
+    }
+    fct_set_error("fct_assemble_vector: unknown form kind %d", kind);
+    return 2;
+}
+
+int fct_row_lump_diag(fct_ctx* ctx, const double* mat, double* out, double* diag);
+int fct_halo_exchange_if(fct_ctx* ctx, double* vec);
+
+extern "C" int fct_assemble_static(fct_ctx* ctx) {
+    FCT_CHECK(ctx, "fct_assemble_static: null context");
+    FCT_CHECK(ctx->cells, "fct_assemble_static: no mesh set (fct_ctx_set_mesh)");
+    FormArgs fa{nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+    if (launch_matrix<FCT_FORM_MASS>(ctx, fa, 1.0, 0, ctx->M)) return 1;
+    if (launch_matrix<FCT_FORM_STIFFNESS>(ctx, fa, 1.0, 0, ctx->K)) return 1;
+    if (fct_row_lump_diag(ctx, ctx->M, ctx->ML, ctx->Mdiag)) return 1;
+    if (fct_halo_exchange_if(ctx, ctx->ML)) return 1;
+    if (fct_halo_exchange_if(ctx, ctx->Mdiag)) return 1;
+    ctx->mass_set = true;
+    return 0;
+}

@@ -1,0 +1,218 @@
+// Shared device/host plumbing for libfctpdeco (sm_100a).
+//
+// Kernel skeleton used by every CSR pass ("row-block staging"):
+//   * one CTA owns FCT_RB consecutive rows and therefore one contiguous range [k0,k1) of the CSR
+//     value / index arrays;
+//   * phase 1 streams that range into shared memory with 16-byte, L1-bypassing loads, perfectly
+//     coalesced whatever the row lengths are;
+//   * phase 2 is thread-per-row on shared memory (P1 rows have <= 7..9 entries; the 8-byte stride
+//     between consecutive rows is odd on P1 meshes, so the row walk is bank-conflict free);
+//     neighbour values x[col] are gathered through L1/L2 -- consecutive rows gather consecutive
+//     addresses, so these gathers coalesce too;
+//   * results that are value arrays go back through shared memory and a coalesced phase 3.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define FCT_RB 256            // rows (= threads) per CTA
+#define FCT_ALIGN 4           // staging alignment in elements (16 B for int32, 32 B for fp64)
+#define FCT_SMEM_OPTIN (200 * 1024)   // dynamic shared memory opt-in ceiling for every row-block kernel
+
+void fct_set_error(const char* fmt, ...);
+
+#define FCT_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            fct_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+#define FCT_CHECK(cond, ...)                                                                    \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            fct_set_error(__VA_ARGS__);                                                         \
+            return 2;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+struct fct_comm;   // NCCL state (fct_comm.cu)
+
+struct fct_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    cudaStream_t copy_stream = 0;
+    int32_t n = 0;              // local rows (= local vector length)
+    int64_t nnz = 0;
+    int32_t row_begin = 0, row_end = 0;
+    int32_t cap = 0;            // max staged entries of any row block (incl. alignment slack)
+    int32_t max_row = 0;
+    int32_t* rowptr = nullptr;  // device
+    int32_t* colidx = nullptr;
+    int32_t* tpos = nullptr;
+    // mesh
+    int64_t ncells = 0;
+    int32_t* cells = nullptr;       // [ncells*3]
+    double* xy = nullptr;           // [n*2]
+    int32_t* v2c_ptr = nullptr;     // vertex -> incident cells (CSR), built on set_mesh
+    int32_t* v2c_idx = nullptr;
+    // static matrices
+    double* M = nullptr;
+    double* ML = nullptr;
+    double* Mdiag = nullptr;
+    double* K = nullptr;
+    bool mass_set = false;
+    // workspace
+    double* Lvals = nullptr;    // low-order operator
+    double* Dvals = nullptr;    // artificial diffusion (off-diagonals)
+    double* Avals = nullptr;    // assembled operator (time loops) / host-call staging
+    double* Svals = nullptr;    // host-call staging
+    double* w[12] = {nullptr};  // vector workspace [n] each
+    double* red = nullptr;      // device scalars for reductions (64 doubles)
+    unsigned long long* jstate = nullptr;  // Jacobi state words
+    double* pinned = nullptr;   // small pinned host buffer (64 doubles)
+    double rtol = 1e-14;
+    int32_t max_sweeps = 200;
+    int64_t launches = 0;
+    fct_comm* comm = nullptr;
+    // halo description (multi-GPU)
+    int32_t send_lo[2] = {0, 0}, send_hi[2] = {0, 0};
+};
+
+static inline int fct_nblocks(const fct_ctx* c) { return (c->row_end - c->row_begin + FCT_RB - 1) / FCT_RB; }
+
+#ifdef __CUDACC__
+// ---- streaming loads (read-once data: bypass L1 so it stays free for the x gathers) -------------
+__device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int4 ld_stream_s32x4(const int32_t* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+struct RowBlock {
+    int r0;      // first row of this CTA
+    int nr;      // rows in this CTA
+    int k0, k1;  // CSR range
+    int ka;      // k0 rounded down to FCT_ALIGN: shared index = k - ka
+};
+
+__device__ __forceinline__ RowBlock row_block(const int32_t* __restrict__ rowptr, int row_begin, int row_end) {
+    RowBlock b;
+    b.r0 = row_begin + blockIdx.x * FCT_RB;
+    b.nr = min(FCT_RB, row_end - b.r0);
+    b.k0 = rowptr[b.r0];
+    b.k1 = rowptr[b.r0 + b.nr];
+    b.ka = b.k0 & ~(FCT_ALIGN - 1);
+    return b;
+}
+
+// stage g[ka .. k1) into s[0 .. k1-ka); vector loads where the whole vector is inside [0,nnz)
+__device__ __forceinline__ void stage_f64(double* __restrict__ s, const double* __restrict__ g, const RowBlock& b,
+                                          int64_t nnz) {
+    const int cnt = b.k1 - b.ka;
+    for (int i = 2 * threadIdx.x; i < cnt; i += 2 * FCT_RB) {
+        const int64_t k = (int64_t)b.ka + i;
+        if (k + 1 < nnz) {
+            double2 v = ld_stream_f64x2(g + k);
+            s[i] = v.x;
+            s[i + 1] = v.y;
+        } else if (k < nnz) {
+            s[i] = ld_stream_f64(g + k);
+        }
+    }
+}
+__device__ __forceinline__ void stage_s32(int32_t* __restrict__ s, const int32_t* __restrict__ g, const RowBlock& b,
+                                          int64_t nnz) {
+    const int cnt = b.k1 - b.ka;
+    for (int i = 4 * threadIdx.x; i < cnt; i += 4 * FCT_RB) {
+        const int64_t k = (int64_t)b.ka + i;
+        if (k + 3 < nnz) {
+            int4 v = ld_stream_s32x4(g + k);
+            s[i] = v.x; s[i + 1] = v.y; s[i + 2] = v.z; s[i + 3] = v.w;
+        } else {
+            for (int q = 0; q < 4; ++q)
+                if (k + q < nnz) s[i + q] = g[k + q];
+        }
+    }
+}
+// write s[k0-ka .. k1-ka) back to g[k0 .. k1): scalar 8-byte stores, fully coalesced
+__device__ __forceinline__ void unstage_f64(double* __restrict__ g, const double* __restrict__ s, const RowBlock& b) {
+    const int off = b.k0 - b.ka;
+    const int cnt = b.k1 - b.k0;
+    for (int i = threadIdx.x; i < cnt; i += FCT_RB) g[(int64_t)b.k0 + i] = s[off + i];
+}
+
+// ---- block reductions (FCT_RB threads) ----------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// deterministic block sum: warp shuffles, then warp 0 adds the FCT_RB/32 partials in a fixed order
+__device__ __forceinline__ double block_sum(double v, double* sred /* >= 8 doubles */) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sred[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = (l < FCT_RB / 32) ? sred[l] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;   // valid in warp 0
+}
+__device__ __forceinline__ double block_max(double v, double* sred) {
+    v = warp_max(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sred[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = (l < FCT_RB / 32) ? sred[l] : sred[0];
+        t = warp_max(t);
+    }
+    return t;
+}
+__device__ __forceinline__ double block_min(double v, double* sred) {
+    v = warp_min(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sred[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = (l < FCT_RB / 32) ? sred[l] : sred[0];
+        t = warp_min(t);
+    }
+    return t;
+}
+#endif  // __CUDACC__
+
+// internal cross-file entry points
+int fct_launch_error(fct_ctx* ctx, const char* what);

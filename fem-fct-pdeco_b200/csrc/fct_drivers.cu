@@ -1,0 +1,506 @@
+// Device-resident time loops of the drift-control advection PDECO (the 4096^2 benchmark shape) and the
+// Krylov/Jacobi solvers that replace the reference's spsolve calls for the second-species systems.
+//
+//   advection_solidbody_FCT_PDECO_alltime.py:210-228  state loop      -> fct_advdrift_state[_host]
+//   advection_solidbody_FCT_PDECO_alltime.py:235-259  adjoint loop    -> fct_advdrift_adjoint
+//   advection_solidbody_FCT_PDECO_alltime.py:265-275  gradient loop   -> fct_advdrift_gradient
+//   helpers.py:596,686,1342,1538 spsolve(Mat, rhs)                    -> fct_solve
+#include "fct_common.cuh"
+#include "../../include/fctpdeco.h"
+
+extern __shared__ __align__(16) unsigned char fct_smem[];
+
+int fct_halo_exchange_if(fct_ctx* ctx, double* vec);
+int fct_allreduce_sum_dev(fct_ctx* ctx, double* dev, int count);
+
+// sweeps bookkeeping across the steps of a time loop: acc[0] += sweeps of the step just finished,
+// acc[1] += 1 if that step did not converge
+__global__ void k_sweeps_accumulate(const unsigned long long* __restrict__ jstate, unsigned long long* __restrict__ acc) {
+    acc[0] += jstate[4];
+    if (jstate[4] > 0 && jstate[3] == 0) acc[1] += 1;
+}
+
+static int acc_reset(fct_ctx* ctx) {
+    FCT_CUDA(cudaMemsetAsync(ctx->jstate + 8, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    return 0;
+}
+static int acc_read(fct_ctx* ctx, int32_t* total_sweeps_host) {
+    if (!total_sweeps_host) return 0;
+    unsigned long long h[2];
+    FCT_CUDA(cudaMemcpyAsync(h, ctx->jstate + 8, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+    FCT_CHECK(h[1] == 0, "low-order Jacobi solve did not converge in %llu time step(s) (max_sweeps=%d, rtol=%g)",
+              h[1], ctx->max_sweeps, ctx->rtol);
+    *total_sweeps_host = (int32_t)h[0];
+    return 0;
+}
+
+// operator of the drift-control problem in FCT_alg_ref sign convention:
+//   state   (legacy A_u = -eps Ad + Adrift1 + Adrift2, FCT_alg(A_u) == FCT_alg_ref(-A_u)):  eps K - drift(c)
+//   adjoint (legacy A_p = -eps Ad - Adrift1 - Adrift2):                                      eps K + drift(c)
+static int assemble_drift_operator(fct_ctx* ctx, const double* c, double bx, double by, double eps, double drift_sign) {
+    if (fct_assemble_matrix(ctx, FCT_FORM_DRIFT, c, nullptr, nullptr, bx, by, drift_sign, 0, ctx->Avals)) return 1;
+    if (eps != 0.0) {
+        FCT_CHECK(ctx->K, "stiffness matrix not assembled");
+        if (fct_axpby(ctx, ctx->nnz, 1.0, ctx->Avals, eps, ctx->K, ctx->Avals)) return 1;
+    }
+    return 0;
+}
+
+extern "C" int fct_advdrift_state(fct_ctx* ctx, const double* c_traj, double* u_traj, int32_t num_steps, double dt,
+                                  double bx, double by, double eps, int32_t* total_sweeps_host) {
+    FCT_CHECK(ctx && c_traj && u_traj && num_steps >= 0, "fct_advdrift_state: bad argument");
+    FCT_CHECK(ctx->cells && ctx->mass_set, "fct_advdrift_state: mesh / static matrices not set");
+    const size_t n = (size_t)ctx->n;
+    if (acc_reset(ctx)) return 1;
+    for (int i = 1; i <= num_steps; ++i) {
+        if (assemble_drift_operator(ctx, c_traj + i * n, bx, by, eps, -1.0)) return 1;
+        if (fct_step(ctx, ctx->Avals, 1.0, nullptr, nullptr, u_traj + (i - 1) * n, dt, u_traj + i * n, nullptr)) return 1;
+        k_sweeps_accumulate<<<1, 1, 0, ctx->stream>>>(ctx->jstate, ctx->jstate + 8);
+        ctx->launches++;
+    }
+    return acc_read(ctx, total_sweeps_host);
+}
+
+__global__ void k_sub(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] - b[i];
+}
+
+extern "C" int fct_advdrift_adjoint(fct_ctx* ctx, const double* c_traj, const double* u_traj, const double* uhat_traj,
+                                    double* p_traj, int32_t num_steps, double dt, double bx, double by, double eps,
+                                    int32_t* total_sweeps_host) {
+    FCT_CHECK(ctx && c_traj && u_traj && uhat_traj && p_traj && num_steps >= 0, "fct_advdrift_adjoint: bad argument");
+    FCT_CHECK(ctx->cells && ctx->mass_set, "fct_advdrift_adjoint: mesh / static matrices not set");
+    const size_t n = (size_t)ctx->n;
+    if (acc_reset(ctx)) return 1;
+    // p(T) = 0   (advection_solidbody_FCT_PDECO_alltime.py:235)
+    FCT_CUDA(cudaMemsetAsync(p_traj + num_steps * n, 0, sizeof(double) * n, ctx->stream));
+    double* diff = ctx->w[10];
+    double* rhs = ctx->w[11];
+    for (int i = num_steps - 1; i >= 0; --i) {
+        if (assemble_drift_operator(ctx, c_traj + i * n, bx, by, eps, 1.0)) return 1;
+        // p_rhs = assemble((uhat_n - u_n) v dx) = M (uhat_n - u_n)     (:255)
+        k_sub<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->n, uhat_traj + i * n, u_traj + i * n, diff);
+        ctx->launches++;
+        if (fct_spmv(ctx, ctx->M, diff, 1.0, 0.0, nullptr, rhs)) return 1;
+        if (fct_step(ctx, ctx->Avals, 1.0, nullptr, rhs, p_traj + (i + 1) * n, dt, p_traj + i * n, nullptr)) return 1;
+        k_sweeps_accumulate<<<1, 1, 0, ctx->stream>>>(ctx->jstate, ctx->jstate + 8);
+        ctx->launches++;
+    }
+    return acc_read(ctx, total_sweeps_host);
+}
+
+extern "C" int fct_advdrift_gradient(fct_ctx* ctx, const double* c_traj, const double* u_traj, const double* p_traj,
+                                     double* d_traj, int32_t num_steps, double beta, double bx, double by) {
+    FCT_CHECK(ctx && c_traj && u_traj && p_traj && d_traj && num_steps >= 0, "fct_advdrift_gradient: bad argument");
+    FCT_CHECK(ctx->cells && ctx->mass_set, "fct_advdrift_gradient: mesh / static matrices not set");
+    const size_t n = (size_t)ctx->n;
+    double* t = ctx->w[10];
+    double* rhs = ctx->w[11];
+    for (int i = 0; i <= num_steps; ++i) {
+        // rhs_dk = -(beta M c + assemble(p (b.grad u) v dx));  dk = ChebSI(rhs_dk, M, diag M, 20, .5, 2)   (:272-275)
+        if (fct_assemble_vector(ctx, FCT_LOAD_DRIFT_GRAD, p_traj + i * n, u_traj + i * n, nullptr, nullptr, bx, by, 1.0, 0, t))
+            return 1;
+        if (fct_spmv(ctx, ctx->M, c_traj + i * n, -beta, -1.0, t, rhs)) return 1;
+        if (fct_chebsi(ctx, ctx->M, ctx->Mdiag, rhs, d_traj + i * n, 20, 0.5, 2.0)) return 1;
+        if (fct_halo_exchange_if(ctx, d_traj + i * n)) return 1;
+    }
+    return 0;
+}
+
+// Forward loop with host trajectories: control slices stream in and state slices stream out on the copy stream,
+// double-buffered and overlapped with the FCT step of the neighbouring time level.
+extern "C" int fct_advdrift_state_host(fct_ctx* ctx, const double* c_host, double* u_host, int32_t num_steps, double dt,
+                                       double bx, double by, double eps, int32_t* total_sweeps_host) {
+    FCT_CHECK(ctx && c_host && u_host && num_steps >= 0, "fct_advdrift_state_host: bad argument");
+    FCT_CHECK(ctx->cells && ctx->mass_set, "fct_advdrift_state_host: mesh / static matrices not set");
+    FCT_CHECK(!ctx->comm, "fct_advdrift_state_host: single-GPU contexts only");
+    const size_t n = (size_t)ctx->n, vb = sizeof(double) * n;
+    double *cbuf[2] = {nullptr, nullptr}, *ubuf[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t c_ready[2], c_free[2], u_ready[3], u_free[3];
+    int rc = 0;
+    for (int i = 0; i < 2; ++i) {
+        if (cudaMalloc((void**)&cbuf[i], vb) != cudaSuccess) rc = 1;
+        cudaEventCreateWithFlags(&c_ready[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c_free[i], cudaEventDisableTiming);
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (cudaMalloc((void**)&ubuf[i], vb) != cudaSuccess) rc = 1;
+        cudaEventCreateWithFlags(&u_ready[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&u_free[i], cudaEventDisableTiming);
+    }
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        for (int i = 0; i < 2; ++i) { cudaFree(cbuf[i]); cudaEventDestroy(c_ready[i]); cudaEventDestroy(c_free[i]); }
+        for (int i = 0; i < 3; ++i) { cudaFree(ubuf[i]); cudaEventDestroy(u_ready[i]); cudaEventDestroy(u_free[i]); }
+    };
+    if (rc) { cleanup(); fct_set_error("fct_advdrift_state_host: device allocation failed"); return 1; }
+#define TRY(call) do { if ((call) != cudaSuccess) { fct_set_error("fct_advdrift_state_host: %s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); cleanup(); return 1; } } while (0)
+    if (acc_reset(ctx)) { cleanup(); return 1; }
+    // initial condition
+    TRY(cudaMemcpyAsync(ubuf[0], u_host, vb, cudaMemcpyHostToDevice, ctx->stream));
+    if (num_steps >= 1) {
+        TRY(cudaMemcpyAsync(cbuf[1], c_host + n, vb, cudaMemcpyHostToDevice, ctx->copy_stream));
+        TRY(cudaEventRecord(c_ready[1], ctx->copy_stream));
+    }
+    for (int i = 1; i <= num_steps; ++i) {
+        const int cb = i & 1, un = (i - 1) % 3, uo = i % 3;
+        // prefetch the next control slice into the other buffer once the step that used it has finished
+        if (i + 1 <= num_steps) {
+            if (i >= 2) TRY(cudaStreamWaitEvent(ctx->copy_stream, c_free[(i + 1) & 1], 0));
+            TRY(cudaMemcpyAsync(cbuf[(i + 1) & 1], c_host + (size_t)(i + 1) * n, vb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            TRY(cudaEventRecord(c_ready[(i + 1) & 1], ctx->copy_stream));
+        }
+        TRY(cudaStreamWaitEvent(ctx->stream, c_ready[cb], 0));
+        if (i >= 3) TRY(cudaStreamWaitEvent(ctx->stream, u_free[uo], 0));   // D2H of slice i-3 done
+        if (assemble_drift_operator(ctx, cbuf[cb], bx, by, eps, -1.0)) { cleanup(); return 1; }
+        if (fct_step(ctx, ctx->Avals, 1.0, nullptr, nullptr, ubuf[un], dt, ubuf[uo], nullptr)) { cleanup(); return 1; }
+        k_sweeps_accumulate<<<1, 1, 0, ctx->stream>>>(ctx->jstate, ctx->jstate + 8);
+        ctx->launches++;
+        TRY(cudaEventRecord(c_free[cb], ctx->stream));
+        TRY(cudaEventRecord(u_ready[uo], ctx->stream));
+        // stream the new slice out
+        TRY(cudaStreamWaitEvent(ctx->copy_stream, u_ready[uo], 0));
+        TRY(cudaMemcpyAsync(u_host + (size_t)i * n, ubuf[uo], vb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        TRY(cudaEventRecord(u_free[uo], ctx->copy_stream));
+    }
+#undef TRY
+    rc = acc_read(ctx, total_sweeps_host);
+    cleanup();
+    return rc;
+}
+
+// ======================================================================================================
+// Solvers for the second-species systems  (mat x = b)
+// ======================================================================================================
+int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, double* x, double* tmp, double rtol,
+                     int max_sweeps);
+int fct_read_step_info(fct_ctx* ctx, fct_step_info* info);
+
+__global__ void k_jstate_reset(unsigned long long* __restrict__ jstate) {
+    for (int i = 0; i < 7; ++i) jstate[i] = 0ull;
+    jstate[7] = 0xFFFFFFFFFFFFFFFFull;
+}
+
+// Krylov scalars live on the device (ctx->red): no host round trip inside an iteration.
+enum { S_RZ = 0, S_PAP = 1, S_RR = 2, S_BB = 3, S_RZN = 4, S_ALPHA = 5, S_OMEGA = 6, S_RHO = 7, S_RHON = 8,
+       S_TS = 9, S_TT = 10, S_R0V = 11, S_DONE = 12, S_ITS = 13 };
+
+// q = A p_new with p_new = z + beta p evaluated on the fly at the neighbours (beta = rzn/rz from device scalars;
+// first iteration: p_new = z); writes p_new_i, q_i and the block partial of p_new . q
+__global__ void __launch_bounds__(FCT_RB)
+k_pcg_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Av,
+           const double* __restrict__ z, const double* __restrict__ p, double* __restrict__ pnew, double* __restrict__ q,
+           const double* __restrict__ sc, int first, double* __restrict__ partial, int row_begin, int row_end,
+           int64_t nnz, int cap) {
+    if (sc[S_DONE] != 0.0) return;
+    double* sA = reinterpret_cast<double*>(fct_smem);
+    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
+    __shared__ double sred[FCT_RB / 32];
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sA, Av, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    __syncthreads();
+    const double beta = first ? 0.0 : sc[S_RZN] / sc[S_RZ];
+    double v = 0.0;
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        double acc = 0.0;
+        for (int k = ks; k < ke; ++k) {
+            const int c = sC[k];
+            const double pc = first ? z[c] : (z[c] + beta * p[c]);
+            acc += sA[k] * pc;
+        }
+        const double pr = first ? z[r] : (z[r] + beta * p[r]);
+        pnew[r] = pr;
+        q[r] = acc;
+        v = pr * acc;
+    }
+    const double s = block_sum(v, sred);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// x += alpha p; r -= alpha q; z = r / diag; partials of r.z and r.r     (alpha = rz / pAp)
+__global__ void __launch_bounds__(FCT_RB)
+k_pcg_update(const double* __restrict__ dinv, const double* __restrict__ p, const double* __restrict__ q,
+             double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, const double* __restrict__ sc,
+             double* __restrict__ partial_rz, double* __restrict__ partial_rr, int row_begin, int row_end) {
+    if (sc[S_DONE] != 0.0) return;
+    __shared__ double sred[FCT_RB / 32];
+    const int i = row_begin + blockIdx.x * FCT_RB + threadIdx.x;
+    const double alpha = sc[S_RZ] / sc[S_PAP];
+    double vrz = 0.0, vrr = 0.0;
+    if (i < row_end) {
+        x[i] += alpha * p[i];
+        const double rn = r[i] - alpha * q[i];
+        r[i] = rn;
+        const double zn = rn * dinv[i];
+        z[i] = zn;
+        vrz = rn * zn;
+        vrr = rn * rn;
+    }
+    const double s1 = block_sum(vrz, sred);
+    const double s2 = block_sum(vrr, sred);
+    if (threadIdx.x == 0) { partial_rz[blockIdx.x] = s1; partial_rr[blockIdx.x] = s2; }
+}
+
+// r = b - A x; z = r/diag; dinv = 1/diag; partials r.z, r.r, b.b
+__global__ void __launch_bounds__(FCT_RB)
+k_krylov_init(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Av,
+              const double* __restrict__ bvec, const double* __restrict__ x, double* __restrict__ r,
+              double* __restrict__ z, double* __restrict__ dinv, double* __restrict__ p_rz, double* __restrict__ p_rr,
+              double* __restrict__ p_bb, int row_begin, int row_end, int64_t nnz, int cap) {
+    double* sA = reinterpret_cast<double*>(fct_smem);
+    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
+    __shared__ double sred[FCT_RB / 32];
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sA, Av, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    __syncthreads();
+    double vrz = 0.0, vrr = 0.0, vbb = 0.0;
+    if ((int)threadIdx.x < b.nr) {
+        const int rr_ = b.r0 + threadIdx.x;
+        const int ks = rowptr[rr_] - b.ka, ke = rowptr[rr_ + 1] - b.ka;
+        double acc = 0.0, dg = 1.0;
+        for (int k = ks; k < ke; ++k) {
+            const int c = sC[k];
+            if (c == rr_) dg = sA[k];
+            acc += sA[k] * x[c];
+        }
+        const double bi = bvec[rr_];
+        const double ri = bi - acc;
+        const double di = 1.0 / dg;
+        r[rr_] = ri;
+        dinv[rr_] = di;
+        const double zi = ri * di;
+        z[rr_] = zi;
+        vrz = ri * zi; vrr = ri * ri; vbb = bi * bi;
+    }
+    const double s1 = block_sum(vrz, sred);
+    const double s2 = block_sum(vrr, sred);
+    const double s3 = block_sum(vbb, sred);
+    if (threadIdx.x == 0) { p_rz[blockIdx.x] = s1; p_rr[blockIdx.x] = s2; p_bb[blockIdx.x] = s3; }
+}
+
+// sc[dst[j]] = sum(partial_j[0..m)) for up to 3 partial arrays (one block, fixed order); then `post` bookkeeping
+__global__ void __launch_bounds__(FCT_RB)
+k_krylov_reduce(const double* __restrict__ p0, int d0, const double* __restrict__ p1, int d1,
+                const double* __restrict__ p2, int d2, int m, double* __restrict__ sc, int post, double rtol) {
+    if (sc[S_DONE] != 0.0) return;
+    __shared__ double sred[FCT_RB / 32];
+    const double* ps[3] = {p0, p1, p2};
+    const int ds[3] = {d0, d1, d2};
+    for (int j = 0; j < 3; ++j) {
+        if (!ps[j]) continue;
+        double v = 0.0;
+        for (int i = threadIdx.x; i < m; i += FCT_RB) v += ps[j][i];
+        const double s = block_sum(v, sred);
+        if (threadIdx.x == 0) sc[ds[j]] = s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (post == 1) {            // after PCG update: rotate rz, test convergence, count the iteration
+            sc[S_ITS] += 1.0;
+            if (sc[S_RR] <= rtol * rtol * sc[S_BB]) sc[S_DONE] = 1.0;
+        } else if (post == 2) {     // after init
+            if (sc[S_BB] == 0.0 || sc[S_RR] <= rtol * rtol * sc[S_BB]) sc[S_DONE] = 1.0;
+        }
+    }
+}
+// rz <- rzn (kept separate so that k_pcg_spmv of the next iteration sees both)
+__global__ void k_pcg_rotate(double* __restrict__ sc) {
+    if (sc[S_DONE] != 0.0) return;
+    sc[S_RZ] = sc[S_RZN];
+}
+
+static size_t smem11(const fct_ctx* c) { return (size_t)c->cap * 12; }
+
+int fct_drivers_configure(fct_ctx* ctx) {
+    const int w = FCT_SMEM_OPTIN; (void)ctx;
+    FCT_CUDA(cudaFuncSetAttribute(k_pcg_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_krylov_init, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    return 0;
+}
+
+// generic vector kernels for BiCGStab
+__global__ void __launch_bounds__(FCT_RB)
+k_dot2(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+       const double* __restrict__ d, double* __restrict__ p_ab, double* __restrict__ p_cd, const double* __restrict__ sc,
+       int row_begin, int row_end) {
+    if (sc[S_DONE] != 0.0) return;
+    __shared__ double sred[FCT_RB / 32];
+    const int i = row_begin + blockIdx.x * FCT_RB + threadIdx.x;
+    double v1 = 0.0, v2 = 0.0;
+    if (i < row_end) {
+        v1 = a[i] * b[i];
+        if (c) v2 = c[i] * d[i];
+    }
+    const double s1 = block_sum(v1, sred);
+    const double s2 = block_sum(v2, sred);
+    if (threadIdx.x == 0) { p_ab[blockIdx.x] = s1; if (p_cd) p_cd[blockIdx.x] = s2; }
+}
+
+// BiCGStab vector updates selected by `mode` (scalars read from the device):
+//  mode 0: p = r + beta (p - omega v), beta = (rhon/rho)(alpha/omega); phat = p * dinv      [first: p = r]
+//  mode 1: s = r - alpha v; shat = s * dinv            (alpha = rhon / r0v)
+//  mode 2: x += alpha phat + omega shat; r = s - omega t   (omega = ts/tt)
+__global__ void __launch_bounds__(FCT_RB)
+k_bicg_vec(int mode, int first, const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
+           double* __restrict__ p, double* __restrict__ v, double* __restrict__ s, double* __restrict__ t,
+           double* __restrict__ phat, double* __restrict__ shat, const double* __restrict__ sc, int row_begin, int row_end) {
+    if (sc[S_DONE] != 0.0) return;
+    const int i = row_begin + blockIdx.x * FCT_RB + threadIdx.x;
+    if (i >= row_end) return;
+    if (mode == 0) {
+        double pi;
+        if (first) pi = r[i];
+        else {
+            const double beta = (sc[S_RHON] / sc[S_RHO]) * (sc[S_ALPHA] / sc[S_OMEGA]);
+            pi = r[i] + beta * (p[i] - sc[S_OMEGA] * v[i]);
+        }
+        p[i] = pi;
+        phat[i] = pi * dinv[i];
+    } else if (mode == 1) {
+        const double alpha = sc[S_RHON] / sc[S_R0V];
+        const double si = r[i] - alpha * v[i];
+        s[i] = si;
+        shat[i] = si * dinv[i];
+    } else {
+        const double alpha = sc[S_RHON] / sc[S_R0V];
+        const double omega = sc[S_TS] / sc[S_TT];
+        x[i] += alpha * phat[i] + omega * shat[i];
+        r[i] = s[i] - omega * t[i];
+    }
+}
+// end-of-iteration scalar bookkeeping for BiCGStab
+__global__ void k_bicg_scalars(double* __restrict__ sc, double rtol) {
+    if (sc[S_DONE] != 0.0) return;
+    sc[S_ALPHA] = sc[S_RHON] / sc[S_R0V];
+    sc[S_OMEGA] = sc[S_TS] / sc[S_TT];
+    sc[S_RHO] = sc[S_RHON];
+    sc[S_ITS] += 1.0;
+    if (sc[S_RR] <= rtol * rtol * sc[S_BB]) sc[S_DONE] = 1.0;
+}
+
+static int reduce_to(fct_ctx* ctx, const double* p0, int d0, const double* p1, int d1, const double* p2, int d2,
+                     int post, double rtol) {
+    k_krylov_reduce<<<1, FCT_RB, 0, ctx->stream>>>(p0, d0, p1, d1, p2, d2, fct_nblocks(ctx), ctx->red, post, rtol);
+    ctx->launches++;
+    // multi-GPU: the partial sums are per rank; all-reduce the freshly written scalars
+    if (ctx->comm) {
+        const int ds[3] = {d0, d1, d2};
+        const double* ps[3] = {p0, p1, p2};
+        for (int j = 0; j < 3; ++j)
+            if (ps[j] && fct_allreduce_sum_dev(ctx, ctx->red + ds[j], 1)) return 1;
+    }
+    return 0;
+}
+
+extern "C" int fct_solve(fct_ctx* ctx, int32_t kind, const double* mat, const double* b, double* x, double rtol,
+                         int32_t maxit, int32_t* its_host, double* res_host) {
+    FCT_CHECK(ctx && mat && b && x && rtol > 0 && maxit >= 1, "fct_solve: bad argument");
+    FCT_CHECK(!ctx->comm || kind == 0, "fct_solve: Krylov solvers are single-GPU in this version");
+    const int nb = fct_nblocks(ctx);
+    if (kind == 0) {
+        k_jstate_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+        ctx->launches++;
+        if (fct_jacobi_solve(ctx, mat, b, x, ctx->w[5], rtol, maxit)) return 1;
+        fct_step_info info;
+        if (fct_read_step_info(ctx, &info)) return 1;
+        if (its_host) *its_host = info.solver_sweeps;
+        if (res_host) *res_host = info.x_norm > 0 ? info.last_delta / info.x_norm : info.last_delta;
+        FCT_CHECK(info.converged, "fct_solve(jacobi): not converged after %d sweeps (delta/|x| = %g)", info.solver_sweeps,
+                  info.x_norm > 0 ? info.last_delta / info.x_norm : info.last_delta);
+        return 0;
+    }
+    FCT_CHECK(kind == 1 || kind == 2, "fct_solve: unknown solver kind %d", kind);
+    double* r = ctx->w[0];
+    double* z = ctx->w[1];
+    double* p = ctx->w[2];
+    double* q = ctx->w[3];
+    double* dinv = ctx->w[4];
+    double* pa = ctx->w[5];       // partial sums (nb <= n entries each)
+    double* pb = ctx->w[6];
+    double* pc = ctx->w[7];
+    double* sc = ctx->red;
+    FCT_CUDA(cudaMemsetAsync(sc, 0, 16 * sizeof(double), ctx->stream));
+    k_krylov_init<<<nb, FCT_RB, smem11(ctx), ctx->stream>>>(ctx->rowptr, ctx->colidx, mat, b, x, r, z, dinv, pa, pb, pc,
+                                                            ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+    ctx->launches++;
+    if (reduce_to(ctx, pa, S_RZ, pb, S_RR, pc, S_BB, 2, rtol)) return 1;
+    double h[16];
+    int it = 0;
+    const int batch = 8;
+    if (kind == 1) {
+        while (it < maxit) {
+            for (int j = 0; j < batch && it < maxit; ++j, ++it) {
+                // p (w[2]) is read at the neighbours while p_new is written: ping-pong between w[2] and w[8]
+                double* pold = (it & 1) ? ctx->w[8] : p;
+                double* pnew = (it & 1) ? p : ctx->w[8];
+                k_pcg_spmv<<<nb, FCT_RB, smem11(ctx), ctx->stream>>>(ctx->rowptr, ctx->colidx, mat, z, pold, pnew, q, sc,
+                                                                     it == 0, pa, ctx->row_begin, ctx->row_end, ctx->nnz,
+                                                                     ctx->cap);
+                ctx->launches++;
+                if (it > 0) { k_pcg_rotate<<<1, 1, 0, ctx->stream>>>(sc); ctx->launches++; }
+                if (reduce_to(ctx, pa, S_PAP, nullptr, 0, nullptr, 0, 0, rtol)) return 1;
+                k_pcg_update<<<nb, FCT_RB, 0, ctx->stream>>>(dinv, pnew, q, x, r, z, sc, pb, pc, ctx->row_begin, ctx->row_end);
+                ctx->launches++;
+                if (reduce_to(ctx, pb, S_RZN, pc, S_RR, nullptr, 0, 1, rtol)) return 1;
+            }
+            FCT_CUDA(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (h[S_DONE] != 0.0) break;
+        }
+    } else {
+        // Jacobi-preconditioned BiCGStab; r0* = r0.   Buffers: v = q, s = w[8], t = w[9], phat = w[10], shat = w[11]
+        double* v = q;
+        double* s = ctx->w[8];
+        double* t = ctx->w[9];
+        double* phat = ctx->w[10];
+        double* shat = ctx->w[11];
+        double* r0 = z;   // z is free in BiCGStab: keep the shadow residual there
+        FCT_CUDA(cudaMemcpyAsync(r0, r, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+        while (it < maxit) {
+            for (int j = 0; j < batch && it < maxit; ++j, ++it) {
+                // rhon = r0 . r
+                k_dot2<<<nb, FCT_RB, 0, ctx->stream>>>(r0, r, nullptr, nullptr, pa, nullptr, sc, ctx->row_begin, ctx->row_end);
+                ctx->launches++;
+                if (reduce_to(ctx, pa, S_RHON, nullptr, 0, nullptr, 0, 0, rtol)) return 1;
+                k_bicg_vec<<<nb, FCT_RB, 0, ctx->stream>>>(0, it == 0, dinv, x, r, p, v, s, t, phat, shat, sc, ctx->row_begin, ctx->row_end);
+                ctx->launches++;
+                if (fct_spmv(ctx, mat, phat, 1.0, 0.0, nullptr, v)) return 1;      // v = A phat
+                k_dot2<<<nb, FCT_RB, 0, ctx->stream>>>(r0, v, nullptr, nullptr, pa, nullptr, sc, ctx->row_begin, ctx->row_end);
+                ctx->launches++;
+                if (reduce_to(ctx, pa, S_R0V, nullptr, 0, nullptr, 0, 0, rtol)) return 1;
+                k_bicg_vec<<<nb, FCT_RB, 0, ctx->stream>>>(1, 0, dinv, x, r, p, v, s, t, phat, shat, sc, ctx->row_begin, ctx->row_end);
+                ctx->launches++;
+                if (fct_spmv(ctx, mat, shat, 1.0, 0.0, nullptr, t)) return 1;      // t = A shat
+                k_dot2<<<nb, FCT_RB, 0, ctx->stream>>>(t, s, t, t, pa, pb, sc, ctx->row_begin, ctx->row_end);
+                ctx->launches++;
+                if (reduce_to(ctx, pa, S_TS, pb, S_TT, nullptr, 0, 0, rtol)) return 1;
+                k_bicg_vec<<<nb, FCT_RB, 0, ctx->stream>>>(2, 0, dinv, x, r, p, v, s, t, phat, shat, sc, ctx->row_begin, ctx->row_end);
+                ctx->launches++;
+                k_dot2<<<nb, FCT_RB, 0, ctx->stream>>>(r, r, nullptr, nullptr, pa, nullptr, sc, ctx->row_begin, ctx->row_end);
+                ctx->launches++;
+                if (reduce_to(ctx, pa, S_RR, nullptr, 0, nullptr, 0, 0, rtol)) return 1;
+                k_bicg_scalars<<<1, 1, 0, ctx->stream>>>(sc, rtol);
+                ctx->launches++;
+            }
+            FCT_CUDA(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (h[S_DONE] != 0.0) break;
+        }
+    }
+    if (fct_launch_error(ctx, "fct_solve")) return 1;
+    FCT_CUDA(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double rel = h[S_BB] > 0 ? sqrt(h[S_RR] / h[S_BB]) : 0.0;
+    if (its_host) *its_host = (int32_t)h[S_ITS];
+    if (res_host) *res_host = rel;
+    FCT_CHECK(h[S_DONE] != 0.0, "fct_solve(kind=%d): not converged after %d iterations (rel. residual %g)", kind,
+              (int)h[S_ITS], rel);
+    return 0;
+}

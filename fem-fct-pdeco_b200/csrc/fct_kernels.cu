@@ -1,0 +1,692 @@
+// CSR passes of the FCT step (fp64, HBM-bound): SpMV, Chebyshev iteration, low-order operator build,
+// Jacobi sweeps, Zalesak limiter.  See fct_common.cuh for the row-block staging skeleton.
+//
+// Reference arithmetic replaced here (KarolinaBenkova/FEM-FCT-PDECO):
+//   helpers.py:143-185  ChebSI                  -> k_cheb_first / k_cheb_iter
+//   helpers.py:206-242  artificial_diffusion_mat -> k_low_build (fused with the next item) / k_art_diff
+//   helpers.py:1775-1782 Mat_u_Low, rhs_u_Low, spsolve -> k_low_build + k_jacobi_sweep (+ k_jacobi_decide)
+//   helpers.py:1814     rhs_du_dt = -A u_Low + rhs -> k_spmv
+//   helpers.py:1818-1851 fluxes, P+-, Q+-, R+-   -> k_flux_limits
+//   helpers.py:1860-1870 limited sum + update    -> k_flux_apply
+#include "fct_common.cuh"
+#include "../../include/fctpdeco.h"
+
+// dynamic shared memory layout helpers ---------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char fct_smem[];
+
+// y = alpha * A x + beta * z
+__global__ void __launch_bounds__(FCT_RB)
+k_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ A,
+       const double* __restrict__ x, double alpha, double beta, const double* __restrict__ z,
+       double* __restrict__ y, int row_begin, int row_end, int64_t nnz, int cap) {
+    double* sA = reinterpret_cast<double*>(fct_smem);
+    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sA, A, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    __syncthreads();
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        double acc = 0.0;
+        for (int k = ks; k < ke; ++k) acc += sA[k] * x[sC[k]];
+        double out = alpha * acc;
+        if (beta != 0.0) out += beta * z[r];
+        y[r] = out;
+    }
+}
+
+// ChebSI iteration k == 1: ymid = yold = 0  =>  y1 = omega1 * (b / Md')  with omega1 = 1
+__global__ void __launch_bounds__(FCT_RB)
+k_cheb_first(const double* __restrict__ g, const double* __restrict__ Md, double dscale, double omega,
+             double* __restrict__ ynew, int row_begin, int row_end) {
+    const int r = row_begin + blockIdx.x * FCT_RB + threadIdx.x;
+    if (r < row_end) {
+        const double z = g[r] / (dscale * Md[r]);
+        ynew[r] = omega * z;
+    }
+}
+
+// ChebSI iteration k >= 2 (helpers.py:176-184):
+//   r = b - M ymid; z = r / Md'; ynew = omega (z + ymid - yold) + yold
+__global__ void __launch_bounds__(FCT_RB)
+k_cheb_iter(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Mv,
+            const double* __restrict__ Md, const double* __restrict__ g, const double* __restrict__ ymid,
+            const double* __restrict__ yold, double* __restrict__ ynew, double omega, double dscale,
+            int has_old, int row_begin, int row_end, int64_t nnz, int cap) {
+    double* sA = reinterpret_cast<double*>(fct_smem);
+    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sA, Mv, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    __syncthreads();
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        double acc = 0.0;
+        for (int k = ks; k < ke; ++k) acc += sA[k] * ymid[sC[k]];
+        const double z = (g[r] - acc) / (dscale * Md[r]);
+        const double ym = ymid[r];
+        const double yo = has_old ? yold[r] : 0.0;
+        ynew[r] = omega * (z + ym - yo) + yo;
+    }
+}
+
+// sortable-key transform for atomicMin on signed doubles
+__device__ __forceinline__ unsigned long long f64_sort_key(double v) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+// Build the low-order operator and right-hand side in one pass:
+//   d_ij = max(0, a_ij, a_ji) (i != j)        [artificial_diffusion_mat(-A), helpers.py:1769]
+//   L    = M_L + dt (A - D) (+ dt S)            [helpers.py:1775-1778]
+//   b    = M_L u_n + dt rhs                     [helpers.py:1780]
+// `sign` folds the legacy FCT_alg convention (A -> -A, old_helpers.py:135-145) into the same kernel.
+// Outputs: Lv (full pattern), Dv (off-diagonals; diagonal slot holds d_ii), b; min row sum of L.
+__global__ void __launch_bounds__(FCT_RB)
+k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ tpos,
+            const double* __restrict__ A, double sign, const double* __restrict__ S, const double* __restrict__ ML,
+            const double* __restrict__ un, const double* __restrict__ rhs, double dt,
+            double* __restrict__ Lv, double* __restrict__ Dv, double* __restrict__ bvec,
+            unsigned long long* __restrict__ min_rowsum_key, int row_begin, int row_end, int64_t nnz, int cap) {
+    double* sA = reinterpret_cast<double*>(fct_smem);      // A, then L
+    double* sD = sA + cap;                                  // D
+    double* sS = sD + cap;                                  // S (if any)
+    int32_t* sC = reinterpret_cast<int32_t*>(sS + (S ? cap : 0));
+    int32_t* sT = sC + cap;
+    __shared__ double sred[FCT_RB / 32];
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sA, A, b, nnz);
+    if (S) stage_f64(sS, S, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    stage_s32(sT, tpos, b, nnz);
+    __syncthreads();
+    double rowsum = 1e300;
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        double dsum = 0.0, lsum = 0.0;
+        int kd = -1;
+        for (int k = ks; k < ke; ++k) {
+            const int c = sC[k];
+            if (c == r) { kd = k; continue; }
+            const double a = sign * sA[k];
+            const double at = sign * A[tpos ? sT[k] : 0];
+            const double d = fmax(0.0, fmax(a, at));
+            dsum += d;
+            double l = dt * (a - d);
+            if (S) l += dt * sS[k];
+            lsum += l;
+            sA[k] = l;
+            sD[k] = d;
+        }
+        // diagonal: d_ii = -sum_j d_ij
+        {
+            const double a = sign * sA[kd];
+            const double dii = -dsum;
+            double l = ML[r] + dt * (a - dii);
+            if (S) l += dt * sS[kd];
+            lsum += l;
+            sA[kd] = l;
+            sD[kd] = dii;
+        }
+        rowsum = lsum;
+        bvec[r] = ML[r] * un[r] + (rhs ? dt * rhs[r] : 0.0);
+    }
+    __syncthreads();
+    unstage_f64(Lv, sA, b);
+    unstage_f64(Dv, sD, b);
+    const double m = block_min(rowsum, sred);
+    if (threadIdx.x == 0) atomicMin(min_rowsum_key, f64_sort_key(m));
+}
+
+// artificial_diffusion_mat as a stand-alone operation (helpers.py:206-242): D from `mat`
+__global__ void __launch_bounds__(FCT_RB)
+k_art_diff(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ tpos,
+           const double* __restrict__ mat, double* __restrict__ Dv, int row_begin, int row_end, int64_t nnz, int cap) {
+    double* sA = reinterpret_cast<double*>(fct_smem);
+    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
+    int32_t* sT = sC + cap;
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sA, mat, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    stage_s32(sT, tpos, b, nnz);
+    __syncthreads();
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        double dsum = 0.0;
+        int kd = -1;
+        for (int k = ks; k < ke; ++k) {
+            if (sC[k] == r) { kd = k; continue; }
+            const double d = fmax(0.0, fmax(-sA[k], -mat[sT[k]]));
+            dsum += d;
+            sA[k] = d;
+        }
+        sA[kd] = -dsum;
+    }
+    __syncthreads();
+    unstage_f64(Dv, sA, b);
+}
+
+// One Jacobi sweep x_new = (b - sum_{j != i} l_ij x_j) / l_ii.  Skipped once jstate[3] (converged) is set.
+// When `check` is set the sweep also accumulates ||x_new - x||_inf and ||x_new||_inf into jstate[0..1].
+__global__ void __launch_bounds__(FCT_RB)
+k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Lv,
+               const double* __restrict__ bvec, const double* __restrict__ x, double* __restrict__ xnew,
+               unsigned long long* __restrict__ jstate, int check, int row_begin, int row_end, int64_t nnz, int cap) {
+    if (*reinterpret_cast<volatile unsigned long long*>(jstate + 3)) return;
+    double* sA = reinterpret_cast<double*>(fct_smem);
+    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
+    __shared__ double sred[FCT_RB / 32];
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sA, Lv, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    __syncthreads();
+    double delta = 0.0, xa = 0.0;
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        double acc = 0.0, diag = 1.0;
+        for (int k = ks; k < ke; ++k) {
+            const int c = sC[k];
+            const double v = sA[k];
+            if (c == r) diag = v;
+            else acc += v * x[c];
+        }
+        const double xn = (bvec[r] - acc) / diag;
+        xnew[r] = xn;
+        if (check) {
+            delta = fabs(xn - x[r]);
+            xa = fabs(xn);
+        }
+    }
+    if (check) {
+        const double dm = block_max(delta, sred);
+        const double xm = block_max(xa, sred);
+        if (threadIdx.x == 0) {
+            atomicMax(jstate + 0, (unsigned long long)__double_as_longlong(dm));
+            atomicMax(jstate + 1, (unsigned long long)__double_as_longlong(xm));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(jstate + 4, 1ull);
+}
+
+// After a checked sweep (and, multi-GPU, after the max-allreduce of jstate[0..1]): decide convergence.
+__global__ void k_jacobi_decide(unsigned long long* __restrict__ jstate, double rtol) {
+    if (jstate[3]) return;
+    const double delta = __longlong_as_double((long long)jstate[0]);
+    const double xm = __longlong_as_double((long long)jstate[1]);
+    jstate[5] = jstate[0];
+    jstate[6] = jstate[1];
+    if (delta <= rtol * xm) jstate[3] = 1ull;
+    jstate[0] = 0ull;
+    jstate[1] = 0ull;
+}
+
+__global__ void k_jacobi_reset(unsigned long long* __restrict__ jstate) {
+    jstate[0] = 0ull; jstate[1] = 0ull; jstate[2] = 0ull; jstate[3] = 0ull; jstate[4] = 0ull;
+    jstate[5] = 0ull; jstate[6] = 0ull;
+    jstate[7] = 0xFFFFFFFFFFFFFFFFull;   // min row-sum key
+}
+
+// Zalesak limiter, pass 1 (helpers.py:1818-1851): raw fluxes f_ij = m_ij (ud_i - ud_j) + d_ij (ul_i - ul_j),
+// P+- = sums of positive/negative fluxes, Q+- = distance to the local extrema of u_low, R+- nodal factors.
+__global__ void __launch_bounds__(FCT_RB)
+k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Mv,
+              const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
+              const double* __restrict__ ulow, double dt, double* __restrict__ Rpos, double* __restrict__ Rneg,
+              int row_begin, int row_end, int64_t nnz, int cap) {
+    double* sM = reinterpret_cast<double*>(fct_smem);
+    double* sD = sM + cap;
+    int32_t* sC = reinterpret_cast<int32_t*>(sD + cap);
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sM, Mv, b, nnz);
+    stage_f64(sD, Dv, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    __syncthreads();
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        const double udi = udot[r], uli = ulow[r];
+        double pp = 0.0, pn = 0.0, umax = uli, umin = uli;
+        for (int k = ks; k < ke; ++k) {
+            const int c = sC[k];
+            if (c == r) continue;
+            const double ulj = ulow[c];
+            const double f = sM[k] * (udi - udot[c]) + sD[k] * (uli - ulj);
+            pp += fmax(f, 0.0);
+            pn += fmin(f, 0.0);
+            umax = fmax(umax, ulj);
+            umin = fmin(umin, ulj);
+        }
+        const double qp = umax - uli, qn = umin - uli;
+        const double ml = ML[r];
+        Rpos[r] = (pp != 0.0) ? fmin(1.0, ml * qp / (dt * pp)) : 1.0;
+        Rneg[r] = (pn != 0.0) ? fmin(1.0, ml * qn / (dt * pn)) : 1.0;
+    }
+}
+
+// Zalesak limiter, pass 2 (helpers.py:1860-1870): alpha_ij, limited sum, explicit correction.
+__global__ void __launch_bounds__(FCT_RB)
+k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Mv,
+             const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
+             const double* __restrict__ ulow, const double* __restrict__ Rpos, const double* __restrict__ Rneg,
+             double dt, double* __restrict__ uout, int row_begin, int row_end, int64_t nnz, int cap) {
+    double* sM = reinterpret_cast<double*>(fct_smem);
+    double* sD = sM + cap;
+    int32_t* sC = reinterpret_cast<int32_t*>(sD + cap);
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sM, Mv, b, nnz);
+    stage_f64(sD, Dv, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    __syncthreads();
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        const double udi = udot[r], uli = ulow[r];
+        const double rpi = Rpos[r], rni = Rneg[r];
+        double fbar = 0.0;
+        for (int k = ks; k < ke; ++k) {
+            const int c = sC[k];
+            if (c == r) continue;
+            const double f = sM[k] * (udi - udot[c]) + sD[k] * (uli - ulow[c]);
+            const double alpha = (f > 0.0) ? fmin(rpi, Rneg[c]) : fmin(rni, Rpos[c]);
+            fbar += alpha * f;
+        }
+        uout[r] = uli + dt * fbar / ML[r];
+    }
+}
+
+// out_i = sum_j mat_ij  (row_lump, helpers.py:309-328); optionally also the diagonal
+__global__ void __launch_bounds__(FCT_RB)
+k_row_lump(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ A,
+           double* __restrict__ out, double* __restrict__ diag_out, int row_begin, int row_end, int64_t nnz, int cap) {
+    double* sA = reinterpret_cast<double*>(fct_smem);
+    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sA, A, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    __syncthreads();
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        double acc = 0.0, dg = 0.0;
+        for (int k = ks; k < ke; ++k) {
+            acc += sA[k];
+            if (sC[k] == r) dg = sA[k];
+        }
+        if (out) out[r] = acc;
+        if (diag_out) diag_out[r] = dg;
+    }
+}
+
+// partial[blockIdx] = sum over the block's rows of w * x_i (M y)_i   (deterministic two-stage reduction)
+__global__ void __launch_bounds__(FCT_RB)
+k_dot_M(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Mv,
+        const double* __restrict__ x, const double* __restrict__ xt, const double* __restrict__ y,
+        const double* __restrict__ yt, double* __restrict__ partial, int row_begin, int row_end, int64_t nnz, int cap) {
+    double* sA = reinterpret_cast<double*>(fct_smem);
+    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
+    __shared__ double sred[FCT_RB / 32];
+    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    stage_f64(sA, Mv, b, nnz);
+    stage_s32(sC, colidx, b, nnz);
+    __syncthreads();
+    double v = 0.0;
+    if ((int)threadIdx.x < b.nr) {
+        const int r = b.r0 + threadIdx.x;
+        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+        double acc = 0.0;
+        for (int k = ks; k < ke; ++k) {
+            const int c = sC[k];
+            const double yc = yt ? (y[c] - yt[c]) : y[c];
+            acc += sA[k] * yc;
+        }
+        const double xr = xt ? (x[r] - xt[r]) : x[r];
+        v = xr * acc;
+    }
+    const double s = block_sum(v, sred);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// out[slot] (+)= scale * sum(partial[0..m))  -- single block, fixed order => deterministic
+__global__ void __launch_bounds__(FCT_RB)
+k_reduce_partials(const double* __restrict__ partial, int m, double scale, double* __restrict__ out, int accumulate) {
+    __shared__ double sred[FCT_RB / 32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < m; i += FCT_RB) v += partial[i];
+    const double s = block_sum(v, sred);
+    if (threadIdx.x == 0) *out = (accumulate ? *out : 0.0) + scale * s;
+}
+
+__global__ void k_axpby(int64_t len, double a, const double* __restrict__ x, double b, const double* __restrict__ y,
+                        double* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride)
+        out[i] = a * x[i] + (y ? b * y[i] : 0.0);
+}
+
+__global__ void k_clip_axpy(int64_t len, const double* __restrict__ x, double s, const double* __restrict__ d,
+                            double lo, double hi, double* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride)
+        out[i] = fmin(fmax(x[i] + s * d[i], lo), hi);
+}
+
+// tpos[k] = position of (j,i) for entry k = (i,j): binary search in row j
+__global__ void k_build_tpos(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n,
+                             int32_t* __restrict__ tpos, int* __restrict__ err) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    bool has_diag = false;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+        const int c = colidx[k];
+        if (c == r) has_diag = true;
+        int lo = rowptr[c], hi = rowptr[c + 1] - 1, pos = -1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const int cc = colidx[mid];
+            if (cc == r) { pos = mid; break; }
+            if (cc < r) lo = mid + 1; else hi = mid - 1;
+        }
+        if (pos < 0) { atomicExch(err, 1); pos = k; }
+        tpos[k] = pos;
+    }
+    if (!has_diag) atomicExch(err, 2);
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+static inline size_t smem_bytes(const fct_ctx* c, int nf64, int ns32) {
+    return (size_t)c->cap * (8 * (size_t)nf64 + 4 * (size_t)ns32);
+}
+
+#define LAUNCH_ROWS(ctx, kern, nf64, ns32, ...)                                                          \
+    do {                                                                                                 \
+        const int nb__ = fct_nblocks(ctx);                                                               \
+        if (nb__ > 0) {                                                                                  \
+            kern<<<nb__, FCT_RB, smem_bytes(ctx, nf64, ns32), (ctx)->stream>>>(__VA_ARGS__);             \
+            (ctx)->launches++;                                                                           \
+        }                                                                                                \
+    } while (0)
+
+int fct_launch_error(fct_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        fct_set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+int fct_kernels_configure(fct_ctx* ctx) {
+    // opt in to the dynamic shared memory the widest kernel needs (3 fp64 + 2 int32 staged arrays)
+    const size_t worst = smem_bytes(ctx, 3, 2);
+    FCT_CHECK(worst <= 200 * 1024, "row blocks need %zu B of shared memory (max row %d): unsupported pattern",
+              worst, ctx->max_row);
+    const int w = FCT_SMEM_OPTIN;   // opt-in ceiling only (never lowered by a later, smaller context)
+    FCT_CUDA(cudaFuncSetAttribute(k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_cheb_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_low_build, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_art_diff, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_flux_limits, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_flux_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_row_lump, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_dot_M, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    return 0;
+}
+
+int fct_build_tpos(fct_ctx* ctx) {
+    int* derr = reinterpret_cast<int*>(ctx->jstate);   // scratch word, reset afterwards
+    FCT_CUDA(cudaMemsetAsync(derr, 0, sizeof(int), ctx->stream));
+    k_build_tpos<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->n, ctx->tpos, derr);
+    ctx->launches++;
+    int herr = 0;
+    FCT_CUDA(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+    FCT_CUDA(cudaMemsetAsync(derr, 0, sizeof(int), ctx->stream));
+    // halo rows of a partitioned pattern are truncated, so asymmetry there is expected: only a missing
+    // diagonal is fatal for them; for a full (single-GPU) pattern both are errors.
+    if (herr == 2) { fct_set_error("pattern is missing a diagonal entry"); return 2; }
+    if (herr == 1 && ctx->row_begin == 0 && ctx->row_end == ctx->n) {
+        fct_set_error("pattern is not structurally symmetric");
+        return 2;
+    }
+    return 0;
+}
+
+extern "C" int fct_spmv(fct_ctx* ctx, const double* A, const double* x, double alpha, double beta, const double* z,
+                        double* y) {
+    FCT_CHECK(ctx && A && x && y, "fct_spmv: null argument");
+    FCT_CHECK(beta == 0.0 || z, "fct_spmv: beta != 0 needs z");
+    LAUNCH_ROWS(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, x, alpha, beta, z, y, ctx->row_begin, ctx->row_end,
+                ctx->nnz, ctx->cap);
+    return fct_launch_error(ctx, "fct_spmv");
+}
+
+int fct_halo_exchange_if(fct_ctx* ctx, double* vec);   // no-op without a communicator (fct_comm.cu)
+int fct_halo_allreduce_max2(fct_ctx* ctx, unsigned long long* two_words);
+
+extern "C" int fct_chebsi(fct_ctx* ctx, const double* M, const double* Md, const double* b, double* y, int32_t iters,
+                          double lmin, double lmax) {
+    FCT_CHECK(ctx && M && Md && b && y, "fct_chebsi: null argument");
+    FCT_CHECK(iters >= 1, "fct_chebsi: iters must be >= 1");
+    // helpers.py:164-180
+    const double rho = (lmax - lmin) / (lmax + lmin);
+    const double dscale = (lmin + lmax) / 2;
+    double omega = 0.0;
+    // rotating buffers: the result of iteration k lands in buf[k % 3]; the last one is redirected to y
+    double* buf[3] = {ctx->w[0], ctx->w[1], ctx->w[2]};
+    const double* ymid = nullptr;
+    const double* yold = nullptr;
+    const int nb = fct_nblocks(ctx);
+    for (int k = 1; k <= iters; ++k) {
+        if (k == 2) omega = 1 / (1 - rho * rho / 2);
+        else omega = 1 / (1 - (omega * rho * rho) / 4);
+        double* ynew = (k == iters) ? y : buf[k % 3];
+        if (k == 1) {
+            if (nb > 0) {
+                k_cheb_first<<<nb, FCT_RB, 0, ctx->stream>>>(b, Md, dscale, omega, ynew, ctx->row_begin, ctx->row_end);
+                ctx->launches++;
+            }
+        } else {
+            LAUNCH_ROWS(ctx, k_cheb_iter, 1, 1, ctx->rowptr, ctx->colidx, M, Md, b, ymid, yold, ynew, omega, dscale,
+                        yold != nullptr, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+        }
+        if (k < iters) {
+            if (fct_halo_exchange_if(ctx, ynew)) return 1;
+        }
+        yold = ymid;
+        ymid = ynew;
+    }
+    return fct_launch_error(ctx, "fct_chebsi");
+}
+
+extern "C" int fct_artificial_diffusion(fct_ctx* ctx, const double* mat, double* D) {
+    FCT_CHECK(ctx && mat && D, "fct_artificial_diffusion: null argument");
+    LAUNCH_ROWS(ctx, k_art_diff, 1, 2, ctx->rowptr, ctx->colidx, ctx->tpos, mat, D, ctx->row_begin, ctx->row_end,
+                ctx->nnz, ctx->cap);
+    return fct_launch_error(ctx, "fct_artificial_diffusion");
+}
+
+extern "C" int fct_row_lump(fct_ctx* ctx, const double* mat, double* out) {
+    FCT_CHECK(ctx && mat && out, "fct_row_lump: null argument");
+    LAUNCH_ROWS(ctx, k_row_lump, 1, 1, ctx->rowptr, ctx->colidx, mat, out, (double*)nullptr, ctx->row_begin,
+                ctx->row_end, ctx->nnz, ctx->cap);
+    return fct_launch_error(ctx, "fct_row_lump");
+}
+
+int fct_row_lump_diag(fct_ctx* ctx, const double* mat, double* out, double* diag) {
+    LAUNCH_ROWS(ctx, k_row_lump, 1, 1, ctx->rowptr, ctx->colidx, mat, out, diag, ctx->row_begin, ctx->row_end,
+                ctx->nnz, ctx->cap);
+    return fct_launch_error(ctx, "fct_row_lump_diag");
+}
+
+// Jacobi solve of Lv x = b, x holds the initial guess on entry and the result on exit (device-side early exit;
+// sweeps run in pairs so that the result always lands back in x).
+int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, double* x, double* tmp, double rtol,
+                     int max_sweeps) {
+    const int pairs = (max_sweeps + 1) / 2;
+    for (int p = 0; p < pairs; ++p) {
+        LAUNCH_ROWS(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0, ctx->row_begin,
+                    ctx->row_end, ctx->nnz, ctx->cap);
+        if (fct_halo_exchange_if(ctx, tmp)) return 1;
+        LAUNCH_ROWS(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, tmp, x, ctx->jstate, 1, ctx->row_begin,
+                    ctx->row_end, ctx->nnz, ctx->cap);
+        if (fct_halo_exchange_if(ctx, x)) return 1;
+        if (fct_halo_allreduce_max2(ctx, ctx->jstate)) return 1;
+        k_jacobi_decide<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol);
+        ctx->launches++;
+    }
+    return fct_launch_error(ctx, "fct_jacobi_solve");
+}
+
+int fct_read_step_info(fct_ctx* ctx, fct_step_info* info) {
+    unsigned long long h[8];
+    FCT_CUDA(cudaMemcpyAsync(h, ctx->jstate, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+    info->solver_sweeps = (int32_t)h[4];
+    info->converged = (int32_t)h[3];
+    memcpy(&info->last_delta, &h[5], 8);
+    memcpy(&info->x_norm, &h[6], 8);
+    unsigned long long key = h[7];
+    unsigned long long bits = (key >> 63) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+    memcpy(&info->min_rowsum_low, &bits, 8);
+    return 0;
+}
+
+extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double* S, const double* rhs,
+                        const double* un, double dt, double* uout, fct_step_info* info) {
+    FCT_CHECK(ctx && A && un && uout, "fct_step: null argument");
+    FCT_CHECK(ctx->mass_set, "fct_step: static mass matrices not set (fct_ctx_set_mass / fct_assemble_static)");
+    FCT_CHECK(sign == 1.0 || sign == -1.0, "fct_step: sign must be +1 (FCT_alg_ref) or -1 (FCT_alg)");
+    double* bvec = ctx->w[3];
+    double* ulow = ctx->w[4];
+    double* tmp = ctx->w[5];
+    double* g = ctx->w[6];
+    double* udot = ctx->w[7];
+    double* Rp = ctx->w[8];
+    double* Rn = ctx->w[9];
+    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+    ctx->launches++;
+    // 1-2. D, L, b
+    if (S) {
+        LAUNCH_ROWS(ctx, k_low_build, 3, 2, ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un, rhs, dt,
+                    ctx->Lvals, ctx->Dvals, bvec, ctx->jstate + 7, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+    } else {
+        LAUNCH_ROWS(ctx, k_low_build, 2, 2, ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un, rhs, dt,
+                    ctx->Lvals, ctx->Dvals, bvec, ctx->jstate + 7, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+    }
+    // low-order solve, initial guess u_n
+    FCT_CUDA(cudaMemcpyAsync(ulow, un, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (fct_jacobi_solve(ctx, ctx->Lvals, bvec, ulow, tmp, ctx->rtol, ctx->max_sweeps)) return 1;
+    // 4. g = -(sign A) u_low + rhs ; udot = ChebSI(g)
+    LAUNCH_ROWS(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, ulow, -sign, rhs ? 1.0 : 0.0, rhs, g, ctx->row_begin,
+                ctx->row_end, ctx->nnz, ctx->cap);
+    if (fct_chebsi(ctx, ctx->M, ctx->Mdiag, g, udot, 20, 0.5, 2.0)) return 1;
+    if (fct_halo_exchange_if(ctx, udot)) return 1;
+    // 5-7. fluxes, P, Q, R
+    LAUNCH_ROWS(ctx, k_flux_limits, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, dt, Rp, Rn,
+                ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+    if (fct_halo_exchange_if(ctx, Rp)) return 1;
+    if (fct_halo_exchange_if(ctx, Rn)) return 1;
+    // 8-9. limited sum + update
+    LAUNCH_ROWS(ctx, k_flux_apply, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, Rp, Rn, dt,
+                uout, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+    if (fct_launch_error(ctx, "fct_step")) return 1;
+    if (fct_halo_exchange_if(ctx, uout)) return 1;
+    if (info) return fct_read_step_info(ctx, info);
+    return 0;
+}
+
+extern "C" int fct_step_host(fct_ctx* ctx, const double* A, double sign, const double* S, const double* rhs,
+                             const double* un, double dt, double* uout, fct_step_info* info) {
+    FCT_CHECK(ctx && A && un && uout, "fct_step_host: null argument");
+    FCT_CHECK(ctx->row_begin == 0 && ctx->row_end == ctx->n, "fct_step_host: single-GPU contexts only");
+    const size_t vb = sizeof(double) * (size_t)ctx->n, mb = sizeof(double) * (size_t)ctx->nnz;
+    double* d_un = ctx->w[0];     // w[0..2] are ChebSI buffers: free until fct_chebsi runs, and un is consumed before
+    double* d_rhs = ctx->w[1];
+    double* d_out = ctx->w[2];
+    // un / rhs are needed after ChebSI starts?  un: no (only k_low_build + initial guess).  rhs: yes (k_spmv runs
+    // before ChebSI).  Both are consumed before the first Chebyshev buffer is written.
+    FCT_CUDA(cudaMemcpyAsync(ctx->Avals, A, mb, cudaMemcpyHostToDevice, ctx->stream));
+    if (S) FCT_CUDA(cudaMemcpyAsync(ctx->Svals, S, mb, cudaMemcpyHostToDevice, ctx->stream));
+    FCT_CUDA(cudaMemcpyAsync(d_un, un, vb, cudaMemcpyHostToDevice, ctx->stream));
+    if (rhs) FCT_CUDA(cudaMemcpyAsync(d_rhs, rhs, vb, cudaMemcpyHostToDevice, ctx->stream));
+    // ChebSI's first iteration writes buf[1] = w[1] (rhs) only after g was formed; w[2] at k == 2; w[0] at k == 3.
+    // d_out = w[2] is written last by k_flux_apply, after ChebSI finished.
+    int rc = fct_step(ctx, ctx->Avals, sign, S ? ctx->Svals : nullptr, rhs ? d_rhs : nullptr, d_un, dt, d_out, nullptr);
+    if (rc) return rc;
+    FCT_CUDA(cudaMemcpyAsync(uout, d_out, vb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (info) return fct_read_step_info(ctx, info);
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int fct_dot_M(fct_ctx* ctx, const double* M, const double* x, const double* y, double* out_host) {
+    FCT_CHECK(ctx && M && x && y && out_host, "fct_dot_M: null argument");
+    double* partial = ctx->w[0];
+    const int nb = fct_nblocks(ctx);
+    LAUNCH_ROWS(ctx, k_dot_M, 1, 1, ctx->rowptr, ctx->colidx, M, x, (const double*)nullptr, y, (const double*)nullptr,
+                partial, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+    k_reduce_partials<<<1, FCT_RB, 0, ctx->stream>>>(partial, nb, 1.0, ctx->red, 0);
+    ctx->launches++;
+    if (fct_launch_error(ctx, "fct_dot_M")) return 1;
+    FCT_CUDA(cudaMemcpyAsync(out_host, ctx->red, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int fct_allreduce_sum_host(fct_ctx* ctx, double* v);   // fct_comm.cu
+
+extern "C" int fct_norm_sq_Q(fct_ctx* ctx, const double* M, const double* phi, const double* target,
+                             int32_t num_steps, double dt, double* out_host) {
+    FCT_CHECK(ctx && M && phi && out_host && num_steps >= 0, "fct_norm_sq_Q: bad argument");
+    double* partial = ctx->w[0];
+    const int nb = fct_nblocks(ctx);
+    // helpers.py:354-359: sum_k w_k phi_k^T M phi_k * dt, w_0 = w_N = 1/2
+    for (int k = 0; k <= num_steps; ++k) {
+        const double* p = phi + (size_t)k * ctx->n;
+        const double* t = target ? target + (size_t)k * ctx->n : nullptr;
+        const double wk = (k == 0 || k == num_steps) ? 0.5 : 1.0;
+        LAUNCH_ROWS(ctx, k_dot_M, 1, 1, ctx->rowptr, ctx->colidx, M, p, t, p, t, partial, ctx->row_begin, ctx->row_end,
+                    ctx->nnz, ctx->cap);
+        k_reduce_partials<<<1, FCT_RB, 0, ctx->stream>>>(partial, nb, wk, ctx->red, k > 0);
+        ctx->launches++;
+    }
+    if (fct_launch_error(ctx, "fct_norm_sq_Q")) return 1;
+    double v = 0.0;
+    FCT_CUDA(cudaMemcpyAsync(&v, ctx->red, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (fct_allreduce_sum_host(ctx, &v)) return 1;
+    *out_host = v * dt;
+    return 0;
+}
+
+extern "C" int fct_axpby(fct_ctx* ctx, int64_t len, double a, const double* x, double b, const double* y, double* out) {
+    FCT_CHECK(ctx && x && out && len >= 0, "fct_axpby: bad argument");
+    if (len == 0) return 0;
+    const int grid = (int)((len + 255) / 256 < 148 * 16 ? (len + 255) / 256 : 148 * 16);
+    k_axpby<<<grid, 256, 0, ctx->stream>>>(len, a, x, b, y, out);
+    ctx->launches++;
+    return fct_launch_error(ctx, "fct_axpby");
+}
+
+extern "C" int fct_vals_axpby(fct_ctx* ctx, double a, const double* X, double b, const double* Y, double* out) {
+    FCT_CHECK(ctx, "fct_vals_axpby: null context");
+    return fct_axpby(ctx, ctx->nnz, a, X, b, Y, out);
+}
+
+extern "C" int fct_clip_axpy(fct_ctx* ctx, int64_t len, const double* x, double s, const double* d, double lo,
+                             double hi, double* out) {
+    FCT_CHECK(ctx && x && d && out && len >= 0, "fct_clip_axpy: bad argument");
+    if (len == 0) return 0;
+    const int grid = (int)((len + 255) / 256 < 148 * 16 ? (len + 255) / 256 : 148 * 16);
+    k_clip_axpy<<<grid, 256, 0, ctx->stream>>>(len, x, s, d, lo, hi, out);
+    ctx->launches++;
+    return fct_launch_error(ctx, "fct_clip_axpy");
+}

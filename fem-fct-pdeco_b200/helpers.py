@@ -1,0 +1,266 @@
+"""Drop-in namespace for the reference's ``helpers.py`` hot-path entry points (same names, argument order
+and error behaviour), computing on the B200 through libfctpdeco.
+
+Reference interface replaced (KarolinaBenkova/FEM-FCT-PDECO):
+    FCT_alg_ref            helpers.py:1715-1872       FCT_alg (legacy)         old_helpers.py:115-204
+    ChebSI                 helpers.py:143-185         artificial_diffusion_mat helpers.py:206-242
+    row_lump               helpers.py:309-328         sparse_nonzero           helpers.py:187-204
+    L2_norm_sq_Q / _Omega  helpers.py:330-381         cost_functional          helpers.py:383-441
+    reorder_vector_to_dof / _from_dof (+ legacy *_time aliases)   helpers.py:13-67
+    rel_err, generate_boundary_nodes, find_node_neighbours        helpers.py:69-85, 244-307
+
+Inputs are the caller's numpy vectors and scipy sparse matrices; outputs are fresh numpy arrays / scipy
+matrices, as in the reference.  Matrices are re-embedded into the full P1 pattern taken from ``M`` (scipy
+arithmetic prunes explicit zeros).  The GPU context for a pattern is created on first
+use and cached.  Nothing here falls back to a CPU implementation of the arithmetic.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from .context import FctContext
+
+# --------------------------------------------------------------------------------------------------
+# context cache: one GPU context per distinct CSR pattern
+# --------------------------------------------------------------------------------------------------
+_CONTEXTS = {}
+_DEVICE = 0
+
+
+def set_device(device):
+    global _DEVICE
+    _DEVICE = int(device)
+
+
+def _full_pattern(mat):
+    """CSR pattern (sorted, with diagonal, structurally symmetric) covering `mat`"""
+    csr = sp.csr_matrix(mat)
+    n = csr.shape[0]
+    P = sp.csr_matrix((np.ones(csr.nnz, dtype=np.int8), csr.indices, csr.indptr), shape=csr.shape)
+    P = (P + P.T + sp.identity(n, dtype=np.int8, format="csr")).tocsr()
+    P.sort_indices()
+    return P.indptr.astype(np.int32), P.indices.astype(np.int32)
+
+
+def context_for(M):
+    """GPU context whose pattern is that of the (mass) matrix M; M's values become the context's mass matrix."""
+    csr = M.tocsr() if sp.issparse(M) else sp.csr_matrix(M)
+    if not csr.has_sorted_indices:
+        csr = csr.sorted_indices()
+    key = (csr.shape[0], csr.nnz, hash(csr.indptr.tobytes()), hash(csr.indices.tobytes()), _DEVICE)
+    ent = _CONTEXTS.get(key)
+    if ent is None:
+        rowptr, colidx = csr.indptr.astype(np.int32), csr.indices.astype(np.int32)
+        try:
+            ctx = FctContext(rowptr, colidx, device=_DEVICE)
+        except _lib.FctError:
+            rowptr, colidx = _full_pattern(csr)          # pruned / unsymmetric pattern: complete it
+            ctx = FctContext(rowptr, colidx, device=_DEVICE)
+        ent = {"ctx": ctx, "mass_hash": None}
+        _CONTEXTS[key] = ent
+    return ent
+
+
+def _ensure_mass(ent, M, M_lumped=None):
+    ctx = ent["ctx"]
+    Mv = ctx.embed(M)
+    ml = None
+    if M_lumped is not None:
+        ml = np.ascontiguousarray(M_lumped.diagonal() if sp.issparse(M_lumped) else np.asarray(M_lumped).ravel(),
+                                  dtype=np.float64)
+    h = (hash(Mv.tobytes()), None if ml is None else hash(ml.tobytes()))
+    if ent["mass_hash"] != h:
+        ctx.set_mass(Mv, ml)
+        ent["mass_hash"] = h
+    return ctx
+
+
+def clear_contexts():
+    for ent in _CONTEXTS.values():
+        ent["ctx"].close()
+    _CONTEXTS.clear()
+
+
+# --------------------------------------------------------------------------------------------------
+# host bookkeeping (same semantics as the reference, vectorised)
+# --------------------------------------------------------------------------------------------------
+def reorder_vector_to_dof(vec, num_steps, nodes, vertex_to_dof):
+    """helpers.py:13-39: vec_dof[n*nodes + vertex_to_dof[i]] = vec[n*nodes + i]."""
+    v = np.asarray(vec, dtype=np.float64).reshape(num_steps, nodes)
+    out = np.zeros_like(v)
+    out[:, np.asarray(vertex_to_dof, dtype=np.int64)] = v
+    return out.reshape(np.shape(vec))
+
+
+def reorder_vector_from_dof(vec_dof, num_steps, nodes, vertex_to_dof):
+    """helpers.py:41-67: vec[n*nodes + i] = vec_dof[n*nodes + vertex_to_dof[i]]."""
+    v = np.asarray(vec_dof, dtype=np.float64).reshape(num_steps, nodes)
+    return v[:, np.asarray(vertex_to_dof, dtype=np.int64)].reshape(np.shape(vec_dof))
+
+
+# legacy names used by the BASELINE scripts (advection_solidbody_FCT.py:121,153)
+reorder_vector_to_dof_time = reorder_vector_to_dof
+reorder_vector_from_dof_time = reorder_vector_from_dof
+
+
+def rel_err(new, old):
+    """helpers.py:69-85."""
+    return np.linalg.norm(new - old) / np.linalg.norm(old)
+
+
+def generate_boundary_nodes(nodes, vertex_to_dof):
+    """helpers.py:244-269."""
+    sqnodes = round(np.sqrt(nodes))
+    boundary_nodes = [n for n in range(nodes)
+                      if n % sqnodes in [0, sqnodes - 1] or n < sqnodes or n >= nodes - sqnodes]
+    boundary_nodes_dof = [int(vertex_to_dof[n]) for n in boundary_nodes]
+    return boundary_nodes, boundary_nodes_dof
+
+
+def find_node_neighbours(mesh, nodes, vertex_to_dof):
+    """helpers.py:271-307 for the dolfin-free mesh stand-in (fem-fct-pdeco_b200/mesh.py)."""
+    return mesh.dof_neighbors()
+
+
+def sparse_nonzero(H):
+    """helpers.py:187-204."""
+    Hx = sp.coo_matrix(H)
+    return np.transpose(np.array([Hx.row, Hx.col, Hx.data, Hx.data > 0]))
+
+
+# --------------------------------------------------------------------------------------------------
+# sparse kernels
+# --------------------------------------------------------------------------------------------------
+def row_lump(mat, nodes):
+    """helpers.py:309-328: diagonal lil_matrix of the row sums, computed on the GPU."""
+    ent = context_for(mat)
+    ctx = ent["ctx"]
+    d_mat = ctx.array(ctx.embed(mat))
+    d_out = ctx.empty(ctx.n)
+    ctx.row_lump(d_mat, d_out)
+    sums = d_out.download()
+    d_mat.free(); d_out.free()
+    lumped = sp.lil_matrix((nodes, nodes))
+    lumped.setdiag(sums)
+    return lumped
+
+
+def artificial_diffusion_mat(mat):
+    """helpers.py:206-242: D_ij = max(0, -m_ij, -m_ji), D_ii = -sum_j D_ij (lil_matrix)."""
+    ent = context_for(mat)
+    ctx = ent["ctx"]
+    d_mat = ctx.array(ctx.embed(mat))
+    d_out = ctx.empty(ctx.nnz)
+    ctx.artificial_diffusion(d_mat, d_out)
+    D = ctx.to_scipy(d_out.download())
+    d_mat.free(); d_out.free()
+    return sp.lil_matrix(D)
+
+
+def ChebSI(vec, M, Md, cheb_iter=20, lmin=0.5, lmax=2):
+    """helpers.py:143-185: exactly `cheb_iter` Chebyshev semi-iterations for M x = vec."""
+    ent = context_for(M)
+    ctx = ent["ctx"]
+    d_M = ctx.array(ctx.embed(M))
+    d_Md = ctx.array(np.asarray(Md, dtype=np.float64).ravel())
+    d_b = ctx.array(np.asarray(vec, dtype=np.float64).ravel())
+    d_y = ctx.empty(ctx.n)
+    ctx.chebsi(d_M, d_Md, d_b, d_y, cheb_iter, lmin, lmax)
+    out = d_y.download()
+    for a in (d_M, d_Md, d_b, d_y):
+        a.free()
+    return out
+
+
+def _print_dt_bounds(A_csr, M_lumped_diag):
+    """the diagnostic branch of helpers.py:1798-1809 (host, only when triggered)"""
+    print("3:", False)
+    row_sums_A = np.asarray(A_csr.sum(axis=1)).ravel()
+    upper = [-M_lumped_diag[i] / s for i, s in enumerate(row_sums_A) if s < 0]
+    lower = [-M_lumped_diag[i] / s for i, s in enumerate(row_sums_A) if s > 0]
+    if upper:
+        print("Upper bound on dt:", min(upper))
+    if lower:
+        print("Lower bound on dt:", max(max(lower), 0))
+
+
+def _fct(A, rhs, u_n, dt, nodes, M, M_lumped, dof_neighbors, extra, sign):
+    ent = context_for(M)
+    ctx = _ensure_mass(ent, M, M_lumped)
+    if ctx.n != nodes:
+        raise ValueError(f"nodes={nodes} does not match the mass matrix ({ctx.n})")
+    if dof_neighbors is not None and len(dof_neighbors) != nodes:
+        raise ValueError("dof_neighbors must have one entry per node")
+    A_vals = ctx.embed(A)
+    S_vals = None if extra is None else ctx.embed(extra)
+    rhs_v = None if rhs is None else np.asarray(rhs, dtype=np.float64).ravel()
+    out, info = ctx.step_host(A_vals, np.asarray(u_n, dtype=np.float64).ravel(), dt, sign=sign, S_vals=S_vals,
+                              rhs=rhs_v)
+    if not info.converged:
+        raise _lib.FctError(f"low-order Jacobi solve did not converge in {info.solver_sweeps} sweeps "
+                            f"(delta/|x| = {info.last_delta / max(info.x_norm, 1e-300):.3e}); dt is too large "
+                            "for the M-matrix property (helpers.py:1795-1809)")
+    if sign > 0 and info.min_rowsum_low <= 0:      # the legacy FCT_alg has no such diagnostic
+        ml = M_lumped.diagonal() if sp.issparse(M_lumped) else np.asarray(M_lumped).ravel()
+        _print_dt_bounds(sp.csr_matrix(A) * sign, ml)
+    return out
+
+
+def FCT_alg_ref(A, rhs, u_n, dt, nodes, M, M_lumped, dof_neighbors, non_flux_mat=None, vertex_to_dof=None):
+    """helpers.py:1715-1872: one FCT step of [M + dt (A + non_flux_mat)] u+ = M u^n + dt rhs."""
+    return _fct(A, rhs, u_n, dt, nodes, M, M_lumped, dof_neighbors, non_flux_mat, +1.0)
+
+
+def FCT_alg(A, rhs, u_n, dt, nodes, M, M_lumped, dof_neighbors, source_mat=None):
+    """old_helpers.py:115-204 (legacy sign convention, M du/dt = A u - S u + r):
+    FCT_alg(A, S) == FCT_alg_ref(-A, S)."""
+    return _fct(A, rhs, u_n, dt, nodes, M, M_lumped, dof_neighbors, source_mat, -1.0)
+
+
+# --------------------------------------------------------------------------------------------------
+# norms and cost functional
+# --------------------------------------------------------------------------------------------------
+def L2_norm_sq_Q(phi, num_steps, dt, M):
+    """helpers.py:330-360."""
+    ent = context_for(M)
+    ctx = ent["ctx"]
+    phi = np.asarray(phi, dtype=np.float64).ravel()
+    if phi.size != (num_steps + 1) * ctx.n:
+        raise ValueError("array split does not result in an equal division")     # np.split's error in the reference
+    d_M = ctx.array(ctx.embed(M))
+    d_phi = ctx.array(phi)
+    val = ctx.norm_sq_Q(d_M, d_phi, num_steps, dt)
+    d_M.free(); d_phi.free()
+    return val
+
+
+def L2_norm_sq_Omega(phi, M):
+    """helpers.py:362-381."""
+    ent = context_for(M)
+    ctx = ent["ctx"]
+    d_M = ctx.array(ctx.embed(M))
+    d_phi = ctx.array(np.asarray(phi, dtype=np.float64).ravel())
+    val = ctx.dot_M(d_M, d_phi, d_phi)
+    d_M.free(); d_phi.free()
+    return val
+
+
+def cost_functional(var1, var1_target, projected_control, num_steps, dt, M, beta, optim, var2=None,
+                    var2_target=None):
+    """helpers.py:383-441."""
+    valid_options = ["alltime", "finaltime"]
+    if optim not in valid_options:
+        raise ValueError(f"Invalid value for 'optim': '{optim}'. Must be one of {valid_options}.")
+    if optim == "alltime":
+        print("Calculating L^2(Q)-norm...")
+        func = 0.5 * L2_norm_sq_Q(var1 - var1_target, num_steps, dt, M)
+        if var2 is not None and var2_target is not None:
+            func += 0.5 * L2_norm_sq_Q(var2 - var2_target, num_steps, dt, M)
+    else:
+        print("Calculating L^2(\\Omega)-norm...")
+        nodes = var1_target.shape[0]
+        func = 0.5 * L2_norm_sq_Omega(var1[num_steps * nodes:] - var1_target, M)
+        if var2 is not None and var2_target is not None:
+            func += 0.5 * L2_norm_sq_Omega(var2[num_steps * nodes:] - var2_target, M)
+    func += beta / 2 * L2_norm_sq_Q(projected_control, num_steps, dt, M)
+    return func

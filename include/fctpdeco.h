@@ -1,0 +1,219 @@
+/*
+ * fctpdeco.h -- C ABI of libfctpdeco.so: the B200 (sm_100a) implementation of the hot path of
+ * KarolinaBenkova/FEM-FCT-PDECO (P1 FEM flux-corrected transport step, element assembly into a fixed
+ * CSR pattern, sparse state/adjoint solves, norms / cost functional, PDECO time loops).
+ *
+ * The reference has no FFI: its boundary is the Python namespace of helpers.py.  Each
+ * entry point below names the reference function (file:line in the reference repo) whose arithmetic it
+ * replaces; the Python package `fem-fct-pdeco_b200/` binds these with ctypes and re-exports the
+ * reference names (FCT_alg_ref, ChebSI, ...).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C, no exceptions: every call returns 0 on success, nonzero on error; fct_last_error()
+ *     returns a message for the calling thread's last failure.
+ *   - one context per (process, device); a context is NOT thread-safe; calls enqueue work on the
+ *     context's CUDA stream.  `_dev` pointers are device pointers (fp64 unless said otherwise) valid
+ *     on the context's device; `_host` pointers are host pointers and the call synchronises before
+ *     returning.  Functions without host outputs return as soon as the work is enqueued.
+ *   - all matrices are *value arrays of length nnz on the context's fixed CSR pattern* (rowptr, colidx,
+ *     columns ascending, diagonal present, structurally symmetric) -- what helpers.py:87-104
+ *     (assemble_sparse: PETSc getValuesCSR) returns.  Vectors are in DoF order.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef FCTPDECO_H
+#define FCTPDECO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fct_ctx fct_ctx;
+
+/* per-step diagnostics written by fct_step (host struct) */
+typedef struct fct_step_info {
+    int32_t solver_sweeps;     /* Jacobi sweeps executed for the low-order system            */
+    int32_t converged;         /* 1 if the stopping test was met within max_sweeps           */
+    double  last_delta;        /* ||x_k - x_{k-1}||_inf at exit                               */
+    double  x_norm;            /* ||x_k||_inf at exit                                         */
+    double  min_rowsum_low;    /* min_i sum_j (M_L + dt(A-D+S))_ij: <= 0 reproduces the       */
+                               /* reference's "3: False" diagnostic (helpers.py:1796-1809)    */
+} fct_step_info;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char* fct_last_error(void);
+int  fct_version(void);
+int  fct_device_count(void);
+
+/* ---- structured mesh bookkeeping (host side, closed form) --------------------------------------
+ * Replaces dolfin RectangleMesh(Point(a1,a1),Point(a2,a2),n,n) + FunctionSpace(mesh,'CG',1) +
+ * vertex_to_dof_map + find_node_neighbours (advection_solidbody_FCT.py:48-50,82-86,
+ * helpers.py:271-307) and the CSR pattern of assemble_sparse (helpers.py:87-104).
+ * Sizes: nodes=(n+1)^2, cells=2n^2, nnz = nodes + 2*(2(n+1)n + n^2). */
+int fct_mesh_rect_sizes(int32_t n, int64_t* nodes, int64_t* cells, int64_t* nnz);
+int fct_mesh_rect_build(int32_t n, double a1, double a2,
+                        int32_t* vertex_to_dof,   /* [nodes]            or NULL */
+                        int32_t* cell_dofs,       /* [cells*3] DoF idx  or NULL */
+                        double*  dof_xy,          /* [nodes*2] DoF order or NULL */
+                        int32_t* rowptr,          /* [nodes+1]          or NULL */
+                        int32_t* colidx);         /* [nnz]              or NULL */
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* rowptr/colidx are HOST arrays of the (local) pattern; they are copied to the device.
+ * row_begin/row_end: the rows this context owns and computes (0,n for a single GPU).  Rows outside
+ * are halo rows: their vector entries are inputs refreshed by fct_halo_exchange. */
+int fct_ctx_create(fct_ctx** out, int device, int32_t n, const int32_t* rowptr, const int32_t* colidx,
+                   int32_t row_begin, int32_t row_end);
+int fct_ctx_destroy(fct_ctx* ctx);
+int fct_ctx_set_stream(fct_ctx* ctx, void* cuda_stream);      /* cudaStream_t; NULL = legacy default */
+int fct_ctx_sync(fct_ctx* ctx);
+int fct_ctx_sizes(fct_ctx* ctx, int32_t* n, int64_t* nnz, int32_t* row_begin, int32_t* row_end);
+/* device pointers of the pattern (int32) */
+int fct_ctx_pattern_dev(fct_ctx* ctx, const int32_t** rowptr_dev, const int32_t** colidx_dev,
+                        const int32_t** tpos_dev);
+/* P1 mesh for the assembly kernels: DoF-indexed cells and DoF-ordered coordinates (host arrays, copied) */
+int fct_ctx_set_mesh(fct_ctx* ctx, int64_t ncells, const int32_t* cell_dofs, const double* dof_xy);
+/* static matrices: consistent mass M (values on the pattern), lumped mass ML, diag(M).
+ * fct_ctx_set_mass copies from device arrays; fct_assemble_static computes M, ML, K on the device
+ * (replaces assemble_sparse_lil(u*v*dx), row_lump, assemble_sparse(dot(grad(u),grad(v))*dx):
+ * helpers.py:553-555, 309-328). */
+int fct_ctx_set_mass(fct_ctx* ctx, const double* M_dev);
+/* override the lumped mass computed by fct_ctx_set_mass with the caller's M_lumped diagonal
+ * (FCT_alg_ref takes M_lumped as an argument, helpers.py:1715) */
+int fct_ctx_set_lumped(fct_ctx* ctx, const double* ML_dev);
+int fct_assemble_static(fct_ctx* ctx);
+int fct_ctx_static_dev(fct_ctx* ctx, const double** M_dev, const double** ML_dev, const double** Mdiag_dev,
+                       const double** K_dev);
+/* solver options for the low-order system (defaults: rtol 1e-14, max_sweeps 200, check_every 2) */
+int fct_ctx_set_solver(fct_ctx* ctx, double rtol, int32_t max_sweeps);
+
+/* ---- device memory helpers (optional; any device allocation works, e.g. torch tensors) -------- */
+int fct_malloc(fct_ctx* ctx, void** ptr_dev, int64_t bytes);
+int fct_free(fct_ctx* ctx, void* ptr_dev);
+int fct_h2d(fct_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);   /* async on ctx stream */
+int fct_d2h(fct_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);   /* synchronises       */
+/* page-locked host memory (so that the host-buffer entry points overlap copies with compute) */
+int fct_host_alloc(fct_ctx* ctx, void** ptr_host, int64_t bytes);
+int fct_host_free(fct_ctx* ctx, void* ptr_host);
+
+/* ---- sparse kernels --------------------------------------------------------------------------- */
+/* y = alpha * A x + beta * z   (z may be NULL when beta == 0; y may alias z).  scipy `A @ x`. */
+int fct_spmv(fct_ctx* ctx, const double* A_dev, const double* x_dev, double alpha, double beta,
+             const double* z_dev, double* y_dev);
+/* ChebSI (helpers.py:143-185): exactly `iters` iterations of the Jacobi-preconditioned Chebyshev
+ * recurrence for M y = b with eigenvalue bounds [lmin,lmax]; Md_dev is the `Md` argument (diag(M)). */
+int fct_chebsi(fct_ctx* ctx, const double* M_dev, const double* Md_dev, const double* b_dev,
+               double* y_dev, int32_t iters, double lmin, double lmax);
+/* artificial_diffusion_mat (helpers.py:206-242): D_ij = max(0,-m_ij,-m_ji), D_ii = -sum_j D_ij. */
+int fct_artificial_diffusion(fct_ctx* ctx, const double* mat_dev, double* D_dev);
+/* row_lump (helpers.py:309-328): out_i = sum_j mat_ij. */
+int fct_row_lump(fct_ctx* ctx, const double* mat_dev, double* out_dev);
+
+/* ---- the FCT step ----------------------------------------------------------------------------- */
+/* FCT_alg_ref (helpers.py:1715-1872), sign = +1:  [M + dt (A + S)] u+ = M u^n + dt rhs.
+ * Legacy FCT_alg (old_helpers.py:115-204), sign = -1: the same with A -> -A.
+ * S_dev (non_flux_mat / source_mat) and rhs_dev may be NULL.  Uses the context's M, ML.
+ * info_host may be NULL (then nothing is copied back and the call does not synchronise). */
+int fct_step(fct_ctx* ctx, const double* A_dev, double sign, const double* S_dev, const double* rhs_dev,
+             const double* u_n_dev, double dt, double* u_out_dev, fct_step_info* info_host);
+/* same call with HOST buffers (A_host[nnz], S_host[nnz]|NULL, rhs_host[n]|NULL, u_n_host[n] -> u_out_host[n]);
+ * copies are inside the call.  This is what the FCT_alg_ref / FCT_alg Python shims use. */
+int fct_step_host(fct_ctx* ctx, const double* A_host, double sign, const double* S_host, const double* rhs_host,
+                  const double* u_n_host, double dt, double* u_out_host, fct_step_info* info_host);
+
+/* ---- linear solvers for the second-species systems -------------------------------------------- */
+/* spsolve replacements (helpers.py:596,686,1342,1538).  kind: 0 = Jacobi, 1 = Jacobi-PCG (SPD),
+ * 2 = Jacobi-BiCGStab (nonsymmetric).  x_dev holds the initial guess on entry.  its_host/res_host may be NULL. */
+int fct_solve(fct_ctx* ctx, int32_t kind, const double* mat_dev, const double* b_dev, double* x_dev,
+              double rtol, int32_t maxit, int32_t* its_host, double* res_host);
+/* out = a*X + b*Y on the pattern values (Y may be NULL), e.g. M + dt*(Df*K + delta*M) */
+int fct_vals_axpby(fct_ctx* ctx, double a, const double* X_dev, double b, const double* Y_dev, double* out_dev);
+
+/* ---- norms / cost functional ------------------------------------------------------------------ */
+/* x^T M y over owned rows (L2_norm_sq_Omega, helpers.py:362-381, when x == y) */
+int fct_dot_M(fct_ctx* ctx, const double* M_dev, const double* x_dev, const double* y_dev, double* out_host);
+/* L2_norm_sq_Q (helpers.py:330-360) of (phi - target) (target may be NULL): trapezoid in time.
+ * phi/target are time-major trajectories [(num_steps+1) * n]. */
+int fct_norm_sq_Q(fct_ctx* ctx, const double* M_dev, const double* phi_dev, const double* target_dev,
+                  int32_t num_steps, double dt, double* out_host);
+/* elementwise helpers on vectors / trajectories: out = clip(x + s*d, lo, hi); out = a*x + b*y */
+int fct_clip_axpy(fct_ctx* ctx, int64_t len, const double* x_dev, double s, const double* d_dev,
+                  double lo, double hi, double* out_dev);
+int fct_axpby(fct_ctx* ctx, int64_t len, double a, const double* x_dev, double b, const double* y_dev,
+              double* out_dev);
+
+/* ---- element assembly into the fixed pattern (needs fct_ctx_set_mesh) ------------------------- */
+/* Form kinds (i = test, j = trial):
+ *   FCT_FORM_MASS          u v                         (helpers.py:553)
+ *   FCT_FORM_STIFFNESS     grad u . grad v             (helpers.py:555)
+ *   FCT_FORM_DRIFT         (b.grad c) u v + (b.grad v) c u   coef0 = c (P1), s0,s1 = b
+ *                          (advection_solidbody_FCT_PDECO_alltime.py:222-223; old_helpers.py:62-63)
+ *   FCT_FORM_WIND_P1       (w.grad v) u, w P1 nodal     coef0 = wx, coef1 = wy   (helpers.py:581)
+ *   FCT_FORM_WIND_P1_T     (w.grad u) v                 coef0 = wx, coef1 = wy   (helpers.py:681)
+ *   FCT_FORM_WMASS1/2/3    (f0 [f1 [f2]]) u v, P1 coefficient fields  (helpers.py:591,683,692,953,1032)
+ *   FCT_FORM_CHTX          (grad f . grad v) u          coef0 = f   (old_helpers.py:102)
+ *   FCT_FORM_CHTX_EXP      exp(-s0 m)(grad f . grad v) u, coef0 = f, coef1 = m, quadrature degree 4
+ *                          (helpers.py:1350-1351)
+ *   FCT_FORM_CHTX_ADJ      (1-s0 u)exp(-s0 u)(grad u_trial . grad vn) w, coef0 = vn, coef1 = u, degree 5
+ *                          (helpers.py:1499-1500)
+ * out_vals = scale * form (+ out_vals if accumulate != 0). */
+enum {
+    FCT_FORM_MASS = 0, FCT_FORM_STIFFNESS = 1, FCT_FORM_DRIFT = 2, FCT_FORM_WIND_P1 = 3,
+    FCT_FORM_WIND_P1_T = 4, FCT_FORM_WMASS1 = 5, FCT_FORM_WMASS2 = 6, FCT_FORM_WMASS3 = 7,
+    FCT_FORM_CHTX = 8, FCT_FORM_CHTX_EXP = 9, FCT_FORM_CHTX_ADJ = 10
+};
+int fct_assemble_matrix(fct_ctx* ctx, int32_t kind, const double* coef0_dev, const double* coef1_dev,
+                        const double* coef2_dev, double s0, double s1, double scale, int32_t accumulate,
+                        double* out_vals_dev);
+/* Linear forms:
+ *   FCT_LOAD_P1_1/2/3/4    (f0 [f1 [f2 [f3]]]) v       (helpers.py:584-585,684,693,956,1339-1340)
+ *   FCT_LOAD_CONST         s0 * v                       (helpers.py:594)
+ *   FCT_LOAD_DRIFT_GRAD    p (b.grad u) v, coef0 = p, coef1 = u, s0,s1 = b
+ *                          (advection_solidbody_FCT_PDECO_alltime.py:273)
+ *   FCT_LOAD_CHTX_ADJ      s1 * u exp(-s0 u) grad p . grad w, coef0 = p, coef1 = u, degree 4 (helpers.py:1531-1532)
+ * out = scale * form (+ out if accumulate). */
+enum {
+    FCT_LOAD_P1_1 = 0, FCT_LOAD_P1_2 = 1, FCT_LOAD_P1_3 = 2, FCT_LOAD_P1_4 = 3, FCT_LOAD_CONST = 4,
+    FCT_LOAD_DRIFT_GRAD = 5, FCT_LOAD_CHTX_ADJ = 6
+};
+int fct_assemble_vector(fct_ctx* ctx, int32_t kind, const double* coef0_dev, const double* coef1_dev,
+                        const double* coef2_dev, const double* coef3_dev, double s0, double s1, double scale,
+                        int32_t accumulate, double* out_dev);
+
+/* ---- device-resident time loops of the drift-control advection PDECO ------------------------------
+ * (advection_solidbody_FCT_PDECO_alltime.py:210-275, the shape of the 4096^2 benchmark).  Trajectories
+ * are time-major device arrays [(num_steps+1) * n]; slice 0 of u must hold the initial condition. */
+int fct_advdrift_state(fct_ctx* ctx, const double* c_traj_dev, double* u_traj_dev, int32_t num_steps, double dt,
+                       double bx, double by, double eps, int32_t* total_sweeps_host);
+int fct_advdrift_adjoint(fct_ctx* ctx, const double* c_traj_dev, const double* u_traj_dev,
+                         const double* uhat_traj_dev, double* p_traj_dev, int32_t num_steps, double dt,
+                         double bx, double by, double eps, int32_t* total_sweeps_host);
+int fct_advdrift_gradient(fct_ctx* ctx, const double* c_traj_dev, const double* u_traj_dev,
+                          const double* p_traj_dev, double* d_traj_dev, int32_t num_steps, double beta,
+                          double bx, double by);
+/* the same forward loop with HOST trajectories (pinned or pageable): c slices are streamed in and u slices
+ * streamed out on a copy stream, overlapped with compute.  This is the end-to-end path bench.py times. */
+int fct_advdrift_state_host(fct_ctx* ctx, const double* c_traj_host, double* u_traj_host, int32_t num_steps,
+                            double dt, double bx, double by, double eps, int32_t* total_sweeps_host);
+
+/* ---- multi-GPU (row-block partition, one-ring halo; one process per GPU) ----------------------- */
+int fct_nccl_unique_id(void* id_out_128bytes);                       /* rank 0 calls, broadcasts the bytes */
+int fct_ctx_init_comm(fct_ctx* ctx, const void* id_128bytes, int32_t rank, int32_t world,
+                      int32_t send_lo_begin, int32_t send_lo_end,    /* local rows sent to rank-1          */
+                      int32_t send_hi_begin, int32_t send_hi_end);   /* local rows sent to rank+1          */
+int fct_halo_exchange(fct_ctx* ctx, double* vec_dev);                /* refresh halo entries of a vector    */
+
+/* ---- instrumentation ---------------------------------------------------------------------------- */
+/* CUDA events on the context's stream (what bench.py times kernels with) */
+int fct_event_create(fct_ctx* ctx, void** event_out);
+int fct_event_record(fct_ctx* ctx, void* event);
+int fct_event_elapsed_ms(fct_ctx* ctx, void* start, void* stop, float* ms_host);   /* synchronises on stop */
+int fct_event_destroy(fct_ctx* ctx, void* event);
+/* number of kernels this library has launched on this context since creation */
+int fct_launch_count(fct_ctx* ctx, int64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCTPDECO_H */

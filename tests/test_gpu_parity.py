@@ -1,0 +1,322 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C-ABI / the reference-named
+Python shims, against (a) outputs of the reference's own functions (tests/golden/ref_fct_cases.npz),
+(b) the reference's shipped data (tests/golden/ref_data.npz) and (c) the numpy oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp64 fields within 1e-12 relative L2 per time step, cost functional
+within 1e-9; sparsity pattern and DoF ordering bit-exact (checked on the CPU in test_abi.py)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import fem_fct_pdeco_b200 as fp
+from fem_fct_pdeco_b200 import _lib, helpers
+from fem_fct_pdeco_b200.mesh import RectMeshP1
+
+from conftest import rel_l2
+from oracle import pdeco_numpy as drv
+from oracle.fct_numpy import Pattern, artificial_diffusion, chebsi, cost_functional, fct_step
+from oracle.p1assembly import P1Assembler
+from oracle.p1mesh import RectMesh
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-12       # relative L2 per FCT step (north_star)
+TOL_COST = 1e-9        # cost functional (north_star)
+TOL_ASM = 1e-13        # assembled operators / vectors (relative to the largest entry)
+
+
+def _oracle(n, a1, a2):
+    mesh = RectMesh(n, a1, a2)
+    return mesh, P1Assembler(mesh), Pattern(*mesh.pattern())
+
+
+@pytest.fixture(scope="module")
+def small():
+    """n=12 mesh on [-1,1]^2: GPU context with static matrices + oracle twins"""
+    m = RectMeshP1(12, -1.0, 1.0)
+    ctx = m.context()
+    mesh, asm, pat = _oracle(12, -1.0, 1.0)
+    return m, ctx, mesh, asm, pat
+
+
+# ---- (a) the reference's own functions ------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["solid", "chtxs", "schnak", "drift"])
+def test_FCT_alg_ref_matches_reference_function(ref_cases, tag):
+    c = ref_cases
+    n = int(c[f"{tag}_n"][0]); a1, a2 = c[f"{tag}_box"]
+    mesh, asm, pat = _oracle(n, a1, a2)
+    M = sp.lil_matrix(pat.csr(asm.mass()))
+    ML = sp.lil_matrix((mesh.nodes, mesh.nodes)); ML.setdiag(asm.lumped(asm.mass()))
+    A = pat.csr(c[f"{tag}_A"]); A.eliminate_zeros()                      # what scipy arithmetic hands over
+    S = pat.csr(c[f"{tag}_S"]) if c[f"{tag}_S"].size else None
+    out = helpers.FCT_alg_ref(A, c[f"{tag}_rhs"], c[f"{tag}_un"], float(c[f"{tag}_dt"][0]), mesh.nodes, M, ML,
+                              mesh.dof_neighbors(), non_flux_mat=S)
+    assert rel_l2(out, c[f"{tag}_out"]) < TOL_STEP
+    # legacy entry point: FCT_alg(A, S) == FCT_alg_ref(-A, S)   (old_helpers.py:135-152)
+    out2 = helpers.FCT_alg(-A, c[f"{tag}_rhs"], c[f"{tag}_un"], float(c[f"{tag}_dt"][0]), mesh.nodes, M, ML,
+                           mesh.dof_neighbors(), source_mat=S)
+    assert np.array_equal(out, out2)
+
+
+def test_ChebSI_adm_rowlump_norms_match_reference_functions(ref_cases):
+    c = ref_cases
+    mesh, asm, pat = _oracle(12, -1.0, 1.0)
+    Mv = asm.mass()
+    M = pat.csr(Mv)
+    assert rel_l2(helpers.ChebSI(c["cheb_b"], M, M.diagonal(), 20, 0.5, 2), c["cheb_out"]) < 1e-14
+    assert rel_l2(helpers.ChebSI(c["cheb_b"], M, M.diagonal(), 7), c["cheb7_out"]) < 1e-14
+    assert rel_l2(helpers.ChebSI(c["cheb_b"], M, M.diagonal(), 1), chebsi(pat, c["cheb_b"], Mv, Mv[pat.diagpos], 1)) < 1e-15
+    D = helpers.artificial_diffusion_mat(sp.lil_matrix(pat.csr(c["adm_in"])))
+    assert np.abs(pat.embed(D) - c["adm_out"]).max() < 1e-15
+    lump = helpers.row_lump(sp.lil_matrix(M), mesh.nodes)
+    assert rel_l2(lump.diagonal(), asm.lumped(Mv)) < 1e-15
+    ns, dt, beta = int(c["norm_meta"][0]), c["norm_meta"][1], c["norm_meta"][2]
+    phi, tgt, ctl = c["norm_phi"], c["norm_tgt"], c["norm_ctl"]
+    assert abs(helpers.L2_norm_sq_Q(phi, ns, dt, M) / c["norm_Q"][0] - 1) < 1e-13
+    assert abs(helpers.L2_norm_sq_Omega(phi[:mesh.nodes], M) / c["norm_Omega"][0] - 1) < 1e-13
+    assert abs(helpers.cost_functional(phi, tgt, ctl, ns, dt, M, beta, "alltime") / c["cost_alltime"][0] - 1) < TOL_COST
+    assert abs(helpers.cost_functional(phi, tgt[:mesh.nodes], ctl, ns, dt, M, beta, "finaltime")
+               / c["cost_finaltime"][0] - 1) < TOL_COST
+    assert abs(helpers.cost_functional(phi, tgt, ctl, ns, dt, M, beta, "alltime", var2=tgt, var2_target=phi)
+               / c["cost_alltime2"][0] - 1) < TOL_COST
+    with pytest.raises(ValueError):
+        helpers.cost_functional(phi, tgt, ctl, ns, dt, M, beta, "sometime")
+
+
+# ---- (c) assembly kernels against the oracle ---------------------------------------------------------
+def _relmax(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300))
+
+
+def test_static_matrices(small):
+    m, ctx, mesh, asm, pat = small
+    M, ML, Md, K = ctx.static()
+    Mo = asm.mass()
+    assert _relmax(M.download(), Mo) < TOL_ASM
+    assert _relmax(K.download(), asm.stiffness()) < TOL_ASM
+    assert _relmax(ML.download(), asm.lumped(Mo)) < TOL_ASM
+    assert _relmax(Md.download(), Mo[pat.diagpos]) < TOL_ASM
+
+
+def test_matrix_forms(small):
+    m, ctx, mesh, asm, pat = small
+    rng = np.random.default_rng(5)
+    f = [1.0 + rng.random(mesh.nodes) for _ in range(3)]
+    d = [ctx.array(x) for x in f]
+    out = ctx.empty(ctx.nnz)
+    L = _lib
+
+    def run(kind, **kw):
+        ctx.assemble_matrix(kind, out, **kw)
+        return out.download()
+
+    assert _relmax(run(L.FORM_MASS), asm.mass()) < TOL_ASM
+    assert _relmax(run(L.FORM_STIFFNESS, scale=0.3), 0.3 * asm.stiffness()) < TOL_ASM
+    ref = asm.drift_mass(f[0], 1.0, 0.5) + asm.drift_conv(f[0], 1.0, 0.5)
+    assert _relmax(run(L.FORM_DRIFT, c0=d[0], s0=1.0, s1=0.5), ref) < TOL_ASM
+    assert _relmax(run(L.FORM_WIND_P1, c0=d[0], c1=d[1]), asm.conv_conservative_p1(f[0], f[1])) < TOL_ASM
+    wt = pat.csr(asm.conv_conservative_p1(f[0], f[1])).T.tocsr(); wt.sort_indices()
+    assert _relmax(run(L.FORM_WIND_P1_T, c0=d[0], c1=d[1]), pat.embed(wt)) < TOL_ASM
+    assert _relmax(run(L.FORM_WMASS1, c0=d[0]), asm.mass_p1_product(f[0])) < TOL_ASM
+    assert _relmax(run(L.FORM_WMASS2, c0=d[0], c1=d[1]), asm.mass_p1_product(f[0], f[1])) < TOL_ASM
+    assert _relmax(run(L.FORM_WMASS3, c0=d[0], c1=d[1], c2=d[2]), asm.mass_p1_product(f[0], f[1], f[2])) < TOL_ASM
+    assert _relmax(run(L.FORM_CHTX, c0=d[0]), asm.chemotaxis_conv(f[0])) < TOL_ASM
+    ref = asm.chemotaxis_conv(f[0], lambda phi, xy: np.exp(-0.5 * asm.at_quad(f[1], phi)), degree=4)
+    assert _relmax(run(L.FORM_CHTX_EXP, c0=d[0], c1=d[1], s0=0.5), ref) < TOL_ASM
+    assert _relmax(run(L.FORM_CHTX_ADJ, c0=d[0], c1=d[1], s0=0.5), asm.chemotaxis_adjoint_mat(f[1], f[0], 0.5)) < TOL_ASM
+    # accumulate: out = K-scaled + previous
+    ctx.assemble_matrix(L.FORM_MASS, out)
+    ctx.assemble_matrix(L.FORM_STIFFNESS, out, scale=2.0, accumulate=True)
+    assert _relmax(out.download(), asm.mass() + 2.0 * asm.stiffness()) < TOL_ASM
+
+
+def test_vector_forms(small):
+    m, ctx, mesh, asm, pat = small
+    rng = np.random.default_rng(6)
+    f = [1.0 + rng.random(mesh.nodes) for _ in range(4)]
+    d = [ctx.array(x) for x in f]
+    out = ctx.empty(ctx.n)
+    L = _lib
+
+    def run(kind, **kw):
+        ctx.assemble_vector(kind, out, **kw)
+        return out.download()
+
+    assert _relmax(run(L.LOAD_P1_1, c0=d[0]), asm.load_p1_product(f[0])) < TOL_ASM
+    assert _relmax(run(L.LOAD_P1_2, c0=d[0], c1=d[1]), asm.load_p1_product(f[0], f[1])) < TOL_ASM
+    assert _relmax(run(L.LOAD_P1_3, c0=d[0], c1=d[1], c2=d[2], scale=2.5), asm.load_p1_product(f[0], f[1], f[2], scale=2.5)) < TOL_ASM
+    assert _relmax(run(L.LOAD_P1_4, c0=d[0], c1=d[1], c2=d[2], c3=d[3]), asm.load_p1_product(*f)) < TOL_ASM
+    assert _relmax(run(L.LOAD_CONST, s0=3.0), asm.load_constant(3.0)) < TOL_ASM
+    assert _relmax(run(L.LOAD_DRIFT_GRAD, c0=d[0], c1=d[1], s0=1.0, s1=1.0), asm.load_drift_grad(f[0], f[1], 1.0, 1.0)) < TOL_ASM
+    ref = asm.load_grad_pair(lambda phi, xy: 0.25 * asm.at_quad(f[1], phi) * np.exp(-0.5 * asm.at_quad(f[1], phi)), f[0], 4)
+    assert _relmax(run(L.LOAD_CHTX_ADJ, c0=d[0], c1=d[1], s0=0.5, s1=0.25), ref) < TOL_ASM
+
+
+def test_spmv_and_solvers(small):
+    m, ctx, mesh, asm, pat = small
+    rng = np.random.default_rng(7)
+    M, ML, Md, K = ctx.static()
+    x = rng.random(mesh.nodes); z = rng.random(mesh.nodes)
+    dx, dz, dy = ctx.array(x), ctx.array(z), ctx.empty(ctx.n)
+    ctx.spmv(M, dx, dy, alpha=-2.0, beta=0.5, z=dz)
+    assert rel_l2(dy.download(), -2.0 * (pat.csr(asm.mass()) @ x) + 0.5 * z) < 1e-14
+    # SPD second-species matrix M + dt (Df K + delta M)   (helpers.py:1308)
+    Mo, Ko = asm.mass(), asm.stiffness()
+    mat = Mo + 1e-3 * (0.05 * Ko + 100 * Mo)
+    dmat = ctx.array(mat)
+    b = pat.csr(mat) @ x
+    for kind in (_lib.SOLVER_JACOBI, _lib.SOLVER_PCG, _lib.SOLVER_BICGSTAB):
+        sol = ctx.array(np.zeros(mesh.nodes))
+        its, res = ctx.solve(kind, dmat, ctx.array(b), sol, rtol=1e-14, maxit=2000)
+        assert rel_l2(sol.download(), x) < 1e-12, (kind, its, res)
+    # nonsymmetric: + wind operator   (helpers.py:595)
+    mat2 = Mo + 1e-3 * (8.6676 * Ko - 0.6 * asm.conv_conservative(lambda X, Y: ((Y - .5) * X * (1 - X), -(X - .5) * Y * (1 - Y))))
+    b2 = pat.csr(mat2) @ x
+    sol = ctx.array(np.zeros(mesh.nodes))
+    its, res = ctx.solve(_lib.SOLVER_BICGSTAB, ctx.array(mat2), ctx.array(b2), sol, rtol=1e-14, maxit=2000)
+    assert rel_l2(sol.download(), x) < 1e-11, (its, res)
+
+
+# ---- (b) golden trajectories -----------------------------------------------------------------------------
+def test_chemotaxis_golden_trajectory(ref_data):
+    """10 steps of solve_chtxs_system (helpers.py:1250-1385): PCG second species, exp-form assembly at
+    quadrature degree 4, FCT step -- all on the device -- against the reference's shipped trajectory."""
+    gm, gf = ref_data["chtxs_m"], ref_data["chtxs_f"]
+    m = RectMeshP1(40, 0.0, 1.0)
+    ctx = m.context()
+    L = _lib
+    delta, Dm, Df, chi, eta = 100.0, 0.05, 0.05, 0.25, 0.5
+    dt = 1e-3
+    M, ML, Md, K = ctx.static()
+    mat2 = ctx.empty(ctx.nnz)
+    ctx.vals_axpby(1.0 + dt * delta, M, dt * Df, K, mat2)          # M + dt (Df K + delta M)
+    mu, fu = ctx.array(gm[0]), ctx.array(gf[0])
+    mn, fn = ctx.empty(ctx.n), ctx.empty(ctx.n)
+    rhs, A = ctx.empty(ctx.n), ctx.empty(ctx.nnz)
+    for s in range(1, 11):
+        ctx.assemble_vector(L.LOAD_P1_1, rhs, c0=fu)
+        ctx.assemble_vector(L.LOAD_P1_1, rhs, c0=mu, scale=dt * 100.0, accumulate=True)
+        ctx.axpby(1.0, fu, 0.0, None, fn)
+        ctx.solve(L.SOLVER_PCG, mat2, rhs, fn, rtol=1e-15, maxit=500)
+        ctx.assemble_matrix(L.FORM_CHTX_EXP, A, c0=fn, c1=mu, s0=eta, scale=-chi)
+        ctx.vals_axpby(1.0, A, Dm, K, A)
+        info = ctx.step(A, mu, dt, mn)
+        assert info.converged
+        assert rel_l2(fn.download(), gf[s]) < TOL_STEP, s
+        assert rel_l2(mn.download(), gm[s]) < TOL_STEP, s
+        mu, mn = mn, mu
+        fu, fn = fn, fu
+
+
+def test_solidbody_golden_t025(ref_data):
+    """data/solidbody_t0.25_u.csv: 400 legacy FCT_alg steps of advection_solidbody_FCT.py (slit 0.05, dt = dx^2)."""
+    m = RectMeshP1(80, -1.0, 1.0)
+    ctx = m.context()
+    prob = drv.SolidBodyProblem(80, -1.0, 1.0, slit_width=0.05)
+    om = np.pi / 40
+    xy = m.dof_xy
+    wx, wy = ctx.array(-xy[:, 1] / om + 2.0), ctx.array(xy[:, 0] / om + 2.0)
+    A = ctx.empty(ctx.nnz)
+    ctx.assemble_matrix(_lib.FORM_WIND_P1, A, c0=wx, c1=wy)
+    assert _relmax(A.download(), prob.A_u) < TOL_ASM
+    u, un = ctx.array(prob.initial_condition()), ctx.empty(ctx.n)
+    sweeps = 0
+    for s in range(400):
+        info = ctx.step(A, u, 0.025 ** 2, un, sign=-1.0, want_info=(s % 50 == 0))
+        if info is not None:
+            assert info.converged
+            sweeps = info.solver_sweeps
+        u, un = un, u
+    assert sweeps > 0
+    # 400 steps: per-step parity 1e-12 accumulates; the oracle itself sits at 1.2e-14 from this file
+    assert rel_l2(u.download(), ref_data["solidbody_t0.25"]) < 1e-11
+
+
+# ---- drift-control PDECO loops (config 2 / 5 shape) against the oracle -----------------------------------
+def test_advdrift_state_adjoint_gradient_cost():
+    n, ns = 16, 8
+    orc = drv.AdvectionDriftPDECO(n, -1.0, 1.0)
+    h = 2.0 / n
+    dt = 0.25 * h / (2 * np.sqrt(2))
+    u0 = orc.gaussian_ic()
+    rng = np.random.default_rng(11)
+    c = 1.0 + rng.random((ns + 1, orc.nodes))
+    uhat = orc.target(u0, ns, dt, c_const=2.0)
+    u_o = orc.state(c, u0, ns, dt)
+    p_o = orc.adjoint(c, u_o, uhat, ns, dt)
+    d_o = orc.gradient(c, u_o, p_o, ns)
+    J_o = orc.cost(u_o, uhat, c, ns, dt)
+
+    m = RectMeshP1(n, -1.0, 1.0)
+    ctx = m.context()
+    dc, duh = ctx.array(c.ravel()), ctx.array(uhat.ravel())
+    utr = np.zeros((ns + 1, m.nodes)); utr[0] = u0
+    du = ctx.array(utr.ravel())
+    dp, dd = ctx.empty(du.size), ctx.empty(du.size)
+    sw = ctx.advdrift_state(dc, du, ns, dt)
+    assert sw >= 2 * ns
+    u_g = du.download().reshape(ns + 1, -1)
+    for i in range(1, ns + 1):
+        assert rel_l2(u_g[i], u_o[i]) < TOL_STEP * i, i
+    ctx.advdrift_adjoint(dc, du, duh, dp, ns, dt)
+    p_g = dp.download().reshape(ns + 1, -1)
+    for i in range(ns):
+        assert rel_l2(p_g[i], p_o[i]) < 1e-11, i
+    ctx.advdrift_gradient(dc, du, dp, dd, ns, 0.01)
+    d_g = dd.download().reshape(ns + 1, -1)
+    assert rel_l2(d_g, d_o) < 1e-11
+    M = ctx.static()[0]
+    J_g = 0.5 * ctx.norm_sq_Q(M, du, ns, dt, target=duh) + 0.01 / 2 * ctx.norm_sq_Q(M, dc, ns, dt)
+    assert abs(J_g / J_o - 1) < TOL_COST
+    # host-streaming variant of the state loop gives the same trajectory bit for bit
+    uh = np.zeros((ns + 1) * m.nodes); uh[:m.nodes] = u0
+    ctx.advdrift_state_host(np.ascontiguousarray(c.ravel()), uh, ns, dt)
+    assert np.array_equal(uh, u_g.ravel())
+    # clip / axpy helper (projection step, advection_solidbody_FCT_PDECO_alltime.py:290)
+    dnew = ctx.empty(dc.size)
+    ctx.clip_axpy(dc, 0.5, dd, 0.0, 5.0, dnew)
+    assert np.array_equal(dnew.download(), np.clip(c.ravel() + 0.5 * d_g.ravel(), 0.0, 5.0))
+
+
+def test_step_vs_oracle_medium_mesh():
+    """one state step at 257^2 (66k DoF) against the oracle's direct-solve step"""
+    n = 256
+    orc = drv.AdvectionDriftPDECO(n, 0.0, 1.0)
+    h = 1.0 / n
+    dt = 0.25 * h / (2 * np.sqrt(2))
+    u0 = orc.gaussian_ic()
+    xy = orc.mesh.dof_xy
+    c = 1.0 + 0.5 * np.sin(3 * xy[:, 0]) * np.cos(2 * xy[:, 1])
+    u_o = orc.state(np.tile(c, (2, 1)), u0, 1, dt)[1]
+    m = RectMeshP1(n, 0.0, 1.0)
+    ctx = m.context()
+    utr = np.zeros(2 * m.nodes); utr[:m.nodes] = u0
+    du = ctx.array(utr)
+    ctx.advdrift_state(ctx.array(np.tile(c, 2)), du, 1, dt)
+    assert rel_l2(du.download()[m.nodes:], u_o) < TOL_STEP
+
+
+def test_full_size_properties_4096():
+    """BASELINE size (4097^2 DoF): size-independent properties of one FCT step with a constant control:
+    discrete mass conservation (zero column sums of the drift operator, antisymmetric fluxes) and the local
+    discrete maximum principle of the limiter w.r.t. the low-order solution's bounds."""
+    n = 4096
+    m = RectMeshP1(n, 0.0, 1.0)
+    ctx = m.context()
+    M, ML, Md, K = ctx.static()
+    ml = ML.download()
+    assert abs(ml.sum() - 1.0) < 1e-12                      # area of the unit square
+    h = 1.0 / n
+    dt = 0.25 * h / (2 * np.sqrt(2))
+    xy = m.dof_xy
+    u0 = np.exp(-20 * ((2 * xy[:, 0] - 1 + 2 / 3) ** 2 + 5 * (2 * xy[:, 1] - 1 + 5 / 6) ** 2))
+    utr = np.zeros(3 * m.nodes); utr[:m.nodes] = u0
+    du = ctx.array(utr)
+    dc = ctx.array(np.full(3 * m.nodes, 2.0))
+    sw = ctx.advdrift_state(dc, du, 2, dt)
+    u = du.download().reshape(3, -1)
+    assert 4 <= sw <= 80
+    for i in (1, 2):
+        assert abs(ml @ u[i] - ml @ u0) <= 1e-12 * abs(ml @ u0)
+        assert u[i].min() >= -1e-14 and u[i].max() <= u0.max() + 1e-12
+    assert rel_l2(u[1], u0) > 1e-4                          # something moved
