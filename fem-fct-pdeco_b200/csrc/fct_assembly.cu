@@ -159,7 +159,8 @@ k_assemble_matrix(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     double* sV = reinterpret_cast<double*>(fct_smem);
     double* sO = sV + cap;                                   // previous values when accumulating
     int32_t* sC = reinterpret_cast<int32_t*>(sO + (accumulate ? cap : 0));
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
     stage_s32(sC, colidx, b, nnz);
     if (accumulate) stage_f64(sO, out, b, nnz);
     __syncthreads();
@@ -185,6 +186,8 @@ k_assemble_matrix(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     }
     __syncthreads();
     unstage_f64(out, sV, b);
+    __syncthreads();
+    }
 }
 
 // ---- linear forms ------------------------------------------------------------------------------------
@@ -250,7 +253,7 @@ template <int KIND>
 static int launch_matrix(fct_ctx* ctx, const FormArgs& fa, double scale, int accumulate, double* out) {
     // all local rows, halo rows included: their entries (j,i) towards owned rows i are complete because every
     // cell containing an owned vertex is local, and those are the only halo-row values the FCT step reads (a_ji).
-    const int nb = (ctx->n + FCT_RB - 1) / FCT_RB;
+    const int nb = fct_grid(ctx, (ctx->n + FCT_RB - 1) / FCT_RB);
     const size_t smem = (size_t)ctx->cap * (8 * (accumulate ? 2 : 1) + 4);
     k_assemble_matrix<KIND><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->v2c_ptr, ctx->v2c_idx,
                                                                ctx->cells, ctx->xy, fa, scale, accumulate, out,

@@ -50,6 +50,7 @@ struct fct_ctx {
     int32_t row_begin = 0, row_end = 0;
     int32_t cap = 0;            // max staged entries of any row block (incl. alignment slack)
     int32_t max_row = 0;
+    int32_t grid_cap = 148 * 8; // persistent grid: SMs x resident 256-thread CTAs
     int32_t* rowptr = nullptr;  // device
     int32_t* colidx = nullptr;
     int32_t* tpos = nullptr;
@@ -75,7 +76,7 @@ struct fct_ctx {
     unsigned long long* jstate = nullptr;  // Jacobi state words
     double* pinned = nullptr;   // small pinned host buffer (64 doubles)
     double rtol = 1e-14;
-    int32_t max_sweeps = 200;
+    int32_t max_sweeps = 100;
     int64_t launches = 0;
     fct_comm* comm = nullptr;
     // halo description (multi-GPU)
@@ -83,6 +84,8 @@ struct fct_ctx {
 };
 
 static inline int fct_nblocks(const fct_ctx* c) { return (c->row_end - c->row_begin + FCT_RB - 1) / FCT_RB; }
+// launch grid of a persistent row-block kernel over `nblocks` row blocks
+static inline int fct_grid(const fct_ctx* c, int nblocks) { return nblocks < c->grid_cap ? nblocks : c->grid_cap; }
 
 #ifdef __CUDACC__
 // ---- streaming loads (read-once data: bypass L1 so it stays free for the x gathers) -------------
@@ -110,9 +113,15 @@ struct RowBlock {
     int ka;      // k0 rounded down to FCT_ALIGN: shared index = k - ka
 };
 
-__device__ __forceinline__ RowBlock row_block(const int32_t* __restrict__ rowptr, int row_begin, int row_end) {
+// Row-block kernels are persistent: a fixed grid (SM count x resident CTAs) strides over the row blocks, so a
+// launch that has nothing to do (converged Jacobi sweep) costs microseconds instead of a 65k-CTA empty grid.
+#define FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end)                                                    \
+    for (int blk = blockIdx.x, nblk__ = ((row_end) - (row_begin) + FCT_RB - 1) / FCT_RB; blk < nblk__; \
+         blk += gridDim.x)
+
+__device__ __forceinline__ RowBlock row_block(const int32_t* __restrict__ rowptr, int row_begin, int row_end, int blk) {
     RowBlock b;
-    b.r0 = row_begin + blockIdx.x * FCT_RB;
+    b.r0 = row_begin + blk * FCT_RB;
     b.nr = min(FCT_RB, row_end - b.r0);
     b.k0 = rowptr[b.r0];
     b.k1 = rowptr[b.r0 + b.nr];

@@ -155,6 +155,11 @@ extern "C" int fct_ctx_create(fct_ctx** out, int device, int32_t n, const int32_
         if (len < 1) { delete c; FCT_CHECK(false, "fct_ctx_create: row %d is empty", r); }
     }
     c->cap = ((cap + 3) & ~3) + 4;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)
+            c->grid_cap = prop.multiProcessorCount * 8;
+    }
     c->max_row = maxrow;
     int rc = 0;
     rc |= dev_alloc(&c->rowptr, (size_t)n + 1);

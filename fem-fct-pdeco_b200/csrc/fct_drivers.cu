@@ -199,12 +199,13 @@ k_pcg_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colid
     double* sA = reinterpret_cast<double*>(fct_smem);
     int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
     __shared__ double sred[FCT_RB / 32];
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    const double beta = first ? 0.0 : sc[S_RZN] / sc[S_RZ];
+    double v = 0.0;
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
     stage_f64(sA, Av, b, nnz);
     stage_s32(sC, colidx, b, nnz);
     __syncthreads();
-    const double beta = first ? 0.0 : sc[S_RZN] / sc[S_RZ];
-    double v = 0.0;
     if ((int)threadIdx.x < b.nr) {
         const int r = b.r0 + threadIdx.x;
         const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
@@ -217,7 +218,9 @@ k_pcg_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colid
         const double pr = first ? z[r] : (z[r] + beta * p[r]);
         pnew[r] = pr;
         q[r] = acc;
-        v = pr * acc;
+        v += pr * acc;
+    }
+    __syncthreads();
     }
     const double s = block_sum(v, sred);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
@@ -256,11 +259,12 @@ k_krylov_init(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     double* sA = reinterpret_cast<double*>(fct_smem);
     int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
     __shared__ double sred[FCT_RB / 32];
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    double vrz = 0.0, vrr = 0.0, vbb = 0.0;
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
     stage_f64(sA, Av, b, nnz);
     stage_s32(sC, colidx, b, nnz);
     __syncthreads();
-    double vrz = 0.0, vrr = 0.0, vbb = 0.0;
     if ((int)threadIdx.x < b.nr) {
         const int rr_ = b.r0 + threadIdx.x;
         const int ks = rowptr[rr_] - b.ka, ke = rowptr[rr_ + 1] - b.ka;
@@ -277,7 +281,9 @@ k_krylov_init(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
         dinv[rr_] = di;
         const double zi = ri * di;
         z[rr_] = zi;
-        vrz = ri * zi; vrr = ri * ri; vbb = bi * bi;
+        vrz += ri * zi; vrr += ri * ri; vbb += bi * bi;
+    }
+    __syncthreads();
     }
     const double s1 = block_sum(vrz, sred);
     const double s2 = block_sum(vrr, sred);

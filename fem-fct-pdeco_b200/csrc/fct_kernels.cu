@@ -21,18 +21,21 @@ k_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, c
        double* __restrict__ y, int row_begin, int row_end, int64_t nnz, int cap) {
     double* sA = reinterpret_cast<double*>(fct_smem);
     int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
-    stage_f64(sA, A, b, nnz);
-    stage_s32(sC, colidx, b, nnz);
-    __syncthreads();
-    if ((int)threadIdx.x < b.nr) {
-        const int r = b.r0 + threadIdx.x;
-        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
-        double acc = 0.0;
-        for (int k = ks; k < ke; ++k) acc += sA[k] * x[sC[k]];
-        double out = alpha * acc;
-        if (beta != 0.0) out += beta * z[r];
-        y[r] = out;
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+        const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
+        stage_f64(sA, A, b, nnz);
+        stage_s32(sC, colidx, b, nnz);
+        __syncthreads();
+        if ((int)threadIdx.x < b.nr) {
+            const int r = b.r0 + threadIdx.x;
+            const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+            double acc = 0.0;
+            for (int k = ks; k < ke; ++k) acc += sA[k] * x[sC[k]];
+            double out = alpha * acc;
+            if (beta != 0.0) out += beta * z[r];
+            y[r] = out;
+        }
+        __syncthreads();
     }
 }
 
@@ -56,19 +59,22 @@ k_cheb_iter(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             int has_old, int row_begin, int row_end, int64_t nnz, int cap) {
     double* sA = reinterpret_cast<double*>(fct_smem);
     int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
-    stage_f64(sA, Mv, b, nnz);
-    stage_s32(sC, colidx, b, nnz);
-    __syncthreads();
-    if ((int)threadIdx.x < b.nr) {
-        const int r = b.r0 + threadIdx.x;
-        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
-        double acc = 0.0;
-        for (int k = ks; k < ke; ++k) acc += sA[k] * ymid[sC[k]];
-        const double z = (g[r] - acc) / (dscale * Md[r]);
-        const double ym = ymid[r];
-        const double yo = has_old ? yold[r] : 0.0;
-        ynew[r] = omega * (z + ym - yo) + yo;
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+        const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
+        stage_f64(sA, Mv, b, nnz);
+        stage_s32(sC, colidx, b, nnz);
+        __syncthreads();
+        if ((int)threadIdx.x < b.nr) {
+            const int r = b.r0 + threadIdx.x;
+            const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+            double acc = 0.0;
+            for (int k = ks; k < ke; ++k) acc += sA[k] * ymid[sC[k]];
+            const double z = (g[r] - acc) / (dscale * Md[r]);
+            const double ym = ymid[r];
+            const double yo = has_old ? yold[r] : 0.0;
+            ynew[r] = omega * (z + ym - yo) + yo;
+        }
+        __syncthreads();
     }
 }
 
@@ -96,13 +102,14 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
     int32_t* sC = reinterpret_cast<int32_t*>(sS + (S ? cap : 0));
     int32_t* sT = sC + cap;
     __shared__ double sred[FCT_RB / 32];
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    double rowsum = 1e300;
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
     stage_f64(sA, A, b, nnz);
     if (S) stage_f64(sS, S, b, nnz);
     stage_s32(sC, colidx, b, nnz);
     stage_s32(sT, tpos, b, nnz);
     __syncthreads();
-    double rowsum = 1e300;
     if ((int)threadIdx.x < b.nr) {
         const int r = b.r0 + threadIdx.x;
         const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
@@ -131,12 +138,14 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             sA[kd] = l;
             sD[kd] = dii;
         }
-        rowsum = lsum;
+        rowsum = fmin(rowsum, lsum);
         bvec[r] = ML[r] * un[r] + (rhs ? dt * rhs[r] : 0.0);
     }
     __syncthreads();
     unstage_f64(Lv, sA, b);
     unstage_f64(Dv, sD, b);
+    __syncthreads();
+    }
     const double m = block_min(rowsum, sred);
     if (threadIdx.x == 0) atomicMin(min_rowsum_key, f64_sort_key(m));
 }
@@ -148,7 +157,8 @@ k_art_diff(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colid
     double* sA = reinterpret_cast<double*>(fct_smem);
     int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
     int32_t* sT = sC + cap;
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
     stage_f64(sA, mat, b, nnz);
     stage_s32(sC, colidx, b, nnz);
     stage_s32(sT, tpos, b, nnz);
@@ -168,6 +178,8 @@ k_art_diff(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colid
     }
     __syncthreads();
     unstage_f64(Dv, sA, b);
+    __syncthreads();
+    }
 }
 
 // One Jacobi sweep x_new = (b - sum_{j != i} l_ij x_j) / l_ii.  Skipped once jstate[3] (converged) is set.
@@ -180,11 +192,12 @@ k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
     double* sA = reinterpret_cast<double*>(fct_smem);
     int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
     __shared__ double sred[FCT_RB / 32];
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    double delta = 0.0, xa = 0.0;
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
     stage_f64(sA, Lv, b, nnz);
     stage_s32(sC, colidx, b, nnz);
     __syncthreads();
-    double delta = 0.0, xa = 0.0;
     if ((int)threadIdx.x < b.nr) {
         const int r = b.r0 + threadIdx.x;
         const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
@@ -198,9 +211,11 @@ k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
         const double xn = (bvec[r] - acc) / diag;
         xnew[r] = xn;
         if (check) {
-            delta = fabs(xn - x[r]);
-            xa = fabs(xn);
+            delta = fmax(delta, fabs(xn - x[r]));
+            xa = fmax(xa, fabs(xn));
         }
+    }
+    __syncthreads();
     }
     if (check) {
         const double dm = block_max(delta, sred);
@@ -241,7 +256,8 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     double* sM = reinterpret_cast<double*>(fct_smem);
     double* sD = sM + cap;
     int32_t* sC = reinterpret_cast<int32_t*>(sD + cap);
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
     stage_f64(sM, Mv, b, nnz);
     stage_f64(sD, Dv, b, nnz);
     stage_s32(sC, colidx, b, nnz);
@@ -266,6 +282,8 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
         Rpos[r] = (pp != 0.0) ? fmin(1.0, ml * qp / (dt * pp)) : 1.0;
         Rneg[r] = (pn != 0.0) ? fmin(1.0, ml * qn / (dt * pn)) : 1.0;
     }
+    __syncthreads();
+    }
 }
 
 // Zalesak limiter, pass 2 (helpers.py:1860-1870): alpha_ij, limited sum, explicit correction.
@@ -277,7 +295,8 @@ k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col
     double* sM = reinterpret_cast<double*>(fct_smem);
     double* sD = sM + cap;
     int32_t* sC = reinterpret_cast<int32_t*>(sD + cap);
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
     stage_f64(sM, Mv, b, nnz);
     stage_f64(sD, Dv, b, nnz);
     stage_s32(sC, colidx, b, nnz);
@@ -297,6 +316,8 @@ k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col
         }
         uout[r] = uli + dt * fbar / ML[r];
     }
+    __syncthreads();
+    }
 }
 
 // out_i = sum_j mat_ij  (row_lump, helpers.py:309-328); optionally also the diagonal
@@ -305,7 +326,8 @@ k_row_lump(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colid
            double* __restrict__ out, double* __restrict__ diag_out, int row_begin, int row_end, int64_t nnz, int cap) {
     double* sA = reinterpret_cast<double*>(fct_smem);
     int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
     stage_f64(sA, A, b, nnz);
     stage_s32(sC, colidx, b, nnz);
     __syncthreads();
@@ -320,6 +342,8 @@ k_row_lump(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colid
         if (out) out[r] = acc;
         if (diag_out) diag_out[r] = dg;
     }
+    __syncthreads();
+    }
 }
 
 // partial[blockIdx] = sum over the block's rows of w * x_i (M y)_i   (deterministic two-stage reduction)
@@ -330,11 +354,12 @@ k_dot_M(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, 
     double* sA = reinterpret_cast<double*>(fct_smem);
     int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
     __shared__ double sred[FCT_RB / 32];
-    const RowBlock b = row_block(rowptr, row_begin, row_end);
+    double v = 0.0;
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
     stage_f64(sA, Mv, b, nnz);
     stage_s32(sC, colidx, b, nnz);
     __syncthreads();
-    double v = 0.0;
     if ((int)threadIdx.x < b.nr) {
         const int r = b.r0 + threadIdx.x;
         const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
@@ -345,7 +370,9 @@ k_dot_M(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, 
             acc += sA[k] * yc;
         }
         const double xr = xt ? (x[r] - xt[r]) : x[r];
-        v = xr * acc;
+        v += xr * acc;
+    }
+    __syncthreads();
     }
     const double s = block_sum(v, sred);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
@@ -406,7 +433,7 @@ static inline size_t smem_bytes(const fct_ctx* c, int nf64, int ns32) {
 
 #define LAUNCH_ROWS(ctx, kern, nf64, ns32, ...)                                                          \
     do {                                                                                                 \
-        const int nb__ = fct_nblocks(ctx);                                                               \
+        const int nb__ = fct_grid(ctx, fct_nblocks(ctx));                                                \
         if (nb__ > 0) {                                                                                  \
             kern<<<nb__, FCT_RB, smem_bytes(ctx, nf64, ns32), (ctx)->stream>>>(__VA_ARGS__);             \
             (ctx)->launches++;                                                                           \
@@ -630,7 +657,7 @@ extern "C" int fct_step_host(fct_ctx* ctx, const double* A, double sign, const d
 extern "C" int fct_dot_M(fct_ctx* ctx, const double* M, const double* x, const double* y, double* out_host) {
     FCT_CHECK(ctx && M && x && y && out_host, "fct_dot_M: null argument");
     double* partial = ctx->w[0];
-    const int nb = fct_nblocks(ctx);
+    const int nb = fct_grid(ctx, fct_nblocks(ctx));
     LAUNCH_ROWS(ctx, k_dot_M, 1, 1, ctx->rowptr, ctx->colidx, M, x, (const double*)nullptr, y, (const double*)nullptr,
                 partial, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
     k_reduce_partials<<<1, FCT_RB, 0, ctx->stream>>>(partial, nb, 1.0, ctx->red, 0);
@@ -647,7 +674,7 @@ extern "C" int fct_norm_sq_Q(fct_ctx* ctx, const double* M, const double* phi, c
                              int32_t num_steps, double dt, double* out_host) {
     FCT_CHECK(ctx && M && phi && out_host && num_steps >= 0, "fct_norm_sq_Q: bad argument");
     double* partial = ctx->w[0];
-    const int nb = fct_nblocks(ctx);
+    const int nb = fct_grid(ctx, fct_nblocks(ctx));
     // helpers.py:354-359: sum_k w_k phi_k^T M phi_k * dt, w_0 = w_N = 1/2
     for (int k = 0; k <= num_steps; ++k) {
         const double* p = phi + (size_t)k * ctx->n;
