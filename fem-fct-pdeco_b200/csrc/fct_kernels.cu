@@ -9,30 +9,43 @@
 //   helpers.py:1818-1851 fluxes, P+-, Q+-, R+-   -> k_flux_limits
 //   helpers.py:1860-1870 limited sum + update    -> k_flux_apply
 #include "fct_common.cuh"
+#include "fct_pipe.cuh"
 #include "../../include/fctpdeco.h"
 
 // dynamic shared memory layout helpers ---------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char fct_smem[];
+
+#define FCT_NST 3   // ring stages of the TMA pipeline
 
 // y = alpha * A x + beta * z
 __global__ void __launch_bounds__(FCT_RB)
 k_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ A,
        const double* __restrict__ x, double alpha, double beta, const double* __restrict__ z,
        double* __restrict__ y, int row_begin, int row_end, int64_t nnz, int cap) {
-    double* sA = reinterpret_cast<double*>(fct_smem);
-    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
-    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
-        const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
-        stage_f64(sA, A, b, nnz);
-        stage_s32(sC, colidx, b, nnz);
-        __syncthreads();
-        if ((int)threadIdx.x < b.nr) {
-            const int r = b.r0 + threadIdx.x;
-            const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+    __shared__ __align__(8) uint64_t bars[FCT_NST];
+    RowPipe<1, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {A}, {colidx}};
+    const int nmine = pipe.my_blocks();
+    pipe.init();
+    pipe.prologue(nmine);
+    for (int i = 0; i < nmine; ++i) {
+        pipe.prefetch(i, nmine);
+        const RowBlock b = pipe.block(i);
+        const bool act = (int)threadIdx.x < b.nr;
+        const int r = b.r0 + threadIdx.x;
+        int ks = 0, ke = 0;
+        double zr = 0.0;
+        if (act) {
+            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
+            if (beta != 0.0) zr = z[r];
+        }
+        pipe.wait(i, b);
+        if (act) {
+            const double* sA = pipe.f64(i % FCT_NST, 0);
+            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
             double acc = 0.0;
             for (int k = ks; k < ke; ++k) acc += sA[k] * x[sC[k]];
             double out = alpha * acc;
-            if (beta != 0.0) out += beta * z[r];
+            if (beta != 0.0) out += beta * zr;
             y[r] = out;
         }
         __syncthreads();
@@ -57,21 +70,30 @@ k_cheb_iter(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             const double* __restrict__ Md, const double* __restrict__ g, const double* __restrict__ ymid,
             const double* __restrict__ yold, double* __restrict__ ynew, double omega, double dscale,
             int has_old, int row_begin, int row_end, int64_t nnz, int cap) {
-    double* sA = reinterpret_cast<double*>(fct_smem);
-    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
-    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
-        const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
-        stage_f64(sA, Mv, b, nnz);
-        stage_s32(sC, colidx, b, nnz);
-        __syncthreads();
-        if ((int)threadIdx.x < b.nr) {
-            const int r = b.r0 + threadIdx.x;
-            const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
+    __shared__ __align__(8) uint64_t bars[FCT_NST];
+    RowPipe<1, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv}, {colidx}};
+    const int nmine = pipe.my_blocks();
+    pipe.init();
+    pipe.prologue(nmine);
+    for (int i = 0; i < nmine; ++i) {
+        pipe.prefetch(i, nmine);
+        const RowBlock b = pipe.block(i);
+        const bool act = (int)threadIdx.x < b.nr;
+        const int r = b.r0 + threadIdx.x;
+        int ks = 0, ke = 0;
+        double gr = 0.0, mdr = 1.0, ym = 0.0, yo = 0.0;
+        if (act) {      // the row's own vector entries: issued before the wait so that they overlap it
+            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
+            gr = g[r]; mdr = Md[r]; ym = ymid[r];
+            if (has_old) yo = yold[r];
+        }
+        pipe.wait(i, b);
+        if (act) {
+            const double* sA = pipe.f64(i % FCT_NST, 0);
+            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
             double acc = 0.0;
             for (int k = ks; k < ke; ++k) acc += sA[k] * ymid[sC[k]];
-            const double z = (g[r] - acc) / (dscale * Md[r]);
-            const double ym = ymid[r];
-            const double yo = has_old ? yold[r] : 0.0;
+            const double z = (gr - acc) / (dscale * mdr);
             ynew[r] = omega * (z + ym - yo) + yo;
         }
         __syncthreads();
@@ -189,33 +211,44 @@ k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
                const double* __restrict__ bvec, const double* __restrict__ x, double* __restrict__ xnew,
                unsigned long long* __restrict__ jstate, int check, int row_begin, int row_end, int64_t nnz, int cap) {
     if (*reinterpret_cast<volatile unsigned long long*>(jstate + 3)) return;
-    double* sA = reinterpret_cast<double*>(fct_smem);
-    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
+    __shared__ __align__(8) uint64_t bars[FCT_NST];
     __shared__ double sred[FCT_RB / 32];
+    RowPipe<1, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Lv}, {colidx}};
+    const int nmine = pipe.my_blocks();
+    pipe.init();
+    pipe.prologue(nmine);
     double delta = 0.0, xa = 0.0;
-    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
-    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
-    stage_f64(sA, Lv, b, nnz);
-    stage_s32(sC, colidx, b, nnz);
-    __syncthreads();
-    if ((int)threadIdx.x < b.nr) {
+    for (int i = 0; i < nmine; ++i) {
+        pipe.prefetch(i, nmine);
+        const RowBlock b = pipe.block(i);
+        const bool act = (int)threadIdx.x < b.nr;
         const int r = b.r0 + threadIdx.x;
-        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
-        double acc = 0.0, diag = 1.0;
-        for (int k = ks; k < ke; ++k) {
-            const int c = sC[k];
-            const double v = sA[k];
-            if (c == r) diag = v;
-            else acc += v * x[c];
+        int ks = 0, ke = 0;
+        double br = 0.0, xr = 0.0;
+        if (act) {
+            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
+            br = bvec[r];
+            if (check) xr = x[r];
         }
-        const double xn = (bvec[r] - acc) / diag;
-        xnew[r] = xn;
-        if (check) {
-            delta = fmax(delta, fabs(xn - x[r]));
-            xa = fmax(xa, fabs(xn));
+        pipe.wait(i, b);
+        if (act) {
+            const double* sA = pipe.f64(i % FCT_NST, 0);
+            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
+            double acc = 0.0, diag = 1.0;
+            for (int k = ks; k < ke; ++k) {
+                const int c = sC[k];
+                const double v = sA[k];
+                if (c == r) diag = v;
+                else acc += v * x[c];
+            }
+            const double xn = (br - acc) / diag;
+            xnew[r] = xn;
+            if (check) {
+                delta = fmax(delta, fabs(xn - xr));
+                xa = fmax(xa, fabs(xn));
+            }
         }
-    }
-    __syncthreads();
+        __syncthreads();
     }
     if (check) {
         const double dm = block_max(delta, sred);
@@ -253,36 +286,43 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
               const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
               const double* __restrict__ ulow, double dt, double* __restrict__ Rpos, double* __restrict__ Rneg,
               int row_begin, int row_end, int64_t nnz, int cap) {
-    double* sM = reinterpret_cast<double*>(fct_smem);
-    double* sD = sM + cap;
-    int32_t* sC = reinterpret_cast<int32_t*>(sD + cap);
-    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
-    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
-    stage_f64(sM, Mv, b, nnz);
-    stage_f64(sD, Dv, b, nnz);
-    stage_s32(sC, colidx, b, nnz);
-    __syncthreads();
-    if ((int)threadIdx.x < b.nr) {
+    __shared__ __align__(8) uint64_t bars[FCT_NST];
+    RowPipe<2, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv, Dv}, {colidx}};
+    const int nmine = pipe.my_blocks();
+    pipe.init();
+    pipe.prologue(nmine);
+    for (int i = 0; i < nmine; ++i) {
+        pipe.prefetch(i, nmine);
+        const RowBlock b = pipe.block(i);
+        const bool act = (int)threadIdx.x < b.nr;
         const int r = b.r0 + threadIdx.x;
-        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
-        const double udi = udot[r], uli = ulow[r];
-        double pp = 0.0, pn = 0.0, umax = uli, umin = uli;
-        for (int k = ks; k < ke; ++k) {
-            const int c = sC[k];
-            if (c == r) continue;
-            const double ulj = ulow[c];
-            const double f = sM[k] * (udi - udot[c]) + sD[k] * (uli - ulj);
-            pp += fmax(f, 0.0);
-            pn += fmin(f, 0.0);
-            umax = fmax(umax, ulj);
-            umin = fmin(umin, ulj);
+        int ks = 0, ke = 0;
+        double udi = 0.0, uli = 0.0, ml = 1.0;
+        if (act) {
+            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
+            udi = udot[r]; uli = ulow[r]; ml = ML[r];
         }
-        const double qp = umax - uli, qn = umin - uli;
-        const double ml = ML[r];
-        Rpos[r] = (pp != 0.0) ? fmin(1.0, ml * qp / (dt * pp)) : 1.0;
-        Rneg[r] = (pn != 0.0) ? fmin(1.0, ml * qn / (dt * pn)) : 1.0;
-    }
-    __syncthreads();
+        pipe.wait(i, b);
+        if (act) {
+            const double* sM = pipe.f64(i % FCT_NST, 0);
+            const double* sD = pipe.f64(i % FCT_NST, 1);
+            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
+            double pp = 0.0, pn = 0.0, umax = uli, umin = uli;
+            for (int k = ks; k < ke; ++k) {
+                const int c = sC[k];
+                if (c == r) continue;
+                const double ulj = ulow[c];
+                const double f = sM[k] * (udi - udot[c]) + sD[k] * (uli - ulj);
+                pp += fmax(f, 0.0);
+                pn += fmin(f, 0.0);
+                umax = fmax(umax, ulj);
+                umin = fmin(umin, ulj);
+            }
+            const double qp = umax - uli, qn = umin - uli;
+            Rpos[r] = (pp != 0.0) ? fmin(1.0, ml * qp / (dt * pp)) : 1.0;
+            Rneg[r] = (pn != 0.0) ? fmin(1.0, ml * qn / (dt * pn)) : 1.0;
+        }
+        __syncthreads();
     }
 }
 
@@ -292,31 +332,38 @@ k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col
              const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
              const double* __restrict__ ulow, const double* __restrict__ Rpos, const double* __restrict__ Rneg,
              double dt, double* __restrict__ uout, int row_begin, int row_end, int64_t nnz, int cap) {
-    double* sM = reinterpret_cast<double*>(fct_smem);
-    double* sD = sM + cap;
-    int32_t* sC = reinterpret_cast<int32_t*>(sD + cap);
-    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
-    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
-    stage_f64(sM, Mv, b, nnz);
-    stage_f64(sD, Dv, b, nnz);
-    stage_s32(sC, colidx, b, nnz);
-    __syncthreads();
-    if ((int)threadIdx.x < b.nr) {
+    __shared__ __align__(8) uint64_t bars[FCT_NST];
+    RowPipe<2, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv, Dv}, {colidx}};
+    const int nmine = pipe.my_blocks();
+    pipe.init();
+    pipe.prologue(nmine);
+    for (int i = 0; i < nmine; ++i) {
+        pipe.prefetch(i, nmine);
+        const RowBlock b = pipe.block(i);
+        const bool act = (int)threadIdx.x < b.nr;
         const int r = b.r0 + threadIdx.x;
-        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
-        const double udi = udot[r], uli = ulow[r];
-        const double rpi = Rpos[r], rni = Rneg[r];
-        double fbar = 0.0;
-        for (int k = ks; k < ke; ++k) {
-            const int c = sC[k];
-            if (c == r) continue;
-            const double f = sM[k] * (udi - udot[c]) + sD[k] * (uli - ulow[c]);
-            const double alpha = (f > 0.0) ? fmin(rpi, Rneg[c]) : fmin(rni, Rpos[c]);
-            fbar += alpha * f;
+        int ks = 0, ke = 0;
+        double udi = 0.0, uli = 0.0, ml = 1.0, rpi = 1.0, rni = 1.0;
+        if (act) {
+            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
+            udi = udot[r]; uli = ulow[r]; ml = ML[r]; rpi = Rpos[r]; rni = Rneg[r];
         }
-        uout[r] = uli + dt * fbar / ML[r];
-    }
-    __syncthreads();
+        pipe.wait(i, b);
+        if (act) {
+            const double* sM = pipe.f64(i % FCT_NST, 0);
+            const double* sD = pipe.f64(i % FCT_NST, 1);
+            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
+            double fbar = 0.0;
+            for (int k = ks; k < ke; ++k) {
+                const int c = sC[k];
+                if (c == r) continue;
+                const double f = sM[k] * (udi - udot[c]) + sD[k] * (uli - ulow[c]);
+                const double alpha = (f > 0.0) ? fmin(rpi, Rneg[c]) : fmin(rni, Rpos[c]);
+                fbar += alpha * f;
+            }
+            uout[r] = uli + dt * fbar / ml;
+        }
+        __syncthreads();
     }
 }
 
@@ -346,33 +393,42 @@ k_row_lump(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colid
     }
 }
 
-// partial[blockIdx] = sum over the block's rows of w * x_i (M y)_i   (deterministic two-stage reduction)
+// partial[blockIdx] = sum over the CTA's rows of x_i (M y)_i   (deterministic two-stage reduction)
 __global__ void __launch_bounds__(FCT_RB)
 k_dot_M(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Mv,
         const double* __restrict__ x, const double* __restrict__ xt, const double* __restrict__ y,
         const double* __restrict__ yt, double* __restrict__ partial, int row_begin, int row_end, int64_t nnz, int cap) {
-    double* sA = reinterpret_cast<double*>(fct_smem);
-    int32_t* sC = reinterpret_cast<int32_t*>(sA + cap);
+    __shared__ __align__(8) uint64_t bars[FCT_NST];
     __shared__ double sred[FCT_RB / 32];
+    RowPipe<1, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv}, {colidx}};
+    const int nmine = pipe.my_blocks();
+    pipe.init();
+    pipe.prologue(nmine);
     double v = 0.0;
-    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
-    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
-    stage_f64(sA, Mv, b, nnz);
-    stage_s32(sC, colidx, b, nnz);
-    __syncthreads();
-    if ((int)threadIdx.x < b.nr) {
+    for (int i = 0; i < nmine; ++i) {
+        pipe.prefetch(i, nmine);
+        const RowBlock b = pipe.block(i);
+        const bool act = (int)threadIdx.x < b.nr;
         const int r = b.r0 + threadIdx.x;
-        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
-        double acc = 0.0;
-        for (int k = ks; k < ke; ++k) {
-            const int c = sC[k];
-            const double yc = yt ? (y[c] - yt[c]) : y[c];
-            acc += sA[k] * yc;
+        int ks = 0, ke = 0;
+        double xr = 0.0;
+        if (act) {
+            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
+            xr = xt ? (x[r] - xt[r]) : x[r];
         }
-        const double xr = xt ? (x[r] - xt[r]) : x[r];
-        v += xr * acc;
-    }
-    __syncthreads();
+        pipe.wait(i, b);
+        if (act) {
+            const double* sA = pipe.f64(i % FCT_NST, 0);
+            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
+            double acc = 0.0;
+            for (int k = ks; k < ke; ++k) {
+                const int c = sC[k];
+                const double yc = yt ? (y[c] - yt[c]) : y[c];
+                acc += sA[k] * yc;
+            }
+            v += xr * acc;
+        }
+        __syncthreads();
     }
     const double s = block_sum(v, sred);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
@@ -440,6 +496,21 @@ static inline size_t smem_bytes(const fct_ctx* c, int nf64, int ns32) {
         }                                                                                                \
     } while (0)
 
+// TMA-ring kernels: FCT_NST stages of (nf64 fp64 + ns32 int32) staged arrays; persistent grid = SMs x resident CTAs
+static inline int pipe_grid(const fct_ctx* c, int nf64) {
+    const int cap = (nf64 >= 2) ? c->grid_pipe2 : c->grid_pipe1;
+    const int nb = fct_nblocks(c);
+    return nb < cap ? nb : cap;
+}
+#define LAUNCH_PIPE(ctx, kern, nf64, ns32, ...)                                                          \
+    do {                                                                                                 \
+        const int nb__ = pipe_grid(ctx, nf64);                                                           \
+        if (nb__ > 0) {                                                                                  \
+            kern<<<nb__, FCT_RB, FCT_NST * smem_bytes(ctx, nf64, ns32), (ctx)->stream>>>(__VA_ARGS__);   \
+            (ctx)->launches++;                                                                           \
+        }                                                                                                \
+    } while (0)
+
 int fct_launch_error(fct_ctx* ctx, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -464,6 +535,17 @@ int fct_kernels_configure(fct_ctx* ctx) {
     FCT_CUDA(cudaFuncSetAttribute(k_flux_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_row_lump, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_dot_M, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CHECK(FCT_NST * smem_bytes(ctx, 2, 1) <= (size_t)FCT_SMEM_OPTIN,
+              "row blocks need %zu B of shared memory for the TMA ring (max row %d): unsupported pattern",
+              FCT_NST * smem_bytes(ctx, 2, 1), ctx->max_row);
+    cudaDeviceProp prop;
+    FCT_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+    int occ1 = 0, occ2 = 0;
+    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_cheb_iter, FCT_RB, FCT_NST * smem_bytes(ctx, 1, 1)));
+    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_flux_apply, FCT_RB, FCT_NST * smem_bytes(ctx, 2, 1)));
+    FCT_CHECK(occ1 >= 1 && occ2 >= 1, "TMA-ring kernels do not fit on an SM (cap=%d)", ctx->cap);
+    ctx->grid_pipe1 = prop.multiProcessorCount * occ1;
+    ctx->grid_pipe2 = prop.multiProcessorCount * occ2;
     return 0;
 }
 
@@ -490,7 +572,7 @@ extern "C" int fct_spmv(fct_ctx* ctx, const double* A, const double* x, double a
                         double* y) {
     FCT_CHECK(ctx && A && x && y, "fct_spmv: null argument");
     FCT_CHECK(beta == 0.0 || z, "fct_spmv: beta != 0 needs z");
-    LAUNCH_ROWS(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, x, alpha, beta, z, y, ctx->row_begin, ctx->row_end,
+    LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, x, alpha, beta, z, y, ctx->row_begin, ctx->row_end,
                 ctx->nnz, ctx->cap);
     return fct_launch_error(ctx, "fct_spmv");
 }
@@ -521,7 +603,7 @@ extern "C" int fct_chebsi(fct_ctx* ctx, const double* M, const double* Md, const
                 ctx->launches++;
             }
         } else {
-            LAUNCH_ROWS(ctx, k_cheb_iter, 1, 1, ctx->rowptr, ctx->colidx, M, Md, b, ymid, yold, ynew, omega, dscale,
+            LAUNCH_PIPE(ctx, k_cheb_iter, 1, 1, ctx->rowptr, ctx->colidx, M, Md, b, ymid, yold, ynew, omega, dscale,
                         yold != nullptr, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
         }
         if (k < iters) {
@@ -559,10 +641,10 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, double* x,
                      int max_sweeps) {
     const int pairs = (max_sweeps + 1) / 2;
     for (int p = 0; p < pairs; ++p) {
-        LAUNCH_ROWS(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0, ctx->row_begin,
+        LAUNCH_PIPE(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0, ctx->row_begin,
                     ctx->row_end, ctx->nnz, ctx->cap);
         if (fct_halo_exchange_if(ctx, tmp)) return 1;
-        LAUNCH_ROWS(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, tmp, x, ctx->jstate, 1, ctx->row_begin,
+        LAUNCH_PIPE(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, tmp, x, ctx->jstate, 1, ctx->row_begin,
                     ctx->row_end, ctx->nnz, ctx->cap);
         if (fct_halo_exchange_if(ctx, x)) return 1;
         if (fct_halo_allreduce_max2(ctx, ctx->jstate)) return 1;
@@ -612,17 +694,17 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     FCT_CUDA(cudaMemcpyAsync(ulow, un, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
     if (fct_jacobi_solve(ctx, ctx->Lvals, bvec, ulow, tmp, ctx->rtol, ctx->max_sweeps)) return 1;
     // 4. g = -(sign A) u_low + rhs ; udot = ChebSI(g)
-    LAUNCH_ROWS(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, ulow, -sign, rhs ? 1.0 : 0.0, rhs, g, ctx->row_begin,
+    LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, ulow, -sign, rhs ? 1.0 : 0.0, rhs, g, ctx->row_begin,
                 ctx->row_end, ctx->nnz, ctx->cap);
     if (fct_chebsi(ctx, ctx->M, ctx->Mdiag, g, udot, 20, 0.5, 2.0)) return 1;
     if (fct_halo_exchange_if(ctx, udot)) return 1;
     // 5-7. fluxes, P, Q, R
-    LAUNCH_ROWS(ctx, k_flux_limits, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, dt, Rp, Rn,
+    LAUNCH_PIPE(ctx, k_flux_limits, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, dt, Rp, Rn,
                 ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
     if (fct_halo_exchange_if(ctx, Rp)) return 1;
     if (fct_halo_exchange_if(ctx, Rn)) return 1;
     // 8-9. limited sum + update
-    LAUNCH_ROWS(ctx, k_flux_apply, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, Rp, Rn, dt,
+    LAUNCH_PIPE(ctx, k_flux_apply, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, Rp, Rn, dt,
                 uout, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
     if (fct_launch_error(ctx, "fct_step")) return 1;
     if (fct_halo_exchange_if(ctx, uout)) return 1;
@@ -657,8 +739,8 @@ extern "C" int fct_step_host(fct_ctx* ctx, const double* A, double sign, const d
 extern "C" int fct_dot_M(fct_ctx* ctx, const double* M, const double* x, const double* y, double* out_host) {
     FCT_CHECK(ctx && M && x && y && out_host, "fct_dot_M: null argument");
     double* partial = ctx->w[0];
-    const int nb = fct_grid(ctx, fct_nblocks(ctx));
-    LAUNCH_ROWS(ctx, k_dot_M, 1, 1, ctx->rowptr, ctx->colidx, M, x, (const double*)nullptr, y, (const double*)nullptr,
+    const int nb = pipe_grid(ctx, 1);
+    LAUNCH_PIPE(ctx, k_dot_M, 1, 1, ctx->rowptr, ctx->colidx, M, x, (const double*)nullptr, y, (const double*)nullptr,
                 partial, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
     k_reduce_partials<<<1, FCT_RB, 0, ctx->stream>>>(partial, nb, 1.0, ctx->red, 0);
     ctx->launches++;
@@ -674,13 +756,13 @@ extern "C" int fct_norm_sq_Q(fct_ctx* ctx, const double* M, const double* phi, c
                              int32_t num_steps, double dt, double* out_host) {
     FCT_CHECK(ctx && M && phi && out_host && num_steps >= 0, "fct_norm_sq_Q: bad argument");
     double* partial = ctx->w[0];
-    const int nb = fct_grid(ctx, fct_nblocks(ctx));
+    const int nb = pipe_grid(ctx, 1);
     // helpers.py:354-359: sum_k w_k phi_k^T M phi_k * dt, w_0 = w_N = 1/2
     for (int k = 0; k <= num_steps; ++k) {
         const double* p = phi + (size_t)k * ctx->n;
         const double* t = target ? target + (size_t)k * ctx->n : nullptr;
         const double wk = (k == 0 || k == num_steps) ? 0.5 : 1.0;
-        LAUNCH_ROWS(ctx, k_dot_M, 1, 1, ctx->rowptr, ctx->colidx, M, p, t, p, t, partial, ctx->row_begin, ctx->row_end,
+        LAUNCH_PIPE(ctx, k_dot_M, 1, 1, ctx->rowptr, ctx->colidx, M, p, t, p, t, partial, ctx->row_begin, ctx->row_end,
                     ctx->nnz, ctx->cap);
         k_reduce_partials<<<1, FCT_RB, 0, ctx->stream>>>(partial, nb, wk, ctx->red, k > 0);
         ctx->launches++;
