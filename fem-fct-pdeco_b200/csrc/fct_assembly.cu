@@ -38,15 +38,22 @@ struct CellGeom {
     double detJ, area;
 };
 
-__device__ __forceinline__ CellGeom cell_geom(const int32_t* __restrict__ cells, const double* __restrict__ xy, int c) {
+// Geometry of cell c seen from its vertex r: the vertices are rotated cyclically (orientation preserved) so that
+// r is local vertex 0 -- every per-vertex array is then indexed with compile-time constants and stays in registers.
+__device__ __forceinline__ CellGeom cell_geom(const int32_t* __restrict__ cells, const double* __restrict__ xy, int c,
+                                              int r) {
     CellGeom g;
-    g.d[0] = cells[3 * c]; g.d[1] = cells[3 * c + 1]; g.d[2] = cells[3 * c + 2];
-    const double2 p0 = reinterpret_cast<const double2*>(xy)[g.d[0]];
-    const double2 p1 = reinterpret_cast<const double2*>(xy)[g.d[1]];
-    const double2 p2 = reinterpret_cast<const double2*>(xy)[g.d[2]];
+    const int d0 = __ldg(cells + 3 * c), d1 = __ldg(cells + 3 * c + 1), d2 = __ldg(cells + 3 * c + 2);
+    if (d0 == r) { g.d[0] = d0; g.d[1] = d1; g.d[2] = d2; }
+    else if (d1 == r) { g.d[0] = d1; g.d[1] = d2; g.d[2] = d0; }
+    else { g.d[0] = d2; g.d[1] = d0; g.d[2] = d1; }
+    const double2 p0 = __ldg(reinterpret_cast<const double2*>(xy) + g.d[0]);
+    const double2 p1 = __ldg(reinterpret_cast<const double2*>(xy) + g.d[1]);
+    const double2 p2 = __ldg(reinterpret_cast<const double2*>(xy) + g.d[2]);
     const double det = (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
-    g.gx[1] = (p2.y - p0.y) / det;  g.gy[1] = -(p2.x - p0.x) / det;
-    g.gx[2] = -(p1.y - p0.y) / det; g.gy[2] = (p1.x - p0.x) / det;
+    const double inv = 1.0 / det;
+    g.gx[1] = (p2.y - p0.y) * inv;  g.gy[1] = -(p2.x - p0.x) * inv;
+    g.gx[2] = -(p1.y - p0.y) * inv; g.gy[2] = (p1.x - p0.x) * inv;
     g.gx[0] = -(g.gx[1] + g.gx[2]); g.gy[0] = -(g.gy[1] + g.gy[2]);
     g.detJ = fabs(det);
     g.area = 0.5 * g.detJ;
@@ -167,16 +174,20 @@ k_assemble_matrix(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     if ((int)threadIdx.x < b.nr) {
         const int r = b.r0 + threadIdx.x;
         const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
-        for (int k = ks; k < ke; ++k) sV[k] = 0.0;
+        int kd = ks;
+        for (int k = ks; k < ke; ++k) {
+            sV[k] = 0.0;
+            if (sC[k] == r) kd = k;
+        }
         const int cs = v2c_ptr[r], ce = v2c_ptr[r + 1];
         for (int ci = cs; ci < ce; ++ci) {
             const int c = v2c_idx[ci];
-            const CellGeom g = cell_geom(cells, xy, c);
-            const int a = (g.d[0] == r) ? 0 : ((g.d[1] == r) ? 1 : 2);
+            const CellGeom g = cell_geom(cells, xy, c, r);
             double e[3];
-            element_row<KIND>(g, a, fa, e);
+            element_row<KIND>(g, 0, fa, e);
+            sV[kd] += e[0];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
+            for (int q = 1; q < 3; ++q) {
                 const int col = g.d[q];
                 for (int k = ks; k < ke; ++k)
                     if (sC[k] == col) { sV[k] += e[q]; break; }
@@ -241,9 +252,8 @@ k_assemble_vector(const int32_t* __restrict__ v2c_ptr, const int32_t* __restrict
     const int cs = v2c_ptr[r], ce = v2c_ptr[r + 1];
     for (int ci = cs; ci < ce; ++ci) {
         const int c = v2c_idx[ci];
-        const CellGeom g = cell_geom(cells, xy, c);
-        const int a = (g.d[0] == r) ? 0 : ((g.d[1] == r) ? 1 : 2);
-        acc += element_load<KIND>(g, a, fa);
+        const CellGeom g = cell_geom(cells, xy, c, r);
+        acc += element_load<KIND>(g, 0, fa);
     }
     out[r] = accumulate ? (out[r] + scale * acc) : (scale * acc);
 }

@@ -15,7 +15,8 @@
 // dynamic shared memory layout helpers ---------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char fct_smem[];
 
-#define FCT_NST 3   // ring stages of the TMA pipeline
+#define FCT_NST 3    // ring stages of the TMA pipeline, kernels staging one fp64 array
+#define FCT_NST2 2   // ... kernels staging two fp64 arrays (leaves L1 room for the four gathered vectors)
 
 // y = alpha * A x + beta * z
 __global__ void __launch_bounds__(FCT_RB)
@@ -112,61 +113,74 @@ __device__ __forceinline__ unsigned long long f64_sort_key(double v) {
 //   b    = M_L u_n + dt rhs                     [helpers.py:1780]
 // `sign` folds the legacy FCT_alg convention (A -> -A, old_helpers.py:135-145) into the same kernel.
 // Outputs: Lv (full pattern), Dv (off-diagonals; diagonal slot holds d_ii), b; min row sum of L.
+// A (and S), colidx, tpos arrive through a 2-stage TMA ring; L and D leave through two staging buffers.
+#define FCT_NST_LOW 2
+template <int HAS_S>
 __global__ void __launch_bounds__(FCT_RB)
 k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ tpos,
             const double* __restrict__ A, double sign, const double* __restrict__ S, const double* __restrict__ ML,
             const double* __restrict__ un, const double* __restrict__ rhs, double dt,
             double* __restrict__ Lv, double* __restrict__ Dv, double* __restrict__ bvec,
             unsigned long long* __restrict__ min_rowsum_key, int row_begin, int row_end, int64_t nnz, int cap) {
-    double* sA = reinterpret_cast<double*>(fct_smem);      // A, then L
-    double* sD = sA + cap;                                  // D
-    double* sS = sD + cap;                                  // S (if any)
-    int32_t* sC = reinterpret_cast<int32_t*>(sS + (S ? cap : 0));
-    int32_t* sT = sC + cap;
+    __shared__ __align__(8) uint64_t bars[FCT_NST_LOW];
     __shared__ double sred[FCT_RB / 32];
+    RowPipe<1 + HAS_S, 2, FCT_NST_LOW> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {A}, {colidx, tpos}};
+    if (HAS_S) pipe.gf[HAS_S] = S;
+    double* sL = reinterpret_cast<double*>(fct_smem + FCT_NST_LOW * pipe.stage_bytes());
+    double* sD = sL + cap;
+    const int nmine = pipe.my_blocks();
+    pipe.init();
+    pipe.prologue(nmine);
     double rowsum = 1e300;
-    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
-    const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
-    stage_f64(sA, A, b, nnz);
-    if (S) stage_f64(sS, S, b, nnz);
-    stage_s32(sC, colidx, b, nnz);
-    stage_s32(sT, tpos, b, nnz);
-    __syncthreads();
-    if ((int)threadIdx.x < b.nr) {
+    for (int i = 0; i < nmine; ++i) {
+        pipe.prefetch(i, nmine);
+        const RowBlock b = pipe.block(i);
+        const bool act = (int)threadIdx.x < b.nr;
         const int r = b.r0 + threadIdx.x;
-        const int ks = rowptr[r] - b.ka, ke = rowptr[r + 1] - b.ka;
-        double dsum = 0.0, lsum = 0.0;
-        int kd = -1;
-        for (int k = ks; k < ke; ++k) {
-            const int c = sC[k];
-            if (c == r) { kd = k; continue; }
-            const double a = sign * sA[k];
-            const double at = sign * A[tpos ? sT[k] : 0];
-            const double d = fmax(0.0, fmax(a, at));
-            dsum += d;
-            double l = dt * (a - d);
-            if (S) l += dt * sS[k];
-            lsum += l;
-            sA[k] = l;
-            sD[k] = d;
+        int ks = 0, ke = 0;
+        double ml = 0.0, unr = 0.0, rr = 0.0;
+        if (act) {
+            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
+            ml = ML[r]; unr = un[r];
+            if (rhs) rr = rhs[r];
         }
-        // diagonal: d_ii = -sum_j d_ij
-        {
+        pipe.wait(i, b);
+        if (act) {
+            const int st = i % FCT_NST_LOW;
+            const double* sA = pipe.f64(st, 0);
+            const double* sS = pipe.f64(st, HAS_S ? 1 : 0);
+            const int32_t* sC = pipe.s32(st, 0);
+            const int32_t* sT = pipe.s32(st, 1);
+            double dsum = 0.0, lsum = 0.0;
+            int kd = ks;
+            for (int k = ks; k < ke; ++k) {
+                const int c = sC[k];
+                if (c == r) { kd = k; continue; }
+                const double a = sign * sA[k];
+                const double at = sign * A[sT[k]];
+                const double d = fmax(0.0, fmax(a, at));
+                dsum += d;
+                double l = dt * (a - d);
+                if (HAS_S) l += dt * sS[k];
+                lsum += l;
+                sL[k] = l;
+                sD[k] = d;
+            }
+            // diagonal: d_ii = -sum_j d_ij
             const double a = sign * sA[kd];
             const double dii = -dsum;
-            double l = ML[r] + dt * (a - dii);
-            if (S) l += dt * sS[kd];
+            double l = ml + dt * (a - dii);
+            if (HAS_S) l += dt * sS[kd];
             lsum += l;
-            sA[kd] = l;
+            sL[kd] = l;
             sD[kd] = dii;
+            rowsum = fmin(rowsum, lsum);
+            bvec[r] = ml * unr + (rhs ? dt * rr : 0.0);
         }
-        rowsum = fmin(rowsum, lsum);
-        bvec[r] = ML[r] * un[r] + (rhs ? dt * rhs[r] : 0.0);
-    }
-    __syncthreads();
-    unstage_f64(Lv, sA, b);
-    unstage_f64(Dv, sD, b);
-    __syncthreads();
+        __syncthreads();
+        unstage_f64(Lv, sL, b);
+        unstage_f64(Dv, sD, b);
+        __syncthreads();
     }
     const double m = block_min(rowsum, sred);
     if (threadIdx.x == 0) atomicMin(min_rowsum_key, f64_sort_key(m));
@@ -286,8 +300,8 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
               const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
               const double* __restrict__ ulow, double dt, double* __restrict__ Rpos, double* __restrict__ Rneg,
               int row_begin, int row_end, int64_t nnz, int cap) {
-    __shared__ __align__(8) uint64_t bars[FCT_NST];
-    RowPipe<2, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv, Dv}, {colidx}};
+    __shared__ __align__(8) uint64_t bars[FCT_NST2];
+    RowPipe<2, 1, FCT_NST2> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv, Dv}, {colidx}};
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
@@ -304,9 +318,9 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
         }
         pipe.wait(i, b);
         if (act) {
-            const double* sM = pipe.f64(i % FCT_NST, 0);
-            const double* sD = pipe.f64(i % FCT_NST, 1);
-            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
+            const double* sM = pipe.f64(i % FCT_NST2, 0);
+            const double* sD = pipe.f64(i % FCT_NST2, 1);
+            const int32_t* sC = pipe.s32(i % FCT_NST2, 0);
             double pp = 0.0, pn = 0.0, umax = uli, umin = uli;
             for (int k = ks; k < ke; ++k) {
                 const int c = sC[k];
@@ -332,8 +346,8 @@ k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col
              const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
              const double* __restrict__ ulow, const double* __restrict__ Rpos, const double* __restrict__ Rneg,
              double dt, double* __restrict__ uout, int row_begin, int row_end, int64_t nnz, int cap) {
-    __shared__ __align__(8) uint64_t bars[FCT_NST];
-    RowPipe<2, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv, Dv}, {colidx}};
+    __shared__ __align__(8) uint64_t bars[FCT_NST2];
+    RowPipe<2, 1, FCT_NST2> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv, Dv}, {colidx}};
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
@@ -350,9 +364,9 @@ k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col
         }
         pipe.wait(i, b);
         if (act) {
-            const double* sM = pipe.f64(i % FCT_NST, 0);
-            const double* sD = pipe.f64(i % FCT_NST, 1);
-            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
+            const double* sM = pipe.f64(i % FCT_NST2, 0);
+            const double* sD = pipe.f64(i % FCT_NST2, 1);
+            const int32_t* sC = pipe.s32(i % FCT_NST2, 0);
             double fbar = 0.0;
             for (int k = ks; k < ke; ++k) {
                 const int c = sC[k];
@@ -506,7 +520,7 @@ static inline int pipe_grid(const fct_ctx* c, int nf64) {
     do {                                                                                                 \
         const int nb__ = pipe_grid(ctx, nf64);                                                           \
         if (nb__ > 0) {                                                                                  \
-            kern<<<nb__, FCT_RB, FCT_NST * smem_bytes(ctx, nf64, ns32), (ctx)->stream>>>(__VA_ARGS__);   \
+            kern<<<nb__, FCT_RB, ((nf64) >= 2 ? FCT_NST2 : FCT_NST) * smem_bytes(ctx, nf64, ns32), (ctx)->stream>>>(__VA_ARGS__); \
             (ctx)->launches++;                                                                           \
         }                                                                                                \
     } while (0)
@@ -528,22 +542,31 @@ int fct_kernels_configure(fct_ctx* ctx) {
     const int w = FCT_SMEM_OPTIN;   // opt-in ceiling only (never lowered by a later, smaller context)
     FCT_CUDA(cudaFuncSetAttribute(k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_cheb_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
-    FCT_CUDA(cudaFuncSetAttribute(k_low_build, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_low_build<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_low_build<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_art_diff, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_flux_limits, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_flux_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_row_lump, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_dot_M, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
-    FCT_CHECK(FCT_NST * smem_bytes(ctx, 2, 1) <= (size_t)FCT_SMEM_OPTIN,
+    FCT_CHECK(FCT_NST_LOW * smem_bytes(ctx, 2, 2) + 2 * smem_bytes(ctx, 1, 0) <= (size_t)FCT_SMEM_OPTIN,
               "row blocks need %zu B of shared memory for the TMA ring (max row %d): unsupported pattern",
-              FCT_NST * smem_bytes(ctx, 2, 1), ctx->max_row);
+              FCT_NST_LOW * smem_bytes(ctx, 2, 2) + 2 * smem_bytes(ctx, 1, 0), ctx->max_row);
     cudaDeviceProp prop;
     FCT_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
     int occ1 = 0, occ2 = 0;
     FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_cheb_iter, FCT_RB, FCT_NST * smem_bytes(ctx, 1, 1)));
-    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_flux_apply, FCT_RB, FCT_NST * smem_bytes(ctx, 2, 1)));
+    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_flux_apply, FCT_RB, FCT_NST2 * smem_bytes(ctx, 2, 1)));
     FCT_CHECK(occ1 >= 1 && occ2 >= 1, "TMA-ring kernels do not fit on an SM (cap=%d)", ctx->cap);
+    int occl0 = 0, occl1 = 0;
+    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &occl0, k_low_build<0>, FCT_RB, FCT_NST_LOW * smem_bytes(ctx, 1, 2) + 2 * smem_bytes(ctx, 1, 0)));
+    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &occl1, k_low_build<1>, FCT_RB, FCT_NST_LOW * smem_bytes(ctx, 2, 2) + 2 * smem_bytes(ctx, 1, 0)));
+    FCT_CHECK(occl0 >= 1 && occl1 >= 1, "k_low_build does not fit on an SM (cap=%d)", ctx->cap);
+    ctx->grid_low[0] = prop.multiProcessorCount * occl0;
+    ctx->grid_low[1] = prop.multiProcessorCount * occl1;
     ctx->grid_pipe1 = prop.multiProcessorCount * occ1;
     ctx->grid_pipe2 = prop.multiProcessorCount * occ2;
     return 0;
@@ -683,12 +706,21 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
     ctx->launches++;
     // 1-2. D, L, b
-    if (S) {
-        LAUNCH_ROWS(ctx, k_low_build, 3, 2, ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un, rhs, dt,
-                    ctx->Lvals, ctx->Dvals, bvec, ctx->jstate + 7, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
-    } else {
-        LAUNCH_ROWS(ctx, k_low_build, 2, 2, ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un, rhs, dt,
-                    ctx->Lvals, ctx->Dvals, bvec, ctx->jstate + 7, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+    {
+        const int nf = S ? 2 : 1;
+        const size_t smem = FCT_NST_LOW * smem_bytes(ctx, nf, 2) + 2 * smem_bytes(ctx, 1, 0);
+        const int nb = fct_nblocks(ctx) < ctx->grid_low[nf - 1] ? fct_nblocks(ctx) : ctx->grid_low[nf - 1];
+        if (nb > 0) {
+            if (S)
+                k_low_build<1><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un,
+                                                                  rhs, dt, ctx->Lvals, ctx->Dvals, bvec, ctx->jstate + 7,
+                                                                  ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+            else
+                k_low_build<0><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un,
+                                                                  rhs, dt, ctx->Lvals, ctx->Dvals, bvec, ctx->jstate + 7,
+                                                                  ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+            ctx->launches++;
+        }
     }
     // low-order solve, initial guess u_n
     FCT_CUDA(cudaMemcpyAsync(ulow, un, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
