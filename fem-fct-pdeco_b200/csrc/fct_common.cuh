@@ -80,6 +80,7 @@ struct fct_ctx {
     double rtol = 1e-14;
     int32_t max_sweeps = 100;
     int64_t launches = 0;
+    int32_t last_pairs = 0;     // Jacobi sweep pairs the previous multi-GPU solve needed
     fct_comm* comm = nullptr;
     // halo description (multi-GPU)
     int32_t send_lo[2] = {0, 0}, send_hi[2] = {0, 0};

@@ -663,6 +663,35 @@ int fct_row_lump_diag(fct_ctx* ctx, const double* mat, double* out, double* diag
 int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, double* x, double* tmp, double rtol,
                      int max_sweeps) {
     const int pairs = (max_sweeps + 1) / 2;
+    if (ctx->comm) {
+        // Multi-GPU: a skipped sweep would still pay its NCCL exchanges, so sweeps are enqueued in a budget learnt
+        // from the previous solve and the (all-reduced, hence rank-uniform) convergence flag is read back before
+        // spending more.
+        int done = 0;
+        int budget = ctx->last_pairs > 0 ? ctx->last_pairs : 6;
+        while (done < pairs) {
+            const int todo = (done + budget <= pairs) ? budget : pairs - done;
+            for (int p = 0; p < todo; ++p) {
+                LAUNCH_PIPE(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0,
+                            ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+                if (fct_halo_exchange_if(ctx, tmp)) return 1;
+                LAUNCH_PIPE(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, tmp, x, ctx->jstate, 1,
+                            ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+                if (fct_halo_exchange_if(ctx, x)) return 1;
+                if (fct_halo_allreduce_max2(ctx, ctx->jstate)) return 1;
+                k_jacobi_decide<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol);
+                ctx->launches++;
+            }
+            done += todo;
+            unsigned long long st[2] = {0, 0};     // {converged flag, sweeps executed}
+            FCT_CUDA(cudaMemcpyAsync(st, ctx->jstate + 3, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+            FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (st[0]) { done = (int)((st[1] + 1) / 2); break; }
+            budget = 1;
+        }
+        ctx->last_pairs = done;      // sweeps per step are very stable: next time enqueue exactly this many first
+        return fct_launch_error(ctx, "fct_jacobi_solve");
+    }
     for (int p = 0; p < pairs; ++p) {
         LAUNCH_PIPE(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0, ctx->row_begin,
                     ctx->row_end, ctx->nnz, ctx->cap);

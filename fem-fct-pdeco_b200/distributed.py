@@ -1,0 +1,247 @@
+"""Multi-GPU layer: contiguous row-block partition of the DoFs with a one-ring halo, one process per GPU.
+
+The reference is single-process; this module is what the B200 build adds for BASELINE config 5 at
+2/4/8 GPUs.  dolfin's CG1 DoF order is an anti-diagonal numbering, so the P1 matrix is block tridiagonal over
+the diagonals and a contiguous DoF block only references a short contiguous range on either side
+(SURVEY.md 8e): rank r owns global rows [R0,R1) and stores the contiguous range [G0,G1) = every column its
+rows reference.  Local index = global - G0; [0,row_begin) is the halo from rank r-1, [row_end,n) from r+1.
+
+Host logic only (numpy + torch.distributed for the rendezvous); the exchanges themselves are NCCL send/recv
+issued by libfctpdeco (fct_ctx_init_comm / fct_halo_exchange).
+"""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .context import FctContext, _hp
+
+
+def partition_rows(n, world):
+    """equal contiguous row blocks: bounds[r]..bounds[r+1]"""
+    base, rem = divmod(int(n), int(world))
+    sizes = [base + (1 if r < rem else 0) for r in range(world)]
+    return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+def column_ranges(rowptr, colidx, bounds):
+    """[G0,G1) per rank: min / max column referenced by the rank's owned rows (columns are sorted per row)"""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    world = len(bounds) - 1
+    g0 = np.empty(world, dtype=np.int64)
+    g1 = np.empty(world, dtype=np.int64)
+    for r in range(world):
+        a, b = int(bounds[r]), int(bounds[r + 1])
+        if b <= a:
+            raise ValueError(f"rank {r} owns no rows: too many ranks for this mesh")
+        first = colidx[rowptr[a:b]]
+        last = colidx[rowptr[a + 1:b + 1] - 1]
+        g0[r] = min(int(first.min()), a)
+        g1[r] = max(int(last.max()) + 1, b)
+    for r in range(world):
+        if r > 0 and g0[r] < bounds[r - 1]:
+            raise ValueError("halo reaches beyond the neighbouring rank: row blocks are thinner than the bandwidth")
+        if r + 1 < world and g1[r] > bounds[r + 2]:
+            raise ValueError("halo reaches beyond the neighbouring rank: row blocks are thinner than the bandwidth")
+    return g0, g1
+
+
+class LocalProblem:
+    """Everything rank `rank` needs to build its context from the global mesh description."""
+
+    def __init__(self, rowptr, colidx, cells, dof_xy, rank, world):
+        n = len(rowptr) - 1
+        self.n_global = n
+        self.rank, self.world = int(rank), int(world)
+        self.bounds = partition_rows(n, world)
+        self.g0_all, self.g1_all = column_ranges(rowptr, colidx, self.bounds)
+        R0, R1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        G0, G1 = int(self.g0_all[rank]), int(self.g1_all[rank])
+        self.R0, self.R1, self.G0, self.G1 = R0, R1, G0, G1
+        self.n = G1 - G0
+        self.row_begin, self.row_end = R0 - G0, R1 - G0
+        rp = np.asarray(rowptr, dtype=np.int64)
+        k0, k1 = int(rp[G0]), int(rp[G1])
+        cols = np.asarray(colidx[k0:k1], dtype=np.int64)
+        rows = np.repeat(np.arange(G0, G1, dtype=np.int64), np.diff(rp[G0:G1 + 1]))
+        keep = (cols >= G0) & (cols < G1)            # halo rows are truncated to the local column range
+        owned = (rows >= R0) & (rows < R1)
+        if not keep[owned].all():
+            raise AssertionError("owned rows must lie completely inside [G0,G1)")
+        self.keep = keep                             # mask into global entries k0..k1 (value-array scatter)
+        self.k0, self.k1 = k0, k1
+        lrows = rows[keep] - G0
+        self.colidx = (cols[keep] - G0).astype(np.int32)
+        counts = np.bincount(lrows, minlength=self.n)
+        self.rowptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        # cells with at least one owned vertex (all their vertices are neighbours of it, hence local)
+        cells = np.asarray(cells, dtype=np.int64).reshape(-1, 3)
+        own_c = ((cells >= R0) & (cells < R1)).any(axis=1)
+        lc = cells[own_c]
+        if lc.size and (lc.min() < G0 or lc.max() >= G1):
+            raise AssertionError("a cell of an owned vertex leaves the local range")
+        self.cells = (lc - G0).astype(np.int32)
+        self.dof_xy = np.ascontiguousarray(np.asarray(dof_xy, dtype=np.float64).reshape(-1, 2)[G0:G1])
+        # what the neighbours need from this rank (local indices)
+        self.send_lo = (0, 0)
+        self.send_hi = (0, 0)
+        if rank > 0:            # rank-1's upper halo is the global range [R0, G1[rank-1])
+            self.send_lo = (R0 - G0, int(self.g1_all[rank - 1]) - G0)
+        if rank + 1 < world:    # rank+1's lower halo is the global range [G0[rank+1], R1)
+            self.send_hi = (int(self.g0_all[rank + 1]) - G0, R1 - G0)
+
+    # global <-> local vectors --------------------------------------------------------------------
+    def scatter(self, vec_global):
+        """local copy (owned + halo entries) of a global DoF vector or time-major trajectory"""
+        v = np.asarray(vec_global, dtype=np.float64)
+        if v.size == self.n_global:
+            return np.ascontiguousarray(v[self.G0:self.G1])
+        v = v.reshape(-1, self.n_global)
+        return np.ascontiguousarray(v[:, self.G0:self.G1]).ravel()
+
+    def owned(self, vec_local):
+        """owned part of a local vector / trajectory"""
+        v = np.asarray(vec_local)
+        if v.size == self.n:
+            return v[self.row_begin:self.row_end]
+        return v.reshape(-1, self.n)[:, self.row_begin:self.row_end]
+
+    def scatter_values(self, vals_global):
+        """local value array of a global value array on the global pattern"""
+        return np.ascontiguousarray(np.asarray(vals_global, dtype=np.float64)[self.k0:self.k1][self.keep])
+
+    def make_context(self, device):
+        ctx = FctContext(self.rowptr, self.colidx, device=device, row_begin=self.row_begin, row_end=self.row_end)
+        ctx.set_mesh(self.cells, self.dof_xy)
+        return ctx
+
+
+def init_comm(ctx, lp, broadcast_bytes):
+    """create the NCCL communicator of a context.  `broadcast_bytes(b: bytes|None) -> bytes` must return rank 0's
+    bytes on every rank (e.g. via torch.distributed.broadcast_object_list)."""
+    buf = (C.c_ubyte * 128)()
+    if lp.rank == 0:
+        check(lib.fct_nccl_unique_id(buf))
+    uid = broadcast_bytes(bytes(buf) if lp.rank == 0 else None)
+    buf2 = (C.c_ubyte * 128).from_buffer_copy(uid)
+    check(lib.fct_ctx_init_comm(ctx.handle, buf2, lp.rank, lp.world, lp.send_lo[0], lp.send_lo[1], lp.send_hi[0],
+                                lp.send_hi[1]))
+
+
+def torch_broadcaster():
+    import torch.distributed as dist
+
+    def bc(b):
+        obj = [b]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+    return bc
+
+
+def setup_rank(mesh, rank, world, local_rank):
+    """LocalProblem + context (mesh set, communicator initialised, static matrices assembled) for this rank"""
+    lp = LocalProblem(mesh.rowptr, mesh.colidx, mesh.cells, mesh.dof_xy, rank, world)
+    ctx = lp.make_context(local_rank)
+    if world > 1:
+        init_comm(ctx, lp, torch_broadcaster())
+    ctx.assemble_static()
+    return lp, ctx
+
+
+# ------------------------------------------------------------------------------------------------------
+# bench.py, N > 1: strong scaling of BASELINE config 5 (one process per GPU, launched by torchrun)
+# ------------------------------------------------------------------------------------------------------
+def bench_multi(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from .mesh import RectMeshP1
+
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    import bench as bench_mod            # the repo-root bench.py (synthetic problem + JSON helpers)
+
+    n_cells, nt = args.cells, args.nt
+    h = 1.0 / n_cells
+    dt = 0.25 * h / (2 * np.sqrt(2))
+    beta = 0.01
+    mesh = RectMeshP1(n_cells, 0.0, 1.0)
+    lp, ctx = setup_rank(mesh, rank, world, local_rank)
+    u0, c0, uhat = bench_mod.synth_problem(mesh, nt, dt)
+    n_glob, nnz_glob, ncell = mesh.nodes, mesh.nnz, mesh.ncells
+    n = lp.n
+    M = ctx.static()[0]
+    d_c = ctx.array(np.tile(lp.scatter(c0), nt + 1))
+    utr = np.zeros((nt + 1, n)); utr[0] = lp.scatter(u0)
+    d_u = ctx.array(utr.ravel())
+    d_uhat = ctx.array(lp.scatter(uhat.ravel()))
+    L = (nt + 1) * n
+    d_p, d_d = ctx.empty(L), ctx.empty(L)
+    del mesh, utr
+    sweeps_hist = []
+
+    def gradient_pass():
+        s1 = ctx.advdrift_state(d_c, d_u, nt, dt)
+        s2 = ctx.advdrift_adjoint(d_c, d_u, d_uhat, d_p, nt, dt)
+        ctx.advdrift_gradient(d_c, d_u, d_p, d_d, nt, beta)
+        J = 0.5 * ctx.norm_sq_Q(M, d_u, nt, dt, target=d_uhat) + beta / 2 * ctx.norm_sq_Q(M, d_c, nt, dt)
+        sweeps_hist.append((s1, s2))
+        return J
+
+    for _ in range(args.warmup):
+        gradient_pass()
+    ctx.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = bench_mod.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    del sweeps_hist[:]
+    e0, e1 = ctx.event(), ctx.event()
+    ctx.record(e0)
+    for _ in range(args.steps):
+        J = gradient_pass()
+    ctx.record(e1)
+    ms = ctx.elapsed_ms(e0, e1)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = ctx.launch_count() - l0
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        fct_steps = 2 * nt * args.steps
+        value = fct_steps / (ms * 1e-3)
+        k_mean = float(np.mean([0.5 * (a + b) / nt for a, b in sweeps_hist]))
+        peak, peak_src = bench_mod._peaks()
+        step_gb = bench_mod.step_bytes(n_glob, nnz_glob, ncell, k_mean) / 1e9
+        line = {
+            "metric": "FCT steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic {n_cells}^2-cell unit-square drift-control advection FCT PDECO "
+                                   f"(BASELINE config 5): {n_glob} DoF, {nnz_glob} nnz, row-block partitioned over "
+                                   f"{world} GPUs (one-ring halo, NCCL send/recv); bench step = state+adjoint sweeps "
+                                   f"over {nt} time levels + gradient + cost",
+                       "time_levels": nt, "dt": dt, "jacobi_sweeps_per_step": k_mean, "cost_functional": J,
+                       "halo_rows": [int(lp.row_begin), int(lp.n - lp.row_end)],
+                       "l2_flush": "per-GPU working set per pass >> L2"},
+            "roofline": {"bound": "hbm", "kernel": "whole FCT step (all kernels)", "achieved": step_gb * value / world,
+                         "peak": peak, "unit": "GB/s", "frac": step_gb * value / world / peak, "traffic": None,
+                         "peak_source": peak_src, "note": "per-GPU: algorithmic bytes of an FCT step x steps/s / N"},
+            "e2e": {"value": None, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "host-buffer entry point is single-GPU; see the N=1 line"},
+            "gpu_launches": int(lt.item()),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
