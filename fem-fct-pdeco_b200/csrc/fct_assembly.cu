@@ -103,6 +103,30 @@ __device__ __forceinline__ void element_row(const CellGeom& g, int a, const Form
             if (KIND == FCT_FORM_WIND_P1) e[b] = g.gx[a] * (m * (sx + wx[b])) + g.gy[a] * (m * (sy + wy[b]));
             else e[b] = g.gx[b] * (m * (sx + wx[a])) + g.gy[b] * (m * (sy + wy[a]));
         }
+    } else if (KIND == FCT_FORM_WIND_POLY3 || KIND == FCT_FORM_WIND_POLY3_T) {
+        // W_b = int w phi_b with the cubic wind evaluated at the 7 quadrature points of the degree-5 rule
+        const double2 p0 = __ldg(reinterpret_cast<const double2*>(fa.f1) + g.d[0]);   // fa.f1 = dof coordinates
+        const double2 p1 = __ldg(reinterpret_cast<const double2*>(fa.f1) + g.d[1]);
+        const double2 p2 = __ldg(reinterpret_cast<const double2*>(fa.f1) + g.d[2]);
+        double Wx[3] = {0, 0, 0}, Wy[3] = {0, 0, 0};
+        const double* cw = fa.f0;
+        for (int q = 0; q < 7; ++q) {
+            const double ph[3] = {1.0 - c_q5[q][0] - c_q5[q][1], c_q5[q][0], c_q5[q][1]};
+            const double x = ph[0] * p0.x + ph[1] * p1.x + ph[2] * p2.x;
+            const double y = ph[0] * p0.y + ph[1] * p1.y + ph[2] * p2.y;
+            const double mono[10] = {1.0, x, y, x * x, x * y, y * y, x * x * x, x * x * y, x * y * y, y * y * y};
+            double wx = 0.0, wy = 0.0;
+#pragma unroll
+            for (int m = 0; m < 10; ++m) { wx += __ldg(cw + m) * mono[m]; wy += __ldg(cw + 10 + m) * mono[m]; }
+            const double w = c_q5[q][2] * g.detJ;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) { Wx[b] += w * wx * ph[b]; Wy[b] += w * wy * ph[b]; }
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (KIND == FCT_FORM_WIND_POLY3) e[b] = g.gx[a] * Wx[b] + g.gy[a] * Wy[b];
+            else e[b] = g.gx[b] * Wx[a] + g.gy[b] * Wy[a];
+        }
     } else if (KIND == FCT_FORM_WMASS1 || KIND == FCT_FORM_WMASS2 || KIND == FCT_FORM_WMASS3) {
         e[0] = e[1] = e[2] = 0.0;
         const double a0[3] = {fa.f0[g.d[0]], fa.f0[g.d[1]], fa.f0[g.d[2]]};
@@ -292,6 +316,8 @@ int fct_assembly_configure(fct_ctx* ctx) {
     rc |= configure_matrix<FCT_FORM_CHTX>(bytes);
     rc |= configure_matrix<FCT_FORM_CHTX_EXP>(bytes);
     rc |= configure_matrix<FCT_FORM_CHTX_ADJ>(bytes);
+    rc |= configure_matrix<FCT_FORM_WIND_POLY3>(bytes);
+    rc |= configure_matrix<FCT_FORM_WIND_POLY3_T>(bytes);
     return rc;
 }
 
@@ -363,6 +389,13 @@ extern "C" int fct_assemble_matrix(fct_ctx* ctx, int32_t kind, const double* c0,
         case FCT_FORM_CHTX_ADJ:
             FCT_CHECK(c0 && c1, "fct_assemble_matrix(CHTX_ADJ): coef0, coef1 required");
             return launch_matrix<FCT_FORM_CHTX_ADJ>(ctx, fa, scale, acc, out);
+        case FCT_FORM_WIND_POLY3:
+        case FCT_FORM_WIND_POLY3_T: {
+            FCT_CHECK(c0, "fct_assemble_matrix(WIND_POLY3): coef0 (20 polynomial coefficients) required");
+            FormArgs fw{c0, ctx->xy, nullptr, nullptr, s0, s1};      // f1 carries the coordinates
+            return kind == FCT_FORM_WIND_POLY3 ? launch_matrix<FCT_FORM_WIND_POLY3>(ctx, fw, scale, acc, out)
+                                               : launch_matrix<FCT_FORM_WIND_POLY3_T>(ctx, fw, scale, acc, out);
+        }
         default: break;
     }
     fct_set_error("fct_assemble_matrix: unknown form kind %d", kind);

@@ -1,0 +1,391 @@
+"""Reference-named state / adjoint time loops and the Armijo line search, running on the B200 kernels.
+
+Same names, argument order, in-place semantics (the caller's trajectory buffers are written AND returned) and
+error behaviour as the reference (KarolinaBenkova/FEM-FCT-PDECO):
+
+    solve_schnak_system                helpers.py:511-597      solve_adjoint_schnak_system        :599-698
+    solve_nonlinear_equation           helpers.py:881-966      solve_adjoint_nonlinear_equation   :968-1038
+    solve_chtxs_system                 helpers.py:1250-1385    solve_adjoint_chtxs_system         :1387-1581
+    armijo_line_search_ref             helpers.py:1583-1713    get_*_params / *_IC                :443-509, 835-879, 1197-1248
+
+`V` is the dolfin-free stand-in `FunctionSpaceP1` (fem-fct-pdeco_b200/mesh.py); `control_fun` may be a number
+(the reference's `Constant`) or a DoF vector (the reference's `Function`).  All assembly, FCT steps and linear
+solves run on the GPU; the loops themselves are host control flow, as in the reference.  Reference quirks that
+parity depends on are reproduced and marked.
+"""
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .helpers import L2_norm_sq_Q, cost_functional, reorder_vector_to_dof
+
+# monomial order 1,x,y,x^2,xy,y^2,x^3,x^2y,xy^2,y^3  (include/fctpdeco.h, FCT_FORM_WIND_POLY3)
+_SCHNAK_WIND = np.array([0, -0.5, 0, 0.5, 1, 0, 0, -1, 0, 0,          # (y-1/2) x (1-x)     helpers.py:506
+                         0, 0, 0.5, 0, -1, -0.5, 0, 0, 1, 0], float)   # -(x-1/2) y (1-y)    helpers.py:507
+
+
+def _grid(V):
+    m = V.mesh()
+    dx = (m.a2 - m.a1) / m.n
+    X = np.arange(m.a1, m.a2 + dx, dx)[: m.n + 1]
+    return np.meshgrid(X, X)
+
+
+# ---- parameter getters / initial conditions ----------------------------------------------------------
+def get_schnak_sys_params():
+    """helpers.py:485-509 (the wind is returned as FCT_FORM_WIND_POLY3 coefficients instead of a df.Expression)"""
+    return 1 / 100, 8.6676, 0.1, 0.9, 230.82, 100, 0.6, _SCHNAK_WIND.copy()
+
+
+def get_nonlinear_eqns_params():
+    """helpers.py:867-879"""
+    speed = 1
+    return 1e-4, speed, 2 * speed * _SCHNAK_WIND
+
+
+def get_chtxs_sys_params():
+    """helpers.py:1197-1211"""
+    return 100, 0.05, 0.05, 0.25, 100, 0.5
+
+
+def schnak_sys_IC(a1, a2, deltax, nodes, vertex_to_dof):
+    """helpers.py:443-483"""
+    X = np.arange(a1, a2 + deltax, deltax)
+    X, Y = np.meshgrid(X, X)
+    _, _, c_a, c_b, _, _, _, _ = get_schnak_sys_params()
+    con = 0.1
+    u_init = c_a + c_b + con * np.cos(2 * np.pi * (X + Y)) + 0.01 * (sum(np.cos(2 * np.pi * X * i) for i in range(1, 9)))
+    v_init = c_b / pow(c_a + c_b, 2) + con * np.cos(2 * np.pi * (X + Y)) + 0.01 * (sum(np.cos(2 * np.pi * X * i) for i in range(1, 9)))
+    return (reorder_vector_to_dof(u_init.reshape(nodes), 1, nodes, vertex_to_dof),
+            reorder_vector_to_dof(v_init.reshape(nodes), 1, nodes, vertex_to_dof))
+
+
+def nonlinear_equation_IC(a1, a2, deltax, nodes, vertex_to_dof):
+    """helpers.py:835-865"""
+    X = np.arange(a1, a2 + deltax, deltax)
+    X, Y = np.meshgrid(X, X)
+    ic = 5 * Y * (Y - 1) * X * (X - 1) * np.sin(4 * X * np.pi)
+    return reorder_vector_to_dof(ic.reshape(nodes), 1, nodes, vertex_to_dof)
+
+
+def chtxs_sys_IC(a1, a2, deltax, nodes, vertex_to_dof):
+    """helpers.py:1213-1248 (np.random.seed(5); u(0) = v(0))"""
+    sqnodes = round(np.sqrt(nodes))
+    np.random.seed(5)
+    u_init = 1.5 + 0.1 * (0.5 - np.random.rand(sqnodes, sqnodes))
+    u_init_dof = reorder_vector_to_dof(u_init.reshape(nodes), 1, nodes, vertex_to_dof)
+    return u_init_dof, u_init_dof
+
+
+# ---- device-side helpers ------------------------------------------------------------------------------
+class _Dev:
+    """context + scratch buffers of a function space"""
+
+    def __init__(self, V, nodes):
+        self.ctx = V.mesh().context()
+        if self.ctx.n != nodes:
+            raise ValueError(f"nodes={nodes} does not match the function space ({self.ctx.n})")
+        self.M, self.ML, self.Md, self.K = self.ctx.static()
+        self._vec = {}
+        self._mat = {}
+
+    def vec(self, name):
+        if name not in self._vec:
+            self._vec[name] = self.ctx.empty(self.ctx.n)
+        return self._vec[name]
+
+    def mat(self, name):
+        if name not in self._mat:
+            self._mat[name] = self.ctx.empty(self.ctx.nnz)
+        return self._mat[name]
+
+    def load_control(self, out, control_fun, other=None, scale=1.0, accumulate=False):
+        """out (+)= scale * assemble(control_fun * [other] * v * dx); control_fun: number or device vector"""
+        ctx, L = self.ctx, _lib
+        if np.isscalar(control_fun):
+            if other is None:
+                ctx.assemble_vector(L.LOAD_CONST, out, s0=float(control_fun), scale=scale, accumulate=accumulate)
+            else:
+                ctx.assemble_vector(L.LOAD_P1_1, out, c0=other, scale=scale * float(control_fun), accumulate=accumulate)
+        elif other is None:
+            ctx.assemble_vector(L.LOAD_P1_1, out, c0=control_fun, scale=scale, accumulate=accumulate)
+        else:
+            ctx.assemble_vector(L.LOAD_P1_2, out, c0=control_fun, c1=other, scale=scale, accumulate=accumulate)
+
+
+def _control_slice(dev, control, control_fun, start, end):
+    """the reference builds control_fun once, from the FIRST step's slice, and then reuses it
+    (helpers.py:577-578, 950-951, 1332-1333) -- reproduced by the callers"""
+    if control_fun is not None:
+        return control_fun if np.isscalar(control_fun) else dev.ctx.array(np.asarray(control_fun, dtype=np.float64))
+    return dev.ctx.array(np.asarray(control[start:end], dtype=np.float64))
+
+
+def _solve(ctx, kind, mat, b, x, what):
+    its, res = ctx.solve(kind, mat, b, x, rtol=1e-14, maxit=20000)
+    return its
+
+
+# ---- Schnakenberg ---------------------------------------------------------------------------------------
+def solve_schnak_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighbors, control_fun=None, rescaling=1):
+    """helpers.py:511-597"""
+    Du, Dv, _, c_b, gamma, omega1, omega2, wind = get_schnak_sys_params()
+    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    var1[nodes:] = np.zeros(num_steps * nodes)
+    var2[nodes:] = np.zeros(num_steps * nodes)
+    dwind = ctx.array(wind)
+    A = dev.mat("A"); ctx.assemble_matrix(L.FORM_WIND_POLY3, A, c0=dwind)
+    Mat1 = dev.mat("Mat1"); ctx.vals_axpby(Du, dev.K, -omega1, A, Mat1)          # Du*Ad - omega1*A
+    S = dev.mat("S"); ctx.vals_axpby(gamma, dev.M, 0.0, None, S)                   # non_flux_mat = gamma*M
+    base2 = dev.mat("base2"); ctx.vals_axpby(dt * Dv, dev.K, -dt * omega2, A, base2)
+    ctx.vals_axpby(1.0, base2, 1.0, dev.M, base2)                                  # M + dt(Dv Ad - omega2 A)
+    Mat2, Mu2 = dev.mat("Mat2"), dev.mat("Mu2")
+    un, vn = ctx.array(var1[:nodes]), ctx.array(var2[:nodes])
+    u1, v1 = dev.vec("u1"), dev.vec("v1")
+    rhs1, rhs2 = dev.vec("rhs1"), dev.vec("rhs2")
+    cfun = None
+    print("Solving the system of advective Schnakenberg state equations...")
+    for i in range(1, num_steps + 1):
+        start, end = i * nodes, (i + 1) * nodes
+        if cfun is None:
+            cfun = _control_slice(dev, control, control_fun, start, end)
+        # rhs_var1 = assemble((gamma/r*c + gamma*u_n^2 v_n) v dx)
+        dev.load_control(rhs1, cfun, scale=gamma / rescaling)
+        ctx.assemble_vector(L.LOAD_P1_3, rhs1, c0=un, c1=un, c2=vn, scale=gamma, accumulate=True)
+        info = ctx.step(Mat1, un, dt, u1, S=S, rhs=rhs1)
+        _check(info)
+        # Mat_var2 = M + dt(Dv Ad - omega2 A + gamma M_u2), M_u2 from u_{n+1}
+        ctx.assemble_matrix(L.FORM_WMASS2, Mu2, c0=u1, c1=u1)
+        ctx.vals_axpby(1.0, base2, dt * gamma, Mu2, Mat2)
+        ctx.spmv(dev.M, vn, rhs2)
+        ctx.assemble_vector(L.LOAD_CONST, rhs2, s0=gamma * c_b, scale=dt, accumulate=True)
+        ctx.axpby(1.0, vn, 0.0, None, v1)                                          # initial guess
+        _solve(ctx, L.SOLVER_BICGSTAB, Mat2, rhs2, v1, "var2")
+        u1.download(var1[start:end]); v1.download(var2[start:end])
+        un, u1 = u1, un
+        vn, v1 = v1, vn
+    return var1, var2
+
+
+def solve_adjoint_schnak_system(uk, vk, uhat_T, vhat_T, pk, qk, T, V, nodes, num_steps, dt, dof_neighbors):
+    """helpers.py:599-698"""
+    Du, Dv, _, _, gamma, omega1, omega2, wind = get_schnak_sys_params()
+    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    pk[num_steps * nodes:] = uhat_T - uk[num_steps * nodes:]
+    qk[num_steps * nodes:] = vhat_T - vk[num_steps * nodes:]
+    dwind = ctx.array(wind)
+    A = dev.mat("A"); ctx.assemble_matrix(L.FORM_WIND_POLY3_T, A, c0=dwind)       # dot(wind, grad(u)) * w
+    Mat_p = dev.mat("Mat1"); ctx.vals_axpby(Du, dev.K, -omega1, A, Mat_p)
+    base_q = dev.mat("base2"); ctx.vals_axpby(dt * Dv, dev.K, -dt * omega2, A, base_q)
+    ctx.vals_axpby(1.0, base_q, 1.0, dev.M, base_q)
+    Mat_q, Mu2, S = dev.mat("Mat2"), dev.mat("Mu2"), dev.mat("S")
+    p1, q1 = ctx.array(pk[num_steps * nodes:]), ctx.array(qk[num_steps * nodes:])
+    p0, q0 = dev.vec("u1"), dev.vec("v1")
+    un, vn = dev.vec("un"), dev.vec("vn")
+    rhs_q, rhs_p = dev.vec("rhs1"), dev.vec("rhs2")
+    print("\nSolving adjoint equation...")
+    for i in reversed(range(0, num_steps)):
+        start, end = i * nodes, (i + 1) * nodes
+        un.upload(uk[start:end]); vn.upload(vk[start:end])
+        ctx.assemble_matrix(L.FORM_WMASS2, Mu2, c0=un, c1=un)
+        ctx.vals_axpby(1.0, base_q, dt * gamma, Mu2, Mat_q)
+        ctx.spmv(dev.M, q1, rhs_q)
+        ctx.assemble_vector(L.LOAD_P1_3, rhs_q, c0=p1, c1=un, c2=un, scale=dt * gamma, accumulate=True)
+        ctx.axpby(1.0, q1, 0.0, None, q0)
+        _solve(ctx, L.SOLVER_BICGSTAB, Mat_q, rhs_q, q0, "q")
+        # non_flux_mat = gamma*M - 2*gamma*M_uv ; rhs_p = assemble(-2 gamma u v q_n w)
+        ctx.assemble_matrix(L.FORM_WMASS2, S, c0=un, c1=vn, scale=-2 * gamma)
+        ctx.vals_axpby(1.0, S, gamma, dev.M, S)
+        ctx.assemble_vector(L.LOAD_P1_3, rhs_p, c0=un, c1=vn, c2=q0, scale=-2 * gamma)
+        _check(ctx.step(Mat_p, p1, dt, p0, S=S, rhs=rhs_p))
+        p0.download(pk[start:end]); q0.download(qk[start:end])
+        p1, p0 = p0, p1
+        q1, q0 = q0, q1
+    return pk, qk
+
+
+# ---- nonlinear advection-reaction ---------------------------------------------------------------------
+def solve_nonlinear_equation(control, var1, var2, V, nodes, num_steps, dt, dof_neighbors, control_fun=None,
+                             show_plots=False, vertex_to_dof=None):
+    """helpers.py:881-966"""
+    if var2 is not None:
+        warnings.warn("Warning: 'var2' is not None. Ensure this is intentional.")
+    eps, _, wind = get_nonlinear_eqns_params()
+    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    var1[nodes:] = np.zeros(num_steps * nodes)
+    A = dev.mat("A"); ctx.assemble_matrix(L.FORM_WIND_POLY3, A, c0=ctx.array(wind))
+    Mat1 = dev.mat("Mat1"); ctx.vals_axpby(-1.0, A, eps, dev.K, Mat1)             # -(A - eps Ad)
+    S = dev.mat("S")
+    un, u1, rhs = ctx.array(var1[:nodes]), dev.vec("u1"), dev.vec("rhs1")
+    cfun = None
+    print("\nSolving nonlinear state equation...")
+    for i in range(1, num_steps + 1):
+        start, end = i * nodes, (i + 1) * nodes
+        if cfun is None:
+            cfun = _control_slice(dev, control, control_fun, start, end)
+            dev.load_control(rhs, cfun)                                            # var1_rhs = assemble(c v dx)
+        ctx.assemble_matrix(L.FORM_WMASS2, S, c0=un, c1=un, scale=1 / 3)           # -M + M_u2/3
+        ctx.vals_axpby(1.0, S, -1.0, dev.M, S)
+        _check(ctx.step(Mat1, un, dt, u1, S=S, rhs=rhs))
+        u1.download(var1[start:end])
+        un, u1 = u1, un
+    return var1, None
+
+
+def solve_adjoint_nonlinear_equation(uk, uhat_T, pk, T, V, nodes, num_steps, dt, dof_neighbors):
+    """helpers.py:968-1038"""
+    eps, _, wind = get_nonlinear_eqns_params()
+    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    pk[num_steps * nodes:] = uhat_T - uk[num_steps * nodes:]
+    A = dev.mat("A"); ctx.assemble_matrix(L.FORM_WIND_POLY3, A, c0=ctx.array(wind))
+    Mat = dev.mat("Mat1"); ctx.vals_axpby(1.0, A, eps, dev.K, Mat)                 # -Mat_p = A + eps Ad
+    S = dev.mat("S")
+    p1, p0, un = ctx.array(pk[num_steps * nodes:]), dev.vec("u1"), dev.vec("un")
+    print("\nSolving adjoint equation...")
+    for i in reversed(range(0, num_steps)):
+        start, end = i * nodes, (i + 1) * nodes
+        un.upload(uk[start:end])
+        ctx.assemble_matrix(L.FORM_WMASS2, S, c0=un, c1=un)                        # M_u2 - M
+        ctx.vals_axpby(1.0, S, -1.0, dev.M, S)
+        _check(ctx.step(Mat, p1, dt, p0, S=S))
+        p0.download(pk[start:end])
+        p1, p0 = p0, p1
+    return pk
+
+
+# ---- chemotaxis -----------------------------------------------------------------------------------------
+def solve_chtxs_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighbors, control_fun=None,
+                       show_plots=False, vertex_to_dof=None, generation_mode=False, output_dir=None, rescaling=1 / 10):
+    """helpers.py:1250-1385"""
+    delta, Dm, Df, chi, _, eta = get_chtxs_sys_params()
+    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    if not generation_mode:
+        var1[nodes:] = np.zeros(num_steps * nodes)
+        var2[nodes:] = np.zeros(num_steps * nodes)
+    elif len(var1) != nodes or len(var2) != nodes or len(control) != nodes:
+        raise ValueError(f"Generation mode, the input vectors should be of length {nodes}")
+    Mat2 = dev.mat("Mat2"); ctx.vals_axpby(1.0 + dt * delta, dev.M, dt * Df, dev.K, Mat2)   # M + dt(Df Ad + delta M)
+    A = dev.mat("A")
+    un, vn = ctx.array(var1[:nodes]), ctx.array(var2[:nodes])
+    u1, v1, rhs = dev.vec("u1"), dev.vec("v1"), dev.vec("rhs1")
+    cfun = None
+    print("Solving the system of chemotaxis state equations...")
+    for i in range(1, num_steps + 1):
+        start, end = i * nodes, (i + 1) * nodes
+        if cfun is None:
+            cfun = _control_slice(dev, control, control_fun, 0 if generation_mode else start,
+                                  nodes if generation_mode else end)
+        # var2_rhs = assemble(v_n w dx + dt * c * u_n / r * w dx)
+        ctx.assemble_vector(L.LOAD_P1_1, rhs, c0=vn)
+        dev.load_control(rhs, cfun, other=un, scale=dt / rescaling, accumulate=True)
+        ctx.axpby(1.0, vn, 0.0, None, v1)
+        _solve(ctx, L.SOLVER_PCG, Mat2, rhs, v1, "var2")
+        # A_var1 = Dm*Ad - chi*Aa, Aa = exp(-eta u_n) grad(v_{n+1}).grad(w) u   (quadrature degree 4)
+        ctx.assemble_matrix(L.FORM_CHTX_EXP, A, c0=v1, c1=un, s0=eta, scale=-chi)
+        ctx.vals_axpby(1.0, A, Dm, dev.K, A)
+        _check(ctx.step(A, un, dt, u1))
+        if not generation_mode:
+            u1.download(var1[start:end]); v1.download(var2[start:end])
+        elif output_dir is not None and i % 100 == 0:
+            t = i * dt
+            u1.download().tofile(output_dir / f"chtxs_m_t{round(t, 2)}.csv", sep=",")
+            v1.download().tofile(output_dir / f"chtxs_f_t{round(t, 2)}.csv", sep=",")
+        un, u1 = u1, un
+        vn, v1 = v1, vn
+    if generation_mode:
+        var1[:] = un.download(); var2[:] = vn.download()
+    return var1, var2
+
+
+def solve_adjoint_chtxs_system(uk, vk, uhat, vhat, pk, qk, control, T, V, nodes, num_steps, dt, dof_neighbors, optim,
+                               show_plots=None, vertex_to_dof=None, out_folder=None, mesh=None, deltax=None,
+                               rescaling=1 / 10):
+    """helpers.py:1387-1581"""
+    valid_options = ["alltime", "finaltime"]
+    if optim not in valid_options:
+        raise ValueError(f"Invalid value for 'optim': '{optim}'. Must be one of {valid_options}.")
+    delta, Dm, Df, chi, _, eta = get_chtxs_sys_params()
+    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    if optim == "finaltime":
+        pk[num_steps * nodes:] = uhat - uk[num_steps * nodes:]
+        qk[num_steps * nodes:] = vhat - vk[num_steps * nodes:]
+    Mat_q = dev.mat("Mat2"); ctx.vals_axpby(1.0 + dt * delta, dev.M, dt * Df, dev.K, Mat_q)
+    A = dev.mat("A")
+    p1, q1 = ctx.array(pk[num_steps * nodes:(num_steps + 1) * nodes]), ctx.array(qk[num_steps * nodes:(num_steps + 1) * nodes])
+    p0, q0 = dev.vec("u1"), dev.vec("v1")
+    un, vn, cn, dif = dev.vec("un"), dev.vec("vn"), dev.vec("cn"), dev.vec("dif")
+    rhs_p, rhs_q = dev.vec("rhs1"), dev.vec("rhs2")
+    print("\nSolving adjoint equation...")
+    for i in reversed(range(0, num_steps)):
+        start, end = i * nodes, (i + 1) * nodes
+        un.upload(uk[start:end]); vn.upload(vk[start:end]); cn.upload(control[start:end])
+        # Mat_p = Dm*Ad - chi*Aa, Aa = (1-eta u)exp(-eta u) grad(p).grad(v_n) w   (quadrature degree 5)
+        ctx.assemble_matrix(L.FORM_CHTX_ADJ, A, c0=vn, c1=un, s0=eta, scale=-chi)
+        ctx.vals_axpby(1.0, A, Dm, dev.K, A)
+        ctx.assemble_vector(L.LOAD_P1_2, rhs_p, c0=cn, c1=q1, scale=1.0 / rescaling)
+        if optim == "alltime":          # the reference adds the NODAL difference (helpers.py:1509)
+            dif.upload(np.asarray(uhat[start:end]) - np.asarray(uk[start:end]))
+            ctx.axpby(1.0, rhs_p, 1.0, dif, rhs_p)
+        _check(ctx.step(A, p1, dt, p0, rhs=rhs_p))
+        # rhs_q = assemble(chi u exp(-eta u) grad(p_n).grad(w) dx)   (quadrature degree 4)
+        ctx.assemble_vector(L.LOAD_CHTX_ADJ, rhs_q, c0=p0, c1=un, s0=eta, s1=chi)
+        if optim == "alltime":          # (helpers.py:1535)
+            dif.upload(np.asarray(vhat[start:end]) - np.asarray(vk[start:end]))
+            ctx.axpby(1.0, rhs_q, 1.0, dif, rhs_q)
+        ctx.spmv(dev.M, q1, rhs_q, alpha=1.0, beta=dt, z=rhs_q)                    # M q_{n+1} + dt rhs_q
+        ctx.axpby(1.0, q1, 0.0, None, q0)
+        _solve(ctx, L.SOLVER_PCG, Mat_q, rhs_q, q0, "q")
+        p0.download(pk[start:end]); q0.download(qk[start:end])
+        p1, p0 = p0, p1
+        q1, q0 = q0, q1
+    return pk, qk
+
+
+def _check(info):
+    if info is not None and not info.converged:
+        raise _lib.FctError(f"low-order Jacobi solve did not converge in {info.solver_sweeps} sweeps: dt violates the "
+                            "M-matrix condition of helpers.py:1795-1809")
+
+
+# ---- projected Armijo line search -------------------------------------------------------------------------
+def armijo_line_search_ref(var1, c, d, var1_target, num_steps, dt, c_lower, c_upper, beta, costfun_init, nodes, optim,
+                           V, gam=1e-4, max_iter=10, s0=1, nonlinear_solver=None, dof_neighbors=None, var2=None,
+                           var2_target=None, w1=None, w2=None):
+    """helpers.py:1583-1713.  Return shape follows the reference: (var1, var2, c_inc, k+1) if var2 is not None else
+    (var1, c_inc, k+1) (App. D-11).  The linear branch (w1 given) never assembles M in the reference and fails there
+    (App. D-10); here M comes from the function space in both branches."""
+    valid_options = ["alltime", "finaltime"]
+    if optim not in valid_options:
+        raise ValueError(f"Invalid value for 'optim': '{optim}'. Must be one of {valid_options}.")
+    ctx = V.mesh().context()
+    M = ctx.to_scipy(ctx.static()[0].download())
+    s = s0
+    control_dif_L2 = 1
+    armijo = float("inf")
+    c_inc = c
+    k = 0
+    for k in range(max_iter):
+        print(f"{k=}")
+        c_inc = np.clip(c + s * d, c_lower, c_upper)
+        if w1 is None:
+            var1, var2 = nonlinear_solver(c_inc, var1, var2, V, nodes, num_steps, dt, dof_neighbors)
+            cost2 = cost_functional(var1, var1_target, c_inc, num_steps, dt, M, beta, optim=optim, var2=var2,
+                                    var2_target=var2_target)
+        else:
+            var1_inc = var1 + s * w1
+            var2_inc = var2 + s * w2 if w2 is not None else None
+            cost2 = cost_functional(var1_inc, var1_target, c_inc, num_steps, dt, M, beta, optim=optim, var2=var2_inc,
+                                    var2_target=var2_target)
+        armijo = cost2 - costfun_init
+        control_dif_L2 = L2_norm_sq_Q(c_inc - c, num_steps, dt, M)
+        print(f"Updated cost={cost2}, Orig. cost={costfun_init}")
+        print(f"Cost difference={armijo}")
+        print(f"Threshold value: {-gam/s*control_dif_L2=}")
+        if armijo <= -gam / s * control_dif_L2:
+            print(f"Converged in {k+1} iterations: Armijo condition satisfied.")
+            break
+        s /= 2
+    if armijo > -gam / s * control_dif_L2:
+        print(f"Stopped: Maximum number of iterations reached ({max_iter}) .")
+    return (var1, var2, c_inc, k + 1) if var2 is not None else (var1, c_inc, k + 1)

@@ -1,0 +1,120 @@
+"""GPU parity tests of the reference-named time loops (solve_*_system, solve_adjoint_*, armijo_line_search_ref)
+against the oracle restatements of helpers.py:511-698, 881-1038, 1250-1581, 1583-1713 on small meshes.
+Tolerance: 1e-12 relative L2 per time step (accumulating over the steps of a trajectory)."""
+import io
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from fem_fct_pdeco_b200 import helpers as hp
+from fem_fct_pdeco_b200.mesh import FunctionSpaceP1, RectMeshP1, vertex_to_dof_map
+from oracle import pdeco_systems as osys
+from oracle.fct_numpy import cost_functional as o_cost
+
+pytestmark = pytest.mark.gpu
+
+
+def _quiet(fn, *a, **k):
+    with redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def _space(n):
+    mesh = RectMeshP1(n, 0.0, 1.0)
+    return mesh, FunctionSpaceP1(mesh)
+
+
+def test_schnak_state_and_adjoint():
+    n, ns, dt = 10, 4, 1e-3
+    mesh, V = _space(n)
+    nodes = V.dim()
+    orc = osys.SchnakProblem(n, 0.0, 1.0)
+    u0, v0 = hp.schnak_sys_IC(0.0, 1.0, 1.0 / n, nodes, vertex_to_dof_map(V))
+    uo0, vo0 = orc.initial_condition()
+    assert np.array_equal(u0, uo0) and np.array_equal(v0, vo0)
+    rng = np.random.default_rng(2)
+    c = 0.1 + 0.05 * rng.random((ns + 1) * nodes)
+    u_o, v_o = orc.state(c, u0, v0, ns, dt, rescaling=1.0)
+    uk = np.zeros((ns + 1) * nodes); vk = np.zeros_like(uk)
+    uk[:nodes], vk[:nodes] = u0, v0
+    r1, r2 = _quiet(hp.solve_schnak_system, c, uk, vk, V, nodes, ns, dt, mesh.dof_neighbors())
+    assert r1 is uk and r2 is vk                                        # in place AND returned
+    for i in range(1, ns + 1):
+        assert rel_l2(uk.reshape(ns + 1, -1)[i], u_o[i]) < 1e-12 * i, i
+        assert rel_l2(vk.reshape(ns + 1, -1)[i], v_o[i]) < 1e-12 * i, i
+    uhat, vhat = u_o[-1] * 1.01 + 0.01, v_o[-1] * 0.99
+    p_o, q_o = orc.adjoint(u_o, v_o, uhat, vhat, ns, dt)
+    pk = np.zeros_like(uk); qk = np.zeros_like(uk)
+    _quiet(hp.solve_adjoint_schnak_system, u_o.ravel().copy(), v_o.ravel().copy(), uhat, vhat, pk, qk, ns * dt, V, nodes,
+           ns, dt, mesh.dof_neighbors())
+    assert rel_l2(pk, p_o.ravel()) < 1e-11 and rel_l2(qk, q_o.ravel()) < 1e-11
+
+
+def test_nonlinear_state_adjoint_and_armijo():
+    n, ns, dt = 12, 5, 2e-3
+    mesh, V = _space(n)
+    nodes = V.dim()
+    orc = osys.NonlinearProblem(n, 0.0, 1.0)
+    u0 = hp.nonlinear_equation_IC(0.0, 1.0, 1.0 / n, nodes, vertex_to_dof_map(V))
+    assert np.array_equal(u0, orc.initial_condition())
+    rng = np.random.default_rng(3)
+    c = rng.random((ns + 1) * nodes)
+    u_o = orc.state(c, u0, ns, dt)
+    uk = np.zeros((ns + 1) * nodes); uk[:nodes] = u0
+    with pytest.warns(UserWarning):
+        _quiet(hp.solve_nonlinear_equation, c, uk.copy(), np.zeros(3), V, nodes, ns, dt, mesh.dof_neighbors())
+    out, none = _quiet(hp.solve_nonlinear_equation, c, uk, None, V, nodes, ns, dt, mesh.dof_neighbors())
+    assert out is uk and none is None
+    assert rel_l2(uk, u_o.ravel()) < 1e-11
+    uhat_T = u_o[-1] + 0.05 * rng.random(nodes)
+    p_o = orc.adjoint(u_o, uhat_T, ns, dt)
+    pk = np.zeros_like(uk)
+    _quiet(hp.solve_adjoint_nonlinear_equation, u_o.ravel().copy(), uhat_T, pk, ns * dt, V, nodes, ns, dt,
+           mesh.dof_neighbors())
+    assert rel_l2(pk, p_o.ravel()) < 1e-11
+    # projected Armijo line search, final-time tracking (nonlinear_FCT_PDECO_refactored.py:148-152)
+    beta = 0.1
+    d = -(beta * c - pk)
+    cost0 = o_cost(orc.pat, u_o.ravel(), uhat_T, c, ns, dt, orc.M, beta, "finaltime")
+    solver = lambda ci: (orc.state(ci, u0, ns, dt).ravel(), None)
+    v1_o, _, c_o, k_o = osys.armijo_ref(orc, solver, u_o.ravel(), c, d, uhat_T, ns, dt, 0.0, 1.0, beta, cost0, "finaltime")
+    res = _quiet(hp.armijo_line_search_ref, uk.copy(), c, d, uhat_T, ns, dt, 0.0, 1.0, beta, cost0, nodes, "finaltime", V,
+                 nonlinear_solver=hp.solve_nonlinear_equation, dof_neighbors=mesh.dof_neighbors())
+    assert len(res) == 3                                               # (var1, c_inc, k+1) when var2 is None
+    v1_g, c_g, k_g = res
+    assert k_g == k_o and np.array_equal(c_g, c_o) and rel_l2(v1_g, v1_o) < 1e-11
+    with pytest.raises(ValueError):
+        hp.armijo_line_search_ref(uk, c, d, uhat_T, ns, dt, 0.0, 1.0, beta, cost0, nodes, "never", V)
+
+
+def test_chemotaxis_state_and_adjoint(ref_data):
+    n, ns, dt = 40, 3, 1e-3
+    mesh, V = _space(n)
+    nodes = V.dim()
+    m0, f0 = hp.chtxs_sys_IC(0.0, 1.0, 1.0 / n, nodes, vertex_to_dof_map(V))
+    assert np.array_equal(m0, ref_data["chtxs_m"][0])
+    mk = np.zeros((ns + 1) * nodes); fk = np.zeros_like(mk)
+    mk[:nodes], fk[:nodes] = m0, f0
+    # the configuration that produced the reference's shipped trajectory: Constant(100), rescaling=1
+    _quiet(hp.solve_chtxs_system, np.zeros(nodes), mk, fk, V, nodes, ns, dt, mesh.dof_neighbors(), control_fun=100.0,
+           rescaling=1)
+    for i in range(1, ns + 1):
+        assert rel_l2(mk.reshape(ns + 1, -1)[i], ref_data["chtxs_m"][i]) < 1e-12
+        assert rel_l2(fk.reshape(ns + 1, -1)[i], ref_data["chtxs_f"][i]) < 1e-12
+    # vector control (stale step-1 slice, App. D-1) against the oracle
+    orc = osys.ChemotaxisAdjoint(n, 0.0, 1.0)
+    rng = np.random.default_rng(4)
+    c = 50 + 10 * rng.random((ns + 1) * nodes)
+    m_o, f_o = orc.forward(c, m0, f0, ns, dt)
+    _quiet(hp.solve_chtxs_system, c, mk, fk, V, nodes, ns, dt, mesh.dof_neighbors())
+    assert rel_l2(mk, m_o.ravel()) < 1e-12 and rel_l2(fk, f_o.ravel()) < 1e-12
+    for optim, uh, vh in (("finaltime", m_o[-1] * 1.02, f_o[-1] * 0.98), ("alltime", m_o * 1.02, f_o * 0.98)):
+        p_o, q_o = orc.adjoint(m_o, f_o, uh, vh, c, ns, dt, optim)
+        pk = np.zeros_like(mk); qk = np.zeros_like(mk)
+        _quiet(hp.solve_adjoint_chtxs_system, m_o.ravel().copy(), f_o.ravel().copy(), np.ravel(uh), np.ravel(vh), pk, qk, c,
+               ns * dt, V, nodes, ns, dt, mesh.dof_neighbors(), optim)
+        assert rel_l2(pk, p_o.ravel()) < 1e-11 and rel_l2(qk, q_o.ravel()) < 1e-11, optim
+    with pytest.raises(ValueError):
+        hp.solve_adjoint_chtxs_system(mk, fk, mk, fk, mk, fk, c, 1.0, V, nodes, ns, dt, None, "sometimes")
