@@ -12,6 +12,8 @@
 #include "fct_pipe.cuh"
 #include "../../include/fctpdeco.h"
 
+#include <stdlib.h>
+
 // dynamic shared memory layout helpers ---------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char fct_smem[];
 
@@ -64,39 +66,90 @@ k_cheb_first(const double* __restrict__ g, const double* __restrict__ Md, double
     }
 }
 
+// Row dot product out of the staged CSR range: sum_k val[k] * x[col[k]] in column order.  Rows of <= 8 entries (every
+// P1 row of the structured mesh) take the unrolled path: all eight gathers are issued before the first FMA, so the
+// L1/L2 latency is paid once per row instead of once per entry.  DIAG: also return the diagonal value and leave it
+// out of the sum (Jacobi).
+template <bool DIAG>
+__device__ __forceinline__ double row_dot(const double* __restrict__ sA, const int32_t* __restrict__ sC, int ks, int ke,
+                                          const double* __restrict__ x, int r, double& diag) {
+    const int len = ke - ks;
+    double acc = 0.0;
+    if (len <= 8) {
+        double v[8], xv[8];
+        int c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool p = j < len;
+            c[j] = p ? sC[ks + j] : r;
+            v[j] = p ? sA[ks + j] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] = x[c[j]];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (DIAG) {
+                const bool isd = (c[j] == r) && (j < len);
+                if (isd) diag = v[j];
+                acc += isd ? 0.0 : v[j] * xv[j];
+            } else {
+                acc += v[j] * xv[j];
+            }
+        }
+    } else {
+        for (int k = ks; k < ke; ++k) {
+            const int c = sC[k];
+            const double v = sA[k];
+            if (DIAG && c == r) diag = v;
+            else acc += v * x[c];
+        }
+    }
+    return acc;
+}
+
 // ChebSI iteration k >= 2 (helpers.py:176-184):
 //   r = b - M ymid; z = r / Md'; ynew = omega (z + ymid - yold) + yold
+template <int NST>
 __global__ void __launch_bounds__(FCT_RB)
 k_cheb_iter(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Mv,
             const double* __restrict__ Md, const double* __restrict__ g, const double* __restrict__ ymid,
             const double* __restrict__ yold, double* __restrict__ ynew, double omega, double dscale,
             int has_old, int row_begin, int row_end, int64_t nnz, int cap) {
-    __shared__ __align__(8) uint64_t bars[FCT_NST];
-    RowPipe<1, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv}, {colidx}};
+    __shared__ __align__(8) uint64_t bars[NST];
+    RowPipe<1, 1, NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv}, {colidx}};
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
+    // the row's own inputs are fetched one block ahead (registers), so their DRAM latency overlaps the previous block
+    struct RowIn { int k0, k1; double g, md, ym, yo; };
+    auto load_row = [&](int i) {
+        RowIn in{0, 0, 0.0, 1.0, 0.0, 0.0};
+        if (i < nmine) {
+            const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+            const int r = row_begin + blk * FCT_RB + (int)threadIdx.x;
+            if (r < row_end) {
+                in.k0 = rowptr[r]; in.k1 = rowptr[r + 1];
+                in.g = g[r]; in.md = Md[r]; in.ym = ymid[r];
+                if (has_old) in.yo = yold[r];
+            }
+        }
+        return in;
+    };
+    RowIn cur = load_row(0);
     for (int i = 0; i < nmine; ++i) {
         pipe.prefetch(i, nmine);
+        const RowIn nxt = load_row(i + 1);
         const RowBlock b = pipe.block(i);
-        const bool act = (int)threadIdx.x < b.nr;
-        const int r = b.r0 + threadIdx.x;
-        int ks = 0, ke = 0;
-        double gr = 0.0, mdr = 1.0, ym = 0.0, yo = 0.0;
-        if (act) {      // the row's own vector entries: issued before the wait so that they overlap it
-            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
-            gr = g[r]; mdr = Md[r]; ym = ymid[r];
-            if (has_old) yo = yold[r];
-        }
         pipe.wait(i, b);
-        if (act) {
-            const double* sA = pipe.f64(i % FCT_NST, 0);
-            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
-            double acc = 0.0;
-            for (int k = ks; k < ke; ++k) acc += sA[k] * ymid[sC[k]];
-            const double z = (gr - acc) / (dscale * mdr);
-            ynew[r] = omega * (z + ym - yo) + yo;
+        if ((int)threadIdx.x < b.nr) {
+            const int r = b.r0 + threadIdx.x;
+            double dummy;
+            const double acc = row_dot<false>(pipe.f64(i % NST, 0), pipe.s32(i % NST, 0), cur.k0 - b.ka, cur.k1 - b.ka,
+                                              ymid, r, dummy);
+            const double z = (cur.g - acc) / (dscale * cur.md);
+            ynew[r] = omega * (z + cur.ym - cur.yo) + cur.yo;
         }
+        cur = nxt;
         __syncthreads();
     }
 }
@@ -220,48 +273,52 @@ k_art_diff(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colid
 
 // One Jacobi sweep x_new = (b - sum_{j != i} l_ij x_j) / l_ii.  Skipped once jstate[3] (converged) is set.
 // When `check` is set the sweep also accumulates ||x_new - x||_inf and ||x_new||_inf into jstate[0..1].
+template <int NST>
 __global__ void __launch_bounds__(FCT_RB)
 k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Lv,
                const double* __restrict__ bvec, const double* __restrict__ x, double* __restrict__ xnew,
                unsigned long long* __restrict__ jstate, int check, int row_begin, int row_end, int64_t nnz, int cap) {
     if (*reinterpret_cast<volatile unsigned long long*>(jstate + 3)) return;
-    __shared__ __align__(8) uint64_t bars[FCT_NST];
+    __shared__ __align__(8) uint64_t bars[NST];
     __shared__ double sred[FCT_RB / 32];
-    RowPipe<1, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Lv}, {colidx}};
+    RowPipe<1, 1, NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Lv}, {colidx}};
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
+    struct RowIn { int k0, k1; double b, x; };
+    auto load_row = [&](int i) {
+        RowIn in{0, 0, 0.0, 0.0};
+        if (i < nmine) {
+            const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+            const int r = row_begin + blk * FCT_RB + (int)threadIdx.x;
+            if (r < row_end) {
+                in.k0 = rowptr[r]; in.k1 = rowptr[r + 1];
+                in.b = bvec[r];
+                if (check) in.x = x[r];
+            }
+        }
+        return in;
+    };
+    RowIn cur = load_row(0);
     double delta = 0.0, xa = 0.0;
     for (int i = 0; i < nmine; ++i) {
         pipe.prefetch(i, nmine);
+        const RowIn nxt = load_row(i + 1);
         const RowBlock b = pipe.block(i);
-        const bool act = (int)threadIdx.x < b.nr;
-        const int r = b.r0 + threadIdx.x;
-        int ks = 0, ke = 0;
-        double br = 0.0, xr = 0.0;
-        if (act) {
-            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
-            br = bvec[r];
-            if (check) xr = x[r];
-        }
         pipe.wait(i, b);
-        if (act) {
-            const double* sA = pipe.f64(i % FCT_NST, 0);
-            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
-            double acc = 0.0, diag = 1.0;
-            for (int k = ks; k < ke; ++k) {
-                const int c = sC[k];
-                const double v = sA[k];
-                if (c == r) diag = v;
-                else acc += v * x[c];
-            }
-            const double xn = (br - acc) / diag;
+        if ((int)threadIdx.x < b.nr) {
+            const int r = b.r0 + threadIdx.x;
+            double diag = 1.0;
+            const double acc = row_dot<true>(pipe.f64(i % NST, 0), pipe.s32(i % NST, 0), cur.k0 - b.ka, cur.k1 - b.ka, x, r,
+                                             diag);
+            const double xn = (cur.b - acc) / diag;
             xnew[r] = xn;
             if (check) {
-                delta = fmax(delta, fabs(xn - xr));
+                delta = fmax(delta, fabs(xn - cur.x));
                 xa = fmax(xa, fabs(xn));
             }
         }
+        cur = nxt;
         __syncthreads();
     }
     if (check) {
@@ -525,6 +582,21 @@ static inline int pipe_grid(const fct_ctx* c, int nf64) {
         }                                                                                                \
     } while (0)
 
+// k_cheb_iter / k_jacobi_sweep are instantiated for 2, 3 and 4 ring stages; the context picks one (FCT_NST env var,
+// default 2) together with the matching persistent grid
+#define LAUNCH_PIPE_NST(ctx, kern, ...)                                                                  \
+    do {                                                                                                 \
+        const int nb0__ = fct_nblocks(ctx);                                                              \
+        const int nb__ = nb0__ < (ctx)->grid_nst1 ? nb0__ : (ctx)->grid_nst1;                            \
+        if (nb__ > 0) {                                                                                  \
+            const size_t sm__ = (size_t)(ctx)->nst1 * smem_bytes(ctx, 1, 1);                             \
+            if ((ctx)->nst1 == 2) kern<2><<<nb__, FCT_RB, sm__, (ctx)->stream>>>(__VA_ARGS__);           \
+            else if ((ctx)->nst1 == 4) kern<4><<<nb__, FCT_RB, sm__, (ctx)->stream>>>(__VA_ARGS__);      \
+            else kern<3><<<nb__, FCT_RB, sm__, (ctx)->stream>>>(__VA_ARGS__);                            \
+            (ctx)->launches++;                                                                           \
+        }                                                                                                \
+    } while (0)
+
 int fct_launch_error(fct_ctx* ctx, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -541,11 +613,15 @@ int fct_kernels_configure(fct_ctx* ctx) {
               worst, ctx->max_row);
     const int w = FCT_SMEM_OPTIN;   // opt-in ceiling only (never lowered by a later, smaller context)
     FCT_CUDA(cudaFuncSetAttribute(k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
-    FCT_CUDA(cudaFuncSetAttribute(k_cheb_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_cheb_iter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_cheb_iter<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_cheb_iter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_low_build<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_low_build<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_art_diff, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
-    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_flux_limits, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_flux_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_row_lump, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
@@ -556,7 +632,20 @@ int fct_kernels_configure(fct_ctx* ctx) {
     cudaDeviceProp prop;
     FCT_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
     int occ1 = 0, occ2 = 0;
-    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_cheb_iter, FCT_RB, FCT_NST * smem_bytes(ctx, 1, 1)));
+    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_spmv, FCT_RB, FCT_NST * smem_bytes(ctx, 1, 1)));
+    {
+        const char* e = getenv("FCT_NST");
+        ctx->nst1 = (e && (atoi(e) == 3 || atoi(e) == 4)) ? atoi(e) : 2;
+        int occn = 0;
+        const size_t sm = (size_t)ctx->nst1 * smem_bytes(ctx, 1, 1);
+        if (ctx->nst1 == 2) FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occn, k_cheb_iter<2>, FCT_RB, sm));
+        else if (ctx->nst1 == 4) FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occn, k_cheb_iter<4>, FCT_RB, sm));
+        else FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occn, k_cheb_iter<3>, FCT_RB, sm));
+        FCT_CHECK(occn >= 1, "k_cheb_iter does not fit on an SM (cap=%d, stages=%d)", ctx->cap, ctx->nst1);
+        const char* o = getenv("FCT_OCC");      // tuning knob: cap the resident CTAs per SM
+        if (o && atoi(o) >= 1 && atoi(o) < occn) occn = atoi(o);
+        ctx->grid_nst1 = prop.multiProcessorCount * occn;
+    }
     FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_flux_apply, FCT_RB, FCT_NST2 * smem_bytes(ctx, 2, 1)));
     FCT_CHECK(occ1 >= 1 && occ2 >= 1, "TMA-ring kernels do not fit on an SM (cap=%d)", ctx->cap);
     int occl0 = 0, occl1 = 0;
@@ -626,7 +715,7 @@ extern "C" int fct_chebsi(fct_ctx* ctx, const double* M, const double* Md, const
                 ctx->launches++;
             }
         } else {
-            LAUNCH_PIPE(ctx, k_cheb_iter, 1, 1, ctx->rowptr, ctx->colidx, M, Md, b, ymid, yold, ynew, omega, dscale,
+            LAUNCH_PIPE_NST(ctx, k_cheb_iter, ctx->rowptr, ctx->colidx, M, Md, b, ymid, yold, ynew, omega, dscale,
                         yold != nullptr, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
         }
         if (k < iters) {
@@ -672,10 +761,10 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, double* x,
         while (done < pairs) {
             const int todo = (done + budget <= pairs) ? budget : pairs - done;
             for (int p = 0; p < todo; ++p) {
-                LAUNCH_PIPE(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0,
+                LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0,
                             ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
                 if (fct_halo_exchange_if(ctx, tmp)) return 1;
-                LAUNCH_PIPE(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, tmp, x, ctx->jstate, 1,
+                LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, tmp, x, ctx->jstate, 1,
                             ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
                 if (fct_halo_exchange_if(ctx, x)) return 1;
                 if (fct_halo_allreduce_max2(ctx, ctx->jstate)) return 1;
@@ -693,10 +782,10 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, double* x,
         return fct_launch_error(ctx, "fct_jacobi_solve");
     }
     for (int p = 0; p < pairs; ++p) {
-        LAUNCH_PIPE(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0, ctx->row_begin,
+        LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0, ctx->row_begin,
                     ctx->row_end, ctx->nnz, ctx->cap);
         if (fct_halo_exchange_if(ctx, tmp)) return 1;
-        LAUNCH_PIPE(ctx, k_jacobi_sweep, 1, 1, ctx->rowptr, ctx->colidx, Lv, b, tmp, x, ctx->jstate, 1, ctx->row_begin,
+        LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, tmp, x, ctx->jstate, 1, ctx->row_begin,
                     ctx->row_end, ctx->nnz, ctx->cap);
         if (fct_halo_exchange_if(ctx, x)) return 1;
         if (fct_halo_allreduce_max2(ctx, ctx->jstate)) return 1;

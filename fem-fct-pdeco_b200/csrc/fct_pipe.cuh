@@ -85,9 +85,24 @@ struct RowPipe {
         }
         __syncthreads();
     }
+    // issuing thread only: CSR range of the next block to issue, loaded one iteration ahead so that the rowptr
+    // round trip to DRAM is off the critical path
+    int c_blk = -1, c_k0 = 0, c_k1 = 0;
+    __device__ __forceinline__ void cache_range(int i, int nmine) {
+        if (i < nmine) {
+            const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+            const int r0 = row_begin + blk * FCT_RB;
+            const int nr = min(FCT_RB, row_end - r0);
+            c_k0 = rowptr[r0];
+            c_k1 = rowptr[r0 + nr];
+            c_blk = i;
+        }
+    }
     // one thread: start the copies of block i into stage i % NST
-    __device__ __forceinline__ void issue(int i) const {
-        const RowBlock b = block(i);
+    __device__ __forceinline__ void issue(int i) {
+        RowBlock b;
+        if (c_blk == i) { b.k0 = c_k0; b.k1 = c_k1; b.ka = c_k0 & ~(FCT_ALIGN - 1); }
+        else b = block(i);
         const int st = i % NST;
         const int cnt = tma_count(b);
         uint64_t* bar = &bars[st];
@@ -99,13 +114,18 @@ struct RowPipe {
             for (int j = 0; j < NI; ++j) tma_load_1d(s32(st, j), gi[j] + b.ka, (uint32_t)cnt * 4, bar);
         }
     }
-    __device__ __forceinline__ void prologue(int nmine) const {
-        if (threadIdx.x == 0)
+    __device__ __forceinline__ void prologue(int nmine) {
+        if (threadIdx.x == 0) {
             for (int i = 0; i < NST - 1 && i < nmine; ++i) issue(i);
+            cache_range(NST - 1, nmine);
+        }
     }
     // top of iteration i: refill the stage that iteration i-1 released
-    __device__ __forceinline__ void prefetch(int i, int nmine) const {
-        if (threadIdx.x == 0 && i + NST - 1 < nmine) issue(i + NST - 1);
+    __device__ __forceinline__ void prefetch(int i, int nmine) {
+        if (threadIdx.x == 0 && i + NST - 1 < nmine) {
+            issue(i + NST - 1);
+            cache_range(i + NST, nmine);
+        }
     }
     // all threads: wait for block i's data; fetch the (rare) clamped tail with ordinary loads
     __device__ __forceinline__ void wait(int i, const RowBlock& b) const {
