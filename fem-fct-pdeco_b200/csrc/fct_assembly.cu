@@ -1,5 +1,6 @@
 // P1 element assembly into the fixed CSR pattern, as a row-gather: one thread per matrix row walks the
-// (<= 6 on the structured mesh) cells incident to its vertex in ascending cell order, evaluates the row of
+// (<= 6 on the structured mesh) cells incident to its vertex in ascending cell order (vertex->cell incidence
+// storing the two other vertices of each incident cell), evaluates the row of
 // each element tensor and adds it into the row's slots held in shared memory; the finished rows leave through
 // a coalesced store.  No atomics: the summation order is the cell order (what dolfin's cell loop and the
 // oracle's bincount do), so results are bit-reproducible and independent of the GPU count.
@@ -38,18 +39,15 @@ struct CellGeom {
     double detJ, area;
 };
 
-// Geometry of cell c seen from its vertex r: the vertices are rotated cyclically (orientation preserved) so that
-// r is local vertex 0 -- every per-vertex array is then indexed with compile-time constants and stays in registers.
-__device__ __forceinline__ CellGeom cell_geom(const int32_t* __restrict__ cells, const double* __restrict__ xy, int c,
-                                              int r) {
+// Geometry of a cell seen from its vertex r.  The vertex->cell incidence stores, per (vertex, incident cell), the cell's
+// two other vertices in the cell's own cyclic order (orientation preserved), so r is always local vertex 0: every
+// per-vertex array is indexed with compile-time constants and stays in registers, and the cell list itself is not read.
+__device__ __forceinline__ CellGeom cell_geom(const double* __restrict__ xy, int r, int j1, int j2) {
     CellGeom g;
-    const int d0 = __ldg(cells + 3 * c), d1 = __ldg(cells + 3 * c + 1), d2 = __ldg(cells + 3 * c + 2);
-    if (d0 == r) { g.d[0] = d0; g.d[1] = d1; g.d[2] = d2; }
-    else if (d1 == r) { g.d[0] = d1; g.d[1] = d2; g.d[2] = d0; }
-    else { g.d[0] = d2; g.d[1] = d0; g.d[2] = d1; }
-    const double2 p0 = __ldg(reinterpret_cast<const double2*>(xy) + g.d[0]);
-    const double2 p1 = __ldg(reinterpret_cast<const double2*>(xy) + g.d[1]);
-    const double2 p2 = __ldg(reinterpret_cast<const double2*>(xy) + g.d[2]);
+    g.d[0] = r; g.d[1] = j1; g.d[2] = j2;
+    const double2 p0 = __ldg(reinterpret_cast<const double2*>(xy) + r);
+    const double2 p1 = __ldg(reinterpret_cast<const double2*>(xy) + j1);
+    const double2 p2 = __ldg(reinterpret_cast<const double2*>(xy) + j2);
     const double det = (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
     const double inv = 1.0 / det;
     g.gx[1] = (p2.y - p0.y) * inv;  g.gy[1] = -(p2.x - p0.x) * inv;
@@ -205,8 +203,8 @@ k_assemble_matrix(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
         }
         const int cs = v2c_ptr[r], ce = v2c_ptr[r + 1];
         for (int ci = cs; ci < ce; ++ci) {
-            const int c = v2c_idx[ci];
-            const CellGeom g = cell_geom(cells, xy, c, r);
+            const int2 nb = __ldg(reinterpret_cast<const int2*>(v2c_idx) + ci);
+            const CellGeom g = cell_geom(xy, r, nb.x, nb.y);
             double e[3];
             element_row<KIND>(g, 0, fa, e);
             sV[kd] += e[0];
@@ -222,6 +220,45 @@ k_assemble_matrix(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     __syncthreads();
     unstage_f64(out, sV, b);
     __syncthreads();
+    }
+}
+
+// Register path for patterns whose rows have at most 8 entries (every P1 row of the structured meshes): the row's
+// column indices and accumulators live in registers, matching is a predicated add per slot, and nothing is staged in
+// shared memory -- the whole L1 serves the cell / coordinate / coefficient gathers, which is what bounds this kernel.
+// Same summation order (ascending cell index) as the staged kernel, hence bit-identical results.
+template <int KIND>
+__global__ void __launch_bounds__(FCT_RB)
+k_assemble_matrix_r8(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                     const int32_t* __restrict__ v2c_ptr, const int32_t* __restrict__ v2c_idx,
+                     const int32_t* __restrict__ cells, const double* __restrict__ xy, FormArgs fa, double scale,
+                     int accumulate, double* __restrict__ out, int row_begin, int row_end) {
+    const int stride = (int)gridDim.x * FCT_RB;
+    for (int r = row_begin + (int)blockIdx.x * FCT_RB + (int)threadIdx.x; r < row_end; r += stride) {
+        const int ks = rowptr[r];
+        const int len = rowptr[r + 1] - ks;
+        int c[8];
+        double acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c[j] = (j < len) ? __ldg(colidx + ks + j) : -1;
+            acc[j] = 0.0;
+        }
+        const int cs = v2c_ptr[r], ce = v2c_ptr[r + 1];
+        for (int ci = cs; ci < ce; ++ci) {
+            const int2 nb = __ldg(reinterpret_cast<const int2*>(v2c_idx) + ci);
+            const CellGeom g = cell_geom(xy, r, nb.x, nb.y);
+            double e[3];
+            element_row<KIND>(g, 0, fa, e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double add = (c[j] == g.d[0]) ? e[0] : ((c[j] == g.d[1]) ? e[1] : ((c[j] == g.d[2]) ? e[2] : 0.0));
+                acc[j] += add;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < len) out[(int64_t)ks + j] = accumulate ? (out[(int64_t)ks + j] + scale * acc[j]) : (scale * acc[j]);
     }
 }
 
@@ -275,8 +312,8 @@ k_assemble_vector(const int32_t* __restrict__ v2c_ptr, const int32_t* __restrict
     double acc = 0.0;
     const int cs = v2c_ptr[r], ce = v2c_ptr[r + 1];
     for (int ci = cs; ci < ce; ++ci) {
-        const int c = v2c_idx[ci];
-        const CellGeom g = cell_geom(cells, xy, c, r);
+        const int2 nb = __ldg(reinterpret_cast<const int2*>(v2c_idx) + ci);
+        const CellGeom g = cell_geom(xy, r, nb.x, nb.y);
         acc += element_load<KIND>(g, 0, fa);
     }
     out[r] = accumulate ? (out[r] + scale * acc) : (scale * acc);
@@ -287,6 +324,14 @@ template <int KIND>
 static int launch_matrix(fct_ctx* ctx, const FormArgs& fa, double scale, int accumulate, double* out) {
     // all local rows, halo rows included: their entries (j,i) towards owned rows i are complete because every
     // cell containing an owned vertex is local, and those are the only halo-row values the FCT step reads (a_ji).
+    if (ctx->max_row <= 8) {
+        const int nbr = fct_grid(ctx, (ctx->n + FCT_RB - 1) / FCT_RB);
+        k_assemble_matrix_r8<KIND><<<nbr, FCT_RB, 0, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->v2c_ptr, ctx->v2c_idx,
+                                                                    ctx->cells, ctx->xy, fa, scale, accumulate, out, 0,
+                                                                    ctx->n);
+        ctx->launches++;
+        return fct_launch_error(ctx, "fct_assemble_matrix");
+    }
     const int nb = fct_grid(ctx, (ctx->n + FCT_RB - 1) / FCT_RB);
     const size_t smem = (size_t)ctx->cap * (8 * (accumulate ? 2 : 1) + 4);
     k_assemble_matrix<KIND><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->v2c_ptr, ctx->v2c_idx,
@@ -333,22 +378,27 @@ extern "C" int fct_ctx_set_mesh(fct_ctx* ctx, int64_t ncells, const int32_t* cel
         ptr[(size_t)d + 1]++;
     }
     for (int i = 0; i < n; ++i) ptr[(size_t)i + 1] += ptr[i];
-    std::vector<int32_t> idx((size_t)(3 * ncells));
+    // per incidence: the cell's two other vertices in cyclic order (ascending cell index per vertex)
+    std::vector<int32_t> idx((size_t)(6 * ncells));
     {
         std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
         for (int64_t c = 0; c < ncells; ++c)
-            for (int q = 0; q < 3; ++q) idx[(size_t)fill[cell_dofs[3 * c + q]]++] = (int32_t)c;
+            for (int q = 0; q < 3; ++q) {
+                const size_t slot = (size_t)fill[cell_dofs[3 * c + q]]++;
+                idx[2 * slot] = cell_dofs[3 * c + (q + 1) % 3];
+                idx[2 * slot + 1] = cell_dofs[3 * c + (q + 2) % 3];
+            }
     }
     cudaFree(ctx->cells); cudaFree(ctx->xy); cudaFree(ctx->v2c_ptr); cudaFree(ctx->v2c_idx);
     ctx->cells = nullptr; ctx->xy = nullptr; ctx->v2c_ptr = nullptr; ctx->v2c_idx = nullptr;
     FCT_CUDA(cudaMalloc((void**)&ctx->cells, sizeof(int32_t) * 3 * (size_t)ncells));
     FCT_CUDA(cudaMalloc((void**)&ctx->xy, sizeof(double) * 2 * (size_t)n));
     FCT_CUDA(cudaMalloc((void**)&ctx->v2c_ptr, sizeof(int32_t) * ((size_t)n + 1)));
-    FCT_CUDA(cudaMalloc((void**)&ctx->v2c_idx, sizeof(int32_t) * 3 * (size_t)ncells));
+    FCT_CUDA(cudaMalloc((void**)&ctx->v2c_idx, sizeof(int32_t) * 6 * (size_t)ncells));
     FCT_CUDA(cudaMemcpy(ctx->cells, cell_dofs, sizeof(int32_t) * 3 * (size_t)ncells, cudaMemcpyHostToDevice));
     FCT_CUDA(cudaMemcpy(ctx->xy, dof_xy, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
     FCT_CUDA(cudaMemcpy(ctx->v2c_ptr, ptr.data(), sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
-    FCT_CUDA(cudaMemcpy(ctx->v2c_idx, idx.data(), sizeof(int32_t) * 3 * (size_t)ncells, cudaMemcpyHostToDevice));
+    FCT_CUDA(cudaMemcpy(ctx->v2c_idx, idx.data(), sizeof(int32_t) * 6 * (size_t)ncells, cudaMemcpyHostToDevice));
     ctx->ncells = ncells;
     return 0;
 }

@@ -62,7 +62,7 @@ struct fct_ctx {
     int32_t* cells = nullptr;       // [ncells*3]
     double* xy = nullptr;           // [n*2]
     int32_t* v2c_ptr = nullptr;     // vertex -> incident cells (CSR), built on set_mesh
-    int32_t* v2c_idx = nullptr;
+    int32_t* v2c_idx = nullptr;     // [2 * incidences]: the two other vertices of each incident cell, cyclic order
     // static matrices
     double* M = nullptr;
     double* ML = nullptr;

@@ -175,8 +175,8 @@ extern "C" int fct_advdrift_state_host(fct_ctx* ctx, const double* c_host, doubl
 // ======================================================================================================
 // Solvers for the second-species systems  (mat x = b)
 // ======================================================================================================
-int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, double* x, double* tmp, double rtol,
-                     int max_sweeps);
+int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const double* dinv, double* x, double* tmp,
+                     double rtol, int max_sweeps);
 int fct_read_step_info(fct_ctx* ctx, fct_step_info* info);
 
 __global__ void k_jstate_reset(unsigned long long* __restrict__ jstate) {
@@ -413,7 +413,7 @@ extern "C" int fct_solve(fct_ctx* ctx, int32_t kind, const double* mat, const do
     if (kind == 0) {
         k_jstate_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
         ctx->launches++;
-        if (fct_jacobi_solve(ctx, mat, b, x, ctx->w[5], rtol, maxit)) return 1;
+        if (fct_jacobi_solve(ctx, mat, b, nullptr, x, ctx->w[5], rtol, maxit)) return 1;
         fct_step_info info;
         if (fct_read_step_info(ctx, &info)) return 1;
         if (its_host) *its_host = info.solver_sweeps;

@@ -20,52 +20,6 @@ extern __shared__ __align__(16) unsigned char fct_smem[];
 #define FCT_NST 3    // ring stages of the TMA pipeline, kernels staging one fp64 array
 #define FCT_NST2 2   // ... kernels staging two fp64 arrays (leaves L1 room for the four gathered vectors)
 
-// y = alpha * A x + beta * z
-__global__ void __launch_bounds__(FCT_RB)
-k_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ A,
-       const double* __restrict__ x, double alpha, double beta, const double* __restrict__ z,
-       double* __restrict__ y, int row_begin, int row_end, int64_t nnz, int cap) {
-    __shared__ __align__(8) uint64_t bars[FCT_NST];
-    RowPipe<1, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {A}, {colidx}};
-    const int nmine = pipe.my_blocks();
-    pipe.init();
-    pipe.prologue(nmine);
-    for (int i = 0; i < nmine; ++i) {
-        pipe.prefetch(i, nmine);
-        const RowBlock b = pipe.block(i);
-        const bool act = (int)threadIdx.x < b.nr;
-        const int r = b.r0 + threadIdx.x;
-        int ks = 0, ke = 0;
-        double zr = 0.0;
-        if (act) {
-            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
-            if (beta != 0.0) zr = z[r];
-        }
-        pipe.wait(i, b);
-        if (act) {
-            const double* sA = pipe.f64(i % FCT_NST, 0);
-            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
-            double acc = 0.0;
-            for (int k = ks; k < ke; ++k) acc += sA[k] * x[sC[k]];
-            double out = alpha * acc;
-            if (beta != 0.0) out += beta * zr;
-            y[r] = out;
-        }
-        __syncthreads();
-    }
-}
-
-// ChebSI iteration k == 1: ymid = yold = 0  =>  y1 = omega1 * (b / Md')  with omega1 = 1
-__global__ void __launch_bounds__(FCT_RB)
-k_cheb_first(const double* __restrict__ g, const double* __restrict__ Md, double dscale, double omega,
-             double* __restrict__ ynew, int row_begin, int row_end) {
-    const int r = row_begin + blockIdx.x * FCT_RB + threadIdx.x;
-    if (r < row_end) {
-        const double z = g[r] / (dscale * Md[r]);
-        ynew[r] = omega * z;
-    }
-}
-
 // Row dot product out of the staged CSR range: sum_k val[k] * x[col[k]] in column order.  Rows of <= 8 entries (every
 // P1 row of the structured mesh) take the unrolled path: all eight gathers are issued before the first FMA, so the
 // L1/L2 latency is paid once per row instead of once per entry.  DIAG: also return the diagonal value and leave it
@@ -105,6 +59,52 @@ __device__ __forceinline__ double row_dot(const double* __restrict__ sA, const i
         }
     }
     return acc;
+}
+
+// y = alpha * A x + beta * z
+__global__ void __launch_bounds__(FCT_RB)
+k_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ A,
+       const double* __restrict__ x, double alpha, double beta, const double* __restrict__ z,
+       double* __restrict__ y, int row_begin, int row_end, int64_t nnz, int cap) {
+    __shared__ __align__(8) uint64_t bars[FCT_NST];
+    RowPipe<1, 1, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {A}, {colidx}};
+    const int nmine = pipe.my_blocks();
+    pipe.init();
+    pipe.prologue(nmine);
+    for (int i = 0; i < nmine; ++i) {
+        pipe.prefetch(i, nmine);
+        const RowBlock b = pipe.block(i);
+        const bool act = (int)threadIdx.x < b.nr;
+        const int r = b.r0 + threadIdx.x;
+        int ks = 0, ke = 0;
+        double zr = 0.0;
+        if (act) {
+            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
+            if (beta != 0.0) zr = z[r];
+        }
+        pipe.wait(i, b);
+        if (act) {
+            const double* sA = pipe.f64(i % FCT_NST, 0);
+            const int32_t* sC = pipe.s32(i % FCT_NST, 0);
+            double dummy;
+            const double acc = row_dot<false>(sA, sC, ks, ke, x, r, dummy);
+            double out = alpha * acc;
+            if (beta != 0.0) out += beta * zr;
+            y[r] = out;
+        }
+        __syncthreads();
+    }
+}
+
+// ChebSI iteration k == 1: ymid = yold = 0  =>  y1 = omega1 * (b / Md')  with omega1 = 1
+__global__ void __launch_bounds__(FCT_RB)
+k_cheb_first(const double* __restrict__ g, const double* __restrict__ Md, double dscale, double omega,
+             double* __restrict__ ynew, int row_begin, int row_end) {
+    const int r = row_begin + blockIdx.x * FCT_RB + threadIdx.x;
+    if (r < row_end) {
+        const double z = g[r] / (dscale * Md[r]);
+        ynew[r] = omega * z;
+    }
 }
 
 // ChebSI iteration k >= 2 (helpers.py:176-184):
@@ -165,7 +165,8 @@ __device__ __forceinline__ unsigned long long f64_sort_key(double v) {
 //   L    = M_L + dt (A - D) (+ dt S)            [helpers.py:1775-1778]
 //   b    = M_L u_n + dt rhs                     [helpers.py:1780]
 // `sign` folds the legacy FCT_alg convention (A -> -A, old_helpers.py:135-145) into the same kernel.
-// Outputs: Lv (full pattern), Dv (off-diagonals; diagonal slot holds d_ii), b; min row sum of L.
+// Outputs: Lv (off-diagonals of L, diagonal slot 0), dinv = 1/l_ii, Dv (off-diagonals; diagonal slot holds d_ii), b;
+// min row sum of L.
 // A (and S), colidx, tpos arrive through a 2-stage TMA ring; L and D leave through two staging buffers.
 #define FCT_NST_LOW 2
 template <int HAS_S>
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(FCT_RB)
 k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ tpos,
             const double* __restrict__ A, double sign, const double* __restrict__ S, const double* __restrict__ ML,
             const double* __restrict__ un, const double* __restrict__ rhs, double dt,
-            double* __restrict__ Lv, double* __restrict__ Dv, double* __restrict__ bvec,
+            double* __restrict__ Lv, double* __restrict__ Dv, double* __restrict__ bvec, double* __restrict__ dinv,
             unsigned long long* __restrict__ min_rowsum_key, int row_begin, int row_end, int64_t nnz, int cap) {
     __shared__ __align__(8) uint64_t bars[FCT_NST_LOW];
     __shared__ double sred[FCT_RB / 32];
@@ -225,7 +226,8 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             double l = ml + dt * (a - dii);
             if (HAS_S) l += dt * sS[kd];
             lsum += l;
-            sL[kd] = l;
+            sL[kd] = 0.0;          // the diagonal travels as 1/l_ii in `dinv`: the Jacobi row loop is branch-free
+            dinv[r] = 1.0 / l;
             sD[kd] = dii;
             rowsum = fmin(rowsum, lsum);
             bvec[r] = ml * unr + (rhs ? dt * rr : 0.0);
@@ -273,11 +275,14 @@ k_art_diff(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colid
 
 // One Jacobi sweep x_new = (b - sum_{j != i} l_ij x_j) / l_ii.  Skipped once jstate[3] (converged) is set.
 // When `check` is set the sweep also accumulates ||x_new - x||_inf and ||x_new||_inf into jstate[0..1].
-template <int NST>
-__global__ void __launch_bounds__(FCT_RB)
-k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Lv,
-               const double* __restrict__ bvec, const double* __restrict__ x, double* __restrict__ xnew,
-               unsigned long long* __restrict__ jstate, int check, int row_begin, int row_end, int64_t nnz, int cap) {
+// `dinv` != nullptr: Lv holds the off-diagonals only (diagonal slot 0) and dinv = 1/diag (the FCT low-order system,
+// written that way by k_low_build); dinv == nullptr: general matrix, the diagonal is picked out of the row.
+template <int NST, bool SEP>
+__device__ __forceinline__ void
+jacobi_sweep_body(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Lv,
+               const double* __restrict__ bvec, const double* __restrict__ dinv, const double* __restrict__ x,
+               double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check, int row_begin, int row_end,
+               int64_t nnz, int cap) {
     if (*reinterpret_cast<volatile unsigned long long*>(jstate + 3)) return;
     __shared__ __align__(8) uint64_t bars[NST];
     __shared__ double sred[FCT_RB / 32];
@@ -285,15 +290,16 @@ k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
-    struct RowIn { int k0, k1; double b, x; };
+    struct RowIn { int k0, k1; double b, x, di; };
     auto load_row = [&](int i) {
-        RowIn in{0, 0, 0.0, 0.0};
+        RowIn in{0, 0, 0.0, 0.0, 1.0};
         if (i < nmine) {
             const int blk = (int)blockIdx.x + i * (int)gridDim.x;
             const int r = row_begin + blk * FCT_RB + (int)threadIdx.x;
             if (r < row_end) {
                 in.k0 = rowptr[r]; in.k1 = rowptr[r + 1];
                 in.b = bvec[r];
+                if (SEP) in.di = dinv[r];
                 if (check) in.x = x[r];
             }
         }
@@ -308,10 +314,18 @@ k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
         pipe.wait(i, b);
         if ((int)threadIdx.x < b.nr) {
             const int r = b.r0 + threadIdx.x;
-            double diag = 1.0;
-            const double acc = row_dot<true>(pipe.f64(i % NST, 0), pipe.s32(i % NST, 0), cur.k0 - b.ka, cur.k1 - b.ka, x, r,
-                                             diag);
-            const double xn = (cur.b - acc) / diag;
+            double xn;
+            if (SEP) {
+                double dummy;
+                const double acc = row_dot<false>(pipe.f64(i % NST, 0), pipe.s32(i % NST, 0), cur.k0 - b.ka,
+                                                  cur.k1 - b.ka, x, r, dummy);
+                xn = (cur.b - acc) * cur.di;
+            } else {
+                double diag = 1.0;
+                const double acc = row_dot<true>(pipe.f64(i % NST, 0), pipe.s32(i % NST, 0), cur.k0 - b.ka,
+                                                 cur.k1 - b.ka, x, r, diag);
+                xn = (cur.b - acc) / diag;
+            }
             xnew[r] = xn;
             if (check) {
                 delta = fmax(delta, fabs(xn - cur.x));
@@ -330,6 +344,23 @@ k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(jstate + 4, 1ull);
+}
+
+template <int NST>
+__global__ void __launch_bounds__(FCT_RB, 5)
+k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Lv,
+               const double* __restrict__ bvec, const double* __restrict__ dinv, const double* __restrict__ x,
+               double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check, int row_begin, int row_end,
+               int64_t nnz, int cap) {
+    jacobi_sweep_body<NST, true>(rowptr, colidx, Lv, bvec, dinv, x, xnew, jstate, check, row_begin, row_end, nnz, cap);
+}
+template <int NST>
+__global__ void __launch_bounds__(FCT_RB)
+k_jacobi_sweep_gen(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Lv,
+                   const double* __restrict__ bvec, const double* __restrict__ dinv, const double* __restrict__ x,
+                   double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check, int row_begin,
+                   int row_end, int64_t nnz, int cap) {
+    jacobi_sweep_body<NST, false>(rowptr, colidx, Lv, bvec, dinv, x, xnew, jstate, check, row_begin, row_end, nnz, cap);
 }
 
 // After a checked sweep (and, multi-GPU, after the max-allreduce of jstate[0..1]): decide convergence.
@@ -622,6 +653,9 @@ int fct_kernels_configure(fct_ctx* ctx) {
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_gen<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_gen<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_gen<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_flux_limits, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_flux_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_row_lump, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
@@ -749,9 +783,18 @@ int fct_row_lump_diag(fct_ctx* ctx, const double* mat, double* out, double* diag
 
 // Jacobi solve of Lv x = b, x holds the initial guess on entry and the result on exit (device-side early exit;
 // sweeps run in pairs so that the result always lands back in x).
-int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, double* x, double* tmp, double rtol,
-                     int max_sweeps) {
+int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const double* dinv, double* x, double* tmp,
+                     double rtol, int max_sweeps) {
     const int pairs = (max_sweeps + 1) / 2;
+#define JACOBI_LAUNCH(xin, xout, chk)                                                                              \
+    do {                                                                                                           \
+        if (dinv)                                                                                                  \
+            LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, dinv, xin, xout, ctx->jstate, chk, \
+                            ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);                                     \
+        else                                                                                                       \
+            LAUNCH_PIPE_NST(ctx, k_jacobi_sweep_gen, ctx->rowptr, ctx->colidx, Lv, b, dinv, xin, xout, ctx->jstate, \
+                            chk, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);                                \
+    } while (0)
     if (ctx->comm) {
         // Multi-GPU: a skipped sweep would still pay its NCCL exchanges, so sweeps are enqueued in a budget learnt
         // from the previous solve and the (all-reduced, hence rank-uniform) convergence flag is read back before
@@ -761,11 +804,9 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, double* x,
         while (done < pairs) {
             const int todo = (done + budget <= pairs) ? budget : pairs - done;
             for (int p = 0; p < todo; ++p) {
-                LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0,
-                            ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+                JACOBI_LAUNCH(x, tmp, 0);
                 if (fct_halo_exchange_if(ctx, tmp)) return 1;
-                LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, tmp, x, ctx->jstate, 1,
-                            ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+                JACOBI_LAUNCH(tmp, x, 1);
                 if (fct_halo_exchange_if(ctx, x)) return 1;
                 if (fct_halo_allreduce_max2(ctx, ctx->jstate)) return 1;
                 k_jacobi_decide<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol);
@@ -782,11 +823,9 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, double* x,
         return fct_launch_error(ctx, "fct_jacobi_solve");
     }
     for (int p = 0; p < pairs; ++p) {
-        LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, x, tmp, ctx->jstate, 0, ctx->row_begin,
-                    ctx->row_end, ctx->nnz, ctx->cap);
+        JACOBI_LAUNCH(x, tmp, 0);
         if (fct_halo_exchange_if(ctx, tmp)) return 1;
-        LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, tmp, x, ctx->jstate, 1, ctx->row_begin,
-                    ctx->row_end, ctx->nnz, ctx->cap);
+        JACOBI_LAUNCH(tmp, x, 1);
         if (fct_halo_exchange_if(ctx, x)) return 1;
         if (fct_halo_allreduce_max2(ctx, ctx->jstate)) return 1;
         k_jacobi_decide<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol);
@@ -818,6 +857,7 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     double* ulow = ctx->w[4];
     double* tmp = ctx->w[5];
     double* g = ctx->w[6];
+    double* dinv = ctx->w[6];      // 1/diag(L): dead once the low-order solve is done, before g is formed
     double* udot = ctx->w[7];
     double* Rp = ctx->w[8];
     double* Rn = ctx->w[9];
@@ -831,18 +871,18 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
         if (nb > 0) {
             if (S)
                 k_low_build<1><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un,
-                                                                  rhs, dt, ctx->Lvals, ctx->Dvals, bvec, ctx->jstate + 7,
+                                                                  rhs, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,
                                                                   ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
             else
                 k_low_build<0><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un,
-                                                                  rhs, dt, ctx->Lvals, ctx->Dvals, bvec, ctx->jstate + 7,
+                                                                  rhs, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,
                                                                   ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
             ctx->launches++;
         }
     }
     // low-order solve, initial guess u_n
     FCT_CUDA(cudaMemcpyAsync(ulow, un, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (fct_jacobi_solve(ctx, ctx->Lvals, bvec, ulow, tmp, ctx->rtol, ctx->max_sweeps)) return 1;
+    if (fct_jacobi_solve(ctx, ctx->Lvals, bvec, dinv, ulow, tmp, ctx->rtol, ctx->max_sweeps)) return 1;
     // 4. g = -(sign A) u_low + rhs ; udot = ChebSI(g)
     LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, ulow, -sign, rhs ? 1.0 : 0.0, rhs, g, ctx->row_begin,
                 ctx->row_end, ctx->nnz, ctx->cap);

@@ -14,12 +14,12 @@ def main(path):
     for row in csv.DictReader(lines):
         if row.get('Metric Name') != 'gpu__time_duration.sum':
             continue
-        name = re.sub(r'\(.*', '', row['Kernel Name'])
+        name = re.sub(r'\(.*', '', row['Kernel Name']).replace('void ', '')
         v = float(row['Metric Value'].replace(',', ''))
         u = row['Metric Unit']
         v = v / 1e6 if u == 'ns' else v / 1e3 if u == 'us' else v
-        if name == 'k_jacobi_sweep' and v < 0.05:
-            name = 'k_jacobi_sweep (skipped: converged)'
+        if name.startswith('k_jacobi_sweep') and v < 0.05:
+            name = name + ' (skipped: converged)'
         a = agg[name]
         a[0] += 1
         a[1] += v
