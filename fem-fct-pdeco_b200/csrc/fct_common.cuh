@@ -41,6 +41,16 @@ void fct_set_error(const char* fmt, ...);
 
 struct fct_comm;   // NCCL state (fct_comm.cu)
 
+// CUDA-graph WHILE loop of the low-order Jacobi solve (fct_kernels.cu), cached per operand set
+struct fct_jgraph {
+    void* graph = nullptr;
+    void* exec = nullptr;
+    const double *Lv = nullptr, *b = nullptr, *dinv = nullptr;
+    double *x = nullptr, *tmp = nullptr;
+    double rtol = 0.0;
+    int max_sweeps = 0;
+};
+
 struct fct_ctx {
     int device = 0;
     cudaStream_t stream = 0;
@@ -81,6 +91,8 @@ struct fct_ctx {
     double rtol = 1e-14;
     int32_t max_sweeps = 100;
     int64_t launches = 0;
+    fct_jgraph jgraph;
+    bool use_graph = true;      // FCT_NO_GRAPH=1 falls back to the static launch sequence with device-side early exit
     int32_t last_pairs = 0;     // Jacobi sweep pairs the previous multi-GPU solve needed
     fct_comm* comm = nullptr;
     // halo description (multi-GPU)

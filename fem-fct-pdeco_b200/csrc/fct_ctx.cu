@@ -155,6 +155,7 @@ extern "C" int fct_ctx_create(fct_ctx** out, int device, int32_t n, const int32_
         if (len < 1) { delete c; FCT_CHECK(false, "fct_ctx_create: row %d is empty", r); }
     }
     c->cap = ((cap + 3) & ~3) + 4;
+    { const char* e = getenv("FCT_NO_GRAPH"); c->use_graph = !(e && atoi(e) == 1); }
     {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)
@@ -205,6 +206,8 @@ extern "C" int fct_ctx_destroy(fct_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->jgraph.exec) cudaGraphExecDestroy((cudaGraphExec_t)c->jgraph.exec);
+    if (c->jgraph.graph) cudaGraphDestroy((cudaGraph_t)c->jgraph.graph);
     fct_comm_destroy(c);
     cudaFree(c->rowptr); cudaFree(c->colidx); cudaFree(c->tpos);
     cudaFree(c->cells); cudaFree(c->xy); cudaFree(c->v2c_ptr); cudaFree(c->v2c_idx);

@@ -186,18 +186,29 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
     pipe.init();
     pipe.prologue(nmine);
     double rowsum = 1e300;
+    struct RowIn { int k0, k1; double ml, un, rhs; };
+    auto load_row = [&](int i) {
+        RowIn in{0, 0, 0.0, 0.0, 0.0};
+        if (i < nmine) {
+            const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+            const int r = row_begin + blk * FCT_RB + (int)threadIdx.x;
+            if (r < row_end) {
+                in.k0 = rowptr[r]; in.k1 = rowptr[r + 1];
+                in.ml = ML[r]; in.un = un[r];
+                if (rhs) in.rhs = rhs[r];
+            }
+        }
+        return in;
+    };
+    RowIn cur = load_row(0);
     for (int i = 0; i < nmine; ++i) {
         pipe.prefetch(i, nmine);
+        const RowIn nxt = load_row(i + 1);
         const RowBlock b = pipe.block(i);
         const bool act = (int)threadIdx.x < b.nr;
         const int r = b.r0 + threadIdx.x;
-        int ks = 0, ke = 0;
-        double ml = 0.0, unr = 0.0, rr = 0.0;
-        if (act) {
-            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
-            ml = ML[r]; unr = un[r];
-            if (rhs) rr = rhs[r];
-        }
+        const int ks = cur.k0 - b.ka, ke = cur.k1 - b.ka;
+        const double ml = cur.ml, unr = cur.un, rr = cur.rhs;
         pipe.wait(i, b);
         if (act) {
             const int st = i % FCT_NST_LOW;
@@ -207,18 +218,47 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             const int32_t* sT = pipe.s32(st, 1);
             double dsum = 0.0, lsum = 0.0;
             int kd = ks;
-            for (int k = ks; k < ke; ++k) {
-                const int c = sC[k];
-                if (c == r) { kd = k; continue; }
-                const double a = sign * sA[k];
-                const double at = sign * A[sT[k]];
-                const double d = fmax(0.0, fmax(a, at));
-                dsum += d;
-                double l = dt * (a - d);
-                if (HAS_S) l += dt * sS[k];
-                lsum += l;
-                sL[k] = l;
-                sD[k] = d;
+            const int len = ke - ks;
+            if (len <= 8) {
+                // all transposed-entry gathers a_ji = A[tpos] are issued before the first use
+                double av[8], atv[8];
+                int cv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool p = j < len;
+                    cv[j] = p ? sC[ks + j] : r;
+                    av[j] = p ? sA[ks + j] : 0.0;
+                    atv[j] = p ? A[sT[ks + j]] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < len) {
+                        if (cv[j] == r) { kd = ks + j; continue; }
+                        const double a = sign * av[j];
+                        const double at = sign * atv[j];
+                        const double d = fmax(0.0, fmax(a, at));
+                        dsum += d;
+                        double l = dt * (a - d);
+                        if (HAS_S) l += dt * sS[ks + j];
+                        lsum += l;
+                        sL[ks + j] = l;
+                        sD[ks + j] = d;
+                    }
+                }
+            } else {
+                for (int k = ks; k < ke; ++k) {
+                    const int c = sC[k];
+                    if (c == r) { kd = k; continue; }
+                    const double a = sign * sA[k];
+                    const double at = sign * A[sT[k]];
+                    const double d = fmax(0.0, fmax(a, at));
+                    dsum += d;
+                    double l = dt * (a - d);
+                    if (HAS_S) l += dt * sS[k];
+                    lsum += l;
+                    sL[k] = l;
+                    sD[k] = d;
+                }
             }
             // diagonal: d_ii = -sum_j d_ij
             const double a = sign * sA[kd];
@@ -232,6 +272,7 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             rowsum = fmin(rowsum, lsum);
             bvec[r] = ml * unr + (rhs ? dt * rr : 0.0);
         }
+        cur = nxt;
         __syncthreads();
         unstage_f64(Lv, sL, b);
         unstage_f64(Dv, sD, b);
@@ -375,6 +416,20 @@ __global__ void k_jacobi_decide(unsigned long long* __restrict__ jstate, double 
     jstate[1] = 0ull;
 }
 
+// the same decision as the body of a CUDA-graph WHILE node: keeps looping until converged or out of sweeps
+__global__ void k_jacobi_decide_cond(unsigned long long* __restrict__ jstate, double rtol, unsigned long long max_sweeps,
+                                     cudaGraphConditionalHandle handle) {
+    const double delta = __longlong_as_double((long long)jstate[0]);
+    const double xm = __longlong_as_double((long long)jstate[1]);
+    jstate[5] = jstate[0];
+    jstate[6] = jstate[1];
+    const bool conv = delta <= rtol * xm;
+    if (conv) jstate[3] = 1ull;
+    jstate[0] = 0ull;
+    jstate[1] = 0ull;
+    cudaGraphSetConditional(handle, (conv || jstate[4] >= max_sweeps) ? 0u : 1u);
+}
+
 __global__ void k_jacobi_reset(unsigned long long* __restrict__ jstate) {
     jstate[0] = 0ull; jstate[1] = 0ull; jstate[2] = 0ull; jstate[3] = 0ull; jstate[4] = 0ull;
     jstate[5] = 0ull; jstate[6] = 0ull;
@@ -393,37 +448,67 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
+    struct RowIn { int k0, k1; double ud, ul, ml; };
+    auto load_row = [&](int i) {
+        RowIn in{0, 0, 0.0, 0.0, 1.0};
+        if (i < nmine) {
+            const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+            const int r = row_begin + blk * FCT_RB + (int)threadIdx.x;
+            if (r < row_end) {
+                in.k0 = rowptr[r]; in.k1 = rowptr[r + 1];
+                in.ud = udot[r]; in.ul = ulow[r]; in.ml = ML[r];
+            }
+        }
+        return in;
+    };
+    RowIn cur = load_row(0);
     for (int i = 0; i < nmine; ++i) {
         pipe.prefetch(i, nmine);
+        const RowIn nxt = load_row(i + 1);
         const RowBlock b = pipe.block(i);
-        const bool act = (int)threadIdx.x < b.nr;
-        const int r = b.r0 + threadIdx.x;
-        int ks = 0, ke = 0;
-        double udi = 0.0, uli = 0.0, ml = 1.0;
-        if (act) {
-            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
-            udi = udot[r]; uli = ulow[r]; ml = ML[r];
-        }
         pipe.wait(i, b);
-        if (act) {
+        if ((int)threadIdx.x < b.nr) {
+            const int r = b.r0 + threadIdx.x;
+            const int ks = cur.k0 - b.ka, ke = cur.k1 - b.ka, len = ke - ks;
             const double* sM = pipe.f64(i % FCT_NST2, 0);
             const double* sD = pipe.f64(i % FCT_NST2, 1);
             const int32_t* sC = pipe.s32(i % FCT_NST2, 0);
+            const double udi = cur.ud, uli = cur.ul;
             double pp = 0.0, pn = 0.0, umax = uli, umin = uli;
-            for (int k = ks; k < ke; ++k) {
-                const int c = sC[k];
-                if (c == r) continue;
-                const double ulj = ulow[c];
-                const double f = sM[k] * (udi - udot[c]) + sD[k] * (uli - ulj);
-                pp += fmax(f, 0.0);
-                pn += fmin(f, 0.0);
-                umax = fmax(umax, ulj);
-                umin = fmin(umin, ulj);
+            if (len <= 8) {
+                int c[8];
+                double udj[8], ulj[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c[j] = (j < len) ? sC[ks + j] : r;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { udj[j] = udot[c[j]]; ulj[j] = ulow[c[j]]; }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < len && c[j] != r) {
+                        const double f = sM[ks + j] * (udi - udj[j]) + sD[ks + j] * (uli - ulj[j]);
+                        pp += fmax(f, 0.0);
+                        pn += fmin(f, 0.0);
+                        umax = fmax(umax, ulj[j]);
+                        umin = fmin(umin, ulj[j]);
+                    }
+                }
+            } else {
+                for (int k = ks; k < ke; ++k) {
+                    const int c = sC[k];
+                    if (c == r) continue;
+                    const double ulj = ulow[c];
+                    const double f = sM[k] * (udi - udot[c]) + sD[k] * (uli - ulj);
+                    pp += fmax(f, 0.0);
+                    pn += fmin(f, 0.0);
+                    umax = fmax(umax, ulj);
+                    umin = fmin(umin, ulj);
+                }
             }
             const double qp = umax - uli, qn = umin - uli;
-            Rpos[r] = (pp != 0.0) ? fmin(1.0, ml * qp / (dt * pp)) : 1.0;
-            Rneg[r] = (pn != 0.0) ? fmin(1.0, ml * qn / (dt * pn)) : 1.0;
+            Rpos[r] = (pp != 0.0) ? fmin(1.0, cur.ml * qp / (dt * pp)) : 1.0;
+            Rneg[r] = (pn != 0.0) ? fmin(1.0, cur.ml * qn / (dt * pn)) : 1.0;
         }
+        cur = nxt;
         __syncthreads();
     }
 }
@@ -439,32 +524,67 @@ k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
+    struct RowIn { int k0, k1; double ud, ul, ml, rp, rn; };
+    auto load_row = [&](int i) {
+        RowIn in{0, 0, 0.0, 0.0, 1.0, 1.0, 1.0};
+        if (i < nmine) {
+            const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+            const int r = row_begin + blk * FCT_RB + (int)threadIdx.x;
+            if (r < row_end) {
+                in.k0 = rowptr[r]; in.k1 = rowptr[r + 1];
+                in.ud = udot[r]; in.ul = ulow[r]; in.ml = ML[r]; in.rp = Rpos[r]; in.rn = Rneg[r];
+            }
+        }
+        return in;
+    };
+    RowIn cur = load_row(0);
     for (int i = 0; i < nmine; ++i) {
         pipe.prefetch(i, nmine);
+        const RowIn nxt = load_row(i + 1);
         const RowBlock b = pipe.block(i);
-        const bool act = (int)threadIdx.x < b.nr;
-        const int r = b.r0 + threadIdx.x;
-        int ks = 0, ke = 0;
-        double udi = 0.0, uli = 0.0, ml = 1.0, rpi = 1.0, rni = 1.0;
-        if (act) {
-            ks = rowptr[r] - b.ka; ke = rowptr[r + 1] - b.ka;
-            udi = udot[r]; uli = ulow[r]; ml = ML[r]; rpi = Rpos[r]; rni = Rneg[r];
-        }
         pipe.wait(i, b);
-        if (act) {
+        if ((int)threadIdx.x < b.nr) {
+            const int r = b.r0 + threadIdx.x;
+            const int ks = cur.k0 - b.ka, ke = cur.k1 - b.ka, len = ke - ks;
             const double* sM = pipe.f64(i % FCT_NST2, 0);
             const double* sD = pipe.f64(i % FCT_NST2, 1);
             const int32_t* sC = pipe.s32(i % FCT_NST2, 0);
+            const double udi = cur.ud, uli = cur.ul, rpi = cur.rp, rni = cur.rn;
             double fbar = 0.0;
-            for (int k = ks; k < ke; ++k) {
-                const int c = sC[k];
-                if (c == r) continue;
-                const double f = sM[k] * (udi - udot[c]) + sD[k] * (uli - ulow[c]);
-                const double alpha = (f > 0.0) ? fmin(rpi, Rneg[c]) : fmin(rni, Rpos[c]);
-                fbar += alpha * f;
+            if (len <= 8) {
+                // two half-rows of four: keeps 16 gathers in flight without blowing the register budget
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int c[4];
+                    double udj[4], ulj[4], rpj[4], rnj[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) c[j] = (4 * h + j < len) ? sC[ks + 4 * h + j] : r;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        udj[j] = udot[c[j]]; ulj[j] = ulow[c[j]]; rpj[j] = Rpos[c[j]]; rnj[j] = Rneg[c[j]];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = ks + 4 * h + j;
+                        if (4 * h + j < len && c[j] != r) {
+                            const double f = sM[k] * (udi - udj[j]) + sD[k] * (uli - ulj[j]);
+                            const double alpha = (f > 0.0) ? fmin(rpi, rnj[j]) : fmin(rni, rpj[j]);
+                            fbar += alpha * f;
+                        }
+                    }
+                }
+            } else {
+                for (int k = ks; k < ke; ++k) {
+                    const int c = sC[k];
+                    if (c == r) continue;
+                    const double f = sM[k] * (udi - udot[c]) + sD[k] * (uli - ulow[c]);
+                    const double alpha = (f > 0.0) ? fmin(rpi, Rneg[c]) : fmin(rni, Rpos[c]);
+                    fbar += alpha * f;
+                }
             }
-            uout[r] = uli + dt * fbar / ml;
+            uout[r] = uli + dt * fbar / cur.ml;
         }
+        cur = nxt;
         __syncthreads();
     }
 }
@@ -795,6 +915,50 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
             LAUNCH_PIPE_NST(ctx, k_jacobi_sweep_gen, ctx->rowptr, ctx->colidx, Lv, b, dinv, xin, xout, ctx->jstate, \
                             chk, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);                                \
     } while (0)
+    if (!ctx->comm && dinv && ctx->use_graph) {
+        // Single GPU, FCT low-order system: the sweep pairs are the body of a CUDA-graph WHILE node whose condition the
+        // decide kernel sets on the device -- exactly as many sweeps as needed are launched, with no host round trip
+        // and no skipped launches.  The graph is rebuilt only if an operand pointer or a solver option changes.
+        fct_jgraph& jg = ctx->jgraph;
+        if (!jg.exec || jg.Lv != Lv || jg.b != b || jg.dinv != dinv || jg.x != x || jg.tmp != tmp || jg.rtol != rtol ||
+            jg.max_sweeps != max_sweeps) {
+            if (jg.exec) { cudaGraphExecDestroy((cudaGraphExec_t)jg.exec); jg.exec = nullptr; }
+            if (jg.graph) { cudaGraphDestroy((cudaGraph_t)jg.graph); jg.graph = nullptr; }
+            cudaGraph_t g;
+            FCT_CUDA(cudaGraphCreate(&g, 0));
+            cudaGraphConditionalHandle h;
+            FCT_CUDA(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));
+            cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+            np.conditional.handle = h;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            cudaGraphNode_t node;
+            FCT_CUDA(cudaGraphAddNode(&node, g, nullptr, 0, &np));
+            cudaGraph_t body = np.conditional.phGraph_out[0];
+            cudaStream_t user = ctx->stream;
+            ctx->stream = ctx->copy_stream;          // capture stream: launches below are recorded, not executed
+            const int64_t launches0 = ctx->launches;
+            FCT_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            JACOBI_LAUNCH(x, tmp, 0);
+            JACOBI_LAUNCH(tmp, x, 1);
+            k_jacobi_decide_cond<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol, (unsigned long long)max_sweeps, h);
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, nullptr);
+            ctx->stream = user;
+            ctx->launches = launches0;
+            if (ce != cudaSuccess) {
+                fct_set_error("fct_jacobi_solve: graph capture failed: %s", cudaGetErrorString(ce));
+                cudaGraphDestroy(g);
+                return 1;
+            }
+            cudaGraphExec_t ex;
+            FCT_CUDA(cudaGraphInstantiate(&ex, g, 0));
+            jg.graph = g; jg.exec = ex;
+            jg.Lv = Lv; jg.b = b; jg.dinv = dinv; jg.x = x; jg.tmp = tmp; jg.rtol = rtol; jg.max_sweeps = max_sweeps;
+        }
+        FCT_CUDA(cudaGraphLaunch((cudaGraphExec_t)jg.exec, ctx->stream));
+        ctx->launches += 3;      // at least one body iteration; the executed sweeps are counted in jstate[4]
+        return 0;
+    }
     if (ctx->comm) {
         // Multi-GPU: a skipped sweep would still pay its NCCL exchanges, so sweeps are enqueued in a budget learnt
         // from the previous solve and the (all-reduced, hence rank-uniform) convergence flag is read back before
