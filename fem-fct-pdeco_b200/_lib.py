@@ -84,6 +84,9 @@ SIGNATURES = {
     "fct_nccl_unique_id": [_p],
     "fct_ctx_init_comm": [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32],
     "fct_halo_exchange": [_p, _p],
+    "fct_p2p_create": [_p, _i32, _i32, _i32, _p],
+    "fct_p2p_connect": [_p, _p],
+    "fct_p2p_error": [_p, _pi32],
     "fct_launch_count": [_p, _pi64],
     "fct_event_create": [_p, C.POINTER(_p)],
     "fct_event_record": [_p, _p],

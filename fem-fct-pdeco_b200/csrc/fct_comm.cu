@@ -125,8 +125,12 @@ static int exchange_ranges(fct_ctx* ctx, double* a, int64_t slo0, int64_t slo1, 
     return 0;
 }
 
+bool fct_p2p_ready(const fct_ctx* ctx);
+int fct_p2p_exchange(fct_ctx* ctx, double* v0, double* v1);
+
 int fct_halo_exchange_if(fct_ctx* ctx, double* vec) {
     if (!ctx->comm || ctx->comm->world == 1) return 0;
+    if (fct_p2p_ready(ctx)) return fct_p2p_exchange(ctx, vec, nullptr);
     return exchange_ranges(ctx, vec, ctx->send_lo[0], ctx->send_lo[1], 0, ctx->row_begin, ctx->send_hi[0],
                            ctx->send_hi[1], ctx->row_end, ctx->n);
 }
@@ -157,4 +161,12 @@ int fct_allreduce_sum_dev(fct_ctx* ctx, double* dev, int count) {
     if (!ctx->comm || ctx->comm->world == 1) return 0;
     FCT_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, ctx->comm->comm, ctx->stream));
     return 0;
+}
+
+// two vectors in one message (R+ and R-)
+int fct_halo_exchange2_if(fct_ctx* ctx, double* v0, double* v1) {
+    if (!ctx->comm || ctx->comm->world == 1) return 0;
+    if (fct_p2p_ready(ctx)) return fct_p2p_exchange(ctx, v0, v1);
+    if (fct_halo_exchange_if(ctx, v0)) return 1;
+    return fct_halo_exchange_if(ctx, v1);
 }

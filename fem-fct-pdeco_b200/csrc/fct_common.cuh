@@ -40,6 +40,7 @@ void fct_set_error(const char* fmt, ...);
     } while (0)
 
 struct fct_comm;   // NCCL state (fct_comm.cu)
+struct fct_p2p;    // NVLink peer-memory mailboxes (fct_p2p.cu)
 
 // CUDA-graph WHILE loop of the low-order Jacobi solve (fct_kernels.cu), cached per operand set
 struct fct_jgraph {
@@ -95,6 +96,7 @@ struct fct_ctx {
     bool use_graph = true;      // FCT_NO_GRAPH=1 falls back to the static launch sequence with device-side early exit
     int32_t last_pairs = 0;     // Jacobi sweep pairs the previous multi-GPU solve needed
     fct_comm* comm = nullptr;
+    fct_p2p* p2p = nullptr;
     // halo description (multi-GPU)
     int32_t send_lo[2] = {0, 0}, send_hi[2] = {0, 0};
 };

@@ -115,6 +115,7 @@ int fct_build_tpos(fct_ctx* ctx);
 int fct_assembly_configure(fct_ctx* ctx);
 int fct_drivers_configure(fct_ctx* ctx);
 void fct_comm_destroy(fct_ctx* ctx);
+void fct_p2p_destroy(fct_ctx* ctx);
 
 template <typename T>
 static int dev_alloc(T** p, size_t count) {
@@ -208,6 +209,7 @@ extern "C" int fct_ctx_destroy(fct_ctx* c) {
     cudaDeviceSynchronize();
     if (c->jgraph.exec) cudaGraphExecDestroy((cudaGraphExec_t)c->jgraph.exec);
     if (c->jgraph.graph) cudaGraphDestroy((cudaGraph_t)c->jgraph.graph);
+    fct_p2p_destroy(c);
     fct_comm_destroy(c);
     cudaFree(c->rowptr); cudaFree(c->colidx); cudaFree(c->tpos);
     cudaFree(c->cells); cudaFree(c->xy); cudaFree(c->v2c_ptr); cudaFree(c->v2c_idx);

@@ -844,6 +844,9 @@ extern "C" int fct_spmv(fct_ctx* ctx, const double* A, const double* x, double a
 }
 
 int fct_halo_exchange_if(fct_ctx* ctx, double* vec);   // no-op without a communicator (fct_comm.cu)
+int fct_halo_exchange2_if(fct_ctx* ctx, double* v0, double* v1);
+bool fct_p2p_ready(const fct_ctx* ctx);
+int fct_p2p_max2_decide(fct_ctx* ctx, double rtol, int max_sweeps, int use_handle, cudaGraphConditionalHandle handle);
 int fct_halo_allreduce_max2(fct_ctx* ctx, unsigned long long* two_words);
 
 extern "C" int fct_chebsi(fct_ctx* ctx, const double* M, const double* Md, const double* b, double* y, int32_t iters,
@@ -915,7 +918,8 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
             LAUNCH_PIPE_NST(ctx, k_jacobi_sweep_gen, ctx->rowptr, ctx->colidx, Lv, b, dinv, xin, xout, ctx->jstate, \
                             chk, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);                                \
     } while (0)
-    if (!ctx->comm && dinv && ctx->use_graph) {
+    const bool p2p = ctx->comm && fct_p2p_ready(ctx);
+    if ((!ctx->comm || p2p) && dinv && ctx->use_graph) {
         // Single GPU, FCT low-order system: the sweep pairs are the body of a CUDA-graph WHILE node whose condition the
         // decide kernel sets on the device -- exactly as many sweeps as needed are launched, with no host round trip
         // and no skipped launches.  The graph is rebuilt only if an operand pointer or a solver option changes.
@@ -940,8 +944,14 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
             const int64_t launches0 = ctx->launches;
             FCT_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
             JACOBI_LAUNCH(x, tmp, 0);
+            if (p2p) fct_halo_exchange_if(ctx, tmp);
             JACOBI_LAUNCH(tmp, x, 1);
-            k_jacobi_decide_cond<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol, (unsigned long long)max_sweeps, h);
+            if (p2p) {
+                fct_halo_exchange_if(ctx, x);
+                fct_p2p_max2_decide(ctx, rtol, max_sweeps, 1, h);
+            } else {
+                k_jacobi_decide_cond<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol, (unsigned long long)max_sweeps, h);
+            }
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, nullptr);
             ctx->stream = user;
             ctx->launches = launches0;
@@ -1055,8 +1065,7 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     // 5-7. fluxes, P, Q, R
     LAUNCH_PIPE(ctx, k_flux_limits, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, dt, Rp, Rn,
                 ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
-    if (fct_halo_exchange_if(ctx, Rp)) return 1;
-    if (fct_halo_exchange_if(ctx, Rn)) return 1;
+    if (fct_halo_exchange2_if(ctx, Rp, Rn)) return 1;
     // 8-9. limited sum + update
     LAUNCH_PIPE(ctx, k_flux_apply, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, Rp, Rn, dt,
                 uout, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);

@@ -132,6 +132,32 @@ def init_comm(ctx, lp, broadcast_bytes):
                                 lp.send_hi[1]))
 
 
+def init_p2p(ctx, lp, all_gather_bytes):
+    """NVLink peer-memory mailboxes (fct_p2p_*): `all_gather_bytes(b) -> [bytes of rank 0, rank 1, ...]`."""
+    max_halo = int(max(np.max(lp.bounds[:-1] - lp.g0_all), np.max(lp.g1_all - lp.bounds[1:]), 1))
+    buf = (C.c_ubyte * 64)()
+    check(lib.fct_p2p_create(ctx.handle, lp.rank, lp.world, max_halo, buf))
+    handles = all_gather_bytes(bytes(buf))
+    blob = (C.c_ubyte * (64 * lp.world)).from_buffer_copy(b"".join(handles))
+    check(lib.fct_p2p_connect(ctx.handle, blob))
+
+
+def p2p_error(ctx):
+    e = C.c_int32()
+    check(lib.fct_p2p_error(ctx.handle, C.byref(e)))
+    return e.value
+
+
+def torch_all_gatherer():
+    import torch.distributed as dist
+
+    def ag(b):
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, b)
+        return out
+    return ag
+
+
 def torch_broadcaster():
     import torch.distributed as dist
 
@@ -148,6 +174,8 @@ def setup_rank(mesh, rank, world, local_rank):
     ctx = lp.make_context(local_rank)
     if world > 1:
         init_comm(ctx, lp, torch_broadcaster())
+        if os.environ.get("FCT_NO_P2P", "0") != "1":
+            init_p2p(ctx, lp, torch_all_gatherer())
     ctx.assemble_static()
     return lp, ctx
 
@@ -229,7 +257,7 @@ def bench_multi(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic {n_cells}^2-cell unit-square drift-control advection FCT PDECO "
                                    f"(BASELINE config 5): {n_glob} DoF, {nnz_glob} nnz, row-block partitioned over "
-                                   f"{world} GPUs (one-ring halo, NCCL send/recv); bench step = state+adjoint sweeps "
+                                   f"{world} GPUs (one-ring halo over NVLink peer mailboxes); bench step = state+adjoint sweeps "
                                    f"over {nt} time levels + gradient + cost",
                        "time_levels": nt, "dt": dt, "jacobi_sweeps_per_step": k_mean, "cost_functional": J,
                        "halo_rows": [int(lp.row_begin), int(lp.n - lp.row_end)],

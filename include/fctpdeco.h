@@ -209,6 +209,13 @@ int fct_ctx_init_comm(fct_ctx* ctx, const void* id_128bytes, int32_t rank, int32
                       int32_t send_lo_begin, int32_t send_lo_end,    /* local rows sent to rank-1          */
                       int32_t send_hi_begin, int32_t send_hi_end);   /* local rows sent to rank+1          */
 int fct_halo_exchange(fct_ctx* ctx, double* vec_dev);                /* refresh halo entries of a vector    */
+/* NVLink peer-memory mailboxes (CUDA IPC) replacing NCCL send/recv for the halo exchanges and the Jacobi stopping
+ * test: fct_p2p_create exports this rank's region (64-byte cudaIpcMemHandle); after gathering all ranks' handles
+ * (rank order) fct_p2p_connect maps them.  Once connected every halo exchange is one kernel (push over NVLink, wait,
+ * unpack) and the multi-GPU Jacobi loop runs as a CUDA-graph WHILE node.  fct_p2p_error reports a timed-out wait. */
+int fct_p2p_create(fct_ctx* ctx, int32_t rank, int32_t world, int32_t max_halo, void* handle_out_64bytes);
+int fct_p2p_connect(fct_ctx* ctx, const void* all_handles_world_x_64bytes);
+int fct_p2p_error(fct_ctx* ctx, int32_t* error_host);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* CUDA events on the context's stream (what bench.py times kernels with) */
