@@ -84,6 +84,7 @@ SIGNATURES = {
     "fct_nccl_unique_id": [_p],
     "fct_ctx_init_comm": [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32],
     "fct_halo_exchange": [_p, _p],
+    "fct_ctx_set_rings": [_p, _i32, _pi32, _pi32],
     "fct_p2p_create": [_p, _i32, _i32, _i32, _p],
     "fct_p2p_connect": [_p, _p],
     "fct_p2p_error": [_p, _pi32],

@@ -457,7 +457,7 @@ static int launch_vector(fct_ctx* ctx, const FormArgs& fa, double scale, int acc
     const int nb = fct_nblocks(ctx);
     if (nb <= 0) return 0;
     k_assemble_vector<KIND><<<nb, FCT_RB, 0, ctx->stream>>>(ctx->v2c_ptr, ctx->v2c_idx, ctx->cells, ctx->xy, fa, scale,
-                                                            accumulate, out, ctx->row_begin, ctx->row_end);
+                                                            accumulate, out, ctx->cur_rb, ctx->cur_re);
     ctx->launches++;
     return fct_launch_error(ctx, "fct_assemble_vector");
 }

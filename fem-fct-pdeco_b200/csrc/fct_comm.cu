@@ -168,5 +168,5 @@ int fct_halo_exchange2_if(fct_ctx* ctx, double* v0, double* v1) {
     if (!ctx->comm || ctx->comm->world == 1) return 0;
     if (fct_p2p_ready(ctx)) return fct_p2p_exchange(ctx, v0, v1);
     if (fct_halo_exchange_if(ctx, v0)) return 1;
-    return fct_halo_exchange_if(ctx, v1);
+    return v1 ? fct_halo_exchange_if(ctx, v1) : 0;
 }

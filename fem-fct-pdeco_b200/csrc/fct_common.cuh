@@ -50,6 +50,7 @@ struct fct_jgraph {
     double *x = nullptr, *tmp = nullptr;
     double rtol = 0.0;
     int max_sweeps = 0;
+    int depth = 0;
 };
 
 struct fct_ctx {
@@ -59,6 +60,12 @@ struct fct_ctx {
     int32_t n = 0;              // local rows (= local vector length)
     int64_t nnz = 0;
     int32_t row_begin = 0, row_end = 0;
+    // Deep halos (multi-GPU): ring j = local rows within j mesh rings of the owned rows, ring 0 = owned, ring `depth`
+    // = all local rows.  A pass computed on ring j reads its inputs on ring j+1, so after one exchange (valid on ring
+    // `depth`) up to `depth` dependent passes run without communication, each on a ring one smaller.
+    int32_t depth = 1;
+    int32_t ring_lo[9] = {0}, ring_hi[9] = {0};
+    int32_t cur_rb = 0, cur_re = 0;          // row range of the next row-block launches (default: the owned rows)
     int32_t cap = 0;            // max staged entries of any row block (incl. alignment slack)
     int32_t max_row = 0;
     int32_t grid_cap = 148 * 8; // persistent grid: SMs x resident 256-thread CTAs
@@ -101,7 +108,13 @@ struct fct_ctx {
     int32_t send_lo[2] = {0, 0}, send_hi[2] = {0, 0};
 };
 
-static inline int fct_nblocks(const fct_ctx* c) { return (c->row_end - c->row_begin + FCT_RB - 1) / FCT_RB; }
+static inline int fct_nblocks(const fct_ctx* c) { return (c->cur_re - c->cur_rb + FCT_RB - 1) / FCT_RB; }
+static inline void fct_set_ring(fct_ctx* c, int j) {
+    if (j < 0) j = 0;
+    if (j > c->depth) j = c->depth;
+    c->cur_rb = c->ring_lo[j];
+    c->cur_re = c->ring_hi[j];
+}
 // launch grid of a persistent row-block kernel over `nblocks` row blocks
 static inline int fct_grid(const fct_ctx* c, int nblocks) { return nblocks < c->grid_cap ? nblocks : c->grid_cap; }
 

@@ -139,16 +139,17 @@ extern "C" int fct_ctx_create(fct_ctx** out, int device, int32_t n, const int32_
     c->nnz = rowptr[n];
     c->row_begin = row_begin;
     c->row_end = row_end;
-    // staging capacity over the owned row blocks
+    c->cur_rb = row_begin;
+    c->cur_re = row_end;
+    c->depth = 1;
+    c->ring_lo[0] = row_begin; c->ring_hi[0] = row_end;
+    for (int j = 1; j < 9; ++j) { c->ring_lo[j] = 0; c->ring_hi[j] = n; }
+    // staging capacity: any window of FCT_RB consecutive rows (row-block launches start at arbitrary ring boundaries)
     int cap = 0, maxrow = 0;
-    // (two blockings: owned rows from row_begin for the FCT passes, all local rows from 0 for assembly)
-    for (int pass = 0; pass < 2; ++pass) {
-        const int rb = pass ? 0 : row_begin, re = pass ? n : row_end;
-        for (int r0 = rb; r0 < re; r0 += FCT_RB) {
-            const int r1 = (r0 + FCT_RB < re) ? r0 + FCT_RB : re;
-            const int cnt = rowptr[r1] - (rowptr[r0] & ~(FCT_ALIGN - 1));
-            if (cnt > cap) cap = cnt;
-        }
+    for (int r0 = 0; r0 < n; ++r0) {
+        const int r1 = (r0 + FCT_RB < n) ? r0 + FCT_RB : n;
+        const int cnt = rowptr[r1] - (rowptr[r0] & ~(FCT_ALIGN - 1));
+        if (cnt > cap) cap = cnt;
     }
     for (int r = 0; r < n; ++r) {
         const int len = rowptr[r + 1] - rowptr[r];
@@ -350,5 +351,18 @@ extern "C" int fct_host_alloc(fct_ctx* ctx, void** p, int64_t bytes) {
 extern "C" int fct_host_free(fct_ctx* ctx, void* p) {
     FCT_CHECK(ctx, "fct_host_free: null context");
     if (p) FCT_CUDA(cudaFreeHost(p));
+    return 0;
+}
+
+extern "C" int fct_ctx_set_rings(fct_ctx* ctx, int32_t depth, const int32_t* ring_lo, const int32_t* ring_hi) {
+    FCT_CHECK(ctx && ring_lo && ring_hi, "fct_ctx_set_rings: null argument");
+    FCT_CHECK(depth >= 1 && depth <= 8, "fct_ctx_set_rings: depth must be in 1..8");
+    FCT_CHECK(ring_lo[0] == ctx->row_begin && ring_hi[0] == ctx->row_end, "fct_ctx_set_rings: ring 0 must be the owned rows");
+    FCT_CHECK(ring_lo[depth] == 0 && ring_hi[depth] == ctx->n, "fct_ctx_set_rings: ring `depth` must be all local rows");
+    for (int j = 1; j <= depth; ++j)
+        FCT_CHECK(ring_lo[j] <= ring_lo[j - 1] && ring_hi[j] >= ring_hi[j - 1], "fct_ctx_set_rings: rings must be nested");
+    ctx->depth = depth;
+    for (int j = 0; j <= depth; ++j) { ctx->ring_lo[j] = ring_lo[j]; ctx->ring_hi[j] = ring_hi[j]; }
+    for (int j = depth + 1; j < 9; ++j) { ctx->ring_lo[j] = 0; ctx->ring_hi[j] = ctx->n; }
     return 0;
 }

@@ -11,6 +11,8 @@
 extern __shared__ __align__(16) unsigned char fct_smem[];
 
 int fct_halo_exchange_if(fct_ctx* ctx, double* vec);
+int fct_chebsi_v(fct_ctx* ctx, const double* M, const double* Md, const double* b, double* y, int32_t iters, double lmin,
+                 double lmax, int vb, int* vy);
 int fct_allreduce_sum_dev(fct_ctx* ctx, double* dev, int count);
 
 // sweeps bookkeeping across the steps of a time loop: acc[0] += sweeps of the step just finished,
@@ -83,7 +85,9 @@ extern "C" int fct_advdrift_adjoint(fct_ctx* ctx, const double* c_traj, const do
         // p_rhs = assemble((uhat_n - u_n) v dx) = M (uhat_n - u_n)     (:255)
         k_sub<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->n, uhat_traj + i * n, u_traj + i * n, diff);
         ctx->launches++;
+        fct_set_ring(ctx, ctx->depth - 1);         // the FCT step wants its right-hand side on ring depth-1
         if (fct_spmv(ctx, ctx->M, diff, 1.0, 0.0, nullptr, rhs)) return 1;
+        fct_set_ring(ctx, 0);
         if (fct_step(ctx, ctx->Avals, 1.0, nullptr, rhs, p_traj + (i + 1) * n, dt, p_traj + i * n, nullptr)) return 1;
         k_sweeps_accumulate<<<1, 1, 0, ctx->stream>>>(ctx->jstate, ctx->jstate + 8);
         ctx->launches++;
@@ -100,10 +104,12 @@ extern "C" int fct_advdrift_gradient(fct_ctx* ctx, const double* c_traj, const d
     double* rhs = ctx->w[11];
     for (int i = 0; i <= num_steps; ++i) {
         // rhs_dk = -(beta M c + assemble(p (b.grad u) v dx));  dk = ChebSI(rhs_dk, M, diag M, 20, .5, 2)   (:272-275)
+        fct_set_ring(ctx, ctx->depth - 1);
         if (fct_assemble_vector(ctx, FCT_LOAD_DRIFT_GRAD, p_traj + i * n, u_traj + i * n, nullptr, nullptr, bx, by, 1.0, 0, t))
             return 1;
         if (fct_spmv(ctx, ctx->M, c_traj + i * n, -beta, -1.0, t, rhs)) return 1;
-        if (fct_chebsi(ctx, ctx->M, ctx->Mdiag, rhs, d_traj + i * n, 20, 0.5, 2.0)) return 1;
+        fct_set_ring(ctx, 0);
+        if (fct_chebsi_v(ctx, ctx->M, ctx->Mdiag, rhs, d_traj + i * n, 20, 0.5, 2.0, ctx->depth - 1, nullptr)) return 1;
         if (fct_halo_exchange_if(ctx, d_traj + i * n)) return 1;
     }
     return 0;

@@ -322,8 +322,8 @@ template <int NST, bool SEP>
 __device__ __forceinline__ void
 jacobi_sweep_body(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Lv,
                const double* __restrict__ bvec, const double* __restrict__ dinv, const double* __restrict__ x,
-               double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check, int row_begin, int row_end,
-               int64_t nnz, int cap) {
+               double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check, int own_rb, int own_re,
+               int row_begin, int row_end, int64_t nnz, int cap) {
     if (*reinterpret_cast<volatile unsigned long long*>(jstate + 3)) return;
     __shared__ __align__(8) uint64_t bars[NST];
     __shared__ double sred[FCT_RB / 32];
@@ -368,7 +368,7 @@ jacobi_sweep_body(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                 xn = (cur.b - acc) / diag;
             }
             xnew[r] = xn;
-            if (check) {
+            if (check && r >= own_rb && r < own_re) {      // the stopping test looks at the owned rows only
                 delta = fmax(delta, fabs(xn - cur.x));
                 xa = fmax(xa, fabs(xn));
             }
@@ -391,17 +391,19 @@ template <int NST>
 __global__ void __launch_bounds__(FCT_RB, 5)
 k_jacobi_sweep(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Lv,
                const double* __restrict__ bvec, const double* __restrict__ dinv, const double* __restrict__ x,
-               double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check, int row_begin, int row_end,
-               int64_t nnz, int cap) {
-    jacobi_sweep_body<NST, true>(rowptr, colidx, Lv, bvec, dinv, x, xnew, jstate, check, row_begin, row_end, nnz, cap);
+               double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check, int own_rb, int own_re,
+               int row_begin, int row_end, int64_t nnz, int cap) {
+    jacobi_sweep_body<NST, true>(rowptr, colidx, Lv, bvec, dinv, x, xnew, jstate, check, own_rb, own_re, row_begin, row_end,
+                                 nnz, cap);
 }
 template <int NST>
 __global__ void __launch_bounds__(FCT_RB)
 k_jacobi_sweep_gen(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Lv,
                    const double* __restrict__ bvec, const double* __restrict__ dinv, const double* __restrict__ x,
-                   double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check, int row_begin,
-                   int row_end, int64_t nnz, int cap) {
-    jacobi_sweep_body<NST, false>(rowptr, colidx, Lv, bvec, dinv, x, xnew, jstate, check, row_begin, row_end, nnz, cap);
+                   double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check, int own_rb, int own_re,
+                   int row_begin, int row_end, int64_t nnz, int cap) {
+    jacobi_sweep_body<NST, false>(rowptr, colidx, Lv, bvec, dinv, x, xnew, jstate, check, own_rb, own_re, row_begin,
+                                  row_end, nnz, cap);
 }
 
 // After a checked sweep (and, multi-GPU, after the max-allreduce of jstate[0..1]): decide convergence.
@@ -838,7 +840,7 @@ extern "C" int fct_spmv(fct_ctx* ctx, const double* A, const double* x, double a
                         double* y) {
     FCT_CHECK(ctx && A && x && y, "fct_spmv: null argument");
     FCT_CHECK(beta == 0.0 || z, "fct_spmv: beta != 0 needs z");
-    LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, x, alpha, beta, z, y, ctx->row_begin, ctx->row_end,
+    LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, x, alpha, beta, z, y, ctx->cur_rb, ctx->cur_re,
                 ctx->nnz, ctx->cap);
     return fct_launch_error(ctx, "fct_spmv");
 }
@@ -849,83 +851,142 @@ bool fct_p2p_ready(const fct_ctx* ctx);
 int fct_p2p_max2_decide(fct_ctx* ctx, double rtol, int max_sweeps, int use_handle, cudaGraphConditionalHandle handle);
 int fct_halo_allreduce_max2(fct_ctx* ctx, unsigned long long* two_words);
 
-extern "C" int fct_chebsi(fct_ctx* ctx, const double* M, const double* Md, const double* b, double* y, int32_t iters,
-                          double lmin, double lmax) {
-    FCT_CHECK(ctx && M && Md && b && y, "fct_chebsi: null argument");
-    FCT_CHECK(iters >= 1, "fct_chebsi: iters must be >= 1");
+// ChebSI with deep-halo bookkeeping.  `vb`: ring on which the right-hand side b is valid.  Iteration k runs on ring
+// min(valid(y_{k-1}) - 1, vb); when that would drop below the owned rows the two live iterates are exchanged in one
+// message (valid on ring `depth` again).  Returns in *vy the ring on which the result is valid.
+int fct_chebsi_v(fct_ctx* ctx, const double* M, const double* Md, const double* b, double* y, int32_t iters, double lmin,
+                 double lmax, int vb, int* vy) {
     // helpers.py:164-180
     const double rho = (lmax - lmin) / (lmax + lmin);
     const double dscale = (lmin + lmax) / 2;
     double omega = 0.0;
     // rotating buffers: the result of iteration k lands in buf[k % 3]; the last one is redirected to y
     double* buf[3] = {ctx->w[0], ctx->w[1], ctx->w[2]};
-    const double* ymid = nullptr;
-    const double* yold = nullptr;
-    const int nb = fct_nblocks(ctx);
+    double* ymid = nullptr;
+    double* yold = nullptr;
+    const int K = ctx->depth;
+    if (vb > K) vb = K;
+    int vmid = K;
     for (int k = 1; k <= iters; ++k) {
         if (k == 2) omega = 1 / (1 - rho * rho / 2);
         else omega = 1 / (1 - (omega * rho * rho) / 4);
         double* ynew = (k == iters) ? y : buf[k % 3];
         if (k == 1) {
+            fct_set_ring(ctx, vb);
+            const int nb = fct_nblocks(ctx);
             if (nb > 0) {
-                k_cheb_first<<<nb, FCT_RB, 0, ctx->stream>>>(b, Md, dscale, omega, ynew, ctx->row_begin, ctx->row_end);
+                k_cheb_first<<<nb, FCT_RB, 0, ctx->stream>>>(b, Md, dscale, omega, ynew, ctx->cur_rb, ctx->cur_re);
                 ctx->launches++;
             }
+            vmid = vb;
         } else {
+            int r = vmid - 1 < vb ? vmid - 1 : vb;
+            if (r < 0) {
+                if (fct_halo_exchange2_if(ctx, ymid, yold)) return 1;      // yold may be null (k == 2)
+                vmid = K;
+                r = K - 1 < vb ? K - 1 : vb;
+                if (r < 0) r = 0;
+            }
+            fct_set_ring(ctx, r);
             LAUNCH_PIPE_NST(ctx, k_cheb_iter, ctx->rowptr, ctx->colidx, M, Md, b, ymid, yold, ynew, omega, dscale,
-                        yold != nullptr, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
-        }
-        if (k < iters) {
-            if (fct_halo_exchange_if(ctx, ynew)) return 1;
+                            yold != nullptr, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+            vmid = r;
         }
         yold = ymid;
         ymid = ynew;
     }
+    fct_set_ring(ctx, 0);
+    if (vy) *vy = vmid;
     return fct_launch_error(ctx, "fct_chebsi");
+}
+
+extern "C" int fct_chebsi(fct_ctx* ctx, const double* M, const double* Md, const double* b, double* y, int32_t iters,
+                          double lmin, double lmax) {
+    FCT_CHECK(ctx && M && Md && b && y, "fct_chebsi: null argument");
+    FCT_CHECK(iters >= 1, "fct_chebsi: iters must be >= 1");
+    return fct_chebsi_v(ctx, M, Md, b, y, iters, lmin, lmax, 0, nullptr);    // b is only trusted on the owned rows
 }
 
 extern "C" int fct_artificial_diffusion(fct_ctx* ctx, const double* mat, double* D) {
     FCT_CHECK(ctx && mat && D, "fct_artificial_diffusion: null argument");
-    LAUNCH_ROWS(ctx, k_art_diff, 1, 2, ctx->rowptr, ctx->colidx, ctx->tpos, mat, D, ctx->row_begin, ctx->row_end,
+    LAUNCH_ROWS(ctx, k_art_diff, 1, 2, ctx->rowptr, ctx->colidx, ctx->tpos, mat, D, ctx->cur_rb, ctx->cur_re,
                 ctx->nnz, ctx->cap);
     return fct_launch_error(ctx, "fct_artificial_diffusion");
 }
 
 extern "C" int fct_row_lump(fct_ctx* ctx, const double* mat, double* out) {
     FCT_CHECK(ctx && mat && out, "fct_row_lump: null argument");
-    LAUNCH_ROWS(ctx, k_row_lump, 1, 1, ctx->rowptr, ctx->colidx, mat, out, (double*)nullptr, ctx->row_begin,
-                ctx->row_end, ctx->nnz, ctx->cap);
+    LAUNCH_ROWS(ctx, k_row_lump, 1, 1, ctx->rowptr, ctx->colidx, mat, out, (double*)nullptr, ctx->cur_rb,
+                ctx->cur_re, ctx->nnz, ctx->cap);
     return fct_launch_error(ctx, "fct_row_lump");
 }
 
 int fct_row_lump_diag(fct_ctx* ctx, const double* mat, double* out, double* diag) {
-    LAUNCH_ROWS(ctx, k_row_lump, 1, 1, ctx->rowptr, ctx->colidx, mat, out, diag, ctx->row_begin, ctx->row_end,
+    LAUNCH_ROWS(ctx, k_row_lump, 1, 1, ctx->rowptr, ctx->colidx, mat, out, diag, ctx->cur_rb, ctx->cur_re,
                 ctx->nnz, ctx->cap);
     return fct_launch_error(ctx, "fct_row_lump_diag");
 }
 
 // Jacobi solve of Lv x = b, x holds the initial guess on entry and the result on exit (device-side early exit;
 // sweeps run in pairs so that the result always lands back in x).
-int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const double* dinv, double* x, double* tmp,
-                     double rtol, int max_sweeps) {
-    const int pairs = (max_sweeps + 1) / 2;
+// One Jacobi "cycle": the sweeps that fit between two halo exchanges.  With halo depth k the iterate is valid on ring k
+// after an exchange, sweep s of the cycle runs on ring k-1-s, and the cycle ends with one exchange (depth 1: the
+// classic pair with an exchange after each sweep).  The stopping test (owned rows, all-reduced max) is evaluated
+// after every second sweep.  `handle` != 0: the cycle is the body of a CUDA-graph WHILE node.
+static int jacobi_cycle(fct_ctx* ctx, const double* Lv, const double* b, const double* dinv, double* x, double* tmp,
+                        double rtol, int max_sweeps, bool p2p, int use_handle, cudaGraphConditionalHandle handle) {
 #define JACOBI_LAUNCH(xin, xout, chk)                                                                              \
     do {                                                                                                           \
         if (dinv)                                                                                                  \
             LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, dinv, xin, xout, ctx->jstate, chk, \
-                            ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);                                     \
+                            ctx->row_begin, ctx->row_end, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);           \
         else                                                                                                       \
             LAUNCH_PIPE_NST(ctx, k_jacobi_sweep_gen, ctx->rowptr, ctx->colidx, Lv, b, dinv, xin, xout, ctx->jstate, \
-                            chk, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);                                \
+                            chk, ctx->row_begin, ctx->row_end, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);      \
     } while (0)
+    const int K = ctx->depth;
+    const int npairs = K >= 2 ? K / 2 : 1;
+    int rc = 0;
+    for (int q = 0; q < npairs && !rc; ++q) {
+        const bool last = (q == npairs - 1);
+        fct_set_ring(ctx, K >= 2 ? K - 1 - 2 * q : 0);
+        JACOBI_LAUNCH(x, tmp, 0);
+        if (K < 2) rc |= fct_halo_exchange_if(ctx, tmp);
+        fct_set_ring(ctx, K >= 2 ? K - 2 - 2 * q : 0);
+        JACOBI_LAUNCH(tmp, x, 1);
+        if (last) rc |= fct_halo_exchange_if(ctx, x);
+        // decision: only the last one of a cycle may end the graph loop (the exchange above must have run)
+        const int uh = (use_handle && last) ? 1 : 0;
+        if (p2p) {
+            rc |= fct_p2p_max2_decide(ctx, rtol, max_sweeps, uh, handle);
+        } else {
+            rc |= fct_halo_allreduce_max2(ctx, ctx->jstate);
+            if (uh) k_jacobi_decide_cond<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol, (unsigned long long)max_sweeps, handle);
+            else k_jacobi_decide<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol);
+            ctx->launches++;
+        }
+    }
+    fct_set_ring(ctx, 0);
+    return rc;
+#undef JACOBI_LAUNCH
+}
+
+// Jacobi solve of Lv x = b; x holds the initial guess on entry (valid on every local row) and the result on exit
+// (valid on every local row: the last cycle ends with an exchange).  dinv != nullptr: Lv has a zero diagonal slot and
+// dinv = 1/diag (FCT low-order system); otherwise a general matrix.
+int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const double* dinv, double* x, double* tmp,
+                     double rtol, int max_sweeps) {
+    const int sweeps_per_cycle = ctx->depth >= 2 ? 2 * (ctx->depth / 2) : 2;
+    const int cycles = (max_sweeps + sweeps_per_cycle - 1) / sweeps_per_cycle;
     const bool p2p = ctx->comm && fct_p2p_ready(ctx);
     if ((!ctx->comm || p2p) && dinv && ctx->use_graph) {
-        // Single GPU, FCT low-order system: the sweep pairs are the body of a CUDA-graph WHILE node whose condition the
-        // decide kernel sets on the device -- exactly as many sweeps as needed are launched, with no host round trip
-        // and no skipped launches.  The graph is rebuilt only if an operand pointer or a solver option changes.
+        // The cycle is the body of a CUDA-graph WHILE node whose condition the decide kernel sets on the device:
+        // exactly as many sweeps as needed are launched, with no host round trip and no skipped launches (multi-GPU:
+        // the halo exchanges and the all-reduced stopping test are peer-memory kernels inside the same body).  The graph
+        // is rebuilt only if an operand pointer or a solver option changes.
         fct_jgraph& jg = ctx->jgraph;
         if (!jg.exec || jg.Lv != Lv || jg.b != b || jg.dinv != dinv || jg.x != x || jg.tmp != tmp || jg.rtol != rtol ||
-            jg.max_sweeps != max_sweeps) {
+            jg.max_sweeps != max_sweeps || jg.depth != ctx->depth) {
             if (jg.exec) { cudaGraphExecDestroy((cudaGraphExec_t)jg.exec); jg.exec = nullptr; }
             if (jg.graph) { cudaGraphDestroy((cudaGraph_t)jg.graph); jg.graph = nullptr; }
             cudaGraph_t g;
@@ -943,20 +1004,12 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
             ctx->stream = ctx->copy_stream;          // capture stream: launches below are recorded, not executed
             const int64_t launches0 = ctx->launches;
             FCT_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-            JACOBI_LAUNCH(x, tmp, 0);
-            if (p2p) fct_halo_exchange_if(ctx, tmp);
-            JACOBI_LAUNCH(tmp, x, 1);
-            if (p2p) {
-                fct_halo_exchange_if(ctx, x);
-                fct_p2p_max2_decide(ctx, rtol, max_sweeps, 1, h);
-            } else {
-                k_jacobi_decide_cond<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol, (unsigned long long)max_sweeps, h);
-            }
+            const int rc = jacobi_cycle(ctx, Lv, b, dinv, x, tmp, rtol, max_sweeps, p2p, 1, h);
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, nullptr);
             ctx->stream = user;
             ctx->launches = launches0;
-            if (ce != cudaSuccess) {
-                fct_set_error("fct_jacobi_solve: graph capture failed: %s", cudaGetErrorString(ce));
+            if (rc || ce != cudaSuccess) {
+                if (!rc) fct_set_error("fct_jacobi_solve: graph capture failed: %s", cudaGetErrorString(ce));
                 cudaGraphDestroy(g);
                 return 1;
             }
@@ -964,47 +1017,35 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
             FCT_CUDA(cudaGraphInstantiate(&ex, g, 0));
             jg.graph = g; jg.exec = ex;
             jg.Lv = Lv; jg.b = b; jg.dinv = dinv; jg.x = x; jg.tmp = tmp; jg.rtol = rtol; jg.max_sweeps = max_sweeps;
+            jg.depth = ctx->depth;
         }
         FCT_CUDA(cudaGraphLaunch((cudaGraphExec_t)jg.exec, ctx->stream));
         ctx->launches += 3;      // at least one body iteration; the executed sweeps are counted in jstate[4]
         return 0;
     }
     if (ctx->comm) {
-        // Multi-GPU: a skipped sweep would still pay its NCCL exchanges, so sweeps are enqueued in a budget learnt
-        // from the previous solve and the (all-reduced, hence rank-uniform) convergence flag is read back before
-        // spending more.
+        // Multi-GPU without peer mailboxes (NCCL): a skipped sweep would still pay its exchanges, so cycles are
+        // enqueued in a budget learnt from the previous solve and the all-reduced (rank-uniform) convergence flag is
+        // read back before spending more.
         int done = 0;
         int budget = ctx->last_pairs > 0 ? ctx->last_pairs : 6;
-        while (done < pairs) {
-            const int todo = (done + budget <= pairs) ? budget : pairs - done;
-            for (int p = 0; p < todo; ++p) {
-                JACOBI_LAUNCH(x, tmp, 0);
-                if (fct_halo_exchange_if(ctx, tmp)) return 1;
-                JACOBI_LAUNCH(tmp, x, 1);
-                if (fct_halo_exchange_if(ctx, x)) return 1;
-                if (fct_halo_allreduce_max2(ctx, ctx->jstate)) return 1;
-                k_jacobi_decide<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol);
-                ctx->launches++;
-            }
+        while (done < cycles) {
+            const int todo = (done + budget <= cycles) ? budget : cycles - done;
+            for (int c = 0; c < todo; ++c)
+                if (jacobi_cycle(ctx, Lv, b, dinv, x, tmp, rtol, max_sweeps, p2p, 0, 0)) return 1;
             done += todo;
             unsigned long long st[2] = {0, 0};     // {converged flag, sweeps executed}
             FCT_CUDA(cudaMemcpyAsync(st, ctx->jstate + 3, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
             FCT_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (st[0]) { done = (int)((st[1] + 1) / 2); break; }
+            if (st[0]) { done = (int)((st[1] + sweeps_per_cycle - 1) / sweeps_per_cycle); break; }
             budget = 1;
         }
         ctx->last_pairs = done;      // sweeps per step are very stable: next time enqueue exactly this many first
         return fct_launch_error(ctx, "fct_jacobi_solve");
     }
-    for (int p = 0; p < pairs; ++p) {
-        JACOBI_LAUNCH(x, tmp, 0);
-        if (fct_halo_exchange_if(ctx, tmp)) return 1;
-        JACOBI_LAUNCH(tmp, x, 1);
-        if (fct_halo_exchange_if(ctx, x)) return 1;
-        if (fct_halo_allreduce_max2(ctx, ctx->jstate)) return 1;
-        k_jacobi_decide<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol);
-        ctx->launches++;
-    }
+    // single GPU, static launch sequence with device-side early exit (general matrices, or FCT_NO_GRAPH=1)
+    for (int c = 0; c < cycles; ++c)
+        if (jacobi_cycle(ctx, Lv, b, dinv, x, tmp, rtol, max_sweeps, false, 0, 0)) return 1;
     return fct_launch_error(ctx, "fct_jacobi_solve");
 }
 
@@ -1037,7 +1078,11 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     double* Rn = ctx->w[9];
     k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
     ctx->launches++;
-    // 1-2. D, L, b
+    // Deep halos: inputs (u_n, rhs, A incl. transposed entries) are valid on ring K (rhs: K-1); every pass below runs
+    // on the largest ring its inputs allow, so that only the Jacobi / Chebyshev cycles and the output need exchanges.
+    const int K = ctx->depth;
+    // 1-2. D, L, b on ring K-1
+    fct_set_ring(ctx, K - 1);
     {
         const int nf = S ? 2 : 1;
         const size_t smem = FCT_NST_LOW * smem_bytes(ctx, nf, 2) + 2 * smem_bytes(ctx, 1, 0);
@@ -1046,29 +1091,39 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
             if (S)
                 k_low_build<1><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un,
                                                                   rhs, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,
-                                                                  ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+                                                                  ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
             else
                 k_low_build<0><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un,
                                                                   rhs, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,
-                                                                  ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+                                                                  ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
             ctx->launches++;
         }
     }
-    // low-order solve, initial guess u_n
+    fct_set_ring(ctx, 0);
+    // low-order solve, initial guess u_n (valid on every local row; so is the result)
     FCT_CUDA(cudaMemcpyAsync(ulow, un, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
     if (fct_jacobi_solve(ctx, ctx->Lvals, bvec, dinv, ulow, tmp, ctx->rtol, ctx->max_sweeps)) return 1;
-    // 4. g = -(sign A) u_low + rhs ; udot = ChebSI(g)
-    LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, ulow, -sign, rhs ? 1.0 : 0.0, rhs, g, ctx->row_begin,
-                ctx->row_end, ctx->nnz, ctx->cap);
-    if (fct_chebsi(ctx, ctx->M, ctx->Mdiag, g, udot, 20, 0.5, 2.0)) return 1;
-    if (fct_halo_exchange_if(ctx, udot)) return 1;
-    // 5-7. fluxes, P, Q, R
+    // 4. g = -(sign A) u_low + rhs on ring K-1; udot = ChebSI(g)
+    fct_set_ring(ctx, K - 1);
+    LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, ulow, -sign, rhs ? 1.0 : 0.0, rhs, g, ctx->cur_rb,
+                ctx->cur_re, ctx->nnz, ctx->cap);
+    int vud = 0;
+    if (fct_chebsi_v(ctx, ctx->M, ctx->Mdiag, g, udot, 20, 0.5, 2.0, K - 1, &vud)) return 1;
+    // 5-7. fluxes, P, Q, R: on ring 1 when the halo is deep enough (then R+- needs no exchange), else on the owned rows
+    const int rflux = K >= 2 ? 1 : 0;
+    if (vud < rflux + 1) {
+        if (fct_halo_exchange_if(ctx, udot)) return 1;
+    }
+    fct_set_ring(ctx, rflux);
     LAUNCH_PIPE(ctx, k_flux_limits, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, dt, Rp, Rn,
-                ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
-    if (fct_halo_exchange2_if(ctx, Rp, Rn)) return 1;
-    // 8-9. limited sum + update
+                ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+    if (K < 2) {
+        if (fct_halo_exchange2_if(ctx, Rp, Rn)) return 1;
+    }
+    // 8-9. limited sum + update on the owned rows
+    fct_set_ring(ctx, 0);
     LAUNCH_PIPE(ctx, k_flux_apply, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, Rp, Rn, dt,
-                uout, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+                uout, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
     if (fct_launch_error(ctx, "fct_step")) return 1;
     if (fct_halo_exchange_if(ctx, uout)) return 1;
     if (info) return fct_read_step_info(ctx, info);
@@ -1104,7 +1159,7 @@ extern "C" int fct_dot_M(fct_ctx* ctx, const double* M, const double* x, const d
     double* partial = ctx->w[0];
     const int nb = pipe_grid(ctx, 1);
     LAUNCH_PIPE(ctx, k_dot_M, 1, 1, ctx->rowptr, ctx->colidx, M, x, (const double*)nullptr, y, (const double*)nullptr,
-                partial, ctx->row_begin, ctx->row_end, ctx->nnz, ctx->cap);
+                partial, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
     k_reduce_partials<<<1, FCT_RB, 0, ctx->stream>>>(partial, nb, 1.0, ctx->red, 0);
     ctx->launches++;
     if (fct_launch_error(ctx, "fct_dot_M")) return 1;

@@ -28,9 +28,21 @@ def partition_rows(n, world):
     return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
 
 
-def column_ranges(rowptr, colidx, bounds):
-    """[G0,G1) per rank: min / max column referenced by the rank's owned rows (columns are sorted per row)"""
+def ring_ranges(rowptr, colidx, a, b, depth):
+    """nested row ranges [lo_j, hi_j), j = 0..depth: ring 0 = [a,b), ring j = every column referenced by the rows of
+    ring j-1 (columns are sorted per row, and the DoF order makes these sets contiguous ranges)"""
     rowptr = np.asarray(rowptr, dtype=np.int64)
+    lo, hi = [int(a)], [int(b)]
+    for _ in range(depth):
+        first = colidx[rowptr[lo[-1]:hi[-1]]]
+        last = colidx[rowptr[lo[-1] + 1:hi[-1] + 1] - 1]
+        lo.append(min(int(first.min()), lo[-1]))
+        hi.append(max(int(last.max()) + 1, hi[-1]))
+    return lo, hi
+
+
+def column_ranges(rowptr, colidx, bounds, depth=1):
+    """[G0,G1) per rank: the depth-ring closure of the rank's owned rows"""
     world = len(bounds) - 1
     g0 = np.empty(world, dtype=np.int64)
     g1 = np.empty(world, dtype=np.int64)
@@ -38,10 +50,8 @@ def column_ranges(rowptr, colidx, bounds):
         a, b = int(bounds[r]), int(bounds[r + 1])
         if b <= a:
             raise ValueError(f"rank {r} owns no rows: too many ranks for this mesh")
-        first = colidx[rowptr[a:b]]
-        last = colidx[rowptr[a + 1:b + 1] - 1]
-        g0[r] = min(int(first.min()), a)
-        g1[r] = max(int(last.max()) + 1, b)
+        lo, hi = ring_ranges(rowptr, colidx, a, b, depth)
+        g0[r], g1[r] = lo[-1], hi[-1]
     for r in range(world):
         if r > 0 and g0[r] < bounds[r - 1]:
             raise ValueError("halo reaches beyond the neighbouring rank: row blocks are thinner than the bandwidth")
@@ -53,14 +63,18 @@ def column_ranges(rowptr, colidx, bounds):
 class LocalProblem:
     """Everything rank `rank` needs to build its context from the global mesh description."""
 
-    def __init__(self, rowptr, colidx, cells, dof_xy, rank, world):
+    def __init__(self, rowptr, colidx, cells, dof_xy, rank, world, depth=1):
         n = len(rowptr) - 1
         self.n_global = n
         self.rank, self.world = int(rank), int(world)
+        self.depth = int(depth)
         self.bounds = partition_rows(n, world)
-        self.g0_all, self.g1_all = column_ranges(rowptr, colidx, self.bounds)
+        self.g0_all, self.g1_all = column_ranges(rowptr, colidx, self.bounds, self.depth)
         R0, R1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
         G0, G1 = int(self.g0_all[rank]), int(self.g1_all[rank])
+        lo, hi = ring_ranges(rowptr, colidx, R0, R1, self.depth)
+        self.ring_lo = np.array([x - G0 for x in lo], dtype=np.int32)      # local row ranges of rings 0..depth
+        self.ring_hi = np.array([x - G0 for x in hi], dtype=np.int32)
         self.R0, self.R1, self.G0, self.G1 = R0, R1, G0, G1
         self.n = G1 - G0
         self.row_begin, self.row_end = R0 - G0, R1 - G0
@@ -68,19 +82,20 @@ class LocalProblem:
         k0, k1 = int(rp[G0]), int(rp[G1])
         cols = np.asarray(colidx[k0:k1], dtype=np.int64)
         rows = np.repeat(np.arange(G0, G1, dtype=np.int64), np.diff(rp[G0:G1 + 1]))
-        keep = (cols >= G0) & (cols < G1)            # halo rows are truncated to the local column range
-        owned = (rows >= R0) & (rows < R1)
-        if not keep[owned].all():
-            raise AssertionError("owned rows must lie completely inside [G0,G1)")
+        keep = (cols >= G0) & (cols < G1)            # the outermost ring's rows are truncated to the local range
+        inner = (rows >= lo[-2]) & (rows < hi[-2])   # rows of ring depth-1 (ring 0 = owned when depth == 1)
+        if not keep[inner].all():
+            raise AssertionError("rows of ring depth-1 must lie completely inside [G0,G1)")
         self.keep = keep                             # mask into global entries k0..k1 (value-array scatter)
         self.k0, self.k1 = k0, k1
         lrows = rows[keep] - G0
         self.colidx = (cols[keep] - G0).astype(np.int32)
         counts = np.bincount(lrows, minlength=self.n)
         self.rowptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
-        # cells with at least one owned vertex (all their vertices are neighbours of it, hence local)
+        # cells with at least one vertex in ring depth-1 (all their vertices are neighbours of it, hence local):
+        # rows of ring depth-1 are then assembled completely, rows of the outermost ring towards ring depth-1
         cells = np.asarray(cells, dtype=np.int64).reshape(-1, 3)
-        own_c = ((cells >= R0) & (cells < R1)).any(axis=1)
+        own_c = ((cells >= lo[-2]) & (cells < hi[-2])).any(axis=1)
         lc = cells[own_c]
         if lc.size and (lc.min() < G0 or lc.max() >= G1):
             raise AssertionError("a cell of an owned vertex leaves the local range")
@@ -117,6 +132,9 @@ class LocalProblem:
     def make_context(self, device):
         ctx = FctContext(self.rowptr, self.colidx, device=device, row_begin=self.row_begin, row_end=self.row_end)
         ctx.set_mesh(self.cells, self.dof_xy)
+        if self.world > 1:
+            check(lib.fct_ctx_set_rings(ctx.handle, self.depth, self.ring_lo.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        self.ring_hi.ctypes.data_as(C.POINTER(C.c_int32))))
         return ctx
 
 
@@ -168,9 +186,12 @@ def torch_broadcaster():
     return bc
 
 
-def setup_rank(mesh, rank, world, local_rank):
-    """LocalProblem + context (mesh set, communicator initialised, static matrices assembled) for this rank"""
-    lp = LocalProblem(mesh.rowptr, mesh.colidx, mesh.cells, mesh.dof_xy, rank, world)
+def setup_rank(mesh, rank, world, local_rank, depth=None):
+    """LocalProblem + context (mesh set, communicator initialised, static matrices assembled) for this rank.
+    depth: halo depth in mesh rings (default 4, FCT_HALO_DEPTH overrides; 1 = exchange after every pass)"""
+    if depth is None:
+        depth = int(os.environ.get("FCT_HALO_DEPTH", "4"))
+    lp = LocalProblem(mesh.rowptr, mesh.colidx, mesh.cells, mesh.dof_xy, rank, world, depth=depth if world > 1 else 1)
     ctx = lp.make_context(local_rank)
     if world > 1:
         init_comm(ctx, lp, torch_broadcaster())

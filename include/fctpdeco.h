@@ -209,6 +209,9 @@ int fct_ctx_init_comm(fct_ctx* ctx, const void* id_128bytes, int32_t rank, int32
                       int32_t send_lo_begin, int32_t send_lo_end,    /* local rows sent to rank-1          */
                       int32_t send_hi_begin, int32_t send_hi_end);   /* local rows sent to rank+1          */
 int fct_halo_exchange(fct_ctx* ctx, double* vec_dev);                /* refresh halo entries of a vector    */
+/* deep halos: ring j = local rows within j mesh rings of the owned rows (ring 0 = [row_begin,row_end), ring `depth`
+ * = [0,n)).  With depth k the dependent passes of the Jacobi / Chebyshev loops exchange every k-th pass only. */
+int fct_ctx_set_rings(fct_ctx* ctx, int32_t depth, const int32_t* ring_lo, const int32_t* ring_hi);
 /* NVLink peer-memory mailboxes (CUDA IPC) replacing NCCL send/recv for the halo exchanges and the Jacobi stopping
  * test: fct_p2p_create exports this rank's region (64-byte cudaIpcMemHandle); after gathering all ranks' handles
  * (rank order) fct_p2p_connect maps them.  Once connected every halo exchange is one kernel (push over NVLink, wait,
