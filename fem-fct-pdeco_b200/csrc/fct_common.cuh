@@ -100,6 +100,8 @@ struct fct_ctx {
     int32_t max_sweeps = 100;
     int64_t launches = 0;
     fct_jgraph jgraph;
+    bool use_pdl = false;       // FCT_PDL=1 enables programmatic dependent launch (measured: no gain, persistent grids)
+    bool capturing = false;
     bool use_graph = true;      // FCT_NO_GRAPH=1 falls back to the static launch sequence with device-side early exit
     int32_t last_pairs = 0;     // Jacobi sweep pairs the previous multi-GPU solve needed
     fct_comm* comm = nullptr;

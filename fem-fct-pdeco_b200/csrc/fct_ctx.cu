@@ -158,6 +158,7 @@ extern "C" int fct_ctx_create(fct_ctx** out, int device, int32_t n, const int32_
     }
     c->cap = ((cap + 3) & ~3) + 4;
     { const char* e = getenv("FCT_NO_GRAPH"); c->use_graph = !(e && atoi(e) == 1); }
+    { const char* e = getenv("FCT_PDL"); c->use_pdl = (e && atoi(e) == 1); }   // measured: no gain with persistent grids
     {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)

@@ -188,6 +188,8 @@ int fct_read_step_info(fct_ctx* ctx, fct_step_info* info);
 __global__ void k_jstate_reset(unsigned long long* __restrict__ jstate) {
     for (int i = 0; i < 7; ++i) jstate[i] = 0ull;
     jstate[7] = 0xFFFFFFFFFFFFFFFFull;
+    jstate[10] = 0ull;   // no learnt check_from for a general system
+    jstate[11] = 0ull;
 }
 
 // Krylov scalars live on the device (ctx->red): no host round trip inside an iteration.

@@ -407,13 +407,23 @@ k_jacobi_sweep_gen(const int32_t* __restrict__ rowptr, const int32_t* __restrict
 }
 
 // After a checked sweep (and, multi-GPU, after the max-allreduce of jstate[0..1]): decide convergence.
+// jstate[10] = "check_from": sweeps before which the stopping test is not attempted.  The sweep count of the
+// low-order solve is nearly constant from one time step to the next, so the early tests (each of which is an
+// all-to-all between the ranks in the multi-GPU case) are skipped; jstate[11] counts the failed tests of this solve.
+__device__ __forceinline__ void jacobi_note_convergence(unsigned long long* jstate) {
+    const unsigned long long s = jstate[4];
+    const unsigned long long back = jstate[11] ? 2ull : 4ull;
+    jstate[10] = s > back ? s - back : 0ull;
+}
 __global__ void k_jacobi_decide(unsigned long long* __restrict__ jstate, double rtol) {
     if (jstate[3]) return;
+    if (jstate[4] < jstate[10]) { jstate[0] = 0ull; jstate[1] = 0ull; return; }   // same schedule as the multi-GPU test
     const double delta = __longlong_as_double((long long)jstate[0]);
     const double xm = __longlong_as_double((long long)jstate[1]);
     jstate[5] = jstate[0];
     jstate[6] = jstate[1];
-    if (delta <= rtol * xm) jstate[3] = 1ull;
+    if (delta <= rtol * xm) { jstate[3] = 1ull; jacobi_note_convergence(jstate); }
+    else jstate[11] += 1ull;
     jstate[0] = 0ull;
     jstate[1] = 0ull;
 }
@@ -421,12 +431,18 @@ __global__ void k_jacobi_decide(unsigned long long* __restrict__ jstate, double 
 // the same decision as the body of a CUDA-graph WHILE node: keeps looping until converged or out of sweeps
 __global__ void k_jacobi_decide_cond(unsigned long long* __restrict__ jstate, double rtol, unsigned long long max_sweeps,
                                      cudaGraphConditionalHandle handle) {
+    if (jstate[4] < jstate[10] && jstate[4] < max_sweeps) {
+        jstate[0] = 0ull; jstate[1] = 0ull;
+        cudaGraphSetConditional(handle, 1u);
+        return;
+    }
     const double delta = __longlong_as_double((long long)jstate[0]);
     const double xm = __longlong_as_double((long long)jstate[1]);
     jstate[5] = jstate[0];
     jstate[6] = jstate[1];
     const bool conv = delta <= rtol * xm;
-    if (conv) jstate[3] = 1ull;
+    if (conv) { jstate[3] = 1ull; jacobi_note_convergence(jstate); }
+    else jstate[11] += 1ull;
     jstate[0] = 0ull;
     jstate[1] = 0ull;
     cudaGraphSetConditional(handle, (conv || jstate[4] >= max_sweeps) ? 0u : 1u);
@@ -436,6 +452,7 @@ __global__ void k_jacobi_reset(unsigned long long* __restrict__ jstate) {
     jstate[0] = 0ull; jstate[1] = 0ull; jstate[2] = 0ull; jstate[3] = 0ull; jstate[4] = 0ull;
     jstate[5] = 0ull; jstate[6] = 0ull;
     jstate[7] = 0xFFFFFFFFFFFFFFFFull;   // min row-sum key
+    jstate[11] = 0ull;                   // failed stopping tests of this solve (jstate[10], check_from, persists)
 }
 
 // Zalesak limiter, pass 1 (helpers.py:1818-1851): raw fluxes f_ij = m_ij (ud_i - ud_j) + d_ij (ul_i - ul_j),
@@ -720,6 +737,28 @@ static inline size_t smem_bytes(const fct_ctx* c, int nf64, int ns32) {
         }                                                                                                \
     } while (0)
 
+// Launch with the programmatic-dependent-launch attribute (see pdl_wait in fct_pipe.cuh) unless disabled or the stream is
+// being captured into the Jacobi WHILE graph.
+template <typename... KArgs, typename... Args>
+static inline void launch_pipe(fct_ctx* ctx, void (*kern)(KArgs...), int grid, size_t smem, Args... args) {
+    if (ctx->use_pdl && !ctx->capturing) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(FCT_RB);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    } else {
+        kern<<<grid, FCT_RB, smem, ctx->stream>>>(KArgs(args)...);
+    }
+    ctx->launches++;
+}
+
 // TMA-ring kernels: FCT_NST stages of (nf64 fp64 + ns32 int32) staged arrays; persistent grid = SMs x resident CTAs
 static inline int pipe_grid(const fct_ctx* c, int nf64) {
     const int cap = (nf64 >= 2) ? c->grid_pipe2 : c->grid_pipe1;
@@ -729,10 +768,8 @@ static inline int pipe_grid(const fct_ctx* c, int nf64) {
 #define LAUNCH_PIPE(ctx, kern, nf64, ns32, ...)                                                          \
     do {                                                                                                 \
         const int nb__ = pipe_grid(ctx, nf64);                                                           \
-        if (nb__ > 0) {                                                                                  \
-            kern<<<nb__, FCT_RB, ((nf64) >= 2 ? FCT_NST2 : FCT_NST) * smem_bytes(ctx, nf64, ns32), (ctx)->stream>>>(__VA_ARGS__); \
-            (ctx)->launches++;                                                                           \
-        }                                                                                                \
+        if (nb__ > 0)                                                                                    \
+            launch_pipe(ctx, kern, nb__, ((nf64) >= 2 ? FCT_NST2 : FCT_NST) * smem_bytes(ctx, nf64, ns32), __VA_ARGS__); \
     } while (0)
 
 // k_cheb_iter / k_jacobi_sweep are instantiated for 2, 3 and 4 ring stages; the context picks one (FCT_NST env var,
@@ -743,10 +780,9 @@ static inline int pipe_grid(const fct_ctx* c, int nf64) {
         const int nb__ = nb0__ < (ctx)->grid_nst1 ? nb0__ : (ctx)->grid_nst1;                            \
         if (nb__ > 0) {                                                                                  \
             const size_t sm__ = (size_t)(ctx)->nst1 * smem_bytes(ctx, 1, 1);                             \
-            if ((ctx)->nst1 == 2) kern<2><<<nb__, FCT_RB, sm__, (ctx)->stream>>>(__VA_ARGS__);           \
-            else if ((ctx)->nst1 == 4) kern<4><<<nb__, FCT_RB, sm__, (ctx)->stream>>>(__VA_ARGS__);      \
-            else kern<3><<<nb__, FCT_RB, sm__, (ctx)->stream>>>(__VA_ARGS__);                            \
-            (ctx)->launches++;                                                                           \
+            if ((ctx)->nst1 == 2) launch_pipe(ctx, kern<2>, nb__, sm__, __VA_ARGS__);                    \
+            else if ((ctx)->nst1 == 4) launch_pipe(ctx, kern<4>, nb__, sm__, __VA_ARGS__);               \
+            else launch_pipe(ctx, kern<3>, nb__, sm__, __VA_ARGS__);                                     \
         }                                                                                                \
     } while (0)
 
@@ -1002,11 +1038,13 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
             cudaGraph_t body = np.conditional.phGraph_out[0];
             cudaStream_t user = ctx->stream;
             ctx->stream = ctx->copy_stream;          // capture stream: launches below are recorded, not executed
+            ctx->capturing = true;
             const int64_t launches0 = ctx->launches;
             FCT_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
             const int rc = jacobi_cycle(ctx, Lv, b, dinv, x, tmp, rtol, max_sweeps, p2p, 1, h);
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, nullptr);
             ctx->stream = user;
+            ctx->capturing = false;
             ctx->launches = launches0;
             if (rc || ce != cudaSuccess) {
                 if (!rc) fct_set_error("fct_jacobi_solve: graph capture failed: %s", cudaGetErrorString(ce));

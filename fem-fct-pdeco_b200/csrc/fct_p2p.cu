@@ -117,7 +117,9 @@ k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, uns
     const unsigned long long seq = H->rseq + 1;
     const int slot = (int)(seq % FCT_P2P_SLOTS);
     const int t = threadIdx.x;
-    const bool skip = jstate[3] != 0ull;                  // already converged: every rank agrees, nothing to exchange
+    // nothing to exchange when already converged, or before the sweep count at which the previous solve converged
+    // (jstate[10], identical on every rank) -- the all-to-all is only paid for the last one or two tests of a solve
+    const bool skip = jstate[3] != 0ull || jstate[4] < jstate[10];
     unsigned long long a = 0ull, b = 0ull;
     bool ok = true;
     if (!skip && t < world) {
@@ -144,11 +146,16 @@ k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, uns
             const double xm = __longlong_as_double((long long)b);
             jstate[5] = a;
             jstate[6] = b;
-            if (delta <= rtol * xm) jstate[3] = 1ull;
-            jstate[0] = 0ull;
-            jstate[1] = 0ull;
+            if (delta <= rtol * xm) {
+                jstate[3] = 1ull;
+                const unsigned long long s = jstate[4], back = jstate[11] ? 2ull : 4ull;
+                jstate[10] = s > back ? s - back : 0ull;
+            } else {
+                jstate[11] += 1ull;
+            }
             H->rseq = seq;
         }
+        if (jstate[3] == 0ull) { jstate[0] = 0ull; jstate[1] = 0ull; }    // restart the running maxima
         if (use_handle) cudaGraphSetConditional(handle, (jstate[3] != 0ull || jstate[4] >= max_sweeps) ? 0u : 1u);
     }
     if (!ok) H->error = 1ull;

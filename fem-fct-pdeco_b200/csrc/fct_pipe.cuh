@@ -46,6 +46,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor is still draining; everything before pdl_wait() (barrier init, index arithmetic)
+// overlaps the predecessor's tail, everything after it sees the predecessor's memory writes.  Both are no-ops for
+// ordinary launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int NF, int NI, int NST>
 struct RowPipe {
     unsigned char* base;     // dynamic shared memory (16-byte aligned)
@@ -79,11 +86,13 @@ struct RowPipe {
         return cnt;
     }
     __device__ __forceinline__ void init() {
+        pdl_trigger();
         if (threadIdx.x == 0) {
             for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
             mbar_fence_init();
         }
         __syncthreads();
+        pdl_wait();            // nothing above touches global memory
     }
     // issuing thread only: CSR range of the next block to issue, loaded one iteration ahead so that the rowptr
     // round trip to DRAM is off the critical path

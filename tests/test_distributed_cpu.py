@@ -108,3 +108,33 @@ def test_halo_exchange_ranges_gloo(world):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, 24, ret), nprocs=world, join=True)
     assert all(ret.get(r) == "ok" for r in range(world))
+
+
+@pytest.mark.parametrize("depth", [2, 4])
+def test_deep_halo_rings(depth):
+    """depth-k halos: nested ring ranges, rows of ring k-1 complete, local cells = cells touching ring k-1,
+    send ranges cover the neighbour's (k rings wide) halo with owned rows only"""
+    m = RectMeshP1(30)
+    world = 3
+    lps = [LocalProblem(m.rowptr, m.colidx, m.cells, m.dof_xy, r, world, depth=depth) for r in range(world)]
+    A = sp.csr_matrix((np.ones(m.nnz), m.colidx, m.rowptr), shape=(m.nodes, m.nodes))
+    for r, lp in enumerate(lps):
+        assert lp.ring_lo[0] == lp.row_begin and lp.ring_hi[0] == lp.row_end
+        assert lp.ring_lo[depth] == 0 and lp.ring_hi[depth] == lp.n
+        for j in range(1, depth + 1):
+            assert lp.ring_lo[j] <= lp.ring_lo[j - 1] and lp.ring_hi[j] >= lp.ring_hi[j - 1]
+            # ring j = exactly the columns referenced by ring j-1 (graph distance j from the owned rows)
+            rows = np.arange(lp.ring_lo[j - 1], lp.ring_hi[j - 1]) + lp.G0
+            cols = A[rows].indices
+            assert cols.min() == lp.ring_lo[j] + lp.G0 and cols.max() + 1 == lp.ring_hi[j] + lp.G0
+        # rows of ring depth-1 keep all their entries
+        for row in (lp.ring_lo[depth - 1], lp.ring_hi[depth - 1] - 1):
+            assert lp.rowptr[row + 1] - lp.rowptr[row] == m.rowptr[row + lp.G0 + 1] - m.rowptr[row + lp.G0]
+        if r > 0:      # what I send down is exactly the lower neighbour's upper halo, all of it rows I own
+            prev = lps[r - 1]
+            assert lp.send_lo[0] == lp.row_begin and lp.send_lo[1] - lp.send_lo[0] == prev.n - prev.row_end
+            assert lp.send_lo[1] <= lp.row_end
+        if r + 1 < world:
+            nxt = lps[r + 1]
+            assert lp.send_hi[1] == lp.row_end and lp.send_hi[1] - lp.send_hi[0] == nxt.row_begin
+            assert lp.send_hi[0] >= lp.row_begin
