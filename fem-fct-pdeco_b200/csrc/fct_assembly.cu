@@ -76,6 +76,20 @@ __device__ __forceinline__ void element_row(const CellGeom& g, int a, const Form
     } else if (KIND == FCT_FORM_STIFFNESS) {
 #pragma unroll
         for (int b = 0; b < 3; ++b) e[b] = g.area * (g.gx[a] * g.gx[b] + g.gy[a] * g.gy[b]);
+    } else if (KIND == FCT_FORM_DRIFT_MASS) {
+        const double c0 = fa.f0[g.d[0]], c1 = fa.f0[g.d[1]], c2 = fa.f0[g.d[2]];
+        const double gcx = c0 * g.gx[0] + c1 * g.gx[1] + c2 * g.gx[2];
+        const double gcy = c0 * g.gy[0] + c1 * g.gy[1] + c2 * g.gy[2];
+        const double sm = (fa.s0 * gcx + fa.s1 * gcy) * (g.area / 12.0);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) e[b] = sm * ((b == a) ? 2.0 : 1.0);
+    } else if (KIND == FCT_FORM_DRIFT_CONV) {
+        const double cc[3] = {fa.f0[g.d[0]], fa.f0[g.d[1]], fa.f0[g.d[2]]};
+        const double m = g.area / 12.0;
+        const double bg = fa.s0 * g.gx[a] + fa.s1 * g.gy[a];
+        const double csum = (cc[0] + cc[1]) + cc[2];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) e[b] = bg * (m * (csum + cc[b]));
     } else if (KIND == FCT_FORM_DRIFT) {
         const double c0 = fa.f0[g.d[0]], c1 = fa.f0[g.d[1]], c2 = fa.f0[g.d[2]];
         const double cc[3] = {c0, c1, c2};
@@ -363,6 +377,8 @@ int fct_assembly_configure(fct_ctx* ctx) {
     rc |= configure_matrix<FCT_FORM_CHTX_ADJ>(bytes);
     rc |= configure_matrix<FCT_FORM_WIND_POLY3>(bytes);
     rc |= configure_matrix<FCT_FORM_WIND_POLY3_T>(bytes);
+    rc |= configure_matrix<FCT_FORM_DRIFT_MASS>(bytes);
+    rc |= configure_matrix<FCT_FORM_DRIFT_CONV>(bytes);
     return rc;
 }
 
@@ -415,6 +431,12 @@ extern "C" int fct_assemble_matrix(fct_ctx* ctx, int32_t kind, const double* c0,
         case FCT_FORM_DRIFT:
             FCT_CHECK(c0, "fct_assemble_matrix(DRIFT): coef0 (control) required");
             return launch_matrix<FCT_FORM_DRIFT>(ctx, fa, scale, acc, out);
+        case FCT_FORM_DRIFT_MASS:
+            FCT_CHECK(c0, "fct_assemble_matrix(DRIFT_MASS): coef0 (control) required");
+            return launch_matrix<FCT_FORM_DRIFT_MASS>(ctx, fa, scale, acc, out);
+        case FCT_FORM_DRIFT_CONV:
+            FCT_CHECK(c0, "fct_assemble_matrix(DRIFT_CONV): coef0 (control) required");
+            return launch_matrix<FCT_FORM_DRIFT_CONV>(ctx, fa, scale, acc, out);
         case FCT_FORM_WIND_P1:
             FCT_CHECK(c0 && c1, "fct_assemble_matrix(WIND_P1): coef0/coef1 (wind components) required");
             return launch_matrix<FCT_FORM_WIND_P1>(ctx, fa, scale, acc, out);

@@ -273,3 +273,6 @@ from .solvers import (armijo_line_search_ref, chtxs_sys_IC, get_chtxs_sys_params
                       get_nonlinear_eqns_params, get_schnak_sys_params, nonlinear_equation_IC, schnak_sys_IC,
                       solve_adjoint_chtxs_system, solve_adjoint_nonlinear_equation, solve_adjoint_schnak_system,
                       solve_chtxs_system, solve_nonlinear_equation, solve_schnak_system)
+
+# UFL-like front end for the reference's assemble_sparse(form) / assemble(form) call sites (fem-fct-pdeco_b200/forms.py)
+from .forms import assemble, assemble_sparse, assemble_sparse_lil, vec_to_function  # noqa: E402,F401

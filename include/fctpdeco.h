@@ -162,12 +162,14 @@ int fct_axpby(fct_ctx* ctx, int64_t len, double a, const double* x_dev, double b
  *                          1,x,y,x^2,xy,y^2,x^3,x^2y,xy^2,y^3; integrated exactly (7-point degree-5 rule), which
  *                          is what dolfin does for Expression(..., degree=4) winds such as
  *                          helpers.py:506-508 (Schnakenberg) and :876-878 (nonlinear)
+ *   FCT_FORM_DRIFT_MASS    (b.grad c) u v      the two parts of FCT_FORM_DRIFT on their own (the legacy scripts
+ *   FCT_FORM_DRIFT_CONV    (b.grad v) c u      assemble them separately: advection_solidbody_FCT_PDECO_alltime.py:222-223)
  * out_vals = scale * form (+ out_vals if accumulate != 0). */
 enum {
     FCT_FORM_MASS = 0, FCT_FORM_STIFFNESS = 1, FCT_FORM_DRIFT = 2, FCT_FORM_WIND_P1 = 3,
     FCT_FORM_WIND_P1_T = 4, FCT_FORM_WMASS1 = 5, FCT_FORM_WMASS2 = 6, FCT_FORM_WMASS3 = 7,
     FCT_FORM_CHTX = 8, FCT_FORM_CHTX_EXP = 9, FCT_FORM_CHTX_ADJ = 10, FCT_FORM_WIND_POLY3 = 11,
-    FCT_FORM_WIND_POLY3_T = 12
+    FCT_FORM_WIND_POLY3_T = 12, FCT_FORM_DRIFT_MASS = 13, FCT_FORM_DRIFT_CONV = 14
 };
 int fct_assemble_matrix(fct_ctx* ctx, int32_t kind, const double* coef0_dev, const double* coef1_dev,
                         const double* coef2_dev, double s0, double s1, double scale, int32_t accumulate,
