@@ -389,3 +389,95 @@ def armijo_line_search_ref(var1, c, d, var1_target, num_steps, dt, c_lower, c_up
     if armijo > -gam / s * control_dif_L2:
         print(f"Stopped: Maximum number of iterations reached ({max_iter}) .")
     return (var1, var2, c_inc, k + 1) if var2 is not None else (var1, c_inc, k + 1)
+
+
+# ---- legacy drift-control line search (config 2 / 5) ------------------------------------------------------------
+def cost_functional_proj(u, w, c, d, s, uhatvec, num_steps, dt, M, c_lower, c_upper, beta):
+    """The reference calls this (old_helpers.py:32,73; advection_FCT_PDECO_alltime_exact.py:213,310) but no definition
+    survives anywhere in the repo.  Re-specified from its call sites as the all-time cost of the
+    state u + s*w and the projected control clip(c, c_lower, c_upper); with w = 0 and an already projected c -- the
+    only way the drift line search uses it -- this is cost_functional(u, uhat, c, ..., 'alltime').  PARITY UNPINNED."""
+    return cost_functional(np.asarray(u) + s * np.asarray(w), uhatvec, np.clip(c, c_lower, c_upper), num_steps, dt, M, beta,
+                           "alltime")
+
+
+def armijo_line_search_sbr_drift(u, p, c, d, uhatvec, eps, drift, num_steps, dt, nodes, M, M_Lump, Ad, Arot, c_lower,
+                                 c_upper, beta, V, dof_neighbors, gam=10 ** -4, max_iter=5, s0=1, optim="alltime"):
+    """old_helpers.py:1-85: projected Armijo search for the drift-speed control; every trial is a full forward solve of
+    du/dt + div(u c b) - eps lap(u) = 0, run here as one device-resident loop (fct_advdrift_state).  `drift` is the
+    constant vector b (a 2-tuple or forms.Constant), `Arot` must be zero (as in the script, :148).  Writes the state
+    of the accepted trial into `u` in place and returns (s, u) like the reference.  optim='finaltime' needs the lost
+    cost_functional_proj_FT and is not supported."""
+    if optim != "alltime":
+        raise NotImplementedError("armijo_line_search_sbr_drift: only optim='alltime' (cost_functional_proj_FT is lost)")
+    if Arot is not None and getattr(Arot, "nnz", 0) and abs(Arot).max() != 0:
+        raise NotImplementedError("armijo_line_search_sbr_drift: the rotation operator must be zero")
+    b = getattr(drift, "b", drift)
+    bx, by = float(b[0]), float(b[1])
+    ctx = V.mesh().context()
+    if ctx.n != nodes:
+        raise ValueError(f"nodes={nodes} does not match the function space ({ctx.n})")
+    k = 0
+    s = 1
+    Z = np.zeros(np.shape(u))
+    grad_costfun_L2 = L2_norm_sq_Q(np.clip(c + s * d, c_lower, c_upper) - c, num_steps, dt, M)
+    print(f"{grad_costfun_L2=}")
+    costfun_init = cost_functional_proj(u, Z, c, d, s, uhatvec, num_steps, dt, M, c_lower, c_upper, beta)
+    d_c, d_u = ctx.empty(u.size), ctx.empty(u.size)
+    armijo = 10 ** 5
+    while armijo > -gam / s * grad_costfun_L2 and k < max_iter:
+        s = s0 * (1 / 2 ** k)
+        c_inc = np.clip(c + s * d, c_lower, c_upper)
+        print(f"{k =}")
+        print("Solving state equations...")
+        u[nodes:] = np.zeros(num_steps * nodes)
+        d_c.upload(c_inc); d_u.upload(u)
+        ctx.advdrift_state(d_c, d_u, num_steps, dt, bx=bx, by=by, eps=float(eps))
+        d_u.download(u)
+        cost2 = cost_functional_proj(u, Z, c_inc, d, s, uhatvec, num_steps, dt, M, c_lower, c_upper, beta)
+        armijo = cost2 - costfun_init
+        grad_costfun_L2 = L2_norm_sq_Q(c_inc - c, num_steps, dt, M)
+        k += 1
+    d_c.free(); d_u.free()
+    print(f"Armijo exit at {k=} with {s=}")
+    return s, u
+
+
+# ---- trajectory I/O (SURVEY.md 8f-3) --------------------------------------------------------------------------------
+def import_data_final(file_path, nodes, vertex_to_dof, num_steps=0, time_dep=False):
+    """helpers.py:1874-1911.  Besides the reference's comma-separated text (`np.tofile(sep=',')`), a `.npy` file with the
+    same flat DoF-ordered layout is accepted: a 4097^2 all-time trajectory is gigabytes of text otherwise."""
+    from .helpers import reorder_vector_from_dof
+    sqnodes = round(np.sqrt(nodes))
+    if str(file_path).endswith(".npy"):
+        data = np.load(file_path, mmap_mode="r")
+    else:
+        data = np.genfromtxt(file_path, delimiter=",")
+    if time_dep:
+        data = np.asarray(data[:(num_steps + 1) * nodes], dtype=np.float64)
+        data_re = reorder_vector_from_dof(data, num_steps + 1, nodes, vertex_to_dof)
+    else:
+        data = np.asarray(data[num_steps * nodes:(num_steps + 1) * nodes], dtype=np.float64)
+        data_re = reorder_vector_from_dof(data, 1, nodes, vertex_to_dof)
+        data_re = data_re.reshape((sqnodes, sqnodes))
+    return data_re, data
+
+
+def extract_data(file_path, file_name, T, dt, nodes, vertex_to_dof):
+    """helpers.py:1913-1956: cut the time slice at T out of a flat trajectory file (csv as in the reference, or .npy)"""
+    import os
+    idx = round(T / dt)
+    start_col, end_col = idx * nodes, (idx + 1) * nodes
+    npy = os.path.join(file_path, f"{file_name}.npy")
+    if os.path.exists(npy):
+        data = np.asarray(np.load(npy, mmap_mode="r")[start_col:end_col])
+        output_file = os.path.join(file_path, f"{file_name}_T{T}.npy")
+        np.save(output_file, data)
+    else:
+        import pandas as pd
+        input_file = os.path.join(file_path, f"{file_name}.csv")
+        output_file = os.path.join(file_path, f"{file_name}_T{T}.csv")
+        data = pd.read_csv(input_file, header=None, usecols=range(start_col, end_col), nrows=1)
+        np.savetxt(output_file, data.to_numpy().flatten(), delimiter=",")
+    print(f"Extracted data at {T=} into {output_file}.")
+    return None

@@ -109,3 +109,21 @@ def test_pattern_embedding_reinserts_pruned_zeros():
     bad[0, m.nodes - 1] = 1.0
     with pytest.raises(ValueError, match="outside the fixed P1 pattern"):
         pat.embed(bad)
+
+
+def test_trajectory_io_csv_and_npy(tmp_path):
+    """import_data_final / extract_data (helpers.py:1874-1956): the reference's comma-separated text and the binary
+    .npy path give the same arrays"""
+    m = RectMeshP1(3)
+    nodes = m.nodes
+    x = np.random.default_rng(2).random(3 * nodes)
+    x.tofile(tmp_path / "a.csv", sep=",")
+    np.save(tmp_path / "a.npy", x)
+    r1, d1 = helpers.import_data_final(str(tmp_path / "a.csv"), nodes, m.vertex_to_dof, num_steps=2)
+    r2, d2 = helpers.import_data_final(str(tmp_path / "a.npy"), nodes, m.vertex_to_dof, num_steps=2)
+    assert np.array_equal(r1, r2) and np.array_equal(d1, x[2 * nodes:]) and np.array_equal(d2, d1)
+    assert r1.shape == (4, 4) and np.array_equal(r1.ravel(), d1[m.vertex_to_dof])
+    r3, d3 = helpers.import_data_final(str(tmp_path / "a.npy"), nodes, m.vertex_to_dof, num_steps=2, time_dep=True)
+    assert np.array_equal(d3, x) and np.array_equal(r3, helpers.reorder_vector_from_dof(x, 3, nodes, m.vertex_to_dof))
+    helpers.extract_data(str(tmp_path), "a", 0.2, 0.1, nodes, m.vertex_to_dof)
+    assert np.array_equal(np.load(tmp_path / "a_T0.2.npy"), x[2 * nodes:])

@@ -118,3 +118,46 @@ def test_chemotaxis_state_and_adjoint(ref_data):
         assert rel_l2(pk, p_o.ravel()) < 1e-11 and rel_l2(qk, q_o.ravel()) < 1e-11, optim
     with pytest.raises(ValueError):
         hp.solve_adjoint_chtxs_system(mk, fk, mk, fk, mk, fk, c, 1.0, V, nodes, ns, dt, None, "sometimes")
+
+
+def test_config2_projected_gradient_iteration():
+    """One projected-gradient iteration of advection_solidbody_FCT_PDECO_alltime.py:196-303 (config 2, the shape of
+    the 4096^2 benchmark) on a 21x21 mesh: state, adjoint, gradient (device loops), legacy Armijo search, projection,
+    cost functional -- against the oracle.  Final cost within 1e-9 (north_star)."""
+    from oracle import pdeco_numpy as drv
+    n, ns = 20, 6
+    a1, a2 = -1.0, 1.0
+    beta, c_lower, c_upper = 0.01, 0.0, 5.0
+    orc = drv.AdvectionDriftPDECO(n, a1, a2, beta=beta, c_lower=c_lower, c_upper=c_upper)
+    h = (a2 - a1) / n
+    dt = 0.25 * h / (2 * np.sqrt(2))
+    u0 = orc.gaussian_ic()
+    uhat = orc.target(u0, ns, dt, c_const=2.0)
+    c = np.ones((ns + 1, orc.nodes))
+    u_o = orc.state(c, u0, ns, dt)
+    p_o = orc.adjoint(c, u_o, uhat, ns, dt)
+    d_o = orc.gradient(c, u_o, p_o, ns)
+    s_o, uinc_o, k_o = orc.armijo(u0, c, d_o, uhat, ns, dt)
+    c1_o = np.clip(c + s_o * d_o, c_lower, c_upper)
+    J_o = orc.cost(uinc_o, uhat, c1_o, ns, dt)
+
+    mesh, V = RectMeshP1(n, a1, a2), None
+    V = FunctionSpaceP1(mesh)
+    nodes = V.dim()
+    ctx = mesh.context()
+    M = ctx.to_scipy(ctx.static()[0].download())
+    uk = np.zeros((ns + 1) * nodes); uk[:nodes] = u0
+    dc, du, duh = ctx.array(c.ravel()), ctx.array(uk), ctx.array(uhat.ravel())
+    dp, dd = ctx.empty(uk.size), ctx.empty(uk.size)
+    ctx.advdrift_state(dc, du, ns, dt)
+    ctx.advdrift_adjoint(dc, du, duh, dp, ns, dt)
+    ctx.advdrift_gradient(dc, du, dp, dd, ns, beta)
+    uk, pk, dk = du.download(), dp.download(), dd.download()
+    assert rel_l2(uk, u_o.ravel()) < 1e-11 and rel_l2(pk, p_o.ravel()) < 1e-11 and rel_l2(dk, d_o.ravel()) < 1e-11
+    sk, u_inc = _quiet(hp.armijo_line_search_sbr_drift, uk, pk, c.ravel(), dk, uhat.ravel(), 0.0, (1.0, 1.0), ns, dt, nodes,
+                       M, None, None, None, c_lower, c_upper, beta, V, mesh.dof_neighbors(), optim="alltime")
+    assert sk == s_o and u_inc is uk
+    ckp1 = np.clip(c.ravel() + sk * dk, c_lower, c_upper)
+    J_g = _quiet(hp.cost_functional, u_inc, uhat.ravel(), ckp1, ns, dt, M, beta, optim="alltime")
+    assert rel_l2(u_inc, uinc_o.ravel()) < 1e-11
+    assert abs(J_g / J_o - 1) < 1e-9
