@@ -519,6 +519,7 @@ extern "C" int fct_assemble_vector(fct_ctx* ctx, int32_t kind, const double* c0,
 
 int fct_row_lump_diag(fct_ctx* ctx, const double* mat, double* out, double* diag);
 int fct_halo_exchange_if(fct_ctx* ctx, double* vec);
+int fct_templates_build(fct_ctx* ctx);
 
 extern "C" int fct_assemble_static(fct_ctx* ctx) {
     FCT_CHECK(ctx, "fct_assemble_static: null context");
@@ -530,5 +531,5 @@ extern "C" int fct_assemble_static(fct_ctx* ctx) {
     if (fct_halo_exchange_if(ctx, ctx->ML)) return 1;
     if (fct_halo_exchange_if(ctx, ctx->Mdiag)) return 1;
     ctx->mass_set = true;
-    return 0;
+    return fct_templates_build(ctx);
 }

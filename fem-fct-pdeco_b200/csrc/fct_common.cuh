@@ -87,6 +87,11 @@ struct fct_ctx {
     double* Mdiag = nullptr;
     double* K = nullptr;
     bool mass_set = false;
+    // row templates of M (fct_templates.cu): 16-bit code per row, T x 8 column offsets / values
+    uint16_t* tpl_code = nullptr;
+    int32_t* tpl_off = nullptr;
+    double* tpl_val = nullptr;
+    int32_t tpl_count = 0;
     // workspace
     double* Lvals = nullptr;    // low-order operator
     double* Dvals = nullptr;    // artificial diffusion (off-diagonals)

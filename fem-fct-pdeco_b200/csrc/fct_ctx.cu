@@ -116,6 +116,8 @@ int fct_assembly_configure(fct_ctx* ctx);
 int fct_drivers_configure(fct_ctx* ctx);
 void fct_comm_destroy(fct_ctx* ctx);
 void fct_p2p_destroy(fct_ctx* ctx);
+void fct_templates_free(fct_ctx* ctx);
+int fct_templates_build(fct_ctx* ctx);
 
 template <typename T>
 static int dev_alloc(T** p, size_t count) {
@@ -211,6 +213,7 @@ extern "C" int fct_ctx_destroy(fct_ctx* c) {
     cudaDeviceSynchronize();
     if (c->jgraph.exec) cudaGraphExecDestroy((cudaGraphExec_t)c->jgraph.exec);
     if (c->jgraph.graph) cudaGraphDestroy((cudaGraph_t)c->jgraph.graph);
+    fct_templates_free(c);
     fct_p2p_destroy(c);
     fct_comm_destroy(c);
     cudaFree(c->rowptr); cudaFree(c->colidx); cudaFree(c->tpos);
@@ -266,7 +269,7 @@ extern "C" int fct_ctx_set_mass(fct_ctx* ctx, const double* M_dev) {
     if (fct_halo_exchange_if(ctx, ctx->ML)) return 1;
     if (fct_halo_exchange_if(ctx, ctx->Mdiag)) return 1;
     ctx->mass_set = true;
-    return 0;
+    return fct_templates_build(ctx);
 }
 
 extern "C" int fct_ctx_static_dev(fct_ctx* ctx, const double** M, const double** ML, const double** Md, const double** K) {

@@ -872,10 +872,18 @@ int fct_build_tpos(fct_ctx* ctx) {
     return 0;
 }
 
+int fct_cheb_iter_tpl(fct_ctx* ctx, const double* Md, const double* g, const double* ymid, const double* yold,
+                      double* ynew, double omega, double dscale);       // fct_templates.cu
+int fct_spmv_tpl(fct_ctx* ctx, const double* x, double alpha, double beta, const double* z, double* y);
+
 extern "C" int fct_spmv(fct_ctx* ctx, const double* A, const double* x, double alpha, double beta, const double* z,
                         double* y) {
     FCT_CHECK(ctx && A && x && y, "fct_spmv: null argument");
     FCT_CHECK(beta == 0.0 || z, "fct_spmv: beta != 0 needs z");
+    if (ctx->tpl_count && A == ctx->M) {
+        if (fct_spmv_tpl(ctx, x, alpha, beta, z, y)) return 1;
+        return fct_launch_error(ctx, "fct_spmv");
+    }
     LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, x, alpha, beta, z, y, ctx->cur_rb, ctx->cur_re,
                 ctx->nnz, ctx->cap);
     return fct_launch_error(ctx, "fct_spmv");
@@ -924,8 +932,13 @@ int fct_chebsi_v(fct_ctx* ctx, const double* M, const double* Md, const double* 
                 if (r < 0) r = 0;
             }
             fct_set_ring(ctx, r);
-            LAUNCH_PIPE_NST(ctx, k_cheb_iter, ctx->rowptr, ctx->colidx, M, Md, b, ymid, yold, ynew, omega, dscale,
-                            yold != nullptr, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+            if (ctx->tpl_count && M == ctx->M) {
+                // static mass matrix with row templates: 2 B per row instead of 12 B per entry (fct_templates.cu)
+                if (fct_cheb_iter_tpl(ctx, Md, b, ymid, yold, ynew, omega, dscale)) return 1;
+            } else {
+                LAUNCH_PIPE_NST(ctx, k_cheb_iter, ctx->rowptr, ctx->colidx, M, Md, b, ymid, yold, ynew, omega, dscale,
+                                yold != nullptr, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+            }
             vmid = r;
         }
         yold = ymid;
