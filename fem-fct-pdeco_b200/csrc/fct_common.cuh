@@ -39,6 +39,15 @@ void fct_set_error(const char* fmt, ...);
         }                                                                                       \
     } while (0)
 
+// staging state of the host-trajectory entry point (fct_advdrift_state_host), allocated on first use
+struct fct_hoststage {
+    bool ready = false;
+    cudaStream_t d2h_stream = 0;
+    double* cbuf[2] = {nullptr, nullptr};
+    double* ubuf[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t c_ready[2] = {}, c_free[2] = {}, u_ready[3] = {}, u_free[3] = {};
+};
+
 struct fct_comm;   // NCCL state (fct_comm.cu)
 struct fct_p2p;    // NVLink peer-memory mailboxes (fct_p2p.cu)
 
@@ -105,6 +114,7 @@ struct fct_ctx {
     int32_t max_sweeps = 100;
     int64_t launches = 0;
     fct_jgraph jgraph;
+    fct_hoststage hs;
     bool use_pdl = false;       // FCT_PDL=1 enables programmatic dependent launch (measured: no gain, persistent grids)
     bool capturing = false;
     bool use_graph = true;      // FCT_NO_GRAPH=1 falls back to the static launch sequence with device-side early exit

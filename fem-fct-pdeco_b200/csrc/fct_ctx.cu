@@ -213,6 +213,11 @@ extern "C" int fct_ctx_destroy(fct_ctx* c) {
     cudaDeviceSynchronize();
     if (c->jgraph.exec) cudaGraphExecDestroy((cudaGraphExec_t)c->jgraph.exec);
     if (c->jgraph.graph) cudaGraphDestroy((cudaGraph_t)c->jgraph.graph);
+    if (c->hs.ready) {
+        for (int i = 0; i < 2; ++i) { cudaFree(c->hs.cbuf[i]); cudaEventDestroy(c->hs.c_ready[i]); cudaEventDestroy(c->hs.c_free[i]); }
+        for (int i = 0; i < 3; ++i) { cudaFree(c->hs.ubuf[i]); cudaEventDestroy(c->hs.u_ready[i]); cudaEventDestroy(c->hs.u_free[i]); }
+        cudaStreamDestroy(c->hs.d2h_stream);
+    }
     fct_templates_free(c);
     fct_p2p_destroy(c);
     fct_comm_destroy(c);
@@ -368,5 +373,11 @@ extern "C" int fct_ctx_set_rings(fct_ctx* ctx, int32_t depth, const int32_t* rin
     ctx->depth = depth;
     for (int j = 0; j <= depth; ++j) { ctx->ring_lo[j] = ring_lo[j]; ctx->ring_hi[j] = ring_hi[j]; }
     for (int j = depth + 1; j < 9; ++j) { ctx->ring_lo[j] = 0; ctx->ring_hi[j] = ctx->n; }
+    return 0;
+}
+
+extern "C" int fct_template_count(fct_ctx* ctx, int32_t* count) {
+    FCT_CHECK(ctx && count, "fct_template_count: null argument");
+    *count = ctx->tpl_count;
     return 0;
 }

@@ -123,41 +123,48 @@ extern "C" int fct_advdrift_state_host(fct_ctx* ctx, const double* c_host, doubl
     FCT_CHECK(ctx->cells && ctx->mass_set, "fct_advdrift_state_host: mesh / static matrices not set");
     FCT_CHECK(!ctx->comm, "fct_advdrift_state_host: single-GPU contexts only");
     const size_t n = (size_t)ctx->n, vb = sizeof(double) * n;
-    double *cbuf[2] = {nullptr, nullptr}, *ubuf[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t c_ready[2], c_free[2], u_ready[3], u_free[3];
-    int rc = 0;
-    for (int i = 0; i < 2; ++i) {
-        if (cudaMalloc((void**)&cbuf[i], vb) != cudaSuccess) rc = 1;
-        cudaEventCreateWithFlags(&c_ready[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&c_free[i], cudaEventDisableTiming);
+    // staging buffers, events and the second copy stream live in the context (allocated on first use): H2D of the
+    // next control slice and D2H of the previous state slice run on different streams, i.e. on both copy engines
+    fct_hoststage& hs = ctx->hs;
+    if (!hs.ready) {
+        bool ok = cudaStreamCreateWithFlags(&hs.d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i) {
+            ok = ok && cudaMalloc((void**)&hs.cbuf[i], vb) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&hs.c_ready[i], cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&hs.c_free[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        for (int i = 0; i < 3 && ok; ++i) {
+            ok = ok && cudaMalloc((void**)&hs.ubuf[i], vb) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&hs.u_ready[i], cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&hs.u_free[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        FCT_CHECK(ok, "fct_advdrift_state_host: staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        hs.ready = true;
     }
-    for (int i = 0; i < 3; ++i) {
-        if (cudaMalloc((void**)&ubuf[i], vb) != cudaSuccess) rc = 1;
-        cudaEventCreateWithFlags(&u_ready[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&u_free[i], cudaEventDisableTiming);
-    }
+    double** cbuf = hs.cbuf;
+    double** ubuf = hs.ubuf;
+    cudaEvent_t *c_ready = hs.c_ready, *c_free = hs.c_free, *u_ready = hs.u_ready, *u_free = hs.u_free;
+    cudaStream_t h2d = ctx->copy_stream, d2h = hs.d2h_stream;
     auto cleanup = [&]() {
-        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(h2d);
+        cudaStreamSynchronize(d2h);
         cudaStreamSynchronize(ctx->stream);
-        for (int i = 0; i < 2; ++i) { cudaFree(cbuf[i]); cudaEventDestroy(c_ready[i]); cudaEventDestroy(c_free[i]); }
-        for (int i = 0; i < 3; ++i) { cudaFree(ubuf[i]); cudaEventDestroy(u_ready[i]); cudaEventDestroy(u_free[i]); }
     };
-    if (rc) { cleanup(); fct_set_error("fct_advdrift_state_host: device allocation failed"); return 1; }
 #define TRY(call) do { if ((call) != cudaSuccess) { fct_set_error("fct_advdrift_state_host: %s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); cleanup(); return 1; } } while (0)
     if (acc_reset(ctx)) { cleanup(); return 1; }
     // initial condition
     TRY(cudaMemcpyAsync(ubuf[0], u_host, vb, cudaMemcpyHostToDevice, ctx->stream));
     if (num_steps >= 1) {
-        TRY(cudaMemcpyAsync(cbuf[1], c_host + n, vb, cudaMemcpyHostToDevice, ctx->copy_stream));
-        TRY(cudaEventRecord(c_ready[1], ctx->copy_stream));
+        TRY(cudaMemcpyAsync(cbuf[1], c_host + n, vb, cudaMemcpyHostToDevice, h2d));
+        TRY(cudaEventRecord(c_ready[1], h2d));
     }
     for (int i = 1; i <= num_steps; ++i) {
         const int cb = i & 1, un = (i - 1) % 3, uo = i % 3;
         // prefetch the next control slice into the other buffer once the step that used it has finished
         if (i + 1 <= num_steps) {
-            if (i >= 2) TRY(cudaStreamWaitEvent(ctx->copy_stream, c_free[(i + 1) & 1], 0));
-            TRY(cudaMemcpyAsync(cbuf[(i + 1) & 1], c_host + (size_t)(i + 1) * n, vb, cudaMemcpyHostToDevice, ctx->copy_stream));
-            TRY(cudaEventRecord(c_ready[(i + 1) & 1], ctx->copy_stream));
+            if (i >= 2) TRY(cudaStreamWaitEvent(h2d, c_free[(i + 1) & 1], 0));
+            TRY(cudaMemcpyAsync(cbuf[(i + 1) & 1], c_host + (size_t)(i + 1) * n, vb, cudaMemcpyHostToDevice, h2d));
+            TRY(cudaEventRecord(c_ready[(i + 1) & 1], h2d));
         }
         TRY(cudaStreamWaitEvent(ctx->stream, c_ready[cb], 0));
         if (i >= 3) TRY(cudaStreamWaitEvent(ctx->stream, u_free[uo], 0));   // D2H of slice i-3 done
@@ -168,12 +175,12 @@ extern "C" int fct_advdrift_state_host(fct_ctx* ctx, const double* c_host, doubl
         TRY(cudaEventRecord(c_free[cb], ctx->stream));
         TRY(cudaEventRecord(u_ready[uo], ctx->stream));
         // stream the new slice out
-        TRY(cudaStreamWaitEvent(ctx->copy_stream, u_ready[uo], 0));
-        TRY(cudaMemcpyAsync(u_host + (size_t)i * n, ubuf[uo], vb, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        TRY(cudaEventRecord(u_free[uo], ctx->copy_stream));
+        TRY(cudaStreamWaitEvent(d2h, u_ready[uo], 0));
+        TRY(cudaMemcpyAsync(u_host + (size_t)i * n, ubuf[uo], vb, cudaMemcpyDeviceToHost, d2h));
+        TRY(cudaEventRecord(u_free[uo], d2h));
     }
 #undef TRY
-    rc = acc_read(ctx, total_sweeps_host);
+    const int rc = acc_read(ctx, total_sweeps_host);
     cleanup();
     return rc;
 }

@@ -1181,6 +1181,50 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     return 0;
 }
 
+// Instrumentation for bench.py: builds the low-order system of (A, u_n, dt) and times `reps` back-to-back Jacobi sweeps
+// (the FCT step's k_jacobi_sweep, stopping test accumulation on every second one) with CUDA events on the context's
+// stream.  Single GPU.
+extern "C" int fct_bench_jacobi_sweeps(fct_ctx* ctx, const double* A, const double* un, double dt, int32_t reps,
+                                       float* ms_per_sweep_host) {
+    FCT_CHECK(ctx && A && un && ms_per_sweep_host && reps >= 2, "fct_bench_jacobi_sweeps: bad argument");
+    FCT_CHECK(ctx->mass_set && !ctx->comm, "fct_bench_jacobi_sweeps: single-GPU context with static matrices required");
+    double* bvec = ctx->w[3];
+    double* x = ctx->w[4];
+    double* tmp = ctx->w[5];
+    double* dinv = ctx->w[6];
+    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+    fct_set_ring(ctx, 0);
+    {
+        const size_t smem = FCT_NST_LOW * smem_bytes(ctx, 1, 2) + 2 * smem_bytes(ctx, 1, 0);
+        const int nb = fct_nblocks(ctx) < ctx->grid_low[0] ? fct_nblocks(ctx) : ctx->grid_low[0];
+        k_low_build<0><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, 1.0, nullptr, ctx->ML, un,
+                                                          nullptr, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,
+                                                          ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+    }
+    FCT_CUDA(cudaMemcpyAsync(x, un, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    cudaEvent_t e0, e1;
+    FCT_CUDA(cudaEventCreate(&e0));
+    FCT_CUDA(cudaEventCreate(&e1));
+    const double* Lv = ctx->Lvals;
+    for (int pass = 0; pass < 2; ++pass) {          // pass 0: warm-up
+        if (pass == 1) FCT_CUDA(cudaEventRecord(e0, ctx->stream));
+        for (int i = 0; i < reps; ++i) {
+            double* xin = (i & 1) ? tmp : x;
+            double* xout = (i & 1) ? x : tmp;
+            LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, bvec, dinv, xin, xout, ctx->jstate, i & 1,
+                            ctx->row_begin, ctx->row_end, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+        }
+    }
+    FCT_CUDA(cudaEventRecord(e1, ctx->stream));
+    FCT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    FCT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_sweep_host = ms / reps;
+    return fct_launch_error(ctx, "fct_bench_jacobi_sweeps");
+}
+
 extern "C" int fct_step_host(fct_ctx* ctx, const double* A, double sign, const double* S, const double* rhs,
                              const double* un, double dt, double* uout, fct_step_info* info) {
     FCT_CHECK(ctx && A && un && uout, "fct_step_host: null argument");

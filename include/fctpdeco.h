@@ -223,6 +223,12 @@ int fct_p2p_connect(fct_ctx* ctx, const void* all_handles_world_x_64bytes);
 int fct_p2p_error(fct_ctx* ctx, int32_t* error_host);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
+/* times `reps` back-to-back Jacobi sweeps of the low-order system of (A, u_n, dt) with CUDA events on the context's
+ * stream (the dominant kernel of the FCT step once the mass matrix runs on row templates); bench.py's roofline */
+int fct_bench_jacobi_sweeps(fct_ctx* ctx, const double* A_dev, const double* u_n_dev, double dt, int32_t reps,
+                            float* ms_per_sweep_host);
+/* number of row templates the static mass matrix compressed to (0 = CSR kernels in use) */
+int fct_template_count(fct_ctx* ctx, int32_t* count);
 /* CUDA events on the context's stream (what bench.py times kernels with) */
 int fct_event_create(fct_ctx* ctx, void** event_out);
 int fct_event_record(fct_ctx* ctx, void* event);
