@@ -79,6 +79,7 @@ struct fct_ctx {
     int32_t max_row = 0;
     int32_t grid_cap = 148 * 8; // persistent grid: SMs x resident 256-thread CTAs
     int32_t nst1 = 2, grid_nst1 = 148 * 4;       // ring stages / persistent grid of k_cheb_iter, k_jacobi_sweep
+    int32_t grid_flux_tpl = 148;                 // persistent grid of the template variants of the flux kernels
     int32_t grid_low[2] = {148, 148};            // persistent grids of k_low_build<0/1>
     int32_t grid_pipe1 = 148, grid_pipe2 = 148;   // persistent grids of the TMA-ring kernels (1 / 2 fp64 arrays)
     int32_t* rowptr = nullptr;  // device

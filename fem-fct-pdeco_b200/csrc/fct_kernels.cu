@@ -457,13 +457,17 @@ __global__ void k_jacobi_reset(unsigned long long* __restrict__ jstate) {
 
 // Zalesak limiter, pass 1 (helpers.py:1818-1851): raw fluxes f_ij = m_ij (ud_i - ud_j) + d_ij (ul_i - ul_j),
 // P+- = sums of positive/negative fluxes, Q+- = distance to the local extrema of u_low, R+- nodal factors.
-__global__ void __launch_bounds__(FCT_RB)
+// TPL: the mass-matrix entries come from the row templates (fct_templates.cu) instead of the TMA ring -- one fp64
+// array less to stream.
+template <bool TPL>
+__global__ void __launch_bounds__(FCT_RB, 3)
 k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Mv,
-              const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
+              const uint16_t* __restrict__ tcode, const double* __restrict__ tval, const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
               const double* __restrict__ ulow, double dt, double* __restrict__ Rpos, double* __restrict__ Rneg,
               int row_begin, int row_end, int64_t nnz, int cap) {
     __shared__ __align__(8) uint64_t bars[FCT_NST2];
-    RowPipe<2, 1, FCT_NST2> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv, Dv}, {colidx}};
+    RowPipe<(TPL ? 1 : 2), 1, FCT_NST2> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {TPL ? Dv : Mv}, {colidx}};
+    if (!TPL) pipe.gf[TPL ? 0 : 1] = Dv;
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
@@ -490,7 +494,13 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
             const int r = b.r0 + threadIdx.x;
             const int ks = cur.k0 - b.ka, ke = cur.k1 - b.ka, len = ke - ks;
             const double* sM = pipe.f64(i % FCT_NST2, 0);
-            const double* sD = pipe.f64(i % FCT_NST2, 1);
+            const double* sD = pipe.f64(i % FCT_NST2, TPL ? 0 : 1);
+            double tm[8];
+            if (TPL) {
+                const double2* tp = reinterpret_cast<const double2*>(tval + 8 * (int)tcode[r]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const double2 v = __ldg(tp + j); tm[2 * j] = v.x; tm[2 * j + 1] = v.y; }
+            }
             const int32_t* sC = pipe.s32(i % FCT_NST2, 0);
             const double udi = cur.ud, uli = cur.ul;
             double pp = 0.0, pn = 0.0, umax = uli, umin = uli;
@@ -504,7 +514,7 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (j < len && c[j] != r) {
-                        const double f = sM[ks + j] * (udi - udj[j]) + sD[ks + j] * (uli - ulj[j]);
+                        const double f = (TPL ? tm[j] : sM[ks + j]) * (udi - udj[j]) + sD[ks + j] * (uli - ulj[j]);
                         pp += fmax(f, 0.0);
                         pn += fmin(f, 0.0);
                         umax = fmax(umax, ulj[j]);
@@ -533,13 +543,15 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
 }
 
 // Zalesak limiter, pass 2 (helpers.py:1860-1870): alpha_ij, limited sum, explicit correction.
-__global__ void __launch_bounds__(FCT_RB)
+template <bool TPL>
+__global__ void __launch_bounds__(FCT_RB, 3)
 k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Mv,
-             const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
+             const uint16_t* __restrict__ tcode, const double* __restrict__ tval, const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
              const double* __restrict__ ulow, const double* __restrict__ Rpos, const double* __restrict__ Rneg,
              double dt, double* __restrict__ uout, int row_begin, int row_end, int64_t nnz, int cap) {
     __shared__ __align__(8) uint64_t bars[FCT_NST2];
-    RowPipe<2, 1, FCT_NST2> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Mv, Dv}, {colidx}};
+    RowPipe<(TPL ? 1 : 2), 1, FCT_NST2> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {TPL ? Dv : Mv}, {colidx}};
+    if (!TPL) pipe.gf[TPL ? 0 : 1] = Dv;
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
@@ -566,7 +578,13 @@ k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col
             const int r = b.r0 + threadIdx.x;
             const int ks = cur.k0 - b.ka, ke = cur.k1 - b.ka, len = ke - ks;
             const double* sM = pipe.f64(i % FCT_NST2, 0);
-            const double* sD = pipe.f64(i % FCT_NST2, 1);
+            const double* sD = pipe.f64(i % FCT_NST2, TPL ? 0 : 1);
+            double tm[8];
+            if (TPL) {
+                const double2* tp = reinterpret_cast<const double2*>(tval + 8 * (int)tcode[r]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const double2 v = __ldg(tp + j); tm[2 * j] = v.x; tm[2 * j + 1] = v.y; }
+            }
             const int32_t* sC = pipe.s32(i % FCT_NST2, 0);
             const double udi = cur.ud, uli = cur.ul, rpi = cur.rp, rni = cur.rn;
             double fbar = 0.0;
@@ -586,7 +604,7 @@ k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col
                     for (int j = 0; j < 4; ++j) {
                         const int k = ks + 4 * h + j;
                         if (4 * h + j < len && c[j] != r) {
-                            const double f = sM[k] * (udi - udj[j]) + sD[k] * (uli - ulj[j]);
+                            const double f = (TPL ? tm[4 * h + j] : sM[k]) * (udi - udj[j]) + sD[k] * (uli - ulj[j]);
                             const double alpha = (f > 0.0) ? fmin(rpi, rnj[j]) : fmin(rni, rpj[j]);
                             fbar += alpha * f;
                         }
@@ -814,8 +832,10 @@ int fct_kernels_configure(fct_ctx* ctx) {
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_gen<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_gen<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_gen<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
-    FCT_CUDA(cudaFuncSetAttribute(k_flux_limits, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
-    FCT_CUDA(cudaFuncSetAttribute(k_flux_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_flux_limits<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_flux_apply<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_flux_limits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_flux_apply<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_row_lump, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_dot_M, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CHECK(FCT_NST_LOW * smem_bytes(ctx, 2, 2) + 2 * smem_bytes(ctx, 1, 0) <= (size_t)FCT_SMEM_OPTIN,
@@ -838,7 +858,10 @@ int fct_kernels_configure(fct_ctx* ctx) {
         if (o && atoi(o) >= 1 && atoi(o) < occn) occn = atoi(o);
         ctx->grid_nst1 = prop.multiProcessorCount * occn;
     }
-    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_flux_apply, FCT_RB, FCT_NST2 * smem_bytes(ctx, 2, 1)));
+    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_flux_apply<false>, FCT_RB, FCT_NST2 * smem_bytes(ctx, 2, 1)));
+    int occ2t = 0;
+    FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2t, k_flux_apply<true>, FCT_RB, FCT_NST2 * smem_bytes(ctx, 1, 1)));
+    ctx->grid_flux_tpl = prop.multiProcessorCount * (occ2t > 0 ? occ2t : 1);
     FCT_CHECK(occ1 >= 1 && occ2 >= 1, "TMA-ring kernels do not fit on an SM (cap=%d)", ctx->cap);
     int occl0 = 0, occl1 = 0;
     FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
@@ -1166,15 +1189,32 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
         if (fct_halo_exchange_if(ctx, udot)) return 1;
     }
     fct_set_ring(ctx, rflux);
-    LAUNCH_PIPE(ctx, k_flux_limits, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, dt, Rp, Rn,
-                ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+    const bool ftpl = ctx->tpl_count > 0;
+    const int gflux = fct_nblocks(ctx) < ctx->grid_flux_tpl ? fct_nblocks(ctx) : ctx->grid_flux_tpl;
+    if (ftpl) {
+        if (gflux > 0)
+            launch_pipe(ctx, k_flux_limits<true>, gflux, FCT_NST2 * smem_bytes(ctx, 1, 1), ctx->rowptr, ctx->colidx, ctx->M,
+                        ctx->tpl_code, ctx->tpl_val, ctx->Dvals, ctx->ML, udot, ulow, dt, Rp, Rn, ctx->cur_rb, ctx->cur_re,
+                        ctx->nnz, ctx->cap);
+    } else {
+        LAUNCH_PIPE(ctx, k_flux_limits<false>, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->tpl_code, ctx->tpl_val, ctx->Dvals,
+                    ctx->ML, udot, ulow, dt, Rp, Rn, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+    }
     if (K < 2) {
         if (fct_halo_exchange2_if(ctx, Rp, Rn)) return 1;
     }
     // 8-9. limited sum + update on the owned rows
     fct_set_ring(ctx, 0);
-    LAUNCH_PIPE(ctx, k_flux_apply, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->Dvals, ctx->ML, udot, ulow, Rp, Rn, dt,
-                uout, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+    if (ftpl) {
+        const int ga = fct_nblocks(ctx) < ctx->grid_flux_tpl ? fct_nblocks(ctx) : ctx->grid_flux_tpl;
+        if (ga > 0)
+            launch_pipe(ctx, k_flux_apply<true>, ga, FCT_NST2 * smem_bytes(ctx, 1, 1), ctx->rowptr, ctx->colidx, ctx->M,
+                        ctx->tpl_code, ctx->tpl_val, ctx->Dvals, ctx->ML, udot, ulow, Rp, Rn, dt, uout, ctx->cur_rb, ctx->cur_re,
+                        ctx->nnz, ctx->cap);
+    } else {
+        LAUNCH_PIPE(ctx, k_flux_apply<false>, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->tpl_code, ctx->tpl_val, ctx->Dvals,
+                    ctx->ML, udot, ulow, Rp, Rn, dt, uout, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+    }
     if (fct_launch_error(ctx, "fct_step")) return 1;
     if (fct_halo_exchange_if(ctx, uout)) return 1;
     if (info) return fct_read_step_info(ctx, info);

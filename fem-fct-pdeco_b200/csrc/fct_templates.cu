@@ -158,6 +158,9 @@ __device__ __forceinline__ double tpl_row_dot(const uint16_t* __restrict__ code,
     return acc;
 }
 
+// Measured on B200 (4097^2): this plain grid-stride form runs at 0.148 ms (4.7 TB/s of actual traffic); fetching the
+// next block's inputs ahead (0.175 ms) or several rows per thread (0.195 ms) is slower -- both widen the window of
+// rows in flight, and the neighbour gathers then miss in L2 more often.
 __global__ void __launch_bounds__(FCT_RB)
 k_cheb_iter_tpl(const uint16_t* __restrict__ code, const int32_t* __restrict__ toff, const double* __restrict__ tval,
                 const double* __restrict__ Md, const double* __restrict__ g, const double* __restrict__ ymid,
