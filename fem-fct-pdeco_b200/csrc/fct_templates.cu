@@ -191,7 +191,10 @@ k_spmv_tpl(const uint16_t* __restrict__ code, const int32_t* __restrict__ toff, 
 
 static inline int tpl_grid(const fct_ctx* ctx) {
     const int nb = fct_nblocks(ctx);
-    const int cap = ctx->grid_cap;       // SMs x 8 resident 256-thread CTAs
+    int cap = ctx->grid_cap;             // SMs x 8 resident 256-thread CTAs
+    static int per_sm = -1;              // tuning knob: FCT_TPL_CTAS = CTAs per SM (1..8)
+    if (per_sm < 0) { const char* e = getenv("FCT_TPL_CTAS"); per_sm = (e && atoi(e) >= 1 && atoi(e) <= 8) ? atoi(e) : 0; }
+    if (per_sm > 0) cap = ctx->grid_cap / 8 * per_sm;
     return nb < cap ? nb : cap;
 }
 
