@@ -19,6 +19,8 @@
 #define FCT_RB 256            // rows (= threads) per CTA
 #define FCT_ALIGN 4           // staging alignment in elements (16 B for int32, 32 B for fp64)
 #define FCT_SMEM_OPTIN (200 * 1024)   // dynamic shared memory opt-in ceiling for every row-block kernel
+#define FCT_TPL_W 8            // row-template width (entries per row), fct_templates.cu
+#define FCT_TPL_MAX 65535
 
 void fct_set_error(const char* fmt, ...);
 
@@ -60,6 +62,8 @@ struct fct_jgraph {
     double rtol = 0.0;
     int max_sweeps = 0;
     int depth = 0;
+    int mode = -1;
+    const void* tpl = nullptr;   // template table the captured sweeps point into (rebuilt by fct_ctx_set_mass)
 };
 
 struct fct_ctx {
@@ -79,6 +83,8 @@ struct fct_ctx {
     int32_t max_row = 0;
     int32_t grid_cap = 148 * 8; // persistent grid: SMs x resident 256-thread CTAs
     int32_t nst1 = 2, grid_nst1 = 148 * 4;       // ring stages / persistent grid of k_cheb_iter, k_jacobi_sweep
+    int32_t nst_jtpl = 3;                        // ring stages of k_jacobi_sweep_tpl (FCT_NST_JTPL)
+    int32_t grid_jtpl = 148 * 4;                 // persistent grid of k_jacobi_sweep_tpl
     int32_t grid_flux_tpl = 148;                 // persistent grid of the template variants of the flux kernels
     int32_t grid_low[2] = {148, 148};            // persistent grids of k_low_build<0/1>
     int32_t grid_pipe1 = 148, grid_pipe2 = 148;   // persistent grids of the TMA-ring kernels (1 / 2 fp64 arrays)
@@ -101,7 +107,12 @@ struct fct_ctx {
     uint16_t* tpl_code = nullptr;
     int32_t* tpl_off = nullptr;
     double* tpl_val = nullptr;
+    double* tpl_diag = nullptr;      // [T] diagonal value of each template (= diag(M) of its rows)
     int32_t tpl_count = 0;
+    // Low-order Jacobi on the row templates: 0 = CSR kernels, 1 = column offsets from the templates (bit-identical to 0),
+    // 2 = additionally rows pre-scaled by 1/l_ii in k_low_build (no dinv read in the sweep).  FCT_JAC_TPL selects.
+    int32_t jac_mode = 0;
+    int32_t cheb_mdtab = 1;          // ChebSI takes diag(M) from the template table when the caller passes ctx->Mdiag
     // workspace
     double* Lvals = nullptr;    // low-order operator
     double* Dvals = nullptr;    // artificial diffusion (off-diagonals)

@@ -166,7 +166,7 @@ __device__ __forceinline__ unsigned long long f64_sort_key(double v) {
 //   b    = M_L u_n + dt rhs                     [helpers.py:1780]
 // `sign` folds the legacy FCT_alg convention (A -> -A, old_helpers.py:135-145) into the same kernel.
 // Outputs: Lv (off-diagonals of L, diagonal slot 0), dinv = 1/l_ii, Dv (off-diagonals; diagonal slot holds d_ii), b;
-// min row sum of L.
+// min row sum of L.  scale_rows: Lv and b are stored divided by l_ii (the Jacobi fixed point is unchanged).
 // A (and S), colidx, tpos arrive through a 2-stage TMA ring; L and D leave through two staging buffers.
 #define FCT_NST_LOW 2
 template <int HAS_S>
@@ -175,7 +175,8 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             const double* __restrict__ A, double sign, const double* __restrict__ S, const double* __restrict__ ML,
             const double* __restrict__ un, const double* __restrict__ rhs, double dt,
             double* __restrict__ Lv, double* __restrict__ Dv, double* __restrict__ bvec, double* __restrict__ dinv,
-            unsigned long long* __restrict__ min_rowsum_key, int row_begin, int row_end, int64_t nnz, int cap) {
+            unsigned long long* __restrict__ min_rowsum_key, int scale_rows, int row_begin, int row_end, int64_t nnz,
+            int cap) {
     __shared__ __align__(8) uint64_t bars[FCT_NST_LOW];
     __shared__ double sred[FCT_RB / 32];
     RowPipe<1 + HAS_S, 2, FCT_NST_LOW> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {A}, {colidx, tpos}};
@@ -267,10 +268,16 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             if (HAS_S) l += dt * sS[kd];
             lsum += l;
             sL[kd] = 0.0;          // the diagonal travels as 1/l_ii in `dinv`: the Jacobi row loop is branch-free
-            dinv[r] = 1.0 / l;
+            const double di = 1.0 / l;
+            dinv[r] = di;
             sD[kd] = dii;
             rowsum = fmin(rowsum, lsum);
-            bvec[r] = ml * unr + (rhs ? dt * rr : 0.0);
+            double br = ml * unr + (rhs ? dt * rr : 0.0);
+            if (scale_rows) {      // Jacobi on the row-scaled system (k_jacobi_sweep_tpl<.., true>): x_new = b' - sum l'_ij x_j
+                for (int k = ks; k < ke; ++k) sL[k] *= di;
+                br *= di;
+            }
+            bvec[r] = br;
         }
         cur = nxt;
         __syncthreads();
@@ -404,6 +411,90 @@ k_jacobi_sweep_gen(const int32_t* __restrict__ rowptr, const int32_t* __restrict
                    int row_begin, int row_end, int64_t nnz, int cap) {
     jacobi_sweep_body<NST, false>(rowptr, colidx, Lv, bvec, dinv, x, xnew, jstate, check, own_rb, own_re, row_begin,
                                   row_end, nnz, cap);
+}
+
+// Jacobi sweep of the FCT low-order system with the column pattern taken from the row templates of M (every matrix of a
+// context lives on the same pattern): per row a 16-bit code replaces the 4 B/entry column indices, the TMA ring carries
+// the matrix values only.  SCALED = false: x_new = (b - sum l_ij x_j) / l_ii with dinv = 1/l_ii -- the same operations in
+// the same order as k_jacobi_sweep, bit-identical.  SCALED = true: k_low_build has divided the row and b by l_ii, so
+// x_new = b' - sum l'_ij x_j and dinv is not read.  The code of a row is fetched two blocks ahead and its offsets one
+// block ahead, so the code -> offsets -> gather chain never waits on DRAM.
+template <int NST, bool SCALED>
+__global__ void __launch_bounds__(FCT_RB, 5)
+k_jacobi_sweep_tpl(const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ code, const int32_t* __restrict__ toff,
+                   const double* __restrict__ Lv, const double* __restrict__ bvec, const double* __restrict__ dinv,
+                   const double* __restrict__ x, double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check,
+                   int own_rb, int own_re, int row_begin, int row_end, int64_t nnz, int cap) {
+    if (*reinterpret_cast<volatile unsigned long long*>(jstate + 3)) return;
+    __shared__ __align__(8) uint64_t bars[NST];
+    __shared__ double sred[FCT_RB / 32];
+    RowPipe<1, 0, NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {Lv}, {nullptr}};
+    const int nmine = pipe.my_blocks();
+    pipe.init();
+    pipe.prologue(nmine);
+    struct RowIn { int k0, len; double b, x, di; int4 o0, o1; };
+    auto row_of = [&](int i) {
+        const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+        const int r = row_begin + blk * FCT_RB + (int)threadIdx.x;
+        return (i < nmine && r < row_end) ? r : -1;
+    };
+    auto load_code = [&](int i) {
+        const int r = row_of(i);
+        return r >= 0 ? (int)code[r] : 0;
+    };
+    auto load_row = [&](int i, int t) {
+        RowIn in{0, 0, 0.0, 0.0, 1.0, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+        const int r = row_of(i);
+        if (r >= 0) {
+            in.k0 = rowptr[r]; in.len = rowptr[r + 1] - in.k0;
+            in.b = bvec[r];
+            if (!SCALED) in.di = dinv[r];
+            if (check) in.x = x[r];
+            in.o0 = __ldg(reinterpret_cast<const int4*>(toff + FCT_TPL_W * t));
+            in.o1 = __ldg(reinterpret_cast<const int4*>(toff + FCT_TPL_W * t) + 1);
+        }
+        return in;
+    };
+    RowIn cur = load_row(0, load_code(0));
+    int tnext = load_code(1);
+    double delta = 0.0, xa = 0.0;
+    for (int i = 0; i < nmine; ++i) {
+        pipe.prefetch(i, nmine);
+        const RowIn nxt = load_row(i + 1, tnext);
+        tnext = load_code(i + 2);
+        const RowBlock b = pipe.block(i);
+        pipe.wait(i, b);
+        if ((int)threadIdx.x < b.nr) {
+            const int r = b.r0 + threadIdx.x;
+            const double* sL = pipe.f64(i % NST, 0) + (cur.k0 - b.ka);
+            const int off[8] = {cur.o0.x, cur.o0.y, cur.o0.z, cur.o0.w, cur.o1.x, cur.o1.y, cur.o1.z, cur.o1.w};
+            double xv[8], v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = x[r + off[j]];          // padded slots: offset 0
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (j < cur.len) ? sL[j] : 0.0;
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += v[j] * xv[j];            // diagonal slot holds 0
+            const double xn = SCALED ? (cur.b - acc) : (cur.b - acc) * cur.di;
+            xnew[r] = xn;
+            if (check && r >= own_rb && r < own_re) {
+                delta = fmax(delta, fabs(xn - cur.x));
+                xa = fmax(xa, fabs(xn));
+            }
+        }
+        cur = nxt;
+        __syncthreads();
+    }
+    if (check) {
+        const double dm = block_max(delta, sred);
+        const double xm = block_max(xa, sred);
+        if (threadIdx.x == 0) {
+            atomicMax(jstate + 0, (unsigned long long)__double_as_longlong(dm));
+            atomicMax(jstate + 1, (unsigned long long)__double_as_longlong(xm));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(jstate + 4, 1ull);
 }
 
 // After a checked sweep (and, multi-GPU, after the max-allreduce of jstate[0..1]): decide convergence.
@@ -804,6 +895,22 @@ static inline int pipe_grid(const fct_ctx* c, int nf64) {
         }                                                                                                \
     } while (0)
 
+// k_jacobi_sweep_tpl: the ring carries one fp64 array and no index array; grid = SMs x its own occupancy
+static inline void launch_jacobi_tpl(fct_ctx* ctx, const double* Lv, const double* b, const double* dinv, const double* xin,
+                                     double* xout, int chk) {
+    const int nb0 = fct_nblocks(ctx);
+    const int nb = nb0 < ctx->grid_jtpl ? nb0 : ctx->grid_jtpl;
+    if (nb <= 0) return;
+    const size_t sm = (size_t)ctx->nst_jtpl * smem_bytes(ctx, 1, 0);
+#define JT_ARGS ctx->rowptr, ctx->tpl_code, ctx->tpl_off, Lv, b, dinv, xin, xout, ctx->jstate, chk, ctx->row_begin, \
+                ctx->row_end, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap
+    const bool sc = ctx->jac_mode == 2;
+    if (ctx->nst_jtpl == 2) { if (sc) launch_pipe(ctx, k_jacobi_sweep_tpl<2, true>, nb, sm, JT_ARGS); else launch_pipe(ctx, k_jacobi_sweep_tpl<2, false>, nb, sm, JT_ARGS); }
+    else if (ctx->nst_jtpl == 4) { if (sc) launch_pipe(ctx, k_jacobi_sweep_tpl<4, true>, nb, sm, JT_ARGS); else launch_pipe(ctx, k_jacobi_sweep_tpl<4, false>, nb, sm, JT_ARGS); }
+    else { if (sc) launch_pipe(ctx, k_jacobi_sweep_tpl<3, true>, nb, sm, JT_ARGS); else launch_pipe(ctx, k_jacobi_sweep_tpl<3, false>, nb, sm, JT_ARGS); }
+#undef JT_ARGS
+}
+
 int fct_launch_error(fct_ctx* ctx, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -829,6 +936,12 @@ int fct_kernels_configure(fct_ctx* ctx) {
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_gen<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_gen<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_gen<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
@@ -857,6 +970,17 @@ int fct_kernels_configure(fct_ctx* ctx) {
         const char* o = getenv("FCT_OCC");      // tuning knob: cap the resident CTAs per SM
         if (o && atoi(o) >= 1 && atoi(o) < occn) occn = atoi(o);
         ctx->grid_nst1 = prop.multiProcessorCount * occn;
+        int occj = 0;
+        const char* ej = getenv("FCT_NST_JTPL");
+        ctx->nst_jtpl = (ej && (atoi(ej) == 2 || atoi(ej) == 4)) ? atoi(ej) : 3;
+        const size_t smj = (size_t)ctx->nst_jtpl * smem_bytes(ctx, 1, 0);
+        if (ctx->nst_jtpl == 2) FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occj, k_jacobi_sweep_tpl<2, true>, FCT_RB, smj));
+        else if (ctx->nst_jtpl == 4) FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occj, k_jacobi_sweep_tpl<4, true>, FCT_RB, smj));
+        else FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occj, k_jacobi_sweep_tpl<3, true>, FCT_RB, smj));
+        if (occj < 1) occj = 1;
+        const char* oj = getenv("FCT_OCC_JTPL");
+        if (oj && atoi(oj) >= 1 && atoi(oj) < occj) occj = atoi(oj);
+        ctx->grid_jtpl = prop.multiProcessorCount * occj;
     }
     FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_flux_apply<false>, FCT_RB, FCT_NST2 * smem_bytes(ctx, 2, 1)));
     int occ2t = 0;
@@ -1009,7 +1133,9 @@ static int jacobi_cycle(fct_ctx* ctx, const double* Lv, const double* b, const d
                         double rtol, int max_sweeps, bool p2p, int use_handle, cudaGraphConditionalHandle handle) {
 #define JACOBI_LAUNCH(xin, xout, chk)                                                                              \
     do {                                                                                                           \
-        if (dinv)                                                                                                  \
+        if (dinv && ctx->jac_mode > 0 && ctx->tpl_count > 0)                                                       \
+            launch_jacobi_tpl(ctx, Lv, b, dinv, xin, xout, chk);                                                   \
+        else if (dinv)                                                                                             \
             LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, b, dinv, xin, xout, ctx->jstate, chk, \
                             ctx->row_begin, ctx->row_end, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);           \
         else                                                                                                       \
@@ -1058,7 +1184,7 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
         // is rebuilt only if an operand pointer or a solver option changes.
         fct_jgraph& jg = ctx->jgraph;
         if (!jg.exec || jg.Lv != Lv || jg.b != b || jg.dinv != dinv || jg.x != x || jg.tmp != tmp || jg.rtol != rtol ||
-            jg.max_sweeps != max_sweeps || jg.depth != ctx->depth) {
+            jg.max_sweeps != max_sweeps || jg.depth != ctx->depth || jg.mode != ctx->jac_mode || jg.tpl != (const void*)ctx->tpl_code) {
             if (jg.exec) { cudaGraphExecDestroy((cudaGraphExec_t)jg.exec); jg.exec = nullptr; }
             if (jg.graph) { cudaGraphDestroy((cudaGraph_t)jg.graph); jg.graph = nullptr; }
             cudaGraph_t g;
@@ -1092,6 +1218,8 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
             jg.graph = g; jg.exec = ex;
             jg.Lv = Lv; jg.b = b; jg.dinv = dinv; jg.x = x; jg.tmp = tmp; jg.rtol = rtol; jg.max_sweeps = max_sweeps;
             jg.depth = ctx->depth;
+            jg.mode = ctx->jac_mode;
+            jg.tpl = ctx->tpl_code;
         }
         FCT_CUDA(cudaGraphLaunch((cudaGraphExec_t)jg.exec, ctx->stream));
         ctx->launches += 3;      // at least one body iteration; the executed sweeps are counted in jstate[4]
@@ -1165,11 +1293,11 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
             if (S)
                 k_low_build<1><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un,
                                                                   rhs, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,
-                                                                  ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+                                                                  ctx->jac_mode == 2, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
             else
                 k_low_build<0><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un,
                                                                   rhs, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,
-                                                                  ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+                                                                  ctx->jac_mode == 2, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
             ctx->launches++;
         }
     }
@@ -1239,7 +1367,7 @@ extern "C" int fct_bench_jacobi_sweeps(fct_ctx* ctx, const double* A, const doub
         const int nb = fct_nblocks(ctx) < ctx->grid_low[0] ? fct_nblocks(ctx) : ctx->grid_low[0];
         k_low_build<0><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, 1.0, nullptr, ctx->ML, un,
                                                           nullptr, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,
-                                                          ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+                                                          ctx->jac_mode == 2, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
     }
     FCT_CUDA(cudaMemcpyAsync(x, un, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
     cudaEvent_t e0, e1;
@@ -1251,8 +1379,11 @@ extern "C" int fct_bench_jacobi_sweeps(fct_ctx* ctx, const double* A, const doub
         for (int i = 0; i < reps; ++i) {
             double* xin = (i & 1) ? tmp : x;
             double* xout = (i & 1) ? x : tmp;
-            LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, bvec, dinv, xin, xout, ctx->jstate, i & 1,
-                            ctx->row_begin, ctx->row_end, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+            if (ctx->jac_mode > 0 && ctx->tpl_count > 0)
+                launch_jacobi_tpl(ctx, Lv, bvec, dinv, xin, xout, i & 1);
+            else
+                LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, Lv, bvec, dinv, xin, xout, ctx->jstate, i & 1,
+                                ctx->row_begin, ctx->row_end, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
         }
     }
     FCT_CUDA(cudaEventRecord(e1, ctx->stream));

@@ -15,9 +15,6 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 
-#define FCT_TPL_W 8            // template width (entries per row)
-#define FCT_TPL_MAX 65535
-
 __device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsigned long long v) {
     h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
     h *= 0xFF51AFD7ED558CCDull;
@@ -54,15 +51,18 @@ __global__ void k_assign_codes(const unsigned long long* __restrict__ hash, cons
 
 __global__ void k_fill_templates(const int* __restrict__ rep, const int32_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ colidx, const double* __restrict__ vals, int T,
-                                 int32_t* __restrict__ toff, double* __restrict__ tval) {
+                                 int32_t* __restrict__ toff, double* __restrict__ tval, double* __restrict__ tdiag) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     const int r = rep[t];
     const int k0 = rowptr[r], len = rowptr[r + 1] - k0;
+    double dg = 0.0;
     for (int j = 0; j < FCT_TPL_W; ++j) {
         toff[FCT_TPL_W * t + j] = (j < len) ? colidx[k0 + j] - r : 0;     // padding: offset 0, value 0
         tval[FCT_TPL_W * t + j] = (j < len) ? vals[k0 + j] : 0.0;
+        if (j < len && colidx[k0 + j] == r) dg = vals[k0 + j];
     }
+    tdiag[t] = dg;
 }
 
 // exact check: every row must reproduce its template bit for bit
@@ -83,9 +83,11 @@ __global__ void k_verify_templates(const int32_t* __restrict__ rowptr, const int
 }
 
 void fct_templates_free(fct_ctx* ctx) {
-    cudaFree(ctx->tpl_code); cudaFree(ctx->tpl_off); cudaFree(ctx->tpl_val);
-    ctx->tpl_code = nullptr; ctx->tpl_off = nullptr; ctx->tpl_val = nullptr;
+    cudaFree(ctx->tpl_code); cudaFree(ctx->tpl_off); cudaFree(ctx->tpl_val); cudaFree(ctx->tpl_diag);
+    ctx->tpl_code = nullptr; ctx->tpl_off = nullptr; ctx->tpl_val = nullptr; ctx->tpl_diag = nullptr;
     ctx->tpl_count = 0;
+    ctx->jac_mode = 0;
+    ctx->jgraph.mode = -1;           // a captured Jacobi loop points into the freed tables: force a rebuild
 }
 
 // (Re)build the templates of ctx->M.  Never fails the caller: on any problem the context simply has no templates.
@@ -122,10 +124,12 @@ int fct_templates_build(fct_ctx* ctx) {
         if (cudaMalloc((void**)&ctx->tpl_code, sizeof(uint16_t) * ((size_t)n + 8)) != cudaSuccess) break;
         if (cudaMalloc((void**)&ctx->tpl_off, sizeof(int32_t) * FCT_TPL_W * (size_t)T) != cudaSuccess) break;
         if (cudaMalloc((void**)&ctx->tpl_val, sizeof(double) * FCT_TPL_W * (size_t)T) != cudaSuccess) break;
+        if (cudaMalloc((void**)&ctx->tpl_diag, sizeof(double) * (size_t)T) != cudaSuccess) break;
         cudaMemsetAsync(rep, 0x7f, sizeof(int) * (size_t)T, st);
         cudaMemsetAsync(bad, 0, sizeof(int), st);
         k_assign_codes<<<(n + 255) / 256, 256, 0, st>>>(hash, uniq, T, n, ctx->tpl_code, rep);
-        k_fill_templates<<<(T + 255) / 256, 256, 0, st>>>(rep, ctx->rowptr, ctx->colidx, ctx->M, T, ctx->tpl_off, ctx->tpl_val);
+        k_fill_templates<<<(T + 255) / 256, 256, 0, st>>>(rep, ctx->rowptr, ctx->colidx, ctx->M, T, ctx->tpl_off, ctx->tpl_val,
+                                                        ctx->tpl_diag);
         k_verify_templates<<<(n + 255) / 256, 256, 0, st>>>(ctx->rowptr, ctx->colidx, ctx->M, n, ctx->tpl_code, ctx->tpl_off,
                                                             ctx->tpl_val, bad);
         ctx->launches += 4;
@@ -135,8 +139,15 @@ int fct_templates_build(fct_ctx* ctx) {
     } while (0);
     cudaFree(hash); cudaFree(sorted); cudaFree(uniq); cudaFree(dT); cudaFree(rep); cudaFree(bad); cudaFree(tmp);
     cudaGetLastError();
-    if (ok) ctx->tpl_count = T;
-    else fct_templates_free(ctx);
+    if (ok) {
+        ctx->tpl_count = T;
+        const char* jm = getenv("FCT_JAC_TPL");      // 0: CSR sweeps, 1: template columns, 2 (default): + pre-scaled rows
+        ctx->jac_mode = (jm && atoi(jm) >= 0 && atoi(jm) <= 2) ? atoi(jm) : 2;
+        const char* mt = getenv("FCT_CHEB_MDTAB");   // 0: ChebSI always reads Md from memory
+        ctx->cheb_mdtab = (mt && atoi(mt) == 0) ? 0 : 1;
+    } else {
+        fct_templates_free(ctx);
+    }
     return 0;
 }
 
@@ -163,12 +174,14 @@ __device__ __forceinline__ double tpl_row_dot(const uint16_t* __restrict__ code,
 // rows in flight, and the neighbour gathers then miss in L2 more often.
 __global__ void __launch_bounds__(FCT_RB)
 k_cheb_iter_tpl(const uint16_t* __restrict__ code, const int32_t* __restrict__ toff, const double* __restrict__ tval,
-                const double* __restrict__ Md, const double* __restrict__ g, const double* __restrict__ ymid,
-                const double* __restrict__ yold, double* __restrict__ ynew, double omega, double dscale, int has_old,
-                int row_begin, int row_end) {
+                const double* __restrict__ tdiag, const double* __restrict__ Md, const double* __restrict__ g,
+                const double* __restrict__ ymid, const double* __restrict__ yold, double* __restrict__ ynew, double omega,
+                double dscale, int has_old, int row_begin, int row_end) {
     const int stride = (int)gridDim.x * FCT_RB;
     for (int r = row_begin + (int)blockIdx.x * FCT_RB + (int)threadIdx.x; r < row_end; r += stride) {
-        const double gr = g[r], mdr = Md[r], ym = ymid[r];
+        // Md == nullptr: the caller's Md is diag(M) of the templated matrix itself, so it comes out of the table
+        // (same bits) and the 8 B/row read is saved
+        const double gr = g[r], mdr = Md ? Md[r] : __ldg(tdiag + code[r]), ym = ymid[r];
         const double yo = has_old ? yold[r] : 0.0;
         const double acc = tpl_row_dot(code, toff, tval, ymid, r);
         const double z = (gr - acc) / (dscale * mdr);
@@ -202,8 +215,9 @@ int fct_cheb_iter_tpl(fct_ctx* ctx, const double* Md, const double* g, const dou
                       double* ynew, double omega, double dscale) {
     const int grid = tpl_grid(ctx);
     if (grid > 0) {
-        k_cheb_iter_tpl<<<grid, FCT_RB, 0, ctx->stream>>>(ctx->tpl_code, ctx->tpl_off, ctx->tpl_val, Md, g, ymid, yold, ynew,
-                                                         omega, dscale, yold != nullptr, ctx->cur_rb, ctx->cur_re);
+        const double* Mdk = (ctx->cheb_mdtab && Md == ctx->Mdiag) ? nullptr : Md;
+        k_cheb_iter_tpl<<<grid, FCT_RB, 0, ctx->stream>>>(ctx->tpl_code, ctx->tpl_off, ctx->tpl_val, ctx->tpl_diag, Mdk, g, ymid,
+                                                         yold, ynew, omega, dscale, yold != nullptr, ctx->cur_rb, ctx->cur_re);
         ctx->launches++;
     }
     return 0;

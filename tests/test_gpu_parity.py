@@ -335,3 +335,31 @@ def test_multi_gpu_matches_single_gpu():
            "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py"), "96"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MGPU_CHECK PASSED" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_template_jacobi_modes(monkeypatch):
+    """Low-order Jacobi sweeps with the column pattern from the row templates: FCT_JAC_TPL=1 (template columns) must be
+    bit-identical to the CSR sweeps (=0); =2 (rows pre-scaled by 1/l_ii, the default) solves the same system to the same
+    stopping test.  ChebSI with diag(M) from the template table is bit-identical to reading Md."""
+    n, ns = 64, 3
+    h = 1.0 / n
+    dt = 0.25 * h / (2 * np.sqrt(2))
+    m = RectMeshP1(n, 0.0, 1.0)
+    xy = m.dof_xy
+    u0 = np.exp(-20 * ((2 * xy[:, 0] - 1 + 2 / 3) ** 2 + 5 * (2 * xy[:, 1] - 1 + 5 / 6) ** 2))
+    rng = np.random.default_rng(5)
+    c = 1.0 + rng.random((ns + 1, m.nodes))
+    res = {}
+    for mode, mdtab in (("0", "0"), ("1", "1"), ("2", "1")):
+        monkeypatch.setenv("FCT_JAC_TPL", mode)
+        monkeypatch.setenv("FCT_CHEB_MDTAB", mdtab)
+        ctx = RectMeshP1(n, 0.0, 1.0).context()
+        assert ctx.template_count() > 0
+        utr = np.zeros((ns + 1, m.nodes)); utr[0] = u0
+        du = ctx.array(utr.ravel())
+        sw = ctx.advdrift_state(ctx.array(c.ravel()), du, ns, dt)
+        res[mode] = (du.download().reshape(ns + 1, -1), sw)
+    assert np.array_equal(res["0"][0], res["1"][0]) and res["0"][1] == res["1"][1]
+    for i in range(1, ns + 1):
+        assert rel_l2(res["2"][0][i], res["0"][0][i]) < 1e-13 * i
+    assert abs(res["2"][1] - res["0"][1]) <= 2 * ns
