@@ -285,6 +285,15 @@ class FctContext:
         check(lib.fct_bench_jacobi_sweeps(self.handle, A.ptr, u_n.ptr, float(dt), int(reps), C.byref(ms)))
         return ms.value
 
+    def debug_jacobi_fixed(self, A, u_n, dt, sweeps, fused, x_out):
+        check(lib.fct_debug_jacobi_fixed(self.handle, A.ptr, u_n.ptr, float(dt), int(sweeps), int(fused), x_out.ptr))
+
+    def bench_jacobi_fused(self, A, u_n, dt, sweeps=14, reps=5):
+        """ms per sweep of the wavefront kernel (all `sweeps` Jacobi sweeps of a solve in one launch)"""
+        ms = C.c_float()
+        check(lib.fct_bench_jacobi_fused(self.handle, A.ptr, u_n.ptr, float(dt), int(sweeps), int(reps), C.byref(ms)))
+        return ms.value
+
     # -- timing ------------------------------------------------------------------------------------
     def event(self):
         e = C.c_void_p()

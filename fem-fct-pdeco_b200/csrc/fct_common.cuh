@@ -52,6 +52,7 @@ struct fct_hoststage {
 
 struct fct_comm;   // NCCL state (fct_comm.cu)
 struct fct_p2p;    // NVLink peer-memory mailboxes (fct_p2p.cu)
+struct fct_win;    // windows + flags of the wavefront kernels (fct_win.cu)
 
 // CUDA-graph WHILE loop of the low-order Jacobi solve (fct_kernels.cu), cached per operand set
 struct fct_jgraph {
@@ -112,6 +113,7 @@ struct fct_ctx {
     // Low-order Jacobi on the row templates: 0 = CSR kernels, 1 = column offsets from the templates (bit-identical to 0),
     // 2 = additionally rows pre-scaled by 1/l_ii in k_low_build (no dinv read in the sweep).  FCT_JAC_TPL selects.
     int32_t jac_mode = 0;
+    fct_win* win = nullptr;          // wavefront (multi-sweep) Jacobi / ChebSI kernels; null = one launch per sweep
     int32_t cheb_mdtab = 1;          // ChebSI takes diag(M) from the template table when the caller passes ctx->Mdiag
     // workspace
     double* Lvals = nullptr;    // low-order operator

@@ -522,6 +522,7 @@ __global__ void k_jacobi_decide(unsigned long long* __restrict__ jstate, double 
 // the same decision as the body of a CUDA-graph WHILE node: keeps looping until converged or out of sweeps
 __global__ void k_jacobi_decide_cond(unsigned long long* __restrict__ jstate, double rtol, unsigned long long max_sweeps,
                                      cudaGraphConditionalHandle handle) {
+    if (jstate[3]) { cudaGraphSetConditional(handle, 0u); return; }     // already converged (wavefront launch)
     if (jstate[4] < jstate[10] && jstate[4] < max_sweeps) {
         jstate[0] = 0ull; jstate[1] = 0ull;
         cudaGraphSetConditional(handle, 1u);
@@ -1045,8 +1046,22 @@ int fct_halo_allreduce_max2(fct_ctx* ctx, unsigned long long* two_words);
 // ChebSI with deep-halo bookkeeping.  `vb`: ring on which the right-hand side b is valid.  Iteration k runs on ring
 // min(valid(y_{k-1}) - 1, vb); when that would drop below the owned rows the two live iterates are exchanged in one
 // message (valid on ring `depth` again).  Returns in *vy the ring on which the result is valid.
+int fct_win_chebsi(fct_ctx* ctx, const double* b, double* y, int iters, double lmin, double lmax);            // fct_win.cu
+int fct_win_jacobi(fct_ctx* ctx, const double* Lv, const double* b, double* x, double* tmp, double rtol, int smax);
+int fct_win_bench_jacobi(fct_ctx* ctx, int sweeps, int reps, int warm, float* ms_per_sweep);
+
 int fct_chebsi_v(fct_ctx* ctx, const double* M, const double* Md, const double* b, double* y, int32_t iters, double lmin,
                  double lmax, int vb, int* vy) {
+    if (ctx->win && !ctx->comm && M == ctx->M && Md == ctx->Mdiag && ctx->cheb_mdtab) {
+        // single GPU, static mass matrix: every iteration in one wavefront launch (fct_win.cu)
+        fct_set_ring(ctx, 0);
+        const int rc = fct_win_chebsi(ctx, b, y, iters, lmin, lmax);
+        if (rc < 0) { fct_set_error("fct_chebsi: wavefront launch failed"); return 1; }
+        if (rc == 1) {
+            if (vy) *vy = 0;
+            return fct_launch_error(ctx, "fct_chebsi");
+        }
+    }
     // helpers.py:164-180
     const double rho = (lmax - lmin) / (lmax + lmin);
     const double dscale = (lmin + lmax) / 2;
@@ -1177,6 +1192,15 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
     const int sweeps_per_cycle = ctx->depth >= 2 ? 2 * (ctx->depth / 2) : 2;
     const int cycles = (max_sweeps + sweeps_per_cycle - 1) / sweeps_per_cycle;
     const bool p2p = ctx->comm && fct_p2p_ready(ctx);
+    if (dinv && !ctx->comm && ctx->win) {
+        // single GPU: the sweeps the previous solve needed run as one wavefront launch (fct_win.cu); the loop below then
+        // finds the converged flag set (its sweeps return at once) or finishes the solve two sweeps at a time
+        fct_set_ring(ctx, 0);
+        if (fct_win_jacobi(ctx, Lv, b, x, tmp, rtol, max_sweeps) < 0) {
+            fct_set_error("fct_jacobi_solve: wavefront launch failed");
+            return 1;
+        }
+    }
     if ((!ctx->comm || p2p) && dinv && ctx->use_graph) {
         // The cycle is the body of a CUDA-graph WHILE node whose condition the decide kernel sets on the device:
         // exactly as many sweeps as needed are launched, with no host round trip and no skipped launches (multi-GPU:
@@ -1394,6 +1418,51 @@ extern "C" int fct_bench_jacobi_sweeps(fct_ctx* ctx, const double* A, const doub
     cudaEventDestroy(e1);
     *ms_per_sweep_host = ms / reps;
     return fct_launch_error(ctx, "fct_bench_jacobi_sweeps");
+}
+
+// Test hook (tests/test_gpu_parity.py): builds the low-order system of (A, u_n, dt) and runs exactly `sweeps` Jacobi
+// sweeps from the initial guess u_n, either one launch per sweep (fused = 0) or as one wavefront launch (fused = 1);
+// copies the iterate to x_out.  The two must agree bit for bit.
+int fct_win_jacobi_fixed(fct_ctx* ctx, int sweeps);
+extern "C" int fct_debug_jacobi_fixed(fct_ctx* ctx, const double* A, const double* un, double dt, int32_t sweeps,
+                                      int32_t fused, double* x_out) {
+    FCT_CHECK(ctx && A && un && x_out && sweeps >= 2 && (sweeps & 1) == 0, "fct_debug_jacobi_fixed: bad argument");
+    float dummy = 0.f;
+    // (re)build L, b; the timing loops of fct_bench_jacobi_sweeps leave a scratch iterate behind, so restart from u_n
+    if (fct_bench_jacobi_sweeps(ctx, A, un, dt, 2, &dummy)) return 1;
+    double* x = ctx->w[4];
+    double* tmp = ctx->w[5];
+    FCT_CUDA(cudaMemcpyAsync(x, un, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (fused) {
+        const int rc = fct_win_jacobi_fixed(ctx, sweeps);
+        FCT_CHECK(rc != 0, "fct_debug_jacobi_fixed: wavefront kernels not available on this context");
+        FCT_CHECK(rc > 0, "fct_debug_jacobi_fixed: launch failed");
+    } else {
+        k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+        for (int i = 0; i < sweeps; ++i) {
+            double* xin = (i & 1) ? tmp : x;
+            double* xout = (i & 1) ? x : tmp;
+            if (ctx->jac_mode > 0 && ctx->tpl_count > 0)
+                launch_jacobi_tpl(ctx, ctx->Lvals, ctx->w[3], ctx->w[6], xin, xout, 0);
+            else
+                LAUNCH_PIPE_NST(ctx, k_jacobi_sweep, ctx->rowptr, ctx->colidx, ctx->Lvals, ctx->w[3], ctx->w[6], xin, xout,
+                                ctx->jstate, 0, ctx->row_begin, ctx->row_end, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+        }
+    }
+    FCT_CUDA(cudaMemcpyAsync(x_out, x, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+    return fct_launch_error(ctx, "fct_debug_jacobi_fixed");
+}
+
+extern "C" int fct_bench_jacobi_fused(fct_ctx* ctx, const double* A, const double* un, double dt, int32_t sweeps,
+                                      int32_t reps, float* ms_per_sweep_host) {
+    FCT_CHECK(ctx && A && un && ms_per_sweep_host && reps >= 1, "fct_bench_jacobi_fused: bad argument");
+    float dummy = 0.f;
+    if (fct_bench_jacobi_sweeps(ctx, A, un, dt, 2, &dummy)) return 1;      // builds L, b and leaves an iterate in w[4]
+    const int rc = fct_win_bench_jacobi(ctx, sweeps, reps, 1, ms_per_sweep_host);
+    FCT_CHECK(rc != 0, "fct_bench_jacobi_fused: wavefront kernels not available on this context");
+    FCT_CHECK(rc > 0, "fct_bench_jacobi_fused: launch failed");
+    return 0;
 }
 
 extern "C" int fct_step_host(fct_ctx* ctx, const double* A, double sign, const double* S, const double* rhs,

@@ -227,6 +227,15 @@ int fct_p2p_error(fct_ctx* ctx, int32_t* error_host);
  * stream (the dominant kernel of the FCT step once the mass matrix runs on row templates); bench.py's roofline */
 int fct_bench_jacobi_sweeps(fct_ctx* ctx, const double* A_dev, const double* u_n_dev, double dt, int32_t reps,
                             float* ms_per_sweep_host);
+/* the same system through the wavefront kernel (fct_win.cu): `reps` launches of exactly `sweeps` (even, <= 32) fused
+ * Jacobi sweeps; returns the CUDA-event time per sweep.  Fails if the context has no wavefront kernels (no row
+ * templates, multi-GPU, FCT_WIN=0). */
+int fct_bench_jacobi_fused(fct_ctx* ctx, const double* A_dev, const double* u_n_dev, double dt, int32_t sweeps,
+                           int32_t reps, float* ms_per_sweep_host);
+/* test hook: exactly `sweeps` (even) Jacobi sweeps on the low-order system of (A, u_n, dt) from the initial guess u_n,
+ * one launch per sweep (fused = 0) or as one wavefront launch (fused = 1); the iterate is copied to x_out_dev */
+int fct_debug_jacobi_fixed(fct_ctx* ctx, const double* A_dev, const double* u_n_dev, double dt, int32_t sweeps,
+                           int32_t fused, double* x_out_dev);
 /* number of row templates the static mass matrix compressed to (0 = CSR kernels in use) */
 int fct_template_count(fct_ctx* ctx, int32_t* count);
 /* CUDA events on the context's stream (what bench.py times kernels with) */

@@ -363,3 +363,45 @@ def test_template_jacobi_modes(monkeypatch):
     for i in range(1, ns + 1):
         assert rel_l2(res["2"][0][i], res["0"][0][i]) < 1e-13 * i
     assert abs(res["2"][1] - res["0"][1]) <= 2 * ns
+
+
+@pytest.mark.parametrize("n", [12, 100, 300])
+def test_wavefront_kernels_bit_identical(monkeypatch, n):
+    """fct_win.cu: all ChebSI iterations / a fixed number of Jacobi sweeps in ONE wavefront launch (TMA-staged windows,
+    per-item flags) must reproduce the one-launch-per-sweep kernels bit for bit; n = 300 spans 350+ row blocks, so the
+    cross-CTA dependencies are exercised.  Then the adaptive fused solve inside the FCT step against FCT_WIN=0."""
+    h = 1.0 / n
+    dt = 0.25 * h / (2 * np.sqrt(2))
+    mesh = RectMeshP1(n, 0.0, 1.0)
+    xy = mesh.dof_xy
+    rng = np.random.default_rng(5)
+    b = rng.random(mesh.nodes) - 0.5
+    u0 = np.exp(-20 * ((2 * xy[:, 0] - 1 + 2 / 3) ** 2 + 5 * (2 * xy[:, 1] - 1 + 5 / 6) ** 2)) + 0.01 * rng.random(mesh.nodes)
+    c = 1.0 + rng.random((3, mesh.nodes))
+    out = {}
+    for win in ("0", "1"):
+        monkeypatch.setenv("FCT_WIN", win)
+        ctx = RectMeshP1(n, 0.0, 1.0).context()
+        M, _, Md, _ = ctx.static()
+        y = ctx.empty(mesh.nodes)
+        ctx.chebsi(M, Md, ctx.array(b), y, 20)
+        y7 = ctx.empty(mesh.nodes)
+        ctx.chebsi(M, Md, ctx.array(b), y7, 7)
+        A = ctx.empty(mesh.nnz)
+        ctx.assemble_matrix(2, A, c0=ctx.array(c[0]), s0=1.0, s1=1.0, scale=-1.0)
+        xs = []
+        for sweeps in (2, 6, 14):
+            x = ctx.empty(mesh.nodes)
+            ctx.debug_jacobi_fixed(A, ctx.array(u0), dt, sweeps, int(win), x)
+            xs.append(x.download())
+        utr = np.zeros((3, mesh.nodes)); utr[0] = u0
+        du = ctx.array(utr.ravel())
+        sw = ctx.advdrift_state(ctx.array(c.ravel()), du, 2, dt)
+        out[win] = (y.download(), y7.download(), xs, du.download().reshape(3, -1), sw)
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.array_equal(out["0"][1], out["1"][1])
+    for a, bb in zip(out["0"][2], out["1"][2]):
+        assert np.array_equal(a, bb)
+    for i in (1, 2):
+        assert rel_l2(out["1"][3][i], out["0"][3][i]) < 1e-13 * i
+    assert out["1"][4] >= 4

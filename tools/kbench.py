@@ -43,8 +43,20 @@ def main():
         ctx.record(e1)
         t1 = ctx.elapsed_ms(e0, e1)
         best = min(best, (t20 - t1) / (5 * 19))
+    best20 = 1e9
+    for _ in range(3):
+        ctx.record(e0)
+        for _ in range(5):
+            ctx.chebsi(M, Md, b, y, 20)
+        ctx.record(e1)
+        best20 = min(best20, ctx.elapsed_ms(e0, e1) / 5)
+    try:
+        fused = min(ctx.bench_jacobi_fused(A, d_u, dt, sweeps=14, reps=5) for _ in range(3))
+    except Exception as e:  # noqa: BLE001
+        fused = str(e)[:60]
     knobs = {k: v for k, v in os.environ.items() if k.startswith("FCT_")}
-    print(json.dumps({"knobs": knobs, "jacobi_sweep_ms": jac, "cheb_iter_ms": best, "templates": ctx.template_count()}))
+    print(json.dumps({"knobs": knobs, "jacobi_sweep_ms": jac, "jacobi_fused_ms_per_sweep": fused, "cheb_iter_ms": best,
+                      "chebsi20_ms": best20, "templates": ctx.template_count()}))
 
 
 if __name__ == "__main__":
