@@ -35,13 +35,35 @@
 #define WIN_THREADS (FCT_RB + 64)    // 8 consumer warps + loader warp + signaller warp
 #define WIN_NCONS (FCT_RB / 32)
 
-struct __align__(16) WinMeta {       // per aligned block of FCT_RB rows (64 B)
+#define WIN_LT 8                     // distinct row templates a block may have on the fast path
+
+struct __align__(16) WinMeta {       // head of the per-block record (64 B)
     int lo[3];                       // first column of the below / around / above window (even)
     int len[3];                      // staged length (even, <= WIN_WCAP; 0 = not staged)
     int dep_lo, dep_hi;              // aligned blocks that hold this block's columns
     int k0, k1;                      // CSR range of the block
-    int pad[6];
+    int fast;                        // 1: <= WIN_LT templates and every column inside a staged window
+    int own_ib;                      // fast path: window index of the row's own entry = tid + own_ib
+    int pad[4];
 };
+
+// Per-block record: everything static a block of FCT_RB rows needs, contiguous, fetched by one or two bulk copies.
+//   [0,64)      WinMeta
+//   [64,320)    local template code of every row (u8)
+//   [320,576)   per local template: window index base of its 8 slots (gather index = tid + ib)
+//   [576,1152)  per local template: 8 mass-matrix values + the diagonal (ChebSI)
+//   [1152,1680) start of every row inside the staged range of matrix values, u16 (Jacobi)
+#define REC_LCODE 64
+#define REC_IB 320
+#define REC_CHEB 576
+#define REC_RS 1152
+#define REC_BYTES 1680
+// ring stage
+#define ST_CODE16 REC_BYTES                  // slow path: 16-bit global template codes
+#define ST_RP (ST_CODE16 + 512)              // slow path (Jacobi): rowptr
+#define ST_WIN (ST_RP + 1040)
+#define ST_OWN (ST_WIN + 3 * WIN_WCAP * 8)
+#define ST_X (ST_OWN + 2048)                 // ChebSI: y_{k-2} (own rows); Jacobi: matrix values
 
 enum { WIN_CHEB = 0, WIN_JAC = 1 };
 
@@ -54,7 +76,8 @@ struct WinSweeps {
     int first[WIN_SMAX];             // ChebSI: iteration k == 1 (no matrix application)
     int nsweeps;
     int lag;                         // blocks by which sweep s+1 trails sweep s
-    int dbg;                         // timing experiments only (FCT_WIN_DBG): 1 = no dependency wait
+    int dbg;                         // timing experiments only (FCT_WIN_DBG): 1 no dependency wait, 2 no proxy fence,
+                                     // 4 proxy fence .global, 8 no signaller fence, 16 consumers skip the arithmetic
 };
 
 struct WinArgs {
@@ -63,7 +86,7 @@ struct WinArgs {
     const int32_t* toff;
     const double* tval;
     const double* tdiag;
-    const WinMeta* meta;
+    const unsigned char* rec;        // per-block records (REC_BYTES each)
     const double* own;               // ChebSI: right-hand side g; Jacobi: b' (own rows)
     const double* Lv;                // Jacobi: row-scaled off-diagonals of the low-order operator
     const int32_t* rowptr;
@@ -109,69 +132,149 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
         }
     }
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-// ---- set-up: windows of every aligned row block --------------------------------------------------------------
-__global__ void __launch_bounds__(FCT_RB)
-k_win_meta(const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ code, const int32_t* __restrict__ toff, int n,
-           WinMeta* __restrict__ meta) {
-    __shared__ int smn[3][FCT_RB / 32], smx[3][FCT_RB / 32];
-    const int j = blockIdx.x;
-    const int r = j * FCT_RB + (int)threadIdx.x;
-    int mn0 = INT_MAX, mn1 = INT_MAX, mn2 = INT_MAX, mx0 = INT_MIN, mx1 = INT_MIN, mx2 = INT_MIN;
-    if (r < n) {
-        const int t = code[r];
-        const int len = rowptr[r + 1] - rowptr[r];
-        for (int q = 0; q < FCT_TPL_W; ++q) {
-            if (q >= len) break;
-            const int off = toff[FCT_TPL_W * t + q];
-            const int c = r + off;
-            if (off < -1) { mn0 = min(mn0, c); mx0 = max(mx0, c); }
-            else if (off > 1) { mn2 = min(mn2, c); mx2 = max(mx2, c); }
-            else { mn1 = min(mn1, c); mx1 = max(mx1, c); }
+// Non-blocking variant for the lane-parallel roles: try_wait may suspend the whole warp, which would stall the other
+// lanes' (independent) waits; test_wait only polls.
+__device__ __forceinline__ void mbar_poll_bounded(uint64_t* bar, uint32_t parity, unsigned long long* err) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
+    for (unsigned it = 0; !done; ++it) {
+        asm volatile(
+            "{\n"
+            " .reg .pred p;\n"
+            " mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && (it & 4095u) == 4095u) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 6000000000ll) { *err = 2ull; return; }
         }
     }
-    mn0 = __reduce_min_sync(0xffffffffu, mn0); mx0 = __reduce_max_sync(0xffffffffu, mx0);
-    mn1 = __reduce_min_sync(0xffffffffu, mn1); mx1 = __reduce_max_sync(0xffffffffu, mx1);
-    mn2 = __reduce_min_sync(0xffffffffu, mn2); mx2 = __reduce_max_sync(0xffffffffu, mx2);
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) {
-        smn[0][w] = mn0; smn[1][w] = mn1; smn[2][w] = mn2;
-        smx[0][w] = mx0; smx[1][w] = mx1; smx[2][w] = mx2;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---- set-up: the record of every aligned row block ---------------------------------------------------------------
+__device__ __forceinline__ int win_class(int off) { return off < -1 ? 0 : (off > 1 ? 2 : 1); }
+
+__global__ void __launch_bounds__(FCT_RB)
+k_win_records(const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ code, const int32_t* __restrict__ toff,
+              const double* __restrict__ tval, const double* __restrict__ tdiag, int n, unsigned char* __restrict__ recs) {
+    __shared__ int smn[3][FCT_RB / 32], smx[3][FCT_RB / 32];
+    __shared__ int s_code[FCT_RB], s_list[WIN_LT], s_nlt, s_bad, s_lo[3], s_len[3];
+    const int j = blockIdx.x, tid = threadIdx.x;
+    const int r0 = j * FCT_RB;
+    const int nr = min(FCT_RB, n - r0);
+    const int r = r0 + tid;
+    unsigned char* rec = recs + (size_t)j * REC_BYTES;
+    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    int t = -1, len = 0;
+    if (tid < nr) {
+        t = code[r];
+        len = rowptr[r + 1] - rowptr[r];
+        for (int q = 0; q < FCT_TPL_W && q < len; ++q) {
+            const int off = toff[FCT_TPL_W * t + q];
+            const int c = r + off, w = win_class(off);
+            for (int k = 0; k < 3; ++k)
+                if (k == w) { mn[k] = min(mn[k], c); mx[k] = max(mx[k], c); }
+        }
+        // the row's own entry (padded template slots point at it) is always looked up in the middle window
+        mn[1] = min(mn[1], r); mx[1] = max(mx[1], r);
+    }
+    s_code[tid] = t;
+    for (int k = 0; k < 3; ++k) {
+        const int a = __reduce_min_sync(0xffffffffu, mn[k]), b = __reduce_max_sync(0xffffffffu, mx[k]);
+        if ((tid & 31) == 0) { smn[k][tid >> 5] = a; smx[k][tid >> 5] = b; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         WinMeta m;
         int allmn = INT_MAX, allmx = INT_MIN;
         for (int q = 0; q < 3; ++q) {
             int a = INT_MAX, b = INT_MIN;
             for (int i = 0; i < FCT_RB / 32; ++i) { a = min(a, smn[q][i]); b = max(b, smx[q][i]); }
-            int lo = 0, len = 0;
+            int lo = 0, ln = 0;
             if (a <= b) {
                 allmn = min(allmn, a); allmx = max(allmx, b);
                 lo = a & ~1;
-                len = ((b + 1 - lo) + 1) & ~1;
-                if (lo + len > n) len = (n - lo) & ~1;          // never read past the vector; the odd tail is an L2 load
-                if (len > WIN_WCAP || len < 0) len = 0;         // does not fit: this window is not staged
+                ln = ((b + 1 - lo) + 1) & ~1;
+                if (lo + ln > n) ln = (n - lo) & ~1;            // never read past the vector; the odd tail is an L2 load
+                if (ln > WIN_WCAP || ln < 0) ln = 0;            // does not fit: this window is not staged
             }
-            m.lo[q] = lo; m.len[q] = len;
+            m.lo[q] = lo; m.len[q] = ln;
+            s_lo[q] = lo; s_len[q] = ln;
         }
-        const int r0 = j * FCT_RB;
         m.dep_lo = allmn <= allmx ? allmn / FCT_RB : j;
         m.dep_hi = allmn <= allmx ? allmx / FCT_RB : j;
         m.k0 = rowptr[r0];
-        m.k1 = rowptr[min(n, r0 + FCT_RB)];
-        for (int q = 0; q < 6; ++q) m.pad[q] = 0;
-        meta[j] = m;
+        m.k1 = rowptr[r0 + nr];
+        // distinct templates of the block (rows of one mesh line share one): at most WIN_LT on the fast path
+        int nlt = 0, bad = 0, prev = -2;
+        for (int i = 0; i < nr; ++i) {
+            const int c = s_code[i];
+            if (c == prev) continue;
+            prev = c;
+            int f = -1;
+            for (int k = 0; k < nlt; ++k) if (s_list[k] == c) f = k;
+            if (f < 0) { if (nlt < WIN_LT) s_list[nlt++] = c; else bad = 1; }
+        }
+        if (m.k1 - (m.k0 & ~1) > 65000) bad = 1;                // row starts are stored as u16
+        s_nlt = nlt; s_bad = bad;
+        m.fast = 0;
+        m.own_ib = r0 - m.lo[1] + WIN_WCAP;
+        for (int q = 0; q < 4; ++q) m.pad[q] = 0;
+        *reinterpret_cast<WinMeta*>(rec) = m;
     }
+    __syncthreads();
+    // coverage: every column of every row inside its staged window?
+    int inside = 1;
+    if (tid < nr) {
+        for (int q = 0; q < FCT_TPL_W && q < len; ++q) {
+            const int off = toff[FCT_TPL_W * t + q];
+            const int w = win_class(off);
+            const int idx = r + off - s_lo[w];
+            if (idx < 0 || idx >= s_len[w]) inside = 0;
+        }
+        const int io = r - s_lo[1];
+        if (io < 0 || io >= s_len[1]) inside = 0;
+    }
+    const int all_inside = __syncthreads_and(inside);
+    const int fast = all_inside && !s_bad;
+    const int nlt = s_nlt;
+    int lc = 0;
+    if (fast && tid < nr)
+        for (int k = 0; k < nlt; ++k) if (s_list[k] == t) lc = k;
+    rec[REC_LCODE + tid] = (unsigned char)lc;
+    if (tid < WIN_LT * 8) {
+        const int lt = tid >> 3, q = tid & 7;
+        int ib = 0;
+        if (fast && lt < nlt) {
+            const int off = toff[FCT_TPL_W * s_list[lt] + q];
+            const int w = win_class(off);
+            ib = r0 + off - s_lo[w] + w * WIN_WCAP;
+        }
+        reinterpret_cast<int*>(rec + REC_IB)[tid] = ib;
+    }
+    if (tid < WIN_LT * 9) {
+        const int lt = tid / 9, q = tid - lt * 9;
+        double v = 0.0;
+        if (fast && lt < nlt) v = q < 8 ? tval[FCT_TPL_W * s_list[lt] + q] : tdiag[s_list[lt]];
+        reinterpret_cast<double*>(rec + REC_CHEB)[tid] = v;
+    }
+    {
+        const int ka = rowptr[r0] & ~1;
+        uint16_t* rs = reinterpret_cast<uint16_t*>(rec + REC_RS);
+        rs[tid] = (uint16_t)((tid <= nr && !s_bad) ? rowptr[r0 + tid] - ka : 0);
+        if (tid < 8) rs[FCT_RB + tid] = (uint16_t)((tid == 0 && nr == FCT_RB && !s_bad) ? rowptr[r0 + FCT_RB] - ka : 0);
+    }
+    if (tid == 0) reinterpret_cast<WinMeta*>(rec)->fast = fast;
 }
 
 // ---- the wavefront kernel ------------------------------------------------------------------------------------------
-#define WIN_STAGE_FIXED (64 + 512 + 3 * WIN_WCAP * 8 + 2048)    // meta + codes + windows + own-row vector
-#define CHEB_STAGE_BYTES (WIN_STAGE_FIXED + 2048)               // + y_{k-2} (own rows)
-__host__ __device__ __forceinline__ size_t jac_stage_bytes(int cap) {
-    return (size_t)WIN_STAGE_FIXED + 1040 + (size_t)cap * 8;   // + rowptr + matrix values
-}
+#define CHEB_STAGE_BYTES (ST_X + 2048)
+__host__ __device__ __forceinline__ size_t jac_stage_bytes(int cap) { return (size_t)ST_X + (size_t)cap * 8; }
 
 // gathered iterate: window hit -> shared memory, else L2
 __device__ __forceinline__ double win_get(const double* __restrict__ sw, const double* __restrict__ xin, int c, int off,
@@ -224,8 +327,12 @@ k_win(const __grid_constant__ WinArgs a) {
     int S = P.nsweeps;
     if (KIND == WIN_JAC) {
         // the sweep count of this launch is decided on the device (k_jacobi_win_decide adapts it from solve to solve)
-        S = a.fixed_sweeps > 0 ? a.fixed_sweeps : (int)a.jstate[12];
-        if (S < 2) S = 14;
+        if (a.fixed_sweeps > 0) {
+            S = a.fixed_sweeps;
+        } else {
+            S = (int)a.jstate[12];
+            if (S < 2) S = 14;
+        }
         if (S > P.nsweeps) S = P.nsweeps;
     }
     const int blk_lo = a.blk_lo, blk_hi = a.blk_hi, n = a.n, nb_all = a.nb_all;
@@ -244,12 +351,12 @@ k_win(const __grid_constant__ WinArgs a) {
         if (lane >= NST) return;
         for (int q = 0; q < lane && valid; ++q) valid = it.next();
         for (int k = 0; valid; ++k) {
-            mbar_wait_bounded(&empty[lane], (uint32_t)(k & 1), ERRP);      // all consumer warps have stored their rows
-            if (S > 1) {
-                fence_acq_rel_gpu();
+            mbar_poll_bounded(&empty[lane], (uint32_t)(k & 1), ERRP);      // all consumer warps have stored their rows
+            mbar_arrive(&freeb[lane]);                                      // the stage can be refilled at once ...
+            if (S > 1) {                                                    // ... while the rows are published
+                if (!(P.dbg & 8)) fence_acq_rel_gpu();
                 red_relaxed_gpu_add(a.flags + (size_t)it.s * a.nchunks + ((it.j >> 5) - chunk_lo), 1);
             }
-            mbar_arrive(&freeb[lane]);
             for (int q = 0; q < NST && valid; ++q) valid = it.next();
         }
         return;
@@ -281,20 +388,22 @@ k_win(const __grid_constant__ WinArgs a) {
             if (d.nc > 2) ok = ok && d.v2 >= chunk_need(d.c0 + 2);
             return ok;
         };
+        auto meta_of = [&](int j) { return *reinterpret_cast<const WinMeta*>(a.rec + (size_t)j * REC_BYTES); };
         WinMeta m;
         Dep dep{nullptr, 0, 0, 0, 0, 0};
-        if (valid) { m = a.meta[it.j]; dep = dep_issue(it.s, m); }
+        if (valid) { m = meta_of(it.j); dep = dep_issue(it.s, m); }
         for (int k = 0; valid; ++k) {
             WinIter nx = it;
             bool valid2 = true;
             for (int q = 0; q < NST && valid2; ++q) valid2 = nx.next();
             WinMeta m2;
-            if (valid2) m2 = a.meta[nx.j];              // in flight while this item is issued
+            if (valid2) m2 = meta_of(nx.j);             // in flight while this item is issued
             const int stage = lane;
             const int s = it.s, j = it.j;
             unsigned char* sb = win_smem + (size_t)stage * sbytes;
-            double* sw = reinterpret_cast<double*>(sb + 64 + 512);
-            double* sown = sw + 3 * WIN_WCAP;
+            const unsigned char* grec = a.rec + (size_t)j * REC_BYTES;
+            double* sw = reinterpret_cast<double*>(sb + ST_WIN);
+            double* sown = reinterpret_cast<double*>(sb + ST_OWN);
             const int r0 = j * FCT_RB;
             const int nr = min(FCT_RB, n - r0);
             const int vcnt = nr & ~1;                   // own-row vector elements the copy engine brings
@@ -304,42 +413,65 @@ k_win(const __grid_constant__ WinArgs a) {
             const int rpcnt = min(260, (nr + 1 + 3) & ~3);     // rowptr entries staged (allocation has 8 entries of slack)
             const int ka = m.k0 & ~1;
             const int lcnt = ((m.k1 - ka) + 1) & ~1;          // Lvals carries 8 entries of slack
-            mbar_wait_bounded(&freeb[stage], (uint32_t)((k & 1) ^ 1), ERRP);
-            uint32_t bytes = 64u + cbytes + (uint32_t)vcnt * 8u;
-            if (!first) bytes += (uint32_t)(m.len[0] + m.len[1] + m.len[2]) * 8u;
-            if (has_old) bytes += (uint32_t)vcnt * 8u;
-            if (KIND == WIN_JAC) bytes += (uint32_t)rpcnt * 4u + (uint32_t)lcnt * 8u;
-            mbar_expect_tx(&full[stage], bytes);
-            tma_load_1d(sb, a.meta + j, 64u, &full[stage]);
-            tma_load_1d(sb + 64, a.code + r0, cbytes, &full[stage]);
-            if (vcnt) tma_load_1d(sown, a.own + r0, (uint32_t)vcnt * 8u, &full[stage]);
-            if (KIND == WIN_JAC) {
-                int32_t* srp = reinterpret_cast<int32_t*>(sb + WIN_STAGE_FIXED);
-                double* sL = reinterpret_cast<double*>(sb + WIN_STAGE_FIXED + 1040);
-                tma_load_1d(srp, a.rowptr + r0, (uint32_t)rpcnt * 4u, &full[stage]);
-                if (lcnt) tma_load_1d(sL, a.Lv + ka, (uint32_t)lcnt * 8u, &full[stage]);
-            }
-            if (!first) {
-                if (s > 0 && !(P.dbg & 1)) {
-                    if (!dep_ok(dep)) {
-                        // not there yet (or an unstructured dependency range): poll, bounded
-                        const long long t0 = clock64();
-                        for (int c = dep.c0; c < dep.c0 + dep.nc; ++c) {
-                            while (ld_relaxed_gpu(dep.f + c) < chunk_need(c)) {
-                                if (*reinterpret_cast<volatile unsigned long long*>(ERRP)) break;
-                                if (clock64() - t0 > 4000000000ll) { *ERRP = 1ull; break; }   // ~2 s: report, do not hang
-                                __nanosleep(100);
-                            }
+            const bool slow = !m.fast;
+            // dependencies first (while the stage is still being consumed), copies after: a fence issued behind this lane's
+            // own bulk copies would wait for them
+            if (!first && s > 0 && !(P.dbg & 1)) {
+                if (!dep_ok(dep)) {
+                    // not there yet (or an unstructured dependency range): poll, bounded
+                    const long long t0 = clock64();
+                    for (int c = dep.c0; c < dep.c0 + dep.nc; ++c) {
+                        while (ld_relaxed_gpu(dep.f + c) < chunk_need(c)) {
+                            if (*reinterpret_cast<volatile unsigned long long*>(ERRP)) break;
+                            if (clock64() - t0 > 4000000000ll) { *ERRP = 1ull; break; }   // ~2 s: report, do not hang
+                            __nanosleep(100);
                         }
                     }
-                    fence_acq_rel_gpu();
                 }
-                fence_proxy_async_all();
+                fence_acq_rel_gpu();
+                if (P.dbg & 4) asm volatile("fence.proxy.async.global;" ::: "memory");
+                else if (!(P.dbg & 2)) fence_proxy_async_all();
+            }
+            mbar_poll_bounded(&freeb[stage], (uint32_t)((k & 1) ^ 1), ERRP);
+            uint32_t bytes = (KIND == WIN_CHEB ? (uint32_t)REC_RS : (uint32_t)REC_CHEB + (uint32_t)(REC_BYTES - REC_RS)) +
+                             (uint32_t)vcnt * 8u;
+            if (slow) bytes += cbytes + (KIND == WIN_JAC ? (uint32_t)rpcnt * 4u : 0u);
+            if (!first) bytes += (uint32_t)(m.len[0] + m.len[1] + m.len[2]) * 8u;
+            if (has_old) bytes += (uint32_t)vcnt * 8u;
+            if (KIND == WIN_JAC) bytes += (uint32_t)lcnt * 8u;
+            if (P.dbg & 32) bytes += 48u;
+            mbar_expect_tx(&full[stage], bytes);
+            if (KIND == WIN_CHEB) {
+                tma_load_1d(sb, grec, (uint32_t)REC_RS, &full[stage]);                     // meta, codes, index bases, values
+            } else {
+                tma_load_1d(sb, grec, (uint32_t)REC_CHEB, &full[stage]);                   // meta, codes, index bases
+                tma_load_1d(sb + REC_RS, grec + REC_RS, (uint32_t)(REC_BYTES - REC_RS), &full[stage]);   // row starts
+                if (lcnt) tma_load_1d(sb + ST_X, a.Lv + ka, (uint32_t)lcnt * 8u, &full[stage]);
+            }
+            if (slow) {
+                tma_load_1d(sb + ST_CODE16, a.code + r0, cbytes, &full[stage]);
+                if (KIND == WIN_JAC) tma_load_1d(sb + ST_RP, a.rowptr + r0, (uint32_t)rpcnt * 4u, &full[stage]);
+            }
+            if (vcnt) tma_load_1d(sown, a.own + r0, (uint32_t)vcnt * 8u, &full[stage]);
+            if (!first) {
                 const double* xin = P.in[s];
 #pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    if (m.len[q]) tma_load_1d(sw + q * WIN_WCAP, xin + m.lo[q], (uint32_t)m.len[q] * 8u, &full[stage]);
-                if (has_old && vcnt) tma_load_1d(sown + FCT_RB, P.old[s] + r0, (uint32_t)vcnt * 8u, &full[stage]);
+                for (int q = 0; q < 3; ++q) {
+                    if (!m.len[q]) continue;
+                    if (P.dbg & 64) {        // experiment: same bytes in twice as many copies
+                        const int h = (m.len[q] / 2) & ~1;
+                        if (h) tma_load_1d(sw + q * WIN_WCAP, xin + m.lo[q], (uint32_t)h * 8u, &full[stage]);
+                        tma_load_1d(sw + q * WIN_WCAP + h, xin + m.lo[q] + h, (uint32_t)(m.len[q] - h) * 8u, &full[stage]);
+                    } else {
+                        tma_load_1d(sw + q * WIN_WCAP, xin + m.lo[q], (uint32_t)m.len[q] * 8u, &full[stage]);
+                    }
+                }
+                if (has_old && vcnt) tma_load_1d(sb + ST_X, P.old[s] + r0, (uint32_t)vcnt * 8u, &full[stage]);
+            }
+            if (P.dbg & 32) {        // experiment: three extra 16-byte copies (op count up, bytes unchanged)
+                tma_load_1d(sb + ST_CODE16, a.code + r0, 16u, &full[stage]);
+                tma_load_1d(sb + ST_CODE16 + 16, a.code + r0 + 64, 16u, &full[stage]);
+                tma_load_1d(sb + ST_CODE16 + 32, a.code + r0 + 128, 16u, &full[stage]);
             }
             it = nx; valid = valid2;
             if (valid2) { m = m2; dep = dep_issue(it.s, m); }
@@ -355,73 +487,100 @@ k_win(const __grid_constant__ WinArgs a) {
         const uint32_t par = (uint32_t)((cnt / NST) & 1);
         ++cnt;
         const int s = it.s, j = it.j;
-        unsigned char* sb = win_smem + (size_t)stage * sbytes;
+        const unsigned char* sb = win_smem + (size_t)stage * sbytes;
         const WinMeta* sm = reinterpret_cast<const WinMeta*>(sb);
-        const uint16_t* scode = reinterpret_cast<const uint16_t*>(sb + 64);
-        const double* sw = reinterpret_cast<const double*>(sb + 64 + 512);
-        const double* sown = sw + 3 * WIN_WCAP;
+        const double* sw = reinterpret_cast<const double*>(sb + ST_WIN);
+        const double* sown = reinterpret_cast<const double*>(sb + ST_OWN);
         const int r0 = j * FCT_RB;
         const int nr = min(FCT_RB, n - r0);
         const int vcnt = nr & ~1;
         const int r = r0 + tid;
         mbar_wait_bounded(&full[stage], par, ERRP);
-        if (tid < nr) {
+        if (tid < nr && !(P.dbg & 16)) {
             const double own = tid < vcnt ? sown[tid] : __ldcg(a.own + r);
-            const int tc = scode[tid];
-            const double* xin = P.in[s];
-            const int lo0 = sm->lo[0], lo1 = sm->lo[1], lo2 = sm->lo[2];
-            const int n0 = sm->len[0], n1 = sm->len[1], n2 = sm->len[2];
             double xnew;
-            if (KIND == WIN_CHEB) {
-                const double md = __ldg(a.tdiag + tc);
-                if (P.first[s]) {
-                    const double z = own / (a.dscale * md);
-                    xnew = P.omega[s] * z;
+            if (KIND == WIN_CHEB && P.first[s]) {
+                // iteration k == 1: y1 = omega1 * g / (dscale * Md)
+                const double md = sm->fast ? reinterpret_cast<const double*>(sb + REC_CHEB)[9 * sb[REC_LCODE + tid] + 8]
+                                           : __ldg(a.tdiag + reinterpret_cast<const uint16_t*>(sb + ST_CODE16)[tid]);
+                const double z = own / (a.dscale * md);
+                xnew = P.omega[s] * z;
+            } else if (sm->fast) {
+                // every operand in shared memory: gather index = tid + base of (local template, slot)
+                const int lc = sb[REC_LCODE + tid];
+                const int4 i0 = *reinterpret_cast<const int4*>(sb + REC_IB + 32 * lc);
+                const int4 i1 = *reinterpret_cast<const int4*>(sb + REC_IB + 32 * lc + 16);
+                const double* swt = sw + tid;
+                const double x0 = swt[i0.x], x1 = swt[i0.y], x2 = swt[i0.z], x3 = swt[i0.w];
+                const double x4 = swt[i1.x], x5 = swt[i1.y], x6 = swt[i1.z], x7 = swt[i1.w];
+                if (KIND == WIN_CHEB) {
+                    const double* vv = reinterpret_cast<const double*>(sb + REC_CHEB) + 9 * lc;
+                    const double ym = swt[sm->own_ib];
+                    const double yo = P.old[s] ? (tid < vcnt ? reinterpret_cast<const double*>(sb + ST_X)[tid] : __ldcg(P.old[s] + r))
+                                               : 0.0;
+                    double acc = 0.0;
+                    acc += vv[0] * x0; acc += vv[1] * x1; acc += vv[2] * x2; acc += vv[3] * x3;
+                    acc += vv[4] * x4; acc += vv[5] * x5; acc += vv[6] * x6; acc += vv[7] * x7;
+                    const double z = (own - acc) / (a.dscale * vv[8]);
+                    xnew = P.omega[s] * (z + ym - yo) + yo;
                 } else {
-                    const int4 o0 = __ldg(reinterpret_cast<const int4*>(a.toff + FCT_TPL_W * tc));
-                    const int4 o1 = __ldg(reinterpret_cast<const int4*>(a.toff + FCT_TPL_W * tc) + 1);
+                    const uint16_t* rs = reinterpret_cast<const uint16_t*>(sb + REC_RS);
+                    const int k0r = rs[tid];
+                    const int len = (int)rs[tid + 1] - k0r;
+                    const double* sLr = reinterpret_cast<const double*>(sb + ST_X) + k0r;
+                    const double xv[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+                    double acc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc += ((q < len) ? sLr[q] : 0.0) * xv[q];
+                    xnew = own - acc;
+                    if ((s == s_last || s == s_early) && r >= a.own_rb && r < a.own_re) {
+                        const double d = fabs(xnew - swt[sm->own_ib]), ax = fabs(xnew);
+                        if (s == s_last) { dl = fmax(dl, d); xl = fmax(xl, ax); }
+                        else { de = fmax(de, d); xe = fmax(xe, ax); }
+                    }
+                }
+            } else {
+                // generic path: global template tables, columns outside the staged windows come from L2
+                const int tc = reinterpret_cast<const uint16_t*>(sb + ST_CODE16)[tid];
+                const double* xin = P.in[s];
+                const int lo0 = sm->lo[0], lo1 = sm->lo[1], lo2 = sm->lo[2];
+                const int n0 = sm->len[0], n1 = sm->len[1], n2 = sm->len[2];
+                const int4 o0 = __ldg(reinterpret_cast<const int4*>(a.toff + FCT_TPL_W * tc));
+                const int4 o1 = __ldg(reinterpret_cast<const int4*>(a.toff + FCT_TPL_W * tc) + 1);
+                const int off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+                double xv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) xv[q] = win_get(sw, xin, r + off[q], off[q], lo0, lo1, lo2, n0, n1, n2);
+                const double xo = win_get(sw, xin, r, 0, lo0, lo1, lo2, n0, n1, n2);
+                if (KIND == WIN_CHEB) {
+                    const double md = __ldg(a.tdiag + tc);
                     const double2 v0 = __ldg(reinterpret_cast<const double2*>(a.tval + FCT_TPL_W * tc));
                     const double2 v1 = __ldg(reinterpret_cast<const double2*>(a.tval + FCT_TPL_W * tc) + 1);
                     const double2 v2 = __ldg(reinterpret_cast<const double2*>(a.tval + FCT_TPL_W * tc) + 2);
                     const double2 v3 = __ldg(reinterpret_cast<const double2*>(a.tval + FCT_TPL_W * tc) + 3);
-#define WG(o) win_get(sw, xin, r + (o), (o), lo0, lo1, lo2, n0, n1, n2)
-                    const double x0 = WG(o0.x), x1 = WG(o0.y), x2 = WG(o0.z), x3 = WG(o0.w);
-                    const double x4 = WG(o1.x), x5 = WG(o1.y), x6 = WG(o1.z), x7 = WG(o1.w);
-                    const double ym = WG(0);
-#undef WG
                     double yo = 0.0;
-                    if (P.old[s]) yo = tid < vcnt ? sown[FCT_RB + tid] : __ldcg(P.old[s] + r);
+                    if (P.old[s]) yo = tid < vcnt ? reinterpret_cast<const double*>(sb + ST_X)[tid] : __ldcg(P.old[s] + r);
                     double acc = 0.0;
-                    acc += v0.x * x0; acc += v0.y * x1; acc += v1.x * x2; acc += v1.y * x3;
-                    acc += v2.x * x4; acc += v2.y * x5; acc += v3.x * x6; acc += v3.y * x7;
+                    acc += v0.x * xv[0]; acc += v0.y * xv[1]; acc += v1.x * xv[2]; acc += v1.y * xv[3];
+                    acc += v2.x * xv[4]; acc += v2.y * xv[5]; acc += v3.x * xv[6]; acc += v3.y * xv[7];
                     const double z = (own - acc) / (a.dscale * md);
-                    xnew = P.omega[s] * (z + ym - yo) + yo;
-                }
-            } else {
-                const int32_t* srp = reinterpret_cast<const int32_t*>(sb + WIN_STAGE_FIXED);
-                const double* sL = reinterpret_cast<const double*>(sb + WIN_STAGE_FIXED + 1040);
-                const int rpcnt = min(260, (nr + 1 + 3) & ~3);
-                const int ka = sm->k0 & ~1;
-                const int k0r = srp[tid];
-                const int len = ((tid + 1 < rpcnt) ? srp[tid + 1] : a.rowptr[r + 1]) - k0r;
-                const int4 o0 = __ldg(reinterpret_cast<const int4*>(a.toff + FCT_TPL_W * tc));
-                const int4 o1 = __ldg(reinterpret_cast<const int4*>(a.toff + FCT_TPL_W * tc) + 1);
-                const int off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-                const double* sLr = sL + (k0r - ka);
-                double xv[8], v[8];
+                    xnew = P.omega[s] * (z + xo - yo) + yo;
+                } else {
+                    const int32_t* srp = reinterpret_cast<const int32_t*>(sb + ST_RP);
+                    const int rpcnt = min(260, (nr + 1 + 3) & ~3);
+                    const int ka = sm->k0 & ~1;
+                    const int k0r = srp[tid];
+                    const int len = ((tid + 1 < rpcnt) ? srp[tid + 1] : a.rowptr[r + 1]) - k0r;
+                    const double* sLr = reinterpret_cast<const double*>(sb + ST_X) + (k0r - ka);
+                    double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) xv[q] = win_get(sw, xin, r + off[q], off[q], lo0, lo1, lo2, n0, n1, n2);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = (q < len) ? sLr[q] : 0.0;
-                double acc = 0.0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) acc += v[q] * xv[q];
-                xnew = own - acc;
-                if ((s == s_last || s == s_early) && r >= a.own_rb && r < a.own_re) {
-                    const double xo = win_get(sw, xin, r, 0, lo0, lo1, lo2, n0, n1, n2);
-                    const double d = fabs(xnew - xo), ax = fabs(xnew);
-                    if (s == s_last) { dl = fmax(dl, d); xl = fmax(xl, ax); }
-                    else { de = fmax(de, d); xe = fmax(xe, ax); }
+                    for (int q = 0; q < 8; ++q) acc += ((q < len) ? sLr[q] : 0.0) * xv[q];
+                    xnew = own - acc;
+                    if ((s == s_last || s == s_early) && r >= a.own_rb && r < a.own_re) {
+                        const double d = fabs(xnew - xo), ax = fabs(xnew);
+                        if (s == s_last) { dl = fmax(dl, d); xl = fmax(xl, ax); }
+                        else { de = fmax(de, d); xe = fmax(xe, ax); }
+                    }
                 }
             }
             if (r >= P.rb[s] && r < P.re[s]) P.out[s][r] = xnew;
@@ -472,19 +631,20 @@ __global__ void k_jacobi_win_decide(unsigned long long* __restrict__ jstate, dou
 // host side
 // ================================================================================================================
 struct fct_win {
-    WinMeta* meta = nullptr;
+    unsigned char* rec = nullptr;
     int* flags = nullptr;
     int nb_all = 0;
     int grid_cheb = 0, grid_jac = 0;
     int nst_cheb = 3, nst_jac = 2;
     int lag_cheb = 0, lag_jac = 0;
     int max_dep = 0;
+    int nfast = 0;                   // blocks on the all-shared-memory path
     bool cheb_on = true, jac_on = true;
 };
 
 void fct_win_free(fct_ctx* ctx) {
     if (!ctx->win) return;
-    cudaFree(ctx->win->meta);
+    cudaFree(ctx->win->rec);
     cudaFree(ctx->win->flags);
     delete ctx->win;
     ctx->win = nullptr;
@@ -513,19 +673,22 @@ int fct_win_build(fct_ctx* ctx) {
     bool ok = false;
     do {
         if ((long long)W->nb_all * WIN_SMAX * 4 > 2000000000ll) break;       // tickets are 32-bit
-        if (cudaMalloc((void**)&W->meta, sizeof(WinMeta) * (size_t)W->nb_all) != cudaSuccess) break;
+        if (cudaMalloc((void**)&W->rec, (size_t)REC_BYTES * (size_t)W->nb_all + 64) != cudaSuccess) break;
         if (cudaMalloc((void**)&W->flags, sizeof(int) * ((size_t)W->nb_all / 32 + 4) * WIN_SMAX) != cudaSuccess) break;
-        k_win_meta<<<W->nb_all, FCT_RB, 0, ctx->stream>>>(ctx->rowptr, ctx->tpl_code, ctx->tpl_off, n, W->meta);
+        k_win_records<<<W->nb_all, FCT_RB, 0, ctx->stream>>>(ctx->rowptr, ctx->tpl_code, ctx->tpl_off, ctx->tpl_val, ctx->tpl_diag, n,
+                                                              W->rec);
         ctx->launches++;
         // largest dependency reach (in blocks) decides the minimum lag
         WinMeta* h = (WinMeta*)malloc(sizeof(WinMeta) * (size_t)W->nb_all);
         if (!h) break;
-        if (cudaMemcpyAsync(h, W->meta, sizeof(WinMeta) * (size_t)W->nb_all, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        if (cudaMemcpy2DAsync(h, sizeof(WinMeta), W->rec, REC_BYTES, sizeof(WinMeta), (size_t)W->nb_all, cudaMemcpyDeviceToHost,
+                              ctx->stream) != cudaSuccess ||
             cudaStreamSynchronize(ctx->stream) != cudaSuccess) { free(h); break; }
         int reach = 0;
         for (int j = 0; j < W->nb_all; ++j) {
             reach = reach > h[j].dep_hi - j ? reach : h[j].dep_hi - j;
             reach = reach > j - h[j].dep_lo ? reach : j - h[j].dep_lo;
+            W->nfast += h[j].fast ? 1 : 0;
         }
         free(h);
         W->max_dep = reach;
@@ -565,7 +728,7 @@ int fct_win_build(fct_ctx* ctx) {
         ok = true;
     } while (0);
     cudaGetLastError();
-    if (!ok) { cudaFree(W->meta); cudaFree(W->flags); delete W; return 0; }
+    if (!ok) { cudaFree(W->rec); cudaFree(W->flags); delete W; return 0; }
     ctx->win = W;
     return 0;
 }
@@ -581,7 +744,7 @@ static int win_lag(const fct_win* W, int forced, int grid, int nst, int S) {
 
 static void win_common_args(fct_ctx* ctx, WinArgs& a) {
     fct_win* W = ctx->win;
-    a.code = ctx->tpl_code; a.toff = ctx->tpl_off; a.tval = ctx->tpl_val; a.tdiag = ctx->tpl_diag; a.meta = W->meta;
+    a.code = ctx->tpl_code; a.toff = ctx->tpl_off; a.tval = ctx->tpl_val; a.tdiag = ctx->tpl_diag; a.rec = W->rec;
     a.rowptr = ctx->rowptr; a.jstate = ctx->jstate; a.flags = W->flags;
     a.blk_lo = ctx->cur_rb / FCT_RB; a.blk_hi = (ctx->cur_re + FCT_RB - 1) / FCT_RB;
     a.n = ctx->n; a.cap = ctx->cap; a.nb_all = W->nb_all; a.own_rb = ctx->row_begin; a.own_re = ctx->row_end;
@@ -680,6 +843,16 @@ int fct_win_bench_jacobi(fct_ctx* ctx, int sweeps, int reps, int warm, float* ms
     for (int pass = warm ? 0 : 1; pass < 2; ++pass) {
         if (pass == 1) cudaEventRecord(e0, ctx->stream);
         for (int i = 0; i < reps; ++i) {
+            if (env_int("FCT_WIN_SINGLE", 0)) {
+                // experiment: the windowed kernel as a one-sweep-per-launch kernel (no dependencies, no flags)
+                WinArgs b = a;
+                b.fixed_sweeps = 1; b.P.nsweeps = 1;
+                for (int q = 0; q < sweeps; ++q) {
+                    b.P.in[0] = a.P.in[q]; b.P.out[0] = a.P.out[q];
+                    win_kernel(WIN_JAC, W->nst_jac)<<<W->grid_jac, WIN_THREADS, sm, ctx->stream>>>(b);
+                }
+                continue;
+            }
             cudaMemsetAsync(W->flags, 0, sizeof(int) * (size_t)a.nchunks * sweeps, ctx->stream);
             win_kernel(WIN_JAC, W->nst_jac)<<<W->grid_jac, WIN_THREADS, sm, ctx->stream>>>(a);
         }
