@@ -113,10 +113,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores (bounded sample)
 # ------------------------------------------------------------------------------------------------------
-def cpu_port_steps_per_s(cells_full, sample_cells, nsteps):
-    """Times the oracle's FCT state step (numpy/scipy, 1 core, Jacobi twin of the GPU solver -- a direct solve
-    is impractical beyond ~1M DoF) on a `sample_cells`^2 mesh and scales linearly in DoF to the
-    full mesh (every pass of the Jacobi-based step is O(nnz))."""
+def _cpu_worker(args):
+    """one host core: `nsteps` FCT state steps of the oracle port on a sample mesh; returns the step-loop seconds"""
+    sample_cells, nsteps = args
     from oracle import pdeco_numpy as drv
     orc = drv.AdvectionDriftPDECO(sample_cells, 0.0, 1.0, solver="jacobi")
     h = 1.0 / sample_cells
@@ -127,31 +126,66 @@ def cpu_port_steps_per_s(cells_full, sample_cells, nsteps):
     c += 0.5 * np.sin(3 * xy[:, 0]) * np.cos(2 * xy[:, 1])
     t0 = time.perf_counter()
     orc.state(c, u0, nsteps, dt)
-    el = time.perf_counter() - t0
-    sps_sample = nsteps / el
+    return time.perf_counter() - t0
+
+
+def cpu_port_steps_per_s(cells_full, sample_cells, nsteps, cores=None):
+    """CPU arm.  The reference's FCT step is single-threaded Python/scipy (and its `FCT_alg_ref` cannot run beyond
+    ~1e5 DoF because of an O(n^2) todense(), a direct solve is impractical beyond ~1M DoF: BASELINE.md), so the
+    baseline is the oracle's vectorised port with the Jacobi twin of the GPU solver, run as `cores` independent
+    replicas (one per host core, i.e. perfect-scaling credit for the host) on a `sample_cells`^2 mesh and scaled
+    linearly in DoF to the full mesh (every pass of the Jacobi-based step is O(nnz)).
+    Returns (steps/s at full size using all cores, steps/s of the sample on all cores, wall seconds, cores)."""
+    import multiprocessing as mp
+    if cores is None:
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            cores = os.cpu_count() or 1
+        cores = max(1, min(cores, 32))
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    t0 = time.perf_counter()
+    if cores == 1:
+        times = [_cpu_worker((sample_cells, nsteps))]
+    else:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            times = pool.map(_cpu_worker, [(sample_cells, nsteps)] * cores)
+    wall = time.perf_counter() - t0
+    sps_sample = cores * nsteps / max(times)          # replicas run concurrently: aggregate over the slowest one
     scale = (sample_cells + 1) ** 2 / float((cells_full + 1) ** 2)
-    return sps_sample * scale, sps_sample, el
+    return sps_sample * scale, sps_sample, wall, cores
+
+
+CPU_SAMPLE_CELLS, CPU_SAMPLE_STEPS = 1024, 3
+
+
+def _cpu_sample_text(cells_full, sample, nsteps, cores, sps_sample, wall):
+    return (f"oracle port (numpy/scipy CSR, Jacobi low-order solve): {cores} independent replicas (one per host core) of "
+            f"{nsteps} FCT state steps on a {sample}^2-cell mesh = {sps_sample:.3f} steps/s aggregate, {wall:.1f} s wall "
+            f"incl. set-up; scaled by the DoF ratio to {cells_full}^2")
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(args.cells, 512)
-    sps, sps_sample, el = 0.0, 0.0, 0.0
-    times = []
+    sample = min(args.cells, CPU_SAMPLE_CELLS)
+    res = []
     for i in range(args.warmup + args.steps):
-        v, vs, e = cpu_port_steps_per_s(args.cells, sample, 2)
+        # every step is one bounded sample; warm-up samples are cheaper (1 step) -- they only page the code in
+        r = cpu_port_steps_per_s(args.cells, sample, CPU_SAMPLE_STEPS if i >= args.warmup else 1)
         if i >= args.warmup:
-            times.append((v, vs, e))
-    sps = float(np.mean([t[0] for t in times]))
-    sample_txt = (f"oracle port (numpy/scipy CSR, Jacobi low-order solve), {2} FCT state steps on a {sample}^2-cell mesh "
-                  f"per bench step, {np.mean([t[1] for t in times]):.3f} steps/s there, scaled by DoF ratio to {args.cells}^2")
+            res.append(r)
+    sps = float(np.mean([r[0] for r in res]))
+    cores = res[0][3]
+    sample_txt = _cpu_sample_text(args.cells, sample, CPU_SAMPLE_STEPS, cores, float(np.mean([r[1] for r in res])),
+                                  float(np.mean([r[2] for r in res])))
     line = {"impl": "reference", "metric": "FCT steps/sec", "value": sps, "unit": "steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([t[2] for t in times])),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([r[2] for r in res])),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic {args.cells}^2-cell unit-square advection FCT PDECO (BASELINE config 5)"},
-            "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample_txt},
+            "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample_txt},
             "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -318,11 +352,10 @@ def run_gpu_arm(args):
         "clocks": clocks,
     }
     if not args.no_cpu:
-        sps, sps_sample, el = cpu_port_steps_per_s(n_cells, min(n_cells, 512), 2)
-        line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": 1, "kind": "port",
-                                "sample": f"oracle port (numpy/scipy, Jacobi low-order solve): 2 FCT state steps on a "
-                                          f"{min(n_cells, 512)}^2-cell mesh = {sps_sample:.3f} steps/s in {el:.1f} s, "
-                                          f"scaled by DoF ratio to {n_cells}^2"}
+        sample = min(n_cells, CPU_SAMPLE_CELLS)
+        sps, sps_sample, wall, cores = cpu_port_steps_per_s(n_cells, sample, CPU_SAMPLE_STEPS)
+        line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+                                "sample": _cpu_sample_text(n_cells, sample, CPU_SAMPLE_STEPS, cores, sps_sample, wall)}
     print(json.dumps(line))
 
 

@@ -89,10 +89,12 @@ SIGNATURES = {
     "fct_p2p_connect": [_p, _p],
     "fct_p2p_error": [_p, _pi32],
     "fct_launch_count": [_p, _pi64],
+    "fct_profiler_range": [_i32],
     "fct_bench_jacobi_sweeps": [_p, _p, _p, _f64, _i32, C.POINTER(C.c_float)],
     "fct_debug_jacobi_fixed": [_p, _p, _p, _f64, _i32, _i32, _p],
     "fct_bench_jacobi_fused": [_p, _p, _p, _f64, _i32, _i32, C.POINTER(C.c_float)],
     "fct_template_count": [_p, _pi32],
+    "fct_geom_template_count": [_p, _pi32],
     "fct_event_create": [_p, C.POINTER(_p)],
     "fct_event_record": [_p, _p],
     "fct_event_elapsed_ms": [_p, _p, _p, C.POINTER(C.c_float)],

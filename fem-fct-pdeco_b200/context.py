@@ -280,6 +280,11 @@ class FctContext:
         check(lib.fct_template_count(self.handle, C.byref(c)))
         return c.value
 
+    def geom_template_count(self):
+        c = C.c_int32()
+        check(lib.fct_geom_template_count(self.handle, C.byref(c)))
+        return c.value
+
     def bench_jacobi_sweeps(self, A, u_n, dt, reps=20):
         ms = C.c_float()
         check(lib.fct_bench_jacobi_sweeps(self.handle, A.ptr, u_n.ptr, float(dt), int(reps), C.byref(ms)))

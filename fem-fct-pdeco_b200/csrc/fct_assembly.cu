@@ -10,6 +10,9 @@
 #include "fct_common.cuh"
 #include "../../include/fctpdeco.h"
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <stdlib.h>
 #include <vector>
 
 extern __shared__ __align__(16) unsigned char fct_smem[];
@@ -334,10 +337,220 @@ k_assemble_vector(const int32_t* __restrict__ v2c_ptr, const int32_t* __restrict
 }
 
 // ======================================================================================================
+// Geometry templates.  On meshes with repeated element shapes the per-row assembly input -- which cells touch the
+// vertex, where their other two vertices sit relative to it, the cells' gradients and areas, and which row slot each
+// local entry goes to -- is the same for most rows.  At fct_ctx_set_mesh the rows are hashed on the device, distinct
+// signatures (<= 65535, <= 6 incident cells, rows of <= 8 entries) become templates and every row gets a 16-bit code.
+// The templated kernels then read 2 B per row instead of the incidence lists, the coordinates of three vertices per
+// cell and the column indices (1.8 GB per assembly at 4097^2); the cell geometry in the table is what cell_geom()
+// computes, the element arithmetic and the summation order are unchanged, so results are bit-identical to the
+// generic kernels.  A mesh that does not compress keeps the generic kernels.
+#define GT_MAXC 6
+struct __align__(16) GeomCell {
+    int off1, off2;        // the cell's other two vertices, relative to the row's vertex
+    int slots;             // row slots of (d0, d1, d2): bits 0-7, 8-15, 16-23
+    int pad;
+    double gx[3], gy[3], detJ;
+};
+struct __align__(16) GeomTpl {
+    int ncell, len, pad0, pad1;
+    GeomCell c[GT_MAXC];
+};
+
+__device__ __forceinline__ unsigned long long gmix(unsigned long long h, unsigned long long v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 33;
+    return h;
+}
+
+// the signature of row r, as a template (valid == false: more cells / entries than a template holds)
+__device__ __forceinline__ bool geom_signature(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                               const int32_t* __restrict__ v2c_ptr, const int32_t* __restrict__ v2c_idx,
+                                               const double* __restrict__ xy, int r, GeomTpl& T) {
+    const int ks = rowptr[r], len = rowptr[r + 1] - ks;
+    const int cs = v2c_ptr[r], nc = v2c_ptr[r + 1] - cs;
+    T.ncell = nc; T.len = len; T.pad0 = 0; T.pad1 = 0;
+    if (nc > GT_MAXC || len > 8) return false;
+    for (int q = 0; q < GT_MAXC; ++q) {
+        GeomCell& c = T.c[q];
+        c.off1 = 0; c.off2 = 0; c.slots = 0; c.pad = 0;
+        for (int k = 0; k < 3; ++k) { c.gx[k] = 0.0; c.gy[k] = 0.0; }
+        c.detJ = 0.0;
+        if (q >= nc) continue;
+        const int2 nb = __ldg(reinterpret_cast<const int2*>(v2c_idx) + cs + q);
+        const CellGeom g = cell_geom(xy, r, nb.x, nb.y);
+        int sl[3] = {255, 255, 255};
+        for (int j = 0; j < len; ++j) {
+            const int col = colidx[ks + j];
+            for (int k = 0; k < 3; ++k) if (col == g.d[k]) sl[k] = j;
+        }
+        c.off1 = nb.x - r; c.off2 = nb.y - r;
+        c.slots = sl[0] | (sl[1] << 8) | (sl[2] << 16);
+        for (int k = 0; k < 3; ++k) { c.gx[k] = g.gx[k]; c.gy[k] = g.gy[k]; }
+        c.detJ = g.detJ;
+    }
+    return true;
+}
+
+__device__ __forceinline__ unsigned long long geom_hash_of(const GeomTpl& T) {
+    unsigned long long h = gmix(0xABCDEFull, ((unsigned long long)(unsigned)T.ncell << 32) | (unsigned)T.len);
+    for (int q = 0; q < GT_MAXC; ++q) {
+        const GeomCell& c = T.c[q];
+        h = gmix(h, ((unsigned long long)(unsigned)c.off1 << 32) | (unsigned)c.off2);
+        h = gmix(h, (unsigned long long)(unsigned)c.slots);
+        for (int k = 0; k < 3; ++k) {
+            h = gmix(h, (unsigned long long)__double_as_longlong(c.gx[k]));
+            h = gmix(h, (unsigned long long)__double_as_longlong(c.gy[k]));
+        }
+        h = gmix(h, (unsigned long long)__double_as_longlong(c.detJ));
+    }
+    return h;
+}
+
+__global__ void k_geom_hash(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                            const int32_t* __restrict__ v2c_ptr, const int32_t* __restrict__ v2c_idx,
+                            const double* __restrict__ xy, int n, unsigned long long* __restrict__ hash, int* __restrict__ bad) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    GeomTpl T;
+    if (!geom_signature(rowptr, colidx, v2c_ptr, v2c_idx, xy, r, T)) { atomicAdd(bad, 1); hash[r] = 0ull; return; }
+    hash[r] = geom_hash_of(T);
+}
+
+__global__ void k_geom_codes(const unsigned long long* __restrict__ hash, const unsigned long long* __restrict__ uniq, int T,
+                             int n, uint16_t* __restrict__ code, int* __restrict__ rep) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const unsigned long long h = hash[r];
+    int lo = 0, hi = T - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (uniq[mid] < h) lo = mid + 1; else hi = mid;
+    }
+    code[r] = (uint16_t)lo;
+    atomicMin(rep + lo, r);
+}
+
+__global__ void k_geom_fill(const int* __restrict__ rep, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                            const int32_t* __restrict__ v2c_ptr, const int32_t* __restrict__ v2c_idx,
+                            const double* __restrict__ xy, int T, GeomTpl* __restrict__ tab) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    GeomTpl G;
+    geom_signature(rowptr, colidx, v2c_ptr, v2c_idx, xy, rep[t], G);
+    tab[t] = G;
+}
+
+// exact check: every row must reproduce its template bit for bit
+__global__ void k_geom_verify(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                              const int32_t* __restrict__ v2c_ptr, const int32_t* __restrict__ v2c_idx,
+                              const double* __restrict__ xy, int n, const uint16_t* __restrict__ code,
+                              const GeomTpl* __restrict__ tab, int* __restrict__ bad) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    GeomTpl G;
+    bool ok = geom_signature(rowptr, colidx, v2c_ptr, v2c_idx, xy, r, G);
+    const GeomTpl& T = tab[code[r]];
+    ok = ok && G.ncell == T.ncell && G.len == T.len;
+    for (int q = 0; q < GT_MAXC && ok; ++q) {
+        const GeomCell &a = G.c[q], &b = T.c[q];
+        ok = a.off1 == b.off1 && a.off2 == b.off2 && a.slots == b.slots &&
+             __double_as_longlong(a.detJ) == __double_as_longlong(b.detJ);
+        for (int k = 0; k < 3 && ok; ++k)
+            ok = __double_as_longlong(a.gx[k]) == __double_as_longlong(b.gx[k]) &&
+                 __double_as_longlong(a.gy[k]) == __double_as_longlong(b.gy[k]);
+    }
+    if (!ok) atomicAdd(bad, 1);
+}
+
+__device__ __forceinline__ CellGeom geom_from_tpl(const GeomCell* __restrict__ c, int r) {
+    CellGeom g;
+    const int4 h = __ldg(reinterpret_cast<const int4*>(c));
+    g.d[0] = r; g.d[1] = r + h.x; g.d[2] = r + h.y;
+    const double* gd = reinterpret_cast<const double*>(c) + 2;
+    const double2 a = __ldg(reinterpret_cast<const double2*>(gd));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(gd) + 1);
+    const double2 cc = __ldg(reinterpret_cast<const double2*>(gd) + 2);
+    g.gx[0] = a.x; g.gx[1] = a.y; g.gx[2] = b.x;
+    g.gy[0] = b.y; g.gy[1] = cc.x; g.gy[2] = cc.y;
+    g.detJ = __ldg(gd + 6);
+    g.area = 0.5 * g.detJ;
+    return g;
+}
+
+// Matrix assembly on geometry templates: thread per row, accumulators in registers, rows leave through shared memory
+// as coalesced stores.
+template <int KIND>
+__global__ void __launch_bounds__(FCT_RB)
+k_assemble_matrix_tpl(const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ gcode, const GeomTpl* __restrict__ gtab,
+                      FormArgs fa, double scale, int accumulate, double* __restrict__ out, int row_begin, int row_end,
+                      int64_t nnz) {
+    double* sV = reinterpret_cast<double*>(fct_smem);
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+        const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
+        if ((int)threadIdx.x < b.nr) {
+            const int r = b.r0 + threadIdx.x;
+            const int ks = rowptr[r];
+            const int len = rowptr[r + 1] - ks;
+            const GeomTpl* T = gtab + gcode[r];
+            const int nc = __ldg(&T->ncell);
+            double acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+            for (int q = 0; q < nc; ++q) {
+                const CellGeom g = geom_from_tpl(&T->c[q], r);
+                const int sl = __ldg(&T->c[q].slots);
+                const int s0 = sl & 255, s1 = (sl >> 8) & 255, s2 = (sl >> 16) & 255;
+                double e[3];
+                element_row<KIND>(g, 0, fa, e);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const double add = (j == s0) ? e[0] : ((j == s1) ? e[1] : ((j == s2) ? e[2] : 0.0));
+                    acc[j] += add;
+                }
+            }
+            double* sr = sV + (ks - b.ka);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < len) sr[j] = accumulate ? (out[(int64_t)ks + j] + scale * acc[j]) : (scale * acc[j]);
+        }
+        __syncthreads();
+        unstage_f64(out, sV, b);
+        __syncthreads();
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(FCT_RB)
+k_assemble_vector_tpl(const uint16_t* __restrict__ gcode, const GeomTpl* __restrict__ gtab, FormArgs fa, double scale,
+                      int accumulate, double* __restrict__ out, int row_begin, int row_end) {
+    const int stride = (int)gridDim.x * FCT_RB;
+    for (int r = row_begin + (int)blockIdx.x * FCT_RB + (int)threadIdx.x; r < row_end; r += stride) {
+        const GeomTpl* T = gtab + gcode[r];
+        const int nc = __ldg(&T->ncell);
+        double acc = 0.0;
+        for (int q = 0; q < nc; ++q) {
+            const CellGeom g = geom_from_tpl(&T->c[q], r);
+            acc += element_load<KIND>(g, 0, fa);
+        }
+        out[r] = accumulate ? (out[r] + scale * acc) : (scale * acc);
+    }
+}
+
+// ======================================================================================================
 template <int KIND>
 static int launch_matrix(fct_ctx* ctx, const FormArgs& fa, double scale, int accumulate, double* out) {
     // all local rows, halo rows included: their entries (j,i) towards owned rows i are complete because every
     // cell containing an owned vertex is local, and those are the only halo-row values the FCT step reads (a_ji).
+    if (ctx->gt_count > 0) {
+        const int nbr = fct_grid(ctx, (ctx->n + FCT_RB - 1) / FCT_RB);
+        k_assemble_matrix_tpl<KIND><<<nbr, FCT_RB, (size_t)ctx->cap * 8, ctx->stream>>>(
+            ctx->rowptr, ctx->gt_code, reinterpret_cast<const GeomTpl*>(ctx->gt_tab), fa, scale, accumulate, out, 0, ctx->n,
+            ctx->nnz);
+        ctx->launches++;
+        return fct_launch_error(ctx, "fct_assemble_matrix");
+    }
     if (ctx->max_row <= 8) {
         const int nbr = fct_grid(ctx, (ctx->n + FCT_RB - 1) / FCT_RB);
         k_assemble_matrix_r8<KIND><<<nbr, FCT_RB, 0, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->v2c_ptr, ctx->v2c_idx,
@@ -358,6 +571,7 @@ static int launch_matrix(fct_ctx* ctx, const FormArgs& fa, double scale, int acc
 template <int KIND>
 static int configure_matrix(int bytes) {
     FCT_CUDA(cudaFuncSetAttribute(k_assemble_matrix<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    FCT_CUDA(cudaFuncSetAttribute(k_assemble_matrix_tpl<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     return 0;
 }
 
@@ -380,6 +594,66 @@ int fct_assembly_configure(fct_ctx* ctx) {
     rc |= configure_matrix<FCT_FORM_DRIFT_MASS>(bytes);
     rc |= configure_matrix<FCT_FORM_DRIFT_CONV>(bytes);
     return rc;
+}
+
+void fct_geom_templates_free(fct_ctx* ctx) {
+    cudaFree(ctx->gt_code); cudaFree(ctx->gt_tab);
+    ctx->gt_code = nullptr; ctx->gt_tab = nullptr; ctx->gt_count = 0;
+}
+
+// (Re)build the geometry templates of the context's mesh.  Never fails the caller: on any problem (too many
+// templates, a vertex with more than GT_MAXC cells, a hash collision caught by the exact verification pass,
+// FCT_NO_GEOM_TPL=1) the generic assembly kernels stay in use.
+static int fct_geom_templates_build(fct_ctx* ctx) {
+    fct_geom_templates_free(ctx);
+    const char* e = getenv("FCT_NO_GEOM_TPL");
+    if (e && atoi(e) == 1) return 0;
+    if (ctx->max_row > 8) return 0;
+    const int n = ctx->n;
+    unsigned long long *hash = nullptr, *sorted = nullptr, *uniq = nullptr;
+    int *dT = nullptr, *rep = nullptr, *bad = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0, tb2 = 0;
+    int T = 0, hbad = 0;
+    bool ok = false;
+    cudaStream_t st = ctx->stream;
+    do {
+        if (cudaMalloc((void**)&hash, 8 * (size_t)n) != cudaSuccess) break;
+        if (cudaMalloc((void**)&sorted, 8 * (size_t)n) != cudaSuccess) break;
+        if (cudaMalloc((void**)&uniq, 8 * (size_t)n) != cudaSuccess) break;
+        if (cudaMalloc((void**)&dT, sizeof(int) * 2) != cudaSuccess) break;
+        if (cudaMalloc((void**)&bad, sizeof(int)) != cudaSuccess) break;
+        cudaMemsetAsync(bad, 0, sizeof(int), st);
+        k_geom_hash<<<(n + 127) / 128, 128, 0, st>>>(ctx->rowptr, ctx->colidx, ctx->v2c_ptr, ctx->v2c_idx, ctx->xy, n, hash, bad);
+        cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, hash, sorted, n, 0, 64, st);
+        cub::DeviceSelect::Unique(nullptr, tb2, sorted, uniq, dT, n, st);
+        if (tb2 > tmp_bytes) tmp_bytes = tb2;
+        if (cudaMalloc(&tmp, tmp_bytes) != cudaSuccess) break;
+        cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, hash, sorted, n, 0, 64, st);
+        cub::DeviceSelect::Unique(tmp, tmp_bytes, sorted, uniq, dT, n, st);
+        if (cudaMemcpyAsync(&T, dT, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        if (hbad != 0 || T < 1 || T > 65535) break;
+        if (cudaMalloc((void**)&rep, sizeof(int) * (size_t)T) != cudaSuccess) break;
+        if (cudaMalloc((void**)&ctx->gt_code, sizeof(uint16_t) * ((size_t)n + 8)) != cudaSuccess) break;
+        if (cudaMalloc((void**)&ctx->gt_tab, sizeof(GeomTpl) * (size_t)T) != cudaSuccess) break;
+        cudaMemsetAsync(rep, 0x7f, sizeof(int) * (size_t)T, st);
+        k_geom_codes<<<(n + 255) / 256, 256, 0, st>>>(hash, uniq, T, n, ctx->gt_code, rep);
+        k_geom_fill<<<(T + 127) / 128, 128, 0, st>>>(rep, ctx->rowptr, ctx->colidx, ctx->v2c_ptr, ctx->v2c_idx, ctx->xy, T,
+                                                     reinterpret_cast<GeomTpl*>(ctx->gt_tab));
+        k_geom_verify<<<(n + 127) / 128, 128, 0, st>>>(ctx->rowptr, ctx->colidx, ctx->v2c_ptr, ctx->v2c_idx, ctx->xy, n,
+                                                       ctx->gt_code, reinterpret_cast<const GeomTpl*>(ctx->gt_tab), bad);
+        ctx->launches += 4;
+        if (cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        ok = (hbad == 0);
+    } while (0);
+    cudaFree(hash); cudaFree(sorted); cudaFree(uniq); cudaFree(dT); cudaFree(rep); cudaFree(bad); cudaFree(tmp);
+    cudaGetLastError();
+    if (ok) ctx->gt_count = T;
+    else fct_geom_templates_free(ctx);
+    return 0;
 }
 
 extern "C" int fct_ctx_set_mesh(fct_ctx* ctx, int64_t ncells, const int32_t* cell_dofs, const double* dof_xy) {
@@ -416,7 +690,7 @@ extern "C" int fct_ctx_set_mesh(fct_ctx* ctx, int64_t ncells, const int32_t* cel
     FCT_CUDA(cudaMemcpy(ctx->v2c_ptr, ptr.data(), sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
     FCT_CUDA(cudaMemcpy(ctx->v2c_idx, idx.data(), sizeof(int32_t) * 6 * (size_t)ncells, cudaMemcpyHostToDevice));
     ctx->ncells = ncells;
-    return 0;
+    return fct_geom_templates_build(ctx);
 }
 
 extern "C" int fct_assemble_matrix(fct_ctx* ctx, int32_t kind, const double* c0, const double* c1, const double* c2,
@@ -478,6 +752,12 @@ template <int KIND>
 static int launch_vector(fct_ctx* ctx, const FormArgs& fa, double scale, int accumulate, double* out) {
     const int nb = fct_nblocks(ctx);
     if (nb <= 0) return 0;
+    if (ctx->gt_count > 0) {
+        k_assemble_vector_tpl<KIND><<<fct_grid(ctx, nb), FCT_RB, 0, ctx->stream>>>(
+            ctx->gt_code, reinterpret_cast<const GeomTpl*>(ctx->gt_tab), fa, scale, accumulate, out, ctx->cur_rb, ctx->cur_re);
+        ctx->launches++;
+        return fct_launch_error(ctx, "fct_assemble_vector");
+    }
     k_assemble_vector<KIND><<<nb, FCT_RB, 0, ctx->stream>>>(ctx->v2c_ptr, ctx->v2c_idx, ctx->cells, ctx->xy, fa, scale,
                                                             accumulate, out, ctx->cur_rb, ctx->cur_re);
     ctx->launches++;

@@ -98,6 +98,10 @@ struct fct_ctx {
     double* xy = nullptr;           // [n*2]
     int32_t* v2c_ptr = nullptr;     // vertex -> incident cells (CSR), built on set_mesh
     int32_t* v2c_idx = nullptr;     // [2 * incidences]: the two other vertices of each incident cell, cyclic order
+    // geometry templates of the mesh (fct_assembly.cu): 16-bit code per row + table; gt_count == 0: generic kernels
+    uint16_t* gt_code = nullptr;
+    void* gt_tab = nullptr;
+    int32_t gt_count = 0;
     // static matrices
     double* M = nullptr;
     double* ML = nullptr;

@@ -1,5 +1,6 @@
 // Context, memory and error plumbing of libfctpdeco; closed-form structured-mesh bookkeeping.
 #include "fct_common.cuh"
+#include <cuda_profiler_api.h>
 #include "../../include/fctpdeco.h"
 
 #include <stdarg.h>
@@ -118,6 +119,7 @@ void fct_comm_destroy(fct_ctx* ctx);
 void fct_p2p_destroy(fct_ctx* ctx);
 void fct_templates_free(fct_ctx* ctx);
 int fct_templates_build(fct_ctx* ctx);
+void fct_geom_templates_free(fct_ctx* ctx);
 
 template <typename T>
 static int dev_alloc(T** p, size_t count) {
@@ -219,6 +221,7 @@ extern "C" int fct_ctx_destroy(fct_ctx* c) {
         cudaStreamDestroy(c->hs.d2h_stream);
     }
     fct_templates_free(c);
+    fct_geom_templates_free(c);
     fct_p2p_destroy(c);
     fct_comm_destroy(c);
     cudaFree(c->rowptr); cudaFree(c->colidx); cudaFree(c->tpos);
@@ -319,6 +322,18 @@ extern "C" int fct_d2h(fct_ctx* ctx, void* dst, const void* src, int64_t bytes) 
 extern "C" int fct_launch_count(fct_ctx* ctx, int64_t* count) {
     FCT_CHECK(ctx && count, "fct_launch_count: null argument");
     *count = ctx->launches;
+    return 0;
+}
+
+extern "C" int fct_geom_template_count(fct_ctx* ctx, int32_t* count) {
+    FCT_CHECK(ctx && count, "fct_geom_template_count: null argument");
+    *count = ctx->gt_count;
+    return 0;
+}
+
+// cudaProfilerStart/Stop of the runtime this library is linked against (ncu --profile-from-start off)
+extern "C" int fct_profiler_range(int32_t start) {
+    if (start) cudaProfilerStart(); else cudaProfilerStop();
     return 0;
 }
 

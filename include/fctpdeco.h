@@ -238,11 +238,16 @@ int fct_debug_jacobi_fixed(fct_ctx* ctx, const double* A_dev, const double* u_n_
                            int32_t fused, double* x_out_dev);
 /* number of row templates the static mass matrix compressed to (0 = CSR kernels in use) */
 int fct_template_count(fct_ctx* ctx, int32_t* count);
+/* number of geometry templates the mesh compressed to (0 = generic assembly kernels in use) */
+int fct_geom_template_count(fct_ctx* ctx, int32_t* count);
 /* CUDA events on the context's stream (what bench.py times kernels with) */
 int fct_event_create(fct_ctx* ctx, void** event_out);
 int fct_event_record(fct_ctx* ctx, void* event);
 int fct_event_elapsed_ms(fct_ctx* ctx, void* start, void* stop, float* ms_host);   /* synchronises on stop */
 int fct_event_destroy(fct_ctx* ctx, void* event);
+/* cudaProfilerStart (start != 0) / cudaProfilerStop of the CUDA runtime inside this library: delimits the region an
+ * `ncu --profile-from-start off` capture records (tools/kprof_step.py) */
+int fct_profiler_range(int32_t start);
 /* number of kernels this library has launched on this context since creation */
 int fct_launch_count(fct_ctx* ctx, int64_t* count);
 

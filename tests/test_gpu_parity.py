@@ -405,3 +405,45 @@ def test_wavefront_kernels_bit_identical(monkeypatch, n):
     for i in (1, 2):
         assert rel_l2(out["1"][3][i], out["0"][3][i]) < 1e-13 * i
     assert out["1"][4] >= 4
+
+
+def test_geometry_template_assembly_bit_identical(monkeypatch):
+    """Assembly on geometry templates (16-bit code per row + table of cell gradients/areas/slots) against the generic
+    row-gather kernels (FCT_NO_GEOM_TPL=1): identical arithmetic and summation order, so every form must agree bit for
+    bit.  n = 64 on [0,1]^2 (dyadic coordinates: the mesh compresses); the general criss-cross mesh of
+    test_gpu_general_mesh.py covers the path where every row is its own template."""
+    n = 64
+    L = _lib
+    rng = np.random.default_rng(9)
+    mesh = RectMeshP1(n, 0.0, 1.0)
+    f = [1.0 + rng.random(mesh.nodes) for _ in range(4)]
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("FCT_NO_GEOM_TPL", flag)
+        ctx = RectMeshP1(n, 0.0, 1.0).context()
+        assert (ctx.geom_template_count() > 0) == (flag == "0")
+        if flag == "0":
+            assert ctx.geom_template_count() < mesh.nodes // 4          # it really compresses
+        d = [ctx.array(x) for x in f]
+        out, vec = ctx.empty(ctx.nnz), ctx.empty(ctx.n)
+        r = []
+        for kind, kw in ((L.FORM_MASS, {}), (L.FORM_STIFFNESS, dict(scale=0.3)), (L.FORM_DRIFT, dict(c0=d[0], s0=1.0, s1=0.5)),
+                         (L.FORM_DRIFT_MASS, dict(c0=d[0], s0=1.0, s1=1.0)), (L.FORM_DRIFT_CONV, dict(c0=d[0], s0=1.0, s1=1.0)),
+                         (L.FORM_WIND_P1, dict(c0=d[0], c1=d[1])), (L.FORM_WIND_P1_T, dict(c0=d[0], c1=d[1])),
+                         (L.FORM_WMASS2, dict(c0=d[0], c1=d[1])), (L.FORM_CHTX_EXP, dict(c0=d[0], c1=d[1], s0=0.5)),
+                         (L.FORM_CHTX_ADJ, dict(c0=d[0], c1=d[1], s0=0.5))):
+            ctx.assemble_matrix(kind, out, **kw)
+            r.append(out.download())
+        ctx.assemble_matrix(L.FORM_MASS, out)
+        ctx.assemble_matrix(L.FORM_STIFFNESS, out, scale=2.0, accumulate=True)
+        r.append(out.download())
+        for kind, kw in ((L.LOAD_P1_2, dict(c0=d[0], c1=d[1])), (L.LOAD_CONST, dict(s0=3.0)),
+                         (L.LOAD_DRIFT_GRAD, dict(c0=d[0], c1=d[1], s0=1.0, s1=1.0)),
+                         (L.LOAD_CHTX_ADJ, dict(c0=d[0], c1=d[1], s0=0.5, s1=0.25))):
+            ctx.assemble_vector(kind, vec, **kw)
+            r.append(vec.download())
+        M, ML, Md, K = ctx.static()
+        r += [M.download(), K.download(), ML.download()]
+        res[flag] = r
+    for a, b in zip(res["1"], res["0"]):
+        assert np.array_equal(a, b)
