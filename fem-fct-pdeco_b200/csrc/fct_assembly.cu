@@ -40,6 +40,7 @@ struct CellGeom {
     int d[3];          // DoFs
     double gx[3], gy[3];
     double detJ, area;
+    double m12;        // area / 12 (mass-matrix scale); comes out of the geometry-template table without the division
 };
 
 // Geometry of a cell seen from its vertex r.  The vertex->cell incidence stores, per (vertex, incident cell), the cell's
@@ -58,6 +59,7 @@ __device__ __forceinline__ CellGeom cell_geom(const double* __restrict__ xy, int
     g.gx[0] = -(g.gx[1] + g.gx[2]); g.gy[0] = -(g.gy[1] + g.gy[2]);
     g.detJ = fabs(det);
     g.area = 0.5 * g.detJ;
+    g.m12 = g.area / 12.0;
     return g;
 }
 
@@ -73,7 +75,7 @@ struct FormArgs {
 template <int KIND>
 __device__ __forceinline__ void element_row(const CellGeom& g, int a, const FormArgs& fa, double e[3]) {
     if (KIND == FCT_FORM_MASS) {
-        const double m = g.area / 12.0;
+        const double m = g.m12;
 #pragma unroll
         for (int b = 0; b < 3; ++b) e[b] = (b == a) ? 2.0 * m : m;
     } else if (KIND == FCT_FORM_STIFFNESS) {
@@ -83,12 +85,12 @@ __device__ __forceinline__ void element_row(const CellGeom& g, int a, const Form
         const double c0 = fa.f0[g.d[0]], c1 = fa.f0[g.d[1]], c2 = fa.f0[g.d[2]];
         const double gcx = c0 * g.gx[0] + c1 * g.gx[1] + c2 * g.gx[2];
         const double gcy = c0 * g.gy[0] + c1 * g.gy[1] + c2 * g.gy[2];
-        const double sm = (fa.s0 * gcx + fa.s1 * gcy) * (g.area / 12.0);
+        const double sm = (fa.s0 * gcx + fa.s1 * gcy) * (g.m12);
 #pragma unroll
         for (int b = 0; b < 3; ++b) e[b] = sm * ((b == a) ? 2.0 : 1.0);
     } else if (KIND == FCT_FORM_DRIFT_CONV) {
         const double cc[3] = {fa.f0[g.d[0]], fa.f0[g.d[1]], fa.f0[g.d[2]]};
-        const double m = g.area / 12.0;
+        const double m = g.m12;
         const double bg = fa.s0 * g.gx[a] + fa.s1 * g.gy[a];
         const double csum = (cc[0] + cc[1]) + cc[2];
 #pragma unroll
@@ -99,7 +101,7 @@ __device__ __forceinline__ void element_row(const CellGeom& g, int a, const Form
         const double gcx = c0 * g.gx[0] + c1 * g.gx[1] + c2 * g.gx[2];
         const double gcy = c0 * g.gy[0] + c1 * g.gy[1] + c2 * g.gy[2];
         const double s = fa.s0 * gcx + fa.s1 * gcy;           // b . grad c
-        const double m = g.area / 12.0;
+        const double m = g.m12;
         const double bg = fa.s0 * g.gx[a] + fa.s1 * g.gy[a];  // b . grad phi_a
         const double csum = (c0 + c1) + c2;
 #pragma unroll
@@ -112,7 +114,7 @@ __device__ __forceinline__ void element_row(const CellGeom& g, int a, const Form
         const double wx[3] = {fa.f0[g.d[0]], fa.f0[g.d[1]], fa.f0[g.d[2]]};
         const double wy[3] = {fa.f1[g.d[0]], fa.f1[g.d[1]], fa.f1[g.d[2]]};
         const double sx = (wx[0] + wx[1]) + wx[2], sy = (wy[0] + wy[1]) + wy[2];
-        const double m = g.area / 12.0;
+        const double m = g.m12;
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
             if (KIND == FCT_FORM_WIND_P1) e[b] = g.gx[a] * (m * (sx + wx[b])) + g.gy[a] * (m * (sy + wy[b]));
@@ -290,7 +292,7 @@ __device__ __forceinline__ double element_load(const CellGeom& g, int a, const F
         const double guy = u0 * g.gy[0] + u1 * g.gy[1] + u2 * g.gy[2];
         const double s = fa.s0 * gux + fa.s1 * guy;
         const double p[3] = {fa.f0[g.d[0]], fa.f0[g.d[1]], fa.f0[g.d[2]]};
-        return (s * (g.area / 12.0)) * (((p[0] + p[1]) + p[2]) + p[a]);
+        return (s * (g.m12)) * (((p[0] + p[1]) + p[2]) + p[a]);
     } else if (KIND == FCT_LOAD_CHTX_ADJ) {
         const double p0 = fa.f0[g.d[0]], p1 = fa.f0[g.d[1]], p2 = fa.f0[g.d[2]];
         const double gpx = p0 * g.gx[0] + p1 * g.gx[1] + p2 * g.gx[2];
@@ -350,7 +352,7 @@ struct __align__(16) GeomCell {
     int off1, off2;        // the cell's other two vertices, relative to the row's vertex
     int slots;             // row slots of (d0, d1, d2): bits 0-7, 8-15, 16-23
     int pad;
-    double gx[3], gy[3], detJ;
+    double gx[3], gy[3], detJ, m12;
 };
 struct __align__(16) GeomTpl {
     int ncell, len, pad0, pad1;
@@ -376,7 +378,7 @@ __device__ __forceinline__ bool geom_signature(const int32_t* __restrict__ rowpt
         GeomCell& c = T.c[q];
         c.off1 = 0; c.off2 = 0; c.slots = 0; c.pad = 0;
         for (int k = 0; k < 3; ++k) { c.gx[k] = 0.0; c.gy[k] = 0.0; }
-        c.detJ = 0.0;
+        c.detJ = 0.0; c.m12 = 0.0;
         if (q >= nc) continue;
         const int2 nb = __ldg(reinterpret_cast<const int2*>(v2c_idx) + cs + q);
         const CellGeom g = cell_geom(xy, r, nb.x, nb.y);
@@ -385,10 +387,11 @@ __device__ __forceinline__ bool geom_signature(const int32_t* __restrict__ rowpt
             const int col = colidx[ks + j];
             for (int k = 0; k < 3; ++k) if (col == g.d[k]) sl[k] = j;
         }
+        if (sl[0] == 255 || sl[1] == 255 || sl[2] == 255) return false;     // a cell vertex missing from the row's pattern
         c.off1 = nb.x - r; c.off2 = nb.y - r;
         c.slots = sl[0] | (sl[1] << 8) | (sl[2] << 16);
         for (int k = 0; k < 3; ++k) { c.gx[k] = g.gx[k]; c.gy[k] = g.gy[k]; }
-        c.detJ = g.detJ;
+        c.detJ = g.detJ; c.m12 = g.m12;
     }
     return true;
 }
@@ -474,8 +477,10 @@ __device__ __forceinline__ CellGeom geom_from_tpl(const GeomCell* __restrict__ c
     const double2 cc = __ldg(reinterpret_cast<const double2*>(gd) + 2);
     g.gx[0] = a.x; g.gx[1] = a.y; g.gx[2] = b.x;
     g.gy[0] = b.y; g.gy[1] = cc.x; g.gy[2] = cc.y;
-    g.detJ = __ldg(gd + 6);
+    const double2 dm = __ldg(reinterpret_cast<const double2*>(gd) + 3);
+    g.detJ = dm.x;
     g.area = 0.5 * g.detJ;
+    g.m12 = dm.y;
     return g;
 }
 
@@ -495,25 +500,28 @@ k_assemble_matrix_tpl(const int32_t* __restrict__ rowptr, const uint16_t* __rest
             const int len = rowptr[r + 1] - ks;
             const GeomTpl* T = gtab + gcode[r];
             const int nc = __ldg(&T->ncell);
-            double acc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.0;
-            for (int q = 0; q < nc; ++q) {
-                const CellGeom g = geom_from_tpl(&T->c[q], r);
-                const int sl = __ldg(&T->c[q].slots);
-                const int s0 = sl & 255, s1 = (sl >> 8) & 255, s2 = (sl >> 16) & 255;
-                double e[3];
-                element_row<KIND>(g, 0, fa, e);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const double add = (j == s0) ? e[0] : ((j == s1) ? e[1] : ((j == s2) ? e[2] : 0.0));
-                    acc[j] += add;
-                }
-            }
+            // the row's slots live in shared memory (odd row stride: conflict-free); contributions are added in cell order
             double* sr = sV + (ks - b.ka);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (j < len) sr[j] = accumulate ? (out[(int64_t)ks + j] + scale * acc[j]) : (scale * acc[j]);
+                if (j < len) sr[j] = 0.0;
+            // Fixed trip count, unconditional body: unused cells of a template are zero-filled (offsets 0, zero geometry ->
+            // zero element row added to slot 0), so the table reads and coefficient gathers of three cells are in flight
+            // together instead of one dependent chain per cell.
+            (void)nc;
+#pragma unroll 3
+            for (int q = 0; q < GT_MAXC; ++q) {
+                const CellGeom g = geom_from_tpl(&T->c[q], r);
+                const int sl = __ldg(&T->c[q].slots);
+                double e[3];
+                element_row<KIND>(g, 0, fa, e);
+                sr[sl & 255] += e[0];
+                sr[(sl >> 8) & 255] += e[1];
+                sr[(sl >> 16) & 255] += e[2];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < len) sr[j] = accumulate ? (out[(int64_t)ks + j] + scale * sr[j]) : (scale * sr[j]);
         }
         __syncthreads();
         unstage_f64(out, sV, b);
@@ -530,7 +538,9 @@ k_assemble_vector_tpl(const uint16_t* __restrict__ gcode, const GeomTpl* __restr
         const GeomTpl* T = gtab + gcode[r];
         const int nc = __ldg(&T->ncell);
         double acc = 0.0;
-        for (int q = 0; q < nc; ++q) {
+        (void)nc;
+#pragma unroll 3
+        for (int q = 0; q < GT_MAXC; ++q) {          // unused cells: zero geometry -> zero contribution
             const CellGeom g = geom_from_tpl(&T->c[q], r);
             acc += element_load<KIND>(g, 0, fa);
         }
