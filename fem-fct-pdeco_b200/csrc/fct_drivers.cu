@@ -121,7 +121,8 @@ extern "C" int fct_advdrift_state_host(fct_ctx* ctx, const double* c_host, doubl
                                        double bx, double by, double eps, int32_t* total_sweeps_host) {
     FCT_CHECK(ctx && c_host && u_host && num_steps >= 0, "fct_advdrift_state_host: bad argument");
     FCT_CHECK(ctx->cells && ctx->mass_set, "fct_advdrift_state_host: mesh / static matrices not set");
-    FCT_CHECK(!ctx->comm, "fct_advdrift_state_host: single-GPU contexts only");
+    // multi-GPU: every rank streams the slices of its own local range (owned rows + halo); fct_step refreshes the halo of
+    // each new slice before it is copied out
     const size_t n = (size_t)ctx->n, vb = sizeof(double) * n;
     // staging buffers, events and the second copy stream live in the context (allocated on first use): H2D of the
     // next control slice and D2H of the previous state slice run on different streams, i.e. on both copy engines

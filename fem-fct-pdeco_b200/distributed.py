@@ -265,6 +265,25 @@ def bench_multi(args, rank, world, local_rank):
     launches = ctx.launch_count() - l0
     lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
     dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    # e2e: the state sweep through the host-buffer entry point, every rank streaming its own local range (pinned host
+    # memory; control slices H2D, state slices D2H inside the timed region); wall clock between barriers, max over ranks
+    hc, hu = ctx.pinned(L), ctx.pinned(L)
+    hc[:] = np.tile(lp.scatter(c0), nt + 1)
+    hu[:] = 0.0
+    hu[:n] = lp.scatter(u0)
+    ctx.advdrift_state_host(hc, hu, nt, dt)          # warm-up
+    reps_e2e = max(1, args.steps // 2)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps_e2e):
+        ctx.advdrift_state_host(hc, hu, nt, dt)      # synchronises before returning
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, float(8 * n)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(te[:1], op=dist.ReduceOp.MAX)
+    dist.all_reduce(te[1:], op=dist.ReduceOp.SUM)
+    e2e_value = nt * reps_e2e / float(te[0].item())
+    e2e_bytes = int(te[1].item())
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         fct_steps = 2 * nt * args.steps
@@ -286,8 +305,9 @@ def bench_multi(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "whole FCT step (all kernels)", "achieved": step_gb * value / world,
                          "peak": peak, "unit": "GB/s", "frac": step_gb * value / world / peak, "traffic": None,
                          "peak_source": peak_src, "note": "per-GPU: algorithmic bytes of an FCT step x steps/s / N"},
-            "e2e": {"value": None, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "host-buffer entry point is single-GPU; see the N=1 line"},
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
+                    "call": "fct_advdrift_state_host on every rank (state sweep, pinned host trajectories of the rank's "
+                            "local range)"},
             "gpu_launches": int(lt.item()),
             "clocks": clocks,
         }

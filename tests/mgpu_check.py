@@ -50,6 +50,11 @@ def main():
         return du.download(), dp.download(), dd.download(), J, sw
 
     u, p, d, J, sw = run(ctx, lp.scatter)
+    # host-trajectory entry point on the partitioned context: same local trajectory, bit for bit
+    utr0 = np.zeros((ns + 1, mesh.nodes)); utr0[0] = u0
+    uh = np.ascontiguousarray(lp.scatter(utr0.ravel()))
+    ctx.advdrift_state_host(np.ascontiguousarray(lp.scatter(c.ravel())), uh, ns, dt)
+    host_ok = bool(np.array_equal(uh, u))
     parts = [None] * world
     dist.all_gather_object(parts, [np.ascontiguousarray(lp.owned(a)) for a in (u, p, d)])
     ok = True
@@ -65,6 +70,11 @@ def main():
         ok = res["u_equal"] and res["p_equal"] and res["d_equal"] and res["J_rel"] < 1e-13
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
+    hflag = torch.tensor([1 if host_ok else 0], device="cuda")
+    dist.all_reduce(hflag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MGPU_CHECK host-trajectory path equal on all ranks:", bool(int(hflag.item())))
+    flag = flag * hflag
     dist.barrier()
     dist.destroy_process_group()
     if not int(flag.item()):
