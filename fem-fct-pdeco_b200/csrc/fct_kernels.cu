@@ -96,6 +96,65 @@ k_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, c
     }
 }
 
+// y = alpha * A x + beta * z with the column pattern of A taken from the row templates (every matrix of a context lives
+// on the pattern of M): 8 B per entry instead of 12; same products in the same order as k_spmv.
+__global__ void __launch_bounds__(FCT_RB)
+k_spmv_tc(const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ code, const int32_t* __restrict__ toff,
+          const double* __restrict__ A, const double* __restrict__ x, double alpha, double beta, const double* __restrict__ z,
+          double* __restrict__ y, int row_begin, int row_end, int64_t nnz, int cap) {
+    __shared__ __align__(8) uint64_t bars[FCT_NST];
+    RowPipe<1, 0, FCT_NST> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {A}, {nullptr}};
+    const int nmine = pipe.my_blocks();
+    pipe.init();
+    pipe.prologue(nmine);
+    struct RowIn { int k0, len; double z; int4 o0, o1; };
+    auto row_of = [&](int i) {
+        const int blk = (int)blockIdx.x + i * (int)gridDim.x;
+        const int r = row_begin + blk * FCT_RB + (int)threadIdx.x;
+        return (i < nmine && r < row_end) ? r : -1;
+    };
+    auto load_code = [&](int i) {
+        const int r = row_of(i);
+        return r >= 0 ? (int)code[r] : 0;
+    };
+    auto load_row = [&](int i, int t) {
+        RowIn in{0, 0, 0.0, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+        const int r = row_of(i);
+        if (r >= 0) {
+            in.k0 = rowptr[r]; in.len = rowptr[r + 1] - in.k0;
+            if (beta != 0.0) in.z = z[r];
+            in.o0 = __ldg(reinterpret_cast<const int4*>(toff + FCT_TPL_W * t));
+            in.o1 = __ldg(reinterpret_cast<const int4*>(toff + FCT_TPL_W * t) + 1);
+        }
+        return in;
+    };
+    RowIn cur = load_row(0, load_code(0));
+    int tnext = load_code(1);
+    for (int i = 0; i < nmine; ++i) {
+        pipe.prefetch(i, nmine);
+        const RowIn nxt = load_row(i + 1, tnext);     // the code of a row is fetched two blocks ahead, its offsets one
+        tnext = load_code(i + 2);
+        const RowBlock b = pipe.block(i);
+        pipe.wait(i, b);
+        if ((int)threadIdx.x < b.nr) {
+            const int r = b.r0 + threadIdx.x;
+            const double* sA = pipe.f64(i % FCT_NST, 0) + (cur.k0 - b.ka);
+            const int off[8] = {cur.o0.x, cur.o0.y, cur.o0.z, cur.o0.w, cur.o1.x, cur.o1.y, cur.o1.z, cur.o1.w};
+            double xv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = x[r + off[j]];
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += ((j < cur.len) ? sA[j] : 0.0) * xv[j];
+            double out = alpha * acc;
+            if (beta != 0.0) out += beta * cur.z;
+            y[r] = out;
+        }
+        cur = nxt;
+        __syncthreads();
+    }
+}
+
 // ChebSI iteration k == 1: ymid = yold = 0  =>  y1 = omega1 * (b / Md')  with omega1 = 1
 __global__ void __launch_bounds__(FCT_RB)
 k_cheb_first(const double* __restrict__ g, const double* __restrict__ Md, double dscale, double omega,
@@ -269,7 +328,7 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             lsum += l;
             sL[kd] = 0.0;          // the diagonal travels as 1/l_ii in `dinv`: the Jacobi row loop is branch-free
             const double di = 1.0 / l;
-            dinv[r] = di;
+            if (dinv) dinv[r] = di;
             sD[kd] = dii;
             rowsum = fmin(rowsum, lsum);
             double br = ml * unr + (rhs ? dt * rr : 0.0);
@@ -554,23 +613,25 @@ __global__ void k_jacobi_reset(unsigned long long* __restrict__ jstate) {
 template <bool TPL>
 __global__ void __launch_bounds__(FCT_RB, 3)
 k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Mv,
-              const uint16_t* __restrict__ tcode, const double* __restrict__ tval, const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
+              const uint16_t* __restrict__ tcode, const int32_t* __restrict__ toff, const double* __restrict__ tval, const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
               const double* __restrict__ ulow, double dt, double* __restrict__ Rpos, double* __restrict__ Rneg,
               int row_begin, int row_end, int64_t nnz, int cap) {
     __shared__ __align__(8) uint64_t bars[FCT_NST2];
-    RowPipe<(TPL ? 1 : 2), 1, FCT_NST2> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {TPL ? Dv : Mv}, {colidx}};
+    RowPipe<(TPL ? 1 : 2), (TPL ? 0 : 1), FCT_NST2> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {TPL ? Dv : Mv},
+                                                             {TPL ? nullptr : colidx}};
     if (!TPL) pipe.gf[TPL ? 0 : 1] = Dv;
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
-    struct RowIn { int k0, k1; double ud, ul, ml; };
+    struct RowIn { int k0, k1, t; double ud, ul, ml; };
     auto load_row = [&](int i) {
-        RowIn in{0, 0, 0.0, 0.0, 1.0};
+        RowIn in{0, 0, 0, 0.0, 0.0, 1.0};
         if (i < nmine) {
             const int blk = (int)blockIdx.x + i * (int)gridDim.x;
             const int r = row_begin + blk * FCT_RB + (int)threadIdx.x;
             if (r < row_end) {
                 in.k0 = rowptr[r]; in.k1 = rowptr[r + 1];
+                if (TPL) in.t = tcode[r];
                 in.ud = udot[r]; in.ul = ulow[r]; in.ml = ML[r];
             }
         }
@@ -588,19 +649,25 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
             const double* sM = pipe.f64(i % FCT_NST2, 0);
             const double* sD = pipe.f64(i % FCT_NST2, TPL ? 0 : 1);
             double tm[8];
+            int toffs[8];
             if (TPL) {
-                const double2* tp = reinterpret_cast<const double2*>(tval + 8 * (int)tcode[r]);
+                // m_ij and the column offsets of the row come from its template (code fetched one block ahead)
+                const double2* tp = reinterpret_cast<const double2*>(tval + 8 * cur.t);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const double2 v = __ldg(tp + j); tm[2 * j] = v.x; tm[2 * j + 1] = v.y; }
+                const int4 o0 = __ldg(reinterpret_cast<const int4*>(toff + 8 * cur.t));
+                const int4 o1 = __ldg(reinterpret_cast<const int4*>(toff + 8 * cur.t) + 1);
+                toffs[0] = o0.x; toffs[1] = o0.y; toffs[2] = o0.z; toffs[3] = o0.w;
+                toffs[4] = o1.x; toffs[5] = o1.y; toffs[6] = o1.z; toffs[7] = o1.w;
             }
-            const int32_t* sC = pipe.s32(i % FCT_NST2, 0);
+            const int32_t* sC = TPL ? nullptr : pipe.s32(i % FCT_NST2, 0);
             const double udi = cur.ud, uli = cur.ul;
             double pp = 0.0, pn = 0.0, umax = uli, umin = uli;
             if (len <= 8) {
                 int c[8];
                 double udj[8], ulj[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) c[j] = (j < len) ? sC[ks + j] : r;
+                for (int j = 0; j < 8; ++j) c[j] = (j < len) ? (TPL ? r + toffs[j] : sC[ks + j]) : r;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { udj[j] = udot[c[j]]; ulj[j] = ulow[c[j]]; }
 #pragma unroll
@@ -638,23 +705,25 @@ k_flux_limits(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
 template <bool TPL>
 __global__ void __launch_bounds__(FCT_RB, 3)
 k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Mv,
-             const uint16_t* __restrict__ tcode, const double* __restrict__ tval, const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
+             const uint16_t* __restrict__ tcode, const int32_t* __restrict__ toff, const double* __restrict__ tval, const double* __restrict__ Dv, const double* __restrict__ ML, const double* __restrict__ udot,
              const double* __restrict__ ulow, const double* __restrict__ Rpos, const double* __restrict__ Rneg,
              double dt, double* __restrict__ uout, int row_begin, int row_end, int64_t nnz, int cap) {
     __shared__ __align__(8) uint64_t bars[FCT_NST2];
+    // column indices stay staged here: taking them from the templates was measured slower (0.64 vs 0.55 ms)
     RowPipe<(TPL ? 1 : 2), 1, FCT_NST2> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {TPL ? Dv : Mv}, {colidx}};
     if (!TPL) pipe.gf[TPL ? 0 : 1] = Dv;
     const int nmine = pipe.my_blocks();
     pipe.init();
     pipe.prologue(nmine);
-    struct RowIn { int k0, k1; double ud, ul, ml, rp, rn; };
+    struct RowIn { int k0, k1, t; double ud, ul, ml, rp, rn; };
     auto load_row = [&](int i) {
-        RowIn in{0, 0, 0.0, 0.0, 1.0, 1.0, 1.0};
+        RowIn in{0, 0, 0, 0.0, 0.0, 1.0, 1.0, 1.0};
         if (i < nmine) {
             const int blk = (int)blockIdx.x + i * (int)gridDim.x;
             const int r = row_begin + blk * FCT_RB + (int)threadIdx.x;
             if (r < row_end) {
                 in.k0 = rowptr[r]; in.k1 = rowptr[r + 1];
+                if (TPL) in.t = tcode[r];
                 in.ud = udot[r]; in.ul = ulow[r]; in.ml = ML[r]; in.rp = Rpos[r]; in.rn = Rneg[r];
             }
         }
@@ -673,7 +742,8 @@ k_flux_apply(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col
             const double* sD = pipe.f64(i % FCT_NST2, TPL ? 0 : 1);
             double tm[8];
             if (TPL) {
-                const double2* tp = reinterpret_cast<const double2*>(tval + 8 * (int)tcode[r]);
+                // m_ij and the column offsets of the row come from its template (code fetched one block ahead)
+                const double2* tp = reinterpret_cast<const double2*>(tval + 8 * cur.t);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const double2 v = __ldg(tp + j); tm[2 * j] = v.x; tm[2 * j + 1] = v.y; }
             }
@@ -958,6 +1028,7 @@ int fct_kernels_configure(fct_ctx* ctx) {
               worst, ctx->max_row);
     const int w = FCT_SMEM_OPTIN;   // opt-in ceiling only (never lowered by a later, smaller context)
     FCT_CUDA(cudaFuncSetAttribute(k_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA(cudaFuncSetAttribute(k_spmv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_cheb_iter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_cheb_iter<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_cheb_iter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
@@ -1054,6 +1125,24 @@ int fct_cheb_iter_tpl(fct_ctx* ctx, const double* Md, const double* g, const dou
                       double* ynew, double omega, double dscale);       // fct_templates.cu
 int fct_spmv_tpl(fct_ctx* ctx, const double* x, double alpha, double beta, const double* z, double* y);
 
+// y = alpha A x + beta z for a per-step matrix: template columns when the context has row templates, else CSR
+static int fct_spmv_any(fct_ctx* ctx, const double* A, const double* x, double alpha, double beta, const double* z, double* y) {
+    // measured at 4097^2: 0.343 ms with template columns vs 0.333 ms CSR (the longer code -> offsets -> gather chain eats
+    // the byte saving), so the CSR kernel stays the default; FCT_SPMV_TC=1 selects the template-column kernel
+    static int use_tc = -1;
+    if (use_tc < 0) { const char* e = getenv("FCT_SPMV_TC"); use_tc = (e && atoi(e) == 1) ? 1 : 0; }
+    if (use_tc && ctx->tpl_count > 0 && ctx->jac_mode > 0) {
+        const int nb = pipe_grid(ctx, 1);
+        if (nb > 0)
+            launch_pipe(ctx, k_spmv_tc, nb, FCT_NST * smem_bytes(ctx, 1, 0), ctx->rowptr, ctx->tpl_code, ctx->tpl_off, A, x, alpha,
+                        beta, z, y, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+        return 0;
+    }
+    LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, x, alpha, beta, z, y, ctx->cur_rb, ctx->cur_re,
+                ctx->nnz, ctx->cap);
+    return 0;
+}
+
 extern "C" int fct_spmv(fct_ctx* ctx, const double* A, const double* x, double alpha, double beta, const double* z,
                         double* y) {
     FCT_CHECK(ctx && A && x && y, "fct_spmv: null argument");
@@ -1062,8 +1151,7 @@ extern "C" int fct_spmv(fct_ctx* ctx, const double* A, const double* x, double a
         if (fct_spmv_tpl(ctx, x, alpha, beta, z, y)) return 1;
         return fct_launch_error(ctx, "fct_spmv");
     }
-    LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, x, alpha, beta, z, y, ctx->cur_rb, ctx->cur_re,
-                ctx->nnz, ctx->cap);
+    if (fct_spmv_any(ctx, A, x, alpha, beta, z, y)) return 1;
     return fct_launch_error(ctx, "fct_spmv");
 }
 
@@ -1341,16 +1429,17 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     fct_set_ring(ctx, K - 1);
     {
         const int nf = S ? 2 : 1;
+        double* dinv_out = ctx->jac_mode == 2 ? nullptr : dinv;      // the row-scaled sweeps never read 1/diag
         const size_t smem = FCT_NST_LOW * smem_bytes(ctx, nf, 2) + 2 * smem_bytes(ctx, 1, 0);
         const int nb = fct_nblocks(ctx) < ctx->grid_low[nf - 1] ? fct_nblocks(ctx) : ctx->grid_low[nf - 1];
         if (nb > 0) {
             if (S)
                 k_low_build<1><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un,
-                                                                  rhs, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,
+                                                                  rhs, dt, ctx->Lvals, ctx->Dvals, bvec, dinv_out, ctx->jstate + 7,
                                                                   ctx->jac_mode == 2, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
             else
                 k_low_build<0><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, sign, S, ctx->ML, un,
-                                                                  rhs, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,
+                                                                  rhs, dt, ctx->Lvals, ctx->Dvals, bvec, dinv_out, ctx->jstate + 7,
                                                                   ctx->jac_mode == 2, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
             ctx->launches++;
         }
@@ -1361,8 +1450,7 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     if (fct_jacobi_solve(ctx, ctx->Lvals, bvec, dinv, ulow, tmp, ctx->rtol, ctx->max_sweeps)) return 1;
     // 4. g = -(sign A) u_low + rhs on ring K-1; udot = ChebSI(g)
     fct_set_ring(ctx, K - 1);
-    LAUNCH_PIPE(ctx, k_spmv, 1, 1, ctx->rowptr, ctx->colidx, A, ulow, -sign, rhs ? 1.0 : 0.0, rhs, g, ctx->cur_rb,
-                ctx->cur_re, ctx->nnz, ctx->cap);
+    if (fct_spmv_any(ctx, A, ulow, -sign, rhs ? 1.0 : 0.0, rhs, g)) return 1;
     int vud = 0;
     if (fct_chebsi_v(ctx, ctx->M, ctx->Mdiag, g, udot, 20, 0.5, 2.0, K - 1, &vud)) return 1;
     // 5-7. fluxes, P, Q, R: on ring 1 when the halo is deep enough (then R+- needs no exchange), else on the owned rows
@@ -1375,11 +1463,11 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     const int gflux = fct_nblocks(ctx) < ctx->grid_flux_tpl ? fct_nblocks(ctx) : ctx->grid_flux_tpl;
     if (ftpl) {
         if (gflux > 0)
-            launch_pipe(ctx, k_flux_limits<true>, gflux, FCT_NST2 * smem_bytes(ctx, 1, 1), ctx->rowptr, ctx->colidx, ctx->M,
-                        ctx->tpl_code, ctx->tpl_val, ctx->Dvals, ctx->ML, udot, ulow, dt, Rp, Rn, ctx->cur_rb, ctx->cur_re,
+            launch_pipe(ctx, k_flux_limits<true>, gflux, FCT_NST2 * smem_bytes(ctx, 1, 0), ctx->rowptr, ctx->colidx, ctx->M,
+                        ctx->tpl_code, ctx->tpl_off, ctx->tpl_val, ctx->Dvals, ctx->ML, udot, ulow, dt, Rp, Rn, ctx->cur_rb, ctx->cur_re,
                         ctx->nnz, ctx->cap);
     } else {
-        LAUNCH_PIPE(ctx, k_flux_limits<false>, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->tpl_code, ctx->tpl_val, ctx->Dvals,
+        LAUNCH_PIPE(ctx, k_flux_limits<false>, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->tpl_code, ctx->tpl_off, ctx->tpl_val, ctx->Dvals,
                     ctx->ML, udot, ulow, dt, Rp, Rn, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
     }
     if (K < 2) {
@@ -1391,10 +1479,10 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
         const int ga = fct_nblocks(ctx) < ctx->grid_flux_tpl ? fct_nblocks(ctx) : ctx->grid_flux_tpl;
         if (ga > 0)
             launch_pipe(ctx, k_flux_apply<true>, ga, FCT_NST2 * smem_bytes(ctx, 1, 1), ctx->rowptr, ctx->colidx, ctx->M,
-                        ctx->tpl_code, ctx->tpl_val, ctx->Dvals, ctx->ML, udot, ulow, Rp, Rn, dt, uout, ctx->cur_rb, ctx->cur_re,
+                        ctx->tpl_code, ctx->tpl_off, ctx->tpl_val, ctx->Dvals, ctx->ML, udot, ulow, Rp, Rn, dt, uout, ctx->cur_rb, ctx->cur_re,
                         ctx->nnz, ctx->cap);
     } else {
-        LAUNCH_PIPE(ctx, k_flux_apply<false>, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->tpl_code, ctx->tpl_val, ctx->Dvals,
+        LAUNCH_PIPE(ctx, k_flux_apply<false>, 2, 1, ctx->rowptr, ctx->colidx, ctx->M, ctx->tpl_code, ctx->tpl_off, ctx->tpl_val, ctx->Dvals,
                     ctx->ML, udot, ulow, Rp, Rn, dt, uout, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
     }
     if (fct_launch_error(ctx, "fct_step")) return 1;

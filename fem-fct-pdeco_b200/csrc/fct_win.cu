@@ -640,6 +640,7 @@ struct fct_win {
     int max_dep = 0;
     int nfast = 0;                   // blocks on the all-shared-memory path
     bool cheb_on = true, jac_on = true;
+    bool single = false;             // FCT_WIN_SINGLE=1: one launch per sweep through the windowed kernel
 };
 
 void fct_win_free(fct_ctx* ctx) {
@@ -723,6 +724,7 @@ int fct_win_build(fct_ctx* ctx) {
         // each; FCT_WIN_LAG_* override (blocks)
         W->lag_cheb = env_int("FCT_WIN_LAG_CHEB", 0);
         W->lag_jac = env_int("FCT_WIN_LAG_JAC", 0);
+        W->single = env_int("FCT_WIN_SINGLE", 0) != 0;
         if (env_int("FCT_WIN_CHEB", 1) == 0) W->cheb_on = false;
         if (env_int("FCT_WIN_JAC", 1) == 0) W->jac_on = false;
         ok = true;
@@ -786,6 +788,20 @@ int fct_win_chebsi(fct_ctx* ctx, const double* b, double* y, int iters, double l
     const long long total = (long long)(a.blk_hi - a.blk_lo + (iters - 1) * P.lag) * iters;
     if (total > 2000000000ll) return 0;
     const int grid = (long long)W->grid_cheb < total ? W->grid_cheb : (int)total;
+    if (W->single) {
+        // one launch per iteration through the same kernel (all operands staged by the copy engine, no dependencies)
+        WinArgs b1 = a;
+        b1.P.nsweeps = 1;
+        for (int s = 0; s < iters; ++s) {
+            b1.P.in[0] = a.P.in[s]; b1.P.old[0] = a.P.old[s]; b1.P.out[0] = a.P.out[s]; b1.P.omega[0] = a.P.omega[s];
+            b1.P.first[0] = a.P.first[s];
+            const int nblk = a.blk_hi - a.blk_lo;
+            win_kernel(WIN_CHEB, W->nst_cheb)<<<W->grid_cheb < nblk ? W->grid_cheb : nblk, WIN_THREADS,
+                                               (size_t)W->nst_cheb * CHEB_STAGE_BYTES, ctx->stream>>>(b1);
+            ctx->launches++;
+        }
+        return 1;
+    }
     win_kernel(WIN_CHEB, W->nst_cheb)<<<grid, WIN_THREADS, (size_t)W->nst_cheb * CHEB_STAGE_BYTES, ctx->stream>>>(a);
     ctx->launches++;
     return 1;
@@ -843,7 +859,7 @@ int fct_win_bench_jacobi(fct_ctx* ctx, int sweeps, int reps, int warm, float* ms
     for (int pass = warm ? 0 : 1; pass < 2; ++pass) {
         if (pass == 1) cudaEventRecord(e0, ctx->stream);
         for (int i = 0; i < reps; ++i) {
-            if (env_int("FCT_WIN_SINGLE", 0)) {
+            if (W->single) {
                 // experiment: the windowed kernel as a one-sweep-per-launch kernel (no dependencies, no flags)
                 WinArgs b = a;
                 b.fixed_sweeps = 1; b.P.nsweeps = 1;

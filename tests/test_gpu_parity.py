@@ -350,16 +350,19 @@ def test_template_jacobi_modes(monkeypatch):
     rng = np.random.default_rng(5)
     c = 1.0 + rng.random((ns + 1, m.nodes))
     res = {}
-    for mode, mdtab in (("0", "0"), ("1", "1"), ("2", "1")):
-        monkeypatch.setenv("FCT_JAC_TPL", mode)
+    for mode, mdtab in (("csr", "0"), ("0", "0"), ("1", "1"), ("2", "1")):
+        monkeypatch.setenv("FCT_NO_TEMPLATES", "1" if mode == "csr" else "0")      # "csr": no row templates at all
+        monkeypatch.setenv("FCT_JAC_TPL", "0" if mode == "csr" else mode)
         monkeypatch.setenv("FCT_CHEB_MDTAB", mdtab)
         ctx = RectMeshP1(n, 0.0, 1.0).context()
-        assert ctx.template_count() > 0
+        assert (ctx.template_count() > 0) == (mode != "csr")
         utr = np.zeros((ns + 1, m.nodes)); utr[0] = u0
         du = ctx.array(utr.ravel())
         sw = ctx.advdrift_state(ctx.array(c.ravel()), du, ns, dt)
         res[mode] = (du.download().reshape(ns + 1, -1), sw)
     assert np.array_equal(res["0"][0], res["1"][0]) and res["0"][1] == res["1"][1]
+    # the pure CSR/TMA kernels (ChebSI, flux limiter, SpMV without any template) give the same bits as well
+    assert np.array_equal(res["csr"][0], res["0"][0]) and res["csr"][1] == res["0"][1]
     for i in range(1, ns + 1):
         assert rel_l2(res["2"][0][i], res["0"][0][i]) < 1e-13 * i
     assert abs(res["2"][1] - res["0"][1]) <= 2 * ns
