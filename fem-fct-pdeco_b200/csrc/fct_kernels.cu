@@ -478,8 +478,8 @@ k_jacobi_sweep_gen(const int32_t* __restrict__ rowptr, const int32_t* __restrict
 // the same order as k_jacobi_sweep, bit-identical.  SCALED = true: k_low_build has divided the row and b by l_ii, so
 // x_new = b' - sum l'_ij x_j and dinv is not read.  The code of a row is fetched two blocks ahead and its offsets one
 // block ahead, so the code -> offsets -> gather chain never waits on DRAM.
-template <int NST, bool SCALED>
-__global__ void __launch_bounds__(FCT_RB, 5)
+template <int NST, bool SCALED, int MINB = 5>
+__global__ void __launch_bounds__(FCT_RB, MINB)
 k_jacobi_sweep_tpl(const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ code, const int32_t* __restrict__ toff,
                    const double* __restrict__ Lv, const double* __restrict__ bvec, const double* __restrict__ dinv,
                    const double* __restrict__ x, double* __restrict__ xnew, unsigned long long* __restrict__ jstate, int check,
@@ -1006,6 +1006,16 @@ static inline void launch_jacobi_tpl(fct_ctx* ctx, const double* Lv, const doubl
 #define JT_ARGS ctx->rowptr, ctx->tpl_code, ctx->tpl_off, Lv, b, dinv, xin, xout, ctx->jstate, chk, ctx->row_begin, \
                 ctx->row_end, ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap
     const bool sc = ctx->jac_mode == 2;
+    static int occ6 = -1;            // FCT_JTPL_OCC6=1: 2-stage ring, 6 resident CTAs (40 registers, some spills)
+    if (occ6 < 0) { const char* e = getenv("FCT_JTPL_OCC6"); occ6 = (e && atoi(e) == 1) ? 1 : 0; }
+    if (occ6 && sc && ctx->nst_jtpl == 2) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int nb6 = nb0 < 6 * sms ? nb0 : 6 * sms;
+        launch_pipe(ctx, k_jacobi_sweep_tpl<2, true, 6>, nb6, sm, JT_ARGS);
+        return;
+    }
     if (ctx->nst_jtpl == 2) { if (sc) launch_pipe(ctx, k_jacobi_sweep_tpl<2, true>, nb, sm, JT_ARGS); else launch_pipe(ctx, k_jacobi_sweep_tpl<2, false>, nb, sm, JT_ARGS); }
     else if (ctx->nst_jtpl == 4) { if (sc) launch_pipe(ctx, k_jacobi_sweep_tpl<4, true>, nb, sm, JT_ARGS); else launch_pipe(ctx, k_jacobi_sweep_tpl<4, false>, nb, sm, JT_ARGS); }
     else { if (sc) launch_pipe(ctx, k_jacobi_sweep_tpl<3, true>, nb, sm, JT_ARGS); else launch_pipe(ctx, k_jacobi_sweep_tpl<3, false>, nb, sm, JT_ARGS); }
@@ -1042,6 +1052,7 @@ int fct_kernels_configure(fct_ctx* ctx) {
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
+    FCT_CUDA((cudaFuncSetAttribute(k_jacobi_sweep_tpl<2, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, w)));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_tpl<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_jacobi_sweep_gen<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));

@@ -157,9 +157,14 @@ int fct_templates_build(fct_ctx* ctx) {
 }
 
 // ---- matrix applications through the templates -------------------------------------------------------------
+__device__ __forceinline__ double tpl_row_dot_t(int t, const int32_t* __restrict__ toff, const double* __restrict__ tval,
+                                                const double* __restrict__ x, int r);
 __device__ __forceinline__ double tpl_row_dot(const uint16_t* __restrict__ code, const int32_t* __restrict__ toff,
                                               const double* __restrict__ tval, const double* __restrict__ x, int r) {
-    const int t = code[r];
+    return tpl_row_dot_t((int)code[r], toff, tval, x, r);
+}
+__device__ __forceinline__ double tpl_row_dot_t(int t, const int32_t* __restrict__ toff, const double* __restrict__ tval,
+                                                const double* __restrict__ x, int r) {
     const int4 o0 = __ldg(reinterpret_cast<const int4*>(toff + FCT_TPL_W * t));
     const int4 o1 = __ldg(reinterpret_cast<const int4*>(toff + FCT_TPL_W * t) + 1);
     const double2 v0 = __ldg(reinterpret_cast<const double2*>(tval + FCT_TPL_W * t));
@@ -177,20 +182,35 @@ __device__ __forceinline__ double tpl_row_dot(const uint16_t* __restrict__ code,
 // Measured on B200 (4097^2): this plain grid-stride form runs at 0.148 ms (4.7 TB/s of actual traffic); fetching the
 // next block's inputs ahead (0.175 ms) or several rows per thread (0.195 ms) is slower -- both widen the window of
 // rows in flight, and the neighbour gathers then miss in L2 more often.
-__global__ void __launch_bounds__(FCT_RB)
+template <bool PF, bool PF2>
+__global__ void __launch_bounds__(FCT_RB, 8)
 k_cheb_iter_tpl(const uint16_t* __restrict__ code, const int32_t* __restrict__ toff, const double* __restrict__ tval,
                 const double* __restrict__ tdiag, const double* __restrict__ Md, const double* __restrict__ g,
                 const double* __restrict__ ymid, const double* __restrict__ yold, double* __restrict__ ynew, double omega,
                 double dscale, int has_old, int row_begin, int row_end) {
     const int stride = (int)gridDim.x * FCT_RB;
-    for (int r = row_begin + (int)blockIdx.x * FCT_RB + (int)threadIdx.x; r < row_end; r += stride) {
+    int r = row_begin + (int)blockIdx.x * FCT_RB + (int)threadIdx.x;
+    // PF: the template code of the thread's next row is fetched one iteration ahead (one register), so the
+    // code -> table -> gather chain of an iteration starts from the (L1-resident) table instead of DRAM
+    int t = (PF && r < row_end) ? (int)code[r] : 0;
+    for (; r < row_end; r += stride) {
+        if (!PF) t = code[r];
+        const int tn = (PF && r + stride < row_end) ? (int)code[r + stride] : 0;
+        if (PF2 && (threadIdx.x & 15) == 0 && r + stride < row_end) {
+            // pull the next iteration's own-row operands into L2 (one request per 128-byte line, no registers); the
+            // neighbour rows it gathers are own rows of other CTAs, prefetched by them
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(g + r + stride));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ymid + r + stride));
+            if (has_old) asm volatile("prefetch.global.L2 [%0];" ::"l"(yold + r + stride));
+        }
         // Md == nullptr: the caller's Md is diag(M) of the templated matrix itself, so it comes out of the table
         // (same bits) and the 8 B/row read is saved
-        const double gr = g[r], mdr = Md ? Md[r] : __ldg(tdiag + code[r]), ym = ymid[r];
+        const double gr = g[r], mdr = Md ? Md[r] : __ldg(tdiag + t), ym = ymid[r];
         const double yo = has_old ? yold[r] : 0.0;
-        const double acc = tpl_row_dot(code, toff, tval, ymid, r);
+        const double acc = tpl_row_dot_t(t, toff, tval, ymid, r);
         const double z = (gr - acc) / (dscale * mdr);
         ynew[r] = omega * (z + ym - yo) + yo;
+        if (PF) t = tn;
     }
 }
 
@@ -221,8 +241,17 @@ int fct_cheb_iter_tpl(fct_ctx* ctx, const double* Md, const double* g, const dou
     const int grid = tpl_grid(ctx);
     if (grid > 0) {
         const double* Mdk = (ctx->cheb_mdtab && Md == ctx->Mdiag) ? nullptr : Md;
-        k_cheb_iter_tpl<<<grid, FCT_RB, 0, ctx->stream>>>(ctx->tpl_code, ctx->tpl_off, ctx->tpl_val, ctx->tpl_diag, Mdk, g, ymid,
-                                                         yold, ynew, omega, dscale, yold != nullptr, ctx->cur_rb, ctx->cur_re);
+        static int pf = -1;                  // FCT_CHEB_PF: 0 plain, 1 (default) next row's template code one iteration ahead,
+        if (pf < 0) {                        // 2: + L2 prefetch of the next iteration's own-row operands
+            const char* e = getenv("FCT_CHEB_PF");
+            pf = (e && atoi(e) >= 0 && atoi(e) <= 2) ? atoi(e) : 1;
+        }
+#define CHEB_TPL_ARGS ctx->tpl_code, ctx->tpl_off, ctx->tpl_val, ctx->tpl_diag, Mdk, g, ymid, yold, ynew, omega, dscale, \
+                      yold != nullptr, ctx->cur_rb, ctx->cur_re
+        if (pf == 2) k_cheb_iter_tpl<true, true><<<grid, FCT_RB, 0, ctx->stream>>>(CHEB_TPL_ARGS);
+        else if (pf == 1) k_cheb_iter_tpl<true, false><<<grid, FCT_RB, 0, ctx->stream>>>(CHEB_TPL_ARGS);
+        else k_cheb_iter_tpl<false, false><<<grid, FCT_RB, 0, ctx->stream>>>(CHEB_TPL_ARGS);
+#undef CHEB_TPL_ARGS
         ctx->launches++;
     }
     return 0;
