@@ -238,7 +238,8 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             int cap) {
     __shared__ __align__(8) uint64_t bars[FCT_NST_LOW];
     __shared__ double sred[FCT_RB / 32];
-    RowPipe<1 + HAS_S, 2, FCT_NST_LOW> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {A}, {colidx, tpos}};
+    // the column indices are not staged: the diagonal is the entry that is its own transpose (tpos[k] == k)
+    RowPipe<1 + HAS_S, 1, FCT_NST_LOW> pipe{fct_smem, bars, cap, row_begin, row_end, nnz, rowptr, {A}, {tpos}};
     if (HAS_S) pipe.gf[HAS_S] = S;
     double* sL = reinterpret_cast<double*>(fct_smem + FCT_NST_LOW * pipe.stage_bytes());
     double* sD = sL + cap;
@@ -274,26 +275,26 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             const int st = i % FCT_NST_LOW;
             const double* sA = pipe.f64(st, 0);
             const double* sS = pipe.f64(st, HAS_S ? 1 : 0);
-            const int32_t* sC = pipe.s32(st, 0);
-            const int32_t* sT = pipe.s32(st, 1);
+            const int32_t* sT = pipe.s32(st, 0);
+            const int kg = cur.k0 - ks;              // global CSR index of staged slot 0
             double dsum = 0.0, lsum = 0.0;
             int kd = ks;
             const int len = ke - ks;
             if (len <= 8) {
                 // all transposed-entry gathers a_ji = A[tpos] are issued before the first use
                 double av[8], atv[8];
-                int cv[8];
+                int tv[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const bool p = j < len;
-                    cv[j] = p ? sC[ks + j] : r;
+                    tv[j] = p ? sT[ks + j] : -1;
                     av[j] = p ? sA[ks + j] : 0.0;
-                    atv[j] = p ? A[sT[ks + j]] : 0.0;
+                    atv[j] = p ? A[tv[j]] : 0.0;
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (j < len) {
-                        if (cv[j] == r) { kd = ks + j; continue; }
+                        if (tv[j] == kg + ks + j) { kd = ks + j; continue; }
                         const double a = sign * av[j];
                         const double at = sign * atv[j];
                         const double d = fmax(0.0, fmax(a, at));
@@ -307,8 +308,7 @@ k_low_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                 }
             } else {
                 for (int k = ks; k < ke; ++k) {
-                    const int c = sC[k];
-                    if (c == r) { kd = k; continue; }
+                    if (sT[k] == kg + k) { kd = k; continue; }
                     const double a = sign * sA[k];
                     const double at = sign * A[sT[k]];
                     const double d = fmax(0.0, fmax(a, at));
@@ -1064,9 +1064,9 @@ int fct_kernels_configure(fct_ctx* ctx) {
     FCT_CUDA(cudaFuncSetAttribute(k_flux_apply<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_row_lump, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
     FCT_CUDA(cudaFuncSetAttribute(k_dot_M, cudaFuncAttributeMaxDynamicSharedMemorySize, w));
-    FCT_CHECK(FCT_NST_LOW * smem_bytes(ctx, 2, 2) + 2 * smem_bytes(ctx, 1, 0) <= (size_t)FCT_SMEM_OPTIN,
+    FCT_CHECK(FCT_NST_LOW * smem_bytes(ctx, 2, 1) + 2 * smem_bytes(ctx, 1, 0) <= (size_t)FCT_SMEM_OPTIN,
               "row blocks need %zu B of shared memory for the TMA ring (max row %d): unsupported pattern",
-              FCT_NST_LOW * smem_bytes(ctx, 2, 2) + 2 * smem_bytes(ctx, 1, 0), ctx->max_row);
+              FCT_NST_LOW * smem_bytes(ctx, 2, 1) + 2 * smem_bytes(ctx, 1, 0), ctx->max_row);
     cudaDeviceProp prop;
     FCT_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
     int occ1 = 0, occ2 = 0;
@@ -1102,10 +1102,14 @@ int fct_kernels_configure(fct_ctx* ctx) {
     FCT_CHECK(occ1 >= 1 && occ2 >= 1, "TMA-ring kernels do not fit on an SM (cap=%d)", ctx->cap);
     int occl0 = 0, occl1 = 0;
     FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &occl0, k_low_build<0>, FCT_RB, FCT_NST_LOW * smem_bytes(ctx, 1, 2) + 2 * smem_bytes(ctx, 1, 0)));
+        &occl0, k_low_build<0>, FCT_RB, FCT_NST_LOW * smem_bytes(ctx, 1, 1) + 2 * smem_bytes(ctx, 1, 0)));
     FCT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &occl1, k_low_build<1>, FCT_RB, FCT_NST_LOW * smem_bytes(ctx, 2, 2) + 2 * smem_bytes(ctx, 1, 0)));
+        &occl1, k_low_build<1>, FCT_RB, FCT_NST_LOW * smem_bytes(ctx, 2, 1) + 2 * smem_bytes(ctx, 1, 0)));
     FCT_CHECK(occl0 >= 1 && occl1 >= 1, "k_low_build does not fit on an SM (cap=%d)", ctx->cap);
+    {
+        const char* ol = getenv("FCT_OCC_LOW");     // tuning knob: resident CTAs per SM of k_low_build
+        if (ol && atoi(ol) >= 1) { if (atoi(ol) < occl0) occl0 = atoi(ol); if (atoi(ol) < occl1) occl1 = atoi(ol); }
+    }
     ctx->grid_low[0] = prop.multiProcessorCount * occl0;
     ctx->grid_low[1] = prop.multiProcessorCount * occl1;
     ctx->grid_pipe1 = prop.multiProcessorCount * occ1;
@@ -1441,7 +1445,7 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     {
         const int nf = S ? 2 : 1;
         double* dinv_out = ctx->jac_mode == 2 ? nullptr : dinv;      // the row-scaled sweeps never read 1/diag
-        const size_t smem = FCT_NST_LOW * smem_bytes(ctx, nf, 2) + 2 * smem_bytes(ctx, 1, 0);
+        const size_t smem = FCT_NST_LOW * smem_bytes(ctx, nf, 1) + 2 * smem_bytes(ctx, 1, 0);
         const int nb = fct_nblocks(ctx) < ctx->grid_low[nf - 1] ? fct_nblocks(ctx) : ctx->grid_low[nf - 1];
         if (nb > 0) {
             if (S)
@@ -1516,7 +1520,7 @@ extern "C" int fct_bench_jacobi_sweeps(fct_ctx* ctx, const double* A, const doub
     k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
     fct_set_ring(ctx, 0);
     {
-        const size_t smem = FCT_NST_LOW * smem_bytes(ctx, 1, 2) + 2 * smem_bytes(ctx, 1, 0);
+        const size_t smem = FCT_NST_LOW * smem_bytes(ctx, 1, 1) + 2 * smem_bytes(ctx, 1, 0);
         const int nb = fct_nblocks(ctx) < ctx->grid_low[0] ? fct_nblocks(ctx) : ctx->grid_low[0];
         k_low_build<0><<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpos, A, 1.0, nullptr, ctx->ML, un,
                                                           nullptr, dt, ctx->Lvals, ctx->Dvals, bvec, dinv, ctx->jstate + 7,

@@ -335,7 +335,7 @@ k_win(const __grid_constant__ WinArgs a) {
         }
         if (S > P.nsweeps) S = P.nsweeps;
     }
-    const int blk_lo = a.blk_lo, blk_hi = a.blk_hi, n = a.n, nb_all = a.nb_all;
+    const int blk_lo = a.blk_lo, blk_hi = a.blk_hi, n = a.n;
     const int total = (blk_hi - blk_lo + (S - 1) * P.lag) * S;
     const size_t sbytes = KIND == WIN_CHEB ? (size_t)CHEB_STAGE_BYTES : jac_stage_bytes(a.cap);
     const int warp = tid >> 5, lane = tid & 31;
