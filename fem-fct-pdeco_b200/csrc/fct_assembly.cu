@@ -548,6 +548,142 @@ k_assemble_vector_tpl(const uint16_t* __restrict__ gcode, const GeomTpl* __restr
     }
 }
 
+// Fused drift-operator assembly + low-order build (the state / adjoint loops of the drift-control problem,
+// advection_solidbody_FCT_PDECO_alltime.py:210-259 -> helpers.py:1769-1780): one pass produces
+//   A   = ascale * [ (b.grad c) u v + (b.grad v) c u ]        (row i: a_ij, written for the later g = -A u_low + rhs)
+//   D, L (row-scaled), b                                        (exactly what k_low_build makes of A)
+// A thread walks the cells of its row once (geometry templates) and evaluates, per cell, the element row of its own
+// vertex AND the element column of its own vertex: a_ij and a_ji come from the same two cells in the same (ascending
+// cell) order in which row j itself would add them, so the transposed entries need no second pass over A, no tpos and
+// no column indices.  (a_ji is evaluated in row i's rotation of the cell; on meshes where cell_geom() is not exact the
+// last bit may differ from row j's own value -- inside the parity tolerance, and independent of the GPU count.)
+__global__ void __launch_bounds__(FCT_RB)
+k_drift_low_build(const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ gcode, const GeomTpl* __restrict__ gtab,
+                  const double* __restrict__ cf, double bx, double by, double ascale, double sign,
+                  const double* __restrict__ ML, const double* __restrict__ un, const double* __restrict__ rhs, double dt,
+                  double* __restrict__ Av, double* __restrict__ Lv, double* __restrict__ Dv, double* __restrict__ bvec,
+                  double* __restrict__ dinv, unsigned long long* __restrict__ min_rowsum_key, int scale_rows, int row_begin,
+                  int row_end, int64_t nnz, int cap) {
+    __shared__ double sred[FCT_RB / 32];
+    double* sA = reinterpret_cast<double*>(fct_smem);      // a_ij, then the scaled row of A
+    double* sT = sA + cap;                                  // a_ji, then the row of L
+    double* sD = sT + cap;
+    double rowsum = 1e300;
+    FCT_FOR_ROW_BLOCKS(blk, row_begin, row_end) {
+        const RowBlock b = row_block(rowptr, row_begin, row_end, blk);
+        if ((int)threadIdx.x < b.nr) {
+            const int r = b.r0 + threadIdx.x;
+            const int ks = rowptr[r];
+            const int len = rowptr[r + 1] - ks;
+            const GeomTpl* T = gtab + gcode[r];
+            double* ra = sA + (ks - b.ka);
+            double* rt = sT + (ks - b.ka);
+            double* rd = sD + (ks - b.ka);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < len) { ra[j] = 0.0; rt[j] = 0.0; }
+            const double c0 = cf[r];
+            const int kd = __ldg(&T->c[0].slots) & 255;          // every incident cell maps the row's vertex to the diagonal slot
+#pragma unroll 3
+            for (int q = 0; q < GT_MAXC; ++q) {                   // unused cells: zero geometry -> zero contributions
+                const CellGeom g = geom_from_tpl(&T->c[q], r);
+                const int sl = __ldg(&T->c[q].slots);
+                const double c1 = cf[g.d[1]], c2 = cf[g.d[2]];
+                // element tensor of FCT_FORM_DRIFT, same expressions as element_row<FCT_FORM_DRIFT>
+                const double gcx = c0 * g.gx[0] + c1 * g.gx[1] + c2 * g.gx[2];
+                const double gcy = c0 * g.gy[0] + c1 * g.gy[1] + c2 * g.gy[2];
+                const double s = bx * gcx + by * gcy;
+                const double m = g.m12;
+                const double csum = (c0 + c1) + c2;
+                const double cc[3] = {c0, c1, c2};
+                const double bg0 = bx * g.gx[0] + by * g.gy[0];
+                double er[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double mass = (s * m) * ((k == 0) ? 2.0 : 1.0);
+                    const double conv = bg0 * (m * (csum + cc[k]));
+                    er[k] = mass + conv;
+                }
+                // element column of the row's vertex: A_e[a][0], a = 1, 2 (what rows j1, j2 add to their entry towards r)
+                const double convc = m * (csum + c0);
+                const double ec1 = (s * m) * 1.0 + (bx * g.gx[1] + by * g.gy[1]) * convc;
+                const double ec2 = (s * m) * 1.0 + (bx * g.gx[2] + by * g.gy[2]) * convc;
+                const int s0 = sl & 255, s1 = (sl >> 8) & 255, s2 = (sl >> 16) & 255;
+                ra[s0] += er[0]; ra[s1] += er[1]; ra[s2] += er[2];
+                rt[s1] += ec1; rt[s2] += ec2;
+            }
+            // low-order operator of this row (k_low_build, helpers.py:1769-1780)
+            const double ml = ML[r], unr = un[r];
+            double dsum = 0.0, lsum = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < len) {
+                    const double av = ascale * ra[j];
+                    ra[j] = av;                                   // A as fct_assemble_matrix(.., scale = ascale) stores it
+                    if (j != kd) {
+                        const double a = sign * av;
+                        const double at = sign * (ascale * rt[j]);
+                        const double d = fmax(0.0, fmax(a, at));
+                        dsum += d;
+                        const double l = dt * (a - d);
+                        lsum += l;
+                        rt[j] = l;
+                        rd[j] = d;
+                    }
+                }
+            }
+            const double a = sign * ra[kd];
+            const double dii = -dsum;
+            const double l = ml + dt * (a - dii);
+            lsum += l;
+            rt[kd] = 0.0;
+            const double di = 1.0 / l;
+            if (dinv) dinv[r] = di;
+            rd[kd] = dii;
+            rowsum = fmin(rowsum, lsum);
+            double br = ml * unr + (rhs ? dt * rhs[r] : 0.0);
+            if (scale_rows) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < len) rt[j] *= di;
+                br *= di;
+            }
+            bvec[r] = br;
+        }
+        __syncthreads();
+        unstage_f64(Av, sA, b);
+        unstage_f64(Lv, sT, b);
+        unstage_f64(Dv, sD, b);
+        __syncthreads();
+    }
+    const double mrs = block_min(rowsum, sred);
+    if (threadIdx.x == 0) {
+        // same sortable-key transform as k_low_build (atomicMin on signed doubles)
+        unsigned long long u = (unsigned long long)__double_as_longlong(mrs);
+        u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+        atomicMin(min_rowsum_key, u);
+    }
+}
+
+// Host side of the fused pass on the context's current ring.  Returns 0 when the fused kernel is not applicable
+// (no geometry templates, FCT_NO_FUSED_DRIFT=1): the caller assembles A and lets fct_step build the low-order system.
+int fct_drift_low_build(fct_ctx* ctx, const double* c, double bx, double by, double ascale, double sign, const double* rhs,
+                        const double* un, double dt, double* bvec, double* dinv_out) {
+    const char* e = getenv("FCT_NO_FUSED_DRIFT");         // read per call: the tests toggle it between contexts
+    if ((e && atoi(e) == 1) || ctx->gt_count <= 0 || ctx->max_row > 8) return 0;
+    const size_t smem = 3 * (size_t)ctx->cap * 8;
+    if (smem > (size_t)FCT_SMEM_OPTIN) return 0;
+    const int nb = fct_grid(ctx, fct_nblocks(ctx));
+    if (nb > 0) {
+        k_drift_low_build<<<nb, FCT_RB, smem, ctx->stream>>>(ctx->rowptr, ctx->gt_code, reinterpret_cast<const GeomTpl*>(ctx->gt_tab),
+                                                             c, bx, by, ascale, sign, ctx->ML, un, rhs, dt, ctx->Avals, ctx->Lvals,
+                                                             ctx->Dvals, bvec, dinv_out, ctx->jstate + 7, ctx->jac_mode == 2,
+                                                             ctx->cur_rb, ctx->cur_re, ctx->nnz, ctx->cap);
+        ctx->launches++;
+    }
+    return 1;
+}
+
 // ======================================================================================================
 template <int KIND>
 static int launch_matrix(fct_ctx* ctx, const FormArgs& fa, double scale, int accumulate, double* out) {
@@ -603,6 +739,7 @@ int fct_assembly_configure(fct_ctx* ctx) {
     rc |= configure_matrix<FCT_FORM_WIND_POLY3_T>(bytes);
     rc |= configure_matrix<FCT_FORM_DRIFT_MASS>(bytes);
     rc |= configure_matrix<FCT_FORM_DRIFT_CONV>(bytes);
+    if (cudaFuncSetAttribute(k_drift_low_build, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) rc |= 1;
     return rc;
 }
 

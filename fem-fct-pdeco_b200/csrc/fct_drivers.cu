@@ -40,6 +40,9 @@ static int acc_read(fct_ctx* ctx, int32_t* total_sweeps_host) {
 // operator of the drift-control problem in FCT_alg_ref sign convention:
 //   state   (legacy A_u = -eps Ad + Adrift1 + Adrift2, FCT_alg(A_u) == FCT_alg_ref(-A_u)):  eps K - drift(c)
 //   adjoint (legacy A_p = -eps Ad - Adrift1 - Adrift2):                                      eps K + drift(c)
+int fct_step_drift(fct_ctx* ctx, const double* c, double bx, double by, double ascale, const double* rhs, const double* un,
+                   double dt, double* uout);      // fct_kernels.cu
+
 static int assemble_drift_operator(fct_ctx* ctx, const double* c, double bx, double by, double eps, double drift_sign) {
     if (fct_assemble_matrix(ctx, FCT_FORM_DRIFT, c, nullptr, nullptr, bx, by, drift_sign, 0, ctx->Avals)) return 1;
     if (eps != 0.0) {
@@ -56,8 +59,12 @@ extern "C" int fct_advdrift_state(fct_ctx* ctx, const double* c_traj, double* u_
     const size_t n = (size_t)ctx->n;
     if (acc_reset(ctx)) return 1;
     for (int i = 1; i <= num_steps; ++i) {
-        if (assemble_drift_operator(ctx, c_traj + i * n, bx, by, eps, -1.0)) return 1;
-        if (fct_step(ctx, ctx->Avals, 1.0, nullptr, nullptr, u_traj + (i - 1) * n, dt, u_traj + i * n, nullptr)) return 1;
+        if (eps == 0.0) {
+            if (fct_step_drift(ctx, c_traj + i * n, bx, by, -1.0, nullptr, u_traj + (i - 1) * n, dt, u_traj + i * n)) return 1;
+        } else {
+            if (assemble_drift_operator(ctx, c_traj + i * n, bx, by, eps, -1.0)) return 1;
+            if (fct_step(ctx, ctx->Avals, 1.0, nullptr, nullptr, u_traj + (i - 1) * n, dt, u_traj + i * n, nullptr)) return 1;
+        }
         k_sweeps_accumulate<<<1, 1, 0, ctx->stream>>>(ctx->jstate, ctx->jstate + 8);
         ctx->launches++;
     }
@@ -81,14 +88,18 @@ extern "C" int fct_advdrift_adjoint(fct_ctx* ctx, const double* c_traj, const do
     double* diff = ctx->w[10];
     double* rhs = ctx->w[11];
     for (int i = num_steps - 1; i >= 0; --i) {
-        if (assemble_drift_operator(ctx, c_traj + i * n, bx, by, eps, 1.0)) return 1;
+        if (eps != 0.0 && assemble_drift_operator(ctx, c_traj + i * n, bx, by, eps, 1.0)) return 1;
         // p_rhs = assemble((uhat_n - u_n) v dx) = M (uhat_n - u_n)     (:255)
         k_sub<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->n, uhat_traj + i * n, u_traj + i * n, diff);
         ctx->launches++;
         fct_set_ring(ctx, ctx->depth - 1);         // the FCT step wants its right-hand side on ring depth-1
         if (fct_spmv(ctx, ctx->M, diff, 1.0, 0.0, nullptr, rhs)) return 1;
         fct_set_ring(ctx, 0);
-        if (fct_step(ctx, ctx->Avals, 1.0, nullptr, rhs, p_traj + (i + 1) * n, dt, p_traj + i * n, nullptr)) return 1;
+        if (eps == 0.0) {
+            if (fct_step_drift(ctx, c_traj + i * n, bx, by, 1.0, rhs, p_traj + (i + 1) * n, dt, p_traj + i * n)) return 1;
+        } else {
+            if (fct_step(ctx, ctx->Avals, 1.0, nullptr, rhs, p_traj + (i + 1) * n, dt, p_traj + i * n, nullptr)) return 1;
+        }
         k_sweeps_accumulate<<<1, 1, 0, ctx->stream>>>(ctx->jstate, ctx->jstate + 8);
         ctx->launches++;
     }
@@ -169,8 +180,12 @@ extern "C" int fct_advdrift_state_host(fct_ctx* ctx, const double* c_host, doubl
         }
         TRY(cudaStreamWaitEvent(ctx->stream, c_ready[cb], 0));
         if (i >= 3) TRY(cudaStreamWaitEvent(ctx->stream, u_free[uo], 0));   // D2H of slice i-3 done
-        if (assemble_drift_operator(ctx, cbuf[cb], bx, by, eps, -1.0)) { cleanup(); return 1; }
-        if (fct_step(ctx, ctx->Avals, 1.0, nullptr, nullptr, ubuf[un], dt, ubuf[uo], nullptr)) { cleanup(); return 1; }
+        if (eps == 0.0) {
+            if (fct_step_drift(ctx, cbuf[cb], bx, by, -1.0, nullptr, ubuf[un], dt, ubuf[uo])) { cleanup(); return 1; }
+        } else {
+            if (assemble_drift_operator(ctx, cbuf[cb], bx, by, eps, -1.0)) { cleanup(); return 1; }
+            if (fct_step(ctx, ctx->Avals, 1.0, nullptr, nullptr, ubuf[un], dt, ubuf[uo], nullptr)) { cleanup(); return 1; }
+        }
         k_sweeps_accumulate<<<1, 1, 0, ctx->stream>>>(ctx->jstate, ctx->jstate + 8);
         ctx->launches++;
         TRY(cudaEventRecord(c_free[cb], ctx->stream));

@@ -1422,8 +1422,30 @@ int fct_read_step_info(fct_ctx* ctx, fct_step_info* info) {
     return 0;
 }
 
+int fct_drift_low_build(fct_ctx* ctx, const double* c, double bx, double by, double ascale, double sign, const double* rhs,
+                        const double* un, double dt, double* bvec, double* dinv_out);     // fct_assembly.cu
+
+// The FCT step.  drift_c != nullptr: A = ascale * drift operator of the control drift_c is not given but produced,
+// together with D, L and b, by the fused assembly pass (fct_assembly.cu) into ctx->Avals; A must then be ctx->Avals.
+static int fct_step_impl(fct_ctx* ctx, const double* A, double sign, const double* S, const double* rhs, const double* un,
+                         double dt, double* uout, fct_step_info* info, const double* drift_c, double bx, double by,
+                         double ascale);
+
 extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double* S, const double* rhs,
                         const double* un, double dt, double* uout, fct_step_info* info) {
+    return fct_step_impl(ctx, A, sign, S, rhs, un, dt, uout, info, nullptr, 0.0, 0.0, 0.0);
+}
+
+// One FCT step of the drift-control problem with A = ascale * [(b.grad c) u v + (b.grad v) c u] (eps = 0): assembly fused
+// into the low-order build when the mesh has geometry templates, else assemble + fct_step.
+int fct_step_drift(fct_ctx* ctx, const double* c, double bx, double by, double ascale, const double* rhs, const double* un,
+                   double dt, double* uout) {
+    return fct_step_impl(ctx, ctx->Avals, 1.0, nullptr, rhs, un, dt, uout, nullptr, c, bx, by, ascale);
+}
+
+static int fct_step_impl(fct_ctx* ctx, const double* A, double sign, const double* S, const double* rhs, const double* un,
+                         double dt, double* uout, fct_step_info* info, const double* drift_c, double bx, double by,
+                         double ascale) {
     FCT_CHECK(ctx && A && un && uout, "fct_step: null argument");
     FCT_CHECK(ctx->mass_set, "fct_step: static mass matrices not set (fct_ctx_set_mass / fct_assemble_static)");
     FCT_CHECK(sign == 1.0 || sign == -1.0, "fct_step: sign must be +1 (FCT_alg_ref) or -1 (FCT_alg)");
@@ -1442,7 +1464,20 @@ extern "C" int fct_step(fct_ctx* ctx, const double* A, double sign, const double
     const int K = ctx->depth;
     // 1-2. D, L, b on ring K-1
     fct_set_ring(ctx, K - 1);
-    {
+    bool built = false;
+    if (drift_c) {
+        const int rcf = fct_drift_low_build(ctx, drift_c, bx, by, ascale, sign, rhs, un, dt, bvec,
+                                            ctx->jac_mode == 2 ? nullptr : dinv);
+        if (rcf == 1) {
+            built = true;
+        } else {
+            // no geometry templates: assemble A (all local rows: the halo rows carry the transposed entries), then build
+            fct_set_ring(ctx, 0);
+            if (fct_assemble_matrix(ctx, FCT_FORM_DRIFT, drift_c, nullptr, nullptr, bx, by, ascale, 0, ctx->Avals)) return 1;
+            fct_set_ring(ctx, K - 1);
+        }
+    }
+    if (!built) {
         const int nf = S ? 2 : 1;
         double* dinv_out = ctx->jac_mode == 2 ? nullptr : dinv;      // the row-scaled sweeps never read 1/diag
         const size_t smem = FCT_NST_LOW * smem_bytes(ctx, nf, 1) + 2 * smem_bytes(ctx, 1, 0);

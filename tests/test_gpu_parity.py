@@ -453,3 +453,35 @@ def test_geometry_template_assembly_bit_identical(monkeypatch):
     # the quadrature-loop forms (8: CHTX_EXP, 9: CHTX_ADJ; 14: LOAD_CHTX_ADJ) leave nvcc a choice of which product of an
     # a*b + c*d it contracts into the FMA, and that choice may differ between two kernels: last-bit differences allowed
     assert all(i in (8, 9, 14) and d < 4e-16 for i, d in diffs), diffs
+
+
+def test_fused_drift_assembly_low_build(monkeypatch):
+    """The drift-control loops assemble the operator inside the low-order build (k_drift_low_build: a_ij and a_ji from the
+    same cells, no second pass over A).  Against the unfused path (FCT_NO_FUSED_DRIFT=1: k_assemble_matrix_tpl +
+    k_low_build) the transposed entries are evaluated in a different rotation of the cell, so the agreement is to
+    rounding, far inside the 1e-12 per-step tolerance; state, adjoint and gradient are compared."""
+    n, ns = 48, 4
+    h = 1.0 / n
+    dt = 0.25 * h / (2 * np.sqrt(2))
+    mesh = RectMeshP1(n, 0.0, 1.0)
+    xy = mesh.dof_xy
+    u0 = np.exp(-20 * ((2 * xy[:, 0] - 1 + 2 / 3) ** 2 + 5 * (2 * xy[:, 1] - 1 + 5 / 6) ** 2))
+    rng = np.random.default_rng(3)
+    c = 1.0 + rng.random((ns + 1, mesh.nodes))
+    uhat = np.array([u0 * (1.0 + 0.1 * k) for k in range(ns + 1)])
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("FCT_NO_FUSED_DRIFT", flag)
+        ctx = RectMeshP1(n, 0.0, 1.0).context()
+        assert ctx.geom_template_count() > 0
+        utr = np.zeros((ns + 1, mesh.nodes)); utr[0] = u0
+        dc, du, duh = ctx.array(c.ravel()), ctx.array(utr.ravel()), ctx.array(uhat.ravel())
+        dp, dd = ctx.empty(du.size), ctx.empty(du.size)
+        ctx.advdrift_state(dc, du, ns, dt)
+        ctx.advdrift_adjoint(dc, du, duh, dp, ns, dt)
+        ctx.advdrift_gradient(dc, du, dp, dd, ns, 0.01)
+        res[flag] = [a.download().reshape(ns + 1, -1) for a in (du, dp, dd)]
+    for a, b in zip(res["1"], res["0"]):
+        for i in range(ns + 1):
+            if np.abs(a[i]).max() > 0:
+                assert rel_l2(b[i], a[i]) < 2e-13, i
