@@ -13,6 +13,10 @@ Writes
                       /root/reference/helpers.py with dolfin/matplotlib stubbed (oracle/ref_loader.py):
                       FCT_alg_ref (4 cases incl. rhs / non_flux_mat / pruned zeros), ChebSI,
                       artificial_diffusion_mat, L2_norm_sq_Q, L2_norm_sq_Omega, cost_functional.
+  ref_armijo.npz      inputs + outputs of the reference's OWN armijo_line_search_ref (helpers.py:1583-1713), run
+                      unmodified with `assemble_sparse` returning the restated mass matrix and the oracle's time
+                      loops as `nonlinear_solver` callbacks (one-species final-time case, two-species all-time case,
+                      a case that exhausts max_iter).
 """
 import os
 import sys
@@ -134,6 +138,83 @@ def ref_fct_cases():
     out["norm_meta"] = np.array([ns, dt, 0.01])
     np.savez_compressed(os.path.join(HERE, "ref_fct_cases.npz"), **out)
     print("ref_fct_cases.npz written:", len(out), "arrays")
+
+
+def ref_armijo():
+    """The reference's projected Armijo search is host control flow around a solver callback and cost_functional;
+    it builds M itself through dolfin (helpers.py:1654-1660), which is the only thing patched here."""
+    import contextlib
+    import io
+    from oracle import pdeco_systems as osys
+    from oracle.fct_numpy import cost_functional as o_cost
+    hp = load_reference_helpers()
+
+    class _Sym:                       # stands in for TrialFunction / TestFunction / dx in `u*v*dx`
+        def __mul__(self, other): return self
+        __rmul__ = __mul__
+
+    out = {}
+    rng = np.random.default_rng(7)
+
+    def run(tag, prob, solver_ref, var1, c, d, target, ns, dt, lo, hi, beta, cost0, optim, **kw):
+        Mc = prob.pat.csr(prob.M)
+        saved = (hp.df.TrialFunction, hp.df.TestFunction, hp.dx, hp.assemble_sparse)
+        hp.df.TrialFunction = lambda V: _Sym()
+        hp.df.TestFunction = lambda V: _Sym()
+        hp.dx = _Sym()
+        hp.assemble_sparse = lambda form: Mc
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                res = hp.armijo_line_search_ref(var1, c, d, target, ns, dt, lo, hi, beta, cost0, prob.nodes, optim, None,
+                                                nonlinear_solver=solver_ref, dof_neighbors=None, **kw)
+        finally:
+            hp.df.TrialFunction, hp.df.TestFunction, hp.dx, hp.assemble_sparse = saved
+        out[f"{tag}_c"] = c; out[f"{tag}_d"] = d; out[f"{tag}_target"] = target
+        out[f"{tag}_meta"] = np.array([ns, dt, lo, hi, beta, cost0, kw.get("max_iter", 10)], dtype=np.float64)
+        out[f"{tag}_var1"] = np.asarray(res[0]).ravel()
+        out[f"{tag}_cinc"] = np.asarray(res[-2]).ravel()
+        out[f"{tag}_k"] = np.array([res[-1]])
+        if len(res) == 4:
+            out[f"{tag}_var2"] = np.asarray(res[1]).ravel()
+        print(tag, "armijo iterations:", res[-1])
+
+    # (a) one species, final-time tracking (nonlinear_FCT_PDECO_refactored.py:148-152)
+    n, ns, dt, beta = 10, 4, 2e-3, 0.1
+    prob = osys.NonlinearProblem(n, 0.0, 1.0)
+    u0 = prob.initial_condition()
+    c = rng.random((ns + 1) * prob.nodes)
+    u = prob.state(c, u0, ns, dt)
+    uhat_T = u[-1] + 0.05 * rng.random(prob.nodes)
+    p = prob.adjoint(u, uhat_T, ns, dt)
+    d = -(beta * c - p.ravel())
+    cost0 = o_cost(prob.pat, u.ravel(), uhat_T, c, ns, dt, prob.M, beta, "finaltime")
+    solver = lambda ci, v1, v2, V, nodes, num_steps, dt_, nb: (prob.state(ci, u0, num_steps, dt_).ravel(), None)
+    out["nl_u0"] = u0
+    run("nl", prob, solver, u.ravel().copy(), c, d, uhat_T, ns, dt, 0.0, 1.0, beta, cost0, "finaltime")
+    # (a'') an overshooting direction with wide bounds: the step is halved a few times before the condition holds
+    run("nlbt", prob, solver, u.ravel().copy(), c, 400.0 * d, uhat_T, ns, dt, -50.0, 50.0, beta, cost0, "finaltime")
+    # (a') the same search with a direction that never satisfies the condition: exhausts max_iter = 3
+    run("nlmax", prob, solver, u.ravel().copy(), c, -d, uhat_T, ns, dt, 0.0, 1.0, beta, cost0, "finaltime", max_iter=3)
+
+    # (b) two species, all-time tracking (Schnak_FCT_PDECO_refactored.py:167-178)
+    n, ns, dt, beta = 8, 3, 1e-3, 0.05
+    prob2 = osys.SchnakProblem(n, 0.0, 1.0)
+    u0, v0 = prob2.initial_condition()
+    c2 = 0.5 + rng.random((ns + 1) * prob2.nodes)
+    uu, vv = prob2.state(c2, u0, v0, ns, dt)
+    uhat = uu.ravel() + 0.01 * rng.random(uu.size)
+    vhat = vv.ravel() + 0.01 * rng.random(vv.size)
+    d2 = rng.random(c2.size) - 0.5
+    cost0 = o_cost(prob2.pat, uu.ravel(), uhat, c2, ns, dt, prob2.M, beta, "alltime", var2=vv.ravel(), var2_target=vhat)
+
+    def solver2(ci, v1, v2, V, nodes, num_steps, dt_, nb):
+        a, b = prob2.state(ci, u0, v0, num_steps, dt_)
+        return a.ravel(), b.ravel()
+    out["sk_u0"] = u0; out["sk_v0"] = v0; out["sk_target2"] = vhat
+    run("sk", prob2, solver2, uu.ravel().copy(), c2, d2, uhat, ns, dt, 0.0, 5.0, beta, cost0, "alltime",
+        var2=vv.ravel().copy(), var2_target=vhat)
+    np.savez_compressed(os.path.join(HERE, "ref_armijo.npz"), **out)
+    print("ref_armijo.npz written:", len(out), "arrays")
 
 
 if __name__ == "__main__":

@@ -97,3 +97,43 @@ def test_solidbody_golden_t025(ref_data):
     prob = drv.SolidBodyProblem(80, -1.0, 1.0, slit_width=0.05)
     u = prob.forward(400, 0.025 ** 2)
     assert rel_l2(u, ref_data["solidbody_t0.25"]) < 1e-13
+
+
+# ---- the reference's own projected Armijo search (helpers.py:1583-1713) --------------------------------------
+@pytest.fixture(scope="module")
+def ref_armijo():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_armijo.npz"))
+
+
+@pytest.mark.parametrize("tag,expect_k", [("nl", 1), ("nlbt", 6), ("nlmax", 3), ("sk", 10)])
+def test_armijo_ref_vs_reference_function(ref_armijo, tag, expect_k):
+    """oracle/pdeco_systems.armijo_ref against outputs of the reference's armijo_line_search_ref (run unmodified in the
+    build container by tests/golden/make_golden.py:ref_armijo with the oracle's time loops as solver callbacks): same
+    number of trials, bit-identical accepted control, same state trajectories."""
+    from oracle import pdeco_systems as osys
+    from oracle.fct_numpy import cost_functional as o_cost  # noqa: F401
+    g = ref_armijo
+    ns, dt, lo, hi, beta, cost0, max_iter = g[f"{tag}_meta"]
+    ns, max_iter = int(ns), int(max_iter)
+    assert int(g[f"{tag}_k"][0]) == expect_k
+    if tag == "sk":
+        prob = osys.SchnakProblem(8, 0.0, 1.0)
+        u0, v0 = g["sk_u0"], g["sk_v0"]
+
+        def solver(ci):
+            a, b = prob.state(ci, u0, v0, ns, dt)
+            return a.ravel(), b.ravel()
+        v1, v2, cinc, k = osys.armijo_ref(prob, solver, None, g["sk_c"], g["sk_d"], g["sk_target"], ns, dt, lo, hi, beta, cost0,
+                                          "alltime", max_iter=max_iter, var2=np.zeros(1), var2_target=g["sk_target2"])
+        assert rel_l2(v2, g["sk_var2"]) < 1e-13
+    else:
+        prob = osys.NonlinearProblem(10, 0.0, 1.0)
+        u0 = g["nl_u0"]
+        solver = lambda ci: (prob.state(ci, u0, ns, dt).ravel(), None)
+        v1, v2, cinc, k = osys.armijo_ref(prob, solver, None, g[f"{tag}_c"], g[f"{tag}_d"], g[f"{tag}_target"], ns, dt, lo, hi,
+                                          beta, cost0, "finaltime", max_iter=max_iter)
+        assert v2 is None
+    assert k == expect_k
+    assert np.array_equal(cinc, g[f"{tag}_cinc"])
+    assert rel_l2(v1, g[f"{tag}_var1"]) < 1e-13
