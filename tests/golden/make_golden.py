@@ -13,6 +13,10 @@ Writes
                       /root/reference/helpers.py with dolfin/matplotlib stubbed (oracle/ref_loader.py):
                       FCT_alg_ref (4 cases incl. rhs / non_flux_mat / pruned zeros), ChebSI,
                       artificial_diffusion_mat, L2_norm_sq_Q, L2_norm_sq_Omega, cost_functional.
+  ref_legacy.npz      inputs + outputs of the reference's OWN legacy FCT_alg (old_helpers.py:112-204, an import-less
+                      fragment: its source is executed unmodified in the namespace of the reference's helpers.py, which
+                      provides numpy / scipy and ChebSI / artificial_diffusion_mat / sparse_nonzero): two cases, one with
+                      source_mat and a right-hand side.
   ref_armijo.npz      inputs + outputs of the reference's OWN armijo_line_search_ref (helpers.py:1583-1713), run
                       unmodified with `assemble_sparse` returning the restated mass matrix and the oracle's time
                       loops as `nonlinear_solver` callbacks (one-species final-time case, two-species all-time case,
@@ -140,6 +144,53 @@ def ref_fct_cases():
     print("ref_fct_cases.npz written:", len(out), "arrays")
 
 
+def ref_legacy():
+    """old_helpers.py has no imports; FCT_alg's source text is compiled as it stands."""
+    import contextlib
+    import io
+    hp = load_reference_helpers()
+    src = open(os.path.join(REFERENCE_DIR, "old_helpers.py")).read().splitlines()
+    start = next(i for i, l in enumerate(src) if l.startswith("def FCT_alg("))
+    ns = dict(vars(hp))
+    exec(compile("\n".join(src[start:]), "old_helpers.py:FCT_alg", "exec"), ns)
+    FCT_alg = ns["FCT_alg"]
+    rng = np.random.default_rng(11)
+    out = {}
+
+    def run_case(tag, n, a1, a2, A_legacy, rhs, u_n, dt, S):
+        mesh = RectMesh(n, a1, a2); asm = P1Assembler(mesh); pat = Pattern(*mesh.pattern())
+        Ml = lil_matrix(pat.csr(asm.mass()))
+        MLl = hp.row_lump(Ml, mesh.nodes)
+        Ain = pat.csr(A_legacy); Ain.eliminate_zeros()
+        Sin = None if S is None else pat.csr(S)
+        with contextlib.redirect_stdout(io.StringIO()):
+            u1 = FCT_alg(Ain, rhs, u_n, dt, mesh.nodes, Ml, MLl, mesh.dof_neighbors(), source_mat=Sin)
+        out[f"{tag}_n"] = np.array([n]); out[f"{tag}_box"] = np.array([a1, a2], dtype=np.float64)
+        out[f"{tag}_A"] = A_legacy; out[f"{tag}_rhs"] = rhs; out[f"{tag}_un"] = u_n; out[f"{tag}_dt"] = np.array([dt])
+        out[f"{tag}_S"] = np.zeros(0) if S is None else S
+        out[f"{tag}_out"] = np.asarray(u1).ravel()
+        print(tag, "legacy FCT_alg done", mesh.nodes)
+
+    # (a) solid-body rotation + drift, legacy sign as in advection_solidbody_FCT.py:106-148
+    n, a1, a2 = 14, -1.0, 1.0
+    mesh = RectMesh(n, a1, a2); asm = P1Assembler(mesh)
+    om = np.pi / 40
+    xy = mesh.dof_xy
+    A_u = asm.conv_conservative_p1(-xy[:, 1] / om + 2, xy[:, 0] / om + 2)
+    u_n = (np.hypot(xy[:, 0], xy[:, 1] - 1 / 3) < 1 / 3).astype(np.float64)
+    run_case("lsolid", n, a1, a2, A_u, np.zeros(mesh.nodes), u_n, (2.0 / n) ** 2 / 4, None)
+    # (b) Schnakenberg-like legacy call with source_mat and a right-hand side (Schnak_FCT_PDECO.py:205)
+    n, a1, a2 = 10, 0.0, 1.0
+    mesh = RectMesh(n, a1, a2); asm = P1Assembler(mesh)
+    wind = lambda x, y: ((y - 0.5) * x * (1 - x), -(x - 0.5) * y * (1 - y))
+    Aw = asm.conv_conservative(wind, degree=5)
+    u_n = 1.0 + 0.1 * np.cos(2 * np.pi * (mesh.dof_xy[:, 0] + mesh.dof_xy[:, 1])) + 0.01 * rng.random(mesh.nodes)
+    rhs = asm.load_p1_product(u_n, u_n, scale=230.82) + asm.load_constant(23.082)
+    run_case("lschnak", n, a1, a2, -(0.01 * asm.stiffness() - 100 * Aw), rhs, u_n, 1e-3, 230.82 * asm.mass())
+    np.savez_compressed(os.path.join(HERE, "ref_legacy.npz"), **out)
+    print("ref_legacy.npz written:", len(out), "arrays")
+
+
 def ref_armijo():
     """The reference's projected Armijo search is host control flow around a solver callback and cost_functional;
     it builds M itself through dolfin (helpers.py:1654-1660), which is the only thing patched here."""
@@ -220,3 +271,5 @@ def ref_armijo():
 if __name__ == "__main__":
     ref_data()
     ref_fct_cases()
+    ref_legacy()
+    ref_armijo()

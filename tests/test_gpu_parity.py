@@ -485,3 +485,20 @@ def test_fused_drift_assembly_low_build(monkeypatch):
         for i in range(ns + 1):
             if np.abs(a[i]).max() > 0:
                 assert rel_l2(b[i], a[i]) < 2e-13, i
+
+
+@pytest.mark.parametrize("tag", ["lsolid", "lschnak"])
+def test_FCT_alg_matches_reference_legacy_function(tag):
+    """helpers.FCT_alg (legacy name and sign convention, source_mat) against outputs of the reference's own legacy
+    function, executed unmodified from old_helpers.py:112-204 (tests/golden/ref_legacy.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_legacy.npz"))
+    n = int(g[f"{tag}_n"][0]); a1, a2 = g[f"{tag}_box"]
+    mesh, asm, pat = _oracle(n, a1, a2)
+    M = sp.lil_matrix(pat.csr(asm.mass()))
+    ML = sp.lil_matrix((mesh.nodes, mesh.nodes)); ML.setdiag(asm.lumped(asm.mass()))
+    A = pat.csr(g[f"{tag}_A"]); A.eliminate_zeros()
+    S = pat.csr(g[f"{tag}_S"]) if g[f"{tag}_S"].size else None
+    out = helpers.FCT_alg(A, g[f"{tag}_rhs"], g[f"{tag}_un"], float(g[f"{tag}_dt"][0]), mesh.nodes, M, ML,
+                          mesh.dof_neighbors(), source_mat=S)
+    assert rel_l2(out, g[f"{tag}_out"]) < TOL_STEP

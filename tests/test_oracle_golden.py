@@ -137,3 +137,22 @@ def test_armijo_ref_vs_reference_function(ref_armijo, tag, expect_k):
     assert k == expect_k
     assert np.array_equal(cinc, g[f"{tag}_cinc"])
     assert rel_l2(v1, g[f"{tag}_var1"]) < 1e-13
+
+
+# ---- the reference's own legacy FCT_alg (old_helpers.py:112-204) -------------------------------------------------
+@pytest.mark.parametrize("tag", ["lsolid", "lschnak"])
+def test_fct_step_legacy_vs_reference_legacy_function(tag):
+    """The legacy sign convention (M du/dt = A u - S u + r) pinned on the legacy function itself, executed unmodified from
+    old_helpers.py by tests/golden/make_golden.py:ref_legacy -- not only through FCT_alg(A, S) == FCT_alg_ref(-A, S)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_legacy.npz"))
+    n = int(g[f"{tag}_n"][0]); a1, a2 = g[f"{tag}_box"]
+    mesh, asm, pat = _setup(n, a1, a2)
+    M = asm.mass()
+    S = g[f"{tag}_S"] if g[f"{tag}_S"].size else None
+    out = fct_step_legacy(pat, g[f"{tag}_A"], g[f"{tag}_rhs"], g[f"{tag}_un"], float(g[f"{tag}_dt"][0]), M, asm.lumped(M),
+                          source=S)
+    assert rel_l2(out, g[f"{tag}_out"]) < 1e-13
+    # and the identity the drop-in relies on
+    out2 = fct_step(pat, -g[f"{tag}_A"], g[f"{tag}_rhs"], g[f"{tag}_un"], float(g[f"{tag}_dt"][0]), M, asm.lumped(M), S=S)
+    assert np.array_equal(out, out2)
