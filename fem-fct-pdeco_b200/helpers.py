@@ -277,3 +277,27 @@ from .solvers import (armijo_line_search_ref, armijo_line_search_sbr_drift, chtx
 
 # UFL-like front end for the reference's assemble_sparse(form) / assemble(form) call sites (fem-fct-pdeco_b200/forms.py)
 from .forms import assemble, assemble_sparse, assemble_sparse_lil, vec_to_function  # noqa: E402,F401
+
+
+# ---- legacy Mimura form builders the config-3 script calls through `from helpers import *` -----------------------------
+def rhs_chtx_f(f_fun, m_fun, c_fun, dt, v):
+    """old_helpers.py:90-91 (chemotaxis_mimura_FCT_PGD.py:175)"""
+    from .forms import dx
+    return np.asarray(assemble(f_fun * v * dx + dt * m_fun * c_fun * v * dx))
+
+
+def rhs_chtx_p(c_fun, q_fun, v):
+    """old_helpers.py:93-94 (chemotaxis_mimura_FCT_PGD.py:223)"""
+    from .forms import dx
+    return np.asarray(assemble(c_fun * q_fun * v * dx))
+
+
+def rhs_chtx_q(q_fun, m_fun, p_fun, chi, dt, v):
+    """old_helpers.py:96-98 (chemotaxis_mimura_FCT_PGD.py:216): assemble(q v dx + dt div(chi m grad p) v dx).
+    For P1 fields div(chi m grad p) = chi grad m . grad p cell-wise (the Laplacian of a P1 function vanishes), and
+    int (grad m . grad p) phi_i = sum_j p_j int (grad m . grad phi_j) phi_i = (C(m)^T p)_i with the catalogue matrix
+    C(m) = assemble_sparse(dot(grad(m), grad(v)) * u * dx) -- so the load needs no kernel of its own."""
+    from .forms import dot, dx, grad, TrialFunction
+    u = TrialFunction(v.V)
+    C = assemble_sparse(dot(grad(m_fun), grad(v)) * u * dx)
+    return np.asarray(assemble(q_fun * v * dx)) + dt * chi * (C.T @ p_fun.vec)

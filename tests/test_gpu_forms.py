@@ -112,3 +112,43 @@ def test_script_advection_solidbody_FCT():
     ref = orc.forward(num_steps, dt, keep=True)
     for i in range(1, num_steps + 1):
         assert rel_l2(uk[i * nodes:(i + 1) * nodes], ref[i]) < 1e-12 * i
+
+
+def test_mimura_legacy_form_builders():
+    """config 3 (chemotaxis_mimura_FCT_PGD.py:175-225): the legacy form builders of old_helpers.py:87-111 and
+    mimura_data_helpers.py:65-109, by name, against the oracle's assembler"""
+    from fem_fct_pdeco_b200 import mimura_data_helpers as mdh
+    n = 9
+    mesh = RectMeshP1(n, 0.0, 16.0)
+    V = FunctionSpaceP1(mesh)
+    om = RectMesh(n, 0.0, 16.0)
+    asm, pat = P1Assembler(om), Pattern(*om.pattern())
+    rng = np.random.default_rng(12)
+    f, m, c, q, p = [1.0 + rng.random(V.dim()) for _ in range(5)]
+    F, Mf, Cf, Q, P = [vec_to_function(x, V) for x in (f, m, c, q, p)]
+    u, v = TrialFunction(V), TestFunction(V)
+    dt, chi, Dm = 0.1, 8.5, 0.0625
+    Mmat = pat.csr(asm.mass())
+    K = asm.stiffness()
+    assert _relmax(mdh.rhs_chtx_m(Mf, v), asm.load_p1_product(m, m) - asm.load_p1_product(m, m, m)) < 1e-13
+    assert _relmax(mdh.rhs_chtx_f(F, Mf, dt, v), Mmat @ f + dt * (Mmat @ m)) < 1e-13
+    assert _relmax(hp.rhs_chtx_f(F, Mf, Cf, dt, v), Mmat @ f + dt * asm.load_p1_product(m, c)) < 1e-13
+    assert _relmax(hp.rhs_chtx_p(Cf, Q, v), asm.load_p1_product(c, q)) < 1e-13
+    Aa_exp = asm.chemotaxis_conv(f, lambda phi, xy: np.exp(-0.5 * asm.at_quad(m, phi)), degree=4)
+    Am = mdh.mat_chtx_m(F, Mf, Dm, chi, u, v)
+    assert _relmax(pat.embed(Am), -Dm * K + chi * Aa_exp) < 1e-13
+    Ap = mdh.mat_chtx_p(F, Mf, Dm, chi, u, v)
+    assert _relmax(pat.embed(Ap), -Dm * K - chi * asm.chemotaxis_conv(f)) < 1e-13
+    # rhs_chtx_q: q v + dt chi (grad m . grad p) v, checked cell by cell
+    xy, cells = om.dof_xy, om.cells
+    load = np.zeros(V.dim())
+    for T in cells:
+        (x0, y0), (x1, y1), (x2, y2) = xy[T]
+        det = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0)
+        gx = np.array([y1 - y2, y2 - y0, y0 - y1]) / det
+        gy = np.array([x2 - x1, x0 - x2, x1 - x0]) / det
+        gm = np.array([gx @ m[T], gy @ m[T]]); gp = np.array([gx @ p[T], gy @ p[T]])
+        load[T] += (gm @ gp) * abs(det) / 6.0
+    assert _relmax(hp.rhs_chtx_q(Q, Mf, P, chi, dt, v), Mmat @ q + dt * chi * load) < 1e-12
+    # (m_initial_condition is pure numpy and is compared with the reference's own function on the CPU:
+    # tests/test_host_shims_vs_reference.py)

@@ -129,3 +129,17 @@ def test_cost_functional_error_behaviour(ref):
     with pytest.raises(ValueError) as e_new:
         helpers.cost_functional(x, x, x, 1, 0.1, M, 0.1, "sometimes")
     assert str(e_new.value) == str(e_ref.value)
+
+
+def test_mimura_initial_condition_vs_reference():
+    """mimura_data_helpers.m_initial_condition (config 3, chemotaxis_mimura_FCT_PGD.py:98): the reference's function is
+    executed from its source (its module imports dolfin/matplotlib at the top; only the function text is compiled)"""
+    import re
+    from fem_fct_pdeco_b200 import mimura_data_helpers as mdh
+    from oracle.ref_loader import REFERENCE_DIR
+    src = open(os.path.join(REFERENCE_DIR, "mimura_data_helpers.py")).read()
+    m = re.search(r"^def m_initial_condition\(.*?(?=^def )", src, flags=re.S | re.M)
+    ns = {"np": np}
+    exec(compile(m.group(0), "mimura_data_helpers.py:m_initial_condition", "exec"), ns)
+    for a1, a2, dx in ((0.0, 16.0, 0.125), (0.0, 1.0, 0.1)):
+        assert np.array_equal(mdh.m_initial_condition(a1, a2, dx), ns["m_initial_condition"](a1, a2, dx))
