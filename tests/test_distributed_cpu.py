@@ -110,7 +110,7 @@ def test_halo_exchange_ranges_gloo(world):
     assert all(ret.get(r) == "ok" for r in range(world))
 
 
-@pytest.mark.parametrize("depth", [2, 4])
+@pytest.mark.parametrize("depth", [2, 4, 8])
 def test_deep_halo_rings(depth):
     """depth-k halos: nested ring ranges, rows of ring k-1 complete, local cells = cells touching ring k-1,
     send ranges cover the neighbour's (k rings wide) halo with owned rows only"""
