@@ -39,20 +39,6 @@ def step_bytes(n, nnz, cells, k_j):
     return (344 + 12 * k_j) * nnz + (1108 + 28 * k_j) * n + 12 * cells
 
 
-def pass_bytes(n, nnz, cells, nt, k_state, k_adj):
-    """algorithmic bytes of one bench step (gradient-iteration pass over nt time levels), same accounting unit:
-    state + adjoint FCT steps, the adjoint right-hand side M(uhat-u), the gradient slices (load vector + SpMV + 20
-    Chebyshev iterations each) and the two cost-functional norms"""
-    V = 8 * n
-    spmv = 12 * nnz + 4 * n + 3 * V
-    cheb20 = 20 * (12 * nnz + 4 * n + 5 * V)
-    adj_rhs = 3 * V + spmv
-    grad = (12 * cells + 3 * V) + spmv + cheb20
-    dots = 2 * (nt + 1) * (12 * nnz + 4 * n + 4 * V)
-    return (nt * step_bytes(n, nnz, cells, k_state) + nt * (step_bytes(n, nnz, cells, k_adj) + adj_rhs)
-            + (nt + 1) * grad + dots)
-
-
 def cheb_iter_bytes(n, nnz):
     """one Chebyshev iteration: M values + column indices + rowptr + 5 vectors (App. E, P4)"""
     return 12 * nnz + 4 * n + 5 * 8 * n
@@ -160,6 +146,16 @@ def cpu_port_steps_per_s(cells_full, sample_cells, nsteps, cores=None):
 CPU_SAMPLE_CELLS, CPU_SAMPLE_STEPS = 1024, 3
 CPU_C_STEPS = 3
 _C_PROBLEM = {}
+BETA, C_LOWER, C_UPPER = 0.01, 0.0, 5.0      # advection_solidbody_FCT_PDECO_alltime.py:47-50
+
+
+def workload_string(cells):
+    """ONE workload name for both arms (the driver compares the strings)"""
+    N = cells + 1
+    n = N * N
+    nnz = n + 2 * (2 * N * (N - 1) + (N - 1) ** 2)
+    return (f"synthetic {cells}^2-cell unit-square drift-control advection FCT PDECO (BASELINE config 5): "
+            f"{n} DoF, {nnz} nnz, fp64")
 
 
 def _cpu_sample_text(cells_full, sample, nsteps, cores, sps_sample, wall):
@@ -168,42 +164,59 @@ def _cpu_sample_text(cells_full, sample, nsteps, cores, sps_sample, wall):
             f"incl. set-up; scaled by the DoF ratio to {cells_full}^2")
 
 
-def cpu_c_port(cells_full, nsteps):
+def synth_fields(xy):
+    """initial condition and (time-constant) initial control of config 5 in DoF order"""
+    x, y = 2 * xy[:, 0] - 1, 2 * xy[:, 1] - 1
+    u0 = np.exp(-20 * ((x + 2 / 3) ** 2 + 5 * (y + 5 / 6) ** 2))
+    c = 1.0 + 0.25 * np.sin(3 * xy[:, 0]) * np.cos(2 * xy[:, 1])
+    return u0, c
+
+
+def synth_target_slice(xy, k, dt):
+    """target state at time level k: the IC translated by the exact drift of the constant control c = 2"""
+    x, y = 2 * xy[:, 0] - 1, 2 * xy[:, 1] - 1
+    s = 2.0 * k * dt * 2          # shift in [-1,1] coordinates
+    return np.exp(-20 * ((x - s + 2 / 3) ** 2 + 5 * (y - s + 5 / 6) ** 2))
+
+
+def cpu_c_port(cells_full, nsteps, keep=False):
     """CPU arm, preferred: the C/OpenMP twin of the oracle (oracle/fct_c.c, pinned on the numpy oracle by
     tests/test_oracle_c.py) runs `nsteps` FCT state steps of the FULL-size problem on all host cores -- the same
     workload as the GPU arm (drift-operator assembly + FCT step with the Jacobi low-order solve), no extrapolation.
-    Returns (steps/s, seconds of the step loop, threads, jacobi sweeps per step) or None when no C compiler works."""
+    Returns (steps/s, seconds of the step loop, threads, jacobi sweeps per step, problem, trajectory | None) or None
+    when no C compiler works."""
     try:
-        from oracle.fct_c import CDriftProblem
+        from oracle import fct_c
+        fct_c.lib(native=True)
+        threads = fct_c.use_all_host_threads()          # not OMP_NUM_THREADS: torchrun exports 1 to its ranks
         prob = _C_PROBLEM.get(cells_full)
         if prob is None:
-            prob = _C_PROBLEM[cells_full] = CDriftProblem(cells_full, 0.0, 1.0)
+            prob = _C_PROBLEM[cells_full] = fct_c.CDriftProblem(cells_full, 0.0, 1.0)
     except Exception as e:  # noqa: BLE001
         sys.stderr.write(f"bench.py: C/OpenMP oracle unavailable ({e}); using the numpy port\n")
         return None
-    xy = prob.dof_xy
-    u0 = np.exp(-20 * ((2 * xy[:, 0] - 1 + 2 / 3) ** 2 + 5 * (2 * xy[:, 1] - 1 + 5 / 6) ** 2))
-    c = 1.0 + 0.25 * np.sin(3 * xy[:, 0]) * np.cos(2 * xy[:, 1])
+    u0, c = synth_fields(prob.dof_xy)
     dt = 0.25 * (1.0 / cells_full) / (2 * np.sqrt(2))
     t0 = time.perf_counter()
-    _, sweeps = prob.state(np.tile(c, nsteps + 1), u0, nsteps, dt)
+    traj, sweeps = prob.state(np.tile(c, nsteps + 1), u0, nsteps, dt)
     el = time.perf_counter() - t0
-    return nsteps / el, el, prob.threads(), sweeps / nsteps
+    return nsteps / el, el, threads, sweeps / nsteps, prob, (traj if keep else None)
 
 
-def cpu_baseline_record(cells_full, nsteps=CPU_C_STEPS):
-    """(value steps/s, dict for the `cpu_baseline` key, wall seconds of the sample)"""
-    r = cpu_c_port(cells_full, nsteps)
+def cpu_baseline_record(cells_full, nsteps=CPU_C_STEPS, keep=False):
+    """(value steps/s, dict for the `cpu_baseline` key, wall seconds of the sample, (problem, trajectory) | None)"""
+    r = cpu_c_port(cells_full, nsteps, keep)
     if r is not None:
-        sps, el, threads, kj = r
+        sps, el, threads, kj, prob, traj = r
         txt = (f"C/OpenMP port of the oracle (oracle/fct_c.c: drift-operator assembly + FCT step, Jacobi low-order solve, "
                f"{kj:.1f} sweeps/step) on {threads} host threads: {nsteps} FCT state steps of the full {cells_full}^2-cell "
                f"problem in {el:.1f} s, no extrapolation")
-        return sps, {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port", "sample": txt}, el
+        return sps, {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port", "sample": txt}, el, \
+            ((prob, traj) if keep else None)
     sample = min(cells_full, CPU_SAMPLE_CELLS)
     sps, sps_sample, wall, cores = cpu_port_steps_per_s(cells_full, sample, CPU_SAMPLE_STEPS)
     return sps, {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
-                 "sample": _cpu_sample_text(cells_full, sample, CPU_SAMPLE_STEPS, cores, sps_sample, wall)}, wall
+                 "sample": _cpu_sample_text(cells_full, sample, CPU_SAMPLE_STEPS, cores, sps_sample, wall)}, wall, None
 
 
 def run_reference_arm(args):
@@ -222,7 +235,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "FCT steps/sec", "value": sps, "unit": "steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([r[2] for r in res])),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic {args.cells}^2-cell unit-square advection FCT PDECO (BASELINE config 5)"},
+            "config": {"workload": workload_string(args.cells)},
             "cpu_baseline": cb,
             "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -232,18 +245,80 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
-def synth_problem(mesh, nt, dt):
-    """config 5: Gaussian IC, initial control c = 1 (+ a smooth perturbation so that the
-    drift-mass term is exercised), target = the IC translated by the exact drift of c = 2."""
-    xy = mesh.dof_xy
-    x, y = 2 * xy[:, 0] - 1, 2 * xy[:, 1] - 1
-    u0 = np.exp(-20 * ((x + 2 / 3) ** 2 + 5 * (y + 5 / 6) ** 2))
-    c = 1.0 + 0.25 * np.sin(3 * xy[:, 0]) * np.cos(2 * xy[:, 1])
-    uhat = []
-    for k in range(nt + 1):
-        s = 2.0 * k * dt * 2          # shift in [-1,1] coordinates
-        uhat.append(np.exp(-20 * ((x - s + 2 / 3) ** 2 + 5 * (y - s + 5 / 6) ** 2)))
-    return u0, c, np.array(uhat)
+PARITY_TOL_FIELD, PARITY_TOL_COST = 1e-12, 1e-9      # BASELINE.json north_star: rel-L2 per time step, final cost
+
+
+def parity_vs_cpu_port(ctx, prob, cpu_traj, dt):
+    """the GPU state trajectory against the C/OpenMP oracle port on the SAME full-size inputs
+    (u0, c, dt of the CPU leg): rel-L2 per time step <= 1e-12, cost functional <= 1e-9 (relative)."""
+    ns = cpu_traj.shape[0] - 1
+    n = prob.nodes
+    u0, c = synth_fields(prob.dof_xy)
+    d_c = ctx.array(np.tile(c, ns + 1))
+    utr = np.zeros((ns + 1) * n); utr[:n] = u0
+    d_u = ctx.array(utr)
+    ctx.advdrift_state(d_c, d_u, ns, dt)
+    gpu = d_u.download().reshape(ns + 1, n)
+    errs = [float(np.linalg.norm(gpu[k] - cpu_traj[k]) / np.linalg.norm(cpu_traj[k])) for k in range(1, ns + 1)]
+    uhat = np.array([synth_target_slice(prob.dof_xy, k, dt) for k in range(ns + 1)])
+    d_uhat = ctx.array(uhat.ravel())
+    M = ctx.static()[0]
+    J_gpu = 0.5 * ctx.norm_sq_Q(M, d_u, ns, dt, target=d_uhat) + BETA / 2 * ctx.norm_sq_Q(M, d_c, ns, dt)
+    J_cpu = 0.5 * prob.norm_sq_Q(cpu_traj, ns, dt, target=uhat) + BETA / 2 * prob.norm_sq_Q(np.tile(c, ns + 1), ns, dt)
+    for a in (d_c, d_u, d_uhat):
+        a.free()
+    cost_rel = abs(J_gpu - J_cpu) / abs(J_cpu)
+    ok = bool(max(errs) <= PARITY_TOL_FIELD and cost_rel <= PARITY_TOL_COST)
+    return {"against": "oracle/fct_c.c (C/OpenMP port of the oracle) on the same u0, c, dt at full size",
+            "time_steps": ns, "rel_l2_per_step": errs, "tol_rel_l2": PARITY_TOL_FIELD, "cost_gpu": J_gpu, "cost_cpu": J_cpu,
+            "cost_rel_diff": cost_rel, "tol_cost": PARITY_TOL_COST, "ok": ok}
+
+
+def load_kernel_profile():
+    """per-kernel ncu figures of one FCT step at HEAD (profiles/r2_kernels.json, written by tools/kernels_table.py
+    from an `ncu` capture of tools/kprof_step.py): {kernel: {launches, ms, dram_bytes, GBs, pct_of_peak}}"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_kernels.json")))
+    except Exception:  # noqa: BLE001
+        return None
+
+
+class GradientIteration:
+    """one projected-gradient iteration of advection_solidbody_FCT_PDECO_alltime.py:196-303 on device trajectories:
+    state sweep, adjoint sweep, gradient (N_t+1 load vectors + ChebSI), ONE Armijo trial (clip, forward solve, cost,
+    ||c_inc - c||^2), cost functional.  The control is not updated, so every bench step does identical work."""
+
+    def __init__(self, ctx, n, nt, dt, d_c, d_u, d_uhat):
+        self.ctx, self.n, self.nt, self.dt = ctx, n, nt, dt
+        L = (nt + 1) * n
+        self.d_c, self.d_u, self.d_uhat = d_c, d_u, d_uhat
+        self.d_p, self.d_d = ctx.empty(L), ctx.empty(L)
+        self.d_cinc, self.d_utrial = ctx.empty(L), ctx.empty(L)
+        ctx.axpby(1.0, d_u, 0.0, None, self.d_utrial, length=n)      # IC of the trial trajectory
+        self.M = ctx.static()[0]
+        self.sweeps = []
+        self.J = self.J_trial = None
+
+    def cost(self, d_u, d_c):
+        ctx = self.ctx
+        return (0.5 * ctx.norm_sq_Q(self.M, d_u, self.nt, self.dt, target=self.d_uhat)
+                + BETA / 2 * ctx.norm_sq_Q(self.M, d_c, self.nt, self.dt))
+
+    def __call__(self):
+        ctx, nt, dt = self.ctx, self.nt, self.dt
+        s1 = ctx.advdrift_state(self.d_c, self.d_u, nt, dt)
+        s2 = ctx.advdrift_adjoint(self.d_c, self.d_u, self.d_uhat, self.d_p, nt, dt)
+        ctx.advdrift_gradient(self.d_c, self.d_u, self.d_p, self.d_d, nt, BETA)
+        self.J = self.cost(self.d_u, self.d_c)
+        # Armijo trial k = 0 (old_helpers.py:40-80): s = 1, c_inc = clip(c + s d), forward solve, cost, ||c_inc - c||^2_Q
+        ctx.clip_axpy(self.d_c, 1.0, self.d_d, C_LOWER, C_UPPER, self.d_cinc)
+        s3 = ctx.advdrift_state(self.d_cinc, self.d_utrial, nt, dt)
+        self.J_trial = self.cost(self.d_utrial, self.d_cinc)
+        self.cdiff = ctx.norm_sq_Q(self.M, self.d_cinc, nt, dt, target=self.d_c)
+        self.sweeps.append((s1, s2, s3))
+        return self.J
+
+    fct_steps_per_pass = property(lambda self: 3 * self.nt)
 
 
 def run_gpu_arm(args):
@@ -262,150 +337,125 @@ def run_gpu_arm(args):
     n_cells, nt = args.cells, args.nt
     h = 1.0 / n_cells
     dt = 0.25 * h / (2 * np.sqrt(2))
-    beta = 0.01
     t_setup = time.perf_counter()
     mesh = RectMeshP1(n_cells, 0.0, 1.0)
     ctx = mesh.context(device=local_rank)
     n, nnz, ncell = mesh.nodes, mesh.nnz, mesh.ncells
-    u0, c0, uhat = synth_problem(mesh, nt, dt)
-    M = ctx.static()[0]
+    u0, c0 = synth_fields(mesh.dof_xy)
     L = (nt + 1) * n
-    d_c = ctx.array(np.tile(c0, nt + 1))
-    utr = np.zeros(L); utr[:n] = u0
-    d_u = ctx.array(utr)
-    d_uhat = ctx.array(uhat.ravel())
-    d_p, d_d = ctx.empty(L), ctx.empty(L)
-    del utr
+    d_c, d_u, d_uhat = ctx.empty(L), ctx.empty(L), ctx.empty(L)
+    for k in range(nt + 1):          # slice by slice: no (nt+1) x n host arrays
+        d_c.slice(k * n, n).upload(c0)
+        d_uhat.slice(k * n, n).upload(synth_target_slice(mesh.dof_xy, k, dt))
+    d_u.slice(0, n).upload(u0)
+    it = GradientIteration(ctx, n, nt, dt, d_c, d_u, d_uhat)
     t_setup = time.perf_counter() - t_setup
 
-    sweeps_hist = []
-
-    def gradient_pass():
-        s1 = ctx.advdrift_state(d_c, d_u, nt, dt)
-        s2 = ctx.advdrift_adjoint(d_c, d_u, d_uhat, d_p, nt, dt)
-        ctx.advdrift_gradient(d_c, d_u, d_p, d_d, nt, beta)
-        J = 0.5 * ctx.norm_sq_Q(M, d_u, nt, dt, target=d_uhat) + beta / 2 * ctx.norm_sq_Q(M, d_c, nt, dt)
-        sweeps_hist.append((s1, s2))
-        return J
-
     for _ in range(args.warmup):
-        gradient_pass()
+        it()
     ctx.sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = ctx.launch_count()
     e0, e1 = ctx.event(), ctx.event()
-    del sweeps_hist[:]
+    del it.sweeps[:]
     ctx.record(e0)
     for _ in range(args.steps):
-        J = gradient_pass()
+        J = it()
     ctx.record(e1)
     ms = ctx.elapsed_ms(e0, e1)
     launches = ctx.launch_count() - l0
-    fct_steps = 2 * nt * args.steps
+    fct_steps = it.fct_steps_per_pass * args.steps
     value = fct_steps / (ms * 1e-3)
-    k_state = np.mean([s[0] for s in sweeps_hist]) / nt
-    k_adj = np.mean([s[1] for s in sweeps_hist]) / nt
+    k_state = np.mean([s[0] for s in it.sweeps]) / nt
+    k_adj = np.mean([s[1] for s in it.sweeps]) / nt
+    k_trial = np.mean([s[2] for s in it.sweeps]) / nt
 
-    # ---- kernels timed live with CUDA events on the library's stream ---------------------------------
-    # dominant kernel: the Jacobi sweep of the low-order solve (k_J ~ 14 launches per FCT step).  Algorithmic bytes per
-    # sweep = 12 nnz + 4 n + 3 V (App. E, P3).
+    # ---- a state sweep on its own (what `e2e` is the host-buffer twin of) ---------------------------------------
+    ctx.record(e0)
+    ctx.advdrift_state(d_c, d_u, nt, dt)
+    ctx.record(e1)
+    state_ms = ctx.elapsed_ms(e0, e1) / nt
+
+    # ---- dominant kernel timed live with CUDA events on the library's stream -----------------------------------
     peak, peak_src = _peaks()
-    A_tmp = ctx.empty(nnz)
-    ctx.assemble_matrix(2, A_tmp, c0=d_c.slice(0, n), s0=1.0, s1=1.0, scale=-1.0)       # FCT_FORM_DRIFT, state sign
-    jac_ms = ctx.bench_jacobi_sweeps(A_tmp, d_u.slice(0, n), dt, reps=20)
-    A_tmp.free()
-    jb = 12 * nnz + 4 * n + 3 * 8 * n
-    jac_gbs = jb / (jac_ms * 1e-3) / 1e9
-    # what the template-column, row-scaled sweep actually moves: 8 B/nnz values + 2 B/row code + 4 B/row rowptr + b, x, x_new
-    jb_actual = (8 * nnz + 6 * n + 3 * 8 * n) if ctx.template_count() else jb
+    kern = ctx.bench_dominant_kernel(d_c.slice(0, n), d_u.slice(0, n), dt)
+    kprof = load_kernel_profile()
+    dom = kern["name"]
     traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_jacobi_sweep_tpl"]
-        traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"]) if ctx.template_count() else None
-    except Exception:
-        pass
-    # second kernel: one Chebyshev iteration.  With the mass matrix on row templates it moves 2 B/row + 5 V instead of
-    # the 12 B/nnz of the accounting unit, so its "algorithmic" rate exceeds the HBM peak; both figures are given.
-    Md = ctx.static()[2]
-    b, y = d_d.slice(0, n), d_p.slice(0, n)        # scratch slices (overwritten by the next pass anyway)
-    reps = 5
-    ctx.chebsi(M, Md, b, y, 20)
-    ctx.record(e0)
-    for _ in range(reps):
-        ctx.chebsi(M, Md, b, y, 20)
-    ctx.record(e1)
-    t20 = ctx.elapsed_ms(e0, e1)
-    ctx.record(e0)
-    for _ in range(reps):
-        ctx.chebsi(M, Md, b, y, 1)                   # the vector-only first iteration (k_cheb_first)
-    ctx.record(e1)
-    t1 = ctx.elapsed_ms(e0, e1)
-    cheb_ms = (t20 - t1) / (reps * 19)               # 19 matrix iterations per ChebSI call
-    cb = cheb_iter_bytes(n, nnz)
-    ntpl = ctx.template_count()
-    cb_actual = (2 * n + 4 * 8 * n) if ntpl else cb     # code + g, y_k (gathered), y_{k-1}, y_{k+1}; diag(M) from the table
+    if kprof and dom in kprof.get("kernels", {}):
+        traffic = kprof["kernels"][dom].get("dram_bytes_per_launch")
+    ach = kern["bytes_per_launch"] / (kern["ms_per_launch"] * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C-ABI (H2D of control slices, D2H of state slices inside) -----
-    hc = ctx.pinned(L); hu = ctx.pinned(L)
-    hc[:] = np.tile(c0, nt + 1); hu[:] = 0.0; hu[:n] = u0
-    ctx.advdrift_state_host(hc, hu, nt, dt)          # warm-up
+    nt_e2e = min(nt, args.e2e_nt)
+    Le = (nt_e2e + 1) * n
+    hc = ctx.pinned(Le); hu = ctx.pinned(Le)
+    hc.reshape(nt_e2e + 1, n)[:] = c0
+    hu[:] = 0.0; hu[:n] = u0
+    ctx.advdrift_state_host(hc, hu, nt_e2e, dt)          # warm-up
     t0 = time.perf_counter()
     reps_e2e = max(1, args.steps // 2)
     for _ in range(reps_e2e):
-        ctx.advdrift_state_host(hc, hu, nt, dt)      # synchronises before returning
+        ctx.advdrift_state_host(hc, hu, nt_e2e, dt)      # synchronises before returning
     e2e_s = time.perf_counter() - t0
-    e2e_value = nt * reps_e2e / e2e_s
+    e2e_value = nt_e2e * reps_e2e / e2e_s
     clocks = sampler.stop()
 
-    # whole-step roofline (algorithmic bytes of an FCT step with the sweeps actually executed)
-    k_mean = 0.5 * (k_state + k_adj)
+    k_mean = (k_state + k_adj + k_trial) / 3
     step_gb = step_bytes(n, nnz, ncell, k_mean) / 1e9
-    pass_gb = pass_bytes(n, nnz, ncell, nt, k_state, k_adj) / 1e9
     line = {
         "metric": "FCT steps/sec", "value": value, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {n_cells}^2-cell unit-square drift-control advection FCT PDECO "
-                               f"(BASELINE config 5): {n} DoF, {nnz} nnz; bench step = state+adjoint sweeps over "
-                               f"{nt} time levels + gradient + cost",
-                   "time_levels": nt, "dt": dt, "l2_flush": "working set per pass >> L2 (matrix values alone are "
-                   f"{8 * nnz / 1e6:.0f} MB)", "jacobi_sweeps_per_step": {"state": k_state, "adjoint": k_adj},
-                   "cost_functional": J, "setup_s": t_setup},
-        "roofline": {"bound": "hbm", "kernel": "k_jacobi_sweep_tpl (low-order solve, ~14 launches per FCT step)",
-                     "achieved": jac_gbs, "peak": peak, "unit": "GB/s", "frac": jac_gbs / peak, "traffic": traffic,
-                     "peak_source": peak_src, "bytes_per_launch": jb, "ms_per_launch": jac_ms,
-                     "actual_bytes_per_launch": jb_actual, "actual_GBs": jb_actual / (jac_ms * 1e-3) / 1e9,
-                     "actual_frac_of_peak": jb_actual / (jac_ms * 1e-3) / 1e9 / peak,
-                     "note": "achieved = algorithmic bytes of SURVEY App. E (12 B/nnz CSR sweep) / measured time; the kernel "
-                             "takes the column pattern from the row templates and moves fewer bytes (actual_*; traffic = "
-                             "ncu dram bytes of one launch, profiles/r1_traffic.json)"},
-        "roofline_chebsi": {"kernel": "k_cheb_iter_tpl" if ntpl else "k_cheb_iter", "ms_per_launch": cheb_ms,
-                            "row_templates": ntpl, "algorithmic_bytes_per_launch": cb,
-                            "algorithmic_GBs": cb / (cheb_ms * 1e-3) / 1e9,
-                            "actual_bytes_per_launch": cb_actual, "actual_GBs": cb_actual / (cheb_ms * 1e-3) / 1e9,
-                            "actual_frac_of_peak": cb_actual / (cheb_ms * 1e-3) / 1e9 / peak,
-                            "note": "row templates replace the 12 B/nnz CSR read of the static mass matrix by a 16-bit "
-                                    "code per row; results are bit-identical to the CSR kernel"},
-        "step_roofline": {"algorithmic_GB_per_fct_step": step_gb, "achieved_GBs": step_gb * value,
-                          "frac": step_gb * value / peak,
-                          "note": "FCT-step bytes only, against the whole pass time (which also contains the gradient "
-                                  "and cost work)"},
-        "pass_roofline": {"algorithmic_GB_per_pass": pass_gb, "achieved_GBs": pass_gb / (ms / args.steps * 1e-3),
-                          "frac": pass_gb / (ms / args.steps * 1e-3) / peak,
-                          "note": "all work of the pass (state + adjoint sweeps, gradient, cost) in the accounting "
-                                  "unit of SURVEY.md App. E; fusions move fewer actual bytes than that"},
+        "config": {"workload": workload_string(n_cells),
+                   "bench_step": f"one projected-gradient iteration over {nt} time levels: state sweep + adjoint sweep + "
+                                 f"gradient ({nt + 1} load vectors + ChebSI) + one Armijo trial (clip, forward sweep, cost) "
+                                 f"+ cost functional = {it.fct_steps_per_pass} FCT steps, device-resident",
+                   "time_levels": nt, "dt": dt, "l2_flush": "working set per FCT step >> L2 (matrix values alone are "
+                   f"{8 * nnz / 1e6:.0f} MB per array)",
+                   "jacobi_sweeps_per_step": {"state": k_state, "adjoint": k_adj, "armijo_trial": k_trial},
+                   "cost_functional": J, "cost_trial": it.J_trial, "setup_s": t_setup},
+        "roofline": {"bound": "hbm", "kernel": dom, "what": kern["what"],
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                     "peak_source": peak_src, "bytes_per_launch": kern["bytes_per_launch"],
+                     "bytes_model": kern["bytes_model"], "ms_per_launch": kern["ms_per_launch"],
+                     "traffic_frac_of_peak": (traffic / (kern["ms_per_launch"] * 1e-3) / 1e9 / peak) if traffic else None,
+                     "appE_bytes_per_launch": kern["appE_bytes"],
+                     "appE_GBs": kern["appE_bytes"] / (kern["ms_per_launch"] * 1e-3) / 1e9,
+                     "note": "achieved = the bytes this kernel has to move per launch (bytes_model; DESIGN.md 4) / CUDA-event "
+                             "time; traffic = ncu dram__bytes_read+write of one launch (profiles/r2_kernels.json); appE_* = the "
+                             "SURVEY App. E accounting unit for the work this launch replaces (not a bound for this "
+                             "implementation: templates and fusion delete bytes from it)"},
+        "state_step": {"ms": state_ms, "steps_per_s": 1e3 / state_ms,
+                       "note": "one FCT state step (assembly + low-order solve + ChebSI + limiter), device-resident"},
+        "step_roofline": {"appE_GB_per_fct_step": step_gb, "note": "SURVEY App. E accounting unit, for reference only"},
+        "kernels": (kprof or {}).get("kernels"),
+        "kernels_source": (kprof or {}).get("source"),
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                "time_levels": nt_e2e,
                 "call": "fct_advdrift_state_host (state sweep, pinned host trajectories)"},
-        "templates": {"mass_rows": ntpl, "geometry": ctx.geom_template_count()},
+        "templates": {"mass_rows": ctx.template_count(), "geometry": ctx.geom_template_count()},
         "gpu_launches": int(launches),
-        "gpu_launches_note": "host-enqueued kernels of libfctpdeco in the timed region; the Jacobi sweeps run as a CUDA-graph "
-                             "WHILE body and are counted once per solve (executed sweeps: jacobi_sweeps_per_step)",
+        "gpu_launches_note": "host-enqueued kernels of libfctpdeco in the timed region; CUDA-graph WHILE bodies are counted "
+                             "once per solve (executed sweeps: jacobi_sweeps_per_step)",
         "clocks": clocks,
     }
+    rc = 0
     if not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline_record(n_cells)[1]
+        _, cb, _, kept = cpu_baseline_record(n_cells, keep=True)
+        line["cpu_baseline"] = cb
+        if kept is not None:
+            prob, traj = kept
+            line["parity"] = parity_vs_cpu_port(ctx, prob, traj, dt)
+            if not line["parity"]["ok"]:
+                sys.stderr.write("bench.py: PARITY VIOLATED against the oracle port at full size\n")
+                rc = 3
+        else:
+            line["parity"] = None
     print(json.dumps(line))
+    if rc:
+        raise SystemExit(rc)
 
 
 def main():
@@ -415,7 +465,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=4096, help="cells per side (4096 = BASELINE config 5)")
-    ap.add_argument("--nt", type=int, default=4, help="time levels per bench step")
+    ap.add_argument("--nt", type=int, default=50, help="time levels per bench step (SURVEY.md 8d: 50)")
+    ap.add_argument("--e2e-nt", type=int, default=50, help="time levels of the host-trajectory (e2e) sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
     procs = []
     for s in SOURCES:
         obj = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", "/usr/include", "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False

@@ -111,6 +111,11 @@ class FctContext:
         check(lib.fct_launch_count(self.handle, C.byref(c)))
         return c.value
 
+    def exchange_count(self):
+        c = C.c_int64()
+        check(lib.fct_exchange_count(self.handle, C.byref(c)))
+        return c.value
+
     # -- buffers ----------------------------------------------------------------------------
     def empty(self, size):
         return DeviceArray(self, size)
@@ -289,6 +294,26 @@ class FctContext:
         ms = C.c_float()
         check(lib.fct_bench_jacobi_sweeps(self.handle, A.ptr, u_n.ptr, float(dt), int(reps), C.byref(ms)))
         return ms.value
+
+    def bench_dominant_kernel(self, c, u_n, dt):
+        """CUDA-event time of the kernel with the largest share of an FCT step (the low-order Jacobi sweep) on the drift
+        operator of control `c`, with the bytes it has to move per launch and the SURVEY App. E accounting
+        bytes of the same work; bench.py's `roofline`"""
+        n, nnz = self.n, self.nnz
+        A = self.empty(nnz)
+        self.assemble_matrix(_lib.FORM_DRIFT, A, c0=c, s0=1.0, s1=1.0, scale=-1.0)
+        ms = self.bench_jacobi_sweeps(A, u_n, dt, reps=20)
+        A.free()
+        appE = 12 * nnz + 4 * n + 3 * 8 * n
+        if self.template_count():
+            return {"name": "k_jacobi_sweep_tpl", "ms_per_launch": ms, "appE_bytes": appE,
+                    "what": "one Jacobi sweep of the low-order solve (~14 launches per FCT step)",
+                    "bytes_per_launch": 8 * nnz + 2 * n + 4 * n + 3 * 8 * n,
+                    "bytes_model": "8 B/nnz row-scaled L values + 2 B/row template code + 4 B/row rowptr + b, x (gathered), "
+                                   "x_new: 3 x 8 B/row"}
+        return {"name": "k_jacobi_sweep", "ms_per_launch": ms, "appE_bytes": appE, "bytes_per_launch": appE,
+                "what": "one Jacobi sweep of the low-order solve (CSR kernel)",
+                "bytes_model": "12 B/nnz values + column indices, 4 B/row rowptr, 3 x 8 B/row vectors"}
 
     def debug_jacobi_fixed(self, A, u_n, dt, sweeps, fused, x_out):
         check(lib.fct_debug_jacobi_fixed(self.handle, A.ptr, u_n.ptr, float(dt), int(sweeps), int(fused), x_out.ptr))

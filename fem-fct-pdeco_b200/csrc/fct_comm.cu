@@ -10,7 +10,15 @@
 #include "../../include/fctpdeco.h"
 
 #include <dlfcn.h>
-#include <nccl.h>
+
+// The handful of NCCL 2.x declarations this file needs, stated locally (ABI-stable since NCCL 2.0) so that the library
+// builds on machines without the NCCL development headers; the functions themselves are resolved with dlsym below.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
+typedef enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5, ncclFloat16 = 6,
+               ncclFloat32 = 7, ncclFloat64 = 8, ncclDouble = 8 } ncclDataType_t;
 
 struct NcclApi {
     void* handle = nullptr;
@@ -130,6 +138,7 @@ int fct_p2p_exchange(fct_ctx* ctx, double* v0, double* v1);
 
 int fct_halo_exchange_if(fct_ctx* ctx, double* vec) {
     if (!ctx->comm || ctx->comm->world == 1) return 0;
+    if (!ctx->capturing) ctx->exchanges++;
     if (fct_p2p_ready(ctx)) return fct_p2p_exchange(ctx, vec, nullptr);
     return exchange_ranges(ctx, vec, ctx->send_lo[0], ctx->send_lo[1], 0, ctx->row_begin, ctx->send_hi[0],
                            ctx->send_hi[1], ctx->row_end, ctx->n);

@@ -131,6 +131,7 @@ struct fct_ctx {
     double rtol = 1e-14;
     int32_t max_sweeps = 100;
     int64_t launches = 0;
+    int64_t exchanges = 0;      // halo exchanges enqueued by the host (NCCL path; the peer-memory path counts on the device)
     fct_jgraph jgraph;
     fct_hoststage hs;
     bool use_pdl = false;       // FCT_PDL=1 enables programmatic dependent launch (measured: no gain, persistent grids)

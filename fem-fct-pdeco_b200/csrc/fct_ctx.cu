@@ -267,6 +267,13 @@ extern "C" int fct_ctx_pattern_dev(fct_ctx* ctx, const int32_t** rp, const int32
 }
 
 int fct_row_lump_diag(fct_ctx* ctx, const double* mat, double* out, double* diag);
+
+// jstate[10] = the sweep count before which the Jacobi stopping test is not attempted, learnt from the previous solve;
+// a new operator family, solver option or halo depth starts without it
+static int fct_reset_check_from(fct_ctx* ctx) {
+    FCT_CUDA(cudaMemsetAsync(ctx->jstate + 10, 0, sizeof(unsigned long long), ctx->stream));
+    return 0;
+}
 int fct_halo_exchange_if(fct_ctx* ctx, double* vec);
 
 extern "C" int fct_ctx_set_mass(fct_ctx* ctx, const double* M_dev) {
@@ -277,6 +284,7 @@ extern "C" int fct_ctx_set_mass(fct_ctx* ctx, const double* M_dev) {
     if (fct_halo_exchange_if(ctx, ctx->ML)) return 1;
     if (fct_halo_exchange_if(ctx, ctx->Mdiag)) return 1;
     ctx->mass_set = true;
+    if (fct_reset_check_from(ctx)) return 1;
     return fct_templates_build(ctx);
 }
 
@@ -293,7 +301,7 @@ extern "C" int fct_ctx_set_solver(fct_ctx* ctx, double rtol, int32_t max_sweeps)
     FCT_CHECK(ctx && rtol > 0 && max_sweeps >= 2, "fct_ctx_set_solver: bad argument");
     ctx->rtol = rtol;
     ctx->max_sweeps = max_sweeps;
-    return 0;
+    return fct_reset_check_from(ctx);
 }
 
 extern "C" int fct_malloc(fct_ctx* ctx, void** p, int64_t bytes) {
@@ -322,6 +330,15 @@ extern "C" int fct_d2h(fct_ctx* ctx, void* dst, const void* src, int64_t bytes) 
 extern "C" int fct_launch_count(fct_ctx* ctx, int64_t* count) {
     FCT_CHECK(ctx && count, "fct_launch_count: null argument");
     *count = ctx->launches;
+    return 0;
+}
+
+int fct_p2p_exchange_count(fct_ctx* ctx, int64_t* count);     // fct_p2p.cu
+
+extern "C" int fct_exchange_count(fct_ctx* ctx, int64_t* count) {
+    FCT_CHECK(ctx && count, "fct_exchange_count: null argument");
+    *count = ctx->exchanges;
+    if (ctx->p2p) return fct_p2p_exchange_count(ctx, count);
     return 0;
 }
 
@@ -388,7 +405,7 @@ extern "C" int fct_ctx_set_rings(fct_ctx* ctx, int32_t depth, const int32_t* rin
     ctx->depth = depth;
     for (int j = 0; j <= depth; ++j) { ctx->ring_lo[j] = ring_lo[j]; ctx->ring_hi[j] = ring_hi[j]; }
     for (int j = depth + 1; j < 9; ++j) { ctx->ring_lo[j] = 0; ctx->ring_hi[j] = ctx->n; }
-    return 0;
+    return fct_reset_check_from(ctx);
 }
 
 extern "C" int fct_template_count(fct_ctx* ctx, int32_t* count) {

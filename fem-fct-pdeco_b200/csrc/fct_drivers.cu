@@ -26,7 +26,10 @@ static int acc_reset(fct_ctx* ctx) {
     FCT_CUDA(cudaMemsetAsync(ctx->jstate + 8, 0, 2 * sizeof(unsigned long long), ctx->stream));
     return 0;
 }
+int fct_p2p_check(fct_ctx* ctx, const char* what);      // fct_p2p.cu
+
 static int acc_read(fct_ctx* ctx, int32_t* total_sweeps_host) {
+    if (fct_p2p_check(ctx, "time loop")) return 1;
     if (!total_sweeps_host) return 0;
     unsigned long long h[2];
     FCT_CUDA(cudaMemcpyAsync(h, ctx->jstate + 8, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));

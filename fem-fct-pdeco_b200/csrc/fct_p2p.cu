@@ -82,9 +82,13 @@ k_halo_xchg(unsigned char* mine, unsigned char* peer_lo, unsigned char* peer_hi,
             P2PHeader* PH = reinterpret_cast<P2PHeader*>(peer);
             st_release_sys(dir == 0 ? &PH->flag_hi[slot] : &PH->flag_lo[slot], seq);
         }
-        // wait for the neighbour's message and unpack it into my halo entries
+        // wait for the neighbour's message and unpack it into my halo entries; once a wait has timed out the context is
+        // in error (the host fails the call at its next synchronisation point, fct_p2p_check) and later exchanges do not
+        // spend another time-out each
         __shared__ int ok;
-        if (threadIdx.x == 0) ok = wait_flag(dir == 0 ? &H->flag_lo[slot] : &H->flag_hi[slot], seq) ? 1 : 0;
+        if (threadIdx.x == 0)
+            ok = (*reinterpret_cast<volatile unsigned long long*>(&H->error) == 0ull &&
+                  wait_flag(dir == 0 ? &H->flag_lo[slot] : &H->flag_hi[slot], seq)) ? 1 : 0;
         __syncthreads();
         if (ok) {
             const double* src = mail_ptr(mine, dir, slot, max_halo);
@@ -119,10 +123,13 @@ k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, uns
     const int t = threadIdx.x;
     // nothing to exchange when already converged, or before the sweep count at which the previous solve converged
     // (jstate[10], identical on every rank) -- the all-to-all is only paid for the last one or two tests of a solve
-    const bool skip = jstate[3] != 0ull || jstate[4] < jstate[10];
+    const bool skip = jstate[3] != 0ull || (jstate[4] < jstate[10] && jstate[4] < max_sweeps);
     unsigned long long a = 0ull, b = 0ull;
-    bool ok = true;
-    if (!skip && t < world) {
+    bool ok = *reinterpret_cast<volatile unsigned long long*>(&H->error) == 0ull;
+    __shared__ int failed;
+    if (t == 0) failed = 0;
+    __syncthreads();
+    if (!skip && t < world && ok) {
         if (t != rank) {
             P2PHeader* PH = reinterpret_cast<P2PHeader*>(peers[t]);
             PH->red_val[rank][slot][0] = jstate[0];
@@ -138,8 +145,15 @@ k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, uns
         }
     }
     m0[t] = a; m1[t] = b;
+    if (!ok) { failed = 1; H->error = 1ull; }
     __syncthreads();
     if (t == 0) {
+        if (failed) {
+            // a peer's words never arrived: do not decide on partial data -- leave the solve unconverged, end the graph
+            // loop (every further test would time out again) and let the host fail the call (fct_p2p_check)
+            if (use_handle) cudaGraphSetConditional(handle, 0u);
+            return;
+        }
         if (!skip) {
             for (int i = 1; i < world; ++i) { a = a > m0[i] ? a : m0[i]; b = b > m1[i] ? b : m1[i]; }
             const double delta = __longlong_as_double((long long)a);
@@ -158,7 +172,6 @@ k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, uns
         if (jstate[3] == 0ull) { jstate[0] = 0ull; jstate[1] = 0ull; }    // restart the running maxima
         if (use_handle) cudaGraphSetConditional(handle, (jstate[3] != 0ull || jstate[4] >= max_sweeps) ? 0u : 1u);
     }
-    if (!ok) H->error = 1ull;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -248,6 +261,27 @@ int fct_p2p_max2_decide(fct_ctx* ctx, double rtol, int max_sweeps, int use_handl
                                                  p->peer[5], p->peer[6], p->peer[7], p->rank, p->world, ctx->jstate, rtol,
                                                  (unsigned long long)max_sweeps, use_handle, handle);
     ctx->launches++;
+    return 0;
+}
+
+// Called wherever the host already synchronises with the stream (fct_read_step_info, the sweep-count read-back of the
+// time loops, fct_norm_sq_Q ...): a timed-out peer wait fails the call instead of leaving stale halo data behind.
+int fct_p2p_check(fct_ctx* ctx, const char* what) {
+    if (!ctx->p2p) return 0;
+    unsigned long long e = 0;
+    FCT_CUDA(cudaMemcpyAsync(&e, ctx->p2p->region + offsetof(P2PHeader, error), sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+    FCT_CHECK(e == 0, "%s: a peer-memory halo exchange / stopping test timed out (a neighbouring rank did not arrive within "
+              "~2 s): results are invalid", what);
+    return 0;
+}
+
+// halo exchanges executed so far on this context (device counter: exchanges inside CUDA-graph bodies are counted too)
+int fct_p2p_exchange_count(fct_ctx* ctx, int64_t* count) {
+    unsigned long long x = 0;
+    FCT_CUDA(cudaMemcpyAsync(&x, ctx->p2p->region + offsetof(P2PHeader, xseq), sizeof(x), cudaMemcpyDeviceToHost, ctx->stream));
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+    *count = (int64_t)x;
     return 0;
 }
 

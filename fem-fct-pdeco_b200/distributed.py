@@ -12,6 +12,7 @@ issued by libfctpdeco (fct_ctx_init_comm / fct_halo_exchange).
 import ctypes as C
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -202,6 +203,78 @@ def setup_rank(mesh, rank, world, local_rank, depth=None):
 
 
 # ------------------------------------------------------------------------------------------------------
+# N ranks against one rank: the row-wise summation order does not depend on the partition, so fields must agree bit for bit
+# ------------------------------------------------------------------------------------------------------
+def mgpu_parity_check(cells, ns, rank, world, local_rank, depth=None, seed=5):
+    """Every rank runs its row block of the drift-control state / adjoint / gradient loops on a `cells`^2 mesh (deep halos,
+    peer-memory or NCCL exchanges, all-rank Jacobi stopping test); rank 0 also runs the same problem on a single-GPU
+    context and compares the gathered owned trajectories.  Needs an initialised torch.distributed process group.
+    Returns on rank 0 a dict (u_equal, p_equal, d_equal bit-identity flags, J_rel, host_path_equal, p2p_error, ok), on
+    the other ranks {"ok": <the same verdict>}."""
+    import torch
+    import torch.distributed as dist
+    from .mesh import RectMeshP1
+
+    mesh = RectMeshP1(cells, 0.0, 1.0)
+    lp, ctx = setup_rank(mesh, rank, world, local_rank, depth=depth)
+    dt = 0.25 * (1.0 / cells) / (2 * np.sqrt(2))
+    xy = mesh.dof_xy
+    x, y = 2 * xy[:, 0] - 1, 2 * xy[:, 1] - 1
+    u0 = np.exp(-20 * ((x + 2 / 3) ** 2 + 5 * (y + 5 / 6) ** 2))
+    rng = np.random.default_rng(seed)
+    c = 1.0 + rng.random((ns + 1, mesh.nodes))
+    uhat = np.array([np.exp(-20 * ((x - 0.1 * k + 2 / 3) ** 2 + 5 * (y - 0.1 * k + 5 / 6) ** 2)) for k in range(ns + 1)])
+
+    def run(cx, scatter):
+        utr = np.zeros((ns + 1, mesh.nodes)); utr[0] = u0
+        dc, du, duh = cx.array(scatter(c.ravel())), cx.array(scatter(utr.ravel())), cx.array(scatter(uhat.ravel()))
+        dp, dd = cx.empty(du.size), cx.empty(du.size)
+        sw = cx.advdrift_state(dc, du, ns, dt)
+        cx.advdrift_adjoint(dc, du, duh, dp, ns, dt)
+        cx.advdrift_gradient(dc, du, dp, dd, ns, 0.01)
+        M = cx.static()[0]
+        J = 0.5 * cx.norm_sq_Q(M, du, ns, dt, target=duh) + 0.005 * cx.norm_sq_Q(M, dc, ns, dt)
+        out = du.download(), dp.download(), dd.download(), J, sw
+        for a in (dc, du, duh, dp, dd):
+            a.free()
+        return out
+
+    u, p, d, J, sw = run(ctx, lp.scatter)
+    # host-trajectory entry point on the partitioned context: same local trajectory, bit for bit
+    utr0 = np.zeros((ns + 1, mesh.nodes)); utr0[0] = u0
+    uh = np.ascontiguousarray(lp.scatter(utr0.ravel()))
+    ctx.advdrift_state_host(np.ascontiguousarray(lp.scatter(c.ravel())), uh, ns, dt)
+    host_ok = bool(np.array_equal(uh, u))
+    perr = p2p_error(ctx) if world > 1 else 0
+    parts = [None] * world
+    dist.all_gather_object(parts, [np.ascontiguousarray(lp.owned(a)) for a in (u, p, d)])
+    flags = torch.tensor([1 if host_ok else 0, 1 if perr == 0 else 0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    res = {"ok": True}
+    if rank == 0:
+        ug, pg, dg = [np.concatenate([parts[r][i] for r in range(world)], axis=1) for i in range(3)]
+        ctx1 = mesh.context(device=local_rank)
+        u1, p1, d1, J1, sw1 = run(ctx1, lambda a: a)
+        u1, p1, d1 = [a.reshape(ns + 1, -1) for a in (u1, p1, d1)]
+        res = {"cells": cells, "time_steps": ns, "ranks": world, "halo_depth": lp.depth,
+               "u_equal": bool(np.array_equal(ug, u1)), "p_equal": bool(np.array_equal(pg, p1)),
+               "d_equal": bool(np.array_equal(dg, d1)), "J_rel": abs(J / J1 - 1), "sweeps": [int(sw), int(sw1)],
+               "halo_rows": [int(lp.row_begin), int(lp.n - lp.row_end)],
+               "host_path_equal": bool(int(flags[0].item())), "p2p_error_free": bool(int(flags[1].item()))}
+        res["ok"] = bool(res["u_equal"] and res["p_equal"] and res["d_equal"] and res["J_rel"] < 1e-13
+                         and res["host_path_equal"] and res["p2p_error_free"])
+        ctx1.close()
+        mesh._ctx = None
+    v = torch.tensor([1 if res["ok"] else 0], device="cuda")
+    dist.broadcast(v, src=0)
+    res["ok"] = bool(int(v.item()))
+    ctx.sync()
+    dist.barrier()
+    ctx.close()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------
 # bench.py, N > 1: strong scaling of BASELINE config 5 (one process per GPU, launched by torchrun)
 # ------------------------------------------------------------------------------------------------------
 def bench_multi(args, rank, world, local_rank):
@@ -214,35 +287,31 @@ def bench_multi(args, rank, world, local_rank):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     import bench as bench_mod            # the repo-root bench.py (synthetic problem + JSON helpers)
 
+    # N ranks vs 1 rank, bit for bit, on a mesh the single-GPU twin finishes in a moment (driver-visible parity of the
+    # multi-GPU path; the full-size single-GPU run carries the parity against the oracle)
+    mg = mgpu_parity_check(min(args.cells, 1024), 3, rank, world, local_rank)
+
     n_cells, nt = args.cells, args.nt
     h = 1.0 / n_cells
     dt = 0.25 * h / (2 * np.sqrt(2))
-    beta = 0.01
     mesh = RectMeshP1(n_cells, 0.0, 1.0)
     lp, ctx = setup_rank(mesh, rank, world, local_rank)
-    u0, c0, uhat = bench_mod.synth_problem(mesh, nt, dt)
+    u0, c0 = bench_mod.synth_fields(mesh.dof_xy)
     n_glob, nnz_glob, ncell = mesh.nodes, mesh.nnz, mesh.ncells
     n = lp.n
-    M = ctx.static()[0]
-    d_c = ctx.array(np.tile(lp.scatter(c0), nt + 1))
-    utr = np.zeros((nt + 1, n)); utr[0] = lp.scatter(u0)
-    d_u = ctx.array(utr.ravel())
-    d_uhat = ctx.array(lp.scatter(uhat.ravel()))
     L = (nt + 1) * n
-    d_p, d_d = ctx.empty(L), ctx.empty(L)
-    del mesh, utr
-    sweeps_hist = []
-
-    def gradient_pass():
-        s1 = ctx.advdrift_state(d_c, d_u, nt, dt)
-        s2 = ctx.advdrift_adjoint(d_c, d_u, d_uhat, d_p, nt, dt)
-        ctx.advdrift_gradient(d_c, d_u, d_p, d_d, nt, beta)
-        J = 0.5 * ctx.norm_sq_Q(M, d_u, nt, dt, target=d_uhat) + beta / 2 * ctx.norm_sq_Q(M, d_c, nt, dt)
-        sweeps_hist.append((s1, s2))
-        return J
+    d_c, d_u, d_uhat = ctx.empty(L), ctx.empty(L), ctx.empty(L)
+    xy_loc = np.ascontiguousarray(mesh.dof_xy[lp.G0:lp.G1])
+    c_loc, u0_loc = lp.scatter(c0), lp.scatter(u0)
+    for k in range(nt + 1):
+        d_c.slice(k * n, n).upload(c_loc)
+        d_uhat.slice(k * n, n).upload(bench_mod.synth_target_slice(xy_loc, k, dt))
+    d_u.slice(0, n).upload(u0_loc)
+    del mesh
+    it = bench_mod.GradientIteration(ctx, n, nt, dt, d_c, d_u, d_uhat)
 
     for _ in range(args.warmup):
-        gradient_pass()
+        it()
     ctx.sync()
     dist.barrier()
     torch.cuda.synchronize()
@@ -250,11 +319,11 @@ def bench_multi(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count()
-    del sweeps_hist[:]
+    del it.sweeps[:]
     e0, e1 = ctx.event(), ctx.event()
     ctx.record(e0)
     for _ in range(args.steps):
-        J = gradient_pass()
+        J = it()
     ctx.record(e1)
     ms = ctx.elapsed_ms(e0, e1)
     dist.barrier()
@@ -265,52 +334,72 @@ def bench_multi(args, rank, world, local_rank):
     launches = ctx.launch_count() - l0
     lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
     dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    xch = ctx.exchange_count()
     # e2e: the state sweep through the host-buffer entry point, every rank streaming its own local range (pinned host
     # memory; control slices H2D, state slices D2H inside the timed region); wall clock between barriers, max over ranks
-    hc, hu = ctx.pinned(L), ctx.pinned(L)
-    hc[:] = np.tile(lp.scatter(c0), nt + 1)
+    nt_e2e = min(nt, args.e2e_nt)
+    Le = (nt_e2e + 1) * n
+    hc, hu = ctx.pinned(Le), ctx.pinned(Le)
+    hc.reshape(nt_e2e + 1, n)[:] = c_loc
     hu[:] = 0.0
-    hu[:n] = lp.scatter(u0)
-    ctx.advdrift_state_host(hc, hu, nt, dt)          # warm-up
+    hu[:n] = u0_loc
+    ctx.advdrift_state_host(hc, hu, nt_e2e, dt)          # warm-up
     reps_e2e = max(1, args.steps // 2)
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(reps_e2e):
-        ctx.advdrift_state_host(hc, hu, nt, dt)      # synchronises before returning
+        ctx.advdrift_state_host(hc, hu, nt_e2e, dt)      # synchronises before returning
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s, float(8 * n)], dtype=torch.float64, device="cuda")
     dist.all_reduce(te[:1], op=dist.ReduceOp.MAX)
     dist.all_reduce(te[1:], op=dist.ReduceOp.SUM)
-    e2e_value = nt * reps_e2e / float(te[0].item())
+    e2e_value = nt_e2e * reps_e2e / float(te[0].item())
     e2e_bytes = int(te[1].item())
+    perr = p2p_error(ctx)
+    pe = torch.tensor([perr], device="cuda")
+    dist.all_reduce(pe, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
+    rc = 0
     if rank == 0:
-        fct_steps = 2 * nt * args.steps
+        fct_steps = it.fct_steps_per_pass * args.steps
         value = fct_steps / (ms * 1e-3)
-        k_mean = float(np.mean([0.5 * (a + b) / nt for a, b in sweeps_hist]))
+        k_mean = float(np.mean([sum(s) / (3.0 * nt) for s in it.sweeps]))
         peak, peak_src = bench_mod._peaks()
         step_gb = bench_mod.step_bytes(n_glob, nnz_glob, ncell, k_mean) / 1e9
         line = {
             "metric": "FCT steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic {n_cells}^2-cell unit-square drift-control advection FCT PDECO "
-                                   f"(BASELINE config 5): {n_glob} DoF, {nnz_glob} nnz, row-block partitioned over "
-                                   f"{world} GPUs (one-ring halo over NVLink peer mailboxes); bench step = state+adjoint sweeps "
-                                   f"over {nt} time levels + gradient + cost",
+            "config": {"workload": bench_mod.workload_string(n_cells),
+                       "partition": f"row blocks over {world} GPUs, depth-{lp.depth} halo rings, NVLink peer mailboxes",
+                       "bench_step": f"one projected-gradient iteration over {nt} time levels: state + adjoint sweeps + gradient + "
+                                     f"one Armijo trial + cost = {it.fct_steps_per_pass} FCT steps, device-resident",
                        "time_levels": nt, "dt": dt, "jacobi_sweeps_per_step": k_mean, "cost_functional": J,
                        "halo_rows": [int(lp.row_begin), int(lp.n - lp.row_end)],
-                       "l2_flush": "per-GPU working set per pass >> L2"},
-            "roofline": {"bound": "hbm", "kernel": "whole FCT step (all kernels)", "achieved": step_gb * value / world,
-                         "peak": peak, "unit": "GB/s", "frac": step_gb * value / world / peak, "traffic": None,
-                         "peak_source": peak_src, "note": "per-GPU: algorithmic bytes of an FCT step x steps/s / N"},
+                       "l2_flush": ("per-GPU working set per FCT step >> L2" if 8 * nnz_glob / world > 200e6 else
+                                    "per-GPU value arrays fit the 126 MB L2 at this N: kernels run partly from L2")},
+            "roofline": {"bound": "hbm", "kernel": "whole FCT step (all kernels), SURVEY App. E accounting bytes",
+                         "achieved": step_gb * value / world, "peak": peak, "unit": "GB/s",
+                         "frac": step_gb * value / world / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "per-GPU: App. E accounting bytes of an FCT step x steps/s / N (the single-GPU line carries "
+                                 "the per-kernel roofline on actual bytes)"},
+            "mgpu_parity": mg, "mgpu_bit_identical": bool(mg.get("ok")),
+            "exchanges_per_fct_step": xch / max(1, (args.warmup + args.steps) * it.fct_steps_per_pass) if xch else None,
+            "launches_per_fct_step_per_rank": lt.item() / world / fct_steps,
+            "p2p_error": int(pe.item()),
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
+                    "time_levels": nt_e2e,
                     "call": "fct_advdrift_state_host on every rank (state sweep, pinned host trajectories of the rank's "
                             "local range)"},
             "gpu_launches": int(lt.item()),
             "clocks": clocks,
         }
         print(json.dumps(line))
+        if not mg.get("ok") or int(pe.item()):
+            sys.stderr.write("bench.py: multi-GPU parity check FAILED\n")
+            rc = 3
     dist.barrier()
     dist.destroy_process_group()
+    if rc:
+        raise SystemExit(rc)

@@ -250,6 +250,9 @@ int fct_event_destroy(fct_ctx* ctx, void* event);
 int fct_profiler_range(int32_t start);
 /* number of kernels this library has launched on this context since creation */
 int fct_launch_count(fct_ctx* ctx, int64_t* count);
+/* number of halo exchanges executed on this context since creation (multi-GPU; exchanges inside CUDA-graph bodies included
+ * on the peer-memory path) */
+int fct_exchange_count(fct_ctx* ctx, int64_t* count);
 
 #ifdef __cplusplus
 }

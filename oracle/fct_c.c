@@ -35,6 +35,16 @@ int fctc_threads(void) {
 #endif
 }
 
+/* bench.py's CPU arm sets the thread count itself: a torchrun launch exports OMP_NUM_THREADS=1 to every rank, which would
+ * silently turn the "all host threads" baseline into a one-thread run */
+void fctc_set_threads(int32_t t) {
+#ifdef _OPENMP
+    if (t >= 1) omp_set_num_threads(t);
+#else
+    (void)t;
+#endif
+}
+
 /* ---- mesh, DoF numbering, pattern ------------------------------------------------------------ */
 static int64_t diag_len(int64_t d, int64_t n) { return (d < 2 * n - d ? d : 2 * n - d) + 1; }
 
@@ -312,4 +322,21 @@ int fctc_step(int32_t n, const int32_t* rowptr, const int32_t* colidx, const int
         out[i] = ulow[i] + dt * fbar / ML[i];
     }
     return its;
+}
+
+/* (x - t)^T M (x - t), t may be NULL: one term of L2_norm_sq_Q / L2_norm_sq_Omega (helpers.py:330-381), used by bench.py's
+ * full-size parity check of the cost functional */
+double fctc_norm_sq_M(int32_t n, const int32_t* rowptr, const int32_t* colidx, const double* M, const double* x,
+                      const double* t) {
+    double s = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : s)
+    for (int32_t i = 0; i < n; ++i) {
+        double acc = 0.0;
+        for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int32_t j = colidx[k];
+            acc += M[k] * (t ? x[j] - t[j] : x[j]);
+        }
+        s += (t ? x[i] - t[i] : x[i]) * acc;
+    }
+    return s;
 }

@@ -14,16 +14,39 @@ from . import build_c
 _lib = None
 
 
-def lib():
+def lib(native=False):
+    """native=True (bench.py's CPU arm): try a -march=native rebuild on THIS host first (oracle/_fct_c_native.so); the
+    portable object built in the build container is the fallback"""
     global _lib
     if _lib is None:
-        path = build_c.build()
+        path = None
+        if native:
+            try:
+                path = build_c.build(native=True)
+            except Exception:  # noqa: BLE001
+                path = None
+        if path is None:
+            path = build_c.build()
         L = C.CDLL(path)
         L.fctc_threads.restype = C.c_int
         L.fctc_tpos.restype = C.c_int
         L.fctc_step.restype = C.c_int
+        L.fctc_norm_sq_M.restype = C.c_double
+        L.fctc_set_threads.restype = None
+        L._path = path
         _lib = L
     return _lib
+
+
+def use_all_host_threads():
+    """set the OpenMP thread count to the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun exports
+    OMP_NUM_THREADS=1 to its ranks); returns the count"""
+    try:
+        t = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        t = os.cpu_count() or 1
+    lib().fctc_set_threads(C.c_int32(t))
+    return lib().fctc_threads()
 
 
 def _p(a):
@@ -67,6 +90,23 @@ class CDriftProblem:
 
     def threads(self):
         return lib().fctc_threads()
+
+    def norm_sq_M(self, x, t=None):
+        """(x - t)^T M (x - t)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        t = None if t is None else np.ascontiguousarray(t, dtype=np.float64)
+        return float(lib().fctc_norm_sq_M(C.c_int32(self.nodes), _p(self.rowptr), _p(self.colidx), _p(self.M), _p(x),
+                                          _p(t) if t is not None else None))
+
+    def norm_sq_Q(self, phi, num_steps, dt, target=None):
+        """helpers.py:330-360 (trapezoid in time) of phi - target"""
+        phi = np.asarray(phi).reshape(num_steps + 1, self.nodes)
+        tg = None if target is None else np.asarray(target).reshape(num_steps + 1, self.nodes)
+        s = 0.0
+        for k in range(num_steps + 1):
+            w = 0.5 if k in (0, num_steps) else 1.0
+            s += w * self.norm_sq_M(phi[k], None if tg is None else tg[k])
+        return s * dt
 
     def _assemble(self, kind, c, bx, by, scale, out):
         lib().fctc_assemble(C.c_int32(kind), C.c_int32(self.nodes), _p(self.rowptr), _p(self.colidx), _p(self.inc_ptr),

@@ -322,6 +322,29 @@ def test_full_size_properties_4096():
     assert rel_l2(u[1], u0) > 1e-4                          # something moved
 
 
+def test_full_size_parity_vs_oracle_port_4096():
+    """BASELINE size (4097^2 DoF): the GPU state trajectory against the C/OpenMP oracle port (oracle/fct_c.c, pinned on the
+    numpy oracle, itself pinned on the reference's goldens) on the same u0, c, dt: rel-L2 <= 1e-12 per time step, cost
+    functional <= 1e-9 (BASELINE.json north_star).  This is the size at which the 24 573 row / geometry
+    templates, the fused drift pass and 65 k row blocks are actually exercised."""
+    import bench
+    from oracle import fct_c
+    n, ns = 4096, 2
+    fct_c.lib(native=True)
+    fct_c.use_all_host_threads()
+    prob = fct_c.CDriftProblem(n, 0.0, 1.0)
+    m = RectMeshP1(n, 0.0, 1.0)
+    assert np.array_equal(m.rowptr, prob.rowptr) and np.array_equal(m.colidx, prob.colidx)      # bit-exact pattern
+    assert np.array_equal(m.vertex_to_dof, prob.vertex_to_dof)                                  # ... and DoF order
+    dt = 0.25 * (1.0 / n) / (2 * np.sqrt(2))
+    u0, c = bench.synth_fields(prob.dof_xy)
+    traj, sweeps = prob.state(np.tile(c, ns + 1), u0, ns, dt)
+    res = bench.parity_vs_cpu_port(m.context(), prob, traj, dt)
+    assert max(res["rel_l2_per_step"]) <= TOL_STEP, res
+    assert res["cost_rel_diff"] <= 1e-9, res
+    assert res["ok"]
+
+
 def test_multi_gpu_matches_single_gpu():
     """2-rank row-block partition (NCCL halo exchange) vs the single-GPU path: fields bit-identical.
     Needs two visible GPUs (`gpurun --gpus 2`); skipped on a 1-GPU box."""
