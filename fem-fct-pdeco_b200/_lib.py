@@ -57,6 +57,9 @@ SIGNATURES = {
     "fct_assemble_static": [_p],
     "fct_ctx_static_dev": [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)],
     "fct_ctx_set_solver": [_p, _f64, _i32],
+    "fct_ctx_set_rect": [_p, _i32, _i64],
+    "fct_tiles_active": [_p, _pi32],
+    "fct_debug_tile_list": [_i32, _i64, _i32, _i32, _i32, _p, _i32, _pi32, _pi32],
     "fct_malloc": [_p, C.POINTER(_p), _i64],
     "fct_free": [_p, _p],
     "fct_h2d": [_p, _p, _p, _i64],

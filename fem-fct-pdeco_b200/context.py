@@ -177,6 +177,15 @@ class FctContext:
         tmp.free()
         self.has_mass = True
 
+    def set_rect(self, n_cells, g0=0):
+        """local row i is DoF g0 + i of the RectangleMesh(n_cells x n_cells) numbering: enables the overlapped-tile kernels"""
+        check(lib.fct_ctx_set_rect(self.handle, int(n_cells), int(g0)))
+
+    def tiles_active(self):
+        a = C.c_int32()
+        check(lib.fct_tiles_active(self.handle, C.byref(a)))
+        return bool(a.value)
+
     def set_solver(self, rtol=1e-14, max_sweeps=200):
         check(lib.fct_ctx_set_solver(self.handle, float(rtol), int(max_sweeps)))
 
@@ -318,8 +327,8 @@ class FctContext:
     def debug_jacobi_fixed(self, A, u_n, dt, sweeps, fused, x_out):
         check(lib.fct_debug_jacobi_fixed(self.handle, A.ptr, u_n.ptr, float(dt), int(sweeps), int(fused), x_out.ptr))
 
-    def bench_jacobi_fused(self, A, u_n, dt, sweeps=14, reps=5):
-        """ms per sweep of the wavefront kernel (all `sweeps` Jacobi sweeps of a solve in one launch)"""
+    def bench_jacobi_fused(self, A, u_n, dt, sweeps=4, reps=5):
+        """ms per sweep of the overlapped-tile kernel (`sweeps` = 2..4 Jacobi sweeps per launch)"""
         ms = C.c_float()
         check(lib.fct_bench_jacobi_fused(self.handle, A.ptr, u_n.ptr, float(dt), int(sweeps), int(reps), C.byref(ms)))
         return ms.value

@@ -52,7 +52,7 @@ struct fct_hoststage {
 
 struct fct_comm;   // NCCL state (fct_comm.cu)
 struct fct_p2p;    // NVLink peer-memory mailboxes (fct_p2p.cu)
-struct fct_win;    // windows + flags of the wavefront kernels (fct_win.cu)
+struct fct_tiles;  // structured-numbering data of the overlapped-tile kernels (fct_tile.cu)
 
 // CUDA-graph WHILE loop of the low-order Jacobi solve (fct_kernels.cu), cached per operand set
 struct fct_jgraph {
@@ -117,7 +117,10 @@ struct fct_ctx {
     // Low-order Jacobi on the row templates: 0 = CSR kernels, 1 = column offsets from the templates (bit-identical to 0),
     // 2 = additionally rows pre-scaled by 1/l_ii in k_low_build (no dinv read in the sweep).  FCT_JAC_TPL selects.
     int32_t jac_mode = 0;
-    fct_win* win = nullptr;          // wavefront (multi-sweep) Jacobi / ChebSI kernels; null = one launch per sweep
+    fct_tiles* tiles = nullptr;      // set by fct_ctx_set_rect: K Jacobi sweeps / Chebyshev iterations per launch (fct_tile.cu)
+    bool tiles_ok = false;           // tile kernels usable (structured numbering verified, row templates present)
+    int32_t tile_kj = 4;             // sweeps per fused Jacobi launch (FCT_TILE_KJ, 2..4)
+    int32_t tile_kc = 5;             // iterations per fused ChebSI launch (FCT_TILE_KC, 2..5)
     int32_t cheb_mdtab = 1;          // ChebSI takes diag(M) from the template table when the caller passes ctx->Mdiag
     // workspace
     double* Lvals = nullptr;    // low-order operator
@@ -125,6 +128,8 @@ struct fct_ctx {
     double* Avals = nullptr;    // assembled operator (time loops) / host-call staging
     double* Svals = nullptr;    // host-call staging
     double* w[12] = {nullptr};  // vector workspace [n] each
+    double* fb_w[12] = {nullptr};   // private workspace of the BiCGStab fallback of the low-order solve (allocated on first use)
+    bool checked_steps = false;     // fct_step reads the Jacobi outcome back after every low-order solve and falls back to BiCGStab
     double* red = nullptr;      // device scalars for reductions (64 doubles)
     unsigned long long* jstate = nullptr;  // Jacobi state words
     double* pinned = nullptr;   // small pinned host buffer (64 doubles)

@@ -120,6 +120,7 @@ void fct_p2p_destroy(fct_ctx* ctx);
 void fct_templates_free(fct_ctx* ctx);
 int fct_templates_build(fct_ctx* ctx);
 void fct_geom_templates_free(fct_ctx* ctx);
+void fct_tiles_free(fct_ctx* ctx);
 
 template <typename T>
 static int dev_alloc(T** p, size_t count) {
@@ -163,6 +164,8 @@ extern "C" int fct_ctx_create(fct_ctx** out, int device, int32_t n, const int32_
     c->cap = ((cap + 3) & ~3) + 4;
     { const char* e = getenv("FCT_NO_GRAPH"); c->use_graph = !(e && atoi(e) == 1); }
     { const char* e = getenv("FCT_PDL"); c->use_pdl = (e && atoi(e) == 1); }   // measured: no gain with persistent grids
+    { const char* e = getenv("FCT_TILE_KJ"); if (e && atoi(e) >= 2 && atoi(e) <= 4) c->tile_kj = atoi(e); }
+    { const char* e = getenv("FCT_TILE_KC"); if (e && atoi(e) >= 2 && atoi(e) <= 5) c->tile_kc = atoi(e); }
     {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)
@@ -221,6 +224,7 @@ extern "C" int fct_ctx_destroy(fct_ctx* c) {
         cudaStreamDestroy(c->hs.d2h_stream);
     }
     fct_templates_free(c);
+    fct_tiles_free(c);
     fct_geom_templates_free(c);
     fct_p2p_destroy(c);
     fct_comm_destroy(c);
@@ -228,7 +232,7 @@ extern "C" int fct_ctx_destroy(fct_ctx* c) {
     cudaFree(c->cells); cudaFree(c->xy); cudaFree(c->v2c_ptr); cudaFree(c->v2c_idx);
     cudaFree(c->M); cudaFree(c->ML); cudaFree(c->Mdiag); cudaFree(c->K);
     cudaFree(c->Lvals); cudaFree(c->Dvals); cudaFree(c->Avals); cudaFree(c->Svals);
-    for (int i = 0; i < 12; ++i) cudaFree(c->w[i]);
+    for (int i = 0; i < 12; ++i) { cudaFree(c->w[i]); cudaFree(c->fb_w[i]); }
     cudaFree(c->red); cudaFree(c->jstate);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(32)
 k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, unsigned char* p2, unsigned char* p3,
                   unsigned char* p4, unsigned char* p5, unsigned char* p6, unsigned char* p7, int rank, int world,
                   unsigned long long* jstate, double rtol, unsigned long long max_sweeps, int use_handle,
-                  cudaGraphConditionalHandle handle) {
+                  cudaGraphConditionalHandle handle, unsigned long long which) {
     unsigned char* peers[FCT_P2P_MAXWORLD] = {p0, p1, p2, p3, p4, p5, p6, p7};
     P2PHeader* H = reinterpret_cast<P2PHeader*>(mine);
     __shared__ unsigned long long m0[32], m1[32];
@@ -162,6 +162,7 @@ k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, uns
             jstate[6] = b;
             if (delta <= rtol * xm) {
                 jstate[3] = 1ull;
+                jstate[12] = which;          // fused tile sweeps: 1 = the converged iterate is in the scratch vector
                 const unsigned long long s = jstate[4], back = jstate[11] ? 2ull : 4ull;
                 jstate[10] = s > back ? s - back : 0ull;
             } else {
@@ -255,11 +256,13 @@ int fct_p2p_exchange(fct_ctx* ctx, double* v0, double* v1) {
     return 0;
 }
 
-int fct_p2p_max2_decide(fct_ctx* ctx, double rtol, int max_sweeps, int use_handle, cudaGraphConditionalHandle handle) {
+int fct_p2p_max2_decide(fct_ctx* ctx, double rtol, int max_sweeps, int use_handle, cudaGraphConditionalHandle handle,
+                        int which) {
     fct_p2p* p = ctx->p2p;
     k_p2p_max2_decide<<<1, 32, 0, ctx->stream>>>(p->region, p->peer[0], p->peer[1], p->peer[2], p->peer[3], p->peer[4],
                                                  p->peer[5], p->peer[6], p->peer[7], p->rank, p->world, ctx->jstate, rtol,
-                                                 (unsigned long long)max_sweeps, use_handle, handle);
+                                                 (unsigned long long)max_sweeps, use_handle, handle,
+                                                 (unsigned long long)which);
     ctx->launches++;
     return 0;
 }

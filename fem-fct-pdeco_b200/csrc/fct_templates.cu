@@ -82,11 +82,10 @@ __global__ void k_verify_templates(const int32_t* __restrict__ rowptr, const int
     if (!ok) atomicAdd(bad, 1);
 }
 
-void fct_win_free(fct_ctx* ctx);          // fct_win.cu
-int fct_win_build(fct_ctx* ctx);
+int fct_tiles_prepare(fct_ctx* ctx);      // fct_tile.cu
 
 void fct_templates_free(fct_ctx* ctx) {
-    fct_win_free(ctx);
+    ctx->tiles_ok = false;           // the tile kernels' neighbour-delta table is indexed by template code
     cudaFree(ctx->tpl_code); cudaFree(ctx->tpl_off); cudaFree(ctx->tpl_val); cudaFree(ctx->tpl_diag);
     ctx->tpl_code = nullptr; ctx->tpl_off = nullptr; ctx->tpl_val = nullptr; ctx->tpl_diag = nullptr;
     ctx->tpl_count = 0;
@@ -149,7 +148,7 @@ int fct_templates_build(fct_ctx* ctx) {
         ctx->jac_mode = (jm && atoi(jm) >= 0 && atoi(jm) <= 2) ? atoi(jm) : 2;
         const char* mt = getenv("FCT_CHEB_MDTAB");   // 0: ChebSI always reads Md from memory
         ctx->cheb_mdtab = (mt && atoi(mt) == 0) ? 0 : 1;
-        fct_win_build(ctx);
+        fct_tiles_prepare(ctx);
     } else {
         fct_templates_free(ctx);
     }

@@ -1,0 +1,589 @@
+// Overlapped 2-D tiles for the two iterative kernels of the FCT step on structured (RectangleMesh) numberings:
+// K Jacobi sweeps of the low-order solve (helpers.py:1782) or K Chebyshev iterations of ChebSI (helpers.py:143-185) per
+// launch, out of shared memory and registers.
+//
+// dolfin's CG1 numbering on RectangleMesh is an anti-diagonal numbering: row = start(d) + pos with
+// d = ix - iy + n.  Every neighbour of (d, pos) lies in (d +- 1, pos +- 1), so a rectangle in (d, pos) space plus a K-wide
+// frame holds everything K dependent passes over its interior need, and each of its diagonals is one contiguous piece of
+// every vector and of the CSR value array.  A CTA (one per SM, persistent over its tiles) owns a 40 x 40 region:
+//   * the NEXT tile streams in while the current one is computed: the matrix rows of each region diagonal with 1-D TMA
+//     bulk copies, the iterate with 8-byte cp.async, the right-hand side into registers, all issued at the start of the
+//     current tile's passes and (the shared-memory part) completing on one mbarrier;
+//   * each compute thread keeps the matrix rows (<= 8 values each) and the right-hand side of its (at most 3) rows in
+//     REGISTERS for all K passes, so a pass costs 7 shared-memory loads + 7 DFMA per row; the iterate ping-pongs between
+//     two shared-memory buffers; pass s updates the rows at least s away from the region's edge (redundant work in the
+//     frame instead of inter-CTA flags); only the interior is written back;
+//   * neighbour positions come from the row templates (fct_templates.cu): per template 8 signed bytes (delta of the
+//     shared-memory index), so boundary rows, corners and the truncated rows of a multi-GPU block need no special case.
+// HBM traffic per K passes: the matrix values, b and x once (+ the frame, mostly L2 hits on the neighbouring tile's
+// interior) instead of K times.  The arithmetic of a row is the same sequence of operations as in the per-pass kernels
+// (k_jacobi_sweep_tpl, k_cheb_iter_tpl): results are bit-identical for the same number of passes
+// (tests/test_gpu_parity.py::test_tile_kernels_bit_identical).
+//
+// Multi-GPU: a rank's rows are the global rows [g0, g0 + n); tiles cover the owned rows and read K rings of halo, so
+// with halo depth >= K one launch replaces the K per-ring launches between two exchanges.
+// General meshes (fct_ctx_set_rect not called, or its verification failed) keep the per-pass kernels.
+#include "fct_common.cuh"
+#include "fct_pipe.cuh"
+#include "../../include/fctpdeco.h"
+
+#include <stdlib.h>
+#include <vector>
+
+extern __shared__ __align__(16) unsigned char fct_smem[];
+
+#define TL_ND 40                      // region: diagonals
+#define TL_NP 40                      // region: positions per diagonal
+#define TL_NC (TL_ND - 2)             // rows that are ever updated ("compute set"): 38 x 38
+#define TL_NQ (TL_NP - 2)
+#define TL_XS TL_NP                   // row stride of the iterate buffers
+#define TL_R 3                        // compute-set rows per thread
+#define TL_NT 512                     // threads per CTA (16 warps leave 128 registers per thread), one CTA per SM
+#define TL_THREADS TL_NT
+#define TL_KMAX 5
+static_assert(TL_R * TL_NT >= TL_NC * TL_NQ, "every compute-set row needs a thread");
+static_assert(TL_XS + 1 <= 127, "neighbour deltas must fit a signed byte");
+
+struct fct_tiles {
+    int n_cells = 0;                  // cells per side of the structured mesh
+    int g0 = 0;                       // global DoF index of local row 0
+    unsigned long long* tdelta = nullptr;      // [templates] 8 signed bytes: shared-memory index delta of each row entry
+    int2* list[TL_KMAX + 1] = {nullptr};       // per K: interior origins (d0, p0) of the tiles covering the owned rows
+    int count[TL_KMAX + 1] = {0};
+    int sms = 148;
+};
+
+struct TileArgs {
+    int n_cells, total, g0, nloc, own_rb, own_re, ntiles;
+    const int2* tiles;
+    const int32_t* rowptr;
+    const uint16_t* code;
+    const unsigned long long* tdelta;
+    const double* tval;
+    const double* tdiag;
+    const double* Lv;      // Jacobi: row-scaled low-order operator (zero diagonal slot)
+    const double* b;       // Jacobi: b'; ChebSI: g
+    const double* xin;     // Jacobi: x; ChebSI: y_mid
+    const double* yold;    // ChebSI: y_old (nullptr: zero)
+    double* xout;          // Jacobi: x after K sweeps; ChebSI: y_mid after K iterations
+    double* yold_out;      // ChebSI: y_old after K iterations (nullptr: not wanted)
+    unsigned long long* jstate;
+    double om[TL_KMAX];
+    double dscale;
+};
+
+// ---- closed-form numbering ----------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int tl_diag_len(int d, int n) { return (d <= n ? d : 2 * n - d) + 1; }
+__host__ __device__ __forceinline__ int tl_diag_start(int d, int n, int total) {
+    if (d <= n) return d * (d + 1) / 2;
+    const int m = 2 * n - d;
+    return total - (m + 1) * (m + 2) / 2;
+}
+// global row -> (d, pos)
+__device__ __forceinline__ void tl_row_to_dp(int g, int n, int total, int& d, int& pos) {
+    const int half = (n + 1) * (n + 2) / 2;
+    const bool upper = g < half;
+    const int q = upper ? g : total - 1 - g;
+    int t = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+    while (t * (t + 1) / 2 > q) --t;
+    while ((t + 1) * (t + 2) / 2 <= q) ++t;
+    const int p = q - t * (t + 1) / 2;
+    if (upper) { d = t; pos = p; }
+    else { d = 2 * n - t; pos = t - p; }      // the mirror reverses the order within a diagonal (len = t + 1)
+}
+
+// ---- set-up: neighbour deltas per template (doubles as the check that the pattern is a (d +- 1, pos +- 1) stencil) ----
+__device__ __forceinline__ bool tl_row_deltas(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int r,
+                                              int n, int total, int g0, unsigned long long& packed) {
+    int d, pos;
+    tl_row_to_dp(g0 + r, n, total, d, pos);
+    const int k0 = rowptr[r], len = rowptr[r + 1] - k0;
+    packed = 0ull;
+    if (len > 8) return false;
+    for (int j = 0; j < len; ++j) {
+        int d2, p2;
+        tl_row_to_dp(g0 + colidx[k0 + j], n, total, d2, p2);
+        const int dd = d2 - d, dp = p2 - pos;
+        if (dd < -1 || dd > 1 || dp < -1 || dp > 1) return false;
+        const int delta = dd * TL_XS + dp;
+        packed |= (unsigned long long)(unsigned char)(signed char)delta << (8 * j);
+    }
+    return true;
+}
+__global__ void k_tile_deltas(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                              const uint16_t* __restrict__ code, int nloc, int n, int total, int g0,
+                              unsigned long long* __restrict__ tdelta, int* __restrict__ bad) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nloc) return;
+    unsigned long long p;
+    if (!tl_row_deltas(rowptr, colidx, r, n, total, g0, p)) { atomicAdd(bad, 1); return; }
+    tdelta[code[r]] = p;          // rows of one template agree (checked by k_tile_deltas_verify)
+}
+__global__ void k_tile_deltas_verify(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                     const uint16_t* __restrict__ code, int nloc, int n, int total, int g0,
+                                     const unsigned long long* __restrict__ tdelta, int* __restrict__ bad) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nloc) return;
+    unsigned long long p;
+    if (!tl_row_deltas(rowptr, colidx, r, n, total, g0, p) || tdelta[code[r]] != p) atomicAdd(bad, 1);
+}
+
+// ---- the tile kernel -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// mbarrier wait that cannot hang the GPU: a wait that has not completed after ~2 s of spinning aborts the launch
+// (cudaErrorLaunchFailure at the next synchronisation) instead of spinning forever
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    while (!done) {
+        asm volatile(
+            "{\n"
+            " .reg .pred p;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ int tl_delta(unsigned long long pk, int j) {
+    return (int)(signed char)(unsigned char)(pk >> (8 * j));
+}
+// the two neighbour layouts of interior rows (7 entries, ascending columns): above the main anti-diagonal (d < n) the
+// neighbours sit at (d-1: pos-1, pos), (d: pos-1, pos, pos+1), (d+1: pos, pos+1); below it (d > n) at (d-1: pos, pos+1),
+// (d: ...), (d+1: pos-1, pos).  Rows with one of these layouts take shared-memory loads with immediate offsets.
+__host__ __device__ constexpr unsigned long long tl_pack7(int a0, int a1, int a2, int a3, int a4, int a5, int a6) {
+    return (unsigned long long)(unsigned char)(signed char)a0 | ((unsigned long long)(unsigned char)(signed char)a1 << 8) |
+           ((unsigned long long)(unsigned char)(signed char)a2 << 16) | ((unsigned long long)(unsigned char)(signed char)a3 << 24) |
+           ((unsigned long long)(unsigned char)(signed char)a4 << 32) | ((unsigned long long)(unsigned char)(signed char)a5 << 40) |
+           ((unsigned long long)(unsigned char)(signed char)a6 << 48);
+}
+#define TL_DPK_UP tl_pack7(-TL_XS - 1, -TL_XS, -1, 0, 1, TL_XS, TL_XS + 1)
+#define TL_DPK_LO tl_pack7(-TL_XS, -TL_XS + 1, -1, 0, 1, TL_XS - 1, TL_XS)
+
+template <int MODE, int W>
+struct TileSmem {
+    static constexpr int SEGCAP = (TL_NQ * W + 2 + 1) & ~1;                        // staged CSR range of one region diagonal (even)
+    static constexpr int L_DOUBLES = (MODE == 0) ? TL_NC * SEGCAP : 0;
+    static constexpr int X_DOUBLES = 3 * TL_ND * TL_XS;
+    static constexpr size_t BYTES = 8 * (size_t)(L_DOUBLES + X_DOUBLES) + 4 * TL_NC;
+    static_assert(L_DOUBLES % 2 == 0, "bulk-copy destinations must stay 16-byte aligned");
+};
+
+// MODE 0: K Jacobi sweeps  x <- b' - sum_j l'_ij x_j  of the row-scaled low-order system (k_jacobi_sweep_tpl<., true>)
+// MODE 1: K Chebyshev iterations  y+ = om (z + y - y-) + y-,  z = (g - M y) / (dscale diag M)  (k_cheb_iter_tpl)
+// Every warp computes; the loads of tile j+1 are issued by all threads at the start of tile j's passes: the iterate of the
+// region with 8-byte cp.async (each thread its own 3-4 entries), the matrix rows of each region diagonal with one 1-D TMA
+// bulk copy (lane 0 of warp c % 16), the right-hand side (and y_old) of the thread's rows straight into registers.  One
+// mbarrier collects all of them (cp.async completions + TMA transaction bytes).
+template <int MODE, int K, int W>
+__global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
+    if (MODE == 0 && *reinterpret_cast<volatile unsigned long long*>(a.jstate + 3)) return;      // already converged
+    using SM = TileSmem<MODE, W>;
+    double* sL = reinterpret_cast<double*>(fct_smem);
+    double* sX = sL + SM::L_DOUBLES;
+    int* sSeg = reinterpret_cast<int*>(sX + SM::X_DOUBLES);          // [TL_NC]: first staged CSR index of each L segment
+    __shared__ __align__(8) uint64_t bar_full;
+    __shared__ double sred[2][TL_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bar_full, TL_NT + (MODE == 0 ? TL_NT / 32 : 0));      // cp.async completions (+ one expect_tx arrival per warp)
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int n = a.n_cells, total = a.total;
+    const int nmine = ((int)blockIdx.x < a.ntiles) ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    // rows this thread updates (compute set) and region entries it loads: fixed for the whole launch
+    int xi[TL_R], ml[TL_R], dlr[TL_R], plr[TL_R];
+#pragma unroll
+    for (int i = 0; i < TL_R; ++i) {
+        const int q = tid + i * TL_NT;
+        const bool has = q < TL_NC * TL_NQ;
+        const int dc = has ? q / TL_NQ : 0, pc = has ? q % TL_NQ : 0;
+        dlr[i] = dc + 1; plr[i] = pc + 1;
+        xi[i] = dlr[i] * TL_XS + plr[i];
+        ml[i] = has ? min(min(dlr[i], TL_ND - 1 - dlr[i]), min(plr[i], TL_NP - 1 - plr[i])) : 0;
+    }
+    constexpr int NE = (TL_ND * TL_NP + TL_NT - 1) / TL_NT;          // region entries per thread
+
+    int row[TL_R], nrow[TL_R], ncode[TL_R], nk0[TL_R], nlen[TL_R];
+    unsigned long long dpk[TL_R];
+    double Lr[TL_R][W], br[TL_R], nb[TL_R], yo[TL_R], nyo[TL_R], md[TL_R];
+    // rows of tile j and the first loads they need (row pointer, template code, right-hand side), issued one tile ahead
+    auto prefetch_meta = [&](int j) {
+#pragma unroll
+        for (int i = 0; i < TL_R; ++i) { nrow[i] = -1; ncode[i] = 0; nk0[i] = 0; nlen[i] = 0; nb[i] = 0.0; nyo[i] = 0.0; }
+        if (j >= nmine) return;
+        const int2 t = a.tiles[(int)blockIdx.x + j * (int)gridDim.x];
+#pragma unroll
+        for (int i = 0; i < TL_R; ++i) {
+            if (ml[i] == 0) continue;
+            const int d = t.x - K + dlr[i], pos = t.y - K + plr[i];
+            if (d < 0 || d > 2 * n || pos < 0 || pos >= tl_diag_len(d, n)) continue;
+            const int r = tl_diag_start(d, n, total) + pos - a.g0;
+            if (r < 0 || r >= a.nloc) continue;
+            nrow[i] = r;
+            ncode[i] = a.code[r];
+            nb[i] = a.b[r];
+            if (MODE == 0) { nk0[i] = a.rowptr[r]; nlen[i] = a.rowptr[r + 1] - nk0[i]; }
+            if (MODE == 1 && a.yold) nyo[i] = a.yold[r];
+        }
+    };
+    // second-level loads (depend on the template code): neighbour deltas, and for ChebSI the mass-matrix row
+    auto load_meta2 = [&]() {
+#pragma unroll
+        for (int i = 0; i < TL_R; ++i) {
+            dpk[i] = 0ull;
+            if (MODE == 1) {
+                md[i] = 1.0;
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = 0.0;
+            }
+            if (nrow[i] < 0) continue;
+            dpk[i] = __ldg(a.tdelta + ncode[i]);
+            if (MODE == 1) {
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = __ldg(a.tval + FCT_TPL_W * ncode[i] + jj);
+                md[i] = a.dscale * __ldg(a.tdiag + ncode[i]);
+            }
+        }
+    };
+    // everything tile j needs in shared memory; the caller guarantees that its destination buffers are free
+    auto issue_loads = [&](int j) {
+        if (j >= nmine) return;
+        const int2 t = a.tiles[(int)blockIdx.x + j * (int)gridDim.x];
+        const int dlo = t.x - K, plo = t.y - K;
+        double* xb = sX + (j % 3) * (TL_ND * TL_XS);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+            const int e = tid + i * TL_NT;
+            if (e >= TL_ND * TL_NP) continue;
+            const int dl = e / TL_NP, pl = e % TL_NP;
+            const int d = dlo + dl, pos = plo + pl;
+            if (d < 0 || d > 2 * n || pos < 0 || pos >= tl_diag_len(d, n)) continue;
+            const int r = tl_diag_start(d, n, total) + pos - a.g0;
+            if (r >= 0 && r < a.nloc) cp_async8(xb + dl * TL_XS + pl, a.xin + r);
+        }
+        cp_async_mbar_arrive(&bar_full);
+        if (MODE == 0 && lane == 0) {
+            uint32_t tx = 0;
+            for (int c = warp; c < TL_NC; c += TL_NT / 32) {
+                const int d = dlo + c + 1;
+                int ka = 0;
+                if (d >= 0 && d <= 2 * n) {
+                    const int len = tl_diag_len(d, n), st = tl_diag_start(d, n, total) - a.g0;
+                    const int pa = max(plo + 1, 0), pb = min(plo + TL_NP - 1, len);
+                    const int ra = max(st + pa, 0), rb = min(st + pb, a.nloc);
+                    if (pb > pa && rb > ra) {
+                        const int k0 = a.rowptr[ra], k1 = a.rowptr[rb];
+                        ka = k0 - (int)((reinterpret_cast<uintptr_t>(a.Lv + k0) >> 3) & 1);
+                        const uint32_t bytes = (uint32_t)(((k1 - ka) + 1) & ~1) * 8u;
+                        tma_load_1d(sL + c * SM::SEGCAP, a.Lv + ka, bytes, &bar_full);
+                        tx += bytes;
+                    }
+                }
+                sSeg[c] = ka;
+            }
+            mbar_expect_tx(&bar_full, tx);          // one arrival per warp (release: the sSeg stores above are ordered before it)
+        }
+    };
+
+    prefetch_meta(0);
+    issue_loads(0);
+    load_meta2();
+    double delta = 0.0, xa = 0.0;
+    for (int j = 0; j < nmine; ++j) {
+        int k0r[TL_R], lenr[TL_R];
+#pragma unroll
+        for (int i = 0; i < TL_R; ++i) { row[i] = nrow[i]; k0r[i] = nk0[i]; lenr[i] = nlen[i]; br[i] = nb[i]; yo[i] = nyo[i]; }
+        mbar_wait_bounded(&bar_full, (uint32_t)(j & 1));
+        if (MODE == 0) {
+            // staged matrix rows -> registers
+#pragma unroll
+            for (int i = 0; i < TL_R; ++i) {
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = 0.0;
+                if (row[i] < 0) continue;
+                const int c = dlr[i] - 1;
+                const double* p = sL + c * SM::SEGCAP + (k0r[i] - sSeg[c]);
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = (jj < lenr[i]) ? p[jj] : 0.0;
+            }
+        }
+        __syncthreads();          // the staging buffer and the third iterate buffer are free (every thread is past tile j-1)
+        prefetch_meta(j + 1);
+        issue_loads(j + 1);
+        double* A = sX + (j % 3) * (TL_ND * TL_XS);
+        double* B = sX + ((j + 2) % 3) * (TL_ND * TL_XS);
+        int kind[TL_R];
+#pragma unroll
+        for (int i = 0; i < TL_R; ++i) kind[i] = (W == 7 && dpk[i] == TL_DPK_UP) ? 1 : (W == 7 && dpk[i] == TL_DPK_LO) ? 2 : 0;
+#pragma unroll
+        for (int s = 1; s <= K; ++s) {
+            const double* in = (s & 1) ? A : B;
+            double* out = (s & 1) ? B : A;
+#pragma unroll
+            for (int i = 0; i < TL_R; ++i) {
+                if (row[i] >= 0 && s <= ml[i]) {
+                    const double* p = in + xi[i];
+                    double acc = 0.0;
+                    if (W == 7 && kind[i] == 1) {
+                        acc += Lr[i][0] * p[-TL_XS - 1]; acc += Lr[i][1] * p[-TL_XS]; acc += Lr[i][2] * p[-1];
+                        acc += Lr[i][3] * p[0]; acc += Lr[i][4] * p[1]; acc += Lr[i][5] * p[TL_XS];
+                        acc += Lr[i][W - 1] * p[TL_XS + 1];
+                    } else if (W == 7 && kind[i] == 2) {
+                        acc += Lr[i][0] * p[-TL_XS]; acc += Lr[i][1] * p[-TL_XS + 1]; acc += Lr[i][2] * p[-1];
+                        acc += Lr[i][3] * p[0]; acc += Lr[i][4] * p[1]; acc += Lr[i][5] * p[TL_XS - 1];
+                        acc += Lr[i][W - 1] * p[TL_XS];
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < W; ++jj) acc += Lr[i][jj] * p[tl_delta(dpk[i], jj)];
+                    }
+                    if (MODE == 0) {
+                        out[xi[i]] = br[i] - acc;
+                    } else {
+                        const double ym = p[0];
+                        const double z = (br[i] - acc) / md[i];
+                        out[xi[i]] = a.om[s - 1] * (z + ym - yo[i]) + yo[i];
+                        yo[i] = ym;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // the next tile's template data travels while this tile's interior is written back
+        load_meta2();
+        const double* fin = (K & 1) ? B : A;
+        const double* prev = (K & 1) ? A : B;
+#pragma unroll
+        for (int i = 0; i < TL_R; ++i) {
+            if (row[i] >= 0 && ml[i] >= K && row[i] >= a.own_rb && row[i] < a.own_re) {
+                const double v = fin[xi[i]];
+                a.xout[row[i]] = v;
+                if (MODE == 0) {
+                    delta = fmax(delta, fabs(v - prev[xi[i]]));
+                    xa = fmax(xa, fabs(v));
+                } else if (a.yold_out) {
+                    a.yold_out[row[i]] = yo[i];
+                }
+            }
+        }
+    }
+    if (MODE == 0) {
+        // stopping test input: ||x_K - x_{K-1}||_inf and ||x_K||_inf over the owned rows (k_jacobi_sweep_tpl's `check`)
+        delta = warp_max(delta);
+        xa = warp_max(xa);
+        if (lane == 0) { sred[0][warp] = delta; sred[1][warp] = xa; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < TL_NT / 32; ++w) { delta = fmax(delta, sred[0][w]); xa = fmax(xa, sred[1][w]); }
+            atomicMax(a.jstate + 0, (unsigned long long)__double_as_longlong(delta));
+            atomicMax(a.jstate + 1, (unsigned long long)__double_as_longlong(xa));
+            if (blockIdx.x == 0) atomicAdd(a.jstate + 4, (unsigned long long)K);
+        }
+    }
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+void fct_tiles_free(fct_ctx* ctx) {
+    fct_tiles* t = ctx->tiles;
+    if (!t) return;
+    cudaFree(t->tdelta);
+    for (int k = 0; k <= TL_KMAX; ++k) cudaFree(t->list[k]);
+    delete t;
+    ctx->tiles = nullptr;
+}
+
+// tiles (interior (TL_ND - 2K) diagonals x (TL_NP - 2K) positions) covering the owned global rows [ga, gb), diagonal block by
+// diagonal block; host code
+static void tile_list_host(int n, long long ga, long long gb, int K, std::vector<int2>& v) {
+    const int total = (n + 1) * (n + 1);
+    const int Td = TL_ND - 2 * K, Tp = TL_NP - 2 * K;
+    v.clear();
+    if (gb <= ga) return;
+    int dA = 0, dB = 2 * n;
+    while (dA < 2 * n && tl_diag_start(dA + 1, n, total) <= ga) ++dA;
+    while (dB > 0 && tl_diag_start(dB, n, total) >= gb) --dB;
+    for (int d0 = dA; d0 <= dB; d0 += Td) {
+        int maxlen = 0;
+        for (int d = d0; d < d0 + Td && d <= 2 * n; ++d) maxlen = std::max(maxlen, tl_diag_len(d, n));
+        for (int p0 = 0; p0 < maxlen; p0 += Tp) {
+            bool any = false;
+            for (int d = d0; d < d0 + Td && d <= dB && !any; ++d) {
+                const long long s = tl_diag_start(d, n, total);
+                const long long lo = std::max(s + p0, ga), hi = std::min(s + std::min(p0 + Tp, tl_diag_len(d, n)), gb);
+                any = hi > lo;
+            }
+            if (any) v.push_back(make_int2(d0, p0));
+        }
+    }
+}
+
+// test hook (CPU-testable, no device needed): the tile list of a row block and the tile geometry constants
+extern "C" int fct_debug_tile_list(int32_t n_cells, int64_t g0, int32_t row_begin, int32_t row_end, int32_t K,
+                                   int32_t* d0p0_out, int32_t cap, int32_t* count_out, int32_t* geom_out /* ND, NP */) {
+    FCT_CHECK(n_cells >= 1 && K >= 1 && 2 * K < TL_NP && count_out, "fct_debug_tile_list: bad argument");
+    std::vector<int2> v;
+    tile_list_host(n_cells, g0 + row_begin, g0 + row_end, K, v);
+    *count_out = (int32_t)v.size();
+    if (geom_out) { geom_out[0] = TL_ND; geom_out[1] = TL_NP; }
+    if (d0p0_out)
+        for (int i = 0; i < (int)v.size() && i < cap; ++i) { d0p0_out[2 * i] = v[i].x; d0p0_out[2 * i + 1] = v[i].y; }
+    return 0;
+}
+
+static int build_tile_list(fct_ctx* ctx, int K) {
+    fct_tiles* t = ctx->tiles;
+    if (t->list[K]) return 0;
+    std::vector<int2> v;
+    tile_list_host(t->n_cells, (long long)t->g0 + ctx->row_begin, (long long)t->g0 + ctx->row_end, K, v);
+    t->count[K] = (int)v.size();
+    if (v.empty()) { FCT_CUDA(cudaMalloc((void**)&t->list[K], sizeof(int2))); return 0; }
+    FCT_CUDA(cudaMalloc((void**)&t->list[K], sizeof(int2) * v.size()));
+    FCT_CUDA(cudaMemcpyAsync(t->list[K], v.data(), sizeof(int2) * v.size(), cudaMemcpyHostToDevice, ctx->stream));
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+template <int MODE, int K, int W>
+static int tile_set_attr() {
+    FCT_CUDA(cudaFuncSetAttribute(k_tile<MODE, K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<MODE, W>::BYTES));
+    return 0;
+}
+template <int MODE, int K, int W>
+static void tile_launch_t(fct_ctx* ctx, const TileArgs& a, int grid) {
+    k_tile<MODE, K, W><<<grid, TL_THREADS, TileSmem<MODE, W>::BYTES, ctx->stream>>>(a);
+}
+
+static int tiles_configure() {
+    static bool done = false;
+    if (done) return 0;
+    if (tile_set_attr<0, 2, 7>() || tile_set_attr<0, 3, 7>() || tile_set_attr<0, 4, 7>() || tile_set_attr<0, 2, 8>() ||
+        tile_set_attr<0, 3, 8>() || tile_set_attr<0, 4, 8>())
+        return 1;
+    if (tile_set_attr<1, 2, 7>() || tile_set_attr<1, 3, 7>() || tile_set_attr<1, 4, 7>() || tile_set_attr<1, 5, 7>() ||
+        tile_set_attr<1, 2, 8>() || tile_set_attr<1, 3, 8>() || tile_set_attr<1, 4, 8>() || tile_set_attr<1, 5, 8>())
+        return 1;
+    done = true;
+    return 0;
+}
+
+// (Re)build what the tile kernels need; called when the structured numbering is declared and whenever the row templates
+// are rebuilt.  Never fails the caller: without tiles the per-pass kernels run.
+int fct_tiles_prepare(fct_ctx* ctx) {
+    fct_tiles* t = ctx->tiles;
+    if (!t) return 0;
+    cudaFree(t->tdelta);
+    t->tdelta = nullptr;
+    ctx->tiles_ok = false;
+    const char* e = getenv("FCT_NO_TILES");
+    if (e && atoi(e) == 1) return 0;
+    if (ctx->tpl_count <= 0 || ctx->jac_mode != 2 || ctx->max_row > 8) return 0;
+    const int n = t->n_cells, total = (n + 1) * (n + 1);
+    if ((long long)t->g0 + ctx->n > total) return 0;
+    int* bad = nullptr;
+    int hbad = 1;
+    do {
+        if (tiles_configure()) break;
+        if (cudaMalloc((void**)&t->tdelta, sizeof(unsigned long long) * (size_t)ctx->tpl_count) != cudaSuccess) break;
+        if (cudaMalloc((void**)&bad, sizeof(int)) != cudaSuccess) break;
+        cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream);
+        cudaMemsetAsync(t->tdelta, 0, sizeof(unsigned long long) * (size_t)ctx->tpl_count, ctx->stream);
+        const int nb = (ctx->n + 255) / 256;
+        k_tile_deltas<<<nb, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpl_code, ctx->n, n, total, t->g0, t->tdelta, bad);
+        k_tile_deltas_verify<<<nb, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->colidx, ctx->tpl_code, ctx->n, n, total, t->g0,
+                                                          t->tdelta, bad);
+        ctx->launches += 2;
+        if (cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) break;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) break;
+    } while (0);
+    cudaFree(bad);
+    cudaGetLastError();
+    for (int k = 0; k <= TL_KMAX; ++k) { cudaFree(t->list[k]); t->list[k] = nullptr; t->count[k] = 0; }
+    if (hbad != 0) { cudaFree(t->tdelta); t->tdelta = nullptr; return 0; }
+    cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    ctx->tiles_ok = true;
+    return 0;
+}
+
+// Declares that local row i is DoF g0 + i of dolfin's CG1 numbering on RectangleMesh(n_cells x n_cells, "right")
+// (fct_mesh_rect_build).  The pattern is verified on the device; on a mismatch the context simply keeps the per-pass kernels.
+extern "C" int fct_ctx_set_rect(fct_ctx* ctx, int32_t n_cells, int64_t g0) {
+    FCT_CHECK(ctx && n_cells >= 1 && g0 >= 0, "fct_ctx_set_rect: bad argument");
+    FCT_CHECK(n_cells <= 23000, "fct_ctx_set_rect: mesh too large for 32-bit row arithmetic");
+    fct_tiles_free(ctx);
+    ctx->tiles = new fct_tiles();
+    ctx->tiles->n_cells = n_cells;
+    ctx->tiles->g0 = (int)g0;
+    return fct_tiles_prepare(ctx);
+}
+
+extern "C" int fct_tiles_active(fct_ctx* ctx, int32_t* active) {
+    FCT_CHECK(ctx && active, "fct_tiles_active: null argument");
+    *active = ctx->tiles_ok ? 1 : 0;
+    return 0;
+}
+
+static int fill_args(fct_ctx* ctx, int K, TileArgs& a) {
+    fct_tiles* t = ctx->tiles;
+    if (build_tile_list(ctx, K)) return 1;
+    a.n_cells = t->n_cells; a.total = (t->n_cells + 1) * (t->n_cells + 1); a.g0 = t->g0; a.nloc = ctx->n;
+    a.own_rb = ctx->row_begin; a.own_re = ctx->row_end; a.ntiles = t->count[K]; a.tiles = t->list[K];
+    a.rowptr = ctx->rowptr; a.code = ctx->tpl_code; a.tdelta = t->tdelta; a.tval = ctx->tpl_val; a.tdiag = ctx->tpl_diag;
+    a.Lv = nullptr; a.b = nullptr; a.xin = nullptr; a.yold = nullptr; a.xout = nullptr; a.yold_out = nullptr;
+    a.jstate = ctx->jstate;
+    for (int i = 0; i < TL_KMAX; ++i) a.om[i] = 0.0;
+    a.dscale = 1.0;
+    return 0;
+}
+
+// K (2..4) Jacobi sweeps of the row-scaled low-order system in one launch: xout <- sweep^K(xin); accumulates the
+// stopping-test maxima of the last sweep and adds K to the sweep counter
+int fct_tile_jacobi(fct_ctx* ctx, int K, const double* Lv, const double* b, const double* xin, double* xout) {
+    FCT_CHECK(ctx->tiles_ok && K >= 2 && K <= 4, "fct_tile_jacobi: not available");
+    TileArgs a;
+    if (fill_args(ctx, K, a)) return 1;
+    a.Lv = Lv; a.b = b; a.xin = xin; a.xout = xout;
+    const int grid = a.ntiles < ctx->tiles->sms ? a.ntiles : ctx->tiles->sms;
+    if (grid <= 0) return 0;
+    const bool w7 = ctx->max_row <= 7;
+    switch (K) {
+        case 2: if (w7) tile_launch_t<0, 2, 7>(ctx, a, grid); else tile_launch_t<0, 2, 8>(ctx, a, grid); break;
+        case 3: if (w7) tile_launch_t<0, 3, 7>(ctx, a, grid); else tile_launch_t<0, 3, 8>(ctx, a, grid); break;
+        default: if (w7) tile_launch_t<0, 4, 7>(ctx, a, grid); else tile_launch_t<0, 4, 8>(ctx, a, grid); break;
+    }
+    ctx->launches++;
+    return 0;
+}
+
+// K (2..5) Chebyshev iterations in one launch with the weights om[0..K): (ymid, yold) -> (ymid_out, yold_out)
+int fct_tile_cheb(fct_ctx* ctx, int K, const double* g, const double* ymid, const double* yold, double* ymid_out,
+                  double* yold_out, const double* om, double dscale) {
+    FCT_CHECK(ctx->tiles_ok && K >= 2 && K <= TL_KMAX, "fct_tile_cheb: not available");
+    TileArgs a;
+    if (fill_args(ctx, K, a)) return 1;
+    a.b = g; a.xin = ymid; a.yold = yold; a.xout = ymid_out; a.yold_out = yold_out; a.dscale = dscale;
+    for (int i = 0; i < K; ++i) a.om[i] = om[i];
+    const int grid = a.ntiles < ctx->tiles->sms ? a.ntiles : ctx->tiles->sms;
+    if (grid <= 0) return 0;
+    const bool w7 = ctx->max_row <= 7;
+    switch (K) {
+        case 2: if (w7) tile_launch_t<1, 2, 7>(ctx, a, grid); else tile_launch_t<1, 2, 8>(ctx, a, grid); break;
+        case 3: if (w7) tile_launch_t<1, 3, 7>(ctx, a, grid); else tile_launch_t<1, 3, 8>(ctx, a, grid); break;
+        case 4: if (w7) tile_launch_t<1, 4, 7>(ctx, a, grid); else tile_launch_t<1, 4, 8>(ctx, a, grid); break;
+        default: if (w7) tile_launch_t<1, 5, 7>(ctx, a, grid); else tile_launch_t<1, 5, 8>(ctx, a, grid); break;
+    }
+    ctx->launches++;
+    return 0;
+}

@@ -64,8 +64,9 @@ def column_ranges(rowptr, colidx, bounds, depth=1):
 class LocalProblem:
     """Everything rank `rank` needs to build its context from the global mesh description."""
 
-    def __init__(self, rowptr, colidx, cells, dof_xy, rank, world, depth=1):
+    def __init__(self, rowptr, colidx, cells, dof_xy, rank, world, depth=1, rect_n=None):
         n = len(rowptr) - 1
+        self.rect_n = rect_n          # cells per side when the global numbering is RectMeshP1's (enables the tile kernels)
         self.n_global = n
         self.rank, self.world = int(rank), int(world)
         self.depth = int(depth)
@@ -133,6 +134,8 @@ class LocalProblem:
     def make_context(self, device):
         ctx = FctContext(self.rowptr, self.colidx, device=device, row_begin=self.row_begin, row_end=self.row_end)
         ctx.set_mesh(self.cells, self.dof_xy)
+        if self.rect_n:
+            ctx.set_rect(self.rect_n, self.G0)
         if self.world > 1:
             check(lib.fct_ctx_set_rings(ctx.handle, self.depth, self.ring_lo.ctypes.data_as(C.POINTER(C.c_int32)),
                                         self.ring_hi.ctypes.data_as(C.POINTER(C.c_int32))))
@@ -192,7 +195,8 @@ def setup_rank(mesh, rank, world, local_rank, depth=None):
     depth: halo depth in mesh rings (default 4, FCT_HALO_DEPTH overrides; 1 = exchange after every pass)"""
     if depth is None:
         depth = int(os.environ.get("FCT_HALO_DEPTH", "4"))
-    lp = LocalProblem(mesh.rowptr, mesh.colidx, mesh.cells, mesh.dof_xy, rank, world, depth=depth if world > 1 else 1)
+    lp = LocalProblem(mesh.rowptr, mesh.colidx, mesh.cells, mesh.dof_xy, rank, world, depth=depth if world > 1 else 1,
+                      rect_n=getattr(mesh, "n", None))
     ctx = lp.make_context(local_rank)
     if world > 1:
         init_comm(ctx, lp, torch_broadcaster())

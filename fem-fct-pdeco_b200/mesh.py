@@ -51,6 +51,7 @@ class RectMeshP1:
         if self._ctx is None:
             ctx = FctContext(self.rowptr, self.colidx, device=device)
             ctx.set_mesh(self.cells, self.dof_xy)
+            ctx.set_rect(self.n, 0)
             ctx.assemble_static()
             self._ctx = ctx
         return self._ctx

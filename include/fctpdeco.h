@@ -85,6 +85,17 @@ int fct_ctx_set_lumped(fct_ctx* ctx, const double* ML_dev);
 int fct_assemble_static(fct_ctx* ctx);
 int fct_ctx_static_dev(fct_ctx* ctx, const double** M_dev, const double** ML_dev, const double** Mdiag_dev,
                        const double** K_dev);
+/* Structured numbering: declares that local row i is DoF g0 + i of dolfin's CG1 numbering on
+ * RectangleMesh(n_cells x n_cells, diagonal "right") -- what fct_mesh_rect_build produces (advection_solidbody_FCT.py:48-50,82;
+ * SURVEY.md App. B.2).  The pattern is verified on the device; when it holds (and the mass matrix has row templates) the
+ * low-order Jacobi solve and ChebSI run K sweeps / iterations per launch on overlapped (diagonal, position) tiles, with
+ * results bit-identical to the per-sweep kernels.  Other meshes simply keep the per-sweep kernels. */
+int fct_ctx_set_rect(fct_ctx* ctx, int32_t n_cells, int64_t g0);
+int fct_tiles_active(fct_ctx* ctx, int32_t* active_out);
+/* test hook (host only, no device needed): interior origins (diagonal, position) of the tiles that cover rows
+ * [row_begin,row_end) of a block starting at global DoF g0, for K fused passes; geom_out = {region diagonals, region positions} */
+int fct_debug_tile_list(int32_t n_cells, int64_t g0, int32_t row_begin, int32_t row_end, int32_t K, int32_t* d0p0_out,
+                        int32_t cap, int32_t* count_out, int32_t* geom_out);
 /* solver options for the low-order system (defaults: rtol 1e-14, max_sweeps 200, check_every 2) */
 int fct_ctx_set_solver(fct_ctx* ctx, double rtol, int32_t max_sweeps);
 
@@ -227,13 +238,13 @@ int fct_p2p_error(fct_ctx* ctx, int32_t* error_host);
  * stream (the dominant kernel of the FCT step once the mass matrix runs on row templates); bench.py's roofline */
 int fct_bench_jacobi_sweeps(fct_ctx* ctx, const double* A_dev, const double* u_n_dev, double dt, int32_t reps,
                             float* ms_per_sweep_host);
-/* the same system through the wavefront kernel (fct_win.cu): `reps` launches of exactly `sweeps` (even, <= 32) fused
- * Jacobi sweeps; returns the CUDA-event time per sweep.  Fails if the context has no wavefront kernels (no row
- * templates, multi-GPU, FCT_WIN=0). */
+/* the same system through the overlapped-tile kernel (fct_tile.cu): `reps` launches of `sweeps` (2..4) fused Jacobi sweeps
+ * each; returns the CUDA-event time per sweep.  Fails if the context has no tile kernels (fct_ctx_set_rect not called or
+ * not verified, no row templates, FCT_NO_TILES=1). */
 int fct_bench_jacobi_fused(fct_ctx* ctx, const double* A_dev, const double* u_n_dev, double dt, int32_t sweeps,
                            int32_t reps, float* ms_per_sweep_host);
-/* test hook: exactly `sweeps` (even) Jacobi sweeps on the low-order system of (A, u_n, dt) from the initial guess u_n,
- * one launch per sweep (fused = 0) or as one wavefront launch (fused = 1); the iterate is copied to x_out_dev */
+/* test hook: exactly `sweeps` Jacobi sweeps on the low-order system of (A, u_n, dt) from the initial guess u_n, one launch
+ * per sweep (fused = 0) or as tile launches of `fused` (2..4) sweeps each; the iterate is copied to x_out_dev */
 int fct_debug_jacobi_fixed(fct_ctx* ctx, const double* A_dev, const double* u_n_dev, double dt, int32_t sweeps,
                            int32_t fused, double* x_out_dev);
 /* number of row templates the static mass matrix compressed to (0 = CSR kernels in use) */
