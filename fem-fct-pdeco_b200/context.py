@@ -305,23 +305,36 @@ class FctContext:
         return ms.value
 
     def bench_dominant_kernel(self, c, u_n, dt):
-        """CUDA-event time of the kernel with the largest share of an FCT step (the low-order Jacobi sweep) on the drift
-        operator of control `c`, with the bytes it has to move per launch and the SURVEY App. E accounting
-        bytes of the same work; bench.py's `roofline`"""
+        """CUDA-event time of the kernel with the largest share of an FCT step (the low-order Jacobi solve: fused K-sweep
+        tile launches on structured numberings, else one launch per sweep) on the drift operator of control `c`, with the
+        bytes it has to move per launch and the SURVEY App. E accounting bytes of the same work; bench.py's
+        `roofline`"""
         n, nnz = self.n, self.nnz
         A = self.empty(nnz)
         self.assemble_matrix(_lib.FORM_DRIFT, A, c0=c, s0=1.0, s1=1.0, scale=-1.0)
-        ms = self.bench_jacobi_sweeps(A, u_n, dt, reps=20)
-        A.free()
         appE = 12 * nnz + 4 * n + 3 * 8 * n
+        try:
+            if self.tiles_active():
+                K = 4
+                ms = min(self.bench_jacobi_fused(A, u_n, dt, sweeps=K, reps=6) for _ in range(3)) * K
+                return {"name": "k_tile", "ms_per_launch": ms, "appE_bytes": K * appE, "sweeps_per_launch": K,
+                        "what": f"{K} fused Jacobi sweeps of the low-order solve on overlapped (diagonal, position) tiles "
+                                "(4 launches per FCT step); shared-memory-bound, not HBM-bound: it moves a quarter of the "
+                                "per-sweep kernels' bytes",
+                        "bytes_per_launch": 8 * nnz + 3 * 8 * n,
+                        "bytes_model": "8 B/nnz row-scaled L values + b, x, x_new: 3 x 8 B/row, once per 4 sweeps (frame "
+                                       "re-reads are L2 hits)"}
+            ms = self.bench_jacobi_sweeps(A, u_n, dt, reps=20)
+        finally:
+            A.free()
         if self.template_count():
-            return {"name": "k_jacobi_sweep_tpl", "ms_per_launch": ms, "appE_bytes": appE,
+            return {"name": "k_jacobi_sweep_tpl", "ms_per_launch": ms, "appE_bytes": appE, "sweeps_per_launch": 1,
                     "what": "one Jacobi sweep of the low-order solve (~14 launches per FCT step)",
                     "bytes_per_launch": 8 * nnz + 2 * n + 4 * n + 3 * 8 * n,
                     "bytes_model": "8 B/nnz row-scaled L values + 2 B/row template code + 4 B/row rowptr + b, x (gathered), "
                                    "x_new: 3 x 8 B/row"}
         return {"name": "k_jacobi_sweep", "ms_per_launch": ms, "appE_bytes": appE, "bytes_per_launch": appE,
-                "what": "one Jacobi sweep of the low-order solve (CSR kernel)",
+                "sweeps_per_launch": 1, "what": "one Jacobi sweep of the low-order solve (CSR kernel)",
                 "bytes_model": "12 B/nnz values + column indices, 4 B/row rowptr, 3 x 8 B/row vectors"}
 
     def debug_jacobi_fixed(self, A, u_n, dt, sweeps, fused, x_out):

@@ -42,20 +42,26 @@ extern __shared__ __align__(16) unsigned char fct_smem[];
 #define TL_THREADS TL_NT
 #define TL_KMAX 5
 static_assert(TL_R * TL_NT >= TL_NC * TL_NQ, "every compute-set row needs a thread");
+static_assert(TL_NQ > 32, "the row -> thread map deals 32 positions of a diagonal to a warp and the rest separately");
 static_assert(TL_XS + 1 <= 127, "neighbour deltas must fit a signed byte");
+// tile flags, set by k_tile_classify from the data (never assumed): every row of the compute set exists, has 7 entries and
+// the interior neighbour layout above (UP) / below (LO) the main anti-diagonal; all its mass-matrix rows carry the same values
+#define TL_F_UP 1
+#define TL_F_LO 2
+#define TL_F_MUNI 4
 
 struct fct_tiles {
     int n_cells = 0;                  // cells per side of the structured mesh
     int g0 = 0;                       // global DoF index of local row 0
     unsigned long long* tdelta = nullptr;      // [templates] 8 signed bytes: shared-memory index delta of each row entry
-    int2* list[TL_KMAX + 1] = {nullptr};       // per K: interior origins (d0, p0) of the tiles covering the owned rows
+    int4* list[TL_KMAX + 1] = {nullptr};       // per K: tile records {d0, p0, flags, value code} covering the owned rows
     int count[TL_KMAX + 1] = {0};
     int sms = 148;
 };
 
 struct TileArgs {
-    int n_cells, total, g0, nloc, own_rb, own_re, ntiles;
-    const int2* tiles;
+    int n_cells, total, g0, nloc, own_rb, own_re, ntiles, K;
+    const int4* tiles;     // {interior origin d0, p0, flags (TL_F_*), template code whose values every row of the tile shares}
     const int32_t* rowptr;
     const uint16_t* code;
     const unsigned long long* tdelta;
@@ -174,23 +180,87 @@ struct TileSmem {
     static constexpr int SEGCAP = (TL_NQ * W + 2 + 1) & ~1;                        // staged CSR range of one region diagonal (even)
     static constexpr int L_DOUBLES = (MODE == 0) ? TL_NC * SEGCAP : 0;
     static constexpr int X_DOUBLES = 3 * TL_ND * TL_XS;
-    static constexpr size_t BYTES = 8 * (size_t)(L_DOUBLES + X_DOUBLES) + 4 * TL_NC;
+    static constexpr size_t BYTES = 8 * (size_t)(L_DOUBLES + X_DOUBLES) + 4 * (2 * TL_NC + 4 * TL_ND);
     static_assert(L_DOUBLES % 2 == 0, "bulk-copy destinations must stay 16-byte aligned");
 };
 
+// local rows [ra, rb) of compute-set diagonal c (region diagonal c + 1) of the tile at (dlo, plo); empty: rb <= ra
+__device__ __forceinline__ void tl_segment_rows(const TileArgs& a, int dlo, int plo, int c, int& ra, int& rb) {
+    const int n = a.n_cells, d = dlo + c + 1;
+    ra = 0; rb = 0;
+    if (d < 0 || d > 2 * n) return;
+    const int len = tl_diag_len(d, n), st = tl_diag_start(d, n, a.total) - a.g0;
+    const int pa = max(plo + 1, 0), pb = min(plo + TL_NP - 1, len);
+    if (pb <= pa) return;
+    ra = max(st + pa, 0); rb = min(st + pb, a.nloc);
+}
+
+// The K dependent passes of one tile.  KIND 1 / 2: every row of the tile has the interior neighbour layout above / below the
+// main anti-diagonal (shared-memory loads with immediate offsets); KIND 0: per-row deltas from the template table.
+// Straight-line code over the thread's rows (no per-row branches: the 21 loads and the three FMA chains interleave); rows
+// that are not part of pass s are computed on whatever their slots hold and simply not stored.
+template <int MODE, int W, int KIND>
+__device__ __forceinline__ void tl_passes(int K, double* A, double* B, const int (&xi)[TL_R], const int (&ml)[TL_R],
+                                          const int (&row)[TL_R], const double (&Lr)[TL_R][W],
+                                          const unsigned long long (&dpk)[TL_R], const double (&br)[TL_R], double (&yo)[TL_R],
+                                          const double (&md)[TL_R], const double* __restrict__ om) {
+#pragma unroll 1
+    for (int s = 1; s <= K; ++s) {
+        const double* in = (s & 1) ? A : B;
+        double* out = (s & 1) ? B : A;
+        double acc[TL_R];
+#pragma unroll
+        for (int i = 0; i < TL_R; ++i) {
+            const double* p = in + xi[i];
+            double t = 0.0;
+            if (KIND == 1) {
+                t += Lr[i][0] * p[-TL_XS - 1]; t += Lr[i][1] * p[-TL_XS]; t += Lr[i][2] * p[-1]; t += Lr[i][3] * p[0];
+                t += Lr[i][4] * p[1]; t += Lr[i][5] * p[TL_XS]; t += Lr[i][W - 1] * p[TL_XS + 1];
+            } else if (KIND == 2) {
+                t += Lr[i][0] * p[-TL_XS]; t += Lr[i][1] * p[-TL_XS + 1]; t += Lr[i][2] * p[-1]; t += Lr[i][3] * p[0];
+                t += Lr[i][4] * p[1]; t += Lr[i][5] * p[TL_XS - 1]; t += Lr[i][W - 1] * p[TL_XS];
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) t += Lr[i][jj] * p[tl_delta(dpk[i], jj)];
+            }
+            acc[i] = t;
+        }
+#pragma unroll
+        for (int i = 0; i < TL_R; ++i) {
+            const bool act = row[i] >= 0 && s <= ml[i];
+            if (MODE == 0) {
+                if (act) out[xi[i]] = br[i] - acc[i];
+            } else {
+                const double ym = in[xi[i]];
+                const double z = (br[i] - acc[i]) / md[i];
+                const double yn = om[s - 1] * (z + ym - yo[i]) + yo[i];
+                if (act) { out[xi[i]] = yn; yo[i] = ym; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // MODE 0: K Jacobi sweeps  x <- b' - sum_j l'_ij x_j  of the row-scaled low-order system (k_jacobi_sweep_tpl<., true>)
 // MODE 1: K Chebyshev iterations  y+ = om (z + y - y-) + y-,  z = (g - M y) / (dscale diag M)  (k_cheb_iter_tpl)
-// Every warp computes; the loads of tile j+1 are issued by all threads at the start of tile j's passes: the iterate of the
-// region with 8-byte cp.async (each thread its own 3-4 entries), the matrix rows of each region diagonal with one 1-D TMA
-// bulk copy (lane 0 of warp c % 16), the right-hand side (and y_old) of the thread's rows straight into registers.  One
-// mbarrier collects all of them (cp.async completions + TMA transaction bytes).
-template <int MODE, int K, int W>
+// Every warp computes.  Software pipeline over the CTA's tiles (all loads are issued by the compute threads themselves):
+//   during tile j   : the CSR bounds of tile j+2's diagonal segments and the template data of tile j+1 travel (registers);
+//                     tile j+1's iterate (8-byte cp.async), matrix rows (one 1-D TMA bulk copy per region diagonal) and
+//                     right-hand side (registers) are in flight, all shared-memory traffic completing on one mbarrier;
+//   top of tile j+1 : matrix rows move from the staging buffer to registers, the buffer is handed to tile j+2.
+// "Regular" tiles (flags from k_tile_classify: every row exists, 7 entries, one of the two interior layouts -- 93 % of the
+// tiles at 4097^2) skip the per-row row-pointer / template look-ups altogether.
+template <int MODE, int W>
 __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
+    const int K = a.K;
     if (MODE == 0 && *reinterpret_cast<volatile unsigned long long*>(a.jstate + 3)) return;      // already converged
     using SM = TileSmem<MODE, W>;
     double* sL = reinterpret_cast<double*>(fct_smem);
     double* sX = sL + SM::L_DOUBLES;
-    int* sSeg = reinterpret_cast<int*>(sX + SM::X_DOUBLES);          // [TL_NC]: first staged CSR index of each L segment
+    int* sKa = reinterpret_cast<int*>(sX + SM::X_DOUBLES);          // [NC] first staged CSR index of each L segment
+    int* sSh = sKa + TL_NC;                                          // [NC] staged offset of the segment's first row
+    int* sRow = sSh + TL_NC;                                         // [2][ND] local row of (dl, pl = 0), per tile parity
+    int* sLen = sRow + 2 * TL_ND;                                    // [2][ND] length of region diagonal dl (0: outside the mesh)
     __shared__ __align__(8) uint64_t bar_full;
     __shared__ double sred[2][TL_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -198,48 +268,100 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
         mbar_init(&bar_full, TL_NT + (MODE == 0 ? TL_NT / 32 : 0));      // cp.async completions (+ one expect_tx arrival per warp)
         mbar_fence_init();
     }
-    __syncthreads();
     const int n = a.n_cells, total = a.total;
     const int nmine = ((int)blockIdx.x < a.ntiles) ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    // tile records are fetched three tiles ahead into registers (rec1..rec3 = tiles j+1..j+3 while tile j is computed), so
+    // that no thread ever waits for one
+    auto fetch_rec = [&](int j) {
+        return j < nmine ? __ldg(a.tiles + (int)blockIdx.x + j * (int)gridDim.x) : make_int4(0, 0, 0, 0);
+    };
+    int4 rec0 = fetch_rec(0), rec1 = fetch_rec(1), rec2 = fetch_rec(2), rec3 = fetch_rec(3);
+    int recj = 0;                                    // rec0 is the record of tile recj
+    auto tile_of = [&](int j) { return j == recj ? rec0 : j == recj + 1 ? rec1 : j == recj + 2 ? rec2 : rec3; };
+    auto is_regular = [&](int flag) { return MODE == 0 ? (W == 7 && (flag & 3) != 0) : (W == 7 && (flag & 3) != 0 && (flag & TL_F_MUNI) != 0); };
 
     // rows this thread updates (compute set) and region entries it loads: fixed for the whole launch
+    // (a warp takes 32 consecutive positions of one diagonal -- conflict-free 8-byte shared-memory accesses --, the
+    // TL_NQ - 32 positions left over on each diagonal are dealt to the remaining slots)
     int xi[TL_R], ml[TL_R], dlr[TL_R], plr[TL_R];
 #pragma unroll
     for (int i = 0; i < TL_R; ++i) {
         const int q = tid + i * TL_NT;
         const bool has = q < TL_NC * TL_NQ;
-        const int dc = has ? q / TL_NQ : 0, pc = has ? q % TL_NQ : 0;
+        int dc = 0, pc = 0;
+        if (has) {
+            if (q < TL_NC * 32) { dc = q >> 5; pc = q & 31; }
+            else { const int t = q - TL_NC * 32; dc = t / (TL_NQ - 32); pc = 32 + t % (TL_NQ - 32); }
+        }
         dlr[i] = dc + 1; plr[i] = pc + 1;
         xi[i] = dlr[i] * TL_XS + plr[i];
         ml[i] = has ? min(min(dlr[i], TL_ND - 1 - dlr[i]), min(plr[i], TL_NP - 1 - plr[i])) : 0;
     }
     constexpr int NE = (TL_ND * TL_NP + TL_NT - 1) / TL_NT;          // region entries per thread
+    int edl[NE], epl[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+        const int e = tid + i * TL_NT;
+        edl[i] = e < TL_ND * TL_NP ? e / TL_NP : -1;
+        epl[i] = e < TL_ND * TL_NP ? e % TL_NP : 0;
+    }
+    // per-tile table of the region's diagonals (threads 0..ND-1), double-buffered by tile parity
+    auto diag_table = [&](int j) {
+        if (tid < TL_ND && j < nmine) {
+            const int4 t = tile_of(j);
+            const int d = t.x - K + tid;
+            const bool in = d >= 0 && d <= 2 * n;
+            sLen[(j & 1) * TL_ND + tid] = in ? tl_diag_len(d, n) : 0;
+            sRow[(j & 1) * TL_ND + tid] = in ? tl_diag_start(d, n, total) + (t.y - K) - a.g0 : 0;
+        }
+    };
+    // CSR bounds of the L segments this lane will issue for tile j (lanes 0..2 of each warp: segments warp + 16 lane)
+    int sb_k0 = 0, sb_k1 = 0;
+    auto load_seg_bounds = [&](int j) {
+        sb_k0 = 0; sb_k1 = 0;
+        if (MODE != 0 || j >= nmine) return;
+        const int c = warp + (TL_NT / 32) * lane;
+        if (lane < 3 && c < TL_NC) {
+            const int4 t = tile_of(j);
+            int ra, rb;
+            tl_segment_rows(a, t.x - K, t.y - K, c, ra, rb);
+            if (rb > ra) { sb_k0 = a.rowptr[ra]; sb_k1 = a.rowptr[rb]; }
+        }
+    };
 
-    int row[TL_R], nrow[TL_R], ncode[TL_R], nk0[TL_R], nlen[TL_R];
+    int row[TL_R], nrow[TL_R], ncode[TL_R], nk0[TL_R], nk1[TL_R];
     unsigned long long dpk[TL_R];
     double Lr[TL_R][W], br[TL_R], nb[TL_R], yo[TL_R], nyo[TL_R], md[TL_R];
-    // rows of tile j and the first loads they need (row pointer, template code, right-hand side), issued one tile ahead
+    int nflag = 0, nvcode = 0;
+    // rows of tile j and the first loads they need (right-hand side; for general tiles row pointer and template code)
     auto prefetch_meta = [&](int j) {
 #pragma unroll
-        for (int i = 0; i < TL_R; ++i) { nrow[i] = -1; ncode[i] = 0; nk0[i] = 0; nlen[i] = 0; nb[i] = 0.0; nyo[i] = 0.0; }
+        for (int i = 0; i < TL_R; ++i) { nrow[i] = -1; ncode[i] = 0; nk0[i] = 0; nk1[i] = 0; nb[i] = 0.0; nyo[i] = 0.0; }
+        nflag = 0; nvcode = 0;
         if (j >= nmine) return;
-        const int2 t = a.tiles[(int)blockIdx.x + j * (int)gridDim.x];
+        const int4 t = tile_of(j);
+        nflag = t.z; nvcode = t.w;
+        const bool reg = is_regular(nflag);
+        const int plo = t.y - K;
+        const int* tr = sRow + (j & 1) * TL_ND;
+        const int* tl = sLen + (j & 1) * TL_ND;
 #pragma unroll
         for (int i = 0; i < TL_R; ++i) {
             if (ml[i] == 0) continue;
-            const int d = t.x - K + dlr[i], pos = t.y - K + plr[i];
-            if (d < 0 || d > 2 * n || pos < 0 || pos >= tl_diag_len(d, n)) continue;
-            const int r = tl_diag_start(d, n, total) + pos - a.g0;
-            if (r < 0 || r >= a.nloc) continue;
+            const int r = tr[dlr[i]] + plr[i];
+            if ((unsigned)(plo + plr[i]) >= (unsigned)tl[dlr[i]] || (unsigned)r >= (unsigned)a.nloc) continue;
             nrow[i] = r;
-            ncode[i] = a.code[r];
             nb[i] = a.b[r];
-            if (MODE == 0) { nk0[i] = a.rowptr[r]; nlen[i] = a.rowptr[r + 1] - nk0[i]; }
             if (MODE == 1 && a.yold) nyo[i] = a.yold[r];
+            if (!reg) {
+                ncode[i] = a.code[r];
+                if (MODE == 0) { nk0[i] = a.rowptr[r]; nk1[i] = a.rowptr[r + 1]; }
+            }
         }
     };
     // second-level loads (depend on the template code): neighbour deltas, and for ChebSI the mass-matrix row
     auto load_meta2 = [&]() {
+        const bool reg = is_regular(nflag);
 #pragma unroll
         for (int i = 0; i < TL_R; ++i) {
             dpk[i] = 0ull;
@@ -249,117 +371,101 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
                 for (int jj = 0; jj < W; ++jj) Lr[i][jj] = 0.0;
             }
             if (nrow[i] < 0) continue;
-            dpk[i] = __ldg(a.tdelta + ncode[i]);
+            const int cd = reg ? nvcode : ncode[i];
+            if (!reg) dpk[i] = __ldg(a.tdelta + cd);
             if (MODE == 1) {
 #pragma unroll
-                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = __ldg(a.tval + FCT_TPL_W * ncode[i] + jj);
-                md[i] = a.dscale * __ldg(a.tdiag + ncode[i]);
+                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = __ldg(a.tval + FCT_TPL_W * cd + jj);
+                md[i] = a.dscale * __ldg(a.tdiag + cd);
             }
         }
     };
-    // everything tile j needs in shared memory; the caller guarantees that its destination buffers are free
-    auto issue_loads = [&](int j) {
-        if (j >= nmine) return;
-        const int2 t = a.tiles[(int)blockIdx.x + j * (int)gridDim.x];
-        const int dlo = t.x - K, plo = t.y - K;
-        double* xb = sX + (j % 3) * (TL_ND * TL_XS);
+    // the iterate of tile j's region -> iterate buffer j % 3; the caller guarantees that the buffer is free
+    auto issue_x = [&](int j) {
+        if (j < nmine) {
+            const int plo = tile_of(j).y - K;
+            const int* tr = sRow + (j & 1) * TL_ND;
+            const int* tl = sLen + (j & 1) * TL_ND;
+            double* xb = sX + (j % 3) * (TL_ND * TL_XS);
 #pragma unroll
-        for (int i = 0; i < NE; ++i) {
-            const int e = tid + i * TL_NT;
-            if (e >= TL_ND * TL_NP) continue;
-            const int dl = e / TL_NP, pl = e % TL_NP;
-            const int d = dlo + dl, pos = plo + pl;
-            if (d < 0 || d > 2 * n || pos < 0 || pos >= tl_diag_len(d, n)) continue;
-            const int r = tl_diag_start(d, n, total) + pos - a.g0;
-            if (r >= 0 && r < a.nloc) cp_async8(xb + dl * TL_XS + pl, a.xin + r);
+            for (int i = 0; i < NE; ++i) {
+                if (edl[i] < 0) continue;
+                const int r = tr[edl[i]] + epl[i];
+                if ((unsigned)(plo + epl[i]) < (unsigned)tl[edl[i]] && (unsigned)r < (unsigned)a.nloc)
+                    cp_async8(xb + edl[i] * TL_XS + epl[i], a.xin + r);
+            }
         }
         cp_async_mbar_arrive(&bar_full);
-        if (MODE == 0 && lane == 0) {
-            uint32_t tx = 0;
-            for (int c = warp; c < TL_NC; c += TL_NT / 32) {
-                const int d = dlo + c + 1;
-                int ka = 0;
-                if (d >= 0 && d <= 2 * n) {
-                    const int len = tl_diag_len(d, n), st = tl_diag_start(d, n, total) - a.g0;
-                    const int pa = max(plo + 1, 0), pb = min(plo + TL_NP - 1, len);
-                    const int ra = max(st + pa, 0), rb = min(st + pb, a.nloc);
-                    if (pb > pa && rb > ra) {
-                        const int k0 = a.rowptr[ra], k1 = a.rowptr[rb];
-                        ka = k0 - (int)((reinterpret_cast<uintptr_t>(a.Lv + k0) >> 3) & 1);
-                        const uint32_t bytes = (uint32_t)(((k1 - ka) + 1) & ~1) * 8u;
-                        tma_load_1d(sL + c * SM::SEGCAP, a.Lv + ka, bytes, &bar_full);
-                        tx += bytes;
-                    }
-                }
-                sSeg[c] = ka;
+    };
+    // the matrix rows of tile j's diagonals -> staging buffer (bounds loaded one tile earlier by load_seg_bounds)
+    auto issue_L = [&](int j) {
+        if (MODE != 0) return;
+        uint32_t tx = 0;
+        const int c = warp + (TL_NT / 32) * lane;
+        if (lane < 3 && c < TL_NC && j < nmine) {
+            int ka = 0, sh = 0;
+            if (sb_k1 > sb_k0) {
+                sh = (int)((reinterpret_cast<uintptr_t>(a.Lv + sb_k0) >> 3) & 1);
+                ka = sb_k0 - sh;
+                const uint32_t bytes = (uint32_t)(((sb_k1 - ka) + 1) & ~1) * 8u;
+                tma_load_1d(sL + c * SM::SEGCAP, a.Lv + ka, bytes, &bar_full);
+                tx = bytes;
             }
-            mbar_expect_tx(&bar_full, tx);          // one arrival per warp (release: the sSeg stores above are ordered before it)
+            sKa[c] = ka; sSh[c] = sh;
         }
+        tx += __shfl_down_sync(0xffffffffu, tx, 1) + __shfl_down_sync(0xffffffffu, tx, 2);
+        __syncwarp();                                          // the sKa / sSh stores of lanes 1, 2 are ordered before ...
+        if (lane == 0) mbar_expect_tx(&bar_full, tx);          // ... the (releasing) arrival, one per warp
     };
 
+    diag_table(0);
+    diag_table(1);
+    load_seg_bounds(0);
+    __syncthreads();          // barrier initialised, diagonal tables of tiles 0 and 1 visible
     prefetch_meta(0);
-    issue_loads(0);
+    issue_x(0);
+    issue_L(0);
+    load_seg_bounds(1);
     load_meta2();
     double delta = 0.0, xa = 0.0;
     for (int j = 0; j < nmine; ++j) {
+        const int flag = nflag;
+        const bool reg = is_regular(flag);
         int k0r[TL_R], lenr[TL_R];
 #pragma unroll
-        for (int i = 0; i < TL_R; ++i) { row[i] = nrow[i]; k0r[i] = nk0[i]; lenr[i] = nlen[i]; br[i] = nb[i]; yo[i] = nyo[i]; }
+        for (int i = 0; i < TL_R; ++i) { row[i] = nrow[i]; k0r[i] = nk0[i]; lenr[i] = nk1[i] - nk0[i]; br[i] = nb[i]; yo[i] = nyo[i]; }
         mbar_wait_bounded(&bar_full, (uint32_t)(j & 1));
         if (MODE == 0) {
             // staged matrix rows -> registers
 #pragma unroll
             for (int i = 0; i < TL_R; ++i) {
-#pragma unroll
-                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = 0.0;
-                if (row[i] < 0) continue;
                 const int c = dlr[i] - 1;
-                const double* p = sL + c * SM::SEGCAP + (k0r[i] - sSeg[c]);
+                if (reg) {
+                    const double* p = sL + c * SM::SEGCAP + sSh[c] + W * (plr[i] - 1);
 #pragma unroll
-                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = (jj < lenr[i]) ? p[jj] : 0.0;
-            }
-        }
-        __syncthreads();          // the staging buffer and the third iterate buffer are free (every thread is past tile j-1)
-        prefetch_meta(j + 1);
-        issue_loads(j + 1);
-        double* A = sX + (j % 3) * (TL_ND * TL_XS);
-        double* B = sX + ((j + 2) % 3) * (TL_ND * TL_XS);
-        int kind[TL_R];
+                    for (int jj = 0; jj < W; ++jj) Lr[i][jj] = (row[i] >= 0) ? p[jj] : 0.0;
+                } else {
 #pragma unroll
-        for (int i = 0; i < TL_R; ++i) kind[i] = (W == 7 && dpk[i] == TL_DPK_UP) ? 1 : (W == 7 && dpk[i] == TL_DPK_LO) ? 2 : 0;
+                    for (int jj = 0; jj < W; ++jj) Lr[i][jj] = 0.0;
+                    if (row[i] < 0) continue;
+                    const double* p = sL + c * SM::SEGCAP + (k0r[i] - sKa[c]);
 #pragma unroll
-        for (int s = 1; s <= K; ++s) {
-            const double* in = (s & 1) ? A : B;
-            double* out = (s & 1) ? B : A;
-#pragma unroll
-            for (int i = 0; i < TL_R; ++i) {
-                if (row[i] >= 0 && s <= ml[i]) {
-                    const double* p = in + xi[i];
-                    double acc = 0.0;
-                    if (W == 7 && kind[i] == 1) {
-                        acc += Lr[i][0] * p[-TL_XS - 1]; acc += Lr[i][1] * p[-TL_XS]; acc += Lr[i][2] * p[-1];
-                        acc += Lr[i][3] * p[0]; acc += Lr[i][4] * p[1]; acc += Lr[i][5] * p[TL_XS];
-                        acc += Lr[i][W - 1] * p[TL_XS + 1];
-                    } else if (W == 7 && kind[i] == 2) {
-                        acc += Lr[i][0] * p[-TL_XS]; acc += Lr[i][1] * p[-TL_XS + 1]; acc += Lr[i][2] * p[-1];
-                        acc += Lr[i][3] * p[0]; acc += Lr[i][4] * p[1]; acc += Lr[i][5] * p[TL_XS - 1];
-                        acc += Lr[i][W - 1] * p[TL_XS];
-                    } else {
-#pragma unroll
-                        for (int jj = 0; jj < W; ++jj) acc += Lr[i][jj] * p[tl_delta(dpk[i], jj)];
-                    }
-                    if (MODE == 0) {
-                        out[xi[i]] = br[i] - acc;
-                    } else {
-                        const double ym = p[0];
-                        const double z = (br[i] - acc) / md[i];
-                        out[xi[i]] = a.om[s - 1] * (z + ym - yo[i]) + yo[i];
-                        yo[i] = ym;
-                    }
+                    for (int jj = 0; jj < W; ++jj) Lr[i][jj] = (jj < lenr[i]) ? p[jj] : 0.0;
                 }
             }
-            __syncthreads();
         }
+        if (j > 0) { rec0 = rec1; rec1 = rec2; rec2 = rec3; rec3 = fetch_rec(j + 3); recj = j; }
+        diag_table(j + 2);          // parity of tile j, whose table nobody reads any more (its x, rows were set up one tile ago)
+        __syncthreads();            // staging buffer and third iterate buffer are free; table of tile j+1 is complete
+        prefetch_meta(j + 1);
+        issue_x(j + 1);
+        issue_L(j + 1);
+        load_seg_bounds(j + 2);
+        double* A = sX + (j % 3) * (TL_ND * TL_XS);
+        double* B = sX + ((j + 2) % 3) * (TL_ND * TL_XS);
+        if (reg && (flag & TL_F_UP)) tl_passes<MODE, W, 1>(K, A, B, xi, ml, row, Lr, dpk, br, yo, md, a.om);
+        else if (reg) tl_passes<MODE, W, 2>(K, A, B, xi, ml, row, Lr, dpk, br, yo, md, a.om);
+        else tl_passes<MODE, W, 0>(K, A, B, xi, ml, row, Lr, dpk, br, yo, md, a.om);
         // the next tile's template data travels while this tile's interior is written back
         load_meta2();
         const double* fin = (K & 1) ? B : A;
@@ -393,6 +499,48 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
     }
 }
 
+// Classifies the tiles of a list from the data: one warp per tile walks the compute set (the rows that are ever updated)
+// and checks that every row exists, has 7 entries and the neighbour layout TL_DPK_UP (or TL_DPK_LO) -- then the kernel may
+// skip the per-row look-ups -- and whether all of them carry the same mass-matrix values (then ChebSI reads them once).
+__global__ void k_tile_classify(int4* __restrict__ tiles, int ntiles, int K, int n, int total, int g0, int nloc,
+                                const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ code,
+                                const unsigned long long* __restrict__ tdelta, const double* __restrict__ tval) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= ntiles) return;
+    int4 t = tiles[w];
+    const int dlo = t.x - K, plo = t.y - K;
+    bool all = true, up = true, lo = true, muni = true;
+    int vcode = -1;
+    {   // reference row for the values: the first compute-set row
+        const int d = dlo + 1, pos = plo + 1;
+        if (d >= 0 && d <= 2 * n && pos >= 0 && pos < tl_diag_len(d, n)) {
+            const int r = tl_diag_start(d, n, total) + pos - g0;
+            if (r >= 0 && r < nloc) vcode = code[r];
+        }
+    }
+    for (int q = lane; q < TL_NC * TL_NQ; q += 32) {
+        const int d = dlo + 1 + q / TL_NQ, pos = plo + 1 + q % TL_NQ;
+        int r = -1;
+        if (d >= 0 && d <= 2 * n && pos >= 0 && pos < tl_diag_len(d, n)) r = tl_diag_start(d, n, total) + pos - g0;
+        if (r < 0 || r >= nloc) { all = false; continue; }
+        if (rowptr[r + 1] - rowptr[r] != 7) all = false;
+        const int cd = code[r];
+        const unsigned long long pk = tdelta[cd];
+        up = up && pk == TL_DPK_UP;
+        lo = lo && pk == TL_DPK_LO;
+        if (vcode >= 0)
+            for (int jj = 0; jj < FCT_TPL_W; ++jj)
+                muni = muni && __double_as_longlong(tval[FCT_TPL_W * cd + jj]) == __double_as_longlong(tval[FCT_TPL_W * vcode + jj]);
+    }
+    all = __all_sync(0xffffffffu, all); up = __all_sync(0xffffffffu, up); lo = __all_sync(0xffffffffu, lo);
+    muni = __all_sync(0xffffffffu, muni);
+    if (lane == 0) {
+        t.z = (all && up ? TL_F_UP : 0) | (all && lo ? TL_F_LO : 0) | (all && muni && vcode >= 0 ? TL_F_MUNI : 0);
+        t.w = vcode >= 0 ? vcode : 0;
+        tiles[w] = t;
+    }
+}
+
 // ======================================================================================================
 // host side
 // ======================================================================================================
@@ -407,7 +555,7 @@ void fct_tiles_free(fct_ctx* ctx) {
 
 // tiles (interior (TL_ND - 2K) diagonals x (TL_NP - 2K) positions) covering the owned global rows [ga, gb), diagonal block by
 // diagonal block; host code
-static void tile_list_host(int n, long long ga, long long gb, int K, std::vector<int2>& v) {
+static void tile_list_host(int n, long long ga, long long gb, int K, std::vector<int4>& v) {
     const int total = (n + 1) * (n + 1);
     const int Td = TL_ND - 2 * K, Tp = TL_NP - 2 * K;
     v.clear();
@@ -425,7 +573,7 @@ static void tile_list_host(int n, long long ga, long long gb, int K, std::vector
                 const long long lo = std::max(s + p0, ga), hi = std::min(s + std::min(p0 + Tp, tl_diag_len(d, n)), gb);
                 any = hi > lo;
             }
-            if (any) v.push_back(make_int2(d0, p0));
+            if (any) v.push_back(make_int4(d0, p0, 0, 0));
         }
     }
 }
@@ -434,7 +582,7 @@ static void tile_list_host(int n, long long ga, long long gb, int K, std::vector
 extern "C" int fct_debug_tile_list(int32_t n_cells, int64_t g0, int32_t row_begin, int32_t row_end, int32_t K,
                                    int32_t* d0p0_out, int32_t cap, int32_t* count_out, int32_t* geom_out /* ND, NP */) {
     FCT_CHECK(n_cells >= 1 && K >= 1 && 2 * K < TL_NP && count_out, "fct_debug_tile_list: bad argument");
-    std::vector<int2> v;
+    std::vector<int4> v;
     tile_list_host(n_cells, g0 + row_begin, g0 + row_end, K, v);
     *count_out = (int32_t)v.size();
     if (geom_out) { geom_out[0] = TL_ND; geom_out[1] = TL_NP; }
@@ -446,35 +594,35 @@ extern "C" int fct_debug_tile_list(int32_t n_cells, int64_t g0, int32_t row_begi
 static int build_tile_list(fct_ctx* ctx, int K) {
     fct_tiles* t = ctx->tiles;
     if (t->list[K]) return 0;
-    std::vector<int2> v;
+    std::vector<int4> v;
     tile_list_host(t->n_cells, (long long)t->g0 + ctx->row_begin, (long long)t->g0 + ctx->row_end, K, v);
     t->count[K] = (int)v.size();
-    if (v.empty()) { FCT_CUDA(cudaMalloc((void**)&t->list[K], sizeof(int2))); return 0; }
-    FCT_CUDA(cudaMalloc((void**)&t->list[K], sizeof(int2) * v.size()));
-    FCT_CUDA(cudaMemcpyAsync(t->list[K], v.data(), sizeof(int2) * v.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (v.empty()) { FCT_CUDA(cudaMalloc((void**)&t->list[K], sizeof(int4))); return 0; }
+    FCT_CUDA(cudaMalloc((void**)&t->list[K], sizeof(int4) * v.size()));
+    FCT_CUDA(cudaMemcpy(t->list[K], v.data(), sizeof(int4) * v.size(), cudaMemcpyHostToDevice));
+    const int n = t->n_cells;
+    k_tile_classify<<<((int)v.size() * 32 + 255) / 256, 256, 0, ctx->stream>>>(t->list[K], (int)v.size(), K, n, (n + 1) * (n + 1),
+                                                                            t->g0, ctx->n, ctx->rowptr, ctx->tpl_code, t->tdelta,
+                                                                            ctx->tpl_val);
+    ctx->launches++;
     FCT_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
-template <int MODE, int K, int W>
+template <int MODE, int W>
 static int tile_set_attr() {
-    FCT_CUDA(cudaFuncSetAttribute(k_tile<MODE, K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<MODE, W>::BYTES));
+    FCT_CUDA(cudaFuncSetAttribute(k_tile<MODE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<MODE, W>::BYTES));
     return 0;
 }
-template <int MODE, int K, int W>
+template <int MODE, int W>
 static void tile_launch_t(fct_ctx* ctx, const TileArgs& a, int grid) {
-    k_tile<MODE, K, W><<<grid, TL_THREADS, TileSmem<MODE, W>::BYTES, ctx->stream>>>(a);
+    k_tile<MODE, W><<<grid, TL_THREADS, TileSmem<MODE, W>::BYTES, ctx->stream>>>(a);
 }
 
 static int tiles_configure() {
     static bool done = false;
     if (done) return 0;
-    if (tile_set_attr<0, 2, 7>() || tile_set_attr<0, 3, 7>() || tile_set_attr<0, 4, 7>() || tile_set_attr<0, 2, 8>() ||
-        tile_set_attr<0, 3, 8>() || tile_set_attr<0, 4, 8>())
-        return 1;
-    if (tile_set_attr<1, 2, 7>() || tile_set_attr<1, 3, 7>() || tile_set_attr<1, 4, 7>() || tile_set_attr<1, 5, 7>() ||
-        tile_set_attr<1, 2, 8>() || tile_set_attr<1, 3, 8>() || tile_set_attr<1, 4, 8>() || tile_set_attr<1, 5, 8>())
-        return 1;
+    if (tile_set_attr<0, 7>() || tile_set_attr<0, 8>() || tile_set_attr<1, 7>() || tile_set_attr<1, 8>()) return 1;
     done = true;
     return 0;
 }
@@ -513,6 +661,10 @@ int fct_tiles_prepare(fct_ctx* ctx) {
     for (int k = 0; k <= TL_KMAX; ++k) { cudaFree(t->list[k]); t->list[k] = nullptr; t->count[k] = 0; }
     if (hbad != 0) { cudaFree(t->tdelta); t->tdelta = nullptr; return 0; }
     cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    // all tile lists now: the first solve may already run inside a stream capture (CUDA-graph WHILE loop of the Jacobi
+    // solve), where allocations and synchronous copies are not allowed
+    for (int k = 2; k <= TL_KMAX; ++k)
+        if (build_tile_list(ctx, k)) { cudaGetLastError(); return 0; }
     ctx->tiles_ok = true;
     return 0;
 }
@@ -537,9 +689,9 @@ extern "C" int fct_tiles_active(fct_ctx* ctx, int32_t* active) {
 
 static int fill_args(fct_ctx* ctx, int K, TileArgs& a) {
     fct_tiles* t = ctx->tiles;
-    if (build_tile_list(ctx, K)) return 1;
+    FCT_CHECK(t->list[K], "tile list for K=%d was not built", K);
     a.n_cells = t->n_cells; a.total = (t->n_cells + 1) * (t->n_cells + 1); a.g0 = t->g0; a.nloc = ctx->n;
-    a.own_rb = ctx->row_begin; a.own_re = ctx->row_end; a.ntiles = t->count[K]; a.tiles = t->list[K];
+    a.own_rb = ctx->row_begin; a.own_re = ctx->row_end; a.ntiles = t->count[K]; a.tiles = t->list[K]; a.K = K;
     a.rowptr = ctx->rowptr; a.code = ctx->tpl_code; a.tdelta = t->tdelta; a.tval = ctx->tpl_val; a.tdiag = ctx->tpl_diag;
     a.Lv = nullptr; a.b = nullptr; a.xin = nullptr; a.yold = nullptr; a.xout = nullptr; a.yold_out = nullptr;
     a.jstate = ctx->jstate;
@@ -557,12 +709,7 @@ int fct_tile_jacobi(fct_ctx* ctx, int K, const double* Lv, const double* b, cons
     a.Lv = Lv; a.b = b; a.xin = xin; a.xout = xout;
     const int grid = a.ntiles < ctx->tiles->sms ? a.ntiles : ctx->tiles->sms;
     if (grid <= 0) return 0;
-    const bool w7 = ctx->max_row <= 7;
-    switch (K) {
-        case 2: if (w7) tile_launch_t<0, 2, 7>(ctx, a, grid); else tile_launch_t<0, 2, 8>(ctx, a, grid); break;
-        case 3: if (w7) tile_launch_t<0, 3, 7>(ctx, a, grid); else tile_launch_t<0, 3, 8>(ctx, a, grid); break;
-        default: if (w7) tile_launch_t<0, 4, 7>(ctx, a, grid); else tile_launch_t<0, 4, 8>(ctx, a, grid); break;
-    }
+    if (ctx->max_row <= 7) tile_launch_t<0, 7>(ctx, a, grid); else tile_launch_t<0, 8>(ctx, a, grid);
     ctx->launches++;
     return 0;
 }
@@ -577,13 +724,7 @@ int fct_tile_cheb(fct_ctx* ctx, int K, const double* g, const double* ymid, cons
     for (int i = 0; i < K; ++i) a.om[i] = om[i];
     const int grid = a.ntiles < ctx->tiles->sms ? a.ntiles : ctx->tiles->sms;
     if (grid <= 0) return 0;
-    const bool w7 = ctx->max_row <= 7;
-    switch (K) {
-        case 2: if (w7) tile_launch_t<1, 2, 7>(ctx, a, grid); else tile_launch_t<1, 2, 8>(ctx, a, grid); break;
-        case 3: if (w7) tile_launch_t<1, 3, 7>(ctx, a, grid); else tile_launch_t<1, 3, 8>(ctx, a, grid); break;
-        case 4: if (w7) tile_launch_t<1, 4, 7>(ctx, a, grid); else tile_launch_t<1, 4, 8>(ctx, a, grid); break;
-        default: if (w7) tile_launch_t<1, 5, 7>(ctx, a, grid); else tile_launch_t<1, 5, 8>(ctx, a, grid); break;
-    }
+    if (ctx->max_row <= 7) tile_launch_t<1, 7>(ctx, a, grid); else tile_launch_t<1, 8>(ctx, a, grid);
     ctx->launches++;
     return 0;
 }
