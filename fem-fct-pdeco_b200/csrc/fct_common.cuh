@@ -53,6 +53,7 @@ struct fct_hoststage {
 struct fct_comm;   // NCCL state (fct_comm.cu)
 struct fct_p2p;    // NVLink peer-memory mailboxes (fct_p2p.cu)
 struct fct_tiles;  // structured-numbering data of the overlapped-tile kernels (fct_tile.cu)
+struct fct_cheb_tiles;
 
 // CUDA-graph WHILE loop of the low-order Jacobi solve (fct_kernels.cu), cached per operand set
 struct fct_jgraph {
@@ -119,9 +120,10 @@ struct fct_ctx {
     int32_t jac_mode = 0;
     fct_tiles* tiles = nullptr;      // set by fct_ctx_set_rect: K Jacobi sweeps / Chebyshev iterations per launch (fct_tile.cu)
     bool tiles_ok = false;           // tile kernels usable (structured numbering verified, row templates present)
+    fct_cheb_tiles* cheb_tiles = nullptr;   // tile lists + exception descriptors of the ChebSI tile kernel
+    bool cheb_tiles_ok = false;
     int32_t tile_kj = 4;             // sweeps per fused Jacobi launch (FCT_TILE_KJ, 2..4)
-    int32_t tile_kc = 0;             // iterations per fused ChebSI launch (FCT_TILE_KC = 2..5; 0 = per-iteration kernels, the default:
-                                     // measured 3.4 ms vs 2.3 ms per ChebSI at 4097^2 -- the mass matrix needs no HBM traffic to begin with)
+    int32_t tile_kc = 5;             // iterations per fused ChebSI launch (FCT_TILE_KC = 2..5; 0 = per-iteration kernels)
     int32_t cheb_mdtab = 1;          // ChebSI takes diag(M) from the template table when the caller passes ctx->Mdiag
     // workspace
     double* Lvals = nullptr;    // low-order operator

@@ -1264,7 +1264,7 @@ static int chebsi_tiles(fct_ctx* ctx, const double* Md, const double* b, double*
 
 int fct_chebsi_v(fct_ctx* ctx, const double* M, const double* Md, const double* b, double* y, int32_t iters, double lmin,
                  double lmax, int vb, int* vy) {
-    if (ctx->tiles_ok && M == ctx->M && Md == ctx->Mdiag && ctx->cheb_mdtab && iters >= 3 && ctx->tile_kc >= 2 &&
+    if (ctx->tiles_ok && ctx->cheb_tiles_ok && M == ctx->M && Md == ctx->Mdiag && ctx->cheb_mdtab && iters >= 3 && ctx->tile_kc >= 2 &&
         (!ctx->comm || (ctx->depth >= 2 && vb >= 1)))
         return chebsi_tiles(ctx, Md, b, y, iters, lmin, lmax, vb, vy);
     // helpers.py:164-180

@@ -544,7 +544,12 @@ __global__ void k_tile_classify(int4* __restrict__ tiles, int ntiles, int K, int
 // ======================================================================================================
 // host side
 // ======================================================================================================
+struct fct_cheb_tiles;
+void fct_cheb_tiles_free(fct_ctx* ctx);
+static int cheb_tiles_prepare(fct_ctx* ctx);
+
 void fct_tiles_free(fct_ctx* ctx) {
+    fct_cheb_tiles_free(ctx);
     fct_tiles* t = ctx->tiles;
     if (!t) return;
     cudaFree(t->tdelta);
@@ -635,6 +640,7 @@ int fct_tiles_prepare(fct_ctx* ctx) {
     cudaFree(t->tdelta);
     t->tdelta = nullptr;
     ctx->tiles_ok = false;
+    ctx->cheb_tiles_ok = false;
     const char* e = getenv("FCT_NO_TILES");
     if (e && atoi(e) == 1) return 0;
     if (ctx->tpl_count <= 0 || ctx->jac_mode != 2 || ctx->max_row > 8) return 0;
@@ -666,7 +672,7 @@ int fct_tiles_prepare(fct_ctx* ctx) {
     for (int k = 2; k <= TL_KMAX; ++k)
         if (build_tile_list(ctx, k)) { cudaGetLastError(); return 0; }
     ctx->tiles_ok = true;
-    return 0;
+    return cheb_tiles_prepare(ctx);
 }
 
 // Declares that local row i is DoF g0 + i of dolfin's CG1 numbering on RectangleMesh(n_cells x n_cells, "right")
@@ -714,17 +720,436 @@ int fct_tile_jacobi(fct_ctx* ctx, int K, const double* Lv, const double* b, cons
     return 0;
 }
 
+// ======================================================================================================
+// ChebSI tiles
+// ======================================================================================================
+// ChebSI (helpers.py:143-185) applies the STATIC mass matrix: away from the boundary every row carries the same seven
+// values, and its neighbour layout depends on the diagonal only: in diagonal d-1 the row's neighbours start at pos-1
+// (d <= n) or pos (d > n), in diagonal d+1 at pos (d < n) or pos-1 (d >= n).  So a ChebSI tile needs no per-row matrix data
+// at all and can be much larger than a Jacobi tile: a CTA owns a 50 x 98 region, every thread three groups of three
+// consecutive positions (9 rows); a group shares its 13 neighbour loads (4 + 5 + 4 instead of 3 x 7, lane stride 3
+// doubles: conflict-free), the seven matrix values and diag(M) sit in registers for the whole launch, y_old of the
+// thread's rows in registers.  Rows that do not follow the nominal pattern (boundary rows, truncated halo rows of a
+// multi-GPU block: found by k_cheb_classify from the data, at most CT_MAXEXC per tile) are recomputed after each pass by
+// one thread each through the generic template path and overwrite the nominal result -- same arithmetic as
+// k_cheb_iter_tpl in both cases, so the result is bit-identical to the per-iteration kernel.
+#define CT_ND 50
+#define CT_NP 98
+#define CT_NC (CT_ND - 2)
+#define CT_NQ (CT_NP - 2)
+#define CT_XS CT_NP
+#define CT_NT 512
+#define CT_RD 3                       // region diagonals per warp: CT_NC == CT_RD * (CT_NT / 32)
+#define CT_RP 3                       // consecutive positions per lane: CT_NQ == CT_RP * 32
+#define CT_MAXEXC CT_NT               // one exceptional row per thread
+static_assert(CT_NC == CT_RD * (CT_NT / 32) && CT_NQ == CT_RP * 32, "ChebSI tile geometry");
+
+struct ChebTileArgs {
+    int n_cells, total, g0, nloc, own_rb, own_re, ntiles, K;
+    const int4* tiles;          // {d0, p0, exceptions, template code carrying the nominal values}
+    const int* exc_off;         // [ntiles] first exception descriptor of each tile
+    const int4* exc;            // {region index, template code, delta bytes 0..3, delta bytes 4..7}
+    const double* tval;
+    const double* tdiag;
+    const double* g;
+    const double* ymid;
+    const double* yold;         // nullptr: zero
+    double* ymid_out;
+    double* yold_out;           // nullptr: not wanted
+    double om[TL_KMAX];
+    double dscale;
+};
+
+struct ChebSmem {
+    static constexpr int X_DOUBLES = 3 * CT_ND * CT_XS;
+    static constexpr int G_DOUBLES = CT_NC * CT_NQ;
+    static constexpr size_t BYTES = 8 * (size_t)(X_DOUBLES + 2 * G_DOUBLES) + 4 * (4 * CT_ND);
+};
+
+// neighbour offsets of the nominal layout on diagonal d: first neighbour in d-1 at pos + ou, in d+1 at pos + od
+__host__ __device__ __forceinline__ int ct_ou(int d, int n) { return d <= n ? -1 : 0; }
+__host__ __device__ __forceinline__ int ct_od(int d, int n) { return d < n ? 0 : -1; }
+
+// x / c for a divisor whose correctly rounded reciprocal rc = 1/c is at hand: q = RN(x rc), r = x - q c (exact, FMA),
+// RN(q + r rc) is the correctly rounded quotient (Markstein's division step -- what the compiler's own DDIV sequence ends
+// with), i.e. the same bits as x / c in three operations instead of ~35; the per-iteration kernel divides, and the
+// bit-identity test of the two covers millions of quotients.  Inputs are finite and far from the exponent limits here.
+__device__ __forceinline__ double ct_div(double x, double c, double rc) {
+    const double q = x * rc;
+    const double r = fma(-q, c, x);
+    return fma(r, rc, q);
+}
+
+__global__ void __launch_bounds__(CT_NT, 1) k_cheb_tile(const ChebTileArgs a) {
+    double* sX = reinterpret_cast<double*>(fct_smem);
+    double* sG = sX + ChebSmem::X_DOUBLES;                   // staged g of the next tile's compute set
+    double* sY = sG + ChebSmem::G_DOUBLES;                   // staged y_old
+    int* sRow = reinterpret_cast<int*>(sY + ChebSmem::G_DOUBLES);      // [2][ND] local row of (dl, pl = 0), per tile parity
+    int* sLen = sRow + 2 * CT_ND;                            // [2][ND] diagonal length (0: outside the mesh)
+    __shared__ __align__(8) uint64_t bar_full;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bar_full, CT_NT); mbar_fence_init(); }
+    const int n = a.n_cells, total = a.total, K = a.K;
+    const int nmine = ((int)blockIdx.x < a.ntiles) ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto fetch_rec = [&](int j) {
+        return j < nmine ? __ldg(a.tiles + (int)blockIdx.x + j * (int)gridDim.x) : make_int4(0, 0, 0, 0);
+    };
+    int4 rec0 = fetch_rec(0), rec1 = fetch_rec(1), rec2 = fetch_rec(2), rec3 = fetch_rec(3);
+    int recj = 0;
+    auto tile_of = [&](int j) { return j == recj ? rec0 : j == recj + 1 ? rec1 : j == recj + 2 ? rec2 : rec3; };
+    auto diag_table = [&](int j) {
+        if (tid < CT_ND && j < nmine) {
+            const int4 t = tile_of(j);
+            const int d = t.x - K + tid;
+            const bool in = d >= 0 && d <= 2 * n;
+            sLen[(j & 1) * CT_ND + tid] = in ? tl_diag_len(d, n) : 0;
+            sRow[(j & 1) * CT_ND + tid] = in ? tl_diag_start(d, n, total) + (t.y - K) - a.g0 : 0;
+        }
+    };
+    // the thread's rows: region diagonals dl = warp + 16 k + 1 (k < 3), positions pl = 3 lane + 1 + m (m < 3)
+    const int pl0 = CT_RP * lane + 1;
+    int mlp[CT_RP];
+#pragma unroll
+    for (int m = 0; m < CT_RP; ++m) mlp[m] = min(pl0 + m, CT_NP - 1 - (pl0 + m));
+    // the seven nominal matrix values and dscale * diag(M): loaded per tile from its value template (the same bits for every tile
+    // of a uniform mesh, but nothing here assumes that)
+    double Mv[7], mdn = 1.0, rmdn = 1.0;
+
+    auto issue_loads = [&](int j) {
+        if (j < nmine) {
+            const int plo = tile_of(j).y - K;
+            const int* tr = sRow + (j & 1) * CT_ND;
+            const int* tl = sLen + (j & 1) * CT_ND;
+            double* xb = sX + (j % 3) * (CT_ND * CT_XS);
+            for (int e = tid; e < CT_ND * CT_NP; e += CT_NT) {
+                const int dl = e / CT_NP, pl = e - dl * CT_NP;
+                const int r = tr[dl] + pl;
+                if ((unsigned)(plo + pl) < (unsigned)tl[dl] && (unsigned)r < (unsigned)a.nloc) cp_async8(xb + e, a.ymid + r);
+            }
+            for (int q = tid; q < CT_NC * CT_NQ; q += CT_NT) {
+                const int c = q / CT_NQ, pc = q - c * CT_NQ;
+                const int r = tr[c + 1] + pc + 1;
+                if ((unsigned)(plo + pc + 1) < (unsigned)tl[c + 1] && (unsigned)r < (unsigned)a.nloc) {
+                    cp_async8(sG + q, a.g + r);
+                    if (a.yold) cp_async8(sY + q, a.yold + r);
+                }
+            }
+        }
+        cp_async_mbar_arrive(&bar_full);
+    };
+
+    diag_table(0);
+    diag_table(1);
+    __syncthreads();
+    issue_loads(0);
+    for (int j = 0; j < nmine; ++j) {
+        const int4 t = tile_of(j);
+        const int dlo = t.x - K, plo = t.y - K, nexc = t.z;
+        const int* tr = sRow + (j & 1) * CT_ND;
+        const int* tl = sLen + (j & 1) * CT_ND;
+        // nominal values of this tile
+#pragma unroll
+        for (int jj = 0; jj < 7; ++jj) Mv[jj] = __ldg(a.tval + FCT_TPL_W * t.w + jj);
+        mdn = a.dscale * __ldg(a.tdiag + t.w);
+        rmdn = 1.0 / mdn;
+        // rows, existence, pass limits, neighbour offsets of the thread's three diagonals
+        int rowb[CT_RD], exm[CT_RD], mld[CT_RD], ou[CT_RD], od[CT_RD], xi[CT_RD];
+#pragma unroll
+        for (int k = 0; k < CT_RD; ++k) {
+            const int dl = warp + (CT_NT / 32) * k + 1, d = dlo + dl;
+            xi[k] = dl * CT_XS + pl0;
+            mld[k] = min(dl, CT_ND - 1 - dl);
+            ou[k] = ct_ou(d, n); od[k] = ct_od(d, n);
+            rowb[k] = tr[dl] + pl0;
+            int msk = 0;
+#pragma unroll
+            for (int m = 0; m < CT_RP; ++m)
+                if ((unsigned)(plo + pl0 + m) < (unsigned)tl[dl] && (unsigned)(rowb[k] + m) < (unsigned)a.nloc) msk |= 1 << m;
+            exm[k] = msk;
+        }
+        mbar_wait_bounded(&bar_full, (uint32_t)(j & 1));
+        double g[CT_RD][CT_RP], yo[CT_RD][CT_RP];
+#pragma unroll
+        for (int k = 0; k < CT_RD; ++k)
+#pragma unroll
+            for (int m = 0; m < CT_RP; ++m) {
+                const int q = (warp + (CT_NT / 32) * k) * CT_NQ + CT_RP * lane + m;
+                const bool ex = (exm[k] >> m) & 1;
+                g[k][m] = ex ? sG[q] : 0.0;
+                yo[k][m] = (ex && a.yold) ? sY[q] : 0.0;
+            }
+        if (j > 0) { rec0 = rec1; rec1 = rec2; rec2 = rec3; rec3 = fetch_rec(j + 3); recj = j; }
+        diag_table(j + 2);
+        __syncthreads();            // staging buffers and the third iterate buffer are free; table of tile j+1 is complete
+        issue_loads(j + 1);
+        // this thread's exceptional row of the tile (boundary rows, truncated halo rows): generic template arithmetic
+        int e_idx = -1, e_ml = 0, e_row = 0;
+        unsigned long long e_dpk = 0ull;
+        double ev[FCT_TPL_W], e_g = 0.0, e_yo = 0.0, e_md = 1.0, e_rmd = 1.0;
+#pragma unroll
+        for (int jj = 0; jj < FCT_TPL_W; ++jj) ev[jj] = 0.0;
+        if (tid < nexc) {
+            const int4 ed = __ldg(a.exc + a.exc_off[(int)blockIdx.x + j * (int)gridDim.x] + tid);
+            e_idx = ed.x;
+            e_dpk = (unsigned long long)(unsigned)ed.z | ((unsigned long long)(unsigned)ed.w << 32);
+            const int edl = e_idx / CT_XS, epl = e_idx - edl * CT_XS;
+            e_ml = min(min(edl, CT_ND - 1 - edl), min(epl, CT_NP - 1 - epl));
+            e_row = tr[edl] + epl;
+#pragma unroll
+            for (int jj = 0; jj < FCT_TPL_W; ++jj) ev[jj] = __ldg(a.tval + FCT_TPL_W * ed.y + jj);
+            e_md = a.dscale * __ldg(a.tdiag + ed.y);
+            e_rmd = 1.0 / e_md;
+            e_g = a.g[e_row];
+            if (a.yold) e_yo = a.yold[e_row];
+        }
+        double* A = sX + (j % 3) * (CT_ND * CT_XS);
+        double* B = sX + ((j + 2) % 3) * (CT_ND * CT_XS);
+#pragma unroll 1
+        for (int s = 1; s <= K; ++s) {
+            const double* in = (s & 1) ? A : B;
+            double* out = (s & 1) ? B : A;
+            const double om = a.om[s - 1];
+#pragma unroll
+            for (int k = 0; k < CT_RD; ++k) {
+                const double* pm = in + xi[k];
+                const double* pu = pm - CT_XS + ou[k];
+                const double* pd = pm + CT_XS + od[k];
+                double u[CT_RP + 1], c[CT_RP + 2], w[CT_RP + 1];
+#pragma unroll
+                for (int m = 0; m < CT_RP + 1; ++m) { u[m] = pu[m]; w[m] = pd[m]; }
+#pragma unroll
+                for (int m = 0; m < CT_RP + 2; ++m) c[m] = pm[m - 1];
+#pragma unroll
+                for (int m = 0; m < CT_RP; ++m) {
+                    double acc = 0.0;
+                    acc += Mv[0] * u[m]; acc += Mv[1] * u[m + 1]; acc += Mv[2] * c[m]; acc += Mv[3] * c[m + 1];
+                    acc += Mv[4] * c[m + 2]; acc += Mv[5] * w[m]; acc += Mv[6] * w[m + 1];
+                    const double ym = c[m + 1];
+                    const double z = ct_div(g[k][m] - acc, mdn, rmdn);
+                    const double yn = om * (z + ym - yo[k][m]) + yo[k][m];
+                    if (((exm[k] >> m) & 1) && s <= min(mld[k], mlp[m])) { out[xi[k] + m] = yn; yo[k][m] = ym; }
+                }
+            }
+            if (nexc > 0) {         // tile-uniform
+                __syncthreads();
+                if (e_idx >= 0 && s <= e_ml) {
+                    const double* p = in + e_idx;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < FCT_TPL_W; ++jj) acc += ev[jj] * p[tl_delta(e_dpk, jj)];
+                    const double ym = p[0];
+                    const double z = ct_div(e_g - acc, e_md, e_rmd);
+                    out[e_idx] = om * (z + ym - e_yo) + e_yo;
+                    e_yo = ym;
+                }
+            }
+            __syncthreads();
+        }
+        const double* fin = (K & 1) ? B : A;
+#pragma unroll
+        for (int k = 0; k < CT_RD; ++k)
+#pragma unroll
+            for (int m = 0; m < CT_RP; ++m) {
+                const int r = rowb[k] + m;
+                if (((exm[k] >> m) & 1) && min(mld[k], mlp[m]) >= K && r >= a.own_rb && r < a.own_re) {
+                    a.ymid_out[r] = fin[xi[k] + m];
+                    if (a.yold_out) a.yold_out[r] = yo[k][m];
+                }
+            }
+    }
+}
+
+// Classification of the ChebSI tiles from the data (one warp per tile; pass 0 counts, pass 1 fills the descriptors):
+// a row of the compute set is nominal when it has 7 entries at the nominal offsets of its diagonal and the values of the
+// tile's value template (the first such row found); every other existing row becomes an exception descriptor.
+__global__ void k_cheb_classify(int pass, int4* __restrict__ tiles, int ntiles, int K, int n, int total, int g0, int nloc,
+                                const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                const uint16_t* __restrict__ code, const double* __restrict__ tval,
+                                const int* __restrict__ exc_off, int4* __restrict__ exc) {
+    const int wdx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wdx >= ntiles) return;
+    int4 t = tiles[wdx];
+    const int dlo = t.x - K, plo = t.y - K;
+    // row -> (exists, nominal layout, deltas in this tile geometry)
+    auto inspect = [&](int q, int& r, unsigned long long& pk, bool& layout_ok) {
+        const int dl = q / CT_NQ + 1, pl = q % CT_NQ + 1;
+        const int d = dlo + dl, pos = plo + pl;
+        r = -1; pk = 0ull; layout_ok = false;
+        if (d < 0 || d > 2 * n || pos < 0 || pos >= tl_diag_len(d, n)) return;
+        const int rr = tl_diag_start(d, n, total) + pos - g0;
+        if (rr < 0 || rr >= nloc) return;
+        r = rr;
+        const int k0 = rowptr[rr], len = rowptr[rr + 1] - k0;
+        bool ok = len <= 8;
+        for (int jj = 0; jj < len && ok; ++jj) {
+            int d2, p2;
+            tl_row_to_dp(g0 + colidx[k0 + jj], n, total, d2, p2);
+            const int dd = d2 - d, dp = p2 - pos;
+            if (dd < -1 || dd > 1 || dp < -1 || dp > 1) { ok = false; break; }
+            pk |= (unsigned long long)(unsigned char)(signed char)(dd * CT_XS + dp) << (8 * jj);
+        }
+        if (!ok) { pk = ~0ull; return; }          // not a (d +- 1, pos +- 1) stencil: caller flags the tile
+        const int ou = ct_ou(d, n), od = ct_od(d, n);
+        const unsigned long long nominal =
+            (unsigned long long)(unsigned char)(signed char)(-CT_XS + ou) | ((unsigned long long)(unsigned char)(signed char)(-CT_XS + ou + 1) << 8) |
+            ((unsigned long long)(unsigned char)(signed char)(-1) << 16) | (0ull << 24) | (1ull << 32) |
+            ((unsigned long long)(unsigned char)(signed char)(CT_XS + od) << 40) | ((unsigned long long)(unsigned char)(signed char)(CT_XS + od + 1) << 48);
+        layout_ok = (len == 7) && pk == nominal;
+    };
+    // value template: the first row with the nominal layout
+    int vcode = -1;
+    for (int q0 = 0; q0 < CT_NC * CT_NQ && vcode < 0; q0 += 32) {
+        int r; unsigned long long pk; bool lok;
+        inspect(q0 + lane, r, pk, lok);
+        const unsigned b = __ballot_sync(0xffffffffu, lok);
+        if (b) { const int src = __ffs(b) - 1; vcode = __shfl_sync(0xffffffffu, lok ? (int)code[r] : 0, src); }
+    }
+    int count = 0;
+    bool bad = false;
+    const int base = pass ? exc_off[wdx] : 0;
+    for (int q0 = 0; q0 < CT_NC * CT_NQ; q0 += 32) {
+        const int q = q0 + lane;
+        int r; unsigned long long pk; bool lok;
+        inspect(q, r, pk, lok);
+        bool exc_row = false;
+        int cd = 0;
+        if (r >= 0) {
+            if (pk == ~0ull) bad = true;
+            cd = code[r];
+            bool same = lok && vcode >= 0;
+            if (same)
+                for (int jj = 0; jj < FCT_TPL_W; ++jj)
+                    same = same && __double_as_longlong(tval[FCT_TPL_W * cd + jj]) == __double_as_longlong(tval[FCT_TPL_W * vcode + jj]);
+            exc_row = !same;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, exc_row);
+        if (pass && exc_row) {
+            const int slot = count + __popc(b & ((1u << lane) - 1));
+            if (slot < CT_MAXEXC) {
+                const int dl = q / CT_NQ + 1, pl = q % CT_NQ + 1;
+                exc[base + slot] = make_int4(dl * CT_XS + pl, cd, (int)(unsigned)(pk & 0xffffffffull), (int)(unsigned)(pk >> 32));
+            }
+        }
+        count += __popc(b);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0 && !pass) {
+        t.z = (bad || count > CT_MAXEXC) ? -1 : count;
+        t.w = vcode >= 0 ? vcode : 0;
+        tiles[wdx] = t;
+    }
+}
+
+struct fct_cheb_tiles {
+    int4* list[TL_KMAX + 1] = {nullptr};
+    int* exc_off[TL_KMAX + 1] = {nullptr};
+    int4* exc[TL_KMAX + 1] = {nullptr};
+    int count[TL_KMAX + 1] = {0};
+    bool ok = false;
+};
+
+static void cheb_tile_list_host(int n, long long ga, long long gb, int K, std::vector<int4>& v) {
+    const int total = (n + 1) * (n + 1);
+    const int Td = CT_ND - 2 * K, Tp = CT_NP - 2 * K;
+    v.clear();
+    if (gb <= ga) return;
+    int dA = 0, dB = 2 * n;
+    while (dA < 2 * n && tl_diag_start(dA + 1, n, total) <= ga) ++dA;
+    while (dB > 0 && tl_diag_start(dB, n, total) >= gb) --dB;
+    for (int d0 = dA; d0 <= dB; d0 += Td) {
+        int maxlen = 0;
+        for (int d = d0; d < d0 + Td && d <= 2 * n; ++d) maxlen = std::max(maxlen, tl_diag_len(d, n));
+        for (int p0 = 0; p0 < maxlen; p0 += Tp) {
+            bool any = false;
+            for (int d = d0; d < d0 + Td && d <= dB && !any; ++d) {
+                const long long s = tl_diag_start(d, n, total);
+                const long long lo = std::max(s + p0, ga), hi = std::min(s + std::min(p0 + Tp, tl_diag_len(d, n)), gb);
+                any = hi > lo;
+            }
+            if (any) v.push_back(make_int4(d0, p0, 0, 0));
+        }
+    }
+}
+
+void fct_cheb_tiles_free(fct_ctx* ctx) {
+    fct_cheb_tiles* c = ctx->cheb_tiles;
+    if (!c) return;
+    for (int k = 0; k <= TL_KMAX; ++k) { cudaFree(c->list[k]); cudaFree(c->exc_off[k]); cudaFree(c->exc[k]); }
+    delete c;
+    ctx->cheb_tiles = nullptr;
+}
+
+// builds and classifies the ChebSI tile lists (K = 2..5); on any problem the context keeps the per-iteration kernel
+static int cheb_tiles_prepare(fct_ctx* ctx) {
+    fct_cheb_tiles_free(ctx);
+    ctx->cheb_tiles_ok = false;
+    fct_tiles* t = ctx->tiles;
+    if (!t || ctx->max_row > 7) return 0;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_cheb_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChebSmem::BYTES) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        attr = true;
+    }
+    fct_cheb_tiles* c = new fct_cheb_tiles();
+    ctx->cheb_tiles = c;
+    const int n = t->n_cells, total = (n + 1) * (n + 1);
+    bool ok = true;
+    for (int K = 2; K <= TL_KMAX && ok; ++K) {
+        std::vector<int4> v;
+        cheb_tile_list_host(n, (long long)t->g0 + ctx->row_begin, (long long)t->g0 + ctx->row_end, K, v);
+        c->count[K] = (int)v.size();
+        const size_t nt = v.size() ? v.size() : 1;
+        ok = ok && cudaMalloc((void**)&c->list[K], sizeof(int4) * nt) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&c->exc_off[K], sizeof(int) * nt) == cudaSuccess;
+        if (!ok || v.empty()) continue;
+        ok = ok && cudaMemcpy(c->list[K], v.data(), sizeof(int4) * v.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        const int grid = ((int)v.size() * 32 + 255) / 256;
+        k_cheb_classify<<<grid, 256, 0, ctx->stream>>>(0, c->list[K], (int)v.size(), K, n, total, t->g0, ctx->n, ctx->rowptr,
+                                                       ctx->colidx, ctx->tpl_code, ctx->tpl_val, nullptr, nullptr);
+        ctx->launches++;
+        ok = ok && cudaMemcpyAsync(v.data(), c->list[K], sizeof(int4) * v.size(), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+        if (!ok) break;
+        std::vector<int> off(v.size());
+        long long tot = 0;
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (v[i].z < 0) { ok = false; break; }
+            off[i] = (int)tot;
+            tot += v[i].z;
+        }
+        if (!ok) break;
+        ok = ok && cudaMalloc((void**)&c->exc[K], sizeof(int4) * (size_t)(tot ? tot : 1)) == cudaSuccess;
+        ok = ok && cudaMemcpy(c->exc_off[K], off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!ok) break;
+        k_cheb_classify<<<grid, 256, 0, ctx->stream>>>(1, c->list[K], (int)v.size(), K, n, total, t->g0, ctx->n, ctx->rowptr,
+                                                       ctx->colidx, ctx->tpl_code, ctx->tpl_val, c->exc_off[K], c->exc[K]);
+        ctx->launches++;
+        ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    }
+    cudaGetLastError();
+    ctx->cheb_tiles_ok = ok;
+    return 0;
+}
+
 // K (2..5) Chebyshev iterations in one launch with the weights om[0..K): (ymid, yold) -> (ymid_out, yold_out)
 int fct_tile_cheb(fct_ctx* ctx, int K, const double* g, const double* ymid, const double* yold, double* ymid_out,
                   double* yold_out, const double* om, double dscale) {
-    FCT_CHECK(ctx->tiles_ok && K >= 2 && K <= TL_KMAX, "fct_tile_cheb: not available");
-    TileArgs a;
-    if (fill_args(ctx, K, a)) return 1;
-    a.b = g; a.xin = ymid; a.yold = yold; a.xout = ymid_out; a.yold_out = yold_out; a.dscale = dscale;
-    for (int i = 0; i < K; ++i) a.om[i] = om[i];
-    const int grid = a.ntiles < ctx->tiles->sms ? a.ntiles : ctx->tiles->sms;
+    FCT_CHECK(ctx->tiles_ok && ctx->cheb_tiles_ok && K >= 2 && K <= TL_KMAX, "fct_tile_cheb: not available");
+    fct_tiles* t = ctx->tiles;
+    fct_cheb_tiles* c = ctx->cheb_tiles;
+    ChebTileArgs a;
+    a.n_cells = t->n_cells; a.total = (t->n_cells + 1) * (t->n_cells + 1); a.g0 = t->g0; a.nloc = ctx->n;
+    a.own_rb = ctx->row_begin; a.own_re = ctx->row_end; a.ntiles = c->count[K]; a.K = K;
+    a.tiles = c->list[K]; a.exc_off = c->exc_off[K]; a.exc = c->exc[K];
+    a.tval = ctx->tpl_val; a.tdiag = ctx->tpl_diag;
+    a.g = g; a.ymid = ymid; a.yold = yold; a.ymid_out = ymid_out; a.yold_out = yold_out; a.dscale = dscale;
+    for (int i = 0; i < TL_KMAX; ++i) a.om[i] = i < K ? om[i] : 0.0;
+    const int grid = a.ntiles < t->sms ? a.ntiles : t->sms;
     if (grid <= 0) return 0;
-    if (ctx->max_row <= 7) tile_launch_t<1, 7>(ctx, a, grid); else tile_launch_t<1, 8>(ctx, a, grid);
+    k_cheb_tile<<<grid, CT_NT, ChebSmem::BYTES, ctx->stream>>>(a);
     ctx->launches++;
     return 0;
 }
