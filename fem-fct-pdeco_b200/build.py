@@ -44,6 +44,7 @@ def build(force=False, verbose=False):
     objs = []
     nvcc = _nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("FCT_NVCC_DEFS", "").split()          # e.g. "-DCT_VARIANT=1" for kernel experiments
     procs = []
     for s in SOURCES:
         obj = os.path.join(CSRC, s.replace(".cu", ".o"))

@@ -120,6 +120,7 @@ struct fct_ctx {
     int32_t jac_mode = 0;
     fct_tiles* tiles = nullptr;      // set by fct_ctx_set_rect: K Jacobi sweeps / Chebyshev iterations per launch (fct_tile.cu)
     bool tiles_ok = false;           // tile kernels usable (structured numbering verified, row templates present)
+    int32_t tile_grid_cap = 0;       // FCT_TILE_GRID: cap on the CTAs of a tile launch (tests: several tiles per CTA on small meshes)
     fct_cheb_tiles* cheb_tiles = nullptr;   // tile lists + exception descriptors of the ChebSI tile kernel
     bool cheb_tiles_ok = false;
     int32_t tile_kj = 4;             // sweeps per fused Jacobi launch (FCT_TILE_KJ, 2..4)

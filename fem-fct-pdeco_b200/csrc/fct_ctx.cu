@@ -165,6 +165,7 @@ extern "C" int fct_ctx_create(fct_ctx** out, int device, int32_t n, const int32_
     { const char* e = getenv("FCT_NO_GRAPH"); c->use_graph = !(e && atoi(e) == 1); }
     { const char* e = getenv("FCT_PDL"); c->use_pdl = (e && atoi(e) == 1); }   // measured: no gain with persistent grids
     { const char* e = getenv("FCT_TILE_KJ"); if (e && atoi(e) >= 2 && atoi(e) <= 4) c->tile_kj = atoi(e); }
+    { const char* e = getenv("FCT_TILE_GRID"); if (e && atoi(e) >= 1) c->tile_grid_cap = atoi(e); }
     { const char* e = getenv("FCT_TILE_KC"); if (e && (atoi(e) == 0 || (atoi(e) >= 2 && atoi(e) <= 5))) c->tile_kc = atoi(e); }
     {
         cudaDeviceProp prop;

@@ -607,6 +607,13 @@ __global__ void k_jacobi_decide_cond(unsigned long long* __restrict__ jstate, do
 __global__ void k_tile_decide(unsigned long long* __restrict__ jstate, double rtol, unsigned long long max_sweeps,
                               unsigned long long which, int use_handle, cudaGraphConditionalHandle handle) {
     if (jstate[3]) { if (use_handle) cudaGraphSetConditional(handle, 0u); return; }
+    // the same test schedule as the multi-GPU decision (k_p2p_max2_decide): no test before the sweep count learnt from the
+    // previous solve -- on one GPU the test is free, but N ranks must stop after the same number of sweeps as one
+    if (jstate[4] < jstate[10] && jstate[4] < max_sweeps) {
+        jstate[0] = 0ull; jstate[1] = 0ull;
+        if (use_handle) cudaGraphSetConditional(handle, 1u);
+        return;
+    }
     const double delta = __longlong_as_double((long long)jstate[0]);
     const double xm = __longlong_as_double((long long)jstate[1]);
     jstate[5] = jstate[0];

@@ -470,13 +470,16 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
         load_meta2();
         const double* fin = (K & 1) ? B : A;
         const double* prev = (K & 1) ? A : B;
+        double fv[TL_R], pv[TL_R];          // all loads first (the slots always exist), then the predicated stores
+#pragma unroll
+        for (int i = 0; i < TL_R; ++i) { fv[i] = fin[xi[i]]; pv[i] = prev[xi[i]]; }
 #pragma unroll
         for (int i = 0; i < TL_R; ++i) {
             if (row[i] >= 0 && ml[i] >= K && row[i] >= a.own_rb && row[i] < a.own_re) {
-                const double v = fin[xi[i]];
+                const double v = fv[i];
                 a.xout[row[i]] = v;
                 if (MODE == 0) {
-                    delta = fmax(delta, fabs(v - prev[xi[i]]));
+                    delta = fmax(delta, fabs(v - pv[i]));
                     xa = fmax(xa, fabs(v));
                 } else if (a.yold_out) {
                     a.yold_out[row[i]] = yo[i];
@@ -627,7 +630,7 @@ static void tile_launch_t(fct_ctx* ctx, const TileArgs& a, int grid) {
 static int tiles_configure() {
     static bool done = false;
     if (done) return 0;
-    if (tile_set_attr<0, 7>() || tile_set_attr<0, 8>() || tile_set_attr<1, 7>() || tile_set_attr<1, 8>()) return 1;
+    if (tile_set_attr<0, 7>() || tile_set_attr<0, 8>()) return 1;      // (MODE 1 of k_tile is superseded by k_cheb_tile)
     done = true;
     return 0;
 }
@@ -713,7 +716,8 @@ int fct_tile_jacobi(fct_ctx* ctx, int K, const double* Lv, const double* b, cons
     TileArgs a;
     if (fill_args(ctx, K, a)) return 1;
     a.Lv = Lv; a.b = b; a.xin = xin; a.xout = xout;
-    const int grid = a.ntiles < ctx->tiles->sms ? a.ntiles : ctx->tiles->sms;
+    int grid = a.ntiles < ctx->tiles->sms ? a.ntiles : ctx->tiles->sms;
+    if (ctx->tile_grid_cap > 0 && grid > ctx->tile_grid_cap) grid = ctx->tile_grid_cap;
     if (grid <= 0) return 0;
     if (ctx->max_row <= 7) tile_launch_t<0, 7>(ctx, a, grid); else tile_launch_t<0, 8>(ctx, a, grid);
     ctx->launches++;
@@ -772,8 +776,13 @@ __host__ __device__ __forceinline__ int ct_od(int d, int n) { return d < n ? 0 :
 
 // x / c for a divisor whose correctly rounded reciprocal rc = 1/c is at hand: q = RN(x rc), r = x - q c (exact, FMA),
 // RN(q + r rc) is the correctly rounded quotient (Markstein's division step -- what the compiler's own DDIV sequence ends
-// with), i.e. the same bits as x / c in three operations instead of ~35; the per-iteration kernel divides, and the
-// bit-identity test of the two covers millions of quotients.  Inputs are finite and far from the exponent limits here.
+// with), i.e. the same bits as x / c in three operations instead of ~35.  The per-iteration kernel divides, and the
+// bit-identity tests of the two (single GPU, and N ranks against one) cover hundreds of millions of quotients.
+// Range: the step is exact while r is representable, i.e. for |x| >= 2^-960 or so (and x = 0 gives 0); below that -- values
+// of order 1e-290, far under anything a state or adjoint of these problems carries -- the result may differ from x / c in
+// the last bit.  A range test in the loop (branch per row or per group of rows) was measured at +0.25 .. +0.4 ms per
+// ChebSI (it breaks the interleaving of the rows' dependent chains), so it is not there; FCT_TILE_KC=0 selects the
+// per-iteration kernel, which divides.
 __device__ __forceinline__ double ct_div(double x, double c, double rc) {
     const double q = x * rc;
     const double r = fma(-q, c, x);
@@ -867,22 +876,8 @@ __global__ void __launch_bounds__(CT_NT, 1) k_cheb_tile(const ChebTileArgs a) {
                 if ((unsigned)(plo + pl0 + m) < (unsigned)tl[dl] && (unsigned)(rowb[k] + m) < (unsigned)a.nloc) msk |= 1 << m;
             exm[k] = msk;
         }
-        mbar_wait_bounded(&bar_full, (uint32_t)(j & 1));
-        double g[CT_RD][CT_RP], yo[CT_RD][CT_RP];
-#pragma unroll
-        for (int k = 0; k < CT_RD; ++k)
-#pragma unroll
-            for (int m = 0; m < CT_RP; ++m) {
-                const int q = (warp + (CT_NT / 32) * k) * CT_NQ + CT_RP * lane + m;
-                const bool ex = (exm[k] >> m) & 1;
-                g[k][m] = ex ? sG[q] : 0.0;
-                yo[k][m] = (ex && a.yold) ? sY[q] : 0.0;
-            }
-        if (j > 0) { rec0 = rec1; rec1 = rec2; rec2 = rec3; rec3 = fetch_rec(j + 3); recj = j; }
-        diag_table(j + 2);
-        __syncthreads();            // staging buffers and the third iterate buffer are free; table of tile j+1 is complete
-        issue_loads(j + 1);
-        // this thread's exceptional row of the tile (boundary rows, truncated halo rows): generic template arithmetic
+        // this thread's exceptional row of the tile (boundary rows, truncated halo rows): generic template arithmetic.  Set up
+        // here, before the barrier below: tile j's diagonal table is recycled for tile j+2 from then on
         int e_idx = -1, e_ml = 0, e_row = 0;
         unsigned long long e_dpk = 0ull;
         double ev[FCT_TPL_W], e_g = 0.0, e_yo = 0.0, e_md = 1.0, e_rmd = 1.0;
@@ -902,6 +897,22 @@ __global__ void __launch_bounds__(CT_NT, 1) k_cheb_tile(const ChebTileArgs a) {
             e_g = a.g[e_row];
             if (a.yold) e_yo = a.yold[e_row];
         }
+        mbar_wait_bounded(&bar_full, (uint32_t)(j & 1));
+        double g[CT_RD][CT_RP], yo[CT_RD][CT_RP];
+#pragma unroll
+        for (int k = 0; k < CT_RD; ++k)
+#pragma unroll
+            for (int m = 0; m < CT_RP; ++m) {
+                const int q = (warp + (CT_NT / 32) * k) * CT_NQ + CT_RP * lane + m;
+                const bool ex = (exm[k] >> m) & 1;
+                g[k][m] = ex ? sG[q] : 0.0;
+                yo[k][m] = (ex && a.yold) ? sY[q] : 0.0;
+            }
+        if (j > 0) { rec0 = rec1; rec1 = rec2; rec2 = rec3; rec3 = fetch_rec(j + 3); recj = j; }
+        __syncthreads();            // staging buffers and the third iterate buffer are free; table of tile j+1 is complete;
+                                    // every warp has taken what it needs from tile j's diagonal table ...
+        diag_table(j + 2);          // ... whose slot is recycled now (read from the next barrier (A) on)
+        issue_loads(j + 1);
         double* A = sX + (j % 3) * (CT_ND * CT_XS);
         double* B = sX + ((j + 2) % 3) * (CT_ND * CT_XS);
 #pragma unroll 1
@@ -946,13 +957,24 @@ __global__ void __launch_bounds__(CT_NT, 1) k_cheb_tile(const ChebTileArgs a) {
             __syncthreads();
         }
         const double* fin = (K & 1) ? B : A;
+#ifndef CT_NOHOIST
+        double fv[CT_RD][CT_RP];          // all loads first (the slots always exist), then the predicated stores
+#pragma unroll
+        for (int k = 0; k < CT_RD; ++k)
+#pragma unroll
+            for (int m = 0; m < CT_RP; ++m) fv[k][m] = fin[xi[k] + m];
+#endif
 #pragma unroll
         for (int k = 0; k < CT_RD; ++k)
 #pragma unroll
             for (int m = 0; m < CT_RP; ++m) {
                 const int r = rowb[k] + m;
                 if (((exm[k] >> m) & 1) && min(mld[k], mlp[m]) >= K && r >= a.own_rb && r < a.own_re) {
+#ifndef CT_NOHOIST
+                    a.ymid_out[r] = fv[k][m];
+#else
                     a.ymid_out[r] = fin[xi[k] + m];
+#endif
                     if (a.yold_out) a.yold_out[r] = yo[k][m];
                 }
             }
@@ -1147,7 +1169,8 @@ int fct_tile_cheb(fct_ctx* ctx, int K, const double* g, const double* ymid, cons
     a.tval = ctx->tpl_val; a.tdiag = ctx->tpl_diag;
     a.g = g; a.ymid = ymid; a.yold = yold; a.ymid_out = ymid_out; a.yold_out = yold_out; a.dscale = dscale;
     for (int i = 0; i < TL_KMAX; ++i) a.om[i] = i < K ? om[i] : 0.0;
-    const int grid = a.ntiles < t->sms ? a.ntiles : t->sms;
+    int grid = a.ntiles < t->sms ? a.ntiles : t->sms;
+    if (ctx->tile_grid_cap > 0 && grid > ctx->tile_grid_cap) grid = ctx->tile_grid_cap;
     if (grid <= 0) return 0;
     k_cheb_tile<<<grid, CT_NT, ChebSmem::BYTES, ctx->stream>>>(a);
     ctx->launches++;

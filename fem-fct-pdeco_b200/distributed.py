@@ -267,6 +267,18 @@ def mgpu_parity_check(cells, ns, rank, world, local_rank, depth=None, seed=5):
                "host_path_equal": bool(int(flags[0].item())), "p2p_error_free": bool(int(flags[1].item()))}
         res["ok"] = bool(res["u_equal"] and res["p_equal"] and res["d_equal"] and res["J_rel"] < 1e-13
                          and res["host_path_equal"] and res["p2p_error_free"])
+        if not res["ok"]:          # where do the fields differ?  (time level, global row, anti-diagonal, position, |diff|)
+            n_c = cells
+            lens = np.array([min(dd, 2 * n_c - dd) + 1 for dd in range(2 * n_c + 1)])
+            start = np.concatenate([[0], np.cumsum(lens)])
+            for name, a, b in (("u", ug, u1), ("p", pg, p1), ("d", dg, d1)):
+                bad = np.argwhere(a != b)
+                info = []
+                for k, r in bad[:6]:
+                    dd = int(np.searchsorted(start, r, side="right") - 1)
+                    info.append([int(k), int(r), dd, int(r - start[dd]), float(abs(a[k, r] - b[k, r]))])
+                res[f"{name}_mismatch"] = {"count": int(len(bad)), "first": info,
+                                           "max_rel": float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))}
         ctx1.close()
         mesh._ctx = None
     v = torch.tensor([1 if res["ok"] else 0], device="cuda")

@@ -415,13 +415,16 @@ def test_template_jacobi_modes(monkeypatch):
     assert abs(res["2"][1] - res["0"][1]) <= 4 * ns      # fused tile sweeps stop at multiples of 4
 
 
-@pytest.mark.parametrize("n", [5, 12, 45, 100, 300])
-def test_tile_kernels_bit_identical(monkeypatch, n):
+@pytest.mark.parametrize("n,grid,kc", [(5, 0, 5), (12, 0, 5), (45, 1, 4), (100, 3, 3), (300, 0, 5), (300, 5, 4), (300, 0, 3),
+                                       (1024, 0, 5), (1024, 0, 4), (1024, 0, 3)])
+def test_tile_kernels_bit_identical(monkeypatch, n, grid, kc):
     """fct_tile.cu: K Jacobi sweeps / K Chebyshev iterations per launch on overlapped (diagonal, position) tiles -- matrix
     rows in registers, iterate in shared memory, redundant work in a K-wide frame -- must reproduce the one-launch-per-pass
     kernels bit for bit (same row arithmetic, same order): ChebSI with 20, 7 and 3 iterations (groups of 5/4/3/2), fixed
     numbers of Jacobi sweeps as launches of 2, 3 and 4, and whole FCT state steps (adaptive solve: K-sweep granularity, so
-    only the stopping point may differ).  n = 5 has tiles larger than the mesh, n = 300 several hundred tiles."""
+    only the stopping point may differ).  n = 5 has tiles larger than the mesh, n = 300 several hundred tiles; grid > 0 caps
+    the CTAs of a tile launch (FCT_TILE_GRID) so that every CTA walks many tiles and the software pipeline across tiles
+    (prefetched records, recycled diagonal tables and staging buffers) is exercised on a small mesh."""
     h = 1.0 / n
     dt = 0.25 * h / (2 * np.sqrt(2))
     mesh = RectMeshP1(n, 0.0, 1.0)
@@ -433,7 +436,8 @@ def test_tile_kernels_bit_identical(monkeypatch, n):
     out = {}
     for tiles in ("0", "1"):
         monkeypatch.setenv("FCT_NO_TILES", "0" if tiles == "1" else "1")
-        monkeypatch.setenv("FCT_TILE_KC", "5")          # the ChebSI tiles are opt-in (slower than the per-iteration kernel)
+        monkeypatch.setenv("FCT_TILE_KC", str(kc))      # ChebSI iterations per launch (multi-GPU runs use <= halo depth)
+        monkeypatch.setenv("FCT_TILE_GRID", str(grid))
         ctx = RectMeshP1(n, 0.0, 1.0).context()
         assert ctx.tiles_active() == (tiles == "1")
         M, _, Md, _ = ctx.static()
