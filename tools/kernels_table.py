@@ -40,7 +40,7 @@ def main(path, out, peak):
     for mid, mets in per.items():
         name = names[mid]
         ms = mets.get("gpu__time_duration.sum", 0.0)
-        if name.startswith("k_jacobi") and "sweep" in name and ms < 0.02:
+        if ((name.startswith("k_jacobi") and "sweep" in name) or name == "k_tile") and ms < 0.02:
             name += " (skipped: converged)"
         a = agg[name]
         a[0] += 1
