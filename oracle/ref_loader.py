@@ -57,3 +57,38 @@ def load_reference_helpers():
             else:
                 sys.modules[k] = v
     return mod
+
+
+def load_reference_helpers_on_fake_dolfin():
+    """The reference's helpers.py, unmodified, with `dolfin` bound to oracle/fake_dolfin.py (numpy P1 assembly behind dolfin's
+    names): its time loops -- solve_schnak_system, solve_adjoint_schnak_system, solve_nonlinear_equation,
+    solve_adjoint_nonlinear_equation, solve_chtxs_system, solve_adjoint_chtxs_system, armijo_line_search_ref -- then run as
+    written.  Cached in sys.modules as `_fct_reference_helpers_fd`."""
+    from . import fake_dolfin
+    name = "_fct_reference_helpers_fd"
+    if name in sys.modules:
+        return sys.modules[name]
+    if not reference_available():
+        raise FileNotFoundError(f"{REFERENCE_DIR}/helpers.py not found")
+    saved = {k: sys.modules.get(k) for k in ("dolfin", "matplotlib", "matplotlib.pyplot")}
+    mpl = types.ModuleType("matplotlib")
+    plt = types.ModuleType("matplotlib.pyplot")
+    mpl.pyplot = plt
+    sys.modules["dolfin"] = fake_dolfin.make_module()
+    if saved["matplotlib"] is None:
+        sys.modules["matplotlib"] = mpl
+        sys.modules["matplotlib.pyplot"] = plt
+    try:
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_DIR, "helpers.py"))
+        mod = importlib.util.module_from_spec(spec)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            spec.loader.exec_module(mod)
+        sys.modules[name] = mod
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod

@@ -21,6 +21,11 @@ Writes
                       unmodified with `assemble_sparse` returning the restated mass matrix and the oracle's time
                       loops as `nonlinear_solver` callbacks (one-species final-time case, two-species all-time case,
                       a case that exhausts max_iter).
+  ref_loops.npz       inputs + outputs of the reference's OWN time loops (solve_schnak_system, solve_adjoint_schnak_system,
+                      solve_nonlinear_equation, solve_adjoint_nonlinear_equation, solve_chtxs_system,
+                      solve_adjoint_chtxs_system all-time / final-time) and of armijo_line_search_ref with the reference's own
+                      solver as callback: helpers.py runs unmodified on oracle/fake_dolfin.py, a numpy stand-in for the slice
+                      of dolfin it uses, which is first checked on the shipped chemotaxis trajectory.
 """
 import os
 import sys
@@ -268,8 +273,115 @@ def ref_armijo():
     print("ref_armijo.npz written:", len(out), "arrays")
 
 
+def ref_loops():
+    """The reference's OWN time loops and line search, helpers.py run unmodified on oracle/fake_dolfin.py (numpy P1 assembly
+    behind dolfin's names): solve_schnak_system / solve_adjoint_schnak_system (helpers.py:511-698), solve_nonlinear_equation /
+    solve_adjoint_nonlinear_equation (:881-1038), solve_chtxs_system / solve_adjoint_chtxs_system (:1250-1581, all-time and
+    final-time), armijo_line_search_ref (:1583-1713) with the reference's own solver as callback.  Before anything is
+    written the stand-in is checked end to end on the reference's shipped data: solve_chtxs_system(control_fun=Constant(100),
+    rescaling=1) on the 40 x 40 mesh must reproduce Chtxs_data_dx0.025_dt0.001/chtxs_{m,f}_t0.01.csv."""
+    import contextlib
+    import io
+    from oracle import fake_dolfin as fd
+    from oracle.ref_loader import load_reference_helpers_on_fake_dolfin
+    hp = load_reference_helpers_on_fake_dolfin()
+    quiet = contextlib.redirect_stdout(io.StringIO())
+
+    def setup(n, a1=0.0, a2=1.0):
+        mesh = RectMesh(n, a1, a2)
+        V = fd.FunctionSpace(mesh)
+        return mesh, V, mesh.nodes, mesh.dof_neighbors(), np.array(mesh.vertex_to_dof)
+
+    # ---- pin: the shipped chemotaxis trajectory through the reference's own loop ----
+    d = os.path.join(REFERENCE_DIR, "Chtxs_data_dx0.025_dt0.001")
+    gm = np.genfromtxt(os.path.join(d, "chtxs_m_t0.01.csv"), delimiter=",").reshape(11, 1681)
+    gf = np.genfromtxt(os.path.join(d, "chtxs_f_t0.01.csv"), delimiter=",").reshape(11, 1681)
+    mesh, V, nodes, nb, v2d = setup(40)
+    ns, dt = 10, 1e-3
+    m0, f0 = hp.chtxs_sys_IC(0.0, 1.0, 0.025, nodes, v2d)
+    var1 = np.zeros((ns + 1) * nodes); var1[:nodes] = m0
+    var2 = np.zeros((ns + 1) * nodes); var2[:nodes] = f0
+    with quiet:
+        var1, var2 = hp.solve_chtxs_system(np.zeros((ns + 1) * nodes), var1, var2, V, nodes, ns, dt, nb,
+                                           control_fun=fd.Constant(100), rescaling=1)
+    em = max(np.linalg.norm(var1.reshape(ns + 1, -1)[k] - gm[k]) / np.linalg.norm(gm[k]) for k in range(ns + 1))
+    ef = max(np.linalg.norm(var2.reshape(ns + 1, -1)[k] - gf[k]) / np.linalg.norm(gf[k]) for k in range(ns + 1))
+    print(f"reference solve_chtxs_system on fake dolfin vs shipped trajectory: rel-L2 m {em:.2e}, f {ef:.2e}")
+    assert em < 1e-13 and ef < 1e-13
+
+    out = {}
+    rng = np.random.default_rng(11)
+    n, ns = 10, 4
+    mesh, V, nodes, nb, v2d = setup(n)
+    xy = mesh.dof_xy
+    L = (ns + 1) * nodes
+    out["n"] = np.array([n]); out["ns"] = np.array([ns])
+
+    # ---- Schnakenberg ----
+    dt = 5e-4
+    u0, v0 = hp.schnak_sys_IC(0.0, 1.0, 1.0 / n, nodes, v2d)
+    c = 0.1 + 0.05 * rng.random(L)
+    uk = np.zeros(L); uk[:nodes] = u0
+    vk = np.zeros(L); vk[:nodes] = v0
+    with quiet:
+        uk, vk = hp.solve_schnak_system(c, uk, vk, V, nodes, ns, dt, nb)
+    uhat_T, vhat_T = uk[ns * nodes:] + 0.1 * rng.random(nodes), vk[ns * nodes:] + 0.1 * rng.random(nodes)
+    pk, qk = np.zeros(L), np.zeros(L)
+    with quiet:
+        pk, qk = hp.solve_adjoint_schnak_system(uk, vk, uhat_T, vhat_T, pk, qk, ns * dt, V, nodes, ns, dt, nb)
+    out.update(schnak_dt=np.array([dt]), schnak_c=c, schnak_u0=u0, schnak_v0=v0, schnak_u=uk.copy(), schnak_v=vk.copy(),
+               schnak_uhat=uhat_T, schnak_vhat=vhat_T, schnak_p=pk.copy(), schnak_q=qk.copy())
+
+    # ---- nonlinear advection-reaction ----
+    dt = 1e-3
+    u0 = hp.nonlinear_equation_IC(0.0, 1.0, 1.0 / n, nodes, v2d)
+    c = rng.random(L) - 0.5
+    uk = np.zeros(L); uk[:nodes] = u0
+    with quiet:
+        uk, _ = hp.solve_nonlinear_equation(c, uk, None, V, nodes, ns, dt, nb)
+    uhat_T = uk[ns * nodes:] + 0.05 * rng.random(nodes)
+    pk = np.zeros(L)
+    with quiet:
+        pk = hp.solve_adjoint_nonlinear_equation(uk, uhat_T, pk, ns * dt, V, nodes, ns, dt, nb)
+    out.update(nonlin_dt=np.array([dt]), nonlin_c=c, nonlin_u0=u0, nonlin_u=uk.copy(), nonlin_uhat=uhat_T, nonlin_p=pk.copy())
+
+    # ---- line search with the reference's own solver as callback (one-species, final time) ----
+    beta = 0.1
+    M = hp.assemble_sparse(fd.TrialFunction(V) * fd.TestFunction(V) * fd.dx)
+    with quiet:
+        cost0 = hp.cost_functional(uk, uhat_T, c, ns, dt, M, beta, optim="finaltime")
+    dk = -(beta * c - pk)
+    var1 = uk.copy()
+    with quiet:
+        u_new, c_new, its = hp.armijo_line_search_ref(var1, c, dk, uhat_T, ns, dt, -0.4, 0.4, beta, cost0, nodes, "finaltime", V,
+                                                      nonlinear_solver=hp.solve_nonlinear_equation, dof_neighbors=nb)
+    out.update(armijo_beta=np.array([beta]), armijo_cost0=np.array([cost0]), armijo_d=dk, armijo_u=np.array(u_new),
+               armijo_c=np.array(c_new), armijo_its=np.array([its]), armijo_bounds=np.array([-0.4, 0.4]))
+
+    # ---- chemotaxis: state and both adjoints ----
+    dt = 1e-3
+    m0, f0 = hp.chtxs_sys_IC(0.0, 1.0, 1.0 / n, nodes, v2d)
+    c = 50.0 + 20.0 * rng.random(L)
+    mk = np.zeros(L); mk[:nodes] = m0
+    fk = np.zeros(L); fk[:nodes] = f0
+    with quiet:
+        mk, fk = hp.solve_chtxs_system(c, mk, fk, V, nodes, ns, dt, nb)
+    mhat, fhat = mk + 0.05 * rng.random(L), fk + 0.05 * rng.random(L)
+    pk, qk = np.zeros(L), np.zeros(L)
+    with quiet:
+        pk, qk = hp.solve_adjoint_chtxs_system(mk, fk, mhat, fhat, pk, qk, c, ns * dt, V, nodes, ns, dt, nb, "alltime")
+    out.update(chtxs_dt=np.array([dt]), chtxs_c=c, chtxs_m0=m0, chtxs_f0=f0, chtxs_m=mk.copy(), chtxs_f=fk.copy(),
+               chtxs_mhat=mhat, chtxs_fhat=fhat, chtxs_p_at=pk.copy(), chtxs_q_at=qk.copy())
+    pk, qk = np.zeros(L), np.zeros(L)
+    with quiet:
+        pk, qk = hp.solve_adjoint_chtxs_system(mk, fk, mhat[ns * nodes:], fhat[ns * nodes:], pk, qk, c, ns * dt, V, nodes, ns,
+                                               dt, nb, "finaltime")
+    out.update(chtxs_p_ft=pk.copy(), chtxs_q_ft=qk.copy())
+    np.savez_compressed(os.path.join(HERE, "ref_loops.npz"), **out)
+    print("ref_loops.npz written:", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    ref_data()
-    ref_fct_cases()
-    ref_legacy()
-    ref_armijo()
+    which = sys.argv[1:] or ["ref_data", "ref_fct_cases", "ref_legacy", "ref_armijo", "ref_loops"]
+    for name in which:
+        globals()[name]()

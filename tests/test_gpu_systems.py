@@ -1,5 +1,6 @@
 """GPU parity tests of the reference-named time loops (solve_*_system, solve_adjoint_*, armijo_line_search_ref)
-against the oracle restatements of helpers.py:511-698, 881-1038, 1250-1581, 1583-1713 on small meshes.
+against the oracle restatements of helpers.py:511-698, 881-1038, 1250-1581, 1583-1713 on small meshes, and against
+outputs of the reference's OWN functions (helpers.py run unmodified on oracle/fake_dolfin.py: tests/golden/ref_loops.npz).
 Tolerance: 1e-12 relative L2 per time step (accumulating over the steps of a trajectory)."""
 import io
 from contextlib import redirect_stdout
@@ -161,3 +162,71 @@ def test_config2_projected_gradient_iteration():
     J_g = _quiet(hp.cost_functional, u_inc, uhat.ravel(), ckp1, ns, dt, M, beta, optim="alltime")
     assert rel_l2(u_inc, uinc_o.ravel()) < 1e-11
     assert abs(J_g / J_o - 1) < 1e-9
+
+
+# ---- the reference's OWN loops (helpers.py run unmodified on oracle/fake_dolfin.py; tests/golden/ref_loops.npz) -------------
+@pytest.fixture(scope="module")
+def loops():
+    import os
+    from conftest import GOLDEN
+    return dict(np.load(os.path.join(GOLDEN, "ref_loops.npz")))
+
+
+def test_reference_loops_schnak(loops):
+    """solve_schnak_system / solve_adjoint_schnak_system (helpers.py:511-698) against outputs of the reference's own functions"""
+    g = loops
+    n, ns, dt = int(g["n"][0]), int(g["ns"][0]), float(g["schnak_dt"][0])
+    mesh, V = _space(n)
+    nodes = V.dim()
+    uk = np.zeros((ns + 1) * nodes); vk = np.zeros_like(uk)
+    uk[:nodes], vk[:nodes] = g["schnak_u0"], g["schnak_v0"]
+    _quiet(hp.solve_schnak_system, g["schnak_c"], uk, vk, V, nodes, ns, dt, mesh.dof_neighbors())
+    ru, rv = g["schnak_u"].reshape(ns + 1, -1), g["schnak_v"].reshape(ns + 1, -1)
+    for i in range(1, ns + 1):
+        assert rel_l2(uk.reshape(ns + 1, -1)[i], ru[i]) < 1e-12 * i, i
+        assert rel_l2(vk.reshape(ns + 1, -1)[i], rv[i]) < 1e-12 * i, i
+    pk = np.zeros_like(uk); qk = np.zeros_like(uk)
+    _quiet(hp.solve_adjoint_schnak_system, g["schnak_u"].copy(), g["schnak_v"].copy(), g["schnak_uhat"], g["schnak_vhat"], pk, qk,
+           ns * dt, V, nodes, ns, dt, mesh.dof_neighbors())
+    assert rel_l2(pk, g["schnak_p"]) < 1e-11 and rel_l2(qk, g["schnak_q"]) < 1e-11
+
+
+def test_reference_loops_nonlinear_and_armijo(loops):
+    """solve_nonlinear_equation / solve_adjoint_nonlinear_equation (helpers.py:881-1038) and armijo_line_search_ref
+    (:1583-1713, the reference's own solver as callback) against outputs of the reference's own functions"""
+    g = loops
+    n, ns, dt = int(g["n"][0]), int(g["ns"][0]), float(g["nonlin_dt"][0])
+    mesh, V = _space(n)
+    nodes = V.dim()
+    uk = np.zeros((ns + 1) * nodes); uk[:nodes] = g["nonlin_u0"]
+    _quiet(hp.solve_nonlinear_equation, g["nonlin_c"], uk, None, V, nodes, ns, dt, mesh.dof_neighbors())
+    assert rel_l2(uk, g["nonlin_u"]) < 1e-11
+    pk = np.zeros_like(uk)
+    _quiet(hp.solve_adjoint_nonlinear_equation, g["nonlin_u"].copy(), g["nonlin_uhat"], pk, ns * dt, V, nodes, ns, dt,
+           mesh.dof_neighbors())
+    assert rel_l2(pk, g["nonlin_p"]) < 1e-11
+    lo, hi = g["armijo_bounds"]
+    res = _quiet(hp.armijo_line_search_ref, g["nonlin_u"].copy(), g["nonlin_c"], g["armijo_d"], g["nonlin_uhat"], ns, dt, lo, hi,
+                 float(g["armijo_beta"][0]), float(g["armijo_cost0"][0]), nodes, "finaltime", V,
+                 nonlinear_solver=hp.solve_nonlinear_equation, dof_neighbors=mesh.dof_neighbors())
+    v1, c_inc, k = res
+    assert k == int(g["armijo_its"][0]) and np.array_equal(c_inc, g["armijo_c"]) and rel_l2(v1, g["armijo_u"]) < 1e-11
+
+
+def test_reference_loops_chemotaxis(loops):
+    """solve_chtxs_system / solve_adjoint_chtxs_system (helpers.py:1250-1581; all-time and final-time) against outputs of
+    the reference's own functions"""
+    g = loops
+    n, ns, dt = int(g["n"][0]), int(g["ns"][0]), float(g["chtxs_dt"][0])
+    mesh, V = _space(n)
+    nodes = V.dim()
+    mk = np.zeros((ns + 1) * nodes); fk = np.zeros_like(mk)
+    mk[:nodes], fk[:nodes] = g["chtxs_m0"], g["chtxs_f0"]
+    _quiet(hp.solve_chtxs_system, g["chtxs_c"], mk, fk, V, nodes, ns, dt, mesh.dof_neighbors())
+    assert rel_l2(mk, g["chtxs_m"]) < 1e-12 and rel_l2(fk, g["chtxs_f"]) < 1e-12
+    for optim, mh, fh, tag in (("alltime", g["chtxs_mhat"], g["chtxs_fhat"], "at"),
+                               ("finaltime", g["chtxs_mhat"][ns * nodes:], g["chtxs_fhat"][ns * nodes:], "ft")):
+        pk = np.zeros_like(mk); qk = np.zeros_like(mk)
+        _quiet(hp.solve_adjoint_chtxs_system, g["chtxs_m"].copy(), g["chtxs_f"].copy(), mh, fh, pk, qk, g["chtxs_c"], ns * dt, V,
+               nodes, ns, dt, mesh.dof_neighbors(), optim)
+        assert rel_l2(pk, g[f"chtxs_p_{tag}"]) < 1e-11 and rel_l2(qk, g[f"chtxs_q_{tag}"]) < 1e-11, optim
