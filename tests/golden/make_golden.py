@@ -26,6 +26,9 @@ Writes
                       solve_adjoint_chtxs_system all-time / final-time) and of armijo_line_search_ref with the reference's own
                       solver as callback: helpers.py runs unmodified on oracle/fake_dolfin.py, a numpy stand-in for the slice
                       of dolfin it uses, which is first checked on the shipped chemotaxis trajectory.
+  ref_cfg2.npz        BASELINE config 2: inputs + outputs of the state / adjoint / gradient loops of
+                      advection_solidbody_FCT_PDECO_alltime.py:206-275 -- the script's own source lines executed with the
+                      reference's helpers.py (on oracle/fake_dolfin.py) and its legacy FCT_alg.
 """
 import os
 import sys
@@ -381,7 +384,52 @@ def ref_loops():
     print("ref_loops.npz written:", len(out), "arrays")
 
 
+def ref_script_cfg2():
+    """BASELINE config 2: the state / adjoint / gradient loops of advection_solidbody_FCT_PDECO_alltime.py (:206-275, the shape
+    of the 4096^2 benchmark) -- the script's own source lines, compiled as they stand and executed in a namespace that holds
+    the reference's helpers.py (on oracle/fake_dolfin.py), the legacy FCT_alg of old_helpers.py (its source, compiled as it
+    stands) and the script's set-up variables on a small mesh.  Pins the drift-control operators Adrift1 / Adrift2, the
+    adjoint right-hand side and the gradient ChebSI solve on the reference's code."""
+    import contextlib
+    import io
+    from oracle import fake_dolfin as fd
+    from oracle.ref_loader import load_reference_helpers_on_fake_dolfin
+    hp = load_reference_helpers_on_fake_dolfin()
+    ns_ = dict(vars(hp))
+    old = open(os.path.join(REFERENCE_DIR, "old_helpers.py")).read().splitlines()
+    start = next(i for i, l in enumerate(old) if l.startswith("def FCT_alg("))
+    exec(compile("\n".join(old[start:]), "old_helpers.py:FCT_alg", "exec"), ns_)
+    script = open(os.path.join(REFERENCE_DIR, "advection_solidbody_FCT_PDECO_alltime.py")).read().splitlines()
+    i0 = next(i for i, l in enumerate(script) if "print('Solving state equation...')" in l)
+    i1 = next(i for i, l in enumerate(script) if "4. step size control" in l) - 1          # the banner line above it
+    body = "\n".join(l[4:] if l.startswith("    ") else l for l in script[i0:i1])           # the loops live inside `while`
+    n, num_steps, dt, beta, eps = 10, 3, 2e-3, 0.01, 0
+    mesh = RectMesh(n, -1.0, 1.0)
+    V = fd.FunctionSpace(mesh)
+    nodes = mesh.nodes
+    u, v = fd.TrialFunction(V), fd.TestFunction(V)
+    rng = np.random.default_rng(21)
+    xy = mesh.dof_xy
+    u0 = np.exp(-20 * ((xy[:, 0] + 2 / 3) ** 2 + 5 * (xy[:, 1] + 5 / 6) ** 2))
+    vec_length = (num_steps + 1) * nodes
+    uk = np.zeros(vec_length); uk[:nodes] = u0
+    ck = 0.5 + rng.random(vec_length)
+    uhat_all = np.tile(u0, num_steps + 1) * (1.0 + 0.1 * rng.random(vec_length))
+    M = hp.assemble_sparse_lil(u * v * fd.dx)
+    Ad = hp.assemble_sparse(fd.dot(fd.grad(u), fd.grad(v)) * fd.dx)
+    ns_.update(np=np, V=V, u=u, v=v, dx=fd.dx, dot=fd.dot, grad=fd.grad, assemble=fd.assemble, nodes=nodes, num_steps=num_steps,
+               dt=dt, T=num_steps * dt, beta=beta, eps=eps, drift=fd.Constant(('1', '1')), M=M, M_diag=M.diagonal(),
+               M_Lump=hp.row_lump(M, nodes), Ad=Ad, Arot=0 * Ad, dof_neighbors=mesh.dof_neighbors(), vec_length=vec_length,
+               uk=uk, ck=ck, uhat_all=uhat_all, pk=np.zeros(vec_length), dk=np.zeros(vec_length))
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(body, "advection_solidbody_FCT_PDECO_alltime.py:loops", "exec"), ns_)
+    out = dict(n=np.array([n]), ns=np.array([num_steps]), dt=np.array([dt]), beta=np.array([beta]), u0=u0, c=ck, uhat=uhat_all,
+               u=ns_["uk"].copy(), p=ns_["pk"].copy(), d=ns_["dk"].copy())
+    np.savez_compressed(os.path.join(HERE, "ref_cfg2.npz"), **out)
+    print("ref_cfg2.npz written; |u|, |p|, |d| =", *(float(np.linalg.norm(out[k])) for k in "upd"))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ref_data", "ref_fct_cases", "ref_legacy", "ref_armijo", "ref_loops"]
+    which = sys.argv[1:] or ["ref_data", "ref_fct_cases", "ref_legacy", "ref_armijo", "ref_loops", "ref_script_cfg2"]
     for name in which:
         globals()[name]()

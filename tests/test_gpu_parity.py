@@ -346,6 +346,26 @@ def test_full_size_properties_4096():
     assert rel_l2(u[1], u0) > 1e-4                          # something moved
 
 
+def test_config2_drift_loops_vs_reference_script():
+    """fct_advdrift_state / _adjoint / _gradient against the loops of advection_solidbody_FCT_PDECO_alltime.py:206-275 executed
+    from the reference script's own source with the reference's helpers.py and legacy FCT_alg (tests/golden/ref_cfg2.npz)"""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "ref_cfg2.npz")))
+    n, ns, dt, beta = int(g["n"][0]), int(g["ns"][0]), float(g["dt"][0]), float(g["beta"][0])
+    m = RectMeshP1(n, -1.0, 1.0)
+    ctx = m.context()
+    utr = np.zeros((ns + 1) * m.nodes); utr[:m.nodes] = g["u0"]
+    dc, du, duh = ctx.array(g["c"]), ctx.array(utr), ctx.array(g["uhat"])
+    dp, dd = ctx.empty(du.size), ctx.empty(du.size)
+    ctx.advdrift_state(dc, du, ns, dt)
+    assert rel_l2(du.download(), g["u"]) < TOL_STEP
+    ctx.advdrift_adjoint(dc, ctx.array(g["u"]), duh, dp, ns, dt)
+    assert rel_l2(dp.download(), g["p"]) < TOL_STEP
+    ctx.advdrift_gradient(dc, ctx.array(g["u"]), ctx.array(g["p"]), dd, ns, beta)
+    assert rel_l2(dd.download(), g["d"]) < TOL_STEP
+
+
 def test_full_size_parity_vs_oracle_port_4096():
     """BASELINE size (4097^2 DoF): the GPU state trajectory against the C/OpenMP oracle port (oracle/fct_c.c, pinned on the
     numpy oracle, itself pinned on the reference's goldens) on the same u0, c, dt: rel-L2 <= 1e-12 per time step, cost
