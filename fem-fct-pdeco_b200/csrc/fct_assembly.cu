@@ -120,6 +120,13 @@ __device__ __forceinline__ void element_row(const CellGeom& g, int a, const Form
             if (KIND == FCT_FORM_WIND_P1) e[b] = g.gx[a] * (m * (sx + wx[b])) + g.gy[a] * (m * (sy + wy[b]));
             else e[b] = g.gx[b] * (m * (sx + wx[a])) + g.gy[b] * (m * (sy + wy[a]));
         }
+    } else if (KIND == FCT_FORM_DIVW_MASS) {
+        // div(w_h) u v with a P1 wind: div(w_h) is constant on the cell
+        const double dv = (fa.f0[g.d[0]] * g.gx[0] + fa.f0[g.d[1]] * g.gx[1] + fa.f0[g.d[2]] * g.gx[2]) +
+                          (fa.f1[g.d[0]] * g.gy[0] + fa.f1[g.d[1]] * g.gy[1] + fa.f1[g.d[2]] * g.gy[2]);
+        const double sm = dv * g.m12;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) e[b] = sm * ((b == a) ? 2.0 : 1.0);
     } else if (KIND == FCT_FORM_WIND_POLY3 || KIND == FCT_FORM_WIND_POLY3_T) {
         // W_b = int w phi_b with the cubic wind evaluated at the 7 quadrature points of the degree-5 rule
         const double2 p0 = __ldg(reinterpret_cast<const double2*>(fa.f1) + g.d[0]);   // fa.f1 = dof coordinates
@@ -305,6 +312,24 @@ __device__ __forceinline__ double element_load(const CellGeom& g, int a, const F
             I += c_q4[q][2] * (fa.s1 * uq * exp(-fa.s0 * uq));
         }
         return (gpx * g.gx[a] + gpy * g.gy[a]) * (I * g.detJ);
+    } else if (KIND == FCT_LOAD_POLY3) {
+        // int p(x, y) phi_a with a polynomial of degree <= 3 (10 monomial coefficients in fa.f0; fa.f1 = DoF coordinates),
+        // 7-point degree-5 rule: exact
+        const double2 p0 = __ldg(reinterpret_cast<const double2*>(fa.f1) + g.d[0]);
+        const double2 p1 = __ldg(reinterpret_cast<const double2*>(fa.f1) + g.d[1]);
+        const double2 p2 = __ldg(reinterpret_cast<const double2*>(fa.f1) + g.d[2]);
+        double acc = 0.0;
+        for (int q = 0; q < 7; ++q) {
+            const double ph[3] = {1.0 - c_q5[q][0] - c_q5[q][1], c_q5[q][0], c_q5[q][1]};
+            const double x = ph[0] * p0.x + ph[1] * p1.x + ph[2] * p2.x;
+            const double y = ph[0] * p0.y + ph[1] * p1.y + ph[2] * p2.y;
+            const double mono[10] = {1.0, x, y, x * x, x * y, y * y, x * x * x, x * x * y, x * y * y, y * y * y};
+            double pv = 0.0;
+#pragma unroll
+            for (int m = 0; m < 10; ++m) pv += __ldg(fa.f0 + m) * mono[m];
+            acc += c_q5[q][2] * pv * ph[a];
+        }
+        return acc * g.detJ;
     } else {   // FCT_LOAD_P1_1..4: product of 1..4 P1 fields, 7-point degree-5 rule
         const double* fs[4] = {fa.f0, fa.f1, fa.f2, fa.f3};
         const int nf = KIND - FCT_LOAD_P1_1 + 1;
@@ -739,6 +764,7 @@ int fct_assembly_configure(fct_ctx* ctx) {
     rc |= configure_matrix<FCT_FORM_WIND_POLY3_T>(bytes);
     rc |= configure_matrix<FCT_FORM_DRIFT_MASS>(bytes);
     rc |= configure_matrix<FCT_FORM_DRIFT_CONV>(bytes);
+    rc |= configure_matrix<FCT_FORM_DIVW_MASS>(bytes);
     if (cudaFuncSetAttribute(k_drift_low_build, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) rc |= 1;
     return rc;
 }
@@ -864,6 +890,9 @@ extern "C" int fct_assemble_matrix(fct_ctx* ctx, int32_t kind, const double* c0,
         case FCT_FORM_WIND_P1_T:
             FCT_CHECK(c0 && c1, "fct_assemble_matrix(WIND_P1_T): coef0/coef1 (wind components) required");
             return launch_matrix<FCT_FORM_WIND_P1_T>(ctx, fa, scale, acc, out);
+        case FCT_FORM_DIVW_MASS:
+            FCT_CHECK(c0 && c1, "fct_assemble_matrix(DIVW_MASS): coef0/coef1 (wind components) required");
+            return launch_matrix<FCT_FORM_DIVW_MASS>(ctx, fa, scale, acc, out);
         case FCT_FORM_WMASS1:
             FCT_CHECK(c0, "fct_assemble_matrix(WMASS1): coef0 required");
             return launch_matrix<FCT_FORM_WMASS1>(ctx, fa, scale, acc, out);
@@ -938,6 +967,11 @@ extern "C" int fct_assemble_vector(fct_ctx* ctx, int32_t kind, const double* c0,
         case FCT_LOAD_CHTX_ADJ:
             FCT_CHECK(c0 && c1, "fct_assemble_vector(CHTX_ADJ): coef0 (p), coef1 (u) required");
             return launch_vector<FCT_LOAD_CHTX_ADJ>(ctx, fa, scale, acc, out);
+        case FCT_LOAD_POLY3: {
+            FCT_CHECK(c0, "fct_assemble_vector(POLY3): coef0 (10 polynomial coefficients) required");
+            FormArgs fp{c0, ctx->xy, nullptr, nullptr, s0, s1};      // f1 carries the coordinates
+            return launch_vector<FCT_LOAD_POLY3>(ctx, fp, scale, acc, out);
+        }
         default: break;
     }
     fct_set_error("fct_assemble_vector: unknown form kind %d", kind);

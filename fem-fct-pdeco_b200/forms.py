@@ -23,7 +23,7 @@ import scipy.sparse as sp
 from . import _lib
 
 __all__ = ["TrialFunction", "TestFunction", "Function", "Constant", "Expression", "dx", "dot", "grad", "exp", "div",
-           "assemble", "assemble_sparse", "assemble_sparse_lil", "vec_to_function"]
+           "assemble", "assemble_sparse", "assemble_sparse_lil", "vec_to_function", "VectorFunctionSpace", "project"]
 
 
 # ---- expression tree -------------------------------------------------------------------------------------
@@ -85,6 +85,19 @@ class VecConst(Expr):
 class PolyWind(Expr):
     """vector field whose components are polynomials of degree <= 3 in (x, y): 2 x 10 monomial coefficients"""
     def __init__(self, coefs): self.coefs = np.asarray(coefs, dtype=np.float64).reshape(2, 10)
+
+
+class VecFunction(Expr):
+    """P1 vector field (what dolfin's project(wind, VectorFunctionSpace(mesh, 'CG', 1)) returns): two nodal arrays"""
+    def __init__(self, W, wx, wy):
+        self.W = W
+        self.wx = np.ascontiguousarray(wx, dtype=np.float64)
+        self.wy = np.ascontiguousarray(wy, dtype=np.float64)
+
+
+class DivWU(Expr):
+    """div(w_h * u) with a P1 vector field w_h and the trial function u (Schnak_FCT_PDECO.py:256)"""
+    def __init__(self, w, u): self.w, self.u = w, u
 
 
 class Grad(Expr):
@@ -168,19 +181,36 @@ class _P:
         return out
 
 
-def Expression(code, degree=None, **params):
+class Expression(PolyWind):
     """dolfin.Expression for polynomial vector fields, e.g. Expression(('-x[1]','x[0]'), degree=4) or
-    ("speed*2*(x[1]-0.5)*x[0]*(1-x[0])", ...) (helpers.py:876-878).  Parsed by evaluating the C-like string on
-    polynomial objects; parameters are passed as keywords."""
-    if isinstance(code, str) or len(code) != 2:
-        raise NotImplementedError("only two-component vector Expressions are supported")
-    env = {"x": [_P({(1, 0): 1.0}), _P({(0, 1): 1.0})], "__builtins__": {}}
-    env.update({k: float(v) for k, v in params.items() if k != "t" or True})
-    rows = []
-    for comp in code:
-        val = eval(str(comp), env)          # noqa: S307  (polynomial objects only; no builtins)
-        rows.append(_P.of(val).coefs())
-    return PolyWind(np.array(rows))
+    ("speed*2*(x[1]-0.5)*x[0]*(1-x[0])", ...) (helpers.py:876-878).  Parsed by evaluating the C-like strings on
+    polynomial objects; parameters are keywords and stay settable (`wind.t = t`, helpers.py:566), the coefficients being
+    re-derived on every change."""
+
+    def __init__(self, code, degree=None, **params):
+        if isinstance(code, str) or len(code) != 2:
+            raise NotImplementedError("only two-component vector Expressions are supported")
+        object.__setattr__(self, "_code", tuple(str(c) for c in code))
+        object.__setattr__(self, "_params", {k: float(v) for k, v in params.items()})
+        self._reparse()
+
+    def _reparse(self):
+        import math
+        env = {"x": [_P({(1, 0): 1.0}), _P({(0, 1): 1.0})], "__builtins__": {}, "pi": math.pi, "sin": math.sin,
+               "cos": math.cos, "exp": math.exp, "sqrt": math.sqrt, "pow": pow}      # functions of the parameters only
+        env.update(self._params)
+        rows = [_P.of(eval(comp, env)).coefs() for comp in self._code]          # noqa: S307  (polynomial objects only)
+        object.__setattr__(self, "coefs", np.array(rows).reshape(2, 10))
+
+    def __setattr__(self, k, v):
+        self._params[k] = float(v)
+        self._reparse()
+
+    def __getattr__(self, k):
+        p = object.__getattribute__(self, "_params")
+        if k in p:
+            return p[k]
+        raise AttributeError(k)
 
 
 def grad(f):
@@ -194,7 +224,47 @@ def dot(a, b):
 
 
 def div(a):
-    raise NotImplementedError("div(...) forms are not on the catalogue (div(grad f) u v is identically 0 for P1)")
+    """div(w_h * u) with w_h = project(wind, W) (Schnak_FCT_PDECO.py:256) is the one div form on the legacy hot path;
+    div(grad f) of a P1 field vanishes cell-wise (mimura_data_helpers.py:105) and contributes nothing"""
+    if isinstance(a, Prod) and len(a.factors) == 2:
+        w = [f for f in a.factors if isinstance(f, VecFunction)]
+        u = [f for f in a.factors if isinstance(f, Arg) and f.kind == "u"]
+        if len(w) == 1 and len(u) == 1:
+            return DivWU(w[0], u[0])
+    if isinstance(a, Grad) and isinstance(a.f, Function):
+        return Num(0.0)
+    raise NotImplementedError("div(...) of this expression is not on the catalogue")
+
+
+class VectorFunctionSpace:
+    """stand-in for dolfin.VectorFunctionSpace(mesh, 'CG', 1)"""
+    def __init__(self, mesh, family="CG", degree=1):
+        if family not in ("CG", "P", "Lagrange") or degree != 1:
+            raise NotImplementedError("only P1 vector spaces")
+        self._mesh = mesh
+    def mesh(self): return self._mesh
+    def dim(self): return 2 * self._mesh.nodes
+
+
+def project(wind, W):
+    """dolfin.project(wind, W) for a polynomial wind (Schnak_FCT_PDECO.py:70,242): the L2 projection onto P1, component by
+    component -- M w_k = int wind_k v dx, right-hand sides by the exact degree-5 rule (FCT_LOAD_POLY3), mass-matrix solves by
+    Jacobi-PCG on the device (dolfin: LU)"""
+    if not isinstance(wind, PolyWind):
+        raise NotImplementedError("project() of a polynomial Expression only")
+    ctx = W.mesh().context()
+    M = ctx.static()[0]
+    comps = []
+    for k in range(2):
+        dco = ctx.array(np.ascontiguousarray(wind.coefs[k]))
+        rhs, x = ctx.empty(ctx.n), ctx.empty(ctx.n)
+        ctx.assemble_vector(_lib.LOAD_POLY3, rhs, c0=dco)
+        ctx.axpby(0.0, rhs, 0.0, None, x)
+        ctx.solve(_lib.SOLVER_PCG, M, rhs, x, rtol=1e-14, maxit=2000)
+        comps.append(x.download())
+        for a in (dco, rhs, x):
+            a.free()
+    return VecFunction(W, comps[0], comps[1])
 
 
 def exp(f):
@@ -244,7 +314,7 @@ def _expand(e):
             for cb, xb in _expand_vec(e.b):
                 out.append((ca * cb, [Dot(xa, xb)]))
         return out
-    if isinstance(e, (Arg, Function, Exp)):
+    if isinstance(e, (Arg, Function, Exp, DivWU)):
         return [(1.0, [e])]
     raise NotImplementedError(f"unsupported expression node {type(e).__name__}")
 
@@ -284,6 +354,8 @@ class _Term:
         self.fns = [a for a in atoms if isinstance(a, Function)]
         self.exps = [a for a in atoms if isinstance(a, Exp)]
         self.dots = [a for a in atoms if isinstance(a, Dot)]
+        self.divs = [a for a in atoms if isinstance(a, DivWU)]
+        self.u += [a.u for a in self.divs]
 
     def space(self):
         for a in self.u + self.v:
@@ -327,6 +399,14 @@ def _assemble_matrix_terms(ctx, terms):
             continue
         used[i] = True
         nu, nv, nf, ne, nd = len(t.u), len(t.v), len(t.fns), len(t.exps), len(t.dots)
+        if len(t.divs) == 1 and nd == 0 and nu == 1 and nv == 1 and nf == 0 and ne == 0:
+            # div(w_h u) v = (w_h . grad u) v + div(w_h) u v        (Schnak_FCT_PDECO.py:256)
+            w = t.divs[0].w
+            emit(L.FORM_WIND_P1_T, t.coef, c0=w.wx, c1=w.wy)
+            emit(L.FORM_DIVW_MASS, t.coef, c0=w.wx, c1=w.wy)
+            continue
+        if len(t.divs):
+            raise NotImplementedError("div(w_h u) outside div(w_h u) * v * dx")
         if nd == 0 and nu == 1 and nv == 1 and ne == 0:                     # (f1 f2 f3) u v
             if nf == 0:
                 emit(L.FORM_MASS, t.coef)

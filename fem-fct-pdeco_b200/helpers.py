@@ -270,14 +270,15 @@ def cost_functional(var1, var1_target, projected_control, num_steps, dt, M, beta
 # --------------------------------------------------------------------------------------------------
 # time loops, line search, parameter getters, initial conditions (fem-fct-pdeco_b200/solvers.py)
 # --------------------------------------------------------------------------------------------------
-from .solvers import (armijo_line_search_ref, armijo_line_search_sbr_drift, chtxs_sys_IC,  # noqa: E402,F401
-                      cost_functional_proj, extract_data, get_chtxs_sys_params, import_data_final,
+from .solvers import (armijo_line_search, armijo_line_search_chtxs, armijo_line_search_ref,  # noqa: E402,F401
+                      armijo_line_search_sbr_drift, chtxs_sys_IC, cost_functional_proj, cost_functional_proj_FT, extract_data, get_chtxs_sys_params, import_data_final,
                       get_nonlinear_eqns_params, get_schnak_sys_params, nonlinear_equation_IC, schnak_sys_IC,
                       solve_adjoint_chtxs_system, solve_adjoint_nonlinear_equation, solve_adjoint_schnak_system,
                       solve_chtxs_system, solve_nonlinear_equation, solve_schnak_system)
 
 # UFL-like front end for the reference's assemble_sparse(form) / assemble(form) call sites (fem-fct-pdeco_b200/forms.py)
-from .forms import assemble, assemble_sparse, assemble_sparse_lil, vec_to_function  # noqa: E402,F401
+from .forms import (VectorFunctionSpace, assemble, assemble_sparse, assemble_sparse_lil, project,  # noqa: E402,F401
+                    vec_to_function)
 
 
 # ---- legacy Mimura form builders the config-3 script calls through `from helpers import *` -----------------------------

@@ -450,6 +450,137 @@ def armijo_line_search_sbr_drift(u, p, c, d, uhatvec, eps, drift, num_steps, dt,
     return s, u
 
 
+# ---- lost legacy names of configs 3 and 4: re-specified, PARITY UNPINNED -------------------------------------
+def cost_functional_proj_FT(var1, var2, c, d, s, var1_target, var2_target, num_steps, dt, M, c_lower, c_upper, beta):
+    """Called by chemotaxis_mimura_FCT_PGD.py:138,252 as (mk, fk, ck, dk, sk, mhat_T, fhat_T, ...) and by old_helpers.py:35,76 /
+    advection_FCT_PDECO_finaltime_exact.py:230 as (u, Z, c, d, s, uhat_T, z, ...) with Z, z zero arrays; no definition
+    survives in the reference.  The one reading that fits both call sites: final-time tracking of BOTH states plus the
+    Tikhonov term of the projected control,
+        1/2 |var1(T) - var1_target|^2_M + 1/2 |var2(T) - var2_target|^2_M + beta/2 |clip(c)|^2_{L2(Q)},
+    (the advection scripts pass zeros for the second species, which then contributes nothing); `d`, `s` describe the step
+    that produced `c` and do not enter.  PARITY UNPINNED."""
+    return cost_functional(np.asarray(var1), var1_target, np.clip(c, c_lower, c_upper), num_steps, dt, M, beta, "finaltime",
+                           var2=np.asarray(var2), var2_target=var2_target)
+
+
+def armijo_line_search(*args, **kwargs):
+    """The reference's scripts call a function of this name in two generations, neither of which survives:
+
+    (A) Schnak_FCT_PDECO.py:297-300, chemotaxis_FCT_PDECO.py:272-276, nonlinear_FCT_PDECO_alltime.py:229-232,
+        advection_FCT_PDECO_finaltime.py:265-267:
+            armijo_line_search(var1, c, d, var1_target, num_steps, dt, M, c_lower, c_upper, beta, costfun_init, nodes,
+                               V=, optim=, dof_neighbors=, example='Schnak'|'chtxs'|'nonlinear', var2=, var2_target=,
+                               w=|w1=, w2=, max_iter=)  ->  (s, var1_inc[, var2_inc])
+    (B) advection_FCT_PDECO_alltime_exact.py:299, advection_FCT_PDECO_finaltime_exact.py:374-376 (linear problems):
+            armijo_line_search(u, p, w, c, d, uhat, num_steps, dt, M, c_lower, c_upper, beta[, costfun_init, optim=])
+                               ->  s   (or (s, u_inc) when costfun_init is given)
+
+    Both are re-specified on armijo_line_search_ref (helpers.py:1583-1713), the surviving refactoring of the same search:
+    projected backtracking s = s0 / 2^k on cost(clip(c + s d)) - cost0 <= -gam / s |clip(c + s d) - c|^2_{L2(Q)}, every trial
+    a full forward solve with the solver `example` names (A) or the linearised state u + s w (B, and A with w / w1 given).
+    PARITY UNPINNED."""
+    if len(args) >= 5 and np.ndim(args[4]) == 0:
+        return _armijo_legacy_a(*args, **kwargs)
+    return _armijo_legacy_b(*args, **kwargs)
+
+
+def _armijo_legacy_a(var1, c, d, var1_target, num_steps, dt, M, c_lower, c_upper, beta, costfun_init, nodes, V=None,
+                     optim="alltime", dof_neighbors=None, example=None, var2=None, var2_target=None, w=None, w1=None, w2=None,
+                     gam=1e-4, max_iter=10, s0=1):
+    if w1 is None:
+        w1 = w
+    solver = None
+    if w1 is None:
+        solvers = {"Schnak": solve_schnak_system, "schnak": solve_schnak_system, "nonlinear": solve_nonlinear_equation,
+                   "chtxs": solve_chtxs_system}
+        if example not in solvers:
+            raise ValueError(f"Invalid value for 'example': '{example}'. Must be one of {sorted(set(solvers))}.")
+        solver = solvers[example]
+    res = armijo_line_search_ref(var1, c, d, var1_target, num_steps, dt, c_lower, c_upper, beta, costfun_init, nodes, optim, V,
+                                 gam=gam, max_iter=max_iter, s0=s0, nonlinear_solver=solver, dof_neighbors=dof_neighbors,
+                                 var2=var2, var2_target=var2_target, w1=w1, w2=w2)
+    its = res[-1]
+    s = s0 / 2 ** (its - 1)                      # the step of the last trial, i.e. of the returned state / control
+    v1 = res[0]
+    v2 = res[1] if var2 is not None else None
+    if w1 is not None:                           # linearised problems: the trial state is u + s w
+        v1 = np.asarray(var1) + s * np.asarray(w1)
+        v2 = None if var2 is None else (np.asarray(var2) + s * np.asarray(w2) if w2 is not None else var2)
+    return (s, v1, v2) if var2 is not None else (s, v1)
+
+
+def _armijo_legacy_b(u, p, w, c, d, uhat, num_steps, dt, M, c_lower, c_upper, beta, costfun_init=None, optim="alltime",
+                     gam=1e-4, max_iter=10, s0=1):
+    if optim not in ("alltime", "finaltime"):
+        raise ValueError(f"Invalid value for 'optim': '{optim}'. Must be one of ['alltime', 'finaltime'].")
+    u, w, c, d = (np.asarray(x, dtype=np.float64) for x in (u, w, c, d))
+    nodes = u.size // (num_steps + 1)
+
+    def cost(ui, ci):
+        return cost_functional(ui, uhat, ci, num_steps, dt, M, beta, optim)
+    cost0 = cost(u, np.clip(c, c_lower, c_upper)) if costfun_init is None else costfun_init
+    s = s0
+    for k in range(max_iter):
+        s = s0 / 2 ** k
+        c_inc = np.clip(c + s * d, c_lower, c_upper)
+        u_inc = u + s * w
+        if cost(u_inc, c_inc) - cost0 <= -gam / s * L2_norm_sq_Q(c_inc - c, num_steps, dt, M):
+            break
+    del nodes
+    return s if costfun_init is None else (s, u + s * w)
+
+
+def armijo_line_search_chtxs(mk, fk, qk, ck, dk, mhat_T, fhat_T, Mat_fq, chi, Dm, Df, num_steps, dt, nodes, M, M_Lump, Ad,
+                             c_lower, c_upper, beta, V, dof_neighbors, gam=10 ** -4, max_iter=5, s0=1):
+    """chemotaxis_mimura_FCT_PGD.py:238-240 calls this; no definition survives.  Re-specified on the pattern of its sibling
+    armijo_line_search_sbr_drift (old_helpers.py:1-85): s = s0 / 2^k, c_inc = clip(c + s d), every trial re-runs the script's
+    own state loop (chemotaxis_mimura_FCT_PGD.py:160-183: rhs_chtx_f, the f-solve with Mat_fq, mat_chtx_m, rhs_chtx_m, the
+    legacy FCT_alg) into mk, fk IN PLACE, the cost is cost_functional_proj_FT; returns the accepted step s.  PARITY UNPINNED."""
+    from . import mimura_data_helpers as mdh
+    from .forms import TestFunction, TrialFunction, vec_to_function
+    from .helpers import FCT_alg, context_for, rhs_chtx_f
+    u_, v_ = TrialFunction(V), TestFunction(V)
+    ctx = V.mesh().context()
+    dMat = ctx.array(ctx.embed(Mat_fq))
+    drhs, dx_ = ctx.empty(ctx.n), ctx.empty(ctx.n)
+    Z = np.zeros_like(ck)
+    k, s = 0, 1
+    grad_costfun_L2 = L2_norm_sq_Q(np.clip(ck + s * dk, c_lower, c_upper) - ck, num_steps, dt, M)
+    print(f"{grad_costfun_L2=}")
+    costfun_init = cost_functional_proj_FT(mk, fk, ck, dk, s, mhat_T, fhat_T, num_steps, dt, M, c_lower, c_upper, beta)
+    armijo = 10 ** 5
+    del Z, context_for
+    while armijo > -gam / s * grad_costfun_L2 and k < max_iter:
+        s = s0 * (1 / 2 ** k)
+        c_inc = np.clip(ck + s * dk, c_lower, c_upper)
+        print(f"{k =}")
+        print("Solving state equations...")
+        fk[nodes:] = np.zeros(num_steps * nodes)
+        mk[nodes:] = np.zeros(num_steps * nodes)
+        for i in range(1, num_steps + 1):
+            start, end = i * nodes, (i + 1) * nodes
+            m_n = mk[start - nodes:start]
+            m_n_fun = vec_to_function(m_n, V)
+            c_np1_fun = vec_to_function(c_inc[start:end], V)
+            f_n_fun = vec_to_function(fk[start - nodes:start], V)
+            f_rhs = rhs_chtx_f(f_n_fun, m_n_fun, c_np1_fun, dt, v_)
+            drhs.upload(f_rhs); dx_.upload(fk[start - nodes:start])
+            _solve(ctx, _lib.SOLVER_PCG, dMat, drhs, dx_, "f (Mat_fq)")
+            dx_.download(fk[start:end])
+            f_np1_fun = vec_to_function(fk[start:end], V)
+            A_m = mdh.mat_chtx_m(f_np1_fun, m_n_fun, Dm, chi, u_, v_)
+            m_rhs = mdh.rhs_chtx_m(m_n_fun, v_)
+            mk[start:end] = FCT_alg(A_m, m_rhs, m_n, dt, nodes, M, M_Lump, dof_neighbors)
+        cost2 = cost_functional_proj_FT(mk, fk, c_inc, dk, s, mhat_T, fhat_T, num_steps, dt, M, c_lower, c_upper, beta)
+        armijo = cost2 - costfun_init
+        grad_costfun_L2 = L2_norm_sq_Q(c_inc - ck, num_steps, dt, M)
+        k += 1
+    for a in (dMat, drhs, dx_):
+        a.free()
+    print(f"Armijo exit at {k=} with {s=}")
+    return s
+
+
 # ---- trajectory I/O (SURVEY.md 8f-3) --------------------------------------------------------------------------------
 def import_data_final(file_path, nodes, vertex_to_dof, num_steps=0, time_dep=False):
     """helpers.py:1874-1911.  Besides the reference's comma-separated text (`np.tofile(sep=',')`), a `.npy` file with the

@@ -175,12 +175,14 @@ int fct_axpby(fct_ctx* ctx, int64_t len, double a, const double* x_dev, double b
  *                          helpers.py:506-508 (Schnakenberg) and :876-878 (nonlinear)
  *   FCT_FORM_DRIFT_MASS    (b.grad c) u v      the two parts of FCT_FORM_DRIFT on their own (the legacy scripts
  *   FCT_FORM_DRIFT_CONV    (b.grad v) c u      assemble them separately: advection_solidbody_FCT_PDECO_alltime.py:222-223)
+ *   FCT_FORM_DIVW_MASS     div(w_h) u v, w_h P1 nodal   coef0 = wx, coef1 = wy: together with FCT_FORM_WIND_P1_T the legacy
+ *                          div(w_h u) v of a projected wind (Schnak_FCT_PDECO.py:70,242,256)
  * out_vals = scale * form (+ out_vals if accumulate != 0). */
 enum {
     FCT_FORM_MASS = 0, FCT_FORM_STIFFNESS = 1, FCT_FORM_DRIFT = 2, FCT_FORM_WIND_P1 = 3,
     FCT_FORM_WIND_P1_T = 4, FCT_FORM_WMASS1 = 5, FCT_FORM_WMASS2 = 6, FCT_FORM_WMASS3 = 7,
     FCT_FORM_CHTX = 8, FCT_FORM_CHTX_EXP = 9, FCT_FORM_CHTX_ADJ = 10, FCT_FORM_WIND_POLY3 = 11,
-    FCT_FORM_WIND_POLY3_T = 12, FCT_FORM_DRIFT_MASS = 13, FCT_FORM_DRIFT_CONV = 14
+    FCT_FORM_WIND_POLY3_T = 12, FCT_FORM_DRIFT_MASS = 13, FCT_FORM_DRIFT_CONV = 14, FCT_FORM_DIVW_MASS = 15
 };
 int fct_assemble_matrix(fct_ctx* ctx, int32_t kind, const double* coef0_dev, const double* coef1_dev,
                         const double* coef2_dev, double s0, double s1, double scale, int32_t accumulate,
@@ -191,10 +193,12 @@ int fct_assemble_matrix(fct_ctx* ctx, int32_t kind, const double* coef0_dev, con
  *   FCT_LOAD_DRIFT_GRAD    p (b.grad u) v, coef0 = p, coef1 = u, s0,s1 = b
  *                          (advection_solidbody_FCT_PDECO_alltime.py:273)
  *   FCT_LOAD_CHTX_ADJ      s1 * u exp(-s0 u) grad p . grad w, coef0 = p, coef1 = u, degree 4 (helpers.py:1531-1532)
+ *   FCT_LOAD_POLY3         p(x,y) v with a polynomial of degree <= 3, coef0 = 10 device doubles (monomial order as for
+ *                          FCT_FORM_WIND_POLY3): the right-hand sides of project(wind, W) (Schnak_FCT_PDECO.py:70,242)
  * out = scale * form (+ out if accumulate). */
 enum {
     FCT_LOAD_P1_1 = 0, FCT_LOAD_P1_2 = 1, FCT_LOAD_P1_3 = 2, FCT_LOAD_P1_4 = 3, FCT_LOAD_CONST = 4,
-    FCT_LOAD_DRIFT_GRAD = 5, FCT_LOAD_CHTX_ADJ = 6
+    FCT_LOAD_DRIFT_GRAD = 5, FCT_LOAD_CHTX_ADJ = 6, FCT_LOAD_POLY3 = 7
 };
 int fct_assemble_vector(fct_ctx* ctx, int32_t kind, const double* coef0_dev, const double* coef1_dev,
                         const double* coef2_dev, const double* coef3_dev, double s0, double s1, double scale,

@@ -71,6 +71,7 @@ class Const(Node):
     def __init__(self, v): self.v = float(v)
     def degree(self): return 0
     def eval(self, ctx): return self.v
+    def grad_eval(self, ctx): return np.zeros((1, 1, 1, 1, 2))
 
 
 class Argument(Node):
@@ -178,6 +179,14 @@ class Prod(Node):
     def degree(self): return self.a.degree() + self.b.degree()
     def args(self): return self.a.args() | self.b.args()
 
+    def grad_eval(self, ctx):            # product rule for scalar factors (needed by div(f * grad(p)))
+        if self.a.rank or self.b.rank:
+            raise TypeError("gradient of a vector-valued product")
+        x, y = self.a.eval(ctx), self.b.eval(ctx)
+        x = x[..., None] if isinstance(x, np.ndarray) else x
+        y = y[..., None] if isinstance(y, np.ndarray) else y
+        return x * self.b.grad_eval(ctx) + y * self.a.grad_eval(ctx)
+
     def eval(self, ctx):
         x, y = self.a.eval(ctx), self.b.eval(ctx)
         if self.a.rank and not self.b.rank and isinstance(y, np.ndarray):
@@ -228,15 +237,44 @@ class Dot(Node):
     def eval(self, ctx): return np.sum(self.a.eval(ctx) * self.b.eval(ctx), axis=-1)
 
 
+class VecFunction(Node):
+    """P1 vector field, e.g. project(wind, VectorFunctionSpace(mesh, 'CG', 1)) (Schnak_FCT_PDECO.py:70,242)"""
+    rank = 1
+    def __init__(self, W, wx, wy):
+        self.W, self.V = W, W.scalar
+        self.wx, self.wy = np.array(wx, dtype=np.float64), np.array(wy, dtype=np.float64)
+    def degree(self): return 1
+    def eval(self, ctx):
+        return np.stack([ctx.asm.at_quad(self.wx, ctx.phi), ctx.asm.at_quad(self.wy, ctx.phi)], axis=-1)[:, :, None, None, :]
+    def div_eval(self, ctx):
+        G, c = ctx.asm.G, ctx.asm.cells
+        return (np.einsum('ca,ca->c', self.wx[c], G[:, :, 0]) + np.einsum('ca,ca->c', self.wy[c], G[:, :, 1]))[:, None, None, None]
+
+
 class DivOp(Node):
-    """div(grad(f)) of a P1 function vanishes cell-wise; div of anything else is not on the hot path"""
+    """div(w_h * u) = div(w_h) u + w_h . grad(u) for a P1 vector field and an argument (Schnak_FCT_PDECO.py:256);
+    div(grad(f)) of a P1 function vanishes cell-wise (mimura_data_helpers.py:105)"""
     def __init__(self, a):
-        if not (isinstance(a, Grad)):
+        self.kind = None
+        if isinstance(a, Grad):
+            self.kind = "lap"
+        elif isinstance(a, Prod) and isinstance(a.b, Grad) and not a.a.rank:
+            self.kind = "fgrad"          # div(f grad(p)) = grad(f) . grad(p) + f lap(p), lap(p) = 0 cell-wise for P1
+        elif isinstance(a, Prod) and {type(a.a), type(a.b)} == {VecFunction, Argument}:
+            self.kind = "wu"
+            self.w = a.a if isinstance(a.a, VecFunction) else a.b
+            self.u = a.a if isinstance(a.a, Argument) else a.b
+        else:
             raise NotImplementedError("div() of a general vector field")
         self.a = a
-    def degree(self): return 0
+    def degree(self): return 0 if self.kind == "lap" else max(self.a.degree() - 1, 0) if self.kind == "fgrad" else 1
     def args(self): return self.a.args()
-    def eval(self, ctx): return 0.0
+    def eval(self, ctx):
+        if self.kind == "lap":
+            return 0.0
+        if self.kind == "fgrad":
+            return np.sum(self.a.a.grad_eval(ctx) * self.a.b.eval(ctx), axis=-1)
+        return self.w.div_eval(ctx) * self.u.eval(ctx) + np.sum(self.w.eval(ctx) * self.u.grad_eval(ctx), axis=-1)
 
 
 def grad(f): return Grad(f)
@@ -273,6 +311,35 @@ class FunctionSpace:
         self.asm = P1Assembler(mesh)
     def dim(self): return self._mesh.nodes
     def mesh(self): return self._mesh
+
+
+class VectorFunctionSpace:
+    """stand-in for dolfin.VectorFunctionSpace(mesh, 'CG', 1)"""
+    def __init__(self, mesh, family="CG", degree=1):
+        assert family in ("CG", "P", "Lagrange") and degree == 1
+        self._mesh = mesh
+        self.scalar = FunctionSpace(mesh)
+    def mesh(self): return self._mesh
+    def dim(self): return 2 * self._mesh.nodes
+
+
+def project(expr, W):
+    """dolfin.project(expr, W): the L2 projection, M w_k = int expr_k v dx per component (dolfin solves with LU)"""
+    from scipy.sparse.linalg import spsolve
+    V = W.scalar
+    v = TestFunction(V)
+    M = V.asm.to_csr(V.asm.mass()).tocsc()
+    comps = []
+    for k in range(2):
+        comp = _Component(expr, k)
+        comps.append(spsolve(M, assemble(comp * v * dx)))
+    return VecFunction(W, comps[0], comps[1])
+
+
+class _Component(Node):
+    def __init__(self, vec, k): self.vec, self.k = vec, k
+    def degree(self): return self.vec.degree()
+    def eval(self, ctx): return self.vec.eval(ctx)[..., self.k]
 
 
 def TrialFunction(V): return Argument(V, 1)
@@ -353,6 +420,6 @@ def make_module():
     """a module object that can stand in for `dolfin` in sys.modules"""
     m = types.ModuleType("dolfin")
     for name in ("TrialFunction", "TestFunction", "Function", "Constant", "Expression", "FunctionSpace", "dx", "dot", "grad",
-                 "div", "exp", "assemble", "as_backend_type", "vertex_to_dof_map"):
+                 "div", "exp", "assemble", "as_backend_type", "vertex_to_dof_map", "VectorFunctionSpace", "project"):
         setattr(m, name, globals()[name])
     return m

@@ -29,6 +29,10 @@ Writes
   ref_cfg2.npz        BASELINE config 2: inputs + outputs of the state / adjoint / gradient loops of
                       advection_solidbody_FCT_PDECO_alltime.py:206-275 -- the script's own source lines executed with the
                       reference's helpers.py (on oracle/fake_dolfin.py) and its legacy FCT_alg.
+  ref_cfg3.npz        BASELINE config 3: state + adjoint loops of chemotaxis_mimura_FCT_PGD.py:157-225, executed from the
+                      script's source with the reference's mimura_data_helpers.py and old_helpers.py form builders.
+  ref_cfg4.npz        BASELINE config 4: state + adjoint loops of Schnak_FCT_PDECO.py:190-279 (time-dependent Expression
+                      wind, project(wind, W), div(w_h u) w), executed from the script's source.
 """
 import os
 import sys
@@ -429,7 +433,133 @@ def ref_script_cfg2():
     print("ref_cfg2.npz written; |u|, |p|, |d| =", *(float(np.linalg.norm(out[k])) for k in "upd"))
 
 
+def _script_namespace(hp, fd):
+    """helpers.py namespace + the legacy definitions of old_helpers.py (FCT_alg, rhs_chtx_*; compiled from their source as
+    it stands) + dolfin's names on the stand-in: what `from dolfin import *; from helpers import *` gives the legacy scripts"""
+    import scipy.sparse.linalg as spl
+    ns_ = dict(vars(hp))
+    for name in ("dx", "dot", "grad", "div", "exp", "assemble", "project", "TrialFunction", "TestFunction", "Function",
+                 "Constant", "Expression", "VectorFunctionSpace"):
+        ns_[name] = getattr(fd, name)
+    old = open(os.path.join(REFERENCE_DIR, "old_helpers.py")).read().splitlines()
+    start = next(i for i, l in enumerate(old) if l.startswith("def rhs_chtx_m("))
+    exec(compile("\n".join(old[start:]), "old_helpers.py:87-204", "exec"), ns_)
+    ns_.update(np=np, spsolve=spl.spsolve)
+    return ns_
+
+
+def _loop_source(script_name, first_marker, last_marker):
+    """source lines of a legacy script from the line containing first_marker up to (not including) the banner line above the
+    line containing last_marker, de-indented by the 4 spaces of the enclosing `while`"""
+    script = open(os.path.join(REFERENCE_DIR, script_name)).read().splitlines()
+    i0 = next(i for i, l in enumerate(script) if first_marker in l)
+    i1 = next(i for i, l in enumerate(script) if last_marker in l and i > i0) - 1
+    return "\n".join(l[4:] if l.startswith("    ") else l for l in script[i0:i1])
+
+
+def ref_script_cfg4():
+    """BASELINE config 4: the state and adjoint loops of Schnak_FCT_PDECO.py (:190-279) -- the script's own source lines, with
+    the time-dependent Expression wind, project(wind, W) and the div(w_h u) w form -- executed with the reference's helpers.py
+    and legacy FCT_alg on oracle/fake_dolfin.py."""
+    import contextlib
+    import io
+    from oracle import fake_dolfin as fd
+    from oracle.ref_loader import load_reference_helpers_on_fake_dolfin
+    hp = load_reference_helpers_on_fake_dolfin()
+    ns_ = _script_namespace(hp, fd)
+    body = _loop_source("Schnak_FCT_PDECO.py", "print('Solving state equations...')", "3. choose the descent direction")
+    n, num_steps, dt = 10, 3, 2e-3
+    mesh = RectMesh(n, 0.0, 1.0)
+    V = fd.FunctionSpace(mesh)
+    W = fd.VectorFunctionSpace(mesh)
+    nodes = mesh.nodes
+    u, w = fd.TrialFunction(V), fd.TestFunction(V)
+    rng = np.random.default_rng(31)
+    v2d = np.array(mesh.vertex_to_dof)
+    u0, v0 = hp.schnak_sys_IC(0.0, 1.0, 1.0 / n, nodes, v2d)
+    vec_length = (num_steps + 1) * nodes
+    uk = np.zeros(vec_length); vk = np.zeros(vec_length)
+    uk[:nodes], vk[:nodes] = u0, v0
+    ck = 0.1 * np.ones(vec_length) + 0.01 * (rng.random(vec_length) - 0.5)
+    uhat_T, vhat_T = u0 * (1 + 0.05 * rng.random(nodes)), v0 * (1 + 0.05 * rng.random(nodes))
+    wind = fd.Expression(('-(x[1]-0.5)*sin(2*pi*t)', '(x[0]-0.5)*sin(2*pi*t)'), degree=4, pi=np.pi, t=0)
+    M = hp.assemble_sparse_lil(u * w * fd.dx)
+    ns_.update(V=V, W=W, u=u, w=w, nodes=nodes, num_steps=num_steps, dt=dt, T=num_steps * dt, vec_length=vec_length, wind=wind,
+               Du=1 / 100, Dv=8.6676, c_a=0.1, c_b=0.9, gamma=230.82, omega1=100, omega2=0.6, M=M, M_Lump=hp.row_lump(M, nodes),
+               Ad=hp.assemble_sparse(fd.dot(fd.grad(u), fd.grad(w)) * fd.dx), dof_neighbors=mesh.dof_neighbors(), uk=uk, vk=vk,
+               ck=ck, uhat_T=uhat_T, vhat_T=vhat_T)
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(body, "Schnak_FCT_PDECO.py:loops", "exec"), ns_)
+    out = dict(n=np.array([n]), ns=np.array([num_steps]), dt=np.array([dt]), u0=u0, v0=v0, c=ck, uhat_T=uhat_T, vhat_T=vhat_T,
+               u=ns_["uk"].copy(), v=ns_["vk"].copy(), p=ns_["pk"].copy(), q=ns_["qk"].copy())
+    np.savez_compressed(os.path.join(HERE, "ref_cfg4.npz"), **out)
+    print("ref_cfg4.npz written; norms", *(float(np.linalg.norm(out[k])) for k in "uvpq"))
+
+
+def ref_script_cfg3():
+    """BASELINE config 3: the state and adjoint loops of chemotaxis_mimura_FCT_PGD.py (:157-225) -- the script's own source
+    lines with the reference's mimura_data_helpers.py and the legacy form builders / FCT_alg of old_helpers.py -- executed on
+    oracle/fake_dolfin.py."""
+    import contextlib
+    import importlib.util
+    import io
+    import types
+    from oracle import fake_dolfin as fd
+    from oracle.ref_loader import load_reference_helpers_on_fake_dolfin
+    hp = load_reference_helpers_on_fake_dolfin()
+    ns_ = _script_namespace(hp, fd)
+    # the reference's mimura_data_helpers.py, unmodified (its image-library imports are stubbed: they serve data loading only)
+    saved = {k: sys.modules.get(k) for k in ("dolfin", "helpers", "PIL", "PIL.Image", "matplotlib", "matplotlib.image")}
+    sys.modules["dolfin"] = fd.make_module()
+    sys.modules["helpers"] = hp
+    for name in ("PIL", "PIL.Image", "matplotlib", "matplotlib.image"):
+        if saved[name] is None:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["PIL"].Image = sys.modules["PIL.Image"]
+    sys.modules["matplotlib"].image = sys.modules["matplotlib.image"]
+    try:
+        spec = importlib.util.spec_from_file_location("_fct_reference_mimura", os.path.join(REFERENCE_DIR, "mimura_data_helpers.py"))
+        mdh = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mdh)
+    finally:
+        for k, v_ in saved.items():
+            if v_ is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v_
+    body = _loop_source("chemotaxis_mimura_FCT_PGD.py", "print('Solving state equations...')", "3. choose the descent direction")
+    n, num_steps, dt = 8, 3, 0.02
+    a1, a2 = 0.0, 4.0
+    delta, Dm, Df, chi = 32, 0.0625, 1, 8.5
+    mesh = RectMesh(n, a1, a2)
+    V = fd.FunctionSpace(mesh)
+    nodes = mesh.nodes
+    u, v = fd.TrialFunction(V), fd.TestFunction(V)
+    rng = np.random.default_rng(41)
+    v2d = np.array(mesh.vertex_to_dof)
+    m0 = hp.reorder_vector_to_dof(mdh.m_initial_condition(a1, a2, (a2 - a1) / n).reshape(nodes), 1, nodes, v2d)
+    f0 = 1 / 32 * np.ones(nodes)
+    vec_length = (num_steps + 1) * nodes
+    mk = np.zeros(vec_length); fk = np.zeros(vec_length)
+    mk[:nodes], fk[:nodes] = m0, f0
+    ck = 0.5 + rng.random(vec_length)
+    mhat_T, fhat_T = m0 * (1 + 0.05 * rng.random(nodes)), f0 * (1 + 0.05 * rng.random(nodes))
+    M = hp.assemble_sparse_lil(u * v * fd.dx)
+    Ad = hp.assemble_sparse(fd.dot(fd.grad(u), fd.grad(v)) * fd.dx)
+    ns_.update(V=V, u=u, v=v, nodes=nodes, num_steps=num_steps, dt=dt, T=num_steps * dt, vec_length=vec_length, Dm=Dm, Df=Df,
+               chi=chi, delta=delta, M=M, M_Lump=hp.row_lump(M, nodes), Ad=Ad, Mat_fq=M + dt * (Df * Ad + delta * M),
+               dof_neighbors=mesh.dof_neighbors(), mk=mk, fk=fk, ck=ck, mhat_T=mhat_T, fhat_T=fhat_T, mimura_data_helpers=mdh)
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(body, "chemotaxis_mimura_FCT_PGD.py:loops", "exec"), ns_)
+    out = dict(n=np.array([n]), ns=np.array([num_steps]), dt=np.array([dt]), box=np.array([a1, a2]), m0=m0, f0=f0, c=ck,
+               mhat_T=mhat_T, fhat_T=fhat_T, m=ns_["mk"].copy(), f=ns_["fk"].copy(), p=ns_["pk"].copy(), q=ns_["qk"].copy(),
+               params=np.array([delta, Dm, Df, chi], dtype=np.float64))
+    np.savez_compressed(os.path.join(HERE, "ref_cfg3.npz"), **out)
+    print("ref_cfg3.npz written; norms", *(float(np.linalg.norm(out[k])) for k in "mfpq"))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ref_data", "ref_fct_cases", "ref_legacy", "ref_armijo", "ref_loops", "ref_script_cfg2"]
+    which = sys.argv[1:] or ["ref_data", "ref_fct_cases", "ref_legacy", "ref_armijo", "ref_loops", "ref_script_cfg2",
+                             "ref_script_cfg3", "ref_script_cfg4"]
     for name in which:
         globals()[name]()
