@@ -134,14 +134,21 @@ static int exchange_ranges(fct_ctx* ctx, double* a, int64_t slo0, int64_t slo1, 
 }
 
 bool fct_p2p_ready(const fct_ctx* ctx);
-int fct_p2p_exchange(fct_ctx* ctx, double* v0, double* v1);
+int fct_p2p_exchange(fct_ctx* ctx, double* v0, double* v1, const unsigned long long* cond);
 
 int fct_halo_exchange_if(fct_ctx* ctx, double* vec) {
     if (!ctx->comm || ctx->comm->world == 1) return 0;
     if (!ctx->capturing) ctx->exchanges++;
-    if (fct_p2p_ready(ctx)) return fct_p2p_exchange(ctx, vec, nullptr);
+    if (fct_p2p_ready(ctx)) return fct_p2p_exchange(ctx, vec, nullptr, nullptr);
     return exchange_ranges(ctx, vec, ctx->send_lo[0], ctx->send_lo[1], 0, ctx->row_begin, ctx->send_hi[0],
                            ctx->send_hi[1], ctx->row_end, ctx->n);
+}
+
+// exchange only if the device word *cond is nonzero (peer mailboxes only; *cond must be the same on every rank)
+int fct_halo_exchange_cond(fct_ctx* ctx, double* vec, const unsigned long long* cond) {
+    if (!ctx->comm || ctx->comm->world == 1) return 0;
+    FCT_CHECK(fct_p2p_ready(ctx), "fct_halo_exchange_cond: needs the peer mailboxes");
+    return fct_p2p_exchange(ctx, vec, nullptr, cond);
 }
 
 extern "C" int fct_halo_exchange(fct_ctx* ctx, double* vec) {
@@ -175,7 +182,7 @@ int fct_allreduce_sum_dev(fct_ctx* ctx, double* dev, int count) {
 // two vectors in one message (R+ and R-)
 int fct_halo_exchange2_if(fct_ctx* ctx, double* v0, double* v1) {
     if (!ctx->comm || ctx->comm->world == 1) return 0;
-    if (fct_p2p_ready(ctx)) return fct_p2p_exchange(ctx, v0, v1);
+    if (fct_p2p_ready(ctx)) return fct_p2p_exchange(ctx, v0, v1, nullptr);
     if (fct_halo_exchange_if(ctx, v0)) return 1;
     return v1 ? fct_halo_exchange_if(ctx, v1) : 0;
 }

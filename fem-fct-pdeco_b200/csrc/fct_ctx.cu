@@ -121,6 +121,7 @@ void fct_templates_free(fct_ctx* ctx);
 int fct_templates_build(fct_ctx* ctx);
 void fct_geom_templates_free(fct_ctx* ctx);
 void fct_tiles_free(fct_ctx* ctx);
+int fct_tiles_prepare(fct_ctx* ctx);
 
 template <typename T>
 static int dev_alloc(T** p, size_t count) {
@@ -410,6 +411,7 @@ extern "C" int fct_ctx_set_rings(fct_ctx* ctx, int32_t depth, const int32_t* rin
     ctx->depth = depth;
     for (int j = 0; j <= depth; ++j) { ctx->ring_lo[j] = ring_lo[j]; ctx->ring_hi[j] = ring_hi[j]; }
     for (int j = depth + 1; j < 9; ++j) { ctx->ring_lo[j] = 0; ctx->ring_hi[j] = ctx->n; }
+    if (fct_tiles_prepare(ctx)) return 1;      // the tile lists depend on the rings
     return fct_reset_check_from(ctx);
 }
 

@@ -1249,15 +1249,24 @@ static int chebsi_tiles(fct_ctx* ctx, const double* Md, const double* b, double*
     const double* yold = nullptr;
     int cur = 0, vmid = multi ? vb : K, it = 2;
     int kmax = ctx->tile_kc;
-    if (multi) { if (kmax > K) kmax = K; if (kmax > vb + 1) kmax = vb + 1; }
+    if (multi && kmax > K) kmax = K;
+    // Multi-GPU: a launch of kk iterations needs its inputs on ring kk and leaves the iterate on ring vmid - kk.  A launch (one
+    // pass over the matrix) costs more than an exchange, so the number of launches stays ceil((iters-1)/kmax); its slack is
+    // spent on shorter groups that fit the rings still valid, which saves the exchange in front of them.
+    int slack = multi ? ((iters - 1 + kmax - 1) / kmax) * kmax - (iters - 1) : 0;
     while (it <= iters) {
         const int rem = iters - it + 1;
         int kk = rem < kmax ? rem : kmax;
-        if (rem - kk == 1 && kk > 2) --kk;               // never leave a single iteration for the last launch
         if (multi && vmid < kk) {
-            if (fct_halo_exchange2_if(ctx, const_cast<double*>(ymid), const_cast<double*>(yold))) return 1;
-            vmid = K;
+            if (vmid >= 2 && kk - vmid <= slack && rem - vmid != 1) {
+                slack -= kk - vmid;
+                kk = vmid;
+            } else {
+                if (fct_halo_exchange2_if(ctx, const_cast<double*>(ymid), const_cast<double*>(yold))) return 1;
+                vmid = K;
+            }
         }
+        if (rem - kk == 1 && kk > 2) --kk;               // never leave a single iteration for the last launch
         const bool last = (it + kk - 1 == iters);
         double* out_mid = last ? y : pair[cur ^ 1][0];
         double* out_old = last ? nullptr : pair[cur ^ 1][1];
@@ -1272,7 +1281,7 @@ static int chebsi_tiles(fct_ctx* ctx, const double* Md, const double* b, double*
 int fct_chebsi_v(fct_ctx* ctx, const double* M, const double* Md, const double* b, double* y, int32_t iters, double lmin,
                  double lmax, int vb, int* vy) {
     if (ctx->tiles_ok && ctx->cheb_tiles_ok && M == ctx->M && Md == ctx->Mdiag && ctx->cheb_mdtab && iters >= 3 && ctx->tile_kc >= 2 &&
-        (!ctx->comm || (ctx->depth >= 2 && vb >= 1)))
+        (!ctx->comm || (ctx->depth >= 3 && vb >= 1)))
         return chebsi_tiles(ctx, Md, b, y, iters, lmin, lmax, vb, vy);
     // helpers.py:164-180
     const double rho = (lmax - lmin) / (lmax + lmin);
@@ -1407,16 +1416,23 @@ static inline int tile_kj(const fct_ctx* ctx) {
 static inline bool jacobi_use_tiles(const fct_ctx* ctx, const double* dinv) {
     return ctx->tiles_ok && dinv && ctx->jac_mode == 2 && tile_kj(ctx) >= 2;
 }
+int fct_halo_exchange_cond(fct_ctx* ctx, double* vec, const unsigned long long* cond);      // fct_comm.cu
+static inline bool jacobi_tiles_deep(const fct_ctx* ctx, bool p2p) {
+    return ctx->comm && p2p && ctx->depth >= 2 * tile_kj(ctx);
+}
 static int jacobi_cycle_tiles(fct_ctx* ctx, const double* Lv, const double* b, double* x, double* tmp, double rtol,
                               int max_sweeps, bool p2p, int use_handle, cudaGraphConditionalHandle handle) {
     const int K = tile_kj(ctx);
+    // halo depth >= 2 K (peer mailboxes): the iterate is valid on ring depth-K after the first launch, which is enough for the
+    // second one -- one exchange per cycle; if the solve ends after a first half, jacobi_copy_back exchanges the result
+    const bool deep = jacobi_tiles_deep(ctx, p2p);
     int rc = 0;
     fct_set_ring(ctx, 0);
     for (int half = 0; half < 2 && !rc; ++half) {
         double* xin = half ? tmp : x;
         double* xout = half ? x : tmp;
         rc |= fct_tile_jacobi(ctx, K, Lv, b, xin, xout);
-        rc |= fct_halo_exchange_if(ctx, xout);
+        if (!(deep && half == 0)) rc |= fct_halo_exchange_if(ctx, xout);
         const int uh = (use_handle && half == 1) ? 1 : 0;
         if (p2p) {
             rc |= fct_p2p_max2_decide(ctx, rtol, max_sweeps, uh, handle, half == 0 ? 1 : 0);
@@ -1429,9 +1445,10 @@ static int jacobi_cycle_tiles(fct_ctx* ctx, const double* Lv, const double* b, d
     }
     return rc;
 }
-static void jacobi_copy_back(fct_ctx* ctx, const double* tmp, double* x) {
+static int jacobi_copy_back(fct_ctx* ctx, const double* tmp, double* x, bool p2p) {
     k_copy_if<<<148 * 4, 256, 0, ctx->stream>>>(ctx->jstate + 12, tmp, x, ctx->n);
     ctx->launches++;
+    return jacobi_tiles_deep(ctx, p2p) ? fct_halo_exchange_cond(ctx, x, ctx->jstate + 12) : 0;
 }
 
 // Jacobi solve of Lv x = b; x holds the initial guess on entry (valid on every local row) and the result on exit
@@ -1491,7 +1508,7 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
         }
         FCT_CUDA(cudaGraphLaunch((cudaGraphExec_t)jg.exec, ctx->stream));
         ctx->launches += 3;      // at least one body iteration; the executed sweeps are counted in jstate[4]
-        if (tiles) jacobi_copy_back(ctx, tmp, x);
+        if (tiles && jacobi_copy_back(ctx, tmp, x, p2p)) return 1;
         return 0;
     }
     if (tiles) {
@@ -1499,7 +1516,7 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
         const int per = 2 * tile_kj(ctx);
         for (int c = 0; c < (max_sweeps + per - 1) / per; ++c)
             if (jacobi_cycle_tiles(ctx, Lv, b, x, tmp, rtol, max_sweeps, p2p, 0, 0)) return 1;
-        jacobi_copy_back(ctx, tmp, x);
+        if (jacobi_copy_back(ctx, tmp, x, p2p)) return 1;
         return fct_launch_error(ctx, "fct_jacobi_solve");
     }
     if (ctx->comm) {

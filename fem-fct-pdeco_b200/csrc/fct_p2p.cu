@@ -25,7 +25,9 @@ struct P2PHeader {
     unsigned long long xseq;                        // exchanges done so far (owner only)
     unsigned long long rseq;                        // reductions done so far (owner only)
     unsigned long long error;                       // set when a wait timed out
-    unsigned long long pad[5];
+    unsigned long long done_cnt;                    // blocks of k_halo_xchg finished so far (owner only)
+    unsigned long long push_cnt[2];                 // blocks that finished their push, per direction (owner only)
+    unsigned long long pad[2];
 };
 
 struct fct_p2p {
@@ -60,14 +62,25 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned 
     return true;
 }
 
-// blockIdx.x = 0: exchange with rank-1; 1: with rank+1.  nvec vectors travel in one message.
-__global__ void __launch_bounds__(1024)
+// Blocks [0, NB) exchange with rank-1, blocks [NB, 2 NB) with rank+1; nvec vectors travel in one message.  A message is
+// split over the NB blocks of its direction (one block alone moves ~5 GB/s over NVLink, which made a 130 KB halo cost 26 us):
+// every block pushes its slice, the last one to finish publishes the sequence number, every block waits for the incoming
+// number and unpacks its slice.  All 2 NB blocks are co-resident (the launch follows the producing kernel in stream order), and
+// a wait depends only on the neighbour's pushes, which never wait.
+#define FCT_P2P_NB 16
+#define FCT_P2P_NT 256
+__global__ void __launch_bounds__(FCT_P2P_NT)
 k_halo_xchg(unsigned char* mine, unsigned char* peer_lo, unsigned char* peer_hi, double* v0, double* v1, int nvec,
-            int send_lo0, int send_lo1, int send_hi0, int send_hi1, int row_begin, int row_end, int n, int max_halo) {
+            int send_lo0, int send_lo1, int send_hi0, int send_hi1, int row_begin, int row_end, int n, int max_halo,
+            const unsigned long long* cond) {
+    // conditional exchange: *cond is a rank-uniform word (a decision taken on all-reduced values), so that either every rank
+    // takes part or none does
+    if (cond && *cond == 0ull) return;
     P2PHeader* H = reinterpret_cast<P2PHeader*>(mine);
     const unsigned long long seq = H->xseq + 1;          // same on every rank: all ranks run the same sequence
     const int slot = (int)(seq % FCT_P2P_SLOTS);
-    const int dir = blockIdx.x;                           // 0: lo neighbour, 1: hi neighbour
+    const int dir = blockIdx.x / FCT_P2P_NB;              // 0: lo neighbour, 1: hi neighbour
+    const int part = blockIdx.x % FCT_P2P_NB;
     unsigned char* peer = dir == 0 ? peer_lo : peer_hi;
     double* vecs[FCT_P2P_MAXVEC] = {v0, v1};
     if (peer) {
@@ -75,36 +88,40 @@ k_halo_xchg(unsigned char* mine, unsigned char* peer_lo, unsigned char* peer_hi,
         const int s0 = dir == 0 ? send_lo0 : send_hi0, s1 = dir == 0 ? send_lo1 : send_hi1;
         double* dst = mail_ptr(peer, dir == 0 ? 1 : 0, slot, max_halo);
         for (int q = 0; q < nvec; ++q)
-            for (int i = threadIdx.x; i < s1 - s0; i += blockDim.x) dst[(size_t)q * max_halo + i] = vecs[q][s0 + i];
+            for (int i = part * FCT_P2P_NT + threadIdx.x; i < s1 - s0; i += FCT_P2P_NB * FCT_P2P_NT)
+                dst[(size_t)q * max_halo + i] = vecs[q][s0 + i];
         __syncthreads();
+        __shared__ int ok;
         if (threadIdx.x == 0) {
             __threadfence_system();
-            P2PHeader* PH = reinterpret_cast<P2PHeader*>(peer);
-            st_release_sys(dir == 0 ? &PH->flag_hi[slot] : &PH->flag_lo[slot], seq);
-        }
-        // wait for the neighbour's message and unpack it into my halo entries; once a wait has timed out the context is
-        // in error (the host fails the call at its next synchronisation point, fct_p2p_check) and later exchanges do not
-        // spend another time-out each
-        __shared__ int ok;
-        if (threadIdx.x == 0)
+            const unsigned long long arrived = atomicAdd(&H->push_cnt[dir], 1ull);
+            if ((arrived + 1ull) % FCT_P2P_NB == 0ull) {
+                __threadfence_system();                   // the other blocks' slices (fenced before their arrival) come first
+                P2PHeader* PH = reinterpret_cast<P2PHeader*>(peer);
+                st_release_sys(dir == 0 ? &PH->flag_hi[slot] : &PH->flag_lo[slot], seq);
+            }
+            // wait for the neighbour's message; once a wait has timed out the context is in error (the host fails the call at
+            // its next synchronisation point, fct_p2p_check) and later exchanges do not spend another time-out each
             ok = (*reinterpret_cast<volatile unsigned long long*>(&H->error) == 0ull &&
                   wait_flag(dir == 0 ? &H->flag_lo[slot] : &H->flag_hi[slot], seq)) ? 1 : 0;
+        }
         __syncthreads();
         if (ok) {
             const double* src = mail_ptr(mine, dir, slot, max_halo);
             const int h0 = dir == 0 ? 0 : row_end, h1 = dir == 0 ? row_begin : n;
             for (int q = 0; q < nvec; ++q)
-                for (int i = threadIdx.x; i < h1 - h0; i += blockDim.x) vecs[q][h0 + i] = __ldcg(src + (size_t)q * max_halo + i);
+                for (int i = part * FCT_P2P_NT + threadIdx.x; i < h1 - h0; i += FCT_P2P_NB * FCT_P2P_NT)
+                    vecs[q][h0 + i] = __ldcg(src + (size_t)q * max_halo + i);
         } else if (threadIdx.x == 0) {
             H->error = 1ull;
         }
     }
-    // the exchange counter advances once both directions are done: last block to finish bumps it
+    // the exchange counter advances once every block is done: the last one to finish bumps it
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned long long t = atomicAdd(&H->pad[0], 1ull);
-        if ((t & 1ull) == 1ull) H->xseq = seq;
+        const unsigned long long t = atomicAdd(&H->done_cnt, 1ull);
+        if ((t + 1ull) % (2 * FCT_P2P_NB) == 0ull) H->xseq = seq;
     }
 }
 
@@ -114,7 +131,7 @@ __global__ void __launch_bounds__(32)
 k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, unsigned char* p2, unsigned char* p3,
                   unsigned char* p4, unsigned char* p5, unsigned char* p6, unsigned char* p7, int rank, int world,
                   unsigned long long* jstate, double rtol, unsigned long long max_sweeps, int use_handle,
-                  cudaGraphConditionalHandle handle, unsigned long long which) {
+                  cudaGraphConditionalHandle handle, unsigned long long which, int dry_force) {
     unsigned char* peers[FCT_P2P_MAXWORLD] = {p0, p1, p2, p3, p4, p5, p6, p7};
     P2PHeader* H = reinterpret_cast<P2PHeader*>(mine);
     __shared__ unsigned long long m0[32], m1[32];
@@ -160,7 +177,7 @@ k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, uns
             const double xm = __longlong_as_double((long long)b);
             jstate[5] = a;
             jstate[6] = b;
-            if (delta <= rtol * xm) {
+            if (delta <= rtol * xm || (dry_force && jstate[4] >= (unsigned long long)dry_force)) {
                 jstate[3] = 1ull;
                 jstate[12] = which;          // fused tile sweeps: 1 = the converged iterate is in the scratch vector
                 const unsigned long long s = jstate[4], back = jstate[11] ? 2ull : 4ull;
@@ -233,6 +250,15 @@ void fct_p2p_destroy(fct_ctx* ctx) {
     ctx->p2p = nullptr;
 }
 
+// FCT_P2P_DRY (diagnostic, timing only -- results are WRONG): 1 = the exchange / stopping-test kernels are launched but neither
+// push, wait nor unpack; 2 = the exchange kernels are not launched at all.  tools/mgpu_diag.py uses it to split the cost of
+// a multi-GPU step into launch overhead and peer waiting.
+static int p2p_dry() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FCT_P2P_DRY"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 bool fct_p2p_ready(const fct_ctx* ctx) {
     const fct_p2p* p = ctx->p2p;
     if (!p) return false;
@@ -241,7 +267,7 @@ bool fct_p2p_ready(const fct_ctx* ctx) {
     return true;
 }
 
-int fct_p2p_exchange(fct_ctx* ctx, double* v0, double* v1) {
+int fct_p2p_exchange(fct_ctx* ctx, double* v0, double* v1, const unsigned long long* cond) {
     fct_p2p* p = ctx->p2p;
     const int halo_lo = ctx->row_begin, halo_hi = ctx->n - ctx->row_end;
     const int slo = ctx->send_lo[1] - ctx->send_lo[0], shi = ctx->send_hi[1] - ctx->send_hi[0];
@@ -249,9 +275,11 @@ int fct_p2p_exchange(fct_ctx* ctx, double* v0, double* v1) {
               "fct_p2p_exchange: halo larger than the mailbox");
     unsigned char* lo = p->rank > 0 ? p->peer[p->rank - 1] : nullptr;
     unsigned char* hi = p->rank + 1 < p->world ? p->peer[p->rank + 1] : nullptr;
-    k_halo_xchg<<<2, 1024, 0, ctx->stream>>>(p->region, lo, hi, v0, v1, v1 ? 2 : 1, ctx->send_lo[0], ctx->send_lo[1],
+    if (p2p_dry() == 2) return 0;
+    if (p2p_dry() == 1) lo = hi = nullptr;
+    k_halo_xchg<<<2 * FCT_P2P_NB, FCT_P2P_NT, 0, ctx->stream>>>(p->region, lo, hi, v0, v1, v1 ? 2 : 1, ctx->send_lo[0], ctx->send_lo[1],
                                              ctx->send_hi[0], ctx->send_hi[1], ctx->row_begin, ctx->row_end, ctx->n,
-                                             p->max_halo);
+                                             p->max_halo, cond);
     ctx->launches++;
     return 0;
 }
@@ -259,10 +287,12 @@ int fct_p2p_exchange(fct_ctx* ctx, double* v0, double* v1) {
 int fct_p2p_max2_decide(fct_ctx* ctx, double rtol, int max_sweeps, int use_handle, cudaGraphConditionalHandle handle,
                         int which) {
     fct_p2p* p = ctx->p2p;
+    const bool dry = p2p_dry() != 0;
     k_p2p_max2_decide<<<1, 32, 0, ctx->stream>>>(p->region, p->peer[0], p->peer[1], p->peer[2], p->peer[3], p->peer[4],
-                                                 p->peer[5], p->peer[6], p->peer[7], p->rank, p->world, ctx->jstate, rtol,
+                                                 p->peer[5], p->peer[6], p->peer[7], dry ? 0 : p->rank, dry ? 1 : p->world,
+                                                 ctx->jstate, rtol,
                                                  (unsigned long long)max_sweeps, use_handle, handle,
-                                                 (unsigned long long)which);
+                                                 (unsigned long long)which, dry ? 16 : 0);
     ctx->launches++;
     return 0;
 }

@@ -60,7 +60,7 @@ struct fct_tiles {
 };
 
 struct TileArgs {
-    int n_cells, total, g0, nloc, own_rb, own_re, ntiles, K;
+    int n_cells, total, g0, nloc, own_rb, own_re, out_rb, out_re, ntiles, K;
     const int4* tiles;     // {interior origin d0, p0, flags (TL_F_*), template code whose values every row of the tile shares}
     const int32_t* rowptr;
     const uint16_t* code;
@@ -475,13 +475,13 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
         for (int i = 0; i < TL_R; ++i) { fv[i] = fin[xi[i]]; pv[i] = prev[xi[i]]; }
 #pragma unroll
         for (int i = 0; i < TL_R; ++i) {
-            if (row[i] >= 0 && ml[i] >= K && row[i] >= a.own_rb && row[i] < a.own_re) {
+            if (row[i] >= 0 && ml[i] >= K && row[i] >= a.out_rb && row[i] < a.out_re) {
                 const double v = fv[i];
                 a.xout[row[i]] = v;
-                if (MODE == 0) {
+                if (MODE == 0 && row[i] >= a.own_rb && row[i] < a.own_re) {
                     delta = fmax(delta, fabs(v - pv[i]));
                     xa = fmax(xa, fabs(v));
-                } else if (a.yold_out) {
+                } else if (MODE != 0 && a.yold_out) {
                     a.yold_out[row[i]] = yo[i];
                 }
             }
@@ -599,11 +599,22 @@ extern "C" int fct_debug_tile_list(int32_t n_cells, int64_t g0, int32_t row_begi
     return 0;
 }
 
+// Rows a launch of K fused passes writes: with halo depth D > K (multi-GPU) ring D-K -- every row whose K-ring lies inside the
+// local range -- so that a second launch can follow without an exchange; else the owned rows.  The stopping test of the
+// Jacobi sweeps always runs on the owned rows only.
+static inline void tile_out_range(const fct_ctx* ctx, int K, int* rb, int* re) {
+    const int j = ctx->depth > K ? ctx->depth - K : 0;
+    *rb = ctx->ring_lo[j];
+    *re = ctx->ring_hi[j];
+}
+
 static int build_tile_list(fct_ctx* ctx, int K) {
     fct_tiles* t = ctx->tiles;
     if (t->list[K]) return 0;
     std::vector<int4> v;
-    tile_list_host(t->n_cells, (long long)t->g0 + ctx->row_begin, (long long)t->g0 + ctx->row_end, K, v);
+    int orb, ore;
+    tile_out_range(ctx, K, &orb, &ore);
+    tile_list_host(t->n_cells, (long long)t->g0 + orb, (long long)t->g0 + ore, K, v);
     t->count[K] = (int)v.size();
     if (v.empty()) { FCT_CUDA(cudaMalloc((void**)&t->list[K], sizeof(int4))); return 0; }
     FCT_CUDA(cudaMalloc((void**)&t->list[K], sizeof(int4) * v.size()));
@@ -701,6 +712,7 @@ static int fill_args(fct_ctx* ctx, int K, TileArgs& a) {
     FCT_CHECK(t->list[K], "tile list for K=%d was not built", K);
     a.n_cells = t->n_cells; a.total = (t->n_cells + 1) * (t->n_cells + 1); a.g0 = t->g0; a.nloc = ctx->n;
     a.own_rb = ctx->row_begin; a.own_re = ctx->row_end; a.ntiles = t->count[K]; a.tiles = t->list[K]; a.K = K;
+    tile_out_range(ctx, K, &a.out_rb, &a.out_re);
     a.rowptr = ctx->rowptr; a.code = ctx->tpl_code; a.tdelta = t->tdelta; a.tval = ctx->tpl_val; a.tdiag = ctx->tpl_diag;
     a.Lv = nullptr; a.b = nullptr; a.xin = nullptr; a.yold = nullptr; a.xout = nullptr; a.yold_out = nullptr;
     a.jstate = ctx->jstate;
@@ -749,7 +761,7 @@ int fct_tile_jacobi(fct_ctx* ctx, int K, const double* Lv, const double* b, cons
 static_assert(CT_NC == CT_RD * (CT_NT / 32) && CT_NQ == CT_RP * 32, "ChebSI tile geometry");
 
 struct ChebTileArgs {
-    int n_cells, total, g0, nloc, own_rb, own_re, ntiles, K;
+    int n_cells, total, g0, nloc, own_rb, own_re, out_rb, out_re, ntiles, K;
     const int4* tiles;          // {d0, p0, exceptions, template code carrying the nominal values}
     const int* exc_off;         // [ntiles] first exception descriptor of each tile
     const int4* exc;            // {region index, template code, delta bytes 0..3, delta bytes 4..7}
@@ -969,7 +981,7 @@ __global__ void __launch_bounds__(CT_NT, 1) k_cheb_tile(const ChebTileArgs a) {
 #pragma unroll
             for (int m = 0; m < CT_RP; ++m) {
                 const int r = rowb[k] + m;
-                if (((exm[k] >> m) & 1) && min(mld[k], mlp[m]) >= K && r >= a.own_rb && r < a.own_re) {
+                if (((exm[k] >> m) & 1) && min(mld[k], mlp[m]) >= K && r >= a.out_rb && r < a.out_re) {
 #ifndef CT_NOHOIST
                     a.ymid_out[r] = fv[k][m];
 #else
@@ -1121,7 +1133,9 @@ static int cheb_tiles_prepare(fct_ctx* ctx) {
     bool ok = true;
     for (int K = 2; K <= TL_KMAX && ok; ++K) {
         std::vector<int4> v;
-        cheb_tile_list_host(n, (long long)t->g0 + ctx->row_begin, (long long)t->g0 + ctx->row_end, K, v);
+        int orb, ore;
+        tile_out_range(ctx, K, &orb, &ore);
+        cheb_tile_list_host(n, (long long)t->g0 + orb, (long long)t->g0 + ore, K, v);
         c->count[K] = (int)v.size();
         const size_t nt = v.size() ? v.size() : 1;
         ok = ok && cudaMalloc((void**)&c->list[K], sizeof(int4) * nt) == cudaSuccess;
@@ -1165,6 +1179,7 @@ int fct_tile_cheb(fct_ctx* ctx, int K, const double* g, const double* ymid, cons
     ChebTileArgs a;
     a.n_cells = t->n_cells; a.total = (t->n_cells + 1) * (t->n_cells + 1); a.g0 = t->g0; a.nloc = ctx->n;
     a.own_rb = ctx->row_begin; a.own_re = ctx->row_end; a.ntiles = c->count[K]; a.K = K;
+    tile_out_range(ctx, K, &a.out_rb, &a.out_re);
     a.tiles = c->list[K]; a.exc_off = c->exc_off[K]; a.exc = c->exc[K];
     a.tval = ctx->tpl_val; a.tdiag = ctx->tpl_diag;
     a.g = g; a.ymid = ymid; a.yold = yold; a.ymid_out = ymid_out; a.yold_out = yold_out; a.dscale = dscale;

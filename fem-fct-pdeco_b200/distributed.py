@@ -134,11 +134,11 @@ class LocalProblem:
     def make_context(self, device):
         ctx = FctContext(self.rowptr, self.colidx, device=device, row_begin=self.row_begin, row_end=self.row_end)
         ctx.set_mesh(self.cells, self.dof_xy)
-        if self.rect_n:
-            ctx.set_rect(self.rect_n, self.G0)
         if self.world > 1:
             check(lib.fct_ctx_set_rings(ctx.handle, self.depth, self.ring_lo.ctypes.data_as(C.POINTER(C.c_int32)),
                                         self.ring_hi.ctypes.data_as(C.POINTER(C.c_int32))))
+        if self.rect_n:
+            ctx.set_rect(self.rect_n, self.G0)
         return ctx
 
 
@@ -192,9 +192,9 @@ def torch_broadcaster():
 
 def setup_rank(mesh, rank, world, local_rank, depth=None):
     """LocalProblem + context (mesh set, communicator initialised, static matrices assembled) for this rank.
-    depth: halo depth in mesh rings (default 4, FCT_HALO_DEPTH overrides; 1 = exchange after every pass)"""
+    depth: halo depth in mesh rings (default 8, FCT_HALO_DEPTH overrides; 1 = exchange after every pass)"""
     if depth is None:
-        depth = int(os.environ.get("FCT_HALO_DEPTH", "4"))
+        depth = int(os.environ.get("FCT_HALO_DEPTH", "8"))
     lp = LocalProblem(mesh.rowptr, mesh.colidx, mesh.cells, mesh.dof_xy, rank, world, depth=depth if world > 1 else 1,
                       rect_n=getattr(mesh, "n", None))
     ctx = lp.make_context(local_rank)
