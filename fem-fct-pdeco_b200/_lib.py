@@ -93,6 +93,7 @@ SIGNATURES = {
     "fct_p2p_error": [_p, _pi32],
     "fct_launch_count": [_p, _pi64],
     "fct_exchange_count": [_p, _pi64],
+    "fct_guard_check": [_pi64, _pi64],
     "fct_profiler_range": [_i32],
     "fct_bench_jacobi_sweeps": [_p, _p, _p, _f64, _i32, C.POINTER(C.c_float)],
     "fct_debug_jacobi_fixed": [_p, _p, _p, _f64, _i32, _i32, _p],

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["fct_ctx.cu", "fct_kernels.cu", "fct_assembly.cu", "fct_drivers.cu", "fct_comm.cu", "fct_p2p.cu",
-           "fct_templates.cu", "fct_tile.cu"]
+           "fct_templates.cu", "fct_tile.cu", "fct_guard.cu"]
 HEADERS = ["fct_common.cuh", "fct_pipe.cuh", os.path.join("..", "..", "include", "fctpdeco.h")]
 LIB = os.path.join(HERE, "libfctpdeco.so")
 

@@ -3,6 +3,7 @@
 Host logic only (numpy); all arithmetic happens in the CUDA library.
 """
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -43,15 +44,19 @@ class DeviceArray:
         host = np.ascontiguousarray(host, dtype=self.dtype).ravel()
         if host.size != self.size:
             raise ValueError(f"upload: expected {self.size} elements, got {host.size}")
+        t0 = self.ctx._xfer_begin()
         check(lib.fct_h2d(self.ctx.handle, self.ptr, _hp(host), host.nbytes))
         check(lib.fct_ctx_sync(self.ctx.handle))      # the host array may be a temporary
+        self.ctx._xfer_end(t0, host.nbytes, 0)
         return self
 
     def download(self, out=None):
         if out is None:
             out = np.empty(self.size, dtype=self.dtype)
         assert out.flags.c_contiguous and out.size == self.size and out.dtype == self.dtype
+        t0 = self.ctx._xfer_begin()
         check(lib.fct_d2h(self.ctx.handle, _hp(out), self.ptr, out.nbytes))
+        self.ctx._xfer_end(t0, 0, out.nbytes)
         return out
 
     def free(self):
@@ -102,6 +107,29 @@ class FctContext:
 
     def sync(self):
         check(lib.fct_ctx_sync(self.handle))
+
+    # -- host<->device traffic of the numpy-facing API (DeviceArray.upload / download) ------------
+    def _xfer_begin(self):
+        """with accounting on (xfer_reset), a copy is timed on its own: wait for the queued kernels first"""
+        if not getattr(self, "_xfer_on", False):
+            return None
+        check(lib.fct_ctx_sync(self.handle))
+        return time.perf_counter()
+
+    def _xfer_end(self, t0, h2d, d2h):
+        if t0 is None:
+            return
+        x = self._xfer
+        x["seconds"] += time.perf_counter() - t0
+        x["h2d_bytes"] += h2d
+        x["d2h_bytes"] += d2h
+
+    def xfer_reset(self, on=True):
+        """start (or stop) accounting; returns the counters collected so far"""
+        old = getattr(self, "_xfer", None)
+        self._xfer = {"seconds": 0.0, "h2d_bytes": 0, "d2h_bytes": 0}
+        self._xfer_on = bool(on)
+        return old
 
     def set_stream(self, cuda_stream):
         check(lib.fct_ctx_set_stream(self.handle, C.c_void_p(cuda_stream)))

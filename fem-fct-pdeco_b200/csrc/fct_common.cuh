@@ -24,6 +24,17 @@
 
 void fct_set_error(const char* fmt, ...);
 
+// Checked allocator (fct_guard.cu).  With FCT_GUARD=1 in the environment every device buffer of the library gets a 4 KB
+// canary band on both sides and a 0xFF fill (NaN doubles / -1 indices); fct_guard_check counts the buffers whose canaries were
+// overwritten.  compute-sanitizer is not available on the target pool, so this plus the oracle comparisons is how
+// out-of-bounds writes and reads of uninitialised memory are caught.  Off (default): plain cudaMalloc / cudaFree.
+cudaError_t fct_guard_malloc(void** p, size_t bytes);
+cudaError_t fct_guard_free(void* p);
+#ifndef FCT_GUARD_IMPL
+#define cudaMalloc(p, b) fct_guard_malloc((void**)(p), (size_t)(b))
+#define cudaFree(p) fct_guard_free((void*)(p))
+#endif
+
 #define FCT_CUDA(call)                                                                          \
     do {                                                                                        \
         cudaError_t e__ = (call);                                                               \

@@ -940,7 +940,7 @@ __global__ void k_clip_axpy(int64_t len, const double* __restrict__ x, double s,
                             double lo, double hi, double* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride)
-        out[i] = fmin(fmax(x[i] + s * d[i], lo), hi);
+        out[i] = fmin(fmax(__dadd_rn(x[i], __dmul_rn(s, d[i])), lo), hi);      // np.clip(c + s*d): product rounded first
 }
 
 // tpos[k] = position of (j,i) for entry k = (i,j): binary search in row j

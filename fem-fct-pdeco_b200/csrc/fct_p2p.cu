@@ -10,6 +10,7 @@
 // Progress: a push never waits; a wait only depends on the neighbour's push of the same sequence number, which that
 // rank issues before its own wait.  A rank can run at most one exchange ahead of a neighbour, so FCT_P2P_SLOTS = 4
 // mailbox slots cannot be lapped.  Waits time out (~2 s) into an error flag instead of hanging the GPU.
+#define FCT_GUARD_IMPL      // the IPC region must be a plain allocation (cudaIpcGetMemHandle wants its base address)
 #include "fct_common.cuh"
 #include "../../include/fctpdeco.h"
 

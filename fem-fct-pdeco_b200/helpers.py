@@ -75,7 +75,30 @@ def _ensure_mass(ent, M, M_lumped=None):
     return ctx
 
 
+# The norm / ChebSI shims are called with the same mass-matrix OBJECT over and over (a lil_matrix in the reference's scripts:
+# converting, hashing and uploading it costs far more than the kernel).  Keep the embedded device copy of the last few objects,
+# keyed by identity; a different object, or one whose nnz changed, is embedded afresh.
+_MASS_ON_DEVICE = {}
+
+
+def _mass_on_device(M):
+    rec = _MASS_ON_DEVICE.get(id(M))
+    if rec is not None and rec[0] is M and rec[1] == M.nnz:
+        return rec[2], rec[3]
+    ent = context_for(M)
+    ctx = ent["ctx"]
+    d_M = ctx.array(ctx.embed(M))
+    if len(_MASS_ON_DEVICE) >= 4:
+        _, _, _, old = _MASS_ON_DEVICE.pop(next(iter(_MASS_ON_DEVICE)))
+        old.free()
+    _MASS_ON_DEVICE[id(M)] = (M, M.nnz, ctx, d_M)
+    return ctx, d_M
+
+
 def clear_contexts():
+    for rec in _MASS_ON_DEVICE.values():
+        rec[3].free()
+    _MASS_ON_DEVICE.clear()
     for ent in _CONTEXTS.values():
         ent["ctx"].close()
     _CONTEXTS.clear()
@@ -159,15 +182,13 @@ def artificial_diffusion_mat(mat):
 
 def ChebSI(vec, M, Md, cheb_iter=20, lmin=0.5, lmax=2):
     """helpers.py:143-185: exactly `cheb_iter` Chebyshev semi-iterations for M x = vec."""
-    ent = context_for(M)
-    ctx = ent["ctx"]
-    d_M = ctx.array(ctx.embed(M))
+    ctx, d_M = _mass_on_device(M)
     d_Md = ctx.array(np.asarray(Md, dtype=np.float64).ravel())
     d_b = ctx.array(np.asarray(vec, dtype=np.float64).ravel())
     d_y = ctx.empty(ctx.n)
     ctx.chebsi(d_M, d_Md, d_b, d_y, cheb_iter, lmin, lmax)
     out = d_y.download()
-    for a in (d_M, d_Md, d_b, d_y):
+    for a in (d_Md, d_b, d_y):
         a.free()
     return out
 
@@ -223,26 +244,22 @@ def FCT_alg(A, rhs, u_n, dt, nodes, M, M_lumped, dof_neighbors, source_mat=None)
 # --------------------------------------------------------------------------------------------------
 def L2_norm_sq_Q(phi, num_steps, dt, M):
     """helpers.py:330-360."""
-    ent = context_for(M)
-    ctx = ent["ctx"]
+    ctx, d_M = _mass_on_device(M)
     phi = np.asarray(phi, dtype=np.float64).ravel()
     if phi.size != (num_steps + 1) * ctx.n:
         raise ValueError("array split does not result in an equal division")     # np.split's error in the reference
-    d_M = ctx.array(ctx.embed(M))
     d_phi = ctx.array(phi)
     val = ctx.norm_sq_Q(d_M, d_phi, num_steps, dt)
-    d_M.free(); d_phi.free()
+    d_phi.free()
     return val
 
 
 def L2_norm_sq_Omega(phi, M):
     """helpers.py:362-381."""
-    ent = context_for(M)
-    ctx = ent["ctx"]
-    d_M = ctx.array(ctx.embed(M))
+    ctx, d_M = _mass_on_device(M)
     d_phi = ctx.array(np.asarray(phi, dtype=np.float64).ravel())
     val = ctx.dot_M(d_M, d_phi, d_phi)
-    d_M.free(); d_phi.free()
+    d_phi.free()
     return val
 
 

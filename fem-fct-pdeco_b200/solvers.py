@@ -80,15 +80,33 @@ def chtxs_sys_IC(a1, a2, deltax, nodes, vertex_to_dof):
 
 # ---- device-side helpers ------------------------------------------------------------------------------
 class _Dev:
-    """context + scratch buffers of a function space"""
+    """context + scratch buffers of a function space (one instance per context: buffers are reused between calls)"""
 
-    def __init__(self, V, nodes):
-        self.ctx = V.mesh().context()
-        if self.ctx.n != nodes:
-            raise ValueError(f"nodes={nodes} does not match the function space ({self.ctx.n})")
-        self.M, self.ML, self.Md, self.K = self.ctx.static()
-        self._vec = {}
-        self._mat = {}
+    def __new__(cls, V, nodes):
+        ctx = V.mesh().context()
+        if ctx.n != nodes:
+            raise ValueError(f"nodes={nodes} does not match the function space ({ctx.n})")
+        self = getattr(ctx, "_solver_dev", None)
+        if self is None:
+            self = object.__new__(cls)
+            self.ctx = ctx
+            self.M, self.ML, self.Md, self.K = ctx.static()
+            self._vec, self._mat, self._traj = {}, {}, {}
+            ctx._solver_dev = self
+        return self
+
+    def traj(self, name, num_steps):
+        """device trajectory of (num_steps + 1) time levels; slice(i) views one level"""
+        size = (num_steps + 1) * self.ctx.n
+        t = self._traj.get(name)
+        if t is None or t.size != size:
+            if t is not None:
+                t.free()
+            t = self._traj[name] = self.ctx.empty(size)
+        return t
+
+    def level(self, traj, i):
+        return traj.slice(i * self.ctx.n, self.ctx.n)
 
     def vec(self, name):
         if name not in self._vec:
@@ -136,10 +154,22 @@ def _solve(ctx, kind, mat, b, x, what):
 # ---- Schnakenberg ---------------------------------------------------------------------------------------
 def solve_schnak_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighbors, control_fun=None, rescaling=1):
     """helpers.py:511-597"""
-    Du, Dv, _, c_b, gamma, omega1, omega2, wind = get_schnak_sys_params()
-    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    dev = _Dev(V, nodes)
     var1[nodes:] = np.zeros(num_steps * nodes)
     var2[nodes:] = np.zeros(num_steps * nodes)
+    d1, d2 = dev.traj("var1", num_steps), dev.traj("var2", num_steps)
+    dev.level(d1, 0).upload(var1[:nodes]); dev.level(d2, 0).upload(var2[:nodes])
+    cfun = _control_slice(dev, control, control_fun, nodes, 2 * nodes) if num_steps >= 1 else None
+    _forward_schnak_dev(dev, cfun, d1, d2, num_steps, dt, rescaling)
+    if num_steps >= 1:
+        d1.slice(nodes, num_steps * nodes).download(var1[nodes:]); d2.slice(nodes, num_steps * nodes).download(var2[nodes:])
+    return var1, var2
+
+
+def _forward_schnak_dev(dev, cfun, d1, d2, num_steps, dt, rescaling=1):
+    """the loop of helpers.py:560-597 on device trajectories (level 0 = initial condition); cfun: number or device vector"""
+    Du, Dv, _, c_b, gamma, omega1, omega2, wind = get_schnak_sys_params()
+    ctx, L = dev.ctx, _lib
     dwind = ctx.array(wind)
     A = dev.mat("A"); ctx.assemble_matrix(L.FORM_WIND_POLY3, A, c0=dwind)
     Mat1 = dev.mat("Mat1"); ctx.vals_axpby(Du, dev.K, -omega1, A, Mat1)          # Du*Ad - omega1*A
@@ -147,20 +177,14 @@ def solve_schnak_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighb
     base2 = dev.mat("base2"); ctx.vals_axpby(dt * Dv, dev.K, -dt * omega2, A, base2)
     ctx.vals_axpby(1.0, base2, 1.0, dev.M, base2)                                  # M + dt(Dv Ad - omega2 A)
     Mat2, Mu2 = dev.mat("Mat2"), dev.mat("Mu2")
-    un, vn = ctx.array(var1[:nodes]), ctx.array(var2[:nodes])
-    u1, v1 = dev.vec("u1"), dev.vec("v1")
     rhs1, rhs2 = dev.vec("rhs1"), dev.vec("rhs2")
-    cfun = None
     print("Solving the system of advective Schnakenberg state equations...")
     for i in range(1, num_steps + 1):
-        start, end = i * nodes, (i + 1) * nodes
-        if cfun is None:
-            cfun = _control_slice(dev, control, control_fun, start, end)
+        un, vn, u1, v1 = dev.level(d1, i - 1), dev.level(d2, i - 1), dev.level(d1, i), dev.level(d2, i)
         # rhs_var1 = assemble((gamma/r*c + gamma*u_n^2 v_n) v dx)
         dev.load_control(rhs1, cfun, scale=gamma / rescaling)
         ctx.assemble_vector(L.LOAD_P1_3, rhs1, c0=un, c1=un, c2=vn, scale=gamma, accumulate=True)
-        info = ctx.step(Mat1, un, dt, u1, S=S, rhs=rhs1)
-        _check(info)
+        _check(ctx.step(Mat1, un, dt, u1, S=S, rhs=rhs1))
         # Mat_var2 = M + dt(Dv Ad - omega2 A + gamma M_u2), M_u2 from u_{n+1}
         ctx.assemble_matrix(L.FORM_WMASS2, Mu2, c0=u1, c1=u1)
         ctx.vals_axpby(1.0, base2, dt * gamma, Mu2, Mat2)
@@ -168,10 +192,6 @@ def solve_schnak_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighb
         ctx.assemble_vector(L.LOAD_CONST, rhs2, s0=gamma * c_b, scale=dt, accumulate=True)
         ctx.axpby(1.0, vn, 0.0, None, v1)                                          # initial guess
         _solve(ctx, L.SOLVER_BICGSTAB, Mat2, rhs2, v1, "var2")
-        u1.download(var1[start:end]); v1.download(var2[start:end])
-        un, u1 = u1, un
-        vn, v1 = v1, vn
-    return var1, var2
 
 
 def solve_adjoint_schnak_system(uk, vk, uhat_T, vhat_T, pk, qk, T, V, nodes, num_steps, dt, dof_neighbors):
@@ -217,26 +237,32 @@ def solve_nonlinear_equation(control, var1, var2, V, nodes, num_steps, dt, dof_n
     """helpers.py:881-966"""
     if var2 is not None:
         warnings.warn("Warning: 'var2' is not None. Ensure this is intentional.")
-    eps, _, wind = get_nonlinear_eqns_params()
-    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    dev = _Dev(V, nodes)
     var1[nodes:] = np.zeros(num_steps * nodes)
+    d1 = dev.traj("var1", num_steps)
+    dev.level(d1, 0).upload(var1[:nodes])
+    cfun = _control_slice(dev, control, control_fun, nodes, 2 * nodes) if num_steps >= 1 else None
+    _forward_nonlinear_dev(dev, cfun, d1, None, num_steps, dt)
+    if num_steps >= 1:
+        d1.slice(nodes, num_steps * nodes).download(var1[nodes:])
+    return var1, None
+
+
+def _forward_nonlinear_dev(dev, cfun, d1, d2, num_steps, dt, rescaling=None):
+    """the loop of helpers.py:935-966 on a device trajectory (level 0 = initial condition)"""
+    eps, _, wind = get_nonlinear_eqns_params()
+    ctx, L = dev.ctx, _lib
     A = dev.mat("A"); ctx.assemble_matrix(L.FORM_WIND_POLY3, A, c0=ctx.array(wind))
     Mat1 = dev.mat("Mat1"); ctx.vals_axpby(-1.0, A, eps, dev.K, Mat1)             # -(A - eps Ad)
-    S = dev.mat("S")
-    un, u1, rhs = ctx.array(var1[:nodes]), dev.vec("u1"), dev.vec("rhs1")
-    cfun = None
+    S, rhs = dev.mat("S"), dev.vec("rhs1")
     print("\nSolving nonlinear state equation...")
+    if num_steps >= 1:
+        dev.load_control(rhs, cfun)                                                # var1_rhs = assemble(c v dx)
     for i in range(1, num_steps + 1):
-        start, end = i * nodes, (i + 1) * nodes
-        if cfun is None:
-            cfun = _control_slice(dev, control, control_fun, start, end)
-            dev.load_control(rhs, cfun)                                            # var1_rhs = assemble(c v dx)
+        un, u1 = dev.level(d1, i - 1), dev.level(d1, i)
         ctx.assemble_matrix(L.FORM_WMASS2, S, c0=un, c1=un, scale=1 / 3)           # -M + M_u2/3
         ctx.vals_axpby(1.0, S, -1.0, dev.M, S)
         _check(ctx.step(Mat1, un, dt, u1, S=S, rhs=rhs))
-        u1.download(var1[start:end])
-        un, u1 = u1, un
-    return var1, None
 
 
 def solve_adjoint_nonlinear_equation(uk, uhat_T, pk, T, V, nodes, num_steps, dt, dof_neighbors):
@@ -264,24 +290,45 @@ def solve_adjoint_nonlinear_equation(uk, uhat_T, pk, T, V, nodes, num_steps, dt,
 def solve_chtxs_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighbors, control_fun=None,
                        show_plots=False, vertex_to_dof=None, generation_mode=False, output_dir=None, rescaling=1 / 10):
     """helpers.py:1250-1385"""
+    dev = _Dev(V, nodes); ctx = dev.ctx
+    if generation_mode:
+        if len(var1) != nodes or len(var2) != nodes or len(control) != nodes:
+            raise ValueError(f"Generation mode, the input vectors should be of length {nodes}")
+        # no trajectory is kept: two time levels ping-pong (helpers.py:1318-1323)
+        d1, d2 = dev.traj("gen1", 1), dev.traj("gen2", 1)
+        dev.level(d1, 0).upload(var1); dev.level(d2, 0).upload(var2)
+        cfun = _control_slice(dev, control, control_fun, 0, nodes) if num_steps >= 1 else None
+
+        def dump(i, u1, v1):
+            if output_dir is not None and i % 100 == 0:
+                t = i * dt
+                u1.download().tofile(output_dir / f"chtxs_m_t{round(t, 2)}.csv", sep=",")
+                v1.download().tofile(output_dir / f"chtxs_f_t{round(t, 2)}.csv", sep=",")
+        _forward_chtxs_dev(dev, cfun, d1, d2, num_steps, dt, rescaling, pingpong=True, after_step=dump)
+        last = num_steps % 2
+        var1[:] = dev.level(d1, last).download(); var2[:] = dev.level(d2, last).download()
+        return var1, var2
+    var1[nodes:] = np.zeros(num_steps * nodes)
+    var2[nodes:] = np.zeros(num_steps * nodes)
+    d1, d2 = dev.traj("var1", num_steps), dev.traj("var2", num_steps)
+    dev.level(d1, 0).upload(var1[:nodes]); dev.level(d2, 0).upload(var2[:nodes])
+    cfun = _control_slice(dev, control, control_fun, nodes, 2 * nodes) if num_steps >= 1 else None
+    _forward_chtxs_dev(dev, cfun, d1, d2, num_steps, dt, rescaling)
+    if num_steps >= 1:
+        d1.slice(nodes, num_steps * nodes).download(var1[nodes:]); d2.slice(nodes, num_steps * nodes).download(var2[nodes:])
+    return var1, var2
+
+
+def _forward_chtxs_dev(dev, cfun, d1, d2, num_steps, dt, rescaling=1 / 10, pingpong=False, after_step=None):
+    """the loop of helpers.py:1318-1385 on device trajectories (level 0 = initial condition; pingpong: two levels only)"""
     delta, Dm, Df, chi, _, eta = get_chtxs_sys_params()
-    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
-    if not generation_mode:
-        var1[nodes:] = np.zeros(num_steps * nodes)
-        var2[nodes:] = np.zeros(num_steps * nodes)
-    elif len(var1) != nodes or len(var2) != nodes or len(control) != nodes:
-        raise ValueError(f"Generation mode, the input vectors should be of length {nodes}")
+    ctx, L = dev.ctx, _lib
     Mat2 = dev.mat("Mat2"); ctx.vals_axpby(1.0 + dt * delta, dev.M, dt * Df, dev.K, Mat2)   # M + dt(Df Ad + delta M)
-    A = dev.mat("A")
-    un, vn = ctx.array(var1[:nodes]), ctx.array(var2[:nodes])
-    u1, v1, rhs = dev.vec("u1"), dev.vec("v1"), dev.vec("rhs1")
-    cfun = None
+    A, rhs = dev.mat("A"), dev.vec("rhs1")
     print("Solving the system of chemotaxis state equations...")
     for i in range(1, num_steps + 1):
-        start, end = i * nodes, (i + 1) * nodes
-        if cfun is None:
-            cfun = _control_slice(dev, control, control_fun, 0 if generation_mode else start,
-                                  nodes if generation_mode else end)
+        a, b = ((i - 1) % 2, i % 2) if pingpong else (i - 1, i)
+        un, vn, u1, v1 = dev.level(d1, a), dev.level(d2, a), dev.level(d1, b), dev.level(d2, b)
         # var2_rhs = assemble(v_n w dx + dt * c * u_n / r * w dx)
         ctx.assemble_vector(L.LOAD_P1_1, rhs, c0=vn)
         dev.load_control(rhs, cfun, other=un, scale=dt / rescaling, accumulate=True)
@@ -291,17 +338,8 @@ def solve_chtxs_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighbo
         ctx.assemble_matrix(L.FORM_CHTX_EXP, A, c0=v1, c1=un, s0=eta, scale=-chi)
         ctx.vals_axpby(1.0, A, Dm, dev.K, A)
         _check(ctx.step(A, un, dt, u1))
-        if not generation_mode:
-            u1.download(var1[start:end]); v1.download(var2[start:end])
-        elif output_dir is not None and i % 100 == 0:
-            t = i * dt
-            u1.download().tofile(output_dir / f"chtxs_m_t{round(t, 2)}.csv", sep=",")
-            v1.download().tofile(output_dir / f"chtxs_f_t{round(t, 2)}.csv", sep=",")
-        un, u1 = u1, un
-        vn, v1 = v1, vn
-    if generation_mode:
-        var1[:] = un.download(); var2[:] = vn.download()
-    return var1, var2
+        if after_step is not None:
+            after_step(i, u1, v1)
 
 
 def solve_adjoint_chtxs_system(uk, vk, uhat, vhat, pk, qk, control, T, V, nodes, num_steps, dt, dof_neighbors, optim,
@@ -365,6 +403,10 @@ def armijo_line_search_ref(var1, c, d, var1_target, num_steps, dt, c_lower, c_up
     valid_options = ["alltime", "finaltime"]
     if optim not in valid_options:
         raise ValueError(f"Invalid value for 'optim': '{optim}'. Must be one of {valid_options}.")
+    fwd = _DEVICE_FORWARD.get(nonlinear_solver) if w1 is None else None
+    if fwd is not None:
+        return _armijo_ref_device(fwd, var1, c, d, var1_target, num_steps, dt, c_lower, c_upper, beta, costfun_init, nodes,
+                                  optim, V, gam, max_iter, s0, var2, var2_target)
     ctx = V.mesh().context()
     M = ctx.to_scipy(ctx.static()[0].download())
     s = s0
@@ -396,6 +438,100 @@ def armijo_line_search_ref(var1, c, d, var1_target, num_steps, dt, c_lower, c_up
     if armijo > -gam / s * control_dif_L2:
         print(f"Stopped: Maximum number of iterations reached ({max_iter}) .")
     return (var1, var2, c_inc, k + 1) if var2 is not None else (var1, c_inc, k + 1)
+
+
+# the reference-named solvers whose loop also exists on device trajectories: the line search then keeps everything on the GPU
+_DEVICE_FORWARD = {solve_nonlinear_equation: _forward_nonlinear_dev, solve_schnak_system: _forward_schnak_dev,
+                   solve_chtxs_system: _forward_chtxs_dev}
+
+
+def _cost_device(dev, d1, d_t1, d_cinc, num_steps, dt, beta, optim, d2=None, d_t2=None):
+    """cost_functional (helpers.py:383-441) on device trajectories: the same kernels and summation order as the numpy-facing
+    shim, without the uploads"""
+    ctx, n = dev.ctx, dev.ctx.n
+    if optim == "alltime":
+        print("Calculating L^2(Q)-norm...")
+        func = 0.5 * ctx.norm_sq_Q(dev.M, d1, num_steps, dt, target=d_t1)
+        if d2 is not None and d_t2 is not None:
+            func += 0.5 * ctx.norm_sq_Q(dev.M, d2, num_steps, dt, target=d_t2)
+    else:
+        print("Calculating L^2(\\Omega)-norm...")
+        dif = dev.vec("dif")
+        ctx.axpby(1.0, dev.level(d1, num_steps), -1.0, d_t1, dif)
+        func = 0.5 * ctx.dot_M(dev.M, dif, dif)
+        if d2 is not None and d_t2 is not None:
+            ctx.axpby(1.0, dev.level(d2, num_steps), -1.0, d_t2, dif)
+            func += 0.5 * ctx.dot_M(dev.M, dif, dif)
+    func += beta / 2 * ctx.norm_sq_Q(dev.M, d_cinc, num_steps, dt)
+    return func
+
+
+def _armijo_ref_device(fwd, var1, c, d, var1_target, num_steps, dt, c_lower, c_upper, beta, costfun_init, nodes, optim, V,
+                       gam, max_iter, s0, var2, var2_target):
+    """armijo_line_search_ref for the solvers of this module: control, direction and targets go to the GPU once, every trial
+    (projection, state solve, cost, ||c_inc - c||) runs on device trajectories and moves scalars only, the accepted state and
+    control come back once.  The share of the host<->device copies is printed."""
+    import time
+    dev = _Dev(V, nodes); ctx = dev.ctx
+    t_start = time.perf_counter()
+    ctx.xfer_reset(True)
+    size = (num_steps + 1) * nodes
+    d_c, d_d, d_cinc, d_dif = (dev.traj(k, num_steps) for k in ("arm_c", "arm_d", "arm_cinc", "arm_dif"))
+    d_c.upload(c); d_d.upload(d)
+    d1 = dev.traj("var1", num_steps)
+    dev.level(d1, 0).upload(var1[:nodes])
+    d2 = d_t2 = None
+    if var2 is not None:
+        d2 = dev.traj("var2", num_steps)
+        dev.level(d2, 0).upload(var2[:nodes])
+    if optim == "alltime":
+        d_t1 = dev.traj("arm_t1", num_steps).upload(var1_target)
+        if var2 is not None and var2_target is not None:
+            d_t2 = dev.traj("arm_t2", num_steps).upload(var2_target)
+    else:
+        d_t1 = dev.vec("arm_t1").upload(var1_target)
+        if var2 is not None and var2_target is not None:
+            d_t2 = dev.vec("arm_t2").upload(var2_target)
+    s = s0
+    control_dif_L2 = 1
+    armijo = float("inf")
+    k = 0
+    for k in range(max_iter):
+        print(f"{k=}")
+        ctx.clip_axpy(d_c, s, d_d, c_lower, c_upper, d_cinc)                       # c_inc = clip(c + s d)
+        cfun = dev.level(d_cinc, 1) if num_steps >= 1 else None                    # App. D-1: the first step's slice, reused
+        fwd(dev, cfun, d1, d2, num_steps, dt)
+        cost2 = _cost_device(dev, d1, d_t1, d_cinc, num_steps, dt, beta, optim, d2, d_t2)
+        armijo = cost2 - costfun_init
+        ctx.axpby(1.0, d_cinc, -1.0, d_c, d_dif, length=size)
+        control_dif_L2 = ctx.norm_sq_Q(dev.M, d_dif, num_steps, dt)
+        print(f"Updated cost={cost2}, Orig. cost={costfun_init}")
+        print(f"Cost difference={armijo}")
+        print(f"Threshold value: {-gam/s*control_dif_L2=}")
+        if armijo <= -gam / s * control_dif_L2:
+            print(f"Converged in {k+1} iterations: Armijo condition satisfied.")
+            break
+        s /= 2
+    if armijo > -gam / s * control_dif_L2:
+        print(f"Stopped: Maximum number of iterations reached ({max_iter}) .")
+    c_inc = d_cinc.download()
+    if num_steps >= 1:
+        var1[nodes:] = 0.0
+        d1.slice(nodes, num_steps * nodes).download(var1[nodes:])
+        if var2 is not None:
+            var2[nodes:] = 0.0
+            d2.slice(nodes, num_steps * nodes).download(var2[nodes:])
+    ctx.sync()
+    x = ctx.xfer_reset(False)
+    total = time.perf_counter() - t_start
+    print(f"H2D/D2H: {x['seconds']:.4f} s of {total:.4f} s ({100 * x['seconds'] / total:.1f} %), "
+          f"{x['h2d_bytes'] / 1e6:.1f} MB in (control, direction, targets, initial state), {x['d2h_bytes'] / 1e6:.1f} MB out "
+          f"(accepted state, control); {k + 1} trial(s) moved scalars only")
+    _LAST_ARMIJO_XFER.update(x, total_seconds=total, trials=k + 1)
+    return (var1, var2, c_inc, k + 1) if var2 is not None else (var1, c_inc, k + 1)
+
+
+_LAST_ARMIJO_XFER = {}
 
 
 # ---- legacy drift-control line search (config 2 / 5) ------------------------------------------------------------

@@ -268,6 +268,10 @@ int fct_launch_count(fct_ctx* ctx, int64_t* count);
 /* number of halo exchanges executed on this context since creation (multi-GPU; exchanges inside CUDA-graph bodies included
  * on the peer-memory path) */
 int fct_exchange_count(fct_ctx* ctx, int64_t* count);
+/* Checked allocator (FCT_GUARD=1 in the environment: canary bands around, and a 0xFF fill of, every device buffer of the
+ * library).  *corrupted = buffers, live now or freed since the last call, whose canaries were overwritten; *live = buffers
+ * checked.  Both 0 when the mode is off.  The test suite asserts corrupted == 0 after every GPU test. */
+int fct_guard_check(int64_t* corrupted, int64_t* live);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""share of host<->device copies in armijo_line_search_ref on a 1025^2-DoF mesh (nonlinear advection-reaction
+system, num_steps time levels).  Prints the line armijo_line_search_ref itself prints plus a JSON summary.
+    python tools/armijo_profile.py [cells] [num_steps]"""
+import io
+import json
+import os
+import sys
+import time
+from contextlib import redirect_stdout
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fem_fct_pdeco_b200 import helpers as hp  # noqa: E402
+from fem_fct_pdeco_b200 import solvers  # noqa: E402
+from fem_fct_pdeco_b200.mesh import FunctionSpaceP1, RectMeshP1  # noqa: E402
+
+
+def main():
+    cells = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    ns = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    mesh = RectMeshP1(cells, 0.0, 1.0)
+    V = FunctionSpaceP1(mesh)
+    nodes = V.dim()
+    dt = 0.1 / cells
+    xy = mesh.dof_xy
+    L = (ns + 1) * nodes
+    var1 = np.zeros(L)
+    var1[:nodes] = 0.5 + 0.4 * np.sin(2 * np.pi * xy[:, 0]) * np.sin(2 * np.pi * xy[:, 1])
+    c = np.tile(0.2 + 0.1 * np.cos(np.pi * xy[:, 0]), ns + 1)
+    d = np.tile(0.05 * np.sin(np.pi * xy[:, 1]), ns + 1)
+    target = 0.5 * np.ones(nodes)
+    ctx = mesh.context()
+    M = ctx.to_scipy(ctx.static()[0].download())
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        v1, _ = hp.solve_nonlinear_equation(c, var1, None, V, nodes, ns, dt, None)
+        J0 = hp.cost_functional(v1, target, c, ns, dt, M, 0.01, optim="finaltime")
+    out = {}
+    for rep in range(2):                     # second call: buffers and graphs exist
+        buf = io.StringIO()
+        t0 = time.perf_counter()
+        with redirect_stdout(buf):
+            res = hp.armijo_line_search_ref(var1.copy(), c, d, target, ns, dt, 0.0, 1.0, 0.01, J0 * 10, nodes, "finaltime", V,
+                                            nonlinear_solver=hp.solve_nonlinear_equation, dof_neighbors=None)
+        wall = time.perf_counter() - t0
+        line = [ln for ln in buf.getvalue().splitlines() if ln.startswith("H2D/D2H")]
+        print(line[-1] if line else "(no transfer line)")
+        out = dict(solvers._LAST_ARMIJO_XFER, wall_seconds=wall, cells=cells, num_steps=ns, nodes=nodes, trials=res[-1])
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
