@@ -116,7 +116,7 @@ FORM_MASS, FORM_STIFFNESS, FORM_DRIFT, FORM_WIND_P1, FORM_WIND_P1_T = 0, 1, 2, 3
 FORM_WMASS1, FORM_WMASS2, FORM_WMASS3, FORM_CHTX, FORM_CHTX_EXP, FORM_CHTX_ADJ = 5, 6, 7, 8, 9, 10
 FORM_WIND_POLY3, FORM_WIND_POLY3_T, FORM_DRIFT_MASS, FORM_DRIFT_CONV, FORM_DIVW_MASS = 11, 12, 13, 14, 15
 LOAD_P1_1, LOAD_P1_2, LOAD_P1_3, LOAD_P1_4, LOAD_CONST, LOAD_DRIFT_GRAD, LOAD_CHTX_ADJ, LOAD_POLY3 = 0, 1, 2, 3, 4, 5, 6, 7
-SOLVER_JACOBI, SOLVER_PCG, SOLVER_BICGSTAB = 0, 1, 2
+SOLVER_JACOBI, SOLVER_PCG, SOLVER_BICGSTAB, SOLVER_CHEB_PCG = 0, 1, 2, 3
 
 
 def check(rc):

@@ -390,6 +390,25 @@ __global__ void k_pcg_rotate(double* __restrict__ sc) {
     sc[S_RZ] = sc[S_RZN];
 }
 
+// Gershgorin bound of the Jacobi-scaled matrix, max_i sum_j |a_ij| / a_ii (>= lambda_max(D^-1 A)), as the bit pattern of a
+// nonnegative double (atomicMax on the pattern is exact); diag_i = a_ii on the way
+__global__ void k_gershgorin(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ Av,
+                             double* __restrict__ diag, unsigned long long* __restrict__ bound_bits, int row_begin, int row_end) {
+    const int r = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (r < row_end) {
+        double s = 0.0, dg = 1.0;
+        for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+            s += fabs(Av[k]);
+            if (colidx[k] == r) dg = Av[k];
+        }
+        diag[r] = dg;
+        v = s / fabs(dg);
+    }
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(bound_bits, (unsigned long long)__double_as_longlong(v));
+}
+
 static size_t smem11(const fct_ctx* c) { return (size_t)c->cap * 12; }
 
 int fct_drivers_configure(fct_ctx* ctx) {
@@ -507,7 +526,13 @@ int fct_solve_ws(fct_ctx* ctx, int32_t kind, const double* mat, const double* b,
                   info.x_norm > 0 ? info.last_delta / info.x_norm : info.last_delta);
         return 0;
     }
-    FCT_CHECK(kind == 1 || kind == 2, "fct_solve: unknown solver kind %d", kind);
+    FCT_CHECK(kind == 1 || kind == 2 || kind == 3, "fct_solve: unknown solver kind %d", kind);
+    if (kind == 3 && ws == ctx->w) {
+        // the Chebyshev preconditioner (fct_chebsi_v) rotates through ctx->w[0..2]: the Krylov vectors move to the private set
+        for (int i = 0; i < 12; ++i)
+            if (!ctx->fb_w[i]) FCT_CUDA(cudaMalloc((void**)&ctx->fb_w[i], sizeof(double) * ((size_t)ctx->n + 8)));
+        ws = ctx->fb_w;
+    }
     double* r = ws[0];
     double* z = ws[1];
     double* p = ws[2];
@@ -525,7 +550,51 @@ int fct_solve_ws(fct_ctx* ctx, int32_t kind, const double* mat, const double* b,
     double h[16];
     int it = 0;
     const int batch = 8;
-    if (kind == 1) {
+    if (kind == 3) {
+        // CG preconditioned with the degree-m Chebyshev polynomial of the Jacobi-scaled matrix: z = p_m(D^-1 A) D^-1 r, i.e. m
+        // steps of the Chebyshev semi-iteration (the recurrence of helpers.py:164-180) for A z = r from z = 0, on the interval
+        // [lmax / m^2, lmax] with lmax the Gershgorin bound.  The polynomial is positive on (0, lmax], so the preconditioner is
+        // SPD whatever the true lambda_min is.  One outer iteration costs m + 1 matrix passes but only 2 reductions: the outer
+        // count drops ~m-fold, which is what matters once the passes are short and the reductions are latency.
+        int m = 8;
+        if (const char* e = getenv("FCT_CHEB_PCG_DEGREE")) { const int v = atoi(e); if (v >= 2 && v <= 32) m = v; }
+        double* diag = ws[9];
+        unsigned long long* bits = reinterpret_cast<unsigned long long*>(sc + 14);
+        k_gershgorin<<<nb, FCT_RB, 0, ctx->stream>>>(ctx->rowptr, ctx->colidx, mat, diag, bits, ctx->row_begin, ctx->row_end);
+        ctx->launches++;
+        double lmax = 0.0;
+        FCT_CUDA(cudaMemcpyAsync(&lmax, sc + 14, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+        FCT_CHECK(lmax > 0.0 && isfinite(lmax), "fct_solve(Chebyshev-PCG): bad Gershgorin bound %g", lmax);
+        const double lmin = lmax / ((double)m * m);
+        auto precondition = [&](int dst) -> int {       // z = Cheb_m(r); sc[dst] = r . z
+            if (fct_chebsi_v(ctx, mat, diag, r, z, m, lmin, lmax, 0, nullptr)) return 1;
+            k_dot2<<<nb, FCT_RB, 0, ctx->stream>>>(r, z, nullptr, nullptr, pa, nullptr, sc, ctx->row_begin, ctx->row_end);
+            ctx->launches++;
+            return reduce_to(ctx, pa, dst, nullptr, 0, nullptr, 0, 0, rtol);
+        };
+        if (precondition(S_RZ)) return 1;
+        while (it < maxit) {
+            for (int j = 0; j < batch && it < maxit; ++j, ++it) {
+                double* pold = (it & 1) ? ws[8] : p;
+                double* pnew = (it & 1) ? p : ws[8];
+                k_pcg_spmv<<<nb, FCT_RB, smem11(ctx), ctx->stream>>>(ctx->rowptr, ctx->colidx, mat, z, pold, pnew, q, sc,
+                                                                     it == 0, pa, ctx->row_begin, ctx->row_end, ctx->nnz,
+                                                                     ctx->cap);
+                ctx->launches++;
+                if (it > 0) { k_pcg_rotate<<<1, 1, 0, ctx->stream>>>(sc); ctx->launches++; }
+                if (reduce_to(ctx, pa, S_PAP, nullptr, 0, nullptr, 0, 0, rtol)) return 1;
+                // x, r update (its Jacobi z and r.z are overwritten by the polynomial below), ||r||, convergence test
+                k_pcg_update<<<nb, FCT_RB, 0, ctx->stream>>>(dinv, pnew, q, x, r, z, sc, pb, pc, ctx->row_begin, ctx->row_end);
+                ctx->launches++;
+                if (reduce_to(ctx, pb, S_RZN, pc, S_RR, nullptr, 0, 1, rtol)) return 1;
+                if (precondition(S_RZN)) return 1;
+            }
+            FCT_CUDA(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            FCT_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (h[S_DONE] != 0.0) break;
+        }
+    } else if (kind == 1) {
         while (it < maxit) {
             for (int j = 0; j < batch && it < maxit; ++j, ++it) {
                 // p (w[2]) is read at the neighbours while p_new is written: ping-pong between w[2] and w[8]
@@ -597,7 +666,7 @@ int fct_solve_ws(fct_ctx* ctx, int32_t kind, const double* mat, const double* b,
     const double attainable = rtol * 1e3 > 1e-11 ? rtol * 1e3 : 1e-11;
     if (isfinite(rel) && rel <= attainable) return 0;
     FCT_CHECK(false, "fct_solve(%s): %s after %d iterations (relative residual %.3e, requested %.1e)",
-              kind == 1 ? "Jacobi-PCG" : "Jacobi-BiCGStab", h[S_DONE] == 2.0 ? "breakdown" : "not converged", (int)h[S_ITS], rel,
+              kind == 1 ? "Jacobi-PCG" : kind == 3 ? "Chebyshev-PCG" : "Jacobi-BiCGStab", h[S_DONE] == 2.0 ? "breakdown" : "not converged", (int)h[S_ITS], rel,
               rtol);
     return 1;
 }

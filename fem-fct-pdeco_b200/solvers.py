@@ -144,6 +144,9 @@ def _solve(ctx, kind, mat, b, x, what):
     """second-species system (the reference: spsolve).  1e-13 on the relative residual: the recursive residual of the Krylov
     loops bottoms out around 1e-13..1e-14 for these M + dt(...) systems, and libfctpdeco accepts a stagnated iterate at that
     level; a genuine failure names the system"""
+    if kind == _lib.SOLVER_PCG and ctx.n >= 50000:
+        # large SPD systems: Chebyshev-polynomial preconditioned CG (7x fewer reductions at 1025^2, profiles/r2_pcg_table.txt)
+        kind = _lib.SOLVER_CHEB_PCG
     try:
         its, res = ctx.solve(kind, mat, b, x, rtol=1e-13, maxit=20000)
     except _lib.FctError as e:

@@ -135,7 +135,9 @@ int fct_step_host(fct_ctx* ctx, const double* A_host, double sign, const double*
 
 /* ---- linear solvers for the second-species systems -------------------------------------------- */
 /* spsolve replacements (helpers.py:596,686,1342,1538).  kind: 0 = Jacobi, 1 = Jacobi-PCG (SPD),
- * 2 = Jacobi-BiCGStab (nonsymmetric).  x_dev holds the initial guess on entry.  its_host/res_host may be NULL. */
+ * 2 = Jacobi-BiCGStab (nonsymmetric), 3 = CG preconditioned with a degree-8 Chebyshev polynomial of the Jacobi-scaled matrix
+ * (SPD; FCT_CHEB_PCG_DEGREE overrides the degree; single GPU).  x_dev holds the initial guess on entry.  its_host/res_host
+ * may be NULL. */
 int fct_solve(fct_ctx* ctx, int32_t kind, const double* mat_dev, const double* b_dev, double* x_dev,
               double rtol, int32_t maxit, int32_t* its_host, double* res_host);
 /* out = a*X + b*Y on the pattern values (Y may be NULL), e.g. M + dt*(Df*K + delta*M) */

@@ -4,6 +4,8 @@ Python shims, against (a) outputs of the reference's own functions (tests/golden
 
 Tolerances (BASELINE.json north_star): fp64 fields within 1e-12 relative L2 per time step, cost functional
 within 1e-9; sparsity pattern and DoF ordering bit-exact (checked on the CPU in test_abi.py)."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -578,3 +580,53 @@ def test_FCT_alg_matches_reference_legacy_function(tag):
     out = helpers.FCT_alg(A, g[f"{tag}_rhs"], g[f"{tag}_un"], float(g[f"{tag}_dt"][0]), mesh.nodes, M, ML,
                           mesh.dof_neighbors(), source_mat=S)
     assert rel_l2(out, g[f"{tag}_out"]) < TOL_STEP
+
+
+def test_chebyshev_pcg_cuts_outer_iterations():
+    """fct_solve kind 3: CG with a degree-8 Chebyshev polynomial preconditioner on the second-species matrix of
+    the chemotaxis system, M + dt (Df Ad + delta M) on [0,16]^2 (chemotaxis_mimura_FCT_PGD.py:39-55, solved at helpers.py:1342):
+    same solution as Jacobi-PCG to the solver tolerance, and several times fewer outer iterations (= reductions)."""
+    dt, Df, delta = 0.1, 1.0, 32.0
+    for n, min_ratio in ((80, 1.5), (320, 5.0)):
+        mesh = RectMeshP1(n, 0.0, 16.0)
+        ctx = mesh.context()
+        M, _, _, K = ctx.static()
+        A = ctx.empty(mesh.nnz)
+        ctx.vals_axpby(1.0 + dt * delta, M, dt * Df, K, A)
+        rng = np.random.default_rng(n)
+        x_true = rng.standard_normal(mesh.nodes)
+        b = ctx.empty(mesh.nodes)
+        ctx.spmv(A, ctx.array(x_true), b)
+        out = {}
+        for kind in (_lib.SOLVER_PCG, _lib.SOLVER_CHEB_PCG):
+            x = ctx.array(np.zeros(mesh.nodes))
+            its, res = ctx.solve(kind, A, b, x, rtol=1e-13, maxit=5000)
+            out[kind] = (its, x.download())
+            assert res <= 1e-11
+            assert rel_l2(out[kind][1], x_true) < 1e-10
+        assert out[_lib.SOLVER_PCG][0] >= min_ratio * out[_lib.SOLVER_CHEB_PCG][0]
+
+
+def test_guard_allocator_detects_overrun():
+    """FCT_GUARD=1 only: a write one element past a device buffer lands in its canary band and fct_guard_check reports it
+    (live, and once more when the buffer is freed); without the mode the check reports nothing."""
+    import ctypes as C
+    bad, live = C.c_int64(), C.c_int64()
+    if os.environ.get("FCT_GUARD", "0") != "1":
+        _lib.check(_lib.lib.fct_guard_check(C.byref(bad), C.byref(live)))
+        assert (bad.value, live.value) == (0, 0)
+        pytest.skip("FCT_GUARD=1 not set")
+    ctx = RectMeshP1(4, 0.0, 1.0).context()
+    a = ctx.empty(10)
+    _lib.check(_lib.lib.fct_guard_check(C.byref(bad), C.byref(live)))
+    assert bad.value == 0 and live.value > 0
+    host = np.zeros(11)
+    _lib.check(_lib.lib.fct_h2d(ctx.handle, a.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))      # 8 bytes too many
+    ctx.sync()
+    _lib.check(_lib.lib.fct_guard_check(C.byref(bad), C.byref(live)))
+    assert bad.value == 1
+    a.free()
+    _lib.check(_lib.lib.fct_guard_check(C.byref(bad), C.byref(live)))      # reported again at the free, then forgotten
+    assert bad.value == 1
+    _lib.check(_lib.lib.fct_guard_check(C.byref(bad), C.byref(live)))
+    assert bad.value == 0
