@@ -283,6 +283,27 @@ def load_kernel_profile():
         return None
 
 
+# kernels of ONE state FCT step on the fused-tile path and how often each runs (16 Jacobi sweeps = 4 launches of 4, 20 Chebyshev
+# iterations = 1 + 4 launches of 5/5/5/4): with the per-launch DRAM bytes of profiles/r2_kernels.json this gives the bytes a
+# step really moves, the whole-step counterpart of the per-kernel roofline
+STATE_STEP_KERNELS = {"k_drift_low_build": 1, "k_tile": 4, "k_spmv": 1, "k_cheb_first": 1, "k_cheb_tile": 4, "k_flux_limits": 1,
+                      "k_flux_apply": 1}
+
+
+def step_roofline(kprof, state_ms, peak, appE_gb):
+    out = {"appE_GB_per_fct_step": appE_gb, "note": "appE = SURVEY App. E accounting unit, for reference only"}
+    ks = (kprof or {}).get("kernels") or {}
+    if all(k in ks for k in STATE_STEP_KERNELS):
+        gb = sum(ks[k]["dram_bytes_per_launch"] * c for k, c in STATE_STEP_KERNELS.items()) / 1e9
+        kernel_ms = sum(ks[k]["ms_per_launch"] * c for k, c in STATE_STEP_KERNELS.items())
+        out.update({"dram_GB_per_state_step": gb, "GBs": gb / (state_ms * 1e-3), "frac_of_peak": gb / (state_ms * 1e-3) / peak,
+                    "ncu_kernel_ms_per_state_step": kernel_ms,
+                    "how": "sum over the kernels of one state step of ncu dram bytes per launch (profiles/r2_kernels.json) / "
+                           "the CUDA-event time of a state step measured in this run; the fused tile kernels moved the step "
+                           "off the HBM roofline (they are bound by shared-memory latency and instruction issue, DESIGN.md 4)"})
+    return out
+
+
 class GradientIteration:
     """one projected-gradient iteration of advection_solidbody_FCT_PDECO_alltime.py:196-303 on device trajectories:
     state sweep, adjoint sweep, gradient (N_t+1 load vectors + ChebSI), ONE Armijo trial (clip, forward solve, cost,
@@ -429,7 +450,7 @@ def run_gpu_arm(args):
                              "implementation: templates and fusion delete bytes from it)"},
         "state_step": {"ms": state_ms, "steps_per_s": 1e3 / state_ms,
                        "note": "one FCT state step (assembly + low-order solve + ChebSI + limiter), device-resident"},
-        "step_roofline": {"appE_GB_per_fct_step": step_gb, "note": "SURVEY App. E accounting unit, for reference only"},
+        "step_roofline": step_roofline(kprof, state_ms, peak, step_gb),
         "kernels": (kprof or {}).get("kernels"),
         "kernels_source": (kprof or {}).get("source"),
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
