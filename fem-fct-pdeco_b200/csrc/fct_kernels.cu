@@ -584,7 +584,7 @@ __global__ void k_jacobi_decide(unsigned long long* __restrict__ jstate, double 
 // the same decision as the body of a CUDA-graph WHILE node: keeps looping until converged or out of sweeps
 __global__ void k_jacobi_decide_cond(unsigned long long* __restrict__ jstate, double rtol, unsigned long long max_sweeps,
                                      cudaGraphConditionalHandle handle) {
-    if (jstate[3]) { cudaGraphSetConditional(handle, 0u); return; }     // already converged (wavefront launch)
+    if (jstate[3]) { cudaGraphSetConditional(handle, 0u); return; }     // already converged (fused launch)
     if (jstate[4] < jstate[10] && jstate[4] < max_sweeps) {
         jstate[0] = 0ull; jstate[1] = 0ull;
         cudaGraphSetConditional(handle, 1u);
