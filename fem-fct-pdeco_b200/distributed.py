@@ -405,7 +405,7 @@ def bench_multi(args, rank, world, local_rank):
             "launches_per_fct_step_per_rank": lt.item() / world / fct_steps,
             "p2p_error": int(pe.item()),
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
-                    "time_levels": nt_e2e,
+                    "time_levels": nt_e2e, "host_link_GBs": e2e_value * 2 * e2e_bytes / 1e9,
                     "call": "fct_advdrift_state_host on every rank (state sweep, pinned host trajectories of the rank's "
                             "local range)"},
             "gpu_launches": int(lt.item()),
