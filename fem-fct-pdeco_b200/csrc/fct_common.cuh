@@ -154,6 +154,9 @@ struct fct_ctx {
     int64_t exchanges = 0;      // halo exchanges enqueued by the host (NCCL path; the peer-memory path counts on the device)
     fct_jgraph jgraph;
     fct_hoststage hs;
+    bool tile_adapt = true;     // FCT_TILE_ADAPT=0: every fused Jacobi launch runs tile_kj sweeps (no device-side sweep schedule)
+    bool tile_sched = false;    // the solve being enqueued uses the sweep schedule (set by fct_step)
+    bool in_time_loop = false;  // a device-resident time loop is being enqueued (fct_drivers.cu): the only place the schedule is used
     bool use_pdl = false;       // FCT_PDL=1 enables programmatic dependent launch (measured: no gain, persistent grids)
     bool capturing = false;
     bool use_graph = true;      // FCT_NO_GRAPH=1 falls back to the static launch sequence with device-side early exit
@@ -175,6 +178,64 @@ static inline void fct_set_ring(fct_ctx* c, int j) {
 static inline int fct_grid(const fct_ctx* c, int nblocks) { return nblocks < c->grid_cap ? nblocks : c->grid_cap; }
 
 #ifdef __CUDACC__
+// ---- sweep schedule of the fused Jacobi tile launches (fct_tile.cu; used by the stopping-test kernels of fct_kernels.cu and
+// fct_p2p.cu, which must agree to the bit) ---------------------------------------------------------------------------------
+// A launch of K sweeps is tested once, at its end, so a solve that needs 14 sweeps costs 16 with launches of 4.  The sweep count
+// of the low-order solve is nearly constant from one time step to the next: jstate[14] keeps the count the previous solve
+// needed, the launches of the next solve are sized to end exactly there (4+4+4+2 for 14; the kernel reads its depth from
+// jstate[13]).  The count is learnt from the last two tests of a solve (geometric decay of ||x_k - x_{k-1}||), and every
+// `period` solves one sweep fewer is tried (a failed probe costs one 2-sweep launch and doubles the period).  Everything is
+// derived from all-reduced test results, so N ranks and one GPU follow the same schedule; a time loop starts without history.
+//   jstate[13] depth of the next launch   [14] learnt count (0: none)   [16] target of this solve   [17] solves since the last
+//   probe   [18] probe period   [19] this solve is a probe   [20] delta bits / [21] sweep count of the last failed test
+__device__ __forceinline__ unsigned long long tile_next_k(unsigned long long done, unsigned long long target,
+                                                          unsigned long long kmax) {
+    if (target == 0ull) return kmax;                 // nothing learnt yet
+    if (done >= target) return 2ull;                 // past the expected count: short launches until the test passes
+    const unsigned long long r = target - done;
+    if (r > kmax + 1ull) return kmax;
+    if (r == kmax + 1ull) return kmax >= 3ull ? kmax - 1ull : 2ull;      // never leave a single sweep for the last launch
+    return r < 2ull ? 2ull : r;
+}
+__device__ __forceinline__ void tile_schedule_begin(unsigned long long* jstate, unsigned long long kmax) {
+    const unsigned long long learnt = jstate[14];
+    unsigned long long target = learnt, probing = 0ull;
+    if (learnt > 6ull) {
+        const unsigned long long period = jstate[18] ? jstate[18] : 8ull;
+        if (++jstate[17] >= period) { target = learnt - 1ull; probing = 1ull; jstate[17] = 0ull; }
+    }
+    jstate[16] = target;
+    jstate[19] = probing;
+    jstate[20] = 0ull;
+    jstate[21] = 0ull;
+    jstate[13] = tile_next_k(0ull, target, kmax);
+}
+__device__ __forceinline__ void tile_schedule_failed(unsigned long long* jstate, double delta, unsigned long long kmax) {
+    jstate[20] = (unsigned long long)__double_as_longlong(delta);
+    jstate[21] = jstate[4];
+    jstate[13] = tile_next_k(jstate[4], jstate[16], kmax);
+}
+// the test passed after jstate[4] sweeps with ||x_k - x_{k-1}|| = delta <= tol
+__device__ __forceinline__ void tile_schedule_converged(unsigned long long* jstate, double tol, double delta) {
+    const unsigned long long done = jstate[4];
+    unsigned long long need = done;
+    const unsigned long long sprev = jstate[21];
+    const double dprev = __longlong_as_double((long long)jstate[20]);
+    if (sprev > 0ull && sprev < done && dprev > tol && delta > 0.0 && delta < dprev) {
+        // decay per sweep between the last failed test and this one; the first sweep count at which the test would pass
+        const double lr = log(delta / dprev) / (double)(done - sprev);          // < 0
+        const double extra = ceil(log(tol / dprev) / lr);
+        if (extra >= 1.0 && extra < (double)(done - sprev)) need = sprev + (unsigned long long)extra;
+    }
+    if (jstate[19]) {
+        const unsigned long long period = jstate[18] ? jstate[18] : 8ull;
+        if (done <= jstate[16]) jstate[14] = done;                                   // the probe passed: one sweep fewer from now on
+        else { jstate[18] = period < 64ull ? 2ull * period : 64ull; if (done > jstate[14] + 1ull) jstate[14] = need; }
+    } else {
+        jstate[14] = need;
+    }
+}
+
 // ---- streaming loads (read-once data: bypass L1 so it stays free for the x gathers) -------------
 __device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
     double2 r;

@@ -164,6 +164,7 @@ extern "C" int fct_ctx_create(fct_ctx** out, int device, int32_t n, const int32_
     }
     c->cap = ((cap + 3) & ~3) + 4;
     { const char* e = getenv("FCT_NO_GRAPH"); c->use_graph = !(e && atoi(e) == 1); }
+    { const char* e = getenv("FCT_TILE_ADAPT"); c->tile_adapt = !(e && atoi(e) == 0); }
     { const char* e = getenv("FCT_PDL"); c->use_pdl = (e && atoi(e) == 1); }   // measured: no gain with persistent grids
     { const char* e = getenv("FCT_TILE_KJ"); if (e && atoi(e) >= 2 && atoi(e) <= 4) c->tile_kj = atoi(e); }
     { const char* e = getenv("FCT_TILE_GRID"); if (e && atoi(e) >= 1) c->tile_grid_cap = atoi(e); }
@@ -188,7 +189,7 @@ extern "C" int fct_ctx_create(fct_ctx** out, int device, int32_t n, const int32_
     rc |= dev_alloc(&c->Mdiag, (size_t)n);
     for (int i = 0; i < 12; ++i) rc |= dev_alloc(&c->w[i], (size_t)n);
     rc |= dev_alloc(&c->red, 64);
-    rc |= dev_alloc(&c->jstate, 16);
+    rc |= dev_alloc(&c->jstate, 32);
     if (rc) { fct_ctx_destroy(c); return 1; }
     if (cudaMallocHost((void**)&c->pinned, 64 * sizeof(double)) != cudaSuccess) {
         fct_set_error("fct_ctx_create: cudaMallocHost failed");
@@ -278,6 +279,7 @@ int fct_row_lump_diag(fct_ctx* ctx, const double* mat, double* out, double* diag
 // a new operator family, solver option or halo depth starts without it
 static int fct_reset_check_from(fct_ctx* ctx) {
     FCT_CUDA(cudaMemsetAsync(ctx->jstate + 10, 0, sizeof(unsigned long long), ctx->stream));
+    FCT_CUDA(cudaMemsetAsync(ctx->jstate + 13, 0, 8 * sizeof(unsigned long long), ctx->stream));      // sweep schedule (fct_kernels.cu)
     return 0;
 }
 int fct_halo_exchange_if(fct_ctx* ctx, double* vec);

@@ -22,8 +22,14 @@ __global__ void k_sweeps_accumulate(const unsigned long long* __restrict__ jstat
     if (jstate[4] > 0 && jstate[3] == 0) acc[1] += 1;
 }
 
+// Start of a time loop.  The learnt test / sweep schedule of the low-order solves (jstate[10], [13..19]; fct_kernels.cu) starts
+// from scratch, so that the result of a loop depends on its inputs only, not on what the context solved before (the host-buffer
+// and the device-resident loop, or N ranks and one GPU, then give the same bits); inside a loop the fused Jacobi launches follow
+// the device-side sweep schedule.
 static int acc_reset(fct_ctx* ctx) {
-    FCT_CUDA(cudaMemsetAsync(ctx->jstate + 8, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    FCT_CUDA(cudaMemsetAsync(ctx->jstate + 8, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    FCT_CUDA(cudaMemsetAsync(ctx->jstate + 13, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    ctx->in_time_loop = true;
     return 0;
 }
 int fct_p2p_check(fct_ctx* ctx, const char* what);      // fct_p2p.cu
@@ -32,6 +38,7 @@ int fct_p2p_check(fct_ctx* ctx, const char* what);      // fct_p2p.cu
 // sweeps -- the caller then repeats the loop with ctx->checked_steps (fct_step checks every low-order solve and falls back
 // to BiCGStab); without it such steps are an error.
 static int acc_read(fct_ctx* ctx, int32_t* total_sweeps_host, int* unconverged = nullptr) {
+    ctx->in_time_loop = false;
     if (fct_p2p_check(ctx, "time loop")) return 1;
     unsigned long long h[2];
     FCT_CUDA(cudaMemcpyAsync(h, ctx->jstate + 8, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));

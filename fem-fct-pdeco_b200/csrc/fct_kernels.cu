@@ -605,12 +605,14 @@ __global__ void k_jacobi_decide_cond(unsigned long long* __restrict__ jstate, do
 // stopping test after a fused K-sweep launch (fct_tile.cu); `which` = 1 when that launch wrote the scratch iterate, so
 // that the solve can copy it back (k_copy_if) when the loop ends there
 __global__ void k_tile_decide(unsigned long long* __restrict__ jstate, double rtol, unsigned long long max_sweeps,
-                              unsigned long long which, int use_handle, cudaGraphConditionalHandle handle) {
+                              unsigned long long which, int use_handle, cudaGraphConditionalHandle handle,
+                              unsigned long long kmax) {
     if (jstate[3]) { if (use_handle) cudaGraphSetConditional(handle, 0u); return; }
     // the same test schedule as the multi-GPU decision (k_p2p_max2_decide): no test before the sweep count learnt from the
     // previous solve -- on one GPU the test is free, but N ranks must stop after the same number of sweeps as one
     if (jstate[4] < jstate[10] && jstate[4] < max_sweeps) {
         jstate[0] = 0ull; jstate[1] = 0ull;
+        if (kmax) jstate[13] = tile_next_k(jstate[4], jstate[16], kmax);
         if (use_handle) cudaGraphSetConditional(handle, 1u);
         return;
     }
@@ -619,8 +621,8 @@ __global__ void k_tile_decide(unsigned long long* __restrict__ jstate, double rt
     jstate[5] = jstate[0];
     jstate[6] = jstate[1];
     const bool conv = delta <= rtol * xm;
-    if (conv) { jstate[3] = 1ull; jstate[12] = which; jacobi_note_convergence(jstate); }
-    else jstate[11] += 1ull;
+    if (conv) { jstate[3] = 1ull; jstate[12] = which; jacobi_note_convergence(jstate); if (kmax) tile_schedule_converged(jstate, rtol * xm, delta); }
+    else { jstate[11] += 1ull; if (kmax) tile_schedule_failed(jstate, delta, kmax); }
     jstate[0] = 0ull;
     jstate[1] = 0ull;
     if (use_handle) cudaGraphSetConditional(handle, (conv || jstate[4] >= max_sweeps) ? 0u : 1u);
@@ -632,7 +634,8 @@ __global__ void k_copy_if(const unsigned long long* __restrict__ flag, const dou
     for (int i = (int)blockIdx.x * (int)blockDim.x + (int)threadIdx.x; i < n; i += stride) dst[i] = src[i];
 }
 
-__global__ void k_jacobi_reset(unsigned long long* __restrict__ jstate) {
+__global__ void k_jacobi_reset(unsigned long long* __restrict__ jstate, unsigned long long tile_kmax) {
+    if (tile_kmax) tile_schedule_begin(jstate, tile_kmax);
     jstate[0] = 0ull; jstate[1] = 0ull; jstate[2] = 0ull; jstate[3] = 0ull; jstate[4] = 0ull;
     jstate[5] = 0ull; jstate[6] = 0ull;
     jstate[12] = 0ull;                   // 1: the converged iterate sits in the scratch vector (fused tile sweeps)
@@ -1208,13 +1211,14 @@ int fct_halo_exchange_if(fct_ctx* ctx, double* vec);   // no-op without a commun
 int fct_halo_exchange2_if(fct_ctx* ctx, double* v0, double* v1);
 bool fct_p2p_ready(const fct_ctx* ctx);
 int fct_p2p_max2_decide(fct_ctx* ctx, double rtol, int max_sweeps, int use_handle, cudaGraphConditionalHandle handle,
-                        int which = 0);
+                        int which = 0, int kmax = 0);
 int fct_halo_allreduce_max2(fct_ctx* ctx, unsigned long long* two_words);
 
 // ChebSI with deep-halo bookkeeping.  `vb`: ring on which the right-hand side b is valid.  Iteration k runs on ring
 // min(valid(y_{k-1}) - 1, vb); when that would drop below the owned rows the two live iterates are exchanged in one
 // message (valid on ring `depth` again).  Returns in *vy the ring on which the result is valid.
-int fct_tile_jacobi(fct_ctx* ctx, int K, const double* Lv, const double* b, const double* xin, double* xout);      // fct_tile.cu
+int fct_tile_jacobi(fct_ctx* ctx, int K, const double* Lv, const double* b, const double* xin, double* xout,
+                    const unsigned long long* kdev);      // fct_tile.cu
 int fct_tile_cheb(fct_ctx* ctx, int K, const double* g, const double* ymid, const double* yold, double* ymid_out,
                   double* yold_out, const double* om, double dscale);
 
@@ -1426,20 +1430,21 @@ static int jacobi_cycle_tiles(fct_ctx* ctx, const double* Lv, const double* b, d
     // halo depth >= 2 K (peer mailboxes): the iterate is valid on ring depth-K after the first launch, which is enough for the
     // second one -- one exchange per cycle; if the solve ends after a first half, jacobi_copy_back exchanges the result
     const bool deep = jacobi_tiles_deep(ctx, p2p);
+    const bool adapt = ctx->tile_adapt && ctx->tile_sched;      // launch depths from the device-side sweep schedule
     int rc = 0;
     fct_set_ring(ctx, 0);
     for (int half = 0; half < 2 && !rc; ++half) {
         double* xin = half ? tmp : x;
         double* xout = half ? x : tmp;
-        rc |= fct_tile_jacobi(ctx, K, Lv, b, xin, xout);
+        rc |= fct_tile_jacobi(ctx, K, Lv, b, xin, xout, adapt ? ctx->jstate + 13 : nullptr);
         if (!(deep && half == 0)) rc |= fct_halo_exchange_if(ctx, xout);
         const int uh = (use_handle && half == 1) ? 1 : 0;
         if (p2p) {
-            rc |= fct_p2p_max2_decide(ctx, rtol, max_sweeps, uh, handle, half == 0 ? 1 : 0);
+            rc |= fct_p2p_max2_decide(ctx, rtol, max_sweeps, uh, handle, half == 0 ? 1 : 0, adapt ? K : 0);
         } else {
             rc |= fct_halo_allreduce_max2(ctx, ctx->jstate);
             k_tile_decide<<<1, 1, 0, ctx->stream>>>(ctx->jstate, rtol, (unsigned long long)max_sweeps,
-                                                    half == 0 ? 1ull : 0ull, uh, handle);
+                                                    half == 0 ? 1ull : 0ull, uh, handle, adapt ? (unsigned long long)K : 0ull);
             ctx->launches++;
         }
     }
@@ -1460,7 +1465,7 @@ int fct_jacobi_solve(fct_ctx* ctx, const double* Lv, const double* b, const doub
     const int cycles = (max_sweeps + sweeps_per_cycle - 1) / sweeps_per_cycle;
     const bool p2p = ctx->comm && fct_p2p_ready(ctx);
     const bool tiles = jacobi_use_tiles(ctx, dinv) && (!ctx->comm || p2p || !ctx->use_graph);
-    const int jmode = tiles ? 10 + tile_kj(ctx) : ctx->jac_mode;
+    const int jmode = tiles ? 10 + tile_kj(ctx) + ((ctx->tile_adapt && ctx->tile_sched) ? 100 : 0) : ctx->jac_mode;
     if ((!ctx->comm || p2p) && dinv && ctx->use_graph) {
         // The cycle is the body of a CUDA-graph WHILE node whose condition the decide kernel sets on the device:
         // exactly as many sweeps as needed are launched, with no host round trip and no skipped launches (multi-GPU:
@@ -1638,7 +1643,9 @@ static int fct_step_impl(fct_ctx* ctx, const double* A, double sign, const doubl
     double* udot = ctx->w[7];
     double* Rp = ctx->w[8];
     double* Rn = ctx->w[9];
-    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+    // fused tile sweeps: the reset also starts the sweep schedule of this solve (depth of the first launch, probe)
+    ctx->tile_sched = ctx->tile_adapt && ctx->in_time_loop && jacobi_use_tiles(ctx, ctx->w[6]) && (!ctx->comm || fct_p2p_ready(ctx) || !ctx->use_graph);
+    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate, ctx->tile_sched ? (unsigned long long)tile_kj(ctx) : 0ull);
     ctx->launches++;
     // Deep halos: inputs (u_n, rhs, A incl. transposed entries) are valid on ring K (rhs: K-1); every pass below runs
     // on the largest ring its inputs allow, so that only the Jacobi / Chebyshev cycles and the output need exchanges.
@@ -1741,7 +1748,7 @@ extern "C" int fct_bench_jacobi_sweeps(fct_ctx* ctx, const double* A, const doub
     double* x = ctx->w[4];
     double* tmp = ctx->w[5];
     double* dinv = ctx->w[6];
-    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate, 0ull);
     fct_set_ring(ctx, 0);
     {
         const size_t smem = FCT_NST_LOW * smem_bytes(ctx, 1, 1) + 2 * smem_bytes(ctx, 1, 0);
@@ -1790,13 +1797,13 @@ extern "C" int fct_debug_jacobi_fixed(fct_ctx* ctx, const double* A, const doubl
     double* x = ctx->w[4];
     double* tmp = ctx->w[5];
     FCT_CUDA(cudaMemcpyAsync(x, un, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate, 0ull);
     int launches = 0;
     if (fused) {
         FCT_CHECK(ctx->tiles_ok && ctx->jac_mode == 2, "fct_debug_jacobi_fixed: tile kernels not available on this context");
         FCT_CHECK(fused >= 2 && fused <= 4 && sweeps % fused == 0, "fct_debug_jacobi_fixed: sweeps must be a multiple of fused (2..4)");
         for (int i = 0; i < sweeps / fused; ++i, ++launches)
-            if (fct_tile_jacobi(ctx, fused, ctx->Lvals, ctx->w[3], (i & 1) ? tmp : x, (i & 1) ? x : tmp)) return 1;
+            if (fct_tile_jacobi(ctx, fused, ctx->Lvals, ctx->w[3], (i & 1) ? tmp : x, (i & 1) ? x : tmp, nullptr)) return 1;
     } else {
         for (int i = 0; i < sweeps; ++i, ++launches) {
             double* xin = (i & 1) ? tmp : x;
@@ -1809,7 +1816,7 @@ extern "C" int fct_debug_jacobi_fixed(fct_ctx* ctx, const double* A, const doubl
         }
     }
     FCT_CUDA(cudaMemcpyAsync(x_out, (launches & 1) ? tmp : x, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate, 0ull);
     return fct_launch_error(ctx, "fct_debug_jacobi_fixed");
 }
 
@@ -1824,14 +1831,14 @@ extern "C" int fct_bench_jacobi_fused(fct_ctx* ctx, const double* A, const doubl
     if (fct_bench_jacobi_sweeps(ctx, A, un, dt, 2, &dummy)) return 1;      // builds L, b and leaves an iterate in w[4]
     double* x = ctx->w[4];
     double* tmp = ctx->w[5];
-    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate, 0ull);
     cudaEvent_t e0, e1;
     FCT_CUDA(cudaEventCreate(&e0));
     FCT_CUDA(cudaEventCreate(&e1));
     for (int pass = 0; pass < 2; ++pass) {          // pass 0: warm-up
         if (pass == 1) FCT_CUDA(cudaEventRecord(e0, ctx->stream));
         for (int i = 0; i < reps; ++i)
-            if (fct_tile_jacobi(ctx, sweeps, ctx->Lvals, ctx->w[3], (i & 1) ? tmp : x, (i & 1) ? x : tmp)) return 1;
+            if (fct_tile_jacobi(ctx, sweeps, ctx->Lvals, ctx->w[3], (i & 1) ? tmp : x, (i & 1) ? x : tmp, nullptr)) return 1;
     }
     FCT_CUDA(cudaEventRecord(e1, ctx->stream));
     FCT_CUDA(cudaEventSynchronize(e1));
@@ -1839,7 +1846,7 @@ extern "C" int fct_bench_jacobi_fused(fct_ctx* ctx, const double* A, const doubl
     FCT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate);
+    k_jacobi_reset<<<1, 1, 0, ctx->stream>>>(ctx->jstate, 0ull);
     *ms_per_sweep_host = ms / (reps * sweeps);
     return fct_launch_error(ctx, "fct_bench_jacobi_fused");
 }

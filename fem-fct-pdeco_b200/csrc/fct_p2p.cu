@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(32)
 k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, unsigned char* p2, unsigned char* p3,
                   unsigned char* p4, unsigned char* p5, unsigned char* p6, unsigned char* p7, int rank, int world,
                   unsigned long long* jstate, double rtol, unsigned long long max_sweeps, int use_handle,
-                  cudaGraphConditionalHandle handle, unsigned long long which, int dry_force) {
+                  cudaGraphConditionalHandle handle, unsigned long long which, int dry_force, unsigned long long kmax) {
     unsigned char* peers[FCT_P2P_MAXWORLD] = {p0, p1, p2, p3, p4, p5, p6, p7};
     P2PHeader* H = reinterpret_cast<P2PHeader*>(mine);
     __shared__ unsigned long long m0[32], m1[32];
@@ -183,10 +183,14 @@ k_p2p_max2_decide(unsigned char* mine, unsigned char* p0, unsigned char* p1, uns
                 jstate[12] = which;          // fused tile sweeps: 1 = the converged iterate is in the scratch vector
                 const unsigned long long s = jstate[4], back = jstate[11] ? 2ull : 4ull;
                 jstate[10] = s > back ? s - back : 0ull;
+                if (kmax) tile_schedule_converged(jstate, rtol * xm, delta);
             } else {
                 jstate[11] += 1ull;
+                if (kmax) tile_schedule_failed(jstate, delta, kmax);
             }
             H->rseq = seq;
+        } else if (kmax && jstate[3] == 0ull) {
+            jstate[13] = tile_next_k(jstate[4], jstate[16], kmax);
         }
         if (jstate[3] == 0ull) { jstate[0] = 0ull; jstate[1] = 0ull; }    // restart the running maxima
         if (use_handle) cudaGraphSetConditional(handle, (jstate[3] != 0ull || jstate[4] >= max_sweeps) ? 0u : 1u);
@@ -286,14 +290,14 @@ int fct_p2p_exchange(fct_ctx* ctx, double* v0, double* v1, const unsigned long l
 }
 
 int fct_p2p_max2_decide(fct_ctx* ctx, double rtol, int max_sweeps, int use_handle, cudaGraphConditionalHandle handle,
-                        int which) {
+                        int which, int kmax) {
     fct_p2p* p = ctx->p2p;
     const bool dry = p2p_dry() != 0;
     k_p2p_max2_decide<<<1, 32, 0, ctx->stream>>>(p->region, p->peer[0], p->peer[1], p->peer[2], p->peer[3], p->peer[4],
                                                  p->peer[5], p->peer[6], p->peer[7], dry ? 0 : p->rank, dry ? 1 : p->world,
                                                  ctx->jstate, rtol,
                                                  (unsigned long long)max_sweeps, use_handle, handle,
-                                                 (unsigned long long)which, dry ? 16 : 0);
+                                                 (unsigned long long)which, dry ? 16 : 0, (unsigned long long)kmax);
     ctx->launches++;
     return 0;
 }

@@ -59,9 +59,14 @@ struct fct_tiles {
     int sms = 148;
 };
 
+struct TileSel { const int4* tiles; int ntiles, out_rb, out_re; };
 struct TileArgs {
     int n_cells, total, g0, nloc, own_rb, own_re, out_rb, out_re, ntiles, K;
     const int4* tiles;     // {interior origin d0, p0, flags (TL_F_*), template code whose values every row of the tile shares}
+    // device-chosen fusion depth (Jacobi): *kdev in 2..4 selects K and sel[K] at launch time (fct_kernels.cu sets it from
+    // the sweep schedule of the solve); nullptr: the K, tiles, ntiles, out_* above
+    const unsigned long long* kdev;
+    TileSel sel[TL_KMAX];
     const int32_t* rowptr;
     const uint16_t* code;
     const unsigned long long* tdelta;
@@ -252,8 +257,24 @@ __device__ __forceinline__ void tl_passes(int K, double* A, double* B, const int
 // tiles at 4097^2) skip the per-row row-pointer / template look-ups altogether.
 template <int MODE, int W>
 __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
-    const int K = a.K;
     if (MODE == 0 && *reinterpret_cast<volatile unsigned long long*>(a.jstate + 3)) return;      // already converged
+    // launch geometry: fixed by the arguments, or selected by the device-side sweep schedule
+    __shared__ TileSel ssel;
+    __shared__ int sK;
+    if (threadIdx.x == 0) {
+        int k = a.K;
+        TileSel t = {a.tiles, a.ntiles, a.out_rb, a.out_re};
+        if (MODE == 0 && a.kdev) {
+            k = (int)*reinterpret_cast<const volatile unsigned long long*>(a.kdev);
+            k = k < 2 ? 2 : k > TL_KMAX - 1 ? TL_KMAX - 1 : k;
+            t = a.sel[k];
+        }
+        ssel = t; sK = k;
+    }
+    __syncthreads();
+    const int K = sK;
+    const int4* const tiles_ = ssel.tiles;
+    const int ntiles_ = ssel.ntiles;
     using SM = TileSmem<MODE, W>;
     double* sL = reinterpret_cast<double*>(fct_smem);
     double* sX = sL + SM::L_DOUBLES;
@@ -269,11 +290,11 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
         mbar_fence_init();
     }
     const int n = a.n_cells, total = a.total;
-    const int nmine = ((int)blockIdx.x < a.ntiles) ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int nmine = ((int)blockIdx.x < ntiles_) ? (ntiles_ - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     // tile records are fetched three tiles ahead into registers (rec1..rec3 = tiles j+1..j+3 while tile j is computed), so
     // that no thread ever waits for one
     auto fetch_rec = [&](int j) {
-        return j < nmine ? __ldg(a.tiles + (int)blockIdx.x + j * (int)gridDim.x) : make_int4(0, 0, 0, 0);
+        return j < nmine ? __ldg(tiles_ + (int)blockIdx.x + j * (int)gridDim.x) : make_int4(0, 0, 0, 0);
     };
     int4 rec0 = fetch_rec(0), rec1 = fetch_rec(1), rec2 = fetch_rec(2), rec3 = fetch_rec(3);
     int recj = 0;                                    // rec0 is the record of tile recj
@@ -475,7 +496,7 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
         for (int i = 0; i < TL_R; ++i) { fv[i] = fin[xi[i]]; pv[i] = prev[xi[i]]; }
 #pragma unroll
         for (int i = 0; i < TL_R; ++i) {
-            if (row[i] >= 0 && ml[i] >= K && row[i] >= a.out_rb && row[i] < a.out_re) {
+            if (row[i] >= 0 && ml[i] >= K && row[i] >= ssel.out_rb && row[i] < ssel.out_re) {
                 const double v = fv[i];
                 a.xout[row[i]] = v;
                 if (MODE == 0 && row[i] >= a.own_rb && row[i] < a.own_re) {
@@ -716,6 +737,14 @@ static int fill_args(fct_ctx* ctx, int K, TileArgs& a) {
     a.rowptr = ctx->rowptr; a.code = ctx->tpl_code; a.tdelta = t->tdelta; a.tval = ctx->tpl_val; a.tdiag = ctx->tpl_diag;
     a.Lv = nullptr; a.b = nullptr; a.xin = nullptr; a.yold = nullptr; a.xout = nullptr; a.yold_out = nullptr;
     a.jstate = ctx->jstate;
+    a.kdev = nullptr;
+    for (int k = 0; k < TL_KMAX; ++k) {
+        a.sel[k] = TileSel{nullptr, 0, 0, 0};
+        if (k >= 2 && t->list[k]) {
+            a.sel[k].tiles = t->list[k]; a.sel[k].ntiles = t->count[k];
+            tile_out_range(ctx, k, &a.sel[k].out_rb, &a.sel[k].out_re);
+        }
+    }
     for (int i = 0; i < TL_KMAX; ++i) a.om[i] = 0.0;
     a.dscale = 1.0;
     return 0;
@@ -723,12 +752,18 @@ static int fill_args(fct_ctx* ctx, int K, TileArgs& a) {
 
 // K (2..4) Jacobi sweeps of the row-scaled low-order system in one launch: xout <- sweep^K(xin); accumulates the
 // stopping-test maxima of the last sweep and adds K to the sweep counter
-int fct_tile_jacobi(fct_ctx* ctx, int K, const double* Lv, const double* b, const double* xin, double* xout) {
+// kdev != nullptr: the launch runs *kdev (2..K) sweeps instead, read on the device (sweep schedule of the solve)
+int fct_tile_jacobi(fct_ctx* ctx, int K, const double* Lv, const double* b, const double* xin, double* xout,
+                    const unsigned long long* kdev) {
     FCT_CHECK(ctx->tiles_ok && K >= 2 && K <= 4, "fct_tile_jacobi: not available");
     TileArgs a;
     if (fill_args(ctx, K, a)) return 1;
     a.Lv = Lv; a.b = b; a.xin = xin; a.xout = xout;
-    int grid = a.ntiles < ctx->tiles->sms ? a.ntiles : ctx->tiles->sms;
+    a.kdev = kdev;
+    int most = a.ntiles;                 // the deepest fusion has the smallest interiors, hence the most tiles
+    if (kdev)
+        for (int k = 2; k <= K; ++k) most = a.sel[k].ntiles > most ? a.sel[k].ntiles : most;
+    int grid = most < ctx->tiles->sms ? most : ctx->tiles->sms;
     if (ctx->tile_grid_cap > 0 && grid > ctx->tile_grid_cap) grid = ctx->tile_grid_cap;
     if (grid <= 0) return 0;
     if (ctx->max_row <= 7) tile_launch_t<0, 7>(ctx, a, grid); else tile_launch_t<0, 8>(ctx, a, grid);

@@ -434,7 +434,7 @@ def test_template_jacobi_modes(monkeypatch):
     assert np.array_equal(res["csr"][0], res["0"][0]) and res["csr"][1] == res["0"][1]
     for i in range(1, ns + 1):
         assert rel_l2(res["2"][0][i], res["0"][0][i]) < 1e-13 * i
-    assert abs(res["2"][1] - res["0"][1]) <= 4 * ns      # fused tile sweeps stop at multiples of 4
+    assert abs(res["2"][1] - res["0"][1]) <= 4 * ns      # fused tile sweeps are tested once per launch (2..4 sweeps)
 
 
 @pytest.mark.parametrize("n,grid,kc", [(5, 0, 5), (12, 0, 5), (45, 1, 4), (100, 3, 3), (300, 0, 5), (300, 5, 4), (300, 0, 3),
@@ -485,7 +485,9 @@ def test_tile_kernels_bit_identical(monkeypatch, n, grid, kc):
         assert np.array_equal(a, bb)
     for i in (1, 2):
         assert rel_l2(out["1"][2][i], out["0"][2][i]) < 1e-13 * i
-    assert out["1"][3] >= 4 and out["1"][3] % 4 == 0
+    # sweep counts: the per-pass path tests after every second sweep; the fused path after every launch, with launch depths
+    # (2..4) chosen by the device-side sweep schedule -- never fewer sweeps than the test needs, at most one launch more
+    assert 4 <= out["1"][3] <= out["0"][3] + 8
 
 
 def test_geometry_template_assembly_bit_identical(monkeypatch):
