@@ -80,6 +80,12 @@ SIGNATURES = {
     "fct_axpby": [_p, _i64, _f64, _p, _f64, _p, _p],
     "fct_assemble_matrix": [_p, _i32, _p, _p, _p, _f64, _f64, _f64, _i32, _p],
     "fct_assemble_vector": [_p, _i32, _p, _p, _p, _p, _f64, _f64, _f64, _i32, _p],
+    "fct_forward_nonlinear": [_p, _p, _f64, _p, _i32, _f64, _f64, _p, _pi32],
+    "fct_adjoint_nonlinear": [_p, _p, _p, _i32, _f64, _f64, _p, _pi32],
+    "fct_forward_schnak": [_p, _p, _f64, _p, _p, _i32, _f64, _p, _p, _f64, _pi32],
+    "fct_adjoint_schnak": [_p, _p, _p, _p, _p, _i32, _f64, _p, _p, _pi32],
+    "fct_forward_chtxs": [_p, _p, _f64, _p, _p, _i32, _f64, _p, _f64, _pi32],
+    "fct_adjoint_chtxs": [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _f64, _p, _f64, _pi32],
     "fct_advdrift_state": [_p, _p, _p, _i32, _f64, _f64, _f64, _f64, _pi32],
     "fct_advdrift_adjoint": [_p, _p, _p, _p, _p, _i32, _f64, _f64, _f64, _f64, _pi32],
     "fct_advdrift_gradient": [_p, _p, _p, _p, _p, _i32, _f64, _f64, _f64],

@@ -143,6 +143,9 @@ struct fct_ctx {
     double* Avals = nullptr;    // assembled operator (time loops) / host-call staging
     double* Svals = nullptr;    // host-call staging
     double* w[12] = {nullptr};  // vector workspace [n] each
+    double* sys_m[6] = {nullptr};   // nnz-sized operators of the PDE-system time loops (fct_drivers.cu, allocated on first use)
+    double* sys_v[4] = {nullptr};   // n-sized right-hand sides of those loops
+    double* sys_wind = nullptr;     // 20 doubles: polynomial wind coefficients
     double* fb_w[12] = {nullptr};   // private workspace of the BiCGStab fallback of the low-order solve (allocated on first use)
     bool checked_steps = false;     // fct_step reads the Jacobi outcome back after every low-order solve and falls back to BiCGStab
     double* red = nullptr;      // device scalars for reductions (64 doubles)

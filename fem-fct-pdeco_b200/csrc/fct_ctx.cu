@@ -236,6 +236,9 @@ extern "C" int fct_ctx_destroy(fct_ctx* c) {
     cudaFree(c->M); cudaFree(c->ML); cudaFree(c->Mdiag); cudaFree(c->K);
     cudaFree(c->Lvals); cudaFree(c->Dvals); cudaFree(c->Avals); cudaFree(c->Svals);
     for (int i = 0; i < 12; ++i) { cudaFree(c->w[i]); cudaFree(c->fb_w[i]); }
+    for (int i = 0; i < 6; ++i) cudaFree(c->sys_m[i]);
+    for (int i = 0; i < 4; ++i) cudaFree(c->sys_v[i]);
+    cudaFree(c->sys_wind);
     cudaFree(c->red); cudaFree(c->jstate);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

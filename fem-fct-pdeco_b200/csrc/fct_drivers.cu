@@ -677,3 +677,254 @@ int fct_solve_ws(fct_ctx* ctx, int32_t kind, const double* mat, const double* b,
               rtol);
     return 1;
 }
+
+
+// ======================================================================================================
+// Device-resident time loops of the three PDE systems of the refactored API
+// ======================================================================================================
+// The loops of helpers.py:511-698 (Schnakenberg), :881-1038 (nonlinear advection-reaction) and :1250-1581 (chemotaxis) on
+// device trajectories [(num_steps+1) * n], time-major: per step 1-4 assemblies, one FCT step and (two-species systems) one
+// Krylov solve, all enqueued from here -- no per-step host round trip except the convergence read-back of the Krylov solver.
+// The model parameters (get_*_params) are arguments, so the drivers do not hard-wire the reference's constants.
+// Control: the reference builds `control_fun` once, from the FIRST step's slice, and reuses it for every step
+// (helpers.py:577-578, 950-951, 1332-1333): the caller passes that one vector (or a constant).
+// Single GPU (the Krylov solvers are).  A step whose Jacobi solve runs out of sweeps makes run_time_loop repeat the sweep with
+// the BiCGStab fallback, like the drift-control loops.
+extern "C" int fct_assemble_matrix(fct_ctx* ctx, int32_t kind, const double* c0, const double* c1, const double* c2, double s0,
+                                   double s1, double scale, int32_t accumulate, double* out);
+extern "C" int fct_assemble_vector(fct_ctx* ctx, int32_t kind, const double* c0, const double* c1, const double* c2,
+                                   const double* c3, double s0, double s1, double scale, int32_t accumulate, double* out);
+
+static int sys_buffers(fct_ctx* ctx, int nm, int nv) {
+    FCT_CHECK(!ctx->comm, "the PDE-system time loops are single-GPU (their Krylov solvers are)");
+    FCT_CHECK(ctx->cells && ctx->mass_set && ctx->K, "PDE-system time loop: mesh / static matrices not set (fct_assemble_static)");
+    for (int i = 0; i < nm; ++i)
+        if (!ctx->sys_m[i]) FCT_CUDA(cudaMalloc((void**)&ctx->sys_m[i], sizeof(double) * ((size_t)ctx->nnz + 8)));
+    for (int i = 0; i < nv; ++i)
+        if (!ctx->sys_v[i]) FCT_CUDA(cudaMalloc((void**)&ctx->sys_v[i], sizeof(double) * ((size_t)ctx->n + 8)));
+    if (!ctx->sys_wind) FCT_CUDA(cudaMalloc((void**)&ctx->sys_wind, sizeof(double) * 20));
+    return 0;
+}
+static int sys_wind(fct_ctx* ctx, const double* wind20_host) {
+    FCT_CHECK(wind20_host, "PDE-system time loop: null wind coefficients");
+    FCT_CUDA(cudaMemcpyAsync(ctx->sys_wind, wind20_host, sizeof(double) * 20, cudaMemcpyHostToDevice, ctx->stream));
+    FCT_CUDA(cudaStreamSynchronize(ctx->stream));      // the host array may be a temporary
+    return 0;
+}
+// out (+)= scale * assemble(control * [other] * v dx); control: device vector, or the constant when the pointer is null
+static int sys_load_control(fct_ctx* ctx, double* out, const double* control, double control_const, const double* other,
+                            double scale, int accumulate) {
+    if (!control) {
+        if (!other) return fct_assemble_vector(ctx, FCT_LOAD_CONST, nullptr, nullptr, nullptr, nullptr, control_const, 0.0, scale, accumulate, out);
+        return fct_assemble_vector(ctx, FCT_LOAD_P1_1, other, nullptr, nullptr, nullptr, 0.0, 0.0, scale * control_const, accumulate, out);
+    }
+    if (!other) return fct_assemble_vector(ctx, FCT_LOAD_P1_1, control, nullptr, nullptr, nullptr, 0.0, 0.0, scale, accumulate, out);
+    return fct_assemble_vector(ctx, FCT_LOAD_P1_2, control, other, nullptr, nullptr, 0.0, 0.0, scale, accumulate, out);
+}
+// second-species system (the reference: spsolve).  1e-13 on the relative residual: the recursive residual of the Krylov loops
+// bottoms out around 1e-13..1e-14 for these M + dt(...) systems and fct_solve accepts a stagnated iterate at that level.
+// kind 1 (SPD): Chebyshev-polynomial preconditioned CG above 50 000 DoF (profiles/r2_pcg_table.txt).
+static int sys_solve(fct_ctx* ctx, int kind, const double* mat, const double* b, double* x, const char* what) {
+    if (kind == 1 && ctx->n >= 50000) kind = 3;
+    if (fct_solve_ws(ctx, kind, mat, b, x, 1e-13, 20000, nullptr, nullptr, ctx->w)) {
+        char msg[900];
+        snprintf(msg, sizeof(msg), "%s", fct_last_error());
+        fct_set_error("linear solve for '%s' failed: %s", what, msg);
+        return 1;
+    }
+    return 0;
+}
+static int sys_step_done(fct_ctx* ctx) {
+    k_sweeps_accumulate<<<1, 1, 0, ctx->stream>>>(ctx->jstate, ctx->jstate + 8);
+    ctx->launches++;
+    return 0;
+}
+
+// helpers.py:881-966: u_t + div(wind u) - eps lap(u) + u - u^3/3 = c
+extern "C" int fct_forward_nonlinear(fct_ctx* ctx, const double* control_dev, double control_const, double* var1_traj,
+                                     int32_t num_steps, double dt, double eps, const double* wind20_host,
+                                     int32_t* total_sweeps_host) {
+    FCT_CHECK(ctx && var1_traj && num_steps >= 0, "fct_forward_nonlinear: bad argument");
+    if (sys_buffers(ctx, 3, 1) || sys_wind(ctx, wind20_host)) return 1;
+    const size_t n = (size_t)ctx->n;
+    double *A = ctx->sys_m[0], *Mat1 = ctx->sys_m[1], *S = ctx->sys_m[2], *rhs = ctx->sys_v[0];
+    if (fct_assemble_matrix(ctx, FCT_FORM_WIND_POLY3, ctx->sys_wind, nullptr, nullptr, 0.0, 0.0, 1.0, 0, A)) return 1;
+    if (fct_vals_axpby(ctx, -1.0, A, eps, ctx->K, Mat1)) return 1;                                   // -(A - eps Ad)
+    if (num_steps >= 1 && sys_load_control(ctx, rhs, control_dev, control_const, nullptr, 1.0, 0)) return 1;      // assemble(c v dx)
+    return run_time_loop(ctx, total_sweeps_host, [&]() -> int {
+        for (int i = 1; i <= num_steps; ++i) {
+            const double* un = var1_traj + (i - 1) * n;
+            if (fct_assemble_matrix(ctx, FCT_FORM_WMASS2, un, un, nullptr, 0.0, 0.0, 1.0 / 3, 0, S)) return 1;      // M_u2/3 - M
+            if (fct_vals_axpby(ctx, 1.0, S, -1.0, ctx->M, S)) return 1;
+            if (fct_step(ctx, Mat1, 1.0, S, rhs, un, dt, var1_traj + i * n, nullptr)) return 1;
+            sys_step_done(ctx);
+        }
+        return 0;
+    });
+}
+
+// helpers.py:968-1038; level num_steps of p_traj holds the terminal condition on entry
+extern "C" int fct_adjoint_nonlinear(fct_ctx* ctx, const double* u_traj, double* p_traj, int32_t num_steps, double dt, double eps,
+                                     const double* wind20_host, int32_t* total_sweeps_host) {
+    FCT_CHECK(ctx && u_traj && p_traj && num_steps >= 0, "fct_adjoint_nonlinear: bad argument");
+    if (sys_buffers(ctx, 3, 0) || sys_wind(ctx, wind20_host)) return 1;
+    const size_t n = (size_t)ctx->n;
+    double *A = ctx->sys_m[0], *Mat = ctx->sys_m[1], *S = ctx->sys_m[2];
+    if (fct_assemble_matrix(ctx, FCT_FORM_WIND_POLY3, ctx->sys_wind, nullptr, nullptr, 0.0, 0.0, 1.0, 0, A)) return 1;
+    if (fct_vals_axpby(ctx, 1.0, A, eps, ctx->K, Mat)) return 1;                                     // -Mat_p = A + eps Ad
+    return run_time_loop(ctx, total_sweeps_host, [&]() -> int {
+        for (int i = num_steps - 1; i >= 0; --i) {
+            const double* un = u_traj + i * n;
+            if (fct_assemble_matrix(ctx, FCT_FORM_WMASS2, un, un, nullptr, 0.0, 0.0, 1.0, 0, S)) return 1;          // M_u2 - M
+            if (fct_vals_axpby(ctx, 1.0, S, -1.0, ctx->M, S)) return 1;
+            if (fct_step(ctx, Mat, 1.0, S, nullptr, p_traj + (i + 1) * n, dt, p_traj + i * n, nullptr)) return 1;
+            sys_step_done(ctx);
+        }
+        return 0;
+    });
+}
+
+// helpers.py:511-597.  params = {Du, Dv, c_b, gamma, omega1, omega2}
+extern "C" int fct_forward_schnak(fct_ctx* ctx, const double* control_dev, double control_const, double* var1_traj,
+                                  double* var2_traj, int32_t num_steps, double dt, const double* params6_host,
+                                  const double* wind20_host, double rescaling, int32_t* total_sweeps_host) {
+    FCT_CHECK(ctx && var1_traj && var2_traj && params6_host && num_steps >= 0, "fct_forward_schnak: bad argument");
+    if (sys_buffers(ctx, 6, 2) || sys_wind(ctx, wind20_host)) return 1;
+    const double Du = params6_host[0], Dv = params6_host[1], c_b = params6_host[2], gamma = params6_host[3],
+                 omega1 = params6_host[4], omega2 = params6_host[5];
+    const size_t n = (size_t)ctx->n;
+    double *A = ctx->sys_m[0], *Mat1 = ctx->sys_m[1], *S = ctx->sys_m[2], *base2 = ctx->sys_m[3], *Mat2 = ctx->sys_m[4],
+           *Mu2 = ctx->sys_m[5], *rhs1 = ctx->sys_v[0], *rhs2 = ctx->sys_v[1];
+    if (fct_assemble_matrix(ctx, FCT_FORM_WIND_POLY3, ctx->sys_wind, nullptr, nullptr, 0.0, 0.0, 1.0, 0, A)) return 1;
+    if (fct_vals_axpby(ctx, Du, ctx->K, -omega1, A, Mat1)) return 1;                                 // Du*Ad - omega1*A
+    if (fct_vals_axpby(ctx, gamma, ctx->M, 0.0, nullptr, S)) return 1;                               // non_flux_mat = gamma*M
+    if (fct_vals_axpby(ctx, dt * Dv, ctx->K, -dt * omega2, A, base2)) return 1;
+    if (fct_vals_axpby(ctx, 1.0, base2, 1.0, ctx->M, base2)) return 1;                               // M + dt(Dv Ad - omega2 A)
+    return run_time_loop(ctx, total_sweeps_host, [&]() -> int {
+        for (int i = 1; i <= num_steps; ++i) {
+            const double *un = var1_traj + (i - 1) * n, *vn = var2_traj + (i - 1) * n;
+            double *u1 = var1_traj + i * n, *v1 = var2_traj + i * n;
+            // rhs_var1 = assemble((gamma/r*c + gamma*u_n^2 v_n) v dx)
+            if (sys_load_control(ctx, rhs1, control_dev, control_const, nullptr, gamma / rescaling, 0)) return 1;
+            if (fct_assemble_vector(ctx, FCT_LOAD_P1_3, un, un, vn, nullptr, 0.0, 0.0, gamma, 1, rhs1)) return 1;
+            if (fct_step(ctx, Mat1, 1.0, S, rhs1, un, dt, u1, nullptr)) return 1;
+            sys_step_done(ctx);
+            // Mat_var2 = M + dt(Dv Ad - omega2 A + gamma M_u2), M_u2 from u_{n+1}
+            if (fct_assemble_matrix(ctx, FCT_FORM_WMASS2, u1, u1, nullptr, 0.0, 0.0, 1.0, 0, Mu2)) return 1;
+            if (fct_vals_axpby(ctx, 1.0, base2, dt * gamma, Mu2, Mat2)) return 1;
+            if (fct_spmv(ctx, ctx->M, vn, 1.0, 0.0, nullptr, rhs2)) return 1;
+            if (fct_assemble_vector(ctx, FCT_LOAD_CONST, nullptr, nullptr, nullptr, nullptr, gamma * c_b, 0.0, dt, 1, rhs2)) return 1;
+            if (fct_axpby(ctx, ctx->n, 1.0, vn, 0.0, nullptr, v1)) return 1;                         // initial guess
+            if (sys_solve(ctx, 2, Mat2, rhs2, v1, "var2")) return 1;
+        }
+        return 0;
+    });
+}
+
+// helpers.py:599-698; level num_steps of p_traj / q_traj holds the terminal conditions on entry.  params as above.
+extern "C" int fct_adjoint_schnak(fct_ctx* ctx, const double* u_traj, const double* v_traj, double* p_traj, double* q_traj,
+                                  int32_t num_steps, double dt, const double* params6_host, const double* wind20_host,
+                                  int32_t* total_sweeps_host) {
+    FCT_CHECK(ctx && u_traj && v_traj && p_traj && q_traj && params6_host && num_steps >= 0, "fct_adjoint_schnak: bad argument");
+    if (sys_buffers(ctx, 6, 2) || sys_wind(ctx, wind20_host)) return 1;
+    const double Du = params6_host[0], Dv = params6_host[1], gamma = params6_host[3], omega1 = params6_host[4],
+                 omega2 = params6_host[5];
+    const size_t n = (size_t)ctx->n;
+    double *A = ctx->sys_m[0], *Mat_p = ctx->sys_m[1], *S = ctx->sys_m[2], *base_q = ctx->sys_m[3], *Mat_q = ctx->sys_m[4],
+           *Mu2 = ctx->sys_m[5], *rhs_q = ctx->sys_v[0], *rhs_p = ctx->sys_v[1];
+    if (fct_assemble_matrix(ctx, FCT_FORM_WIND_POLY3_T, ctx->sys_wind, nullptr, nullptr, 0.0, 0.0, 1.0, 0, A)) return 1;   // dot(wind, grad(u)) w
+    if (fct_vals_axpby(ctx, Du, ctx->K, -omega1, A, Mat_p)) return 1;
+    if (fct_vals_axpby(ctx, dt * Dv, ctx->K, -dt * omega2, A, base_q)) return 1;
+    if (fct_vals_axpby(ctx, 1.0, base_q, 1.0, ctx->M, base_q)) return 1;
+    return run_time_loop(ctx, total_sweeps_host, [&]() -> int {
+        for (int i = num_steps - 1; i >= 0; --i) {
+            const double *un = u_traj + i * n, *vn = v_traj + i * n, *p1 = p_traj + (i + 1) * n, *q1 = q_traj + (i + 1) * n;
+            double *p0 = p_traj + i * n, *q0 = q_traj + i * n;
+            if (fct_assemble_matrix(ctx, FCT_FORM_WMASS2, un, un, nullptr, 0.0, 0.0, 1.0, 0, Mu2)) return 1;
+            if (fct_vals_axpby(ctx, 1.0, base_q, dt * gamma, Mu2, Mat_q)) return 1;
+            if (fct_spmv(ctx, ctx->M, q1, 1.0, 0.0, nullptr, rhs_q)) return 1;
+            if (fct_assemble_vector(ctx, FCT_LOAD_P1_3, p1, un, un, nullptr, 0.0, 0.0, dt * gamma, 1, rhs_q)) return 1;
+            if (fct_axpby(ctx, ctx->n, 1.0, q1, 0.0, nullptr, q0)) return 1;
+            if (sys_solve(ctx, 2, Mat_q, rhs_q, q0, "q")) return 1;
+            // non_flux_mat = gamma*M - 2*gamma*M_uv ; rhs_p = assemble(-2 gamma u v q_n w)
+            if (fct_assemble_matrix(ctx, FCT_FORM_WMASS2, un, vn, nullptr, 0.0, 0.0, -2 * gamma, 0, S)) return 1;
+            if (fct_vals_axpby(ctx, 1.0, S, gamma, ctx->M, S)) return 1;
+            if (fct_assemble_vector(ctx, FCT_LOAD_P1_3, un, vn, q0, nullptr, 0.0, 0.0, -2 * gamma, 0, rhs_p)) return 1;
+            if (fct_step(ctx, Mat_p, 1.0, S, rhs_p, p1, dt, p0, nullptr)) return 1;
+            sys_step_done(ctx);
+        }
+        return 0;
+    });
+}
+
+// helpers.py:1250-1385 (trajectory mode).  params = {delta, Dm, Df, chi, eta}
+extern "C" int fct_forward_chtxs(fct_ctx* ctx, const double* control_dev, double control_const, double* var1_traj,
+                                 double* var2_traj, int32_t num_steps, double dt, const double* params5_host, double rescaling,
+                                 int32_t* total_sweeps_host) {
+    FCT_CHECK(ctx && var1_traj && var2_traj && params5_host && num_steps >= 0, "fct_forward_chtxs: bad argument");
+    if (sys_buffers(ctx, 2, 1)) return 1;
+    const double delta = params5_host[0], Dm = params5_host[1], Df = params5_host[2], chi = params5_host[3], eta = params5_host[4];
+    const size_t n = (size_t)ctx->n;
+    double *Mat2 = ctx->sys_m[0], *A = ctx->sys_m[1], *rhs = ctx->sys_v[0];
+    if (fct_vals_axpby(ctx, 1.0 + dt * delta, ctx->M, dt * Df, ctx->K, Mat2)) return 1;              // M + dt(Df Ad + delta M)
+    return run_time_loop(ctx, total_sweeps_host, [&]() -> int {
+        for (int i = 1; i <= num_steps; ++i) {
+            const double *un = var1_traj + (i - 1) * n, *vn = var2_traj + (i - 1) * n;
+            double *u1 = var1_traj + i * n, *v1 = var2_traj + i * n;
+            // var2_rhs = assemble(v_n w dx + dt * c * u_n / r * w dx)
+            if (fct_assemble_vector(ctx, FCT_LOAD_P1_1, vn, nullptr, nullptr, nullptr, 0.0, 0.0, 1.0, 0, rhs)) return 1;
+            if (sys_load_control(ctx, rhs, control_dev, control_const, un, dt / rescaling, 1)) return 1;
+            if (fct_axpby(ctx, ctx->n, 1.0, vn, 0.0, nullptr, v1)) return 1;
+            if (sys_solve(ctx, 1, Mat2, rhs, v1, "var2")) return 1;
+            // A_var1 = Dm*Ad - chi*Aa, Aa = exp(-eta u_n) grad(v_{n+1}).grad(w) u   (quadrature degree 4)
+            if (fct_assemble_matrix(ctx, FCT_FORM_CHTX_EXP, v1, un, nullptr, eta, 0.0, -chi, 0, A)) return 1;
+            if (fct_vals_axpby(ctx, 1.0, A, Dm, ctx->K, A)) return 1;
+            if (fct_step(ctx, A, 1.0, nullptr, nullptr, un, dt, u1, nullptr)) return 1;
+            sys_step_done(ctx);
+        }
+        return 0;
+    });
+}
+
+// helpers.py:1387-1581; level num_steps of p_traj / q_traj holds the terminal conditions (zero for "alltime") on entry.
+// uhat_traj / vhat_traj != NULL: the all-time tracking terms, added NODALLY as the reference does (helpers.py:1509,1535).
+extern "C" int fct_adjoint_chtxs(fct_ctx* ctx, const double* u_traj, const double* v_traj, const double* uhat_traj,
+                                 const double* vhat_traj, double* p_traj, double* q_traj, const double* control_traj,
+                                 int32_t num_steps, double dt, const double* params5_host, double rescaling,
+                                 int32_t* total_sweeps_host) {
+    FCT_CHECK(ctx && u_traj && v_traj && p_traj && q_traj && control_traj && params5_host && num_steps >= 0,
+              "fct_adjoint_chtxs: bad argument");
+    FCT_CHECK((uhat_traj == nullptr) == (vhat_traj == nullptr), "fct_adjoint_chtxs: give both targets (all-time) or none");
+    if (sys_buffers(ctx, 2, 3)) return 1;
+    const double delta = params5_host[0], Dm = params5_host[1], Df = params5_host[2], chi = params5_host[3], eta = params5_host[4];
+    const size_t n = (size_t)ctx->n;
+    double *Mat_q = ctx->sys_m[0], *A = ctx->sys_m[1], *rhs_p = ctx->sys_v[0], *rhs_q = ctx->sys_v[1], *dif = ctx->sys_v[2];
+    if (fct_vals_axpby(ctx, 1.0 + dt * delta, ctx->M, dt * Df, ctx->K, Mat_q)) return 1;
+    return run_time_loop(ctx, total_sweeps_host, [&]() -> int {
+        for (int i = num_steps - 1; i >= 0; --i) {
+            const double *un = u_traj + i * n, *vn = v_traj + i * n, *cn = control_traj + i * n;
+            const double *p1 = p_traj + (i + 1) * n, *q1 = q_traj + (i + 1) * n;
+            double *p0 = p_traj + i * n, *q0 = q_traj + i * n;
+            // Mat_p = Dm*Ad - chi*Aa, Aa = (1-eta u)exp(-eta u) grad(p).grad(v_n) w   (quadrature degree 5)
+            if (fct_assemble_matrix(ctx, FCT_FORM_CHTX_ADJ, vn, un, nullptr, eta, 0.0, -chi, 0, A)) return 1;
+            if (fct_vals_axpby(ctx, 1.0, A, Dm, ctx->K, A)) return 1;
+            if (fct_assemble_vector(ctx, FCT_LOAD_P1_2, cn, q1, nullptr, nullptr, 0.0, 0.0, 1.0 / rescaling, 0, rhs_p)) return 1;
+            if (uhat_traj) {
+                if (fct_axpby(ctx, ctx->n, 1.0, uhat_traj + i * n, -1.0, un, dif)) return 1;
+                if (fct_axpby(ctx, ctx->n, 1.0, rhs_p, 1.0, dif, rhs_p)) return 1;
+            }
+            if (fct_step(ctx, A, 1.0, nullptr, rhs_p, p1, dt, p0, nullptr)) return 1;
+            sys_step_done(ctx);
+            // rhs_q = assemble(chi u exp(-eta u) grad(p_n).grad(w) dx)   (quadrature degree 4)
+            if (fct_assemble_vector(ctx, FCT_LOAD_CHTX_ADJ, p0, un, nullptr, nullptr, eta, chi, 1.0, 0, rhs_q)) return 1;
+            if (vhat_traj) {
+                if (fct_axpby(ctx, ctx->n, 1.0, vhat_traj + i * n, -1.0, vn, dif)) return 1;
+                if (fct_axpby(ctx, ctx->n, 1.0, rhs_q, 1.0, dif, rhs_q)) return 1;
+            }
+            if (fct_spmv(ctx, ctx->M, q1, 1.0, dt, rhs_q, rhs_q)) return 1;                          // M q_{n+1} + dt rhs_q
+            if (fct_axpby(ctx, ctx->n, 1.0, q1, 0.0, nullptr, q0)) return 1;
+            if (sys_solve(ctx, 1, Mat_q, rhs_q, q0, "q")) return 1;
+        }
+        return 0;
+    });
+}

@@ -9,10 +9,12 @@ error behaviour as the reference (KarolinaBenkova/FEM-FCT-PDECO):
     armijo_line_search_ref             helpers.py:1583-1713    get_*_params / *_IC                :443-509, 835-879, 1197-1248
 
 `V` is the dolfin-free stand-in `FunctionSpaceP1` (fem-fct-pdeco_b200/mesh.py); `control_fun` may be a number
-(the reference's `Constant`) or a DoF vector (the reference's `Function`).  All assembly, FCT steps and linear
-solves run on the GPU; the loops themselves are host control flow, as in the reference.  Reference quirks that
+(the reference's `Constant`) or a DoF vector (the reference's `Function`).  The six time loops run inside libfctpdeco
+(fct_forward_* / fct_adjoint_*, csrc/fct_drivers.cu) on device trajectories: these functions upload the caller's arrays once,
+call the driver and download the result into the caller's buffers.  Reference quirks that
 parity depends on are reproduced and marked.
 """
+import ctypes as C
 import warnings
 
 import numpy as np
@@ -132,6 +134,26 @@ class _Dev:
             ctx.assemble_vector(L.LOAD_P1_2, out, c0=control_fun, c1=other, scale=scale, accumulate=accumulate)
 
 
+def _hostp(a):
+    """(keep-alive array, pointer) of a small host parameter array"""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def _ctl(cfun):
+    """(device pointer or None, constant) of a control that is a number or a device vector"""
+    if cfun is None:
+        return None, 0.0
+    return (None, float(cfun)) if np.isscalar(cfun) else (cfun.ptr, 0.0)
+
+
+def _run(what, fn, *args):
+    try:
+        _lib.check(fn(*args))
+    except _lib.FctError as e:
+        raise _lib.FctError(f"{what}: {e}") from None
+
+
 def _control_slice(dev, control, control_fun, start, end):
     """the reference builds control_fun once, from the FIRST step's slice, and then reuses it
     (helpers.py:577-578, 950-951, 1332-1333) -- reproduced by the callers"""
@@ -170,67 +192,34 @@ def solve_schnak_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighb
 
 
 def _forward_schnak_dev(dev, cfun, d1, d2, num_steps, dt, rescaling=1):
-    """the loop of helpers.py:560-597 on device trajectories (level 0 = initial condition); cfun: number or device vector"""
+    """the loop of helpers.py:560-597 on device trajectories (level 0 = initial condition); cfun: number or device vector.
+    Runs in libfctpdeco (fct_forward_schnak, csrc/fct_drivers.cu): assemblies, FCT step and BiCGStab solve of every time
+    level are enqueued from C."""
     Du, Dv, _, c_b, gamma, omega1, omega2, wind = get_schnak_sys_params()
-    ctx, L = dev.ctx, _lib
-    dwind = ctx.array(wind)
-    A = dev.mat("A"); ctx.assemble_matrix(L.FORM_WIND_POLY3, A, c0=dwind)
-    Mat1 = dev.mat("Mat1"); ctx.vals_axpby(Du, dev.K, -omega1, A, Mat1)          # Du*Ad - omega1*A
-    S = dev.mat("S"); ctx.vals_axpby(gamma, dev.M, 0.0, None, S)                   # non_flux_mat = gamma*M
-    base2 = dev.mat("base2"); ctx.vals_axpby(dt * Dv, dev.K, -dt * omega2, A, base2)
-    ctx.vals_axpby(1.0, base2, 1.0, dev.M, base2)                                  # M + dt(Dv Ad - omega2 A)
-    Mat2, Mu2 = dev.mat("Mat2"), dev.mat("Mu2")
-    rhs1, rhs2 = dev.vec("rhs1"), dev.vec("rhs2")
     print("Solving the system of advective Schnakenberg state equations...")
-    for i in range(1, num_steps + 1):
-        un, vn, u1, v1 = dev.level(d1, i - 1), dev.level(d2, i - 1), dev.level(d1, i), dev.level(d2, i)
-        # rhs_var1 = assemble((gamma/r*c + gamma*u_n^2 v_n) v dx)
-        dev.load_control(rhs1, cfun, scale=gamma / rescaling)
-        ctx.assemble_vector(L.LOAD_P1_3, rhs1, c0=un, c1=un, c2=vn, scale=gamma, accumulate=True)
-        _check(ctx.step(Mat1, un, dt, u1, S=S, rhs=rhs1))
-        # Mat_var2 = M + dt(Dv Ad - omega2 A + gamma M_u2), M_u2 from u_{n+1}
-        ctx.assemble_matrix(L.FORM_WMASS2, Mu2, c0=u1, c1=u1)
-        ctx.vals_axpby(1.0, base2, dt * gamma, Mu2, Mat2)
-        ctx.spmv(dev.M, vn, rhs2)
-        ctx.assemble_vector(L.LOAD_CONST, rhs2, s0=gamma * c_b, scale=dt, accumulate=True)
-        ctx.axpby(1.0, vn, 0.0, None, v1)                                          # initial guess
-        _solve(ctx, L.SOLVER_BICGSTAB, Mat2, rhs2, v1, "var2")
+    cp, cc = _ctl(cfun)
+    par, ppar = _hostp([Du, Dv, c_b, gamma, omega1, omega2])
+    w, pw = _hostp(wind)
+    _run("solve_schnak_system", _lib.lib.fct_forward_schnak, dev.ctx.handle, cp, cc, d1.ptr, d2.ptr, int(num_steps), float(dt),
+         ppar, pw, float(rescaling), None)
 
 
 def solve_adjoint_schnak_system(uk, vk, uhat_T, vhat_T, pk, qk, T, V, nodes, num_steps, dt, dof_neighbors):
     """helpers.py:599-698"""
-    Du, Dv, _, _, gamma, omega1, omega2, wind = get_schnak_sys_params()
-    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    Du, Dv, _, c_b, gamma, omega1, omega2, wind = get_schnak_sys_params()
+    dev = _Dev(V, nodes)
     pk[num_steps * nodes:] = uhat_T - uk[num_steps * nodes:]
     qk[num_steps * nodes:] = vhat_T - vk[num_steps * nodes:]
-    dwind = ctx.array(wind)
-    A = dev.mat("A"); ctx.assemble_matrix(L.FORM_WIND_POLY3_T, A, c0=dwind)       # dot(wind, grad(u)) * w
-    Mat_p = dev.mat("Mat1"); ctx.vals_axpby(Du, dev.K, -omega1, A, Mat_p)
-    base_q = dev.mat("base2"); ctx.vals_axpby(dt * Dv, dev.K, -dt * omega2, A, base_q)
-    ctx.vals_axpby(1.0, base_q, 1.0, dev.M, base_q)
-    Mat_q, Mu2, S = dev.mat("Mat2"), dev.mat("Mu2"), dev.mat("S")
-    p1, q1 = ctx.array(pk[num_steps * nodes:]), ctx.array(qk[num_steps * nodes:])
-    p0, q0 = dev.vec("u1"), dev.vec("v1")
-    un, vn = dev.vec("un"), dev.vec("vn")
-    rhs_q, rhs_p = dev.vec("rhs1"), dev.vec("rhs2")
+    du, dv = dev.traj("var1", num_steps).upload(uk), dev.traj("var2", num_steps).upload(vk)
+    dp, dq = dev.traj("adj1", num_steps), dev.traj("adj2", num_steps)
+    dev.level(dp, num_steps).upload(pk[num_steps * nodes:]); dev.level(dq, num_steps).upload(qk[num_steps * nodes:])
     print("\nSolving adjoint equation...")
-    for i in reversed(range(0, num_steps)):
-        start, end = i * nodes, (i + 1) * nodes
-        un.upload(uk[start:end]); vn.upload(vk[start:end])
-        ctx.assemble_matrix(L.FORM_WMASS2, Mu2, c0=un, c1=un)
-        ctx.vals_axpby(1.0, base_q, dt * gamma, Mu2, Mat_q)
-        ctx.spmv(dev.M, q1, rhs_q)
-        ctx.assemble_vector(L.LOAD_P1_3, rhs_q, c0=p1, c1=un, c2=un, scale=dt * gamma, accumulate=True)
-        ctx.axpby(1.0, q1, 0.0, None, q0)
-        _solve(ctx, L.SOLVER_BICGSTAB, Mat_q, rhs_q, q0, "q")
-        # non_flux_mat = gamma*M - 2*gamma*M_uv ; rhs_p = assemble(-2 gamma u v q_n w)
-        ctx.assemble_matrix(L.FORM_WMASS2, S, c0=un, c1=vn, scale=-2 * gamma)
-        ctx.vals_axpby(1.0, S, gamma, dev.M, S)
-        ctx.assemble_vector(L.LOAD_P1_3, rhs_p, c0=un, c1=vn, c2=q0, scale=-2 * gamma)
-        _check(ctx.step(Mat_p, p1, dt, p0, S=S, rhs=rhs_p))
-        p0.download(pk[start:end]); q0.download(qk[start:end])
-        p1, p0 = p0, p1
-        q1, q0 = q0, q1
+    par, ppar = _hostp([Du, Dv, c_b, gamma, omega1, omega2])
+    w, pw = _hostp(wind)
+    _run("solve_adjoint_schnak_system", _lib.lib.fct_adjoint_schnak, dev.ctx.handle, du.ptr, dv.ptr, dp.ptr, dq.ptr,
+         int(num_steps), float(dt), ppar, pw, None)
+    if num_steps >= 1:
+        dp.slice(0, num_steps * nodes).download(pk[:num_steps * nodes]); dq.slice(0, num_steps * nodes).download(qk[:num_steps * nodes])
     return pk, qk
 
 
@@ -252,44 +241,31 @@ def solve_nonlinear_equation(control, var1, var2, V, nodes, num_steps, dt, dof_n
 
 
 def _forward_nonlinear_dev(dev, cfun, d1, d2, num_steps, dt, rescaling=None):
-    """the loop of helpers.py:935-966 on a device trajectory (level 0 = initial condition)"""
+    """the loop of helpers.py:935-966 on a device trajectory (level 0 = initial condition); fct_forward_nonlinear"""
     eps, _, wind = get_nonlinear_eqns_params()
-    ctx, L = dev.ctx, _lib
-    A = dev.mat("A"); ctx.assemble_matrix(L.FORM_WIND_POLY3, A, c0=ctx.array(wind))
-    Mat1 = dev.mat("Mat1"); ctx.vals_axpby(-1.0, A, eps, dev.K, Mat1)             # -(A - eps Ad)
-    S, rhs = dev.mat("S"), dev.vec("rhs1")
     print("\nSolving nonlinear state equation...")
-    if num_steps >= 1:
-        dev.load_control(rhs, cfun)                                                # var1_rhs = assemble(c v dx)
-    for i in range(1, num_steps + 1):
-        un, u1 = dev.level(d1, i - 1), dev.level(d1, i)
-        ctx.assemble_matrix(L.FORM_WMASS2, S, c0=un, c1=un, scale=1 / 3)           # -M + M_u2/3
-        ctx.vals_axpby(1.0, S, -1.0, dev.M, S)
-        _check(ctx.step(Mat1, un, dt, u1, S=S, rhs=rhs))
+    cp, cc = _ctl(cfun)
+    w, pw = _hostp(wind)
+    _run("solve_nonlinear_equation", _lib.lib.fct_forward_nonlinear, dev.ctx.handle, cp, cc, d1.ptr, int(num_steps), float(dt),
+         float(eps), pw, None)
 
 
 def solve_adjoint_nonlinear_equation(uk, uhat_T, pk, T, V, nodes, num_steps, dt, dof_neighbors):
     """helpers.py:968-1038"""
     eps, _, wind = get_nonlinear_eqns_params()
-    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    dev = _Dev(V, nodes)
     pk[num_steps * nodes:] = uhat_T - uk[num_steps * nodes:]
-    A = dev.mat("A"); ctx.assemble_matrix(L.FORM_WIND_POLY3, A, c0=ctx.array(wind))
-    Mat = dev.mat("Mat1"); ctx.vals_axpby(1.0, A, eps, dev.K, Mat)                 # -Mat_p = A + eps Ad
-    S = dev.mat("S")
-    p1, p0, un = ctx.array(pk[num_steps * nodes:]), dev.vec("u1"), dev.vec("un")
+    du, dp = dev.traj("var1", num_steps).upload(uk), dev.traj("adj1", num_steps)
+    dev.level(dp, num_steps).upload(pk[num_steps * nodes:])
     print("\nSolving adjoint equation...")
-    for i in reversed(range(0, num_steps)):
-        start, end = i * nodes, (i + 1) * nodes
-        un.upload(uk[start:end])
-        ctx.assemble_matrix(L.FORM_WMASS2, S, c0=un, c1=un)                        # M_u2 - M
-        ctx.vals_axpby(1.0, S, -1.0, dev.M, S)
-        _check(ctx.step(Mat, p1, dt, p0, S=S))
-        p0.download(pk[start:end])
-        p1, p0 = p0, p1
+    w, pw = _hostp(wind)
+    _run("solve_adjoint_nonlinear_equation", _lib.lib.fct_adjoint_nonlinear, dev.ctx.handle, du.ptr, dp.ptr, int(num_steps),
+         float(dt), float(eps), pw, None)
+    if num_steps >= 1:
+        dp.slice(0, num_steps * nodes).download(pk[:num_steps * nodes])
     return pk
 
 
-# ---- chemotaxis -----------------------------------------------------------------------------------------
 def solve_chtxs_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighbors, control_fun=None,
                        show_plots=False, vertex_to_dof=None, generation_mode=False, output_dir=None, rescaling=1 / 10):
     """helpers.py:1250-1385"""
@@ -323,14 +299,21 @@ def solve_chtxs_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighbo
 
 
 def _forward_chtxs_dev(dev, cfun, d1, d2, num_steps, dt, rescaling=1 / 10, pingpong=False, after_step=None):
-    """the loop of helpers.py:1318-1385 on device trajectories (level 0 = initial condition; pingpong: two levels only)"""
+    """the loop of helpers.py:1318-1385 on device trajectories (level 0 = initial condition): fct_forward_chtxs; the
+    generation mode (pingpong: two time levels only, periodic dumps) stays a Python loop over the same device calls"""
     delta, Dm, Df, chi, _, eta = get_chtxs_sys_params()
     ctx, L = dev.ctx, _lib
+    print("Solving the system of chemotaxis state equations...")
+    if not pingpong:
+        cp, cc = _ctl(cfun)
+        par, ppar = _hostp([delta, Dm, Df, chi, eta])
+        _run("solve_chtxs_system", L.lib.fct_forward_chtxs, ctx.handle, cp, cc, d1.ptr, d2.ptr, int(num_steps), float(dt), ppar,
+             float(rescaling), None)
+        return
     Mat2 = dev.mat("Mat2"); ctx.vals_axpby(1.0 + dt * delta, dev.M, dt * Df, dev.K, Mat2)   # M + dt(Df Ad + delta M)
     A, rhs = dev.mat("A"), dev.vec("rhs1")
-    print("Solving the system of chemotaxis state equations...")
     for i in range(1, num_steps + 1):
-        a, b = ((i - 1) % 2, i % 2) if pingpong else (i - 1, i)
+        a, b = (i - 1) % 2, i % 2
         un, vn, u1, v1 = dev.level(d1, a), dev.level(d2, a), dev.level(d1, b), dev.level(d2, b)
         # var2_rhs = assemble(v_n w dx + dt * c * u_n / r * w dx)
         ctx.assemble_vector(L.LOAD_P1_1, rhs, c0=vn)
@@ -353,39 +336,25 @@ def solve_adjoint_chtxs_system(uk, vk, uhat, vhat, pk, qk, control, T, V, nodes,
     if optim not in valid_options:
         raise ValueError(f"Invalid value for 'optim': '{optim}'. Must be one of {valid_options}.")
     delta, Dm, Df, chi, _, eta = get_chtxs_sys_params()
-    dev = _Dev(V, nodes); ctx, L = dev.ctx, _lib
+    dev = _Dev(V, nodes)
     if optim == "finaltime":
         pk[num_steps * nodes:] = uhat - uk[num_steps * nodes:]
         qk[num_steps * nodes:] = vhat - vk[num_steps * nodes:]
-    Mat_q = dev.mat("Mat2"); ctx.vals_axpby(1.0 + dt * delta, dev.M, dt * Df, dev.K, Mat_q)
-    A = dev.mat("A")
-    p1, q1 = ctx.array(pk[num_steps * nodes:(num_steps + 1) * nodes]), ctx.array(qk[num_steps * nodes:(num_steps + 1) * nodes])
-    p0, q0 = dev.vec("u1"), dev.vec("v1")
-    un, vn, cn, dif = dev.vec("un"), dev.vec("vn"), dev.vec("cn"), dev.vec("dif")
-    rhs_p, rhs_q = dev.vec("rhs1"), dev.vec("rhs2")
+    du, dv = dev.traj("var1", num_steps).upload(uk), dev.traj("var2", num_steps).upload(vk)
+    dc = dev.traj("ctl", num_steps).upload(control)
+    dp, dq = dev.traj("adj1", num_steps), dev.traj("adj2", num_steps)
+    dev.level(dp, num_steps).upload(pk[num_steps * nodes:(num_steps + 1) * nodes])
+    dev.level(dq, num_steps).upload(qk[num_steps * nodes:(num_steps + 1) * nodes])
+    uh = vh = None
+    if optim == "alltime":          # the reference adds the NODAL differences (helpers.py:1509,1535)
+        uh, vh = dev.traj("tgt1", num_steps).upload(uhat), dev.traj("tgt2", num_steps).upload(vhat)
     print("\nSolving adjoint equation...")
-    for i in reversed(range(0, num_steps)):
-        start, end = i * nodes, (i + 1) * nodes
-        un.upload(uk[start:end]); vn.upload(vk[start:end]); cn.upload(control[start:end])
-        # Mat_p = Dm*Ad - chi*Aa, Aa = (1-eta u)exp(-eta u) grad(p).grad(v_n) w   (quadrature degree 5)
-        ctx.assemble_matrix(L.FORM_CHTX_ADJ, A, c0=vn, c1=un, s0=eta, scale=-chi)
-        ctx.vals_axpby(1.0, A, Dm, dev.K, A)
-        ctx.assemble_vector(L.LOAD_P1_2, rhs_p, c0=cn, c1=q1, scale=1.0 / rescaling)
-        if optim == "alltime":          # the reference adds the NODAL difference (helpers.py:1509)
-            dif.upload(np.asarray(uhat[start:end]) - np.asarray(uk[start:end]))
-            ctx.axpby(1.0, rhs_p, 1.0, dif, rhs_p)
-        _check(ctx.step(A, p1, dt, p0, rhs=rhs_p))
-        # rhs_q = assemble(chi u exp(-eta u) grad(p_n).grad(w) dx)   (quadrature degree 4)
-        ctx.assemble_vector(L.LOAD_CHTX_ADJ, rhs_q, c0=p0, c1=un, s0=eta, s1=chi)
-        if optim == "alltime":          # (helpers.py:1535)
-            dif.upload(np.asarray(vhat[start:end]) - np.asarray(vk[start:end]))
-            ctx.axpby(1.0, rhs_q, 1.0, dif, rhs_q)
-        ctx.spmv(dev.M, q1, rhs_q, alpha=1.0, beta=dt, z=rhs_q)                    # M q_{n+1} + dt rhs_q
-        ctx.axpby(1.0, q1, 0.0, None, q0)
-        _solve(ctx, L.SOLVER_PCG, Mat_q, rhs_q, q0, "q")
-        p0.download(pk[start:end]); q0.download(qk[start:end])
-        p1, p0 = p0, p1
-        q1, q0 = q0, q1
+    par, ppar = _hostp([delta, Dm, Df, chi, eta])
+    _run("solve_adjoint_chtxs_system", _lib.lib.fct_adjoint_chtxs, dev.ctx.handle, du.ptr, dv.ptr,
+         uh.ptr if uh is not None else None, vh.ptr if vh is not None else None, dp.ptr, dq.ptr, dc.ptr, int(num_steps),
+         float(dt), ppar, float(rescaling), None)
+    if num_steps >= 1:
+        dp.slice(0, num_steps * nodes).download(pk[:num_steps * nodes]); dq.slice(0, num_steps * nodes).download(qk[:num_steps * nodes])
     return pk, qk
 
 

@@ -206,6 +206,34 @@ int fct_assemble_vector(fct_ctx* ctx, int32_t kind, const double* coef0_dev, con
                         const double* coef2_dev, const double* coef3_dev, double s0, double s1, double scale,
                         int32_t accumulate, double* out_dev);
 
+/* ---- device-resident time loops of the three PDE systems of the refactored API --
+ * solve_nonlinear_equation / solve_adjoint_nonlinear_equation (helpers.py:881-1038), solve_schnak_system /
+ * solve_adjoint_schnak_system (:511-698), solve_chtxs_system / solve_adjoint_chtxs_system (:1250-1581) on device
+ * trajectories [(num_steps+1) * n], time-major.  Level 0 of a state trajectory holds the initial condition on entry,
+ * level num_steps of an adjoint trajectory the terminal condition.  control_dev: the ONE control vector the reference
+ * builds from the first step's slice and reuses (App. D-1), or NULL for the constant control_const.  The model
+ * parameters of get_*_params are arguments: params6 = {Du, Dv, c_b, gamma, omega1, omega2}, params5 = {delta, Dm, Df,
+ * chi, eta}, wind20 = polynomial wind coefficients as for FCT_FORM_WIND_POLY3 (host arrays).  Single GPU.
+ * total_sweeps_host (may be NULL): Jacobi sweeps of all FCT steps. */
+int fct_forward_nonlinear(fct_ctx* ctx, const double* control_dev, double control_const, double* var1_traj_dev,
+                          int32_t num_steps, double dt, double eps, const double* wind20_host, int32_t* total_sweeps_host);
+int fct_adjoint_nonlinear(fct_ctx* ctx, const double* u_traj_dev, double* p_traj_dev, int32_t num_steps, double dt,
+                          double eps, const double* wind20_host, int32_t* total_sweeps_host);
+int fct_forward_schnak(fct_ctx* ctx, const double* control_dev, double control_const, double* var1_traj_dev,
+                       double* var2_traj_dev, int32_t num_steps, double dt, const double* params6_host,
+                       const double* wind20_host, double rescaling, int32_t* total_sweeps_host);
+int fct_adjoint_schnak(fct_ctx* ctx, const double* u_traj_dev, const double* v_traj_dev, double* p_traj_dev,
+                       double* q_traj_dev, int32_t num_steps, double dt, const double* params6_host,
+                       const double* wind20_host, int32_t* total_sweeps_host);
+int fct_forward_chtxs(fct_ctx* ctx, const double* control_dev, double control_const, double* var1_traj_dev,
+                      double* var2_traj_dev, int32_t num_steps, double dt, const double* params5_host, double rescaling,
+                      int32_t* total_sweeps_host);
+/* uhat/vhat_traj_dev: both NULL ("finaltime") or both given ("alltime": nodal tracking terms, helpers.py:1509,1535) */
+int fct_adjoint_chtxs(fct_ctx* ctx, const double* u_traj_dev, const double* v_traj_dev, const double* uhat_traj_dev,
+                      const double* vhat_traj_dev, double* p_traj_dev, double* q_traj_dev, const double* control_traj_dev,
+                      int32_t num_steps, double dt, const double* params5_host, double rescaling,
+                      int32_t* total_sweeps_host);
+
 /* ---- device-resident time loops of the drift-control advection PDECO ------------------------------
  * (advection_solidbody_FCT_PDECO_alltime.py:210-275, the shape of the 4096^2 benchmark).  Trajectories
  * are time-major device arrays [(num_steps+1) * n]; slice 0 of u must hold the initial condition. */
