@@ -288,7 +288,8 @@ def cost_functional(var1, var1_target, projected_control, num_steps, dt, M, beta
 # time loops, line search, parameter getters, initial conditions (fem-fct-pdeco_b200/solvers.py)
 # --------------------------------------------------------------------------------------------------
 from .solvers import (armijo_line_search, armijo_line_search_chtxs, armijo_line_search_ref,  # noqa: E402,F401
-                      armijo_line_search_sbr_drift, chtxs_sys_IC, cost_functional_proj, cost_functional_proj_FT, extract_data, get_chtxs_sys_params, import_data_final,
+                      armijo_line_search_sbr_drift, chtxs_sys_IC, cost_functional_proj, cost_functional_proj_FT, export_trajectory, extract_data, get_chtxs_sys_params,
+                      import_data_final,
                       get_nonlinear_eqns_params, get_schnak_sys_params, nonlinear_equation_IC, schnak_sys_IC,
                       solve_adjoint_chtxs_system, solve_adjoint_nonlinear_equation, solve_adjoint_schnak_system,
                       solve_chtxs_system, solve_nonlinear_equation, solve_schnak_system)

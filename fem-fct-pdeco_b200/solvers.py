@@ -709,6 +709,18 @@ def import_data_final(file_path, nodes, vertex_to_dof, num_steps=0, time_dep=Fal
     return data_re, data
 
 
+def export_trajectory(file_path, data):
+    """Writer counterpart of import_data_final / extract_data: the flat DoF-ordered trajectory either as the
+    reference's comma-separated text (`data.tofile(path, sep=",")`, e.g. advection_solidbody_FCT_PDECO_alltime.py:409-411) or,
+    for a path ending in .npy, as a binary array with the same layout (memory-mappable; 8 B instead of ~25 B per value)."""
+    data = np.ascontiguousarray(data, dtype=np.float64).ravel()
+    if str(file_path).endswith(".npy"):
+        np.save(file_path, data)
+    else:
+        data.tofile(file_path, sep=",")
+    return None
+
+
 def extract_data(file_path, file_name, T, dt, nodes, vertex_to_dof):
     """helpers.py:1913-1956: cut the time slice at T out of a flat trajectory file (csv as in the reference, or .npy)"""
     import os

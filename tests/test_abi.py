@@ -117,8 +117,9 @@ def test_trajectory_io_csv_and_npy(tmp_path):
     m = RectMeshP1(3)
     nodes = m.nodes
     x = np.random.default_rng(2).random(3 * nodes)
-    x.tofile(tmp_path / "a.csv", sep=",")
-    np.save(tmp_path / "a.npy", x)
+    helpers.export_trajectory(str(tmp_path / "a.csv"), x)          # the reference's np.tofile(sep=",") text
+    helpers.export_trajectory(str(tmp_path / "a.npy"), x)          # binary, same flat DoF-ordered layout
+    assert np.array_equal(np.genfromtxt(tmp_path / "a.csv", delimiter=","), x)
     r1, d1 = helpers.import_data_final(str(tmp_path / "a.csv"), nodes, m.vertex_to_dof, num_steps=2)
     r2, d2 = helpers.import_data_final(str(tmp_path / "a.npy"), nodes, m.vertex_to_dof, num_steps=2)
     assert np.array_equal(r1, r2) and np.array_equal(d1, x[2 * nodes:]) and np.array_equal(d2, d1)
