@@ -372,6 +372,26 @@ def bench_multi(args, rank, world, local_rank):
     dist.all_reduce(te[1:], op=dist.ReduceOp.SUM)
     e2e_value = nt_e2e * reps_e2e / float(te[0].item())
     e2e_bytes = int(te[1].item())
+    # what the box's host<->device path gives the N ranks together when they do nothing but the copies of the e2e sweep (one
+    # H2D and one D2H of a local slice per time level, two streams, pinned memory): the ceiling of `e2e` at this N
+    th_in, th_out = torch.empty(n, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory()
+    td_in, td_out = torch.empty(n, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    for rep in range(2):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(nt_e2e):
+            with torch.cuda.stream(s_in):
+                td_in.copy_(th_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                th_out.copy_(td_out, non_blocking=True)
+        torch.cuda.synchronize()
+        probe_s = time.perf_counter() - t0
+    tp = torch.tensor([probe_s], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    probe_steps_per_s = nt_e2e / float(tp.item())
+    del th_in, th_out, td_in, td_out
     perr = p2p_error(ctx)
     pe = torch.tensor([perr], device="cuda")
     dist.all_reduce(pe, op=dist.ReduceOp.MAX)
@@ -406,6 +426,9 @@ def bench_multi(args, rank, world, local_rank):
             "p2p_error": int(pe.item()),
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
                     "time_levels": nt_e2e, "host_link_GBs": e2e_value * 2 * e2e_bytes / 1e9,
+                    "copy_only_steps_per_s": probe_steps_per_s, "copy_only_GBs": probe_steps_per_s * 2 * e2e_bytes / 1e9,
+                    "copy_only_note": "the same per-level H2D + D2H of every rank's local slice without any compute (pinned "
+                                      "memory, two streams per rank): the host-side ceiling of e2e at this N",
                     "call": "fct_advdrift_state_host on every rank (state sweep, pinned host trajectories of the rank's "
                             "local range)"},
             "gpu_launches": int(lt.item()),

@@ -610,8 +610,9 @@ def test_chebyshev_pcg_cuts_outer_iterations():
 
 
 def test_guard_allocator_detects_overrun():
-    """FCT_GUARD=1 only: a write one element past a device buffer lands in its canary band and fct_guard_check reports it
-    (live, and once more when the buffer is freed); without the mode the check reports nothing."""
+    """FCT_GUARD=1 only: a write past a device buffer (beyond the 64 bytes of slack every fct_malloc buffer carries for the
+    16-byte staging loads of a last row block) lands in its canary band and fct_guard_check reports it (live, and once more
+    when the buffer is freed); without the mode the check reports nothing."""
     import ctypes as C
     bad, live = C.c_int64(), C.c_int64()
     if os.environ.get("FCT_GUARD", "0") != "1":
@@ -622,8 +623,8 @@ def test_guard_allocator_detects_overrun():
     a = ctx.empty(10)
     _lib.check(_lib.lib.fct_guard_check(C.byref(bad), C.byref(live)))
     assert bad.value == 0 and live.value > 0
-    host = np.zeros(11)
-    _lib.check(_lib.lib.fct_h2d(ctx.handle, a.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))      # 8 bytes too many
+    host = np.zeros(10 + 8 + 1)
+    _lib.check(_lib.lib.fct_h2d(ctx.handle, a.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))      # 8 bytes into the band
     ctx.sync()
     _lib.check(_lib.lib.fct_guard_check(C.byref(bad), C.byref(live)))
     assert bad.value == 1
