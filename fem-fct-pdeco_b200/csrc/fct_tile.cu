@@ -1,5 +1,5 @@
 // Overlapped 2-D tiles for the two iterative kernels of the FCT step on structured (RectangleMesh) numberings:
-// K Jacobi sweeps of the low-order solve (helpers.py:1782) or K Chebyshev iterations of ChebSI (helpers.py:143-185) per
+// K Jacobi sweeps of the low-order solve (helpers.py:1782; k_tile) or K Chebyshev iterations of ChebSI (helpers.py:143-185; k_cheb_tile) per
 // launch, out of shared memory and registers.
 //
 // dolfin's CG1 numbering on RectangleMesh is an anti-diagonal numbering: row = start(d) + pos with
@@ -70,17 +70,11 @@ struct TileArgs {
     const int32_t* rowptr;
     const uint16_t* code;
     const unsigned long long* tdelta;
-    const double* tval;
-    const double* tdiag;
-    const double* Lv;      // Jacobi: row-scaled low-order operator (zero diagonal slot)
-    const double* b;       // Jacobi: b'; ChebSI: g
-    const double* xin;     // Jacobi: x; ChebSI: y_mid
-    const double* yold;    // ChebSI: y_old (nullptr: zero)
-    double* xout;          // Jacobi: x after K sweeps; ChebSI: y_mid after K iterations
-    double* yold_out;      // ChebSI: y_old after K iterations (nullptr: not wanted)
+    const double* Lv;      // row-scaled low-order operator (zero diagonal slot)
+    const double* b;       // b'
+    const double* xin;     // x
+    double* xout;          // x after K sweeps
     unsigned long long* jstate;
-    double om[TL_KMAX];
-    double dscale;
 };
 
 // ---- closed-form numbering ----------------------------------------------------------------------------------
@@ -180,10 +174,10 @@ __host__ __device__ constexpr unsigned long long tl_pack7(int a0, int a1, int a2
 #define TL_DPK_UP tl_pack7(-TL_XS - 1, -TL_XS, -1, 0, 1, TL_XS, TL_XS + 1)
 #define TL_DPK_LO tl_pack7(-TL_XS, -TL_XS + 1, -1, 0, 1, TL_XS - 1, TL_XS)
 
-template <int MODE, int W>
+template <int W>
 struct TileSmem {
     static constexpr int SEGCAP = (TL_NQ * W + 2 + 1) & ~1;                        // staged CSR range of one region diagonal (even)
-    static constexpr int L_DOUBLES = (MODE == 0) ? TL_NC * SEGCAP : 0;
+    static constexpr int L_DOUBLES = TL_NC * SEGCAP;
     static constexpr int X_DOUBLES = 3 * TL_ND * TL_XS;
     static constexpr size_t BYTES = 8 * (size_t)(L_DOUBLES + X_DOUBLES) + 4 * (2 * TL_NC + 4 * TL_ND);
     static_assert(L_DOUBLES % 2 == 0, "bulk-copy destinations must stay 16-byte aligned");
@@ -204,11 +198,10 @@ __device__ __forceinline__ void tl_segment_rows(const TileArgs& a, int dlo, int 
 // main anti-diagonal (shared-memory loads with immediate offsets); KIND 0: per-row deltas from the template table.
 // Straight-line code over the thread's rows (no per-row branches: the 21 loads and the three FMA chains interleave); rows
 // that are not part of pass s are computed on whatever their slots hold and simply not stored.
-template <int MODE, int W, int KIND>
+template <int W, int KIND>
 __device__ __forceinline__ void tl_passes(int K, double* A, double* B, const int (&xi)[TL_R], const int (&ml)[TL_R],
                                           const int (&row)[TL_R], const double (&Lr)[TL_R][W],
-                                          const unsigned long long (&dpk)[TL_R], const double (&br)[TL_R], double (&yo)[TL_R],
-                                          const double (&md)[TL_R], const double* __restrict__ om) {
+                                          const unsigned long long (&dpk)[TL_R], const double (&br)[TL_R]) {
 #pragma unroll 1
     for (int s = 1; s <= K; ++s) {
         const double* in = (s & 1) ? A : B;
@@ -233,21 +226,14 @@ __device__ __forceinline__ void tl_passes(int K, double* A, double* B, const int
 #pragma unroll
         for (int i = 0; i < TL_R; ++i) {
             const bool act = row[i] >= 0 && s <= ml[i];
-            if (MODE == 0) {
-                if (act) out[xi[i]] = br[i] - acc[i];
-            } else {
-                const double ym = in[xi[i]];
-                const double z = (br[i] - acc[i]) / md[i];
-                const double yn = om[s - 1] * (z + ym - yo[i]) + yo[i];
-                if (act) { out[xi[i]] = yn; yo[i] = ym; }
-            }
+            if (act) out[xi[i]] = br[i] - acc[i];
         }
         __syncthreads();
     }
 }
 
-// MODE 0: K Jacobi sweeps  x <- b' - sum_j l'_ij x_j  of the row-scaled low-order system (k_jacobi_sweep_tpl<., true>)
-// MODE 1: K Chebyshev iterations  y+ = om (z + y - y-) + y-,  z = (g - M y) / (dscale diag M)  (k_cheb_iter_tpl)
+// K Jacobi sweeps  x <- b' - sum_j l'_ij x_j  of the row-scaled low-order system (k_jacobi_sweep_tpl<., true>); the ChebSI
+// counterpart is k_cheb_tile below.
 // Every warp computes.  Software pipeline over the CTA's tiles (all loads are issued by the compute threads themselves):
 //   during tile j   : the CSR bounds of tile j+2's diagonal segments and the template data of tile j+1 travel (registers);
 //                     tile j+1's iterate (8-byte cp.async), matrix rows (one 1-D TMA bulk copy per region diagonal) and
@@ -255,16 +241,16 @@ __device__ __forceinline__ void tl_passes(int K, double* A, double* B, const int
 //   top of tile j+1 : matrix rows move from the staging buffer to registers, the buffer is handed to tile j+2.
 // "Regular" tiles (flags from k_tile_classify: every row exists, 7 entries, one of the two interior layouts -- 93 % of the
 // tiles at 4097^2) skip the per-row row-pointer / template look-ups altogether.
-template <int MODE, int W>
+template <int W>
 __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
-    if (MODE == 0 && *reinterpret_cast<volatile unsigned long long*>(a.jstate + 3)) return;      // already converged
+    if (*reinterpret_cast<volatile unsigned long long*>(a.jstate + 3)) return;      // already converged
     // launch geometry: fixed by the arguments, or selected by the device-side sweep schedule
     __shared__ TileSel ssel;
     __shared__ int sK;
     if (threadIdx.x == 0) {
         int k = a.K;
         TileSel t = {a.tiles, a.ntiles, a.out_rb, a.out_re};
-        if (MODE == 0 && a.kdev) {
+        if (a.kdev) {
             k = (int)*reinterpret_cast<const volatile unsigned long long*>(a.kdev);
             k = k < 2 ? 2 : k > TL_KMAX - 1 ? TL_KMAX - 1 : k;
             t = a.sel[k];
@@ -275,7 +261,7 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
     const int K = sK;
     const int4* const tiles_ = ssel.tiles;
     const int ntiles_ = ssel.ntiles;
-    using SM = TileSmem<MODE, W>;
+    using SM = TileSmem<W>;
     double* sL = reinterpret_cast<double*>(fct_smem);
     double* sX = sL + SM::L_DOUBLES;
     int* sKa = reinterpret_cast<int*>(sX + SM::X_DOUBLES);          // [NC] first staged CSR index of each L segment
@@ -286,7 +272,7 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
     __shared__ double sred[2][TL_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        mbar_init(&bar_full, TL_NT + (MODE == 0 ? TL_NT / 32 : 0));      // cp.async completions (+ one expect_tx arrival per warp)
+        mbar_init(&bar_full, TL_NT + TL_NT / 32);      // cp.async completions + one expect_tx arrival per warp
         mbar_fence_init();
     }
     const int n = a.n_cells, total = a.total;
@@ -299,7 +285,7 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
     int4 rec0 = fetch_rec(0), rec1 = fetch_rec(1), rec2 = fetch_rec(2), rec3 = fetch_rec(3);
     int recj = 0;                                    // rec0 is the record of tile recj
     auto tile_of = [&](int j) { return j == recj ? rec0 : j == recj + 1 ? rec1 : j == recj + 2 ? rec2 : rec3; };
-    auto is_regular = [&](int flag) { return MODE == 0 ? (W == 7 && (flag & 3) != 0) : (W == 7 && (flag & 3) != 0 && (flag & TL_F_MUNI) != 0); };
+    auto is_regular = [&](int flag) { return W == 7 && (flag & 3) != 0; };
 
     // rows this thread updates (compute set) and region entries it loads: fixed for the whole launch
     // (a warp takes 32 consecutive positions of one diagonal -- conflict-free 8-byte shared-memory accesses --, the
@@ -340,7 +326,7 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
     int sb_k0 = 0, sb_k1 = 0;
     auto load_seg_bounds = [&](int j) {
         sb_k0 = 0; sb_k1 = 0;
-        if (MODE != 0 || j >= nmine) return;
+        if (j >= nmine) return;
         const int c = warp + (TL_NT / 32) * lane;
         if (lane < 3 && c < TL_NC) {
             const int4 t = tile_of(j);
@@ -352,16 +338,16 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
 
     int row[TL_R], nrow[TL_R], ncode[TL_R], nk0[TL_R], nk1[TL_R];
     unsigned long long dpk[TL_R];
-    double Lr[TL_R][W], br[TL_R], nb[TL_R], yo[TL_R], nyo[TL_R], md[TL_R];
-    int nflag = 0, nvcode = 0;
+    double Lr[TL_R][W], br[TL_R], nb[TL_R];
+    int nflag = 0;
     // rows of tile j and the first loads they need (right-hand side; for general tiles row pointer and template code)
     auto prefetch_meta = [&](int j) {
 #pragma unroll
-        for (int i = 0; i < TL_R; ++i) { nrow[i] = -1; ncode[i] = 0; nk0[i] = 0; nk1[i] = 0; nb[i] = 0.0; nyo[i] = 0.0; }
-        nflag = 0; nvcode = 0;
+        for (int i = 0; i < TL_R; ++i) { nrow[i] = -1; ncode[i] = 0; nk0[i] = 0; nk1[i] = 0; nb[i] = 0.0; }
+        nflag = 0;
         if (j >= nmine) return;
         const int4 t = tile_of(j);
-        nflag = t.z; nvcode = t.w;
+        nflag = t.z;
         const bool reg = is_regular(nflag);
         const int plo = t.y - K;
         const int* tr = sRow + (j & 1) * TL_ND;
@@ -373,32 +359,20 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
             if ((unsigned)(plo + plr[i]) >= (unsigned)tl[dlr[i]] || (unsigned)r >= (unsigned)a.nloc) continue;
             nrow[i] = r;
             nb[i] = a.b[r];
-            if (MODE == 1 && a.yold) nyo[i] = a.yold[r];
             if (!reg) {
                 ncode[i] = a.code[r];
-                if (MODE == 0) { nk0[i] = a.rowptr[r]; nk1[i] = a.rowptr[r + 1]; }
+                nk0[i] = a.rowptr[r]; nk1[i] = a.rowptr[r + 1];
             }
         }
     };
-    // second-level loads (depend on the template code): neighbour deltas, and for ChebSI the mass-matrix row
+    // second-level loads (depend on the template code): the neighbour deltas of the rows of a general tile
     auto load_meta2 = [&]() {
         const bool reg = is_regular(nflag);
 #pragma unroll
         for (int i = 0; i < TL_R; ++i) {
             dpk[i] = 0ull;
-            if (MODE == 1) {
-                md[i] = 1.0;
-#pragma unroll
-                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = 0.0;
-            }
             if (nrow[i] < 0) continue;
-            const int cd = reg ? nvcode : ncode[i];
-            if (!reg) dpk[i] = __ldg(a.tdelta + cd);
-            if (MODE == 1) {
-#pragma unroll
-                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = __ldg(a.tval + FCT_TPL_W * cd + jj);
-                md[i] = a.dscale * __ldg(a.tdiag + cd);
-            }
+            if (!reg) dpk[i] = __ldg(a.tdelta + ncode[i]);
         }
     };
     // the iterate of tile j's region -> iterate buffer j % 3; the caller guarantees that the buffer is free
@@ -420,7 +394,6 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
     };
     // the matrix rows of tile j's diagonals -> staging buffer (bounds loaded one tile earlier by load_seg_bounds)
     auto issue_L = [&](int j) {
-        if (MODE != 0) return;
         uint32_t tx = 0;
         const int c = warp + (TL_NT / 32) * lane;
         if (lane < 3 && c < TL_NC && j < nmine) {
@@ -454,25 +427,23 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
         const bool reg = is_regular(flag);
         int k0r[TL_R], lenr[TL_R];
 #pragma unroll
-        for (int i = 0; i < TL_R; ++i) { row[i] = nrow[i]; k0r[i] = nk0[i]; lenr[i] = nk1[i] - nk0[i]; br[i] = nb[i]; yo[i] = nyo[i]; }
+        for (int i = 0; i < TL_R; ++i) { row[i] = nrow[i]; k0r[i] = nk0[i]; lenr[i] = nk1[i] - nk0[i]; br[i] = nb[i]; }
         mbar_wait_bounded(&bar_full, (uint32_t)(j & 1));
-        if (MODE == 0) {
-            // staged matrix rows -> registers
+        // staged matrix rows -> registers
 #pragma unroll
-            for (int i = 0; i < TL_R; ++i) {
-                const int c = dlr[i] - 1;
-                if (reg) {
-                    const double* p = sL + c * SM::SEGCAP + sSh[c] + W * (plr[i] - 1);
+        for (int i = 0; i < TL_R; ++i) {
+            const int c = dlr[i] - 1;
+            if (reg) {
+                const double* p = sL + c * SM::SEGCAP + sSh[c] + W * (plr[i] - 1);
 #pragma unroll
-                    for (int jj = 0; jj < W; ++jj) Lr[i][jj] = (row[i] >= 0) ? p[jj] : 0.0;
-                } else {
+                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = (row[i] >= 0) ? p[jj] : 0.0;
+            } else {
 #pragma unroll
-                    for (int jj = 0; jj < W; ++jj) Lr[i][jj] = 0.0;
-                    if (row[i] < 0) continue;
-                    const double* p = sL + c * SM::SEGCAP + (k0r[i] - sKa[c]);
+                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = 0.0;
+                if (row[i] < 0) continue;
+                const double* p = sL + c * SM::SEGCAP + (k0r[i] - sKa[c]);
 #pragma unroll
-                    for (int jj = 0; jj < W; ++jj) Lr[i][jj] = (jj < lenr[i]) ? p[jj] : 0.0;
-                }
+                for (int jj = 0; jj < W; ++jj) Lr[i][jj] = (jj < lenr[i]) ? p[jj] : 0.0;
             }
         }
         if (j > 0) { rec0 = rec1; rec1 = rec2; rec2 = rec3; rec3 = fetch_rec(j + 3); recj = j; }
@@ -484,9 +455,9 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
         load_seg_bounds(j + 2);
         double* A = sX + (j % 3) * (TL_ND * TL_XS);
         double* B = sX + ((j + 2) % 3) * (TL_ND * TL_XS);
-        if (reg && (flag & TL_F_UP)) tl_passes<MODE, W, 1>(K, A, B, xi, ml, row, Lr, dpk, br, yo, md, a.om);
-        else if (reg) tl_passes<MODE, W, 2>(K, A, B, xi, ml, row, Lr, dpk, br, yo, md, a.om);
-        else tl_passes<MODE, W, 0>(K, A, B, xi, ml, row, Lr, dpk, br, yo, md, a.om);
+        if (reg && (flag & TL_F_UP)) tl_passes<W, 1>(K, A, B, xi, ml, row, Lr, dpk, br);
+        else if (reg) tl_passes<W, 2>(K, A, B, xi, ml, row, Lr, dpk, br);
+        else tl_passes<W, 0>(K, A, B, xi, ml, row, Lr, dpk, br);
         // the next tile's template data travels while this tile's interior is written back
         load_meta2();
         const double* fin = (K & 1) ? B : A;
@@ -499,27 +470,23 @@ __global__ void __launch_bounds__(TL_NT, 1) k_tile(const TileArgs a) {
             if (row[i] >= 0 && ml[i] >= K && row[i] >= ssel.out_rb && row[i] < ssel.out_re) {
                 const double v = fv[i];
                 a.xout[row[i]] = v;
-                if (MODE == 0 && row[i] >= a.own_rb && row[i] < a.own_re) {
+                if (row[i] >= a.own_rb && row[i] < a.own_re) {
                     delta = fmax(delta, fabs(v - pv[i]));
                     xa = fmax(xa, fabs(v));
-                } else if (MODE != 0 && a.yold_out) {
-                    a.yold_out[row[i]] = yo[i];
                 }
             }
         }
     }
-    if (MODE == 0) {
-        // stopping test input: ||x_K - x_{K-1}||_inf and ||x_K||_inf over the owned rows (k_jacobi_sweep_tpl's `check`)
-        delta = warp_max(delta);
-        xa = warp_max(xa);
-        if (lane == 0) { sred[0][warp] = delta; sred[1][warp] = xa; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < TL_NT / 32; ++w) { delta = fmax(delta, sred[0][w]); xa = fmax(xa, sred[1][w]); }
-            atomicMax(a.jstate + 0, (unsigned long long)__double_as_longlong(delta));
-            atomicMax(a.jstate + 1, (unsigned long long)__double_as_longlong(xa));
-            if (blockIdx.x == 0) atomicAdd(a.jstate + 4, (unsigned long long)K);
-        }
+    // stopping test input: ||x_K - x_{K-1}||_inf and ||x_K||_inf over the owned rows (k_jacobi_sweep_tpl's `check`)
+    delta = warp_max(delta);
+    xa = warp_max(xa);
+    if (lane == 0) { sred[0][warp] = delta; sred[1][warp] = xa; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < TL_NT / 32; ++w) { delta = fmax(delta, sred[0][w]); xa = fmax(xa, sred[1][w]); }
+        atomicMax(a.jstate + 0, (unsigned long long)__double_as_longlong(delta));
+        atomicMax(a.jstate + 1, (unsigned long long)__double_as_longlong(xa));
+        if (blockIdx.x == 0) atomicAdd(a.jstate + 4, (unsigned long long)K);
     }
 }
 
@@ -649,20 +616,20 @@ static int build_tile_list(fct_ctx* ctx, int K) {
     return 0;
 }
 
-template <int MODE, int W>
+template <int W>
 static int tile_set_attr() {
-    FCT_CUDA(cudaFuncSetAttribute(k_tile<MODE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<MODE, W>::BYTES));
+    FCT_CUDA(cudaFuncSetAttribute(k_tile<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileSmem<W>::BYTES));
     return 0;
 }
-template <int MODE, int W>
+template <int W>
 static void tile_launch_t(fct_ctx* ctx, const TileArgs& a, int grid) {
-    k_tile<MODE, W><<<grid, TL_THREADS, TileSmem<MODE, W>::BYTES, ctx->stream>>>(a);
+    k_tile<W><<<grid, TL_THREADS, TileSmem<W>::BYTES, ctx->stream>>>(a);
 }
 
 static int tiles_configure() {
     static bool done = false;
     if (done) return 0;
-    if (tile_set_attr<0, 7>() || tile_set_attr<0, 8>()) return 1;      // (MODE 1 of k_tile is superseded by k_cheb_tile)
+    if (tile_set_attr<7>() || tile_set_attr<8>()) return 1;
     done = true;
     return 0;
 }
@@ -734,8 +701,8 @@ static int fill_args(fct_ctx* ctx, int K, TileArgs& a) {
     a.n_cells = t->n_cells; a.total = (t->n_cells + 1) * (t->n_cells + 1); a.g0 = t->g0; a.nloc = ctx->n;
     a.own_rb = ctx->row_begin; a.own_re = ctx->row_end; a.ntiles = t->count[K]; a.tiles = t->list[K]; a.K = K;
     tile_out_range(ctx, K, &a.out_rb, &a.out_re);
-    a.rowptr = ctx->rowptr; a.code = ctx->tpl_code; a.tdelta = t->tdelta; a.tval = ctx->tpl_val; a.tdiag = ctx->tpl_diag;
-    a.Lv = nullptr; a.b = nullptr; a.xin = nullptr; a.yold = nullptr; a.xout = nullptr; a.yold_out = nullptr;
+    a.rowptr = ctx->rowptr; a.code = ctx->tpl_code; a.tdelta = t->tdelta;
+    a.Lv = nullptr; a.b = nullptr; a.xin = nullptr; a.xout = nullptr;
     a.jstate = ctx->jstate;
     a.kdev = nullptr;
     for (int k = 0; k < TL_KMAX; ++k) {
@@ -745,8 +712,6 @@ static int fill_args(fct_ctx* ctx, int K, TileArgs& a) {
             tile_out_range(ctx, k, &a.sel[k].out_rb, &a.sel[k].out_re);
         }
     }
-    for (int i = 0; i < TL_KMAX; ++i) a.om[i] = 0.0;
-    a.dscale = 1.0;
     return 0;
 }
 
@@ -766,7 +731,7 @@ int fct_tile_jacobi(fct_ctx* ctx, int K, const double* Lv, const double* b, cons
     int grid = most < ctx->tiles->sms ? most : ctx->tiles->sms;
     if (ctx->tile_grid_cap > 0 && grid > ctx->tile_grid_cap) grid = ctx->tile_grid_cap;
     if (grid <= 0) return 0;
-    if (ctx->max_row <= 7) tile_launch_t<0, 7>(ctx, a, grid); else tile_launch_t<0, 8>(ctx, a, grid);
+    if (ctx->max_row <= 7) tile_launch_t<7>(ctx, a, grid); else tile_launch_t<8>(ctx, a, grid);
     ctx->launches++;
     return 0;
 }
