@@ -118,3 +118,25 @@ def test_tiles_on_row_blocks_with_truncated_halo_rows(n, world, K):
         own = slice(lp.row_begin, lp.row_end)
         assert np.all(written[own] == 1) and written.sum() == lp.row_end - lp.row_begin
         assert np.allclose(out[own], ref[lp.R0:lp.R1], rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("n,world,K", [(40, 2, 4), (48, 3, 3)])
+def test_two_fused_launches_share_one_exchange_on_deep_halos(n, world, K):
+    """halo depth 2K (csrc/fct_tile.cu: tile_out_range): the first launch writes ring depth-K = every row whose K-ring lies
+    inside the local range, the second one follows WITHOUT an exchange and must give the owned rows of 2K global sweeps.
+    Rows the first launch does not write stay NaN here, so any read of a stale row by a row that matters would show."""
+    m, rowptr, colidx, vals, b, x = jacobi_system(n, seed=2)
+    A = sp.csr_matrix((vals, colidx, rowptr), shape=(m.nodes, m.nodes))
+    ref = x.copy()
+    for _ in range(2 * K):
+        ref = b - A @ ref
+    for rank in range(world):
+        lp = LocalProblem(rowptr.astype(np.int32), colidx.astype(np.int32), m.cells, m.dof_xy, rank, world, depth=2 * K, rect_n=n)
+        lr, lc, lv = lp.rowptr.astype(np.int64), lp.colidx.astype(np.int64), lp.scatter_values(vals)
+        mid_rb, mid_re = int(lp.ring_lo[K]), int(lp.ring_hi[K])              # ring depth-K of a depth-2K halo
+        mid, _ = emulate_launch(n, K, lp.G0, lr, lc, lv, lp.scatter(b), lp.scatter(x), mid_rb, mid_re)
+        assert not np.isnan(mid[mid_rb:mid_re]).any()
+        out, written = emulate_launch(n, K, lp.G0, lr, lc, lv, lp.scatter(b), mid, lp.row_begin, lp.row_end)
+        own = slice(lp.row_begin, lp.row_end)
+        assert np.all(written[own] == 1)
+        assert np.allclose(out[own], ref[lp.R0:lp.R1], rtol=0, atol=1e-15)
