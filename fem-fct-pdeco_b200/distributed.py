@@ -234,7 +234,7 @@ def mgpu_parity_check(cells, ns, rank, world, local_rank, depth=None, seed=5):
         dc, du, duh = cx.array(scatter(c.ravel())), cx.array(scatter(utr.ravel())), cx.array(scatter(uhat.ravel()))
         dp, dd = cx.empty(du.size), cx.empty(du.size)
         sw = cx.advdrift_state(dc, du, ns, dt)
-        cx.advdrift_adjoint(dc, du, duh, dp, ns, dt)
+        sw = (sw, cx.advdrift_adjoint(dc, du, duh, dp, ns, dt))
         cx.advdrift_gradient(dc, du, dp, dd, ns, 0.01)
         M = cx.static()[0]
         J = 0.5 * cx.norm_sq_Q(M, du, ns, dt, target=duh) + 0.005 * cx.norm_sq_Q(M, dc, ns, dt)
@@ -262,11 +262,28 @@ def mgpu_parity_check(cells, ns, rank, world, local_rank, depth=None, seed=5):
         u1, p1, d1 = [a.reshape(ns + 1, -1) for a in (u1, p1, d1)]
         res = {"cells": cells, "time_steps": ns, "ranks": world, "halo_depth": lp.depth,
                "u_equal": bool(np.array_equal(ug, u1)), "p_equal": bool(np.array_equal(pg, p1)),
-               "d_equal": bool(np.array_equal(dg, d1)), "J_rel": abs(J / J1 - 1), "sweeps": [int(sw), int(sw1)],
+               "d_equal": bool(np.array_equal(dg, d1)), "J_rel": abs(J / J1 - 1), "sweeps": [int(sw[0]), int(sw1[0])],
+               "adjoint_sweeps": [int(sw[1]), int(sw1[1])],
                "halo_rows": [int(lp.row_begin), int(lp.n - lp.row_end)],
                "host_path_equal": bool(int(flags[0].item())), "p2p_error_free": bool(int(flags[1].item()))}
-        res["ok"] = bool(res["u_equal"] and res["p_equal"] and res["d_equal"] and res["J_rel"] < 1e-13
-                         and res["host_path_equal"] and res["p2p_error_free"])
+        # The row arithmetic does not depend on the partition, so N ranks and one GPU give the same bits whenever their
+        # low-order solves stop after the same sweeps -- the default configuration (peer mailboxes, fused tile sweeps of the
+        # same depth on both sides).  A fallback configuration that tests convergence at other sweep counts (NCCL + graph:
+        # per-sweep kernels; halo depth < 4: shallower fused launches) may stop elsewhere: then the fields agree to the solver
+        # tolerance instead, and the check says which of the two it verified.
+        rel = [float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)) for a, b in ((ug, u1), (pg, p1), (dg, d1))]
+        res["max_rel"] = max(rel)
+        res["bit_identical"] = bool(res["u_equal"] and res["p_equal"] and res["d_equal"])
+        # same solver path on both sides?  fused tile sweeps of the same depth (N ranks: only with peer mailboxes or without the
+        # CUDA-graph loop, and never deeper than the halo), or per-sweep kernels on both
+        kj = int(os.environ.get("FCT_TILE_KJ", "4"))
+        fused1 = bool(ctx1.tiles_active())
+        fusedN = bool(ctx.tiles_active()) and (os.environ.get("FCT_NO_P2P", "0") != "1" or os.environ.get("FCT_NO_GRAPH", "0") == "1")
+        same_path = (fused1 and fusedN and min(kj, lp.depth) == kj) or (not fused1 and not fusedN)
+        res["same_solver_path"] = bool(same_path)
+        fields_ok = res["bit_identical"] if same_path else max(rel) <= 1e-12
+        res["verified"] = "bit-identical" if res["bit_identical"] else "1e-12 (different stopping points)"
+        res["ok"] = bool(fields_ok and res["J_rel"] < 1e-13 and res["host_path_equal"] and res["p2p_error_free"])
         if not res["ok"]:          # where do the fields differ?  (time level, global row, anti-diagonal, position, |diff|)
             n_c = cells
             lens = np.array([min(dd, 2 * n_c - dd) + 1 for dd in range(2 * n_c + 1)])
@@ -420,7 +437,7 @@ def bench_multi(args, rank, world, local_rank):
                          "frac": step_gb * value / world / peak, "traffic": None, "peak_source": peak_src,
                          "note": "per-GPU: App. E accounting bytes of an FCT step x steps/s / N (the single-GPU line carries "
                                  "the per-kernel roofline on actual bytes)"},
-            "mgpu_parity": mg, "mgpu_bit_identical": bool(mg.get("ok")),
+            "mgpu_parity": mg, "mgpu_bit_identical": bool(mg.get("ok") and mg.get("bit_identical")),
             "exchanges_per_fct_step": xch / max(1, (args.warmup + args.steps) * it.fct_steps_per_pass) if xch else None,
             "launches_per_fct_step_per_rank": lt.item() / world / fct_steps,
             "p2p_error": int(pe.item()),

@@ -392,8 +392,8 @@ def test_full_size_parity_vs_oracle_port_4096():
 
 
 def test_multi_gpu_matches_single_gpu():
-    """2-rank row-block partition (NCCL halo exchange) vs the single-GPU path: fields bit-identical.
-    Needs two visible GPUs (`gpurun --gpus 2`); skipped on a 1-GPU box."""
+    """2-rank row-block partition (deep halos, NVLink peer mailboxes) vs the single-GPU path in the default configuration:
+    fields bit-identical.  Needs two visible GPUs (`gpurun --gpus 2`); skipped on a 1-GPU box."""
     import os
     import subprocess
     import sys
@@ -404,6 +404,7 @@ def test_multi_gpu_matches_single_gpu():
            "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py"), "96"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MGPU_CHECK PASSED" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert '"bit_identical": true' in out.stdout, out.stdout[-2000:]
 
 
 def test_template_jacobi_modes(monkeypatch):
