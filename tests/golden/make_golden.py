@@ -457,8 +457,9 @@ def _loop_source(script_name, first_marker, last_marker):
     return "\n".join(l[4:] if l.startswith("    ") else l for l in script[i0:i1])
 
 
-def ref_script_cfg4():
-    """BASELINE config 4: the state and adjoint loops of Schnak_FCT_PDECO.py (:190-279) -- the script's own source lines, with
+def ref_script_cfg4(n=10, name="ref_cfg4.npz"):
+    """BASELINE config 4 (n = 50 is the script's own mesh, deltax = 0.02, with its own dt = 0.002 and T = 3 dt): the state and
+    adjoint loops of Schnak_FCT_PDECO.py (:190-279) -- the script's own source lines, with
     the time-dependent Expression wind, project(wind, W) and the div(w_h u) w form -- executed with the reference's helpers.py
     and legacy FCT_alg on oracle/fake_dolfin.py."""
     import contextlib
@@ -468,7 +469,7 @@ def ref_script_cfg4():
     hp = load_reference_helpers_on_fake_dolfin()
     ns_ = _script_namespace(hp, fd)
     body = _loop_source("Schnak_FCT_PDECO.py", "print('Solving state equations...')", "3. choose the descent direction")
-    n, num_steps, dt = 10, 3, 2e-3
+    num_steps, dt = 3, 2e-3
     mesh = RectMesh(n, 0.0, 1.0)
     V = fd.FunctionSpace(mesh)
     W = fd.VectorFunctionSpace(mesh)
@@ -492,12 +493,14 @@ def ref_script_cfg4():
         exec(compile(body, "Schnak_FCT_PDECO.py:loops", "exec"), ns_)
     out = dict(n=np.array([n]), ns=np.array([num_steps]), dt=np.array([dt]), u0=u0, v0=v0, c=ck, uhat_T=uhat_T, vhat_T=vhat_T,
                u=ns_["uk"].copy(), v=ns_["vk"].copy(), p=ns_["pk"].copy(), q=ns_["qk"].copy())
-    np.savez_compressed(os.path.join(HERE, "ref_cfg4.npz"), **out)
-    print("ref_cfg4.npz written; norms", *(float(np.linalg.norm(out[k])) for k in "uvpq"))
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, "written; norms", *(float(np.linalg.norm(out[k])) for k in "uvpq"))
 
 
-def ref_script_cfg3():
-    """BASELINE config 3: the state and adjoint loops of chemotaxis_mimura_FCT_PGD.py (:157-225) -- the script's own source
+def ref_script_cfg3(n=8, a2=4.0, dt=0.02, num_steps=3, sample=1, out_name="ref_cfg3.npz"):
+    """BASELINE config 3 (n = 128, a2 = 16, dt = 0.1: the script's own mesh and time step; `sample` > 1 stores every sample-th
+    DoF of each time level plus the norms of the full fields, so that the 129^2 fixture stays small): the state and adjoint
+    loops of chemotaxis_mimura_FCT_PGD.py (:157-225) -- the script's own source
     lines with the reference's mimura_data_helpers.py and the legacy form builders / FCT_alg of old_helpers.py -- executed on
     oracle/fake_dolfin.py."""
     import contextlib
@@ -528,8 +531,7 @@ def ref_script_cfg3():
             else:
                 sys.modules[k] = v_
     body = _loop_source("chemotaxis_mimura_FCT_PGD.py", "print('Solving state equations...')", "3. choose the descent direction")
-    n, num_steps, dt = 8, 3, 0.02
-    a1, a2 = 0.0, 4.0
+    a1 = 0.0
     delta, Dm, Df, chi = 32, 0.0625, 1, 8.5
     mesh = RectMesh(n, a1, a2)
     V = fd.FunctionSpace(mesh)
@@ -554,12 +556,29 @@ def ref_script_cfg3():
     out = dict(n=np.array([n]), ns=np.array([num_steps]), dt=np.array([dt]), box=np.array([a1, a2]), m0=m0, f0=f0, c=ck,
                mhat_T=mhat_T, fhat_T=fhat_T, m=ns_["mk"].copy(), f=ns_["fk"].copy(), p=ns_["pk"].copy(), q=ns_["qk"].copy(),
                params=np.array([delta, Dm, Df, chi], dtype=np.float64))
-    np.savez_compressed(os.path.join(HERE, "ref_cfg3.npz"), **out)
-    print("ref_cfg3.npz written; norms", *(float(np.linalg.norm(out[k])) for k in "mfpq"))
+    print(out_name, "norms", *(float(np.linalg.norm(out[k])) for k in "mfpq"))
+    if sample > 1:
+        # inputs other than m0 are regenerated by the test from the same seeded generator (default_rng(41): c, then the two
+        # targets); outputs are stored at every sample-th DoF of each time level, with the 2-norms of the full fields
+        full = {k: out[k] for k in "mfpq"}
+        out = dict(n=out["n"], ns=out["ns"], dt=out["dt"], box=out["box"], params=out["params"], sample=np.array([sample]),
+                   seed=np.array([41]), m0_s=m0[::sample])
+        for k, a in full.items():
+            out[k + "_s"] = a.reshape(num_steps + 1, nodes)[:, ::sample].copy()
+            out[k + "_norm"] = np.linalg.norm(a.reshape(num_steps + 1, nodes), axis=1)
+    np.savez_compressed(os.path.join(HERE, out_name), **out)
+    print(out_name, "written")
+
+
+def ref_script_full_sizes():
+    """configs 3 and 4 on the meshes BASELINE names: 129^2 DoF on [0,16]^2 with dt = 0.1 (two time levels, sampled), 51^2 DoF
+    with dt = 0.002 and the script's own three time levels"""
+    ref_script_cfg4(n=50, name="ref_cfg4_K.npz")
+    ref_script_cfg3(n=128, a2=16.0, dt=0.1, num_steps=2, sample=8, out_name="ref_cfg3_C.npz")
 
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ref_data", "ref_fct_cases", "ref_legacy", "ref_armijo", "ref_loops", "ref_script_cfg2",
-                             "ref_script_cfg3", "ref_script_cfg4"]
+                             "ref_script_cfg3", "ref_script_cfg4", "ref_script_full_sizes"]
     for name in which:
         globals()[name]()

@@ -26,8 +26,9 @@ def _quiet(fn, *a, **k):
         return fn(*a, **k)
 
 
-def test_script_schnak_fct_pdeco_cfg4():
-    g = dict(np.load(os.path.join(GOLDEN, "ref_cfg4.npz")))
+@pytest.mark.parametrize("fixture", ["ref_cfg4.npz", "ref_cfg4_K.npz"])      # 11^2 DoF; K = the script's own 51^2-DoF mesh
+def test_script_schnak_fct_pdeco_cfg4(fixture):
+    g = dict(np.load(os.path.join(GOLDEN, fixture)))
     n, num_steps, dt = int(g["n"][0]), int(g["ns"][0]), float(g["dt"][0])
     a1, a2 = 0, 1
     beta, c_lower, c_upper = 0.1, -1, 1
@@ -111,11 +112,26 @@ def test_script_schnak_fct_pdeco_cfg4():
                               optim='finaltime', example='no such example')
 
 
-def test_script_chemotaxis_mimura_pgd_cfg3():
-    g = dict(np.load(os.path.join(GOLDEN, "ref_cfg3.npz")))
+@pytest.mark.parametrize("fixture", ["ref_cfg3.npz", "ref_cfg3_C.npz"])      # 9^2 DoF; C = the script's own 129^2 mesh, dt
+def test_script_chemotaxis_mimura_pgd_cfg3(fixture):
+    g = dict(np.load(os.path.join(GOLDEN, fixture)))
     n, num_steps, dt = int(g["n"][0]), int(g["ns"][0]), float(g["dt"][0])
     a1, a2 = g["box"]
     delta, Dm, Df, chi = g["params"]
+    sampled = "sample" in g
+    if sampled:
+        # the 129^2 fixture holds every sample-th DoF of each time level and the norms of the full fields; its inputs are
+        # regenerated here exactly as tests/golden/make_golden.py:ref_script_cfg3 draws them
+        nodes_ = (n + 1) ** 2
+        rng = np.random.default_rng(int(g["seed"][0]))
+        m_ = RectMeshP1(n, a1, a2)
+        g["m0"] = hp.reorder_vector_to_dof(mimura_data_helpers.m_initial_condition(a1, a2, (a2 - a1) / n).reshape(nodes_), 1, nodes_,
+                                           m_.vertex_to_dof)
+        assert np.array_equal(g["m0"][::int(g["sample"][0])], g["m0_s"])
+        g["f0"] = 1 / 32 * np.ones(nodes_)
+        g["c"] = 0.5 + rng.random((num_steps + 1) * nodes_)
+        g["mhat_T"] = g["m0"] * (1 + 0.05 * rng.random(nodes_))
+        g["fhat_T"] = g["f0"] * (1 + 0.05 * rng.random(nodes_))
     beta, c_lower, c_upper = 1, 0, 1.5
     T = num_steps * dt
     mesh = RectMeshP1(n, a1, a2)
@@ -165,8 +181,15 @@ def test_script_chemotaxis_mimura_pgd_cfg3():
         return pk, qk
 
     pk, qk = _quiet(state_and_adjoint)
-    assert rel_l2(mk, g["m"]) < 1e-11 and rel_l2(fk, g["f"]) < 1e-11
-    assert rel_l2(pk, g["p"]) < 1e-11 and rel_l2(qk, g["q"]) < 1e-11
+    if sampled:
+        st = int(g["sample"][0])
+        for name, a in (("m", mk), ("f", fk), ("p", pk), ("q", qk)):
+            a = a.reshape(num_steps + 1, nodes)
+            assert rel_l2(a[:, ::st], g[name + "_s"]) < 1e-11, name
+            assert np.allclose(np.linalg.norm(a, axis=1), g[name + "_norm"], rtol=1e-12, atol=0), name
+    else:
+        assert rel_l2(mk, g["m"]) < 1e-11 and rel_l2(fk, g["f"]) < 1e-11
+        assert rel_l2(pk, g["p"]) < 1e-11 and rel_l2(qk, g["q"]) < 1e-11
     # :231-256: descent direction, the lost line search and cost (re-specified), projection, stopping criteria
     dk = -(beta * ck - qk * mk)
     cost_fun_k = _quiet(hp.cost_functional_proj_FT, mk, fk, ck, dk, 0, mhat_T, fhat_T, num_steps, dt, M, c_lower, c_upper, beta)
