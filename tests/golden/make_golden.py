@@ -388,8 +388,9 @@ def ref_loops():
     print("ref_loops.npz written:", len(out), "arrays")
 
 
-def ref_script_cfg2():
-    """BASELINE config 2: the state / adjoint / gradient loops of advection_solidbody_FCT_PDECO_alltime.py (:206-275, the shape
+def ref_script_cfg2(n=10, dt=2e-3, sample=1, out_name="ref_cfg2.npz"):
+    """BASELINE config 2 (n = 80, dt = 0.001 are the script's own mesh and time step; `sample` > 1 stores every sample-th DoF of
+    each time level plus the norms of the full fields): the state / adjoint / gradient loops of advection_solidbody_FCT_PDECO_alltime.py (:206-275, the shape
     of the 4096^2 benchmark) -- the script's own source lines, compiled as they stand and executed in a namespace that holds
     the reference's helpers.py (on oracle/fake_dolfin.py), the legacy FCT_alg of old_helpers.py (its source, compiled as it
     stands) and the script's set-up variables on a small mesh.  Pins the drift-control operators Adrift1 / Adrift2, the
@@ -407,7 +408,7 @@ def ref_script_cfg2():
     i0 = next(i for i, l in enumerate(script) if "print('Solving state equation...')" in l)
     i1 = next(i for i, l in enumerate(script) if "4. step size control" in l) - 1          # the banner line above it
     body = "\n".join(l[4:] if l.startswith("    ") else l for l in script[i0:i1])           # the loops live inside `while`
-    n, num_steps, dt, beta, eps = 10, 3, 2e-3, 0.01, 0
+    num_steps, beta, eps = 3, 0.01, 0
     mesh = RectMesh(n, -1.0, 1.0)
     V = fd.FunctionSpace(mesh)
     nodes = mesh.nodes
@@ -429,8 +430,16 @@ def ref_script_cfg2():
         exec(compile(body, "advection_solidbody_FCT_PDECO_alltime.py:loops", "exec"), ns_)
     out = dict(n=np.array([n]), ns=np.array([num_steps]), dt=np.array([dt]), beta=np.array([beta]), u0=u0, c=ck, uhat=uhat_all,
                u=ns_["uk"].copy(), p=ns_["pk"].copy(), d=ns_["dk"].copy())
-    np.savez_compressed(os.path.join(HERE, "ref_cfg2.npz"), **out)
-    print("ref_cfg2.npz written; |u|, |p|, |d| =", *(float(np.linalg.norm(out[k])) for k in "upd"))
+    print(out_name, "|u|, |p|, |d| =", *(float(np.linalg.norm(out[k])) for k in "upd"))
+    if sample > 1:
+        # u0 is a closed form of the DoF coordinates and c, uhat come from default_rng(21) (c first): the test regenerates them
+        full = {k: out[k] for k in "upd"}
+        out = dict(n=out["n"], ns=out["ns"], dt=out["dt"], beta=out["beta"], sample=np.array([sample]), seed=np.array([21]))
+        for k, a in full.items():
+            out[k + "_s"] = a.reshape(num_steps + 1, nodes)[:, ::sample].copy()
+            out[k + "_norm"] = np.linalg.norm(a.reshape(num_steps + 1, nodes), axis=1)
+    np.savez_compressed(os.path.join(HERE, out_name), **out)
+    print(out_name, "written")
 
 
 def _script_namespace(hp, fd):
@@ -571,8 +580,9 @@ def ref_script_cfg3(n=8, a2=4.0, dt=0.02, num_steps=3, sample=1, out_name="ref_c
 
 
 def ref_script_full_sizes():
-    """configs 3 and 4 on the meshes BASELINE names: 129^2 DoF on [0,16]^2 with dt = 0.1 (two time levels, sampled), 51^2 DoF
-    with dt = 0.002 and the script's own three time levels"""
+    """configs 2, 3 and 4 on the meshes BASELINE names: 81^2 DoF on [-1,1]^2 (three time levels, sampled), 129^2 DoF on
+    [0,16]^2 with dt = 0.1 (two time levels, sampled), 51^2 DoF with dt = 0.002 and the script's own three time levels"""
+    ref_script_cfg2(n=80, dt=0.001, sample=4, out_name="ref_cfg2_M.npz")
     ref_script_cfg4(n=50, name="ref_cfg4_K.npz")
     ref_script_cfg3(n=128, a2=16.0, dt=0.1, num_steps=2, sample=8, out_name="ref_cfg3_C.npz")
 

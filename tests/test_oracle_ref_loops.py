@@ -129,18 +129,22 @@ def test_reference_chtxs_loop_on_fake_dolfin_reproduces_shipped_data(ref_data):
         assert rel_l2(var2.reshape(ns + 1, -1)[k], ref_data["chtxs_f"][k]) < 1e-13
 
 
-def test_config2_drift_loops_vs_reference_script():
+@pytest.mark.parametrize("fixture", ["ref_cfg2.npz", "ref_cfg2_M.npz"])      # 11^2 DoF; M = the script's own 81^2 mesh, dt
+def test_config2_drift_loops_vs_reference_script(fixture):
     """BASELINE config 2 / 5: oracle AdvectionDriftPDECO and its C/OpenMP twin against the loops of
-    advection_solidbody_FCT_PDECO_alltime.py:206-275 executed from the script's own source (ref_cfg2.npz)"""
+    advection_solidbody_FCT_PDECO_alltime.py:206-275 executed from the script's own source"""
+    from conftest import cfg2_inputs, golden_field_error
     from oracle import pdeco_numpy as drv
     from oracle.fct_c import CDriftProblem
-    g = dict(np.load(os.path.join(GOLDEN, "ref_cfg2.npz")))
+    g = dict(np.load(os.path.join(GOLDEN, fixture)))
     n, ns, dt = int(g["n"][0]), int(g["ns"][0]), float(g["dt"][0])
     orc = drv.AdvectionDriftPDECO(n, -1.0, 1.0, beta=float(g["beta"][0]))
-    U, UH = g["u"].reshape(ns + 1, -1), g["uhat"].reshape(ns + 1, -1)
-    assert rel_l2(orc.state(g["c"], g["u0"], ns, dt).ravel(), g["u"]) < 1e-13
-    assert rel_l2(orc.adjoint(g["c"], U, UH, ns, dt).ravel(), g["p"]) < 1e-13
-    assert rel_l2(orc.gradient(g["c"], U, g["p"].reshape(ns + 1, -1), ns).ravel(), g["d"]) < 1e-13
+    u0, c, uhat = cfg2_inputs(g, orc.mesh.dof_xy)
+    U = orc.state(c, u0, ns, dt)
+    assert golden_field_error(g, "u", U) < 1e-13
+    P = orc.adjoint(c, U, uhat.reshape(ns + 1, -1), ns, dt)
+    assert golden_field_error(g, "p", P) < 1e-12
+    assert golden_field_error(g, "d", orc.gradient(c, U, P, ns)) < 1e-12
     cprob = CDriftProblem(n, -1.0, 1.0)               # the CPU baseline / full-size parity checker of bench.py
-    uc, _ = cprob.state(g["c"], g["u0"], ns, dt)
-    assert rel_l2(uc.ravel(), g["u"]) < 1e-12
+    uc, _ = cprob.state(c, u0, ns, dt)
+    assert golden_field_error(g, "u", uc) < 1e-12
