@@ -201,3 +201,38 @@ def test_manufactured_solution_projected_gradient_iterations():
     # what the iteration must do is leave the initial cost far behind and move the control towards the exact one every time.
     assert cost[1] < 0.05 * cost[0] and all(c < 0.05 * cost[0] for c in cost[1:]), (cost, steps, dist)
     assert all(b < a for a, b in zip(dist, dist[1:])), (cost, steps, dist)
+
+
+def test_final_time_line_search_call_shape():
+    """advection_FCT_PDECO_finaltime_exact.py:230, 296-297, 374-385: the final-time generation of the legacy calls --
+    cost_functional_proj_FT(u, 0, c, 0, 0, uhat_T, zeros, ...), p(T) = uhat_T - u(T) with a homogeneous adjoint, and
+    armijo_line_search(u, p, w, c, d, uhat_T, ..., cost_fun_k, optim='finaltime') returning (s, u + s w)."""
+    s = _quiet(Setup, 10, 0.1)
+    nodes, ns, dt = s.nodes, s.num_steps, s.dt
+    L = (ns + 1) * nodes
+    zeros_nt = np.zeros(L)
+    uhat_T = s.u_ex[ns * nodes:]
+    ck = np.zeros(L)
+    uk = _quiet(s.state, ck)
+    cost_fun_k = _quiet(hp.cost_functional_proj_FT, uk, zeros_nt, ck, zeros_nt, 0, uhat_T, np.zeros(nodes), ns, dt, s.M, C_LO, C_UP, BETA)
+    assert cost_fun_k == _quiet(hp.cost_functional, uk, uhat_T, ck, ns, dt, s.M, BETA, optim="finaltime")
+    pk = np.zeros(L)
+    pk[ns * nodes:] = uhat_T - uk[ns * nodes:]
+    for i in reversed(range(0, ns)):
+        start, end = i * nodes, (i + 1) * nodes
+        pk[start:end] = _quiet(hp.FCT_alg, s.A_p, np.zeros(nodes), pk[end:end + nodes], dt, nodes, s.M, s.M_Lump, s.dof_neighbors)
+    dk = -(BETA * ck - pk)
+    wk = np.zeros(L)
+    for i in range(1, ns + 1):
+        start, end = i * nodes, (i + 1) * nodes
+        wk[start:end] = _quiet(hp.FCT_alg, s.A_u, s.load(dk[start:end]), wk[start - nodes:start], dt, nodes, s.M, s.M_Lump,
+                               s.dof_neighbors)
+    sk, u_inc = _quiet(hp.armijo_line_search, uk, pk, wk, ck, dk, uhat_T, ns, dt, s.M, C_LO, C_UP, BETA, cost_fun_k,
+                       optim='finaltime')
+    assert 0 < sk <= 1 and np.array_equal(u_inc, uk + sk * wk)
+    ckp1 = np.clip(ck + sk * dk, C_LO, C_UP)
+    cost_fun_kp1 = _quiet(hp.cost_functional, u_inc, uhat_T, ckp1, ns, dt, s.M, BETA, optim='finaltime')
+    dif = _quiet(hp.L2_norm_sq_Q, ckp1 - ck, ns, dt, s.M)
+    assert sk == 2.0 ** -9 or cost_fun_kp1 - cost_fun_k <= -1e-4 / sk * dif        # Armijo condition, or max_iter reached
+    with pytest.raises(ValueError):
+        hp.armijo_line_search(uk, pk, wk, ck, dk, uhat_T, ns, dt, s.M, C_LO, C_UP, BETA, cost_fun_k, optim='sometime')
