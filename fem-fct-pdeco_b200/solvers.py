@@ -269,7 +269,7 @@ def solve_adjoint_nonlinear_equation(uk, uhat_T, pk, T, V, nodes, num_steps, dt,
 def solve_chtxs_system(control, var1, var2, V, nodes, num_steps, dt, dof_neighbors, control_fun=None,
                        show_plots=False, vertex_to_dof=None, generation_mode=False, output_dir=None, rescaling=1 / 10):
     """helpers.py:1250-1385"""
-    dev = _Dev(V, nodes); ctx = dev.ctx
+    dev = _Dev(V, nodes)
     if generation_mode:
         if len(var1) != nodes or len(var2) != nodes or len(control) != nodes:
             raise ValueError(f"Generation mode, the input vectors should be of length {nodes}")
@@ -420,7 +420,7 @@ _DEVICE_FORWARD = {solve_nonlinear_equation: _forward_nonlinear_dev, solve_schna
 def _cost_device(dev, d1, d_t1, d_cinc, num_steps, dt, beta, optim, d2=None, d_t2=None):
     """cost_functional (helpers.py:383-441) on device trajectories: the same kernels and summation order as the numpy-facing
     shim, without the uploads"""
-    ctx, n = dev.ctx, dev.ctx.n
+    ctx = dev.ctx
     if optim == "alltime":
         print("Calculating L^2(Q)-norm...")
         func = 0.5 * ctx.norm_sq_Q(dev.M, d1, num_steps, dt, target=d_t1)
