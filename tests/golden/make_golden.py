@@ -579,6 +579,50 @@ def ref_script_cfg3(n=8, a2=4.0, dt=0.02, num_steps=3, sample=1, out_name="ref_c
     print(out_name, "written")
 
 
+def ref_script_refactored_nonlinear():
+    """the projected-gradient loop of nonlinear_FCT_PDECO_refactored.py (:105-210) -- the script's own source
+    lines: initial state / adjoint solve, dk = -(beta ck - pk), armijo_line_search_ref with hp.solve_nonlinear_equation as
+    the callback, adjoint solve, cost_functional / rel_err stopping test, the fail / restart bookkeeping -- executed with
+    the reference's helpers.py on oracle/fake_dolfin.py for two iterations on a 10 x 10 mesh (the plotting calls of the
+    script are replaced by no-ops; the target is synthetic, the script reads its own from a CSV)."""
+    import contextlib
+    import io
+    import time
+    import types
+    from oracle import fake_dolfin as fd
+    from oracle.ref_loader import load_reference_helpers_on_fake_dolfin
+    hp = load_reference_helpers_on_fake_dolfin()
+    script = open(os.path.join(REFERENCE_DIR, "nonlinear_FCT_PDECO_refactored.py")).read().splitlines()
+    i0 = next(i for i, l in enumerate(script) if l.startswith("vec_length = (num_steps + 1) * nodes"))
+    i1 = next(i for i, l in enumerate(script) if "Save results" in l)
+    body = "\n".join(script[i0:i1])
+    hp_ns = types.SimpleNamespace(**{k: v for k, v in vars(hp).items() if not k.startswith("__")})
+    hp_ns.plot_nonlinear_solution = lambda *a, **k: None
+    hp_ns.plot_progress = lambda *a, **k: None
+    n, num_steps, dt = 10, 4, 1e-3
+    a1, a2 = 0, 1
+    mesh = RectMesh(n, float(a1), float(a2))
+    V = fd.FunctionSpace(mesh)
+    nodes = mesh.nodes
+    v2d = np.array(mesh.vertex_to_dof)
+    u, v = fd.TrialFunction(V), fd.TestFunction(V)
+    M = hp.assemble_sparse(u * v * fd.dx)
+    u0 = hp.nonlinear_equation_IC(a1, a2, 1.0 / n, nodes, v2d)
+    rng = np.random.default_rng(51)
+    uhat_T = u0 * (0.6 + 0.2 * rng.random(nodes))
+    ns_ = dict(np=np, hp=hp_ns, time=time, a1=a1, a2=a2, dt=dt, T=num_steps * dt, T_data=num_steps * dt, num_steps=num_steps,
+               nodes=nodes, V=V, M=M, u0=u0, uhat_T=uhat_T, uhat_T_re=None, vertex_to_dof=v2d, dof_neighbors=mesh.dof_neighbors(),
+               beta=1e-1, c_lower=-1, c_upper=1, optim="finaltime", tol=1e-4, max_iter_armijo=5, max_iter_GD=2,
+               produce_plots=False, out_folder=None)
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(body, "nonlinear_FCT_PDECO_refactored.py:105-210", "exec"), ns_)
+    out = dict(n=np.array([n]), ns=np.array([num_steps]), dt=np.array([dt]), u0=u0, uhat_T=uhat_T, u=ns_["uk"].copy(),
+               p=ns_["pk"].copy(), c=ns_["ck"].copy(), d=ns_["dk"].copy(), cost=np.array(ns_["cost_fun_vals"]),
+               armijo_its=np.array(ns_["armijo_its"]), it=np.array([ns_["it"]]), stop_crit=np.array([ns_["stop_crit"]]))
+    np.savez_compressed(os.path.join(HERE, "ref_pgd_nonlinear.npz"), **out)
+    print("ref_pgd_nonlinear.npz written; cost", out["cost"], "armijo its", out["armijo_its"], "it", out["it"])
+
+
 def ref_script_full_sizes():
     """configs 2, 3 and 4 on the meshes BASELINE names: 81^2 DoF on [-1,1]^2 (three time levels, sampled), 129^2 DoF on
     [0,16]^2 with dt = 0.1 (two time levels, sampled), 51^2 DoF with dt = 0.002 and the script's own three time levels"""
@@ -589,6 +633,6 @@ def ref_script_full_sizes():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ref_data", "ref_fct_cases", "ref_legacy", "ref_armijo", "ref_loops", "ref_script_cfg2",
-                             "ref_script_cfg3", "ref_script_cfg4", "ref_script_full_sizes"]
+                             "ref_script_cfg3", "ref_script_cfg4", "ref_script_full_sizes", "ref_script_refactored_nonlinear"]
     for name in which:
         globals()[name]()

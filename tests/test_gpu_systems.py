@@ -230,3 +230,72 @@ def test_reference_loops_chemotaxis(loops):
         _quiet(hp.solve_adjoint_chtxs_system, g["chtxs_m"].copy(), g["chtxs_f"].copy(), mh, fh, pk, qk, g["chtxs_c"], ns * dt, V,
                nodes, ns, dt, mesh.dof_neighbors(), optim)
         assert rel_l2(pk, g[f"chtxs_p_{tag}"]) < 1e-11 and rel_l2(qk, g[f"chtxs_q_{tag}"]) < 1e-11, optim
+
+
+def test_refactored_nonlinear_pgd_script_loop():
+    """the projected-gradient loop of nonlinear_FCT_PDECO_refactored.py:105-210 written against the drop-in
+    `hp` (same calls, same order, same fail / restart bookkeeping), against the run of the reference script's OWN source
+    lines with the reference's helpers.py on oracle/fake_dolfin.py (tests/golden/ref_pgd_nonlinear.npz): costs within 1e-9,
+    state / adjoint / control / direction within 1e-11, the same number of line-search trials."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "ref_pgd_nonlinear.npz")))
+    n, num_steps, dt = int(g["n"][0]), int(g["ns"][0]), float(g["dt"][0])
+    mesh, V = _space(n)
+    nodes = V.dim()
+    vertex_to_dof = vertex_to_dof_map(V)
+    dof_neighbors = hp.find_node_neighbours(mesh, nodes, vertex_to_dof)
+    from fem_fct_pdeco_b200.forms import TestFunction, TrialFunction, dx
+    M = hp.assemble_sparse(TrialFunction(V) * TestFunction(V) * dx)
+    a1, a2, T = 0, 1, num_steps * dt
+    beta, c_lower, c_upper, optim, tol, max_iter_armijo, max_iter_GD = 1e-1, -1, 1, "finaltime", 1e-4, 5, 2
+    u0 = hp.nonlinear_equation_IC(a1, a2, 1.0 / n, nodes, vertex_to_dof)
+    assert np.array_equal(u0, g["u0"])
+    uhat_T = g["uhat_T"]
+
+    def script():
+        vec_length = (num_steps + 1) * nodes
+        ck = np.zeros(vec_length)
+        uk = np.zeros(vec_length)
+        uk[:nodes] = u0
+        uk, _ = hp.solve_nonlinear_equation(ck, uk, None, V, nodes, num_steps, dt, dof_neighbors)
+        pk = np.zeros(vec_length)
+        pk = hp.solve_adjoint_nonlinear_equation(uk, uhat_T, pk, T, V, nodes, num_steps, dt, dof_neighbors)
+        cost_fun_old = hp.cost_functional(uk, uhat_T, ck, num_steps, dt, M, beta, optim)
+        cost_fun_new = (2 + tol) * cost_fun_old
+        stop_crit = hp.rel_err(cost_fun_new, cost_fun_old)
+        dk = np.zeros(vec_length)
+        it = fail_count = fail_restart_count = 0
+        fail_pass = False
+        cost_fun_vals, armijo_its = [cost_fun_old], []
+        while (stop_crit >= tol or fail_pass) and it < max_iter_GD:
+            dk = -(beta * ck - pk)
+            uk, ck, iters = hp.armijo_line_search_ref(
+                uk, ck, dk, uhat_T, num_steps, dt, c_lower, c_upper, beta, cost_fun_old, nodes, optim, V,
+                dof_neighbors=dof_neighbors, nonlinear_solver=hp.solve_nonlinear_equation, max_iter=max_iter_armijo)
+            pk = hp.solve_adjoint_nonlinear_equation(uk, uhat_T, pk, T, V, nodes, num_steps, dt, dof_neighbors)
+            if iters == max_iter_armijo:
+                fail_count += 1
+                fail_pass = True
+                if fail_count == 3:
+                    break
+            elif fail_count > 0:
+                fail_count = 0
+                fail_restart_count += 1
+                fail_pass = False
+                if fail_restart_count == 5:
+                    break
+            cost_fun_new = hp.cost_functional(uk, uhat_T, ck, num_steps, dt, M, beta, optim)
+            stop_crit = hp.rel_err(cost_fun_new, cost_fun_old)
+            cost_fun_vals.append(cost_fun_new)
+            armijo_its.append(iters)
+            it += 1
+            cost_fun_old = cost_fun_new
+        return uk, pk, ck, dk, cost_fun_vals, armijo_its, it, stop_crit
+
+    uk, pk, ck, dk, cost_fun_vals, armijo_its, it, stop_crit = _quiet(script)
+    assert it == int(g["it"][0]) and armijo_its == list(g["armijo_its"])
+    assert np.allclose(cost_fun_vals, g["cost"], rtol=1e-9, atol=0)
+    assert abs(stop_crit - float(g["stop_crit"][0])) <= 1e-6 * abs(float(g["stop_crit"][0]))
+    for name, a in (("u", uk), ("p", pk), ("c", ck), ("d", dk)):
+        assert rel_l2(a, g[name]) < 1e-11, name
