@@ -623,6 +623,74 @@ def ref_script_refactored_nonlinear():
     print("ref_pgd_nonlinear.npz written; cost", out["cost"], "armijo its", out["armijo_its"], "it", out["it"])
 
 
+def _exec_refactored_pgd(script_name, ns_):
+    """executes lines `vec_length = ...` .. `Save results` of a *_refactored.py script (its projected-gradient loop) in ns_,
+    with the reference's helpers.py on oracle/fake_dolfin.py as `hp` (plotting entry points replaced by no-ops)"""
+    import contextlib
+    import io
+    import time
+    import types
+    from oracle.ref_loader import load_reference_helpers_on_fake_dolfin
+    hp = load_reference_helpers_on_fake_dolfin()
+    script = open(os.path.join(REFERENCE_DIR, script_name)).read().splitlines()
+    i0 = next(i for i, l in enumerate(script) if l.startswith("vec_length = (num_steps + 1) * nodes"))
+    i1 = next(i for i, l in enumerate(script) if "Save results" in l)
+    hp_ns = types.SimpleNamespace(**{k: v for k, v in vars(hp).items() if not k.startswith("__")})
+    for name in ("plot_nonlinear_solution", "plot_two_var_solution", "plot_progress"):
+        setattr(hp_ns, name, lambda *a, **k: None)
+    ns_.update(np=np, hp=hp_ns, time=time, produce_plots=False, out_folder=None)
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile("\n".join(script[i0:i1]), script_name + ":pgd-loop", "exec"), ns_)
+    return hp, ns_
+
+
+def ref_script_refactored_two_species():
+    """The projected-gradient loops of Schnak_FCT_PDECO_refactored.py (:122-246, final-time, dk = -(beta ck - gamma/r pk)) and
+    chemotaxis_FCT_PDECO_AT_refactored.py (:122-257, all-time, dk = -(beta ck - qk uk / r), line search with gam / s0) -- the
+    scripts' own source lines with the reference's helpers.py on oracle/fake_dolfin.py, two iterations on a 10 x 10 mesh,
+    synthetic targets."""
+    from oracle import fake_dolfin as fd
+    from oracle.ref_loader import load_reference_helpers_on_fake_dolfin
+    hp = load_reference_helpers_on_fake_dolfin()
+    n, a1, a2 = 10, 0, 1
+    mesh = RectMesh(n, float(a1), float(a2))
+    V = fd.FunctionSpace(mesh)
+    nodes = mesh.nodes
+    v2d = np.array(mesh.vertex_to_dof)
+    M = hp.assemble_sparse(fd.TrialFunction(V) * fd.TestFunction(V) * fd.dx)
+    base = dict(a1=a1, a2=a2, nodes=nodes, V=V, M=M, mesh=mesh, dx=1.0 / n, vertex_to_dof=v2d, dof_neighbors=mesh.dof_neighbors())
+    # ---- Schnakenberg, final time ----
+    rng = np.random.default_rng(61)
+    num_steps, dt = 4, 5e-4
+    u0, v0 = hp.schnak_sys_IC(a1, a2, 1.0 / n, nodes, v2d)
+    Du, Dv, true_control, c_b, gamma, omega1, omega2, wind = hp.get_schnak_sys_params()
+    uhat_T, vhat_T = u0 * (1 + 0.1 * rng.random(nodes)), v0 * (1 + 0.1 * rng.random(nodes))
+    _, ns_ = _exec_refactored_pgd("Schnak_FCT_PDECO_refactored.py", dict(
+        base, dt=dt, T=num_steps * dt, T_data=num_steps * dt, num_steps=num_steps, u0=u0, v0=v0, uhat_T=uhat_T, vhat_T=vhat_T,
+        uhat_T_re=None, vhat_T_re=None, gamma=gamma, rescaling=1, beta=1e-1, c_lower=0, c_upper=10, optim="finaltime", tol=1e-3,
+        max_iter_armijo=10, max_iter_GD=2))
+    out = dict(n=np.array([n]), s_ns=np.array([num_steps]), s_dt=np.array([dt]), s_u0=u0, s_v0=v0, s_uhat=uhat_T, s_vhat=vhat_T,
+               s_u=ns_["uk"].copy(), s_v=ns_["vk"].copy(), s_p=ns_["pk"].copy(), s_q=ns_["qk"].copy(), s_c=ns_["ck"].copy(),
+               s_cost=np.array(ns_["cost_fun_vals"]), s_its=np.array(ns_["armijo_its"]), s_it=np.array([ns_["it"]]))
+    print("Schnak: cost", out["s_cost"], "armijo its", out["s_its"], "it", out["s_it"])
+    # ---- chemotaxis, all time ----
+    num_steps, dt = 4, 5e-4
+    L = (num_steps + 1) * nodes
+    u0, v0 = hp.chtxs_sys_IC(a1, a2, 1.0 / n, nodes, v2d)
+    uhat = np.tile(u0, num_steps + 1) * (1 + 0.1 * rng.random(L))
+    vhat = np.tile(v0, num_steps + 1) * (1 + 0.1 * rng.random(L))
+    _, ns_ = _exec_refactored_pgd("chemotaxis_FCT_PDECO_AT_refactored.py", dict(
+        base, dt=dt, T=num_steps * dt, num_steps=num_steps, u0=u0, v0=v0, uhat=uhat, vhat=vhat, uhat_re=None, vhat_re=None,
+        rescaling=1 / 10, beta=1e-3, c_lower=0, c_upper=20, optim="alltime", tol=1e-4, max_iter_armijo=20, max_iter_GD=2,
+        armijo_gamma=1e-5, armijo_s0=2))
+    out.update(c_ns=np.array([num_steps]), c_dt=np.array([dt]), c_u0=u0, c_v0=v0, c_uhat=uhat, c_vhat=vhat,
+               c_u=ns_["uk"].copy(), c_v=ns_["vk"].copy(), c_p=ns_["pk"].copy(), c_q=ns_["qk"].copy(), c_c=ns_["ck"].copy(),
+               c_cost=np.array(ns_["cost_fun_vals"]), c_its=np.array(ns_["armijo_its"]), c_it=np.array([ns_["it"]]))
+    print("chemotaxis AT: cost", out["c_cost"], "armijo its", out["c_its"], "it", out["c_it"])
+    np.savez_compressed(os.path.join(HERE, "ref_pgd_two_species.npz"), **out)
+    print("ref_pgd_two_species.npz written")
+
+
 def ref_script_full_sizes():
     """configs 2, 3 and 4 on the meshes BASELINE names: 81^2 DoF on [-1,1]^2 (three time levels, sampled), 129^2 DoF on
     [0,16]^2 with dt = 0.1 (two time levels, sampled), 51^2 DoF with dt = 0.002 and the script's own three time levels"""
@@ -633,6 +701,7 @@ def ref_script_full_sizes():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ref_data", "ref_fct_cases", "ref_legacy", "ref_armijo", "ref_loops", "ref_script_cfg2",
-                             "ref_script_cfg3", "ref_script_cfg4", "ref_script_full_sizes", "ref_script_refactored_nonlinear"]
+                             "ref_script_cfg3", "ref_script_cfg4", "ref_script_full_sizes", "ref_script_refactored_nonlinear",
+                             "ref_script_refactored_two_species"]
     for name in which:
         globals()[name]()

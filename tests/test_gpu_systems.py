@@ -299,3 +299,101 @@ def test_refactored_nonlinear_pgd_script_loop():
     assert abs(stop_crit - float(g["stop_crit"][0])) <= 1e-6 * abs(float(g["stop_crit"][0]))
     for name, a in (("u", uk), ("p", pk), ("c", ck), ("d", dk)):
         assert rel_l2(a, g[name]) < 1e-11, name
+
+
+def _two_species_pgd(solve, solve_adj, direction, cost_kw, armijo_kw, u0, v0, V, nodes, num_steps, dt, dof_neighbors, M, beta,
+                     c_lower, c_upper, optim, tol, max_iter_armijo, max_iter_GD, targets, at_least_two):
+    """the projected-gradient loop shared by Schnak_FCT_PDECO_refactored.py:122-246 and
+    chemotaxis_FCT_PDECO_AT_refactored.py:122-257 (same calls, same order, same fail / restart bookkeeping)"""
+    uhat, vhat = targets
+    vec_length = (num_steps + 1) * nodes
+    ck = np.zeros(vec_length)
+    uk = np.zeros(vec_length); vk = np.zeros(vec_length)
+    uk[:nodes] = u0; vk[:nodes] = v0
+    uk, vk = solve(ck, uk, vk, V, nodes, num_steps, dt, dof_neighbors)
+    pk = np.zeros(vec_length); qk = np.zeros(vec_length)
+    pk, qk = solve_adj(uk, vk, pk, qk, ck)
+    cost_fun_old = hp.cost_functional(uk, uhat, ck, num_steps, dt, M, beta, optim, var2=vk, var2_target=vhat)
+    cost_fun_new = (2 + tol) * cost_fun_old
+    stop_crit = hp.rel_err(cost_fun_new, cost_fun_old)
+    it = fail_count = fail_restart_count = 0
+    fail_pass = False
+    cost_fun_vals, armijo_its = [cost_fun_old], []
+    while (stop_crit >= tol or fail_pass or (at_least_two and it < 2)) and it < max_iter_GD:
+        dk = direction(ck, uk, pk, qk)
+        uk, vk, ck, iters = hp.armijo_line_search_ref(uk, ck, dk, uhat, num_steps, dt, c_lower, c_upper, beta, cost_fun_old, nodes,
+                                                      optim, V, dof_neighbors=dof_neighbors, var2=vk, var2_target=vhat,
+                                                      nonlinear_solver=solve, max_iter=max_iter_armijo, **armijo_kw)
+        pk, qk = solve_adj(uk, vk, pk, qk, ck)
+        if iters == max_iter_armijo:
+            fail_count += 1
+            fail_pass = True
+            if fail_count == cost_kw["fail_max"]:
+                break
+        elif fail_count > 0:
+            fail_count = 0
+            fail_restart_count += 1
+            fail_pass = False
+            if fail_restart_count == 5:
+                break
+        cost_fun_new = hp.cost_functional(uk, uhat, ck, num_steps, dt, M, beta, optim, var2=vk, var2_target=vhat)
+        stop_crit = hp.rel_err(cost_fun_new, cost_fun_old)
+        cost_fun_vals.append(cost_fun_new)
+        armijo_its.append(iters)
+        it += 1
+        cost_fun_old = cost_fun_new
+    return uk, vk, pk, qk, ck, cost_fun_vals, armijo_its, it
+
+
+def test_refactored_two_species_pgd_script_loops():
+    """The projected-gradient loops of Schnak_FCT_PDECO_refactored.py (final time, dk = -(beta ck - gamma/r pk), eight
+    backtracking trials per iteration) and chemotaxis_FCT_PDECO_AT_refactored.py (all time, dk = -(beta ck - qk uk / r), line
+    search with gam = 1e-5, s0 = 2) on the drop-in `hp`, against the runs of the scripts' OWN source lines with the reference's
+    helpers.py on oracle/fake_dolfin.py (tests/golden/ref_pgd_two_species.npz)."""
+    import os
+    from conftest import GOLDEN
+    from fem_fct_pdeco_b200.forms import TestFunction, TrialFunction, dx
+    g = dict(np.load(os.path.join(GOLDEN, "ref_pgd_two_species.npz")))
+    n = int(g["n"][0])
+    mesh, V = _space(n)
+    nodes = V.dim()
+    vertex_to_dof = vertex_to_dof_map(V)
+    dof_neighbors = hp.find_node_neighbours(mesh, nodes, vertex_to_dof)
+    M = hp.assemble_sparse(TrialFunction(V) * TestFunction(V) * dx)
+
+    # ---- Schnakenberg, final time (Schnak_FCT_PDECO_refactored.py) ----
+    num_steps, dt = int(g["s_ns"][0]), float(g["s_dt"][0])
+    T = num_steps * dt
+    gamma = hp.get_schnak_sys_params()[4]
+    uhat_T, vhat_T = g["s_uhat"], g["s_vhat"]
+    u0, v0 = hp.schnak_sys_IC(0, 1, 1.0 / n, nodes, vertex_to_dof)
+    assert np.array_equal(u0, g["s_u0"]) and np.array_equal(v0, g["s_v0"])
+    res = _quiet(_two_species_pgd, hp.solve_schnak_system,
+                 lambda uk, vk, pk, qk, ck: hp.solve_adjoint_schnak_system(uk, vk, uhat_T, vhat_T, pk, qk, T, V, nodes, num_steps,
+                                                                           dt, dof_neighbors),
+                 lambda ck, uk, pk, qk: -(1e-1 * ck - gamma / 1 * pk), {"fail_max": 3}, {}, u0, v0, V, nodes, num_steps, dt,
+                 dof_neighbors, M, 1e-1, 0, 10, "finaltime", 1e-3, 10, 2, (uhat_T, vhat_T), False)
+    uk, vk, pk, qk, ck, cost, its, it = res
+    assert it == int(g["s_it"][0]) and its == list(g["s_its"])
+    assert np.allclose(cost, g["s_cost"], rtol=1e-9, atol=0)
+    for name, a in (("u", uk), ("v", vk), ("p", pk), ("q", qk), ("c", ck)):
+        assert rel_l2(a, g["s_" + name]) < 1e-10, name
+
+    # ---- chemotaxis, all time (chemotaxis_FCT_PDECO_AT_refactored.py) ----
+    num_steps, dt = int(g["c_ns"][0]), float(g["c_dt"][0])
+    T = num_steps * dt
+    rescaling = 1 / 10
+    uhat, vhat = g["c_uhat"], g["c_vhat"]
+    u0, v0 = hp.chtxs_sys_IC(0, 1, 1.0 / n, nodes, vertex_to_dof)
+    assert np.array_equal(u0, g["c_u0"]) and np.array_equal(v0, g["c_v0"])
+    res = _quiet(_two_species_pgd, hp.solve_chtxs_system,
+                 lambda uk, vk, pk, qk, ck: hp.solve_adjoint_chtxs_system(uk, vk, uhat, vhat, pk, qk, ck, T, V, nodes, num_steps, dt,
+                                                                          dof_neighbors, "alltime", mesh=mesh, deltax=1.0 / n,
+                                                                          vertex_to_dof=vertex_to_dof, rescaling=rescaling),
+                 lambda ck, uk, pk, qk: -(1e-3 * ck - qk * uk / rescaling), {"fail_max": 5}, {"gam": 1e-5, "s0": 2}, u0, v0, V,
+                 nodes, num_steps, dt, dof_neighbors, M, 1e-3, 0, 20, "alltime", 1e-4, 20, 2, (uhat, vhat), True)
+    uk, vk, pk, qk, ck, cost, its, it = res
+    assert it == int(g["c_it"][0]) and its == list(g["c_its"])
+    assert np.allclose(cost, g["c_cost"], rtol=1e-9, atol=0)
+    for name, a in (("u", uk), ("v", vk), ("p", pk), ("q", qk), ("c", ck)):
+        assert rel_l2(a, g["c_" + name]) < 1e-10, name
