@@ -299,6 +299,59 @@ from .forms import (VectorFunctionSpace, assemble, assemble_sparse, assemble_spa
                     vec_to_function)
 
 
+# ---- host-side post-processing helpers of helpers.py:1958-2133 ---------------------------------------------------------
+def norm_true_control(example, T, dt, M, V, c_a=None):
+    """helpers.py:1958-2001: squared L2(Q) norm of the control that generated the target states
+    (nonlinear_FCT_PDECO_refactored.py:235).  df.interpolate of the degree-4 Expression onto P1 is its nodal values."""
+    valid_options = ["nonlinear", "Schnak", "chtxs"]
+    if example not in valid_options:
+        raise ValueError(f"Invalid value for 'example': '{example}'. Must be one of {valid_options}.")
+    num_steps = round(T / dt)
+    if example == "nonlinear":
+        k, l = 2, 2
+        xy = V.mesh().dof_xy
+        control_vector = np.sin(k * np.pi * xy[:, 0]) * np.sin(l * np.pi * xy[:, 1])
+        control_vector_td = np.tile(control_vector, num_steps + 1)
+    elif example == "Schnak":
+        vec_length = (num_steps + 1) * M.shape[0]
+        control_vector_td = c_a * np.ones(vec_length)
+    else:
+        # the reference has no branch for "chtxs" and fails on the unbound name (helpers.py:1999)
+        raise UnboundLocalError("local variable 'control_vector_td' referenced before assignment")
+    return L2_norm_sq_Q(control_vector_td, num_steps, dt, M)
+
+
+def smooth_corners_on_boundary(vec, V, vertex_to_dof, a1, a2, deltax):
+    """helpers.py:2003-2052: each corner DoF becomes the mean of its two boundary neighbours"""
+    sq = round((a2 - a1) / deltax) + 1
+    v2d = np.asarray(vertex_to_dof)
+    corners = {0: (1, sq), sq - 1: (sq - 2, 2 * sq - 1), (sq - 1) * sq: ((sq - 2) * sq, (sq - 1) * sq + 1),
+               sq * sq - 1: ((sq - 1) * sq + sq - 2, sq * (sq - 1) - 1)}
+    new_vec = vec.copy()
+    for corner, nbrs in corners.items():
+        new_vec[int(v2d[corner])] = np.mean([vec[int(v2d[k])] for k in nbrs])
+    return new_vec
+
+
+def rescale_boundary_nodes(u_vec, vertex_to_dof, a1=0, a2=1, deltax=0.025):
+    """helpers.py:2054-2121: boundary values rescaled linearly into the range of the adjacent inner row / column; the four
+    sides are processed in the reference's order (bottom, top, left, right: corners end up with the last side's value)"""
+    new_u = u_vec.copy()
+    sq = round((a2 - a1) / deltax) + 1
+    v2d = np.asarray(vertex_to_dof)
+    idx = np.arange(sq)
+    sides = ((idx, sq + idx), ((sq - 1) * sq + idx, (sq - 2) * sq + idx), (idx * sq, idx * sq + 1),
+             (idx * sq + sq - 1, idx * sq + sq - 2))
+    gmin, gmax = np.min(u_vec), np.max(u_vec)
+    den = max(gmax - gmin, 1e-12)
+    for b, a in sides:
+        inner = u_vec[v2d[a]]
+        lo, hi = inner.min(), inner.max()
+        t = (u_vec[v2d[b]] - gmin) / den
+        new_u[v2d[b]] = lo + t * (hi - lo)
+    return new_u
+
+
 # ---- legacy Mimura form builders the config-3 script calls through `from helpers import *` -----------------------------
 def rhs_chtx_f(f_fun, m_fun, c_fun, dt, v):
     """old_helpers.py:90-91 (chemotaxis_mimura_FCT_PGD.py:175)"""
@@ -310,6 +363,31 @@ def rhs_chtx_p(c_fun, q_fun, v):
     """old_helpers.py:93-94 (chemotaxis_mimura_FCT_PGD.py:223)"""
     from .forms import dx
     return np.asarray(assemble(c_fun * q_fun * v * dx))
+
+
+def rhs_chtx_m(m_fun, v):
+    """old_helpers.py:87-88 (the legacy Mimura reaction term; chemotaxis_FCT_PDECO.py:190)"""
+    from .forms import dx
+    return np.asarray(assemble(4 * m_fun * v * dx))
+
+
+def mat_chtx_m(f_fun, m_fun, Dm, chi, u, v):
+    """old_helpers.py:100-104 (chemotaxis_FCT_PDECO.py:189,266): -Dm K + chi (grad f . grad v) u + m u v"""
+    from .forms import dot, dx, grad
+    Ad = assemble_sparse(dot(grad(u), grad(v)) * dx)
+    Aa = assemble_sparse(dot(grad(f_fun), grad(v)) * u * dx)
+    Ar = assemble_sparse(m_fun * u * v * dx)
+    return - Dm * Ad + chi * Aa + Ar
+
+
+def mat_chtx_p(f_fun, m_fun, Dm, chi, u, v):
+    """old_helpers.py:106-111 (chemotaxis_FCT_PDECO.py:229): -Dm K - chi (grad f . grad v) u - chi div(grad f) u v + (4 - 2m) u v;
+    div(grad f) of a P1 field vanishes cell-wise, so dolfin assembles zeros for that term"""
+    from .forms import dot, dx, grad
+    Ad = assemble_sparse(dot(grad(u), grad(v)) * dx)
+    Aa = assemble_sparse(dot(grad(f_fun), grad(v)) * u * dx)
+    Ar = assemble_sparse((4 - 2 * m_fun) * u * v * dx)
+    return - Dm * Ad - chi * Aa + Ar
 
 
 def rhs_chtx_q(q_fun, m_fun, p_fun, chi, dt, v):

@@ -150,5 +150,19 @@ def test_mimura_legacy_form_builders():
         gm = np.array([gx @ m[T], gy @ m[T]]); gp = np.array([gx @ p[T], gy @ p[T]])
         load[T] += (gm @ gp) * abs(det) / 6.0
     assert _relmax(hp.rhs_chtx_q(Q, Mf, P, chi, dt, v), Mmat @ q + dt * chi * load) < 1e-12
+    # the same-named builders of old_helpers.py:87-111 (star-imported by chemotaxis_FCT_PDECO.py:189-266): other reaction terms
+    Mw = asm.mass_p1_product(m)
+    assert _relmax(hp.rhs_chtx_m(Mf, v), 4 * (Mmat @ m)) < 1e-13
+    assert _relmax(pat.embed(hp.mat_chtx_m(F, Mf, Dm, chi, u, v)), -Dm * K + chi * asm.chemotaxis_conv(f) + Mw) < 1e-13
+    assert _relmax(pat.embed(hp.mat_chtx_p(F, Mf, Dm, chi, u, v)),
+                   -Dm * K - chi * asm.chemotaxis_conv(f) + 4 * asm.mass() - 2 * Mw) < 1e-13
+    # norm_true_control (helpers.py:1958-2001; nonlinear_FCT_PDECO_refactored.py:235)
+    T, dts = 0.3, 0.1
+    cv = np.sin(2 * np.pi * om.dof_xy[:, 0]) * np.sin(2 * np.pi * om.dof_xy[:, 1])
+    Msp = hp.assemble_sparse(u * v * dx)
+    exp_nl = sum(w * (cv @ (Mmat @ cv)) for w in (0.5, 1.0, 1.0, 0.5)) * dts
+    assert abs(hp.norm_true_control("nonlinear", T, dts, Msp, V) / exp_nl - 1) < 1e-12
+    ones = np.ones(V.dim())
+    assert abs(hp.norm_true_control("Schnak", T, dts, Msp, V, c_a=0.1) / (0.01 * 3 * dts * (ones @ (Mmat @ ones))) - 1) < 1e-12
     # (m_initial_condition is pure numpy and is compared with the reference's own function on the CPU:
     # tests/test_host_shims_vs_reference.py)

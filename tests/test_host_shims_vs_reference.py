@@ -143,3 +143,23 @@ def test_mimura_initial_condition_vs_reference():
     exec(compile(m.group(0), "mimura_data_helpers.py:m_initial_condition", "exec"), ns)
     for a1, a2, dx in ((0.0, 16.0, 0.125), (0.0, 1.0, 0.1)):
         assert np.array_equal(mdh.m_initial_condition(a1, a2, dx), ns["m_initial_condition"](a1, a2, dx))
+
+
+def test_boundary_postprocessing_helpers_vs_reference(ref):
+    """smooth_corners_on_boundary / rescale_boundary_nodes (helpers.py:2003-2121): vectorised here, compared with the
+    reference's loops bit for bit; norm_true_control's error behaviour (helpers.py:1982-1984)"""
+    n = 7
+    m = RectMeshP1(n, 0.0, 1.0)
+    rng = np.random.default_rng(4)
+    vec = rng.random(m.nodes)
+    got = helpers.smooth_corners_on_boundary(vec, None, m.vertex_to_dof, 0.0, 1.0, 1.0 / n)
+    exp = ref.smooth_corners_on_boundary(vec, None, m.vertex_to_dof, 0.0, 1.0, 1.0 / n)
+    assert np.array_equal(got, exp) and not np.array_equal(got, vec)
+    got = helpers.rescale_boundary_nodes(vec, m.vertex_to_dof, a1=0.0, a2=1.0, deltax=1.0 / n)
+    exp = ref.rescale_boundary_nodes(vec, m.vertex_to_dof, a1=0.0, a2=1.0, deltax=1.0 / n)
+    assert np.array_equal(got, exp) and not np.array_equal(got, vec)
+    with pytest.raises(ValueError) as e_ref:
+        ref.norm_true_control("linear", 1, 0.1, None, None)
+    with pytest.raises(ValueError) as e_new:
+        helpers.norm_true_control("linear", 1, 0.1, None, None)
+    assert str(e_new.value) == str(e_ref.value)
